@@ -1,0 +1,109 @@
+// Error string, version and the host-side scene schedule.
+//
+// The schedule replaces the per-scene python loop headers of the reference
+// (sgan/models.py:507-510, 256-262, 639-644): seq_start_end is read ONCE per minibatch on the
+// host and turned into flat per-ped arrays that every kernel indexes without a device sync.
+#include <algorithm>
+#include <numeric>
+#include <queue>
+#include <vector>
+
+#include "sgx_common.cuh"
+
+namespace sgx {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace sgx
+
+extern "C" const char* sgx_last_error(void) { return sgx::g_err; }
+extern "C" int sgx_version(void) { return 100; }
+
+static int validate(const int64_t* sse, int64_t S, int64_t* batch_out, int64_t* max_n, int64_t* pairs) {
+    SGX_REQUIRE(sse != nullptr && S >= 1, "seq_start_end must hold at least one scene");
+    int64_t cur = 0, mx = 0, p = 0;
+    for (int64_t s = 0; s < S; ++s) {
+        int64_t a = sse[2 * s], b = sse[2 * s + 1];
+        SGX_REQUIRE(a == cur, "scene %lld starts at %lld, expected %lld: scenes must tile [0,batch) contiguously",
+                    (long long)s, (long long)a, (long long)cur);
+        SGX_REQUIRE(b > a, "scene %lld is empty (start=%lld end=%lld)", (long long)s, (long long)a, (long long)b);
+        int64_t n = b - a;
+        mx = std::max(mx, n);
+        p += n * n;
+        cur = b;
+    }
+    SGX_REQUIRE(cur < (int64_t)1 << 31, "batch too large for int32 indexing");
+    *batch_out = cur;
+    *max_n = mx;
+    *pairs = p;
+    return SGX_OK;
+}
+
+extern "C" int sgx_schedule_stats(const int64_t* sse, int64_t S, int64_t* stats) {
+    SGX_REQUIRE(stats != nullptr, "null stats");
+    int64_t batch, mx, pairs;
+    int rc = validate(sse, S, &batch, &mx, &pairs);
+    if (rc) return rc;
+    stats[0] = batch;
+    stats[1] = mx;
+    stats[2] = pairs;
+    stats[3] = (pairs + 127) / 128;
+    stats[4] = S;
+    return SGX_OK;
+}
+
+extern "C" int sgx_schedule_fill(const int64_t* sse, int64_t S, int32_t* scene_start, int32_t* ped_start,
+                                 int32_t* ped_end, int64_t* pair_off, int32_t* tile_first) {
+    int64_t batch, mx, pairs;
+    int rc = validate(sse, S, &batch, &mx, &pairs);
+    if (rc) return rc;
+    SGX_REQUIRE(scene_start && ped_start && ped_end && pair_off && tile_first, "null output array");
+    int64_t acc = 0, next_tile = 0;
+    for (int64_t s = 0; s < S; ++s) {
+        int64_t a = sse[2 * s], b = sse[2 * s + 1], n = b - a;
+        scene_start[s] = (int32_t)a;
+        for (int64_t i = a; i < b; ++i) {
+            ped_start[i] = (int32_t)a;
+            ped_end[i] = (int32_t)b;
+            pair_off[i] = acc;
+            // every 128-pair tile whose first pair lies in ped i's row block
+            while (next_tile * 128 < acc + n) tile_first[next_tile++] = (int32_t)i;
+            acc += n;
+        }
+    }
+    scene_start[S] = (int32_t)batch;
+    pair_off[batch] = acc;
+    return SGX_OK;
+}
+
+// Longest-processing-time-first partition of scenes over ranks, cost = N^2 (pairwise pooling).
+extern "C" int sgx_schedule_partition(const int64_t* sse, int64_t S, int32_t world, int32_t* rank_of_scene,
+                                      int64_t* rank_cost) {
+    int64_t batch, mx, pairs;
+    int rc = validate(sse, S, &batch, &mx, &pairs);
+    if (rc) return rc;
+    SGX_REQUIRE(world >= 1 && rank_of_scene != nullptr, "bad world size / null output");
+    std::vector<int64_t> order(S);
+    std::iota(order.begin(), order.end(), 0);
+    auto cost = [&](int64_t s) { int64_t n = sse[2 * s + 1] - sse[2 * s]; return n * n; };
+    std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return cost(x) > cost(y); });
+    typedef std::pair<int64_t, int32_t> Load;  // (cost so far, rank): min-heap, ties -> lower rank
+    std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
+    for (int32_t r = 0; r < world; ++r) heap.push(Load(0, r));
+    std::vector<int64_t> tot(world, 0);
+    for (int64_t k = 0; k < S; ++k) {
+        Load l = heap.top();
+        heap.pop();
+        rank_of_scene[order[k]] = l.second;
+        l.first += cost(order[k]);
+        tot[l.second] = l.first;
+        heap.push(l);
+    }
+    if (rank_cost)
+        for (int32_t r = 0; r < world; ++r) rank_cost[r] = tot[r];
+    return SGX_OK;
+}

@@ -1,0 +1,71 @@
+// Shared helpers for libsgx_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <algorithm>
+
+#include "../../include/sgx.h"
+
+namespace sgx {
+
+void set_error(const char* fmt, ...);
+
+#define SGX_REQUIRE(cond, ...)                 \
+    do {                                       \
+        if (!(cond)) {                         \
+            sgx::set_error(__VA_ARGS__);       \
+            return SGX_ERR_INVALID;            \
+        }                                      \
+    } while (0)
+
+#define SGX_UNSUPPORTED(cond, ...)             \
+    do {                                       \
+        if (cond) {                            \
+            sgx::set_error(__VA_ARGS__);       \
+            return SGX_ERR_UNSUPPORTED;        \
+        }                                      \
+    } while (0)
+
+#define SGX_CUDA(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (expr);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            sgx::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__,   \
+                           __LINE__);                                                           \
+            return SGX_ERR_CUDA;                                                                \
+        }                                                                                       \
+    } while (0)
+
+#define SGX_LAUNCH_CHECK() SGX_CUDA(cudaGetLastError())
+
+static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+static inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+// carve typed regions out of a caller-provided workspace
+struct Carver {
+    char* base;
+    int64_t off;
+    explicit Carver(void* p) : base((char*)p), off(0) {}
+    template <typename T>
+    T* take(int64_t n) {
+        T* r = (T*)(base + off);
+        off += align_up(n * (int64_t)sizeof(T), 256);
+        return r;
+    }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// generic fp32 GEMM used inside the library (same as the exported sgx_gemm)
+// bias_m / bias_n (nullable): per-row / per-column bias added to C (disables split-K)
+int gemm(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn, float* C, int64_t ldc,
+         int64_t M, int64_t N, int64_t K, int accumulate, int relu, cudaStream_t st, const float* bias_m = nullptr,
+         const float* bias_n = nullptr);
+
+}  // namespace sgx

@@ -1,0 +1,493 @@
+// GATEncoder forward/backward (sgan/models.py:254-294; GraphAttentionLayer 184-220; GAT 222-237).
+//
+// What the reference does per scene, with dense N x N tensors ([N,N,2F] pair tensor, masked softmax):
+//   intra GAT on the group adjacency -> GPool (group mean) -> inter GAT on the all-ones adjacency of
+//   the scene's groups -> unpool (row-normalised R^T) -> Linear(32, 24).
+// What this file does instead:
+//   * e_ij = LeakyReLU(a1.Wh_i + a2.Wh_j) = LeakyReLU(s_i + t_j): scores from two per-node scalars,
+//     never the [N,N,2F] tensor.
+//   * masked entries are -9e15 before the softmax, i.e. exactly 0 after it (every row keeps its
+//     diagonal), so attention runs over the *members of the row's group* (intra) or the scene's group
+//     leaders (inter): a segmented, ragged attention with one thread per node and an online pass.
+//   * all per-node linear maps (x W, Wh [a1 a2], x1a Wout, cat Wo^T) are batch-wide GEMMs (sgx::gemm).
+//   * group-level tensors are stored at the row of the group's leader pedestrian (no compaction pass).
+// Backward mirrors it: per attention layer one "row" kernel (recompute softmax stats, d(pre-activation),
+// ds) and one "column" kernel (dt and dWh by gathering over the symmetric neighbourhood), GEMMs for the
+// parameter gradients.  dropout must be 0 (all shipped checkpoints; the module raises otherwise).
+#include "sgx_common.cuh"
+
+namespace sgx {
+
+__global__ void colsum_kernel(const float* __restrict__ m, int64_t rows, int cols, float* __restrict__ out);
+
+enum { INTRA = 0, INTER = 1 };
+enum { POST_ELU = 1, POST_ELU_LOGSOFTMAX = 2 };
+
+template <int MODE>
+__device__ __forceinline__ bool node_active(const int32_t* __restrict__ leader, int i) {
+    return MODE == INTRA ? true : (leader[i] == i);
+}
+template <int MODE>
+__device__ __forceinline__ bool is_neighbour(const int32_t* __restrict__ leader, int li, int q) {
+    return MODE == INTRA ? (leader[q] == li) : (leader[q] == q);
+}
+__device__ __forceinline__ float lrelu(float v, float alpha) { return v > 0.f ? v : alpha * v; }
+__device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : expm1f(v); }
+
+// one thread per node: hp_i = sum_j softmax_j(lrelu(s_i + t_j)) Wh_j  over the node's neighbourhood
+template <int F, int MODE>
+__device__ __forceinline__ void attend(const float* __restrict__ Wh, int ldw, const float* __restrict__ st, int lds,
+                                       const int32_t* __restrict__ leader, int b, int e, int li, float s_i,
+                                       float alpha, float (&hp)[F], float& m_out, float& den_out) {
+    float m = -INFINITY;
+    for (int q = b; q < e; ++q)
+        if (is_neighbour<MODE>(leader, li, q)) m = fmaxf(m, lrelu(s_i + st[(int64_t)q * lds + 1], alpha));
+    float den = 0.f;
+#pragma unroll
+    for (int f = 0; f < F; ++f) hp[f] = 0.f;
+    for (int q = b; q < e; ++q) {
+        if (!is_neighbour<MODE>(leader, li, q)) continue;
+        const float w = expf(lrelu(s_i + st[(int64_t)q * lds + 1], alpha) - m);
+        den += w;
+        const float4* row = reinterpret_cast<const float4*>(Wh + (int64_t)q * ldw);
+#pragma unroll
+        for (int f = 0; f < F / 4; ++f) {
+            float4 v = row[f];
+            hp[4 * f] = fmaf(w, v.x, hp[4 * f]); hp[4 * f + 1] = fmaf(w, v.y, hp[4 * f + 1]);
+            hp[4 * f + 2] = fmaf(w, v.z, hp[4 * f + 2]); hp[4 * f + 3] = fmaf(w, v.w, hp[4 * f + 3]);
+        }
+    }
+    const float inv = 1.f / den;
+#pragma unroll
+    for (int f = 0; f < F; ++f) hp[f] *= inv;
+    m_out = m;
+    den_out = den;
+}
+
+template <int F, int MODE, int POST>
+__global__ void __launch_bounds__(128)
+att_fwd_kernel(const float* __restrict__ Wh, int ldw, const float* __restrict__ st, int lds,
+               const int32_t* __restrict__ leader, const int32_t* __restrict__ ped_start,
+               const int32_t* __restrict__ ped_end, int n, float alpha, float* __restrict__ out, int ldo,
+               float* __restrict__ U) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float hp[F];
+    if (!node_active<MODE>(leader, i)) {
+#pragma unroll
+        for (int f = 0; f < F; ++f) out[(int64_t)i * ldo + f] = 0.f;
+        if (POST == POST_ELU_LOGSOFTMAX && U)
+#pragma unroll
+            for (int f = 0; f < F; ++f) U[(int64_t)i * F + f] = 0.f;
+        return;
+    }
+    float m, den;
+    attend<F, MODE>(Wh, ldw, st, lds, leader, ped_start[i], ped_end[i], leader[i], st[(int64_t)i * lds], alpha, hp, m,
+                    den);
+    if (POST == POST_ELU) {
+#pragma unroll
+        for (int f = 0; f < F; ++f) out[(int64_t)i * ldo + f] = elu1(hp[f]);
+    } else {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int f = 0; f < F; ++f) { hp[f] = elu1(hp[f]); mx = fmaxf(mx, hp[f]); }
+        float sum = 0.f;
+#pragma unroll
+        for (int f = 0; f < F; ++f) sum += expf(hp[f] - mx);
+        const float lse = mx + logf(sum);
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+            if (U) U[(int64_t)i * F + f] = hp[f];
+            out[(int64_t)i * ldo + f] = hp[f] - lse;
+        }
+    }
+}
+
+// Row role of the backward: recompute the node's softmax statistics and hp, turn the upstream gradient
+// into d(hp), and reduce ds_i = sum_j d(pre_ij).  stats[i] = (m_i, den_i, c_i = dhp_i . hp_i).
+template <int F, int MODE, int POST>
+__global__ void __launch_bounds__(128)
+att_bwd_row_kernel(const float* __restrict__ Wh, int ldw, const float* __restrict__ st, int lds,
+                   const int32_t* __restrict__ leader, const int32_t* __restrict__ ped_start,
+                   const int32_t* __restrict__ ped_end, int n, float alpha, const float* __restrict__ dOut, int ldd,
+                   float* __restrict__ dhp_out /*[n][F]*/, float* __restrict__ stats /*[n][3]*/,
+                   float* __restrict__ dst, int ldds) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float hp[F];
+    if (!node_active<MODE>(leader, i)) {
+#pragma unroll
+        for (int f = 0; f < F; ++f) dhp_out[(int64_t)i * F + f] = 0.f;
+        stats[3 * (int64_t)i] = 0.f; stats[3 * (int64_t)i + 1] = 1.f; stats[3 * (int64_t)i + 2] = 0.f;
+        dst[(int64_t)i * ldds] = 0.f;
+        return;
+    }
+    const int b = ped_start[i], e = ped_end[i], li = leader[i];
+    const float s_i = st[(int64_t)i * lds];
+    float m, den;
+    attend<F, MODE>(Wh, ldw, st, lds, leader, b, e, li, s_i, alpha, hp, m, den);
+    float c = 0.f;
+    if (POST == POST_ELU) {
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+            float d = dOut[(int64_t)i * ldd + f] * (hp[f] > 0.f ? 1.f : expf(hp[f]));
+            c = fmaf(d, hp[f], c);
+            hp[f] = d;   // hp[] now holds d(hp)
+        }
+    } else {
+        float u[F];
+        float mx = -INFINITY, gsum = 0.f;
+#pragma unroll
+        for (int f = 0; f < F; ++f) { u[f] = elu1(hp[f]); mx = fmaxf(mx, u[f]); gsum += dOut[(int64_t)i * ldd + f]; }
+        float sum = 0.f;
+#pragma unroll
+        for (int f = 0; f < F; ++f) sum += expf(u[f] - mx);
+        const float inv = 1.f / sum;
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+            float du = dOut[(int64_t)i * ldd + f] - expf(u[f] - mx) * inv * gsum;
+            float d = du * (hp[f] > 0.f ? 1.f : expf(hp[f]));
+            c = fmaf(d, hp[f], c);
+            hp[f] = d;
+        }
+    }
+#pragma unroll
+    for (int f = 0; f < F; ++f) dhp_out[(int64_t)i * F + f] = hp[f];
+    stats[3 * (int64_t)i] = m; stats[3 * (int64_t)i + 1] = den; stats[3 * (int64_t)i + 2] = c;
+    // ds_i = sum_j alpha_ij (dhp_i . Wh_j - c_i) lrelu'(s_i + t_j)
+    float ds = 0.f;
+    const float inv_den = 1.f / den;
+    for (int q = b; q < e; ++q) {
+        if (!is_neighbour<MODE>(leader, li, q)) continue;
+        const float pre = s_i + st[(int64_t)q * lds + 1];
+        const float a_ij = expf(lrelu(pre, alpha) - m) * inv_den;
+        const float4* row = reinterpret_cast<const float4*>(Wh + (int64_t)q * ldw);
+        float dot = 0.f;
+#pragma unroll
+        for (int f = 0; f < F / 4; ++f) {
+            float4 v = row[f];
+            dot = fmaf(hp[4 * f], v.x, dot); dot = fmaf(hp[4 * f + 1], v.y, dot);
+            dot = fmaf(hp[4 * f + 2], v.z, dot); dot = fmaf(hp[4 * f + 3], v.w, dot);
+        }
+        ds += a_ij * (dot - c) * (pre > 0.f ? 1.f : alpha);
+    }
+    dst[(int64_t)i * ldds] = ds;
+}
+
+// Column role: node j gathers over every row i that attends to it (the neighbourhood is symmetric):
+//   dt_j = sum_i d(pre_ij) ;  dWh_j = sum_i alpha_ij dhp_i + ds_j a1 + dt_j a2
+template <int F, int MODE>
+__global__ void __launch_bounds__(128)
+att_bwd_col_kernel(const float* __restrict__ Wh, int ldw, const float* __restrict__ st, int lds,
+                   const int32_t* __restrict__ leader, const int32_t* __restrict__ ped_start,
+                   const int32_t* __restrict__ ped_end, int n, float alpha, const float* __restrict__ dhp,
+                   const float* __restrict__ stats, const float* __restrict__ avec /*[2F]*/,
+                   float* __restrict__ dWh, int lddw, float* __restrict__ dst, int ldds) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    if (!node_active<MODE>(leader, j)) {
+#pragma unroll
+        for (int f = 0; f < F; ++f) dWh[(int64_t)j * lddw + f] = 0.f;
+        dst[(int64_t)j * ldds + 1] = 0.f;
+        return;
+    }
+    const int b = ped_start[j], e = ped_end[j], lj = leader[j];
+    float whj[F], acc[F];
+    {
+        const float4* row = reinterpret_cast<const float4*>(Wh + (int64_t)j * ldw);
+#pragma unroll
+        for (int f = 0; f < F / 4; ++f) {
+            float4 v = row[f];
+            whj[4 * f] = v.x; whj[4 * f + 1] = v.y; whj[4 * f + 2] = v.z; whj[4 * f + 3] = v.w;
+        }
+    }
+#pragma unroll
+    for (int f = 0; f < F; ++f) acc[f] = 0.f;
+    const float t_j = st[(int64_t)j * lds + 1];
+    float dt = 0.f;
+    for (int i = b; i < e; ++i) {
+        if (!is_neighbour<MODE>(leader, lj, i)) continue;
+        const float pre = st[(int64_t)i * lds] + t_j;
+        const float m = stats[3 * (int64_t)i], den = stats[3 * (int64_t)i + 1], c = stats[3 * (int64_t)i + 2];
+        const float a_ij = expf(lrelu(pre, alpha) - m) / den;
+        const float4* row = reinterpret_cast<const float4*>(dhp + (int64_t)i * F);
+        float dot = 0.f;
+#pragma unroll
+        for (int f = 0; f < F / 4; ++f) {
+            float4 v = row[f];
+            dot = fmaf(v.x, whj[4 * f], dot); dot = fmaf(v.y, whj[4 * f + 1], dot);
+            dot = fmaf(v.z, whj[4 * f + 2], dot); dot = fmaf(v.w, whj[4 * f + 3], dot);
+            acc[4 * f] = fmaf(a_ij, v.x, acc[4 * f]); acc[4 * f + 1] = fmaf(a_ij, v.y, acc[4 * f + 1]);
+            acc[4 * f + 2] = fmaf(a_ij, v.z, acc[4 * f + 2]); acc[4 * f + 3] = fmaf(a_ij, v.w, acc[4 * f + 3]);
+        }
+        dt += a_ij * (dot - c) * (pre > 0.f ? 1.f : alpha);
+    }
+    const float ds = dst[(int64_t)j * ldds];
+    dst[(int64_t)j * ldds + 1] = dt;
+#pragma unroll
+    for (int f = 0; f < F; ++f)
+        dWh[(int64_t)j * lddw + f] = acc[f] + ds * avec[f] + dt * avec[F + f];
+}
+
+// GPool: Xg[l] = sum_{j in g} a X1_j at leader rows, zero elsewhere      (R_n @ X1, models.py:280)
+template <int OUT>
+__global__ void gat_pool_kernel(const float* __restrict__ X1, const int32_t* __restrict__ leader,
+                                const int32_t* __restrict__ gsize, const int32_t* __restrict__ ped_end, int batch,
+                                float* __restrict__ Xg) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= batch) return;
+    float acc[OUT];
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) acc[o] = 0.f;
+    if (leader[p] == p) {
+        const float a = __frcp_rn((float)gsize[p]);
+        for (int q = p; q < ped_end[p]; ++q) {
+            if (leader[q] != p) continue;
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) acc[o] = fmaf(a, X1[(int64_t)q * OUT + o], acc[o]);
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) Xg[(int64_t)p * OUT + o] = acc[o];
+}
+
+// cat_p = [X1_p ; a_p Yg[leader_p]]                                 (R_n^T @ Yg, models.py:286-288)
+template <int OUT>
+__global__ void gat_cat_kernel(const float* __restrict__ X1, const float* __restrict__ Yg,
+                               const int32_t* __restrict__ leader, const int32_t* __restrict__ gsize, int batch,
+                               float* __restrict__ cat) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)batch * OUT) return;
+    int p = (int)(idx / OUT), o = (int)(idx % OUT);
+    cat[(int64_t)p * 2 * OUT + o] = X1[idx];
+    cat[(int64_t)p * 2 * OUT + OUT + o] = __frcp_rn((float)gsize[p]) * Yg[(int64_t)leader[p] * OUT + o];
+}
+
+// dYg[l] = sum_{p in g} a dcat[p][OUT:]  at leader rows, zero elsewhere
+template <int OUT>
+__global__ void gat_unpool_bwd_kernel(const float* __restrict__ dcat, const int32_t* __restrict__ leader,
+                                      const int32_t* __restrict__ gsize, const int32_t* __restrict__ ped_end,
+                                      int batch, float* __restrict__ dYg) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= batch) return;
+    float acc[OUT];
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) acc[o] = 0.f;
+    if (leader[p] == p) {
+        const float a = __frcp_rn((float)gsize[p]);
+        for (int q = p; q < ped_end[p]; ++q) {
+            if (leader[q] != p) continue;
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) acc[o] = fmaf(a, dcat[(int64_t)q * 2 * OUT + OUT + o], acc[o]);
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) dYg[(int64_t)p * OUT + o] = acc[o];
+}
+
+// dX1_p = dcat[p][:OUT] + a_p dXg[leader_p]
+template <int OUT>
+__global__ void gat_pool_bwd_kernel(const float* __restrict__ dcat, const float* __restrict__ dXg,
+                                    const int32_t* __restrict__ leader, const int32_t* __restrict__ gsize, int batch,
+                                    float* __restrict__ dX1) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)batch * OUT) return;
+    int p = (int)(idx / OUT), o = (int)(idx % OUT);
+    dX1[idx] = dcat[(int64_t)p * 2 * OUT + o] + __frcp_rn((float)gsize[p]) * dXg[(int64_t)leader[p] * OUT + o];
+}
+
+constexpr int HID = 72, OUT = 16;
+
+struct Level {   // buffers of one GAT (intra or inter)
+    float *Wh1, *st1, *x1a, *Wh2, *st2, *U, *Xo;
+};
+struct GatWs {
+    Level intra, inter;
+    float *Xg, *cat;
+    // backward
+    float *dcat, *dYg, *dXg, *dX1, *dhp, *stats, *dst, *dWh, *dx1a;
+};
+
+static int64_t carve_gat(Carver& c, GatWs& w, int64_t n, int nh) {
+    Level* lv[2] = {&w.intra, &w.inter};
+    for (int k = 0; k < 2; ++k) {
+        lv[k]->Wh1 = c.take<float>(n * nh * HID); lv[k]->st1 = c.take<float>(n * nh * 2);
+        lv[k]->x1a = c.take<float>(n * nh * HID); lv[k]->Wh2 = c.take<float>(n * OUT);
+        lv[k]->st2 = c.take<float>(n * 2); lv[k]->U = c.take<float>(n * OUT); lv[k]->Xo = c.take<float>(n * OUT);
+    }
+    w.Xg = c.take<float>(n * OUT); w.cat = c.take<float>(n * 2 * OUT);
+    w.dcat = c.take<float>(n * 2 * OUT); w.dYg = c.take<float>(n * OUT); w.dXg = c.take<float>(n * OUT);
+    w.dX1 = c.take<float>(n * OUT); w.dhp = c.take<float>(n * HID); w.stats = c.take<float>(n * 3);
+    w.dst = c.take<float>(n * nh * 2); w.dWh = c.take<float>(n * nh * HID); w.dx1a = c.take<float>(n * nh * HID);
+    return c.off;
+}
+
+template <int MODE>
+static int gat_level_fwd(const float* feat, int fin, const float* W, const float* a, const float* Wout,
+                         const float* aout, int nh, float alpha, const int32_t* leader, const int32_t* ps,
+                         const int32_t* pe, int64_t n, Level& L, cudaStream_t st) {
+    int rc;
+    const int ldh = nh * HID;
+    for (int k = 0; k < nh; ++k) {
+        // Wh1[:, k] = feat W_k ;  st1[:, k] = Wh1[:, k] [a1 a2]
+        if ((rc = gemm(feat, fin, 1, W + (int64_t)k * fin * HID, HID, 1, L.Wh1 + k * HID, ldh, n, HID, fin, 0, 0, st)))
+            return rc;
+        if ((rc = gemm(L.Wh1 + k * HID, ldh, 1, a + (int64_t)k * 2 * HID, 1, HID, L.st1 + 2 * k, 2 * nh, n, 2, HID, 0, 0,
+                       st)))
+            return rc;
+        att_fwd_kernel<HID, MODE, POST_ELU><<<blocks_for(n, 128), 128, 0, st>>>(
+            L.Wh1 + k * HID, ldh, L.st1 + 2 * k, 2 * nh, leader, ps, pe, (int)n, alpha, L.x1a + k * HID, ldh, nullptr);
+        SGX_LAUNCH_CHECK();
+    }
+    if ((rc = gemm(L.x1a, ldh, 1, Wout, OUT, 1, L.Wh2, OUT, n, OUT, ldh, 0, 0, st))) return rc;
+    if ((rc = gemm(L.Wh2, OUT, 1, aout, 1, OUT, L.st2, 2, n, 2, OUT, 0, 0, st))) return rc;
+    att_fwd_kernel<OUT, MODE, POST_ELU_LOGSOFTMAX><<<blocks_for(n, 128), 128, 0, st>>>(
+        L.Wh2, OUT, L.st2, 2, leader, ps, pe, (int)n, alpha, L.Xo, OUT, L.U);
+    SGX_LAUNCH_CHECK();
+    return SGX_OK;
+}
+
+// upstream dXo [n,OUT] -> dfeat [n,fin] (overwritten) + parameter grads (overwritten)
+template <int MODE>
+static int gat_level_bwd(const float* feat, int fin, const float* W, const float* a, const float* Wout,
+                         const float* aout, int nh, float alpha, const int32_t* leader, const int32_t* ps,
+                         const int32_t* pe, int64_t n, Level& L, GatWs& w, const float* dXo, float* dfeat, float* gW,
+                         float* ga, float* gWout, float* gaout, cudaStream_t st) {
+    int rc;
+    const int ldh = nh * HID;
+    const unsigned nb = blocks_for(n, 128);
+    // ---- out_att layer ----
+    att_bwd_row_kernel<OUT, MODE, POST_ELU_LOGSOFTMAX><<<nb, 128, 0, st>>>(L.Wh2, OUT, L.st2, 2, leader, ps, pe, (int)n,
+                                                                           alpha, dXo, OUT, w.dhp, w.stats, w.dst, 2);
+    SGX_LAUNCH_CHECK();
+    att_bwd_col_kernel<OUT, MODE><<<nb, 128, 0, st>>>(L.Wh2, OUT, L.st2, 2, leader, ps, pe, (int)n, alpha, w.dhp,
+                                                      w.stats, aout, w.dWh, OUT, w.dst, 2);
+    SGX_LAUNCH_CHECK();
+    // d(aout) [2][OUT] = dst^T Wh2 ; dWout = x1a^T dWh2 ; dx1a = dWh2 Wout^T
+    if ((rc = gemm(w.dst, 1, 2, L.Wh2, OUT, 1, gaout, OUT, 2, OUT, n, 0, 0, st))) return rc;
+    if ((rc = gemm(L.x1a, 1, ldh, w.dWh, OUT, 1, gWout, OUT, ldh, OUT, n, 0, 0, st))) return rc;
+    if ((rc = gemm(w.dWh, OUT, 1, Wout, 1, OUT, w.dx1a, ldh, n, ldh, OUT, 0, 0, st))) return rc;
+    // ---- heads ----
+    for (int k = 0; k < nh; ++k) {
+        att_bwd_row_kernel<HID, MODE, POST_ELU><<<nb, 128, 0, st>>>(L.Wh1 + k * HID, ldh, L.st1 + 2 * k, 2 * nh, leader,
+                                                                    ps, pe, (int)n, alpha, w.dx1a + k * HID, ldh, w.dhp,
+                                                                    w.stats, w.dst, 2);
+        SGX_LAUNCH_CHECK();
+        att_bwd_col_kernel<HID, MODE><<<nb, 128, 0, st>>>(L.Wh1 + k * HID, ldh, L.st1 + 2 * k, 2 * nh, leader, ps, pe,
+                                                          (int)n, alpha, w.dhp, w.stats, a + (int64_t)k * 2 * HID,
+                                                          w.dWh, HID, w.dst, 2);
+        SGX_LAUNCH_CHECK();
+        if ((rc = gemm(w.dst, 1, 2, L.Wh1 + k * HID, ldh, 1, ga + (int64_t)k * 2 * HID, HID, 2, HID, n, 0, 0, st)))
+            return rc;
+        if ((rc = gemm(feat, 1, fin, w.dWh, HID, 1, gW + (int64_t)k * fin * HID, HID, fin, HID, n, 0, 0, st))) return rc;
+        if ((rc = gemm(w.dWh, HID, 1, W + (int64_t)k * fin * HID, 1, HID, dfeat, fin, n, fin, HID, k > 0, 0, st)))
+            return rc;
+    }
+    return SGX_OK;
+}
+
+static int gat_forward(const float* x, const int32_t* leader, const int32_t* gsize, const int32_t* ps,
+                       const int32_t* pe, int64_t n, const float* Wi, const float* ai, const float* Wio,
+                       const float* aio, const float* We, const float* ae, const float* Weo, const float* aeo,
+                       const float* Wo, const float* bo, float alpha, int nh, int IN, int FIN, float* out, GatWs& w,
+                       cudaStream_t st) {
+    int rc;
+    if ((rc = gat_level_fwd<INTRA>(x, IN, Wi, ai, Wio, aio, nh, alpha, leader, ps, pe, n, w.intra, st))) return rc;
+    gat_pool_kernel<OUT><<<blocks_for(n, 128), 128, 0, st>>>(w.intra.Xo, leader, gsize, pe, (int)n, w.Xg);
+    SGX_LAUNCH_CHECK();
+    if ((rc = gat_level_fwd<INTER>(w.Xg, OUT, We, ae, Weo, aeo, nh, alpha, leader, ps, pe, n, w.inter, st))) return rc;
+    gat_cat_kernel<OUT><<<blocks_for(n * OUT, 256), 256, 0, st>>>(w.intra.Xo, w.inter.Xo, leader, gsize, (int)n, w.cat);
+    SGX_LAUNCH_CHECK();
+    if (out) {
+        // out = cat Wo^T + bo
+        if ((rc = gemm(w.cat, 2 * OUT, 1, Wo, 1, 2 * OUT, out, FIN, n, FIN, 2 * OUT, 0, 0, st, nullptr, bo))) return rc;
+    }
+    return SGX_OK;
+}
+
+}  // namespace sgx
+
+using namespace sgx;
+
+extern "C" int64_t sgx_gat_encoder_ws_bytes(int64_t batch, int64_t n_scenes, int32_t n_heads, int32_t IN, int32_t HID_,
+                                            int32_t OUT_, int32_t FIN) {
+    (void)n_scenes; (void)IN; (void)HID_; (void)OUT_; (void)FIN;
+    Carver c(nullptr);
+    GatWs w;
+    return carve_gat(c, w, batch, n_heads);
+}
+
+static int gat_check(int nh, int IN, int HID_, int OUT_, int FIN) {
+    SGX_REQUIRE(nh >= 1 && nh <= 16 && IN >= 1 && FIN >= 1, "gat_encoder: bad dims");
+    SGX_UNSUPPORTED(HID_ != HID || OUT_ != OUT,
+                    "gat_encoder: only hidden=72, out=16 are built (the reference hard-codes them, models.py:242-243); "
+                    "got hidden=%d out=%d", HID_, OUT_);
+    return SGX_OK;
+}
+
+extern "C" int sgx_gat_encoder_fwd(const float* x, const int32_t* leader, const int32_t* group_size,
+                                   const int32_t* ped_start, const int32_t* ped_end, int64_t batch, int64_t n_scenes,
+                                   const float* Wi, const float* ai, const float* Wio, const float* aio,
+                                   const float* We, const float* ae, const float* Weo, const float* aeo,
+                                   const float* Wo, const float* bo, float alpha, int32_t n_heads, int32_t IN,
+                                   int32_t HID_, int32_t OUT_, int32_t FIN, float* out, void* workspace,
+                                   int64_t ws_bytes, void* stream) {
+    SGX_REQUIRE(x && leader && group_size && ped_start && ped_end && Wi && ai && Wio && aio && We && ae && Weo && aeo &&
+                    Wo && bo && out && workspace, "sgx_gat_encoder_fwd: null pointer");
+    SGX_REQUIRE(batch > 0, "sgx_gat_encoder_fwd: empty batch");
+    int rc = gat_check(n_heads, IN, HID_, OUT_, FIN);
+    if (rc) return rc;
+    SGX_REQUIRE(ws_bytes >= sgx_gat_encoder_ws_bytes(batch, n_scenes, n_heads, IN, HID_, OUT_, FIN),
+                "sgx_gat_encoder_fwd: workspace too small");
+    Carver c(workspace);
+    GatWs w;
+    carve_gat(c, w, batch, n_heads);
+    return gat_forward(x, leader, group_size, ped_start, ped_end, batch, Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo,
+                       alpha, n_heads, IN, FIN, out, w, (cudaStream_t)stream);
+}
+
+extern "C" int sgx_gat_encoder_bwd(const float* x, const float* grad_out, const int32_t* leader,
+                                   const int32_t* group_size, const int32_t* ped_start, const int32_t* ped_end,
+                                   int64_t batch, int64_t n_scenes, const float* Wi, const float* ai, const float* Wio,
+                                   const float* aio, const float* We, const float* ae, const float* Weo,
+                                   const float* aeo, const float* Wo, const float* bo, float alpha, int32_t n_heads,
+                                   int32_t IN, int32_t HID_, int32_t OUT_, int32_t FIN, float* grad_x, float* grad_Wi,
+                                   float* grad_ai, float* grad_Wio, float* grad_aio, float* grad_We, float* grad_ae,
+                                   float* grad_Weo, float* grad_aeo, float* grad_Wo, float* grad_bo, void* workspace,
+                                   int64_t ws_bytes, void* stream) {
+    SGX_REQUIRE(x && grad_out && leader && group_size && ped_start && ped_end && Wi && ai && Wio && aio && We && ae &&
+                    Weo && aeo && Wo && bo && grad_x && grad_Wi && grad_ai && grad_Wio && grad_aio && grad_We &&
+                    grad_ae && grad_Weo && grad_aeo && grad_Wo && grad_bo && workspace,
+                "sgx_gat_encoder_bwd: null pointer");
+    SGX_REQUIRE(batch > 0, "sgx_gat_encoder_bwd: empty batch");
+    int rc = gat_check(n_heads, IN, HID_, OUT_, FIN);
+    if (rc) return rc;
+    SGX_REQUIRE(ws_bytes >= sgx_gat_encoder_ws_bytes(batch, n_scenes, n_heads, IN, HID_, OUT_, FIN),
+                "sgx_gat_encoder_bwd: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    Carver c(workspace);
+    GatWs w;
+    carve_gat(c, w, batch, n_heads);
+    const int64_t n = batch;
+    // recompute the forward intermediates (cheaper than keeping ~2 KB per ped alive between fwd and bwd)
+    if ((rc = gat_forward(x, leader, group_size, ped_start, ped_end, n, Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo, alpha,
+                          n_heads, IN, FIN, nullptr, w, st)))
+        return rc;
+    // final Linear: dcat = gout Wo ; dWo = gout^T cat ; dbo = colsum(gout)
+    if ((rc = gemm(grad_out, FIN, 1, Wo, 2 * OUT, 1, w.dcat, 2 * OUT, n, 2 * OUT, FIN, 0, 0, st))) return rc;
+    if ((rc = gemm(grad_out, 1, FIN, w.cat, 2 * OUT, 1, grad_Wo, 2 * OUT, FIN, 2 * OUT, n, 0, 0, st))) return rc;
+    SGX_CUDA(cudaMemsetAsync(grad_bo, 0, (size_t)FIN * 4, st));
+    colsum_kernel<<<dim3((FIN + 31) / 32, 64), 256, 0, st>>>(grad_out, n, FIN, grad_bo);
+    SGX_LAUNCH_CHECK();
+    gat_unpool_bwd_kernel<OUT><<<blocks_for(n, 128), 128, 0, st>>>(w.dcat, leader, group_size, ped_end, (int)n, w.dYg);
+    SGX_LAUNCH_CHECK();
+    if ((rc = gat_level_bwd<INTER>(w.Xg, OUT, We, ae, Weo, aeo, n_heads, alpha, leader, ped_start, ped_end, n, w.inter, w,
+                                   w.dYg, w.dXg, grad_We, grad_ae, grad_Weo, grad_aeo, st)))
+        return rc;
+    gat_pool_bwd_kernel<OUT><<<blocks_for(n * OUT, 256), 256, 0, st>>>(w.dcat, w.dXg, leader, group_size, (int)n, w.dX1);
+    SGX_LAUNCH_CHECK();
+    if ((rc = gat_level_bwd<INTRA>(x, IN, Wi, ai, Wio, aio, n_heads, alpha, leader, ped_start, ped_end, n, w.intra, w,
+                                   w.dX1, grad_x, grad_Wi, grad_ai, grad_Wio, grad_aio, st)))
+        return rc;
+    return SGX_OK;
+}

@@ -1,0 +1,491 @@
+// GCNModule forward/backward (sgan/models.py:628-712, GCN.forward 573-580), gcn_layers = 2.
+//
+// The reference multiplies dense N x N (row-normalised) adjacencies: A_intra has fl(1/|g|) on the
+// members of the row's group, A_inter = 1/G everywhere.  A.H is therefore a *segmented mean*:
+// every member of a group sees the same aggregated row, every group of a scene sees the same
+// inter-group row.  The kernels below work on that structure directly (segmented SpMM):
+//
+//   gcn_group_kernel  (thread per ped, leaders work):  M1 = sum_{j in g} a X_j ; H1 = relu(M1 W0)
+//                      M2 = sum_{j in g} a H1 ; X1 = relu(M2 W1) ; Xg = sum_{j in g} a X1
+//   gcn_scene_kernel  (thread per scene):              N1 = sum_g c Xg ; K1 = relu(N1 V0)
+//                      N2 = sum_g c K1 ; Y = relu(N2 V1)
+//   gcn_out_kernel    (thread per ped):                out = Wo [X1_g ; a Y] + bo
+//
+// Sums over identical rows are performed term by term (k additions of a*v) so the arithmetic stays
+// as close to the dense matmul as a different summation order allows.  Backward reuses the same three
+// levels in reverse; parameter gradients are tall-skinny GEMMs over per-group / per-scene rows.
+#include "sgx_common.cuh"
+
+namespace sgx {
+
+template <int NI, int NO>
+__device__ __forceinline__ void matvec(const float* __restrict__ sW /*[NO][NI] in smem*/, const float (&x)[NI],
+                                       float (&y)[NO]) {
+#pragma unroll
+    for (int o = 0; o < NO; ++o) {
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < NI; c += 4) {
+            float4 w = *reinterpret_cast<const float4*>(sW + o * NI + c);
+            s = fmaf(x[c], w.x, s); s = fmaf(x[c + 1], w.y, s); s = fmaf(x[c + 2], w.z, s); s = fmaf(x[c + 3], w.w, s);
+        }
+        y[o] = s;
+    }
+}
+
+__device__ __forceinline__ float repeat_sum(float term, int k) {
+    float s = 0.f;
+    for (int t = 0; t < k; ++t) s += term;
+    return s;
+}
+
+// load a [R][C] row-major global matrix into smem, optionally transposed to [C][R]
+__device__ __forceinline__ void load_w(float* dst, const float* __restrict__ src, int R, int C, bool transpose) {
+    for (int e = threadIdx.x; e < R * C; e += blockDim.x) {
+        int r = e / C, c = e % C;
+        dst[transpose ? c * R + r : e] = src[e];
+    }
+}
+
+template <int IN, int HID, int OUT>
+__global__ void __launch_bounds__(128)
+gcn_group_kernel(const float* __restrict__ x, const int32_t* __restrict__ leader, const int32_t* __restrict__ gsize,
+                 const int32_t* __restrict__ ped_start, const int32_t* __restrict__ ped_end, int batch,
+                 const float* __restrict__ W0, const float* __restrict__ W1, float* __restrict__ X1g,
+                 float* __restrict__ Xg, float* __restrict__ M1s, float* __restrict__ M2s) {
+    __shared__ __align__(16) float sW0t[HID * IN];   // [HID][IN]
+    __shared__ __align__(16) float sW1[HID * OUT];   // [HID][OUT]
+    load_w(sW0t, W0, IN, HID, true);
+    load_w(sW1, W1, HID, OUT, false);
+    __syncthreads();
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= batch) return;
+    const bool lead = (leader[p] == p);
+    float x1[OUT];
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) x1[o] = 0.f;
+    if (lead) {
+        const int k = gsize[p];
+        const float a = __frcp_rn((float)k);
+        float m1[IN];
+#pragma unroll
+        for (int c = 0; c < IN; ++c) m1[c] = 0.f;
+        const int e = ped_end[p];
+        for (int q = p; q < e; ++q) {
+            if (leader[q] != p) continue;
+            const float4* row = reinterpret_cast<const float4*>(x + (int64_t)q * IN);
+#pragma unroll
+            for (int c = 0; c < IN / 4; ++c) {
+                float4 v = row[c];
+                m1[4 * c] = fmaf(a, v.x, m1[4 * c]); m1[4 * c + 1] = fmaf(a, v.y, m1[4 * c + 1]);
+                m1[4 * c + 2] = fmaf(a, v.z, m1[4 * c + 2]); m1[4 * c + 3] = fmaf(a, v.w, m1[4 * c + 3]);
+            }
+        }
+        if (M1s) {
+#pragma unroll
+            for (int c = 0; c < IN; ++c) M1s[(int64_t)p * IN + c] = m1[c];
+        }
+        for (int f = 0; f < HID; ++f) {
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < IN; c += 4) {
+                float4 w = *reinterpret_cast<const float4*>(sW0t + f * IN + c);
+                s = fmaf(m1[c], w.x, s); s = fmaf(m1[c + 1], w.y, s); s = fmaf(m1[c + 2], w.z, s); s = fmaf(m1[c + 3], w.w, s);
+            }
+            const float h1 = fmaxf(s, 0.f);
+            const float m2 = repeat_sum(a * h1, k);
+            if (M2s) M2s[(int64_t)p * HID + f] = m2;
+#pragma unroll
+            for (int o = 0; o < OUT; o += 4) {
+                float4 w = *reinterpret_cast<const float4*>(sW1 + f * OUT + o);
+                x1[o] = fmaf(m2, w.x, x1[o]); x1[o + 1] = fmaf(m2, w.y, x1[o + 1]);
+                x1[o + 2] = fmaf(m2, w.z, x1[o + 2]); x1[o + 3] = fmaf(m2, w.w, x1[o + 3]);
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) {
+            x1[o] = fmaxf(x1[o], 0.f);
+            X1g[(int64_t)p * OUT + o] = x1[o];
+            Xg[(int64_t)p * OUT + o] = repeat_sum(a * x1[o], k);
+        }
+    } else if (M1s) {  // backward consumes these as GEMM operands: non-leader rows must be zero
+#pragma unroll
+        for (int c = 0; c < IN; ++c) M1s[(int64_t)p * IN + c] = 0.f;
+        for (int f = 0; f < HID; ++f) M2s[(int64_t)p * HID + f] = 0.f;
+    }
+}
+
+// per scene: rows of Yrow / N1s / N2s / K1s are indexed by the scene's first pedestrian
+template <int HID, int OUT>
+__global__ void __launch_bounds__(128)
+gcn_scene_kernel(const float* __restrict__ Xg, const int32_t* __restrict__ leader,
+                 const int32_t* __restrict__ scene_start, const int32_t* __restrict__ n_group, int n_scenes,
+                 const float* __restrict__ V0, const float* __restrict__ V1, float* __restrict__ Yrow,
+                 float* __restrict__ N1s, float* __restrict__ N2s, float* __restrict__ K1s) {
+    __shared__ __align__(16) float sV0t[HID * OUT];  // [HID][OUT]
+    __shared__ __align__(16) float sV1[HID * OUT];   // [HID][OUT]
+    load_w(sV0t, V0, OUT, HID, true);
+    load_w(sV1, V1, HID, OUT, false);
+    __syncthreads();
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_scenes) return;
+    const int b = scene_start[s], e = scene_start[s + 1], G = n_group[s];
+    const float c = __frcp_rn((float)G);
+    float n1[OUT];
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) n1[o] = 0.f;
+    for (int q = b; q < e; ++q) {
+        if (leader[q] != q) continue;
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) n1[o] = fmaf(c, Xg[(int64_t)q * OUT + o], n1[o]);
+    }
+    float y[OUT];
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) y[o] = 0.f;
+    for (int f = 0; f < HID; ++f) {
+        float sacc = 0.f;
+#pragma unroll
+        for (int o = 0; o < OUT; o += 4) {
+            float4 w = *reinterpret_cast<const float4*>(sV0t + f * OUT + o);
+            sacc = fmaf(n1[o], w.x, sacc); sacc = fmaf(n1[o + 1], w.y, sacc);
+            sacc = fmaf(n1[o + 2], w.z, sacc); sacc = fmaf(n1[o + 3], w.w, sacc);
+        }
+        const float k1 = fmaxf(sacc, 0.f);
+        const float n2 = repeat_sum(c * k1, G);
+        if (N2s) { N2s[(int64_t)b * HID + f] = n2; K1s[(int64_t)b * HID + f] = k1; }
+#pragma unroll
+        for (int o = 0; o < OUT; o += 4) {
+            float4 w = *reinterpret_cast<const float4*>(sV1 + f * OUT + o);
+            y[o] = fmaf(n2, w.x, y[o]); y[o + 1] = fmaf(n2, w.y, y[o + 1]);
+            y[o + 2] = fmaf(n2, w.z, y[o + 2]); y[o + 3] = fmaf(n2, w.w, y[o + 3]);
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) {
+        Yrow[(int64_t)b * OUT + o] = fmaxf(y[o], 0.f);
+        if (N1s) N1s[(int64_t)b * OUT + o] = n1[o];
+    }
+}
+
+template <int OUT, int FIN>
+__global__ void __launch_bounds__(128)
+gcn_out_kernel(const float* __restrict__ X1g, const float* __restrict__ Yrow, const int32_t* __restrict__ leader,
+               const int32_t* __restrict__ gsize, const int32_t* __restrict__ ped_start, int batch,
+               const float* __restrict__ Wo, const float* __restrict__ bo, float* __restrict__ out,
+               float* __restrict__ cat_save) {
+    __shared__ __align__(16) float sWo[FIN * 2 * OUT];
+    __shared__ float sbo[FIN];
+    load_w(sWo, Wo, FIN, 2 * OUT, false);
+    for (int e = threadIdx.x; e < FIN; e += blockDim.x) sbo[e] = bo[e];
+    __syncthreads();
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= batch) return;
+    const int l = leader[p];
+    const float a = __frcp_rn((float)gsize[p]);
+    float cat[2 * OUT];
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) {
+        cat[o] = X1g[(int64_t)l * OUT + o];
+        cat[OUT + o] = a * Yrow[(int64_t)ped_start[p] * OUT + o];
+    }
+    if (cat_save) {
+#pragma unroll
+        for (int o = 0; o < 2 * OUT; ++o) cat_save[(int64_t)p * 2 * OUT + o] = cat[o];
+    }
+    if (!out) return;
+    float y[FIN];
+    matvec<2 * OUT, FIN>(sWo, cat, y);
+#pragma unroll
+    for (int o = 0; o < FIN; ++o) out[(int64_t)p * FIN + o] = y[o] + sbo[o];
+}
+
+// ---- backward -----------------------------------------------------------------------------------
+// per ped: dcat = Wo^T dOut   ([dx1 | dx2])
+template <int OUT, int FIN>
+__global__ void __launch_bounds__(128)
+gcn_bwd_out_kernel(const float* __restrict__ gout, int batch, const float* __restrict__ Wo, float* __restrict__ dcat) {
+    __shared__ __align__(16) float sWot[2 * OUT * FIN];  // [2*OUT][FIN]
+    load_w(sWot, Wo, FIN, 2 * OUT, true);
+    __syncthreads();
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= batch) return;
+    float g[FIN];
+#pragma unroll
+    for (int o = 0; o < FIN; ++o) g[o] = gout[(int64_t)p * FIN + o];
+    float d[2 * OUT];
+    matvec<FIN, 2 * OUT>(sWot, g, d);
+#pragma unroll
+    for (int o = 0; o < 2 * OUT; ++o) dcat[(int64_t)p * 2 * OUT + o] = d[o];
+}
+
+// per scene: dYsum = sum_p a_p dx2_p ; back through the inter GCN; writes dXg (same for every group of
+// the scene) at the scene row, and the GEMM operands for dV0 / dV1.
+template <int HID, int OUT>
+__global__ void __launch_bounds__(128)
+gcn_bwd_scene_kernel(const float* __restrict__ dcat, const float* __restrict__ Yrow, const float* __restrict__ K1s,
+                     const int32_t* __restrict__ gsize, const int32_t* __restrict__ scene_start,
+                     const int32_t* __restrict__ n_group, int n_scenes, const float* __restrict__ V0,
+                     const float* __restrict__ V1, float* __restrict__ dXg_row, float* __restrict__ dYm,
+                     float* __restrict__ dK1m) {
+    __shared__ __align__(16) float sV1[HID * OUT];  // [HID][OUT]  (dN2[f] = sum_o dYm[o] V1[f][o])
+    __shared__ __align__(16) float sV0[OUT * HID];  // [OUT][HID]  (dN1[o] = sum_f dK1m[f] V0[o][f])
+    load_w(sV1, V1, HID, OUT, false);
+    load_w(sV0, V0, OUT, HID, false);
+    __syncthreads();
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_scenes) return;
+    const int b = scene_start[s], e = scene_start[s + 1], G = n_group[s];
+    const float c = __frcp_rn((float)G);
+    float dy[OUT];
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) dy[o] = 0.f;
+    for (int q = b; q < e; ++q) {
+        const float a = __frcp_rn((float)gsize[q]);
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) dy[o] = fmaf(a, dcat[(int64_t)q * 2 * OUT + OUT + o], dy[o]);
+    }
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) {
+        if (!(Yrow[(int64_t)b * OUT + o] > 0.f)) dy[o] = 0.f;
+        dYm[(int64_t)b * OUT + o] = dy[o];
+    }
+    float dn1[OUT];
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) dn1[o] = 0.f;
+    for (int f = 0; f < HID; ++f) {
+        float dn2 = 0.f;
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) dn2 = fmaf(dy[o], sV1[f * OUT + o], dn2);
+        // N2_i = sum_g c K1_g for each of the G rows i  =>  dK1 (per row g) = c * sum_i dN2_i = c * dn2
+        float dk1 = (K1s[(int64_t)b * HID + f] > 0.f) ? c * dn2 : 0.f;
+        // operand for dV0 = sum_g N1^T (dK1_g * mask) = N1^T (G * dk1)
+        dK1m[(int64_t)b * HID + f] = (float)G * dk1;
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) dn1[o] = fmaf(dk1, sV0[o * HID + f], dn1[o]);
+    }
+    // N1_g = sum_g' c Xg_g' for each of the G rows  =>  dXg_g' = c * sum_g dN1_g = c * G * dn1
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) dXg_row[(int64_t)b * OUT + o] = c * (float)G * dn1[o];
+}
+
+// per leader: gather dx1 of the members, add the GPool path, back through the intra GCN.
+template <int IN, int HID, int OUT>
+__global__ void __launch_bounds__(128)
+gcn_bwd_group_kernel(const float* __restrict__ dcat, const float* __restrict__ dXg_row,
+                     const float* __restrict__ X1g, const float* __restrict__ M1s, const int32_t* __restrict__ leader,
+                     const int32_t* __restrict__ gsize, const int32_t* __restrict__ ped_start,
+                     const int32_t* __restrict__ ped_end, int batch, const float* __restrict__ W0,
+                     const float* __restrict__ W1, float* __restrict__ dX1m, float* __restrict__ dH1m,
+                     float* __restrict__ dM1sum) {
+    __shared__ __align__(16) float sW0t[HID * IN];   // [HID][IN]: recompute H1 mask and dM1 = dH1m W0^T
+    __shared__ __align__(16) float sW1[HID * OUT];   // [HID][OUT]
+    load_w(sW0t, W0, IN, HID, true);
+    load_w(sW1, W1, HID, OUT, false);
+    __syncthreads();
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= batch) return;
+    if (leader[p] != p) {
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) dX1m[(int64_t)p * OUT + o] = 0.f;
+        for (int f = 0; f < HID; ++f) dH1m[(int64_t)p * HID + f] = 0.f;
+        return;
+    }
+    const int k = gsize[p];
+    const float a = __frcp_rn((float)k);
+    const int sb = ped_start[p], e = ped_end[p];
+    float dx1[OUT];
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) dx1[o] = 0.f;
+    for (int q = p; q < e; ++q) {
+        if (leader[q] != p) continue;
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) dx1[o] += dcat[(int64_t)q * 2 * OUT + o];
+    }
+    // Xg_g = sum_{j in g} a X1_j: every member row receives a * dXg; k members
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) {
+        dx1[o] += (float)k * a * dXg_row[(int64_t)sb * OUT + o];
+        if (!(X1g[(int64_t)p * OUT + o] > 0.f)) dx1[o] = 0.f;
+        dX1m[(int64_t)p * OUT + o] = dx1[o];   // operand of dW1 = M2^T dX1m
+    }
+    float m1[IN], dm1[IN];
+#pragma unroll
+    for (int c = 0; c < IN; ++c) { m1[c] = M1s[(int64_t)p * IN + c]; dm1[c] = 0.f; }
+    for (int f = 0; f < HID; ++f) {
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < IN; ++c) s = fmaf(m1[c], sW0t[f * IN + c], s);
+        float dm2 = 0.f;
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) dm2 = fmaf(dx1[o], sW1[f * OUT + o], dm2);
+        // M2_i = sum_j a H1_j (k rows i, k rows j) => dH1_j = a * sum_i dM2_i = a * dm2 ; summed over j: k*a*dm2
+        float dh1 = (s > 0.f) ? (float)k * a * dm2 : 0.f;
+        dH1m[(int64_t)p * HID + f] = dh1;       // operand of dW0 = M1^T dH1m
+#pragma unroll
+        for (int c = 0; c < IN; ++c) dm1[c] = fmaf(dh1, sW0t[f * IN + c], dm1[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < IN; ++c) dM1sum[(int64_t)p * IN + c] = dm1[c];
+}
+
+// per ped: dX_p = a * dM1sum[leader]
+template <int IN>
+__global__ void gcn_bwd_x_kernel(const float* __restrict__ dM1sum, const int32_t* __restrict__ leader,
+                                 const int32_t* __restrict__ gsize, int batch, float* __restrict__ dx) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)batch * IN) return;
+    int p = (int)(idx / IN), c = (int)(idx % IN);
+    dx[idx] = __frcp_rn((float)gsize[p]) * dM1sum[(int64_t)leader[p] * IN + c];
+}
+
+__global__ void colsum_kernel(const float* __restrict__ m, int64_t rows, int cols, float* __restrict__ out) {
+    // out[c] = sum_r m[r][c]; one block per column chunk of 32, grid-stride over rows, atomics to finish
+    int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    int r0 = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int stride = gridDim.y * (blockDim.x >> 5);
+    float s = 0.f;
+    if (c < cols)
+        for (int64_t r = r0; r < rows; r += stride) s += m[r * cols + c];
+    if (c < cols && s != 0.f) atomicAdd(&out[c], s);
+}
+
+struct GcnWs {
+    float *X1g, *Xg, *M1s, *M2s, *Yrow, *N1s, *N2s, *K1s, *cat, *dcat, *dXg_row, *dYm, *dK1m, *dX1m, *dH1m, *dM1sum;
+};
+
+static int64_t carve_gcn(Carver& c, GcnWs& w, int64_t batch, int IN, int HID, int OUT) {
+    w.X1g = c.take<float>(batch * OUT); w.Xg = c.take<float>(batch * OUT);
+    w.M1s = c.take<float>(batch * IN); w.M2s = c.take<float>(batch * HID);
+    w.Yrow = c.take<float>(batch * OUT); w.N1s = c.take<float>(batch * OUT);
+    w.N2s = c.take<float>(batch * HID); w.K1s = c.take<float>(batch * HID);
+    w.cat = c.take<float>(batch * 2 * OUT); w.dcat = c.take<float>(batch * 2 * OUT);
+    w.dXg_row = c.take<float>(batch * OUT); w.dYm = c.take<float>(batch * OUT);
+    w.dK1m = c.take<float>(batch * HID); w.dX1m = c.take<float>(batch * OUT);
+    w.dH1m = c.take<float>(batch * HID); w.dM1sum = c.take<float>(batch * IN);
+    return c.off;
+}
+
+template <int IN, int HID, int OUT, int FIN>
+static int gcn_forward(const float* x, const int32_t* leader, const int32_t* gsize, const int32_t* ped_start,
+                       const int32_t* ped_end, const int32_t* scene_start, const int32_t* n_group, int64_t batch,
+                       int64_t S, const float* W0, const float* W1, const float* V0, const float* V1, const float* Wo,
+                       const float* bo, float* out, GcnWs& w, bool save, cudaStream_t st) {
+    gcn_group_kernel<IN, HID, OUT><<<blocks_for(batch, 128), 128, 0, st>>>(
+        x, leader, gsize, ped_start, ped_end, (int)batch, W0, W1, w.X1g, w.Xg, save ? w.M1s : nullptr,
+        save ? w.M2s : nullptr);
+    SGX_LAUNCH_CHECK();
+    gcn_scene_kernel<HID, OUT><<<blocks_for(S, 128), 128, 0, st>>>(w.Xg, leader, scene_start, n_group, (int)S, V0, V1,
+                                                                  w.Yrow, save ? w.N1s : nullptr,
+                                                                  save ? w.N2s : nullptr, save ? w.K1s : nullptr);
+    SGX_LAUNCH_CHECK();
+    if (out || save) {
+        gcn_out_kernel<OUT, FIN><<<blocks_for(batch, 128), 128, 0, st>>>(w.X1g, w.Yrow, leader, gsize, ped_start,
+                                                                        (int)batch, Wo, bo, out,
+                                                                        save ? w.cat : nullptr);
+        SGX_LAUNCH_CHECK();
+    }
+    return SGX_OK;
+}
+
+}  // namespace sgx
+
+using namespace sgx;
+
+extern "C" int64_t sgx_gcn_module_ws_bytes(int64_t batch, int64_t n_scenes, int32_t IN, int32_t HID, int32_t OUT,
+                                           int32_t FIN) {
+    (void)n_scenes; (void)FIN;
+    Carver c(nullptr);
+    GcnWs w;
+    return carve_gcn(c, w, batch, IN, HID, OUT);
+}
+
+#define GCN_DISPATCH(CALL)                                                                        \
+    if (IN == 40 && HID == 72 && OUT == 16 && FIN == 24) { constexpr int I = 40, F = 24; CALL; }      \
+    else if (IN == 32 && HID == 72 && OUT == 16 && FIN == 24) { constexpr int I = 32, F = 24; CALL; } \
+    else if (IN == 40 && HID == 72 && OUT == 16 && FIN == 32) { constexpr int I = 40, F = 32; CALL; } \
+    else if (IN == 32 && HID == 72 && OUT == 16 && FIN == 32) { constexpr int I = 32, F = 32; CALL; } \
+    else {                                                                                        \
+        sgx::set_error("GCNModule dims (in=%d hid=%d out=%d final=%d) have no kernel instance; "      \
+                       "built: in {32,40}, hid 72, out 16, final {24,32}", IN, HID, OUT, FIN);         \
+        return SGX_ERR_UNSUPPORTED;                                                               \
+    }
+
+extern "C" int sgx_gcn_module_fwd(const float* x, const int32_t* leader, const int32_t* group_size,
+                                  const int32_t* ped_start, const int32_t* ped_end, const int32_t* scene_start,
+                                  const int32_t* n_group, int64_t batch, int64_t n_scenes, const float* W0,
+                                  const float* W1, const float* V0, const float* V1, const float* Wo, const float* bo,
+                                  int32_t IN, int32_t HID, int32_t OUT, int32_t FIN, float* out, void* workspace,
+                                  int64_t ws_bytes, void* stream) {
+    SGX_REQUIRE(x && leader && group_size && ped_start && ped_end && scene_start && n_group && W0 && W1 && V0 && V1 &&
+                    Wo && bo && out && workspace, "sgx_gcn_module_fwd: null pointer");
+    SGX_REQUIRE(batch > 0 && n_scenes > 0, "sgx_gcn_module_fwd: empty batch");
+    SGX_REQUIRE(ws_bytes >= sgx_gcn_module_ws_bytes(batch, n_scenes, IN, HID, OUT, FIN), "workspace too small");
+    Carver c(workspace);
+    GcnWs w;
+    carve_gcn(c, w, batch, IN, HID, OUT);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = SGX_OK;
+    GCN_DISPATCH((rc = gcn_forward<I, 72, 16, F>(x, leader, group_size, ped_start, ped_end, scene_start, n_group, batch,
+                                                 n_scenes, W0, W1, V0, V1, Wo, bo, out, w, false, st)));
+    return rc;
+}
+
+template <int IN, int HID, int OUT, int FIN>
+static int gcn_backward(const float* x, const float* gout, const int32_t* leader, const int32_t* gsize,
+                        const int32_t* ped_start, const int32_t* ped_end, const int32_t* scene_start,
+                        const int32_t* n_group, int64_t batch, int64_t S, const float* W0, const float* W1,
+                        const float* V0, const float* V1, const float* Wo, const float* bo, float* gx, float* gW0,
+                        float* gW1, float* gV0, float* gV1, float* gWo, float* gbo, GcnWs& w, cudaStream_t st) {
+    // per-scene operands live at the row of the scene's first ped; all other rows must be zero for the GEMMs
+    SGX_CUDA(cudaMemsetAsync(w.N1s, 0, (size_t)batch * OUT * 4, st));
+    SGX_CUDA(cudaMemsetAsync(w.N2s, 0, (size_t)batch * HID * 4, st));
+    SGX_CUDA(cudaMemsetAsync(w.dYm, 0, (size_t)batch * OUT * 4, st));
+    SGX_CUDA(cudaMemsetAsync(w.dK1m, 0, (size_t)batch * HID * 4, st));
+    int rc = gcn_forward<IN, HID, OUT, FIN>(x, leader, gsize, ped_start, ped_end, scene_start, n_group, batch, S, W0, W1,
+                                            V0, V1, Wo, bo, nullptr, w, true, st);
+    if (rc) return rc;
+    gcn_bwd_out_kernel<OUT, FIN><<<blocks_for(batch, 128), 128, 0, st>>>(gout, (int)batch, Wo, w.dcat);
+    SGX_LAUNCH_CHECK();
+    // dWo = gout^T cat ; dbo = colsum(gout)
+    if ((rc = gemm(gout, 1, FIN, w.cat, 2 * OUT, 1, gWo, 2 * OUT, FIN, 2 * OUT, batch, 0, 0, st))) return rc;
+    SGX_CUDA(cudaMemsetAsync(gbo, 0, FIN * 4, st));
+    colsum_kernel<<<dim3((FIN + 31) / 32, 64), 256, 0, st>>>(gout, batch, FIN, gbo);
+    SGX_LAUNCH_CHECK();
+    gcn_bwd_scene_kernel<HID, OUT><<<blocks_for(S, 128), 128, 0, st>>>(w.dcat, w.Yrow, w.K1s, gsize, scene_start,
+                                                                      n_group, (int)S, V0, V1, w.dXg_row, w.dYm, w.dK1m);
+    SGX_LAUNCH_CHECK();
+    if ((rc = gemm(w.N2s, 1, HID, w.dYm, OUT, 1, gV1, OUT, HID, OUT, batch, 0, 0, st))) return rc;
+    if ((rc = gemm(w.N1s, 1, OUT, w.dK1m, HID, 1, gV0, HID, OUT, HID, batch, 0, 0, st))) return rc;
+    gcn_bwd_group_kernel<IN, HID, OUT><<<blocks_for(batch, 128), 128, 0, st>>>(
+        w.dcat, w.dXg_row, w.X1g, w.M1s, leader, gsize, ped_start, ped_end, (int)batch, W0, W1, w.dX1m, w.dH1m,
+        w.dM1sum);
+    SGX_LAUNCH_CHECK();
+    if ((rc = gemm(w.M2s, 1, HID, w.dX1m, OUT, 1, gW1, OUT, HID, OUT, batch, 0, 0, st))) return rc;
+    if ((rc = gemm(w.M1s, 1, IN, w.dH1m, HID, 1, gW0, HID, IN, HID, batch, 0, 0, st))) return rc;
+    gcn_bwd_x_kernel<IN><<<blocks_for(batch * IN, 256), 256, 0, st>>>(w.dM1sum, leader, gsize, (int)batch, gx);
+    SGX_LAUNCH_CHECK();
+    return SGX_OK;
+}
+
+extern "C" int sgx_gcn_module_bwd(const float* x, const float* grad_out, const int32_t* leader,
+                                  const int32_t* group_size, const int32_t* ped_start, const int32_t* ped_end,
+                                  const int32_t* scene_start, const int32_t* n_group, int64_t batch, int64_t n_scenes,
+                                  const float* W0, const float* W1, const float* V0, const float* V1, const float* Wo,
+                                  const float* bo, int32_t IN, int32_t HID, int32_t OUT, int32_t FIN, float* grad_x,
+                                  float* grad_W0, float* grad_W1, float* grad_V0, float* grad_V1, float* grad_Wo,
+                                  float* grad_bo, void* workspace, int64_t ws_bytes, void* stream) {
+    SGX_REQUIRE(x && grad_out && leader && group_size && ped_start && ped_end && scene_start && n_group && W0 && W1 &&
+                    V0 && V1 && Wo && bo && grad_x && grad_W0 && grad_W1 && grad_V0 && grad_V1 && grad_Wo && grad_bo &&
+                    workspace, "sgx_gcn_module_bwd: null pointer");
+    SGX_REQUIRE(batch > 0 && n_scenes > 0, "sgx_gcn_module_bwd: empty batch");
+    SGX_REQUIRE(ws_bytes >= sgx_gcn_module_ws_bytes(batch, n_scenes, IN, HID, OUT, FIN), "workspace too small");
+    Carver c(workspace);
+    GcnWs w;
+    carve_gcn(c, w, batch, IN, HID, OUT);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = SGX_OK;
+    GCN_DISPATCH((rc = gcn_backward<I, 72, 16, F>(x, grad_out, leader, group_size, ped_start, ped_end, scene_start,
+                                                  n_group, batch, n_scenes, W0, W1, V0, V1, Wo, bo, grad_x, grad_W0,
+                                                  grad_W1, grad_V0, grad_V1, grad_Wo, grad_bo, w, st)));
+    return rc;
+}

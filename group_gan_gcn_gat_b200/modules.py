@@ -1,0 +1,218 @@
+"""nn.Module mirror of the reference's social-interaction modules, backed by libsgx_b200.so.
+
+Same constructor arguments, forward signatures and ``state_dict`` key names as sgan/models.py, so
+``checkpoint['g_state']`` / ``['d_state']`` load with ``strict=True`` and the reference's callers
+(sgan/models.py:164, 880, 905, 902, 989) work unchanged:
+
+    PoolHiddenNet.forward(h_states, seq_start_end, end_pos)             sgan/models.py:497
+    GraphAttentionLayer.forward(h, adj) / GAT.forward(x, adj)           sgan/models.py:198 / 231
+    GATEncoder.forward(h_states, seq_start_end, end_pos, end_group)     sgan/models.py:254
+    GCN.forward(A, X)                                                   sgan/models.py:573
+    GCNModule.forward(h_states, seq_start_end, end_pos, end_group)      sgan/models.py:628
+
+The per-scene python loops of the reference are gone: every forward is a handful of kernel launches
+over the whole ragged batch.  Unsupported reference options raise instead of silently changing
+numerics: batch_norm=1 / dropout>0 inside the fused ops (never used by any shipped checkpoint).
+"""
+import os
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .schedule import get_schedule
+
+
+def make_mlp(dim_list, activation='relu', batch_norm=True, dropout=0):
+    """[Linear, (BatchNorm1d), ReLU|LeakyReLU, (Dropout)] per consecutive dim pair -- the activation also
+    follows the LAST Linear, as in sgan/models.py:7-20 (pooled features and D scores are >= 0)."""
+    mods = []
+    for d_in, d_out in zip(dim_list, dim_list[1:]):
+        mods.append(nn.Linear(d_in, d_out))
+        if batch_norm:
+            mods.append(nn.BatchNorm1d(d_out))
+        if activation == 'relu':
+            mods.append(nn.ReLU())
+        elif activation == 'leakyrelu':
+            mods.append(nn.LeakyReLU())
+        if dropout > 0:
+            mods.append(nn.Dropout(p=dropout))
+    return nn.Sequential(*mods)
+
+
+def _precision_code(name):
+    name = (name or 'fp32').lower()
+    if name in ('fp32', 'float32'):
+        return ops.PRECISION_FP32
+    if name in ('bf16', 'bfloat16'):
+        return ops.PRECISION_BF16
+    raise ValueError('unknown pooling precision %r (fp32 | bf16)' % (name,))
+
+
+class PoolHiddenNet(nn.Module):
+    """Pairwise social pooling (sgan/models.py:458-549), fused: no N^2 x 512 tensor is materialised.
+
+    ``precision``: 'fp32' (CUDA cores, 1e-5 parity, default) or 'bf16' (tcgen05 tensor cores, 2e-2);
+    can also be set process-wide with SGX_POOL_PRECISION.
+    """
+
+    def __init__(self, embedding_dim=64, h_dim=64, mlp_dim=1024, bottleneck_dim=1024, activation='relu',
+                 batch_norm=True, dropout=0.0, precision=None):
+        super().__init__()
+        self.mlp_dim = 1024                      # kept (and ignored) like the reference, models.py:467
+        self.h_dim = h_dim
+        self.bottleneck_dim = bottleneck_dim
+        self.embedding_dim = embedding_dim
+        self.activation = activation
+        self.batch_norm = bool(batch_norm)
+        self.dropout = float(dropout)
+        self.precision = precision or os.environ.get('SGX_POOL_PRECISION', 'fp32')
+        self.spatial_embedding = nn.Linear(2, embedding_dim)
+        self.mlp_pre_pool = make_mlp([embedding_dim + h_dim, 512, bottleneck_dim], activation=activation,
+                                     batch_norm=batch_norm, dropout=dropout)
+
+    def _fused_params(self):
+        if self.batch_norm or self.activation != 'relu' or (self.dropout > 0 and self.training):
+            raise NotImplementedError(
+                'PoolHiddenNet fused kernel supports activation=relu, batch_norm=0, dropout=0 (every shipped '
+                'checkpoint); got activation=%s batch_norm=%s dropout=%s' % (self.activation, self.batch_norm, self.dropout))
+        linears = [m for m in self.mlp_pre_pool if isinstance(m, nn.Linear)]
+        return linears[0], linears[1]
+
+    def forward(self, h_states, seq_start_end, end_pos):
+        l1, l2 = self._fused_params()
+        sched = get_schedule(seq_start_end, end_pos.device)
+        h = h_states.reshape(-1, self.h_dim)
+        if h.shape[0] != sched.batch:
+            raise ValueError('h_states has %d rows but seq_start_end covers %d pedestrians' % (h.shape[0], sched.batch))
+        out, _ = ops.pool_fwd(h, end_pos, sched.ped_start, sched.ped_end, sched.pair_off, sched.tile_first,
+                              sched.n_pairs, self.spatial_embedding.weight, self.spatial_embedding.bias,
+                              l1.weight, l1.bias, l2.weight, l2.bias, _precision_code(self.precision))
+        return out
+
+
+def _groups_for(sched, end_group):
+    return ops.group_ids(end_group.reshape(-1).float(), sched.ped_start, sched.ped_end, sched.scene_start)
+
+
+class GraphAttentionLayer(nn.Module):
+    """Dense-adjacency GAT layer (sgan/models.py:184-220).  Parameters ``W`` [in,out], ``a`` [2*out,1]."""
+
+    def __init__(self, in_features, out_features, dropout, alpha, concat=True):
+        super().__init__()
+        self.dropout = dropout
+        self.in_features = in_features
+        self.out_features = out_features
+        self.alpha = alpha
+        self.concat = concat
+        self.W = nn.Parameter(torch.empty(in_features, out_features))
+        nn.init.xavier_uniform_(self.W.data, gain=1.414)
+        self.a = nn.Parameter(torch.empty(2 * out_features, 1))
+        nn.init.xavier_uniform_(self.a.data, gain=1.414)
+
+    def forward(self, h, adj):
+        if self.dropout > 0 and self.training:
+            raise NotImplementedError('attention dropout > 0 is not supported by the sgx kernels')
+        from . import dense
+        return dense.gat_layer(h, adj, self.W, self.a, float(self.alpha), bool(self.concat))
+
+
+class GAT(nn.Module):
+    """n_heads concat layers + out_att, ELU, log_softmax over features (sgan/models.py:222-237)."""
+
+    def __init__(self, nfeat, nhid, nclass, dropout, alpha, nheads):
+        super().__init__()
+        self.dropout = dropout
+        self.nheads = nheads
+        self.alpha = alpha
+        for k in range(nheads):
+            self.add_module('attention_%d' % k, GraphAttentionLayer(nfeat, nhid, dropout=dropout, alpha=alpha, concat=True))
+        self.out_att = GraphAttentionLayer(nhid * nheads, nclass, dropout=dropout, alpha=alpha, concat=False)
+
+    @property
+    def attentions(self):
+        return [getattr(self, 'attention_%d' % k) for k in range(self.nheads)]
+
+    def forward(self, x, adj):
+        if self.dropout > 0 and self.training:
+            raise NotImplementedError('GAT dropout > 0 is not supported by the sgx kernels')
+        x = torch.cat([att(x, adj) for att in self.attentions], dim=1)
+        x = nn.functional.elu(self.out_att(x, adj))
+        return nn.functional.log_softmax(x, dim=1)
+
+    def stacked(self):
+        """-> (W [heads,in,hid], a [heads,2*hid], Wout [heads*hid,out], aout [2*out]) for the fused encoder op."""
+        atts = self.attentions
+        return (torch.stack([l.W for l in atts], 0), torch.stack([l.a.reshape(-1) for l in atts], 0),
+                self.out_att.W, self.out_att.a.reshape(-1))
+
+
+class GATEncoder(nn.Module):
+    """Group-aware graph attention context (sgan/models.py:239-294), one fused op over the ragged batch."""
+
+    def __init__(self, n_units, n_heads, dropout, alpha):
+        super().__init__()
+        self.n_heads = n_heads
+        self.alpha = alpha
+        self.dropout = dropout
+        self.gat_intra = GAT(40, 72, 16, dropout, alpha, n_heads)    # dims hard-coded upstream, models.py:242-244
+        self.gat_inter = GAT(16, 72, 16, dropout, alpha, n_heads)
+        self.out_embedding = nn.Linear(16 * 2, 24)
+
+    def forward(self, h_states, seq_start_end, end_pos, end_group):
+        if self.dropout > 0 and self.training:
+            raise NotImplementedError('GATEncoder dropout > 0 is not supported by the sgx kernels')
+        sched = get_schedule(seq_start_end, h_states.device)
+        if h_states.shape[0] != sched.batch:
+            raise ValueError('h_states has %d rows but seq_start_end covers %d pedestrians' % (h_states.shape[0], sched.batch))
+        leader, gsize, _gid, _ng = _groups_for(sched, end_group)
+        Wi, ai, Wio, aio = self.gat_intra.stacked()
+        We, ae, Weo, aeo = self.gat_inter.stacked()
+        return ops.gat_encoder_fwd(h_states, leader, gsize, sched.ped_start, sched.ped_end, sched.n_scenes, Wi, ai, Wio,
+                                   aio, We, ae, Weo, aeo, self.out_embedding.weight, self.out_embedding.bias,
+                                   float(self.alpha))
+
+
+class GCN(nn.Module):
+    """H <- ReLU((A H) W_l) for gcn_layers layers; parameters ``W.0 .. W.{L-1}`` (sgan/models.py:552-580)."""
+
+    def __init__(self, input_dim=48, hidden_dim=72, out_dim=8, gcn_layers=2):
+        super().__init__()
+        self.X_dim = input_dim
+        self.hidden_dim = hidden_dim
+        self.out_dim = out_dim
+        self.gcn_layers = gcn_layers
+        self.W = nn.ParameterList()
+        for l in range(gcn_layers):
+            d_in = input_dim if l == 0 else hidden_dim
+            d_out = out_dim if (l == gcn_layers - 1 and l > 0) else hidden_dim
+            self.W.append(nn.Parameter(torch.randn(d_in, d_out)))
+
+    def forward(self, A, X):
+        from . import dense
+        h = X
+        for l in range(self.gcn_layers):
+            h = dense.gcn_layer(A, h, self.W[l])
+        return h
+
+
+class GCNModule(nn.Module):
+    """Group-aware graph convolution context (sgan/models.py:583-712), fused segmented-mean kernels."""
+
+    def __init__(self, input_dim=40, hidden_dim=72, out_dim=16, gcn_layers=2, final_dim=24):
+        super().__init__()
+        self.gcn_layers = gcn_layers
+        self.gcn_intra = GCN(input_dim=input_dim, hidden_dim=hidden_dim, out_dim=out_dim, gcn_layers=gcn_layers)
+        self.gcn_inter = GCN(input_dim=16, hidden_dim=hidden_dim, out_dim=out_dim, gcn_layers=gcn_layers)
+        self.out_embedding = nn.Linear(out_dim * 2, final_dim)
+
+    def forward(self, h_states, seq_start_end, end_pos, end_group):
+        if self.gcn_layers != 2:
+            raise NotImplementedError('GCNModule fused kernel is built for gcn_layers=2 (the reference wiring)')
+        sched = get_schedule(seq_start_end, h_states.device)
+        if h_states.shape[0] != sched.batch:
+            raise ValueError('h_states has %d rows but seq_start_end covers %d pedestrians' % (h_states.shape[0], sched.batch))
+        leader, gsize, _gid, ngrp = _groups_for(sched, end_group)
+        return ops.gcn_module_fwd(h_states, leader, gsize, sched.ped_start, sched.ped_end, sched.scene_start, ngrp,
+                                  self.gcn_intra.W[0], self.gcn_intra.W[1], self.gcn_inter.W[0], self.gcn_inter.W[1],
+                                  self.out_embedding.weight, self.out_embedding.bias)

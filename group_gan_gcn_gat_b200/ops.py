@@ -1,0 +1,309 @@
+"""torch.library custom ops over the C ABI (include/sgx.h), with hand-written backward kernels.
+
+Every op here is a thin marshalling layer: it allocates outputs/workspace with torch, passes raw
+device pointers + the current CUDA stream to libsgx_b200.so and returns.  Autograd is registered
+with ``register_autograd`` and calls the matching ``*_bwd`` entry point.  There is no eager/CPU
+fallback: tensors must be CUDA fp32 and the library must be present.
+"""
+from typing import List, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import PRECISION_BF16, PRECISION_FP32  # noqa: F401
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _f32(t, name):
+    if not t.is_cuda:
+        raise RuntimeError('%s must be a CUDA tensor: the sgx ops have no CPU fallback' % name)
+    if t.dtype != torch.float32:
+        raise TypeError('%s must be float32, got %s' % (name, t.dtype))
+    return t.contiguous()
+
+
+def _i32(t, name):
+    if not t.is_cuda or t.dtype != torch.int32:
+        raise TypeError('%s must be a CUDA int32 tensor' % name)
+    return t.contiguous()
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+# ---------------------------------------------------------------------------------------------
+# group structure
+# ---------------------------------------------------------------------------------------------
+@torch.library.custom_op('sgx::group_ids', mutates_args=())
+def group_ids(labels: Tensor, ped_start: Tensor, ped_end: Tensor, scene_start: Tensor) -> List[Tensor]:
+    """-> [leader, group_size, group_id, n_group] (int32).  sgan/models.py:263-278."""
+    labels = _f32(labels.reshape(-1), 'labels')
+    batch = labels.numel()
+    S = scene_start.numel() - 1
+    dev = labels.device
+    leader = torch.empty(batch, dtype=torch.int32, device=dev)
+    gsize = torch.empty_like(leader)
+    gid = torch.empty_like(leader)
+    ngrp = torch.empty(S, dtype=torch.int32, device=dev)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        _lib.check(L.sgx_group_ids(_ptr(labels), _ptr(ped_start), _ptr(ped_end), _ptr(scene_start), batch, S,
+                                   _ptr(leader), _ptr(gsize), _ptr(gid), _ptr(ngrp), _stream(labels)), 'sgx_group_ids')
+    return [leader, gsize, gid, ngrp]
+
+
+@group_ids.register_fake
+def _(labels, ped_start, ped_end, scene_start):
+    b = labels.numel()
+    mk = lambda n: torch.empty(n, dtype=torch.int32, device=labels.device)
+    return [mk(b), mk(b), mk(b), mk(scene_start.numel() - 1)]
+
+
+def group_dense(labels, groups, start, end):
+    """Dense M (bool), A (fp32), R (bool [G,N]), Rn (fp32 [G,N]) of one scene -- parity tests only."""
+    labels = _f32(labels.reshape(-1), 'labels')
+    leader, gsize, gid, _ = groups
+    n = end - start
+    dev = labels.device
+    M = torch.empty(n, n, dtype=torch.uint8, device=dev)
+    A = torch.empty(n, n, dtype=torch.float32, device=dev)
+    R = torch.empty(n, n, dtype=torch.uint8, device=dev)
+    Rn = torch.empty(n, n, dtype=torch.float32, device=dev)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        _lib.check(L.sgx_group_dense(_ptr(labels), _ptr(leader), _ptr(gsize), _ptr(gid), start, end, _ptr(M), _ptr(A),
+                                     _ptr(R), _ptr(Rn), _stream(labels)), 'sgx_group_dense')
+    g = int(gid[start:end].max().item()) + 1
+    return M.bool(), A, R[:g].bool(), Rn[:g]
+
+
+# ---------------------------------------------------------------------------------------------
+# PoolHiddenNet
+# ---------------------------------------------------------------------------------------------
+@torch.library.custom_op('sgx::pool_fwd', mutates_args=())
+def pool_fwd(h: Tensor, pos: Tensor, ped_start: Tensor, ped_end: Tensor, pair_off: Tensor, tile_first: Tensor,
+             n_pairs: int, We: Tensor, be: Tensor, W1: Tensor, b1: Tensor, W2: Tensor, b2: Tensor,
+             precision: int) -> Tuple[Tensor, Tensor]:
+    h, pos = _f32(h, 'h_states'), _f32(pos, 'end_pos')
+    We, be, W1, b1, W2, b2 = (_f32(t, n) for t, n in zip((We, be, W1, b1, W2, b2), ('We', 'be', 'W1', 'b1', 'W2', 'b2')))
+    batch, H = h.shape
+    E = We.shape[0]
+    B = W2.shape[0]
+    if W1.shape != (512, E + H) or W2.shape[1] != 512 or pos.shape != (batch, 2):
+        raise ValueError('pool_fwd: inconsistent shapes h%s pos%s W1%s W2%s' % (tuple(h.shape), tuple(pos.shape),
+                                                                               tuple(W1.shape), tuple(W2.shape)))
+    dev = h.device
+    out = torch.empty(batch, B, dtype=torch.float32, device=dev)
+    arg = torch.empty(batch, B, dtype=torch.int32, device=dev)
+    L = _lib.lib()
+    nbytes = L.sgx_pool_ws_bytes(batch, E, H, B, precision)
+    ws = _ws(nbytes, dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.sgx_pool_fwd(_ptr(h), _ptr(pos), _ptr(ped_start), _ptr(ped_end), _ptr(pair_off), _ptr(tile_first),
+                                  batch, n_pairs, _ptr(We), _ptr(be), _ptr(W1), _ptr(b1), _ptr(W2), _ptr(b2), E, H, B,
+                                  precision, _ptr(out), _ptr(arg), _ptr(ws), ws.numel(), _stream(h)), 'sgx_pool_fwd')
+    return out, arg
+
+
+@pool_fwd.register_fake
+def _(h, pos, ped_start, ped_end, pair_off, tile_first, n_pairs, We, be, W1, b1, W2, b2, precision):
+    return (h.new_empty(h.shape[0], W2.shape[0]), torch.empty(h.shape[0], W2.shape[0], dtype=torch.int32, device=h.device))
+
+
+@torch.library.custom_op('sgx::pool_bwd', mutates_args=())
+def pool_bwd(h: Tensor, pos: Tensor, out: Tensor, argmax: Tensor, grad_out: Tensor, We: Tensor, be: Tensor,
+             W1: Tensor, b1: Tensor, W2: Tensor, b2: Tensor) -> List[Tensor]:
+    h, pos, out, grad_out = _f32(h, 'h'), _f32(pos, 'pos'), _f32(out, 'out'), _f32(grad_out, 'grad_out')
+    We, be, W1, b1, W2, b2 = (t.contiguous() for t in (We, be, W1, b1, W2, b2))
+    batch, H = h.shape
+    E, B = We.shape[0], W2.shape[0]
+    dev = h.device
+    gh, gpos = torch.empty_like(h), torch.empty_like(pos)
+    gWe, gbe, gW1, gb1, gW2, gb2 = (torch.empty_like(t) for t in (We, be, W1, b1, W2, b2))
+    L = _lib.lib()
+    ws = _ws(L.sgx_pool_bwd_ws_bytes(batch, E, H, B), dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.sgx_pool_bwd(_ptr(h), _ptr(pos), _ptr(out), _ptr(argmax.contiguous()), _ptr(grad_out), batch,
+                                  _ptr(We), _ptr(be), _ptr(W1), _ptr(b1), _ptr(W2), _ptr(b2), E, H, B, _ptr(gh),
+                                  _ptr(gpos), _ptr(gWe), _ptr(gbe), _ptr(gW1), _ptr(gb1), _ptr(gW2), _ptr(gb2),
+                                  _ptr(ws), ws.numel(), _stream(h)), 'sgx_pool_bwd')
+    return [gh, gpos, gWe, gbe, gW1, gb1, gW2, gb2]
+
+
+@pool_bwd.register_fake
+def _(h, pos, out, argmax, grad_out, We, be, W1, b1, W2, b2):
+    return [torch.empty_like(t) for t in (h, pos, We, be, W1, b1, W2, b2)]
+
+
+def _pool_setup(ctx, inputs, output):
+    h, pos, _ps, _pe, _po, _tf, _np, We, be, W1, b1, W2, b2, _prec = inputs
+    out, arg = output
+    ctx.save_for_backward(h, pos, out, arg, We, be, W1, b1, W2, b2)
+
+
+def _pool_backward(ctx, grad_out, _grad_arg):
+    h, pos, out, arg, We, be, W1, b1, W2, b2 = ctx.saved_tensors
+    gh, gpos, gWe, gbe, gW1, gb1, gW2, gb2 = pool_bwd(h, pos, out, arg, grad_out.contiguous(), We, be, W1, b1, W2, b2)
+    return gh, gpos, None, None, None, None, None, gWe, gbe, gW1, gb1, gW2, gb2, None
+
+
+pool_fwd.register_autograd(_pool_backward, setup_context=_pool_setup)
+
+
+# ---------------------------------------------------------------------------------------------
+# GCNModule
+# ---------------------------------------------------------------------------------------------
+@torch.library.custom_op('sgx::gcn_module_fwd', mutates_args=())
+def gcn_module_fwd(x: Tensor, leader: Tensor, gsize: Tensor, ped_start: Tensor, ped_end: Tensor, scene_start: Tensor,
+                   n_group: Tensor, W0: Tensor, W1: Tensor, V0: Tensor, V1: Tensor, Wo: Tensor, bo: Tensor) -> Tensor:
+    x = _f32(x, 'h_states')
+    W0, W1, V0, V1, Wo, bo = (_f32(t, 'gcn weight') for t in (W0, W1, V0, V1, Wo, bo))
+    batch, IN = x.shape
+    HID, OUT, FIN = W0.shape[1], W1.shape[1], Wo.shape[0]
+    S = scene_start.numel() - 1
+    out = torch.empty(batch, FIN, dtype=torch.float32, device=x.device)
+    L = _lib.lib()
+    ws = _ws(L.sgx_gcn_module_ws_bytes(batch, S, IN, HID, OUT, FIN), x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(L.sgx_gcn_module_fwd(_ptr(x), _ptr(leader), _ptr(gsize), _ptr(ped_start), _ptr(ped_end),
+                                        _ptr(scene_start), _ptr(n_group), batch, S, _ptr(W0), _ptr(W1), _ptr(V0),
+                                        _ptr(V1), _ptr(Wo), _ptr(bo), IN, HID, OUT, FIN, _ptr(out), _ptr(ws), ws.numel(),
+                                        _stream(x)), 'sgx_gcn_module_fwd')
+    return out
+
+
+@gcn_module_fwd.register_fake
+def _(x, leader, gsize, ped_start, ped_end, scene_start, n_group, W0, W1, V0, V1, Wo, bo):
+    return x.new_empty(x.shape[0], Wo.shape[0])
+
+
+@torch.library.custom_op('sgx::gcn_module_bwd', mutates_args=())
+def gcn_module_bwd(x: Tensor, grad_out: Tensor, leader: Tensor, gsize: Tensor, ped_start: Tensor, ped_end: Tensor,
+                   scene_start: Tensor, n_group: Tensor, W0: Tensor, W1: Tensor, V0: Tensor, V1: Tensor, Wo: Tensor,
+                   bo: Tensor) -> List[Tensor]:
+    x, grad_out = _f32(x, 'x'), _f32(grad_out, 'grad_out')
+    W0, W1, V0, V1, Wo, bo = (t.contiguous() for t in (W0, W1, V0, V1, Wo, bo))
+    batch, IN = x.shape
+    HID, OUT, FIN = W0.shape[1], W1.shape[1], Wo.shape[0]
+    S = scene_start.numel() - 1
+    grads = [torch.empty_like(t) for t in (x, W0, W1, V0, V1, Wo, bo)]
+    L = _lib.lib()
+    ws = _ws(L.sgx_gcn_module_ws_bytes(batch, S, IN, HID, OUT, FIN), x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(L.sgx_gcn_module_bwd(_ptr(x), _ptr(grad_out), _ptr(leader), _ptr(gsize), _ptr(ped_start),
+                                        _ptr(ped_end), _ptr(scene_start), _ptr(n_group), batch, S, _ptr(W0), _ptr(W1),
+                                        _ptr(V0), _ptr(V1), _ptr(Wo), _ptr(bo), IN, HID, OUT, FIN,
+                                        *[_ptr(g) for g in grads], _ptr(ws), ws.numel(), _stream(x)),
+                   'sgx_gcn_module_bwd')
+    return grads
+
+
+@gcn_module_bwd.register_fake
+def _(x, grad_out, leader, gsize, ped_start, ped_end, scene_start, n_group, W0, W1, V0, V1, Wo, bo):
+    return [torch.empty_like(t) for t in (x, W0, W1, V0, V1, Wo, bo)]
+
+
+def _gcn_setup(ctx, inputs, output):
+    ctx.save_for_backward(*inputs)
+
+
+def _gcn_backward(ctx, grad_out):
+    x, leader, gsize, ps, pe, ss, ng, W0, W1, V0, V1, Wo, bo = ctx.saved_tensors
+    g = gcn_module_bwd(x, grad_out.contiguous(), leader, gsize, ps, pe, ss, ng, W0, W1, V0, V1, Wo, bo)
+    return g[0], None, None, None, None, None, None, g[1], g[2], g[3], g[4], g[5], g[6]
+
+
+gcn_module_fwd.register_autograd(_gcn_backward, setup_context=_gcn_setup)
+
+
+# ---------------------------------------------------------------------------------------------
+# GATEncoder
+# ---------------------------------------------------------------------------------------------
+@torch.library.custom_op('sgx::gat_encoder_fwd', mutates_args=())
+def gat_encoder_fwd(x: Tensor, leader: Tensor, gsize: Tensor, ped_start: Tensor, ped_end: Tensor, n_scenes: int,
+                    Wi: Tensor, ai: Tensor, Wio: Tensor, aio: Tensor, We: Tensor, ae: Tensor, Weo: Tensor,
+                    aeo: Tensor, Wo: Tensor, bo: Tensor, alpha: float) -> Tensor:
+    x = _f32(x, 'h_states')
+    ps = [_f32(t, 'gat weight') for t in (Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo)]
+    batch, IN = x.shape
+    nh, _, HID = Wi.shape
+    OUT, FIN = Wio.shape[1], Wo.shape[0]
+    out = torch.empty(batch, FIN, dtype=torch.float32, device=x.device)
+    L = _lib.lib()
+    ws = _ws(L.sgx_gat_encoder_ws_bytes(batch, n_scenes, nh, IN, HID, OUT, FIN), x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(L.sgx_gat_encoder_fwd(_ptr(x), _ptr(leader), _ptr(gsize), _ptr(ped_start), _ptr(ped_end), batch,
+                                         n_scenes, *[_ptr(p) for p in ps], alpha, nh, IN, HID, OUT, FIN, _ptr(out),
+                                         _ptr(ws), ws.numel(), _stream(x)), 'sgx_gat_encoder_fwd')
+    return out
+
+
+@gat_encoder_fwd.register_fake
+def _(x, leader, gsize, ped_start, ped_end, n_scenes, Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo, alpha):
+    return x.new_empty(x.shape[0], Wo.shape[0])
+
+
+@torch.library.custom_op('sgx::gat_encoder_bwd', mutates_args=())
+def gat_encoder_bwd(x: Tensor, grad_out: Tensor, leader: Tensor, gsize: Tensor, ped_start: Tensor, ped_end: Tensor,
+                    n_scenes: int, Wi: Tensor, ai: Tensor, Wio: Tensor, aio: Tensor, We: Tensor, ae: Tensor,
+                    Weo: Tensor, aeo: Tensor, Wo: Tensor, bo: Tensor, alpha: float) -> List[Tensor]:
+    x, grad_out = _f32(x, 'x'), _f32(grad_out, 'grad_out')
+    ps = [t.contiguous() for t in (Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo)]
+    batch, IN = x.shape
+    nh, _, HID = Wi.shape
+    OUT, FIN = Wio.shape[1], Wo.shape[0]
+    grads = [torch.empty_like(t) for t in [x] + ps]
+    L = _lib.lib()
+    ws = _ws(L.sgx_gat_encoder_ws_bytes(batch, n_scenes, nh, IN, HID, OUT, FIN), x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(L.sgx_gat_encoder_bwd(_ptr(x), _ptr(grad_out), _ptr(leader), _ptr(gsize), _ptr(ped_start),
+                                         _ptr(ped_end), batch, n_scenes, *[_ptr(p) for p in ps], alpha, nh, IN, HID,
+                                         OUT, FIN, *[_ptr(g) for g in grads], _ptr(ws), ws.numel(), _stream(x)),
+                   'sgx_gat_encoder_bwd')
+    return grads
+
+
+@gat_encoder_bwd.register_fake
+def _(x, grad_out, leader, gsize, ped_start, ped_end, n_scenes, Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo, alpha):
+    return [torch.empty_like(t) for t in (x, Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo)]
+
+
+def _gat_setup(ctx, inputs, output):
+    x, leader, gsize, ps, pe, S, *params, alpha = inputs
+    ctx.save_for_backward(x, leader, gsize, ps, pe, *params)
+    ctx.n_scenes, ctx.alpha = S, alpha
+
+
+def _gat_backward(ctx, grad_out):
+    x, leader, gsize, ps, pe, *params = ctx.saved_tensors
+    g = gat_encoder_bwd(x, grad_out.contiguous(), leader, gsize, ps, pe, ctx.n_scenes, *params, ctx.alpha)
+    return (g[0], None, None, None, None, None, *g[1:], None)
+
+
+gat_encoder_fwd.register_autograd(_gat_backward, setup_context=_gat_setup)
+
+
+# ---------------------------------------------------------------------------------------------
+# generic GEMM (dense standalone layers; exported mostly for tests)
+# ---------------------------------------------------------------------------------------------
+def gemm(a, b, relu=False):
+    """C = a @ b through sgx_gemm (fp32, arbitrary strides)."""
+    assert a.is_cuda and b.is_cuda and a.dtype == torch.float32 and b.dtype == torch.float32
+    M, K = a.shape
+    K2, N = b.shape
+    assert K == K2
+    c = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    L = _lib.lib()
+    with torch.cuda.device(a.device):
+        _lib.check(L.sgx_gemm(_ptr(a), a.stride(0), a.stride(1), _ptr(b), b.stride(0), b.stride(1), _ptr(c), N, M, N, K,
+                              0, int(relu), _stream(a)), 'sgx_gemm')
+    return c

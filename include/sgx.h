@@ -1,0 +1,176 @@
+/* sgx.h -- C ABI of libsgx_b200.so: the sgan social-interaction hot path on B200 (sm_100a).
+ *
+ * The reference (peaceminusones/Group-GAN-GCN-GAT) has no FFI: its boundary for this path is the
+ * nn.Module API of sgan/models.py.  Each entry point below replaces the body of one reference
+ * method; the Python modules in group_gan_gcn_gat_b200/ keep the reference signatures and
+ * state_dict names and call these through ctypes + torch.library.
+ *
+ * Conventions
+ *   - plain C symbols, POD arguments; every pointer is a raw CUDA device pointer unless the
+ *     parameter name starts with `h_` (host memory).  No torch types.
+ *   - the CALLER owns and allocates every buffer (outputs and workspace; sizes via *_ws_bytes),
+ *     the library never allocates device memory and never synchronises: all work is queued on
+ *     `stream` (a cudaStream_t passed as void*).
+ *   - fp32 tensors are dense row-major; "batch" = total pedestrians of the minibatch,
+ *     scenes are the ragged segments seq_start_end[s] = (start, end) of sgan/models.py:507-510.
+ *   - return value: 0 = ok, <0 = error (see SGX_ERR_*); sgx_last_error() gives the text.
+ *     No C++ exception crosses the ABI.
+ *   - re-entrant per stream; no global state except the last-error string (thread local).
+ */
+#ifndef SGX_H_
+#define SGX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGX_OK 0
+#define SGX_ERR_INVALID (-1)     /* bad shape / size / null pointer / non-contiguous scenes */
+#define SGX_ERR_UNSUPPORTED (-2) /* valid request this build has no kernel for               */
+#define SGX_ERR_CUDA (-3)        /* a CUDA runtime call failed                               */
+
+#define SGX_PRECISION_FP32 0     /* CUDA-core path, 1e-5 relative parity                     */
+#define SGX_PRECISION_BF16 1     /* tcgen05/TMEM path, 2e-2 parity                           */
+
+#define SGX_POOL_HIDDEN 512      /* hard-coded mid width of mlp_pre_pool, sgan/models.py:473 */
+
+const char* sgx_last_error(void);
+int sgx_version(void);
+/* 1 when the loaded binary carries sm_100a code for the tcgen05 pooling kernel */
+int sgx_has_tcgen05(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Scene schedule (host).  Replaces the per-scene `.item()` loop headers of
+ * sgan/models.py:507-510, 256-262, 639-644 and the seq_start_end layout of
+ * sgan/data/trajectories_GCN.py:19-22,36.  Built once per minibatch, reused by every call.
+ *
+ * sgx_schedule_stats : validates h_seq_start_end (int64 [S,2], scenes must tile [0,batch)
+ *                      contiguously, every scene >= 1 ped) and returns
+ *                      h_stats[0]=batch, [1]=max scene size, [2]=sum N^2 (ordered pairs),
+ *                      [3]=number of 128-pair tiles, [4]=S.
+ * sgx_schedule_fill  : fills the host arrays (caller uploads them):
+ *      h_scene_start int32 [S+1]
+ *      h_ped_start   int32 [batch]   start of the ped's scene
+ *      h_ped_end     int32 [batch]   end of the ped's scene
+ *      h_pair_off    int64 [batch+1] prefix sum of scene sizes over peds: ordered pair (i,j)
+ *                                    has flat index pair_off[i] + (j - ped_start[i])
+ *      h_tile_first  int32 [n_tiles] ped owning the first pair of every 128-pair tile
+ * sgx_schedule_partition : LPT split of scenes over `world` ranks by cost N^2;
+ *      h_rank_of_scene int32 [S].  Deterministic: ties broken by scene index.
+ */
+int sgx_schedule_stats(const int64_t* h_seq_start_end, int64_t n_scenes, int64_t* h_stats);
+int sgx_schedule_fill(const int64_t* h_seq_start_end, int64_t n_scenes, int32_t* h_scene_start,
+                      int32_t* h_ped_start, int32_t* h_ped_end, int64_t* h_pair_off, int32_t* h_tile_first);
+int sgx_schedule_partition(const int64_t* h_seq_start_end, int64_t n_scenes, int32_t world,
+                           int32_t* h_rank_of_scene, int64_t* h_rank_cost);
+
+/* ---------------------------------------------------------------------------------------------
+ * Group structure.  Replaces sgan/models.py:263-278 (GATEncoder) == 654-680 (GCNModule):
+ * M_intra = (g_i == g_j & g_i != 0) | eye, its row normalisation, unique-rows + reverse.
+ *   labels      fp32 [batch]  group label of the last observed frame (float compare, 0 = none)
+ *   leader      int32 [batch] global index of the smallest member of the ped's group
+ *   group_size  int32 [batch]
+ *   group_id    int32 [batch] scene-local id, groups numbered by ascending smallest member
+ *   n_group     int32 [S]
+ * sgx_group_dense writes, for ONE scene, the dense matrices the reference materialises
+ * (for bit-exact parity tests): M uint8 [N,N], A fp32 [N,N] (= M * fl(1/rowsum)),
+ * R uint8 [N,N] and Rn fp32 [N,N] whose first n_group rows are R_intra / its row normalisation
+ * (row g = members of group g) and whose other rows are zero.  Any pointer may be null.
+ */
+int sgx_group_ids(const float* labels, const int32_t* ped_start, const int32_t* ped_end, const int32_t* scene_start,
+                  int64_t batch, int64_t n_scenes, int32_t* leader, int32_t* group_size, int32_t* group_id,
+                  int32_t* n_group, void* stream);
+int sgx_group_dense(const float* labels, const int32_t* leader, const int32_t* group_size, const int32_t* group_id,
+                    int64_t start, int64_t end, uint8_t* M, float* A, uint8_t* R, float* Rn, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * PoolHiddenNet.forward (sgan/models.py:497-549):
+ *   out[i,b] = max_j ReLU(b2[b] + W2[b,:] . ReLU(b1 + W1 [We (P_j - P_i) + be ; h_j]))   j in scene(i)
+ *   h [batch,H]  pos [batch,2]  We [E,2] be [E]  W1 [512,E+H] b1 [512]  W2 [B,512] b2 [B]
+ *   out fp32 [batch,B]   argmax int32 [batch,B] (global index j attaining the max; ties -> larger j)
+ * precision: SGX_PRECISION_FP32 (any E<=64, H<=128, B<=64 multiple of 8) or
+ *            SGX_PRECISION_BF16 (tcgen05; (E,H,B) in {(16,32,8),(16,48,48)} ... see DESIGN.md).
+ * workspace: sgx_pool_ws_bytes(batch, H, B, precision).
+ * Backward (argmax-sparse, fp32): grads of sum(out*grad_out) w.r.t. every input; gradient
+ * buffers are OVERWRITTEN (not accumulated).  Reference: autograd through models.py:516-541.
+ */
+int64_t sgx_pool_ws_bytes(int64_t batch, int32_t E, int32_t H, int32_t B, int32_t precision);
+int sgx_pool_fwd(const float* h, const float* pos, const int32_t* ped_start, const int32_t* ped_end,
+                 const int64_t* pair_off, const int32_t* tile_first, int64_t batch, int64_t n_pairs,
+                 const float* We, const float* be, const float* W1, const float* b1, const float* W2,
+                 const float* b2, int32_t E, int32_t H, int32_t B, int32_t precision, float* out,
+                 int32_t* argmax, void* workspace, int64_t ws_bytes, void* stream);
+int64_t sgx_pool_bwd_ws_bytes(int64_t batch, int32_t E, int32_t H, int32_t B);
+int sgx_pool_bwd(const float* h, const float* pos, const float* out, const int32_t* argmax, const float* grad_out,
+                 int64_t batch, const float* We, const float* be, const float* W1, const float* b1,
+                 const float* W2, const float* b2, int32_t E, int32_t H, int32_t B, float* grad_h,
+                 float* grad_pos, float* grad_We, float* grad_be, float* grad_W1, float* grad_b1,
+                 float* grad_W2, float* grad_b2, void* workspace, int64_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * GCNModule.forward (sgan/models.py:628-712) with gcn_layers = 2:
+ *   x [batch,IN]  W0 [IN,HID] W1 [HID,OUT] (intra)  V0 [OUT,HID] V1 [HID,OUT] (inter)
+ *   Wo [FIN,2*OUT] bo [FIN]  ->  out [batch,FIN]
+ * Needs the group structure of sgx_group_ids.  Gradient buffers are overwritten.
+ */
+int64_t sgx_gcn_module_ws_bytes(int64_t batch, int64_t n_scenes, int32_t IN, int32_t HID, int32_t OUT, int32_t FIN);
+int sgx_gcn_module_fwd(const float* x, const int32_t* leader, const int32_t* group_size, const int32_t* ped_start,
+                       const int32_t* ped_end, const int32_t* scene_start, const int32_t* n_group, int64_t batch,
+                       int64_t n_scenes, const float* W0, const float* W1, const float* V0, const float* V1,
+                       const float* Wo, const float* bo, int32_t IN, int32_t HID, int32_t OUT, int32_t FIN,
+                       float* out, void* workspace, int64_t ws_bytes, void* stream);
+int sgx_gcn_module_bwd(const float* x, const float* grad_out, const int32_t* leader, const int32_t* group_size,
+                       const int32_t* ped_start, const int32_t* ped_end, const int32_t* scene_start,
+                       const int32_t* n_group, int64_t batch, int64_t n_scenes, const float* W0, const float* W1,
+                       const float* V0, const float* V1, const float* Wo, const float* bo, int32_t IN, int32_t HID,
+                       int32_t OUT, int32_t FIN, float* grad_x, float* grad_W0, float* grad_W1, float* grad_V0,
+                       float* grad_V1, float* grad_Wo, float* grad_bo, void* workspace, int64_t ws_bytes,
+                       void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * GATEncoder.forward (sgan/models.py:254-294), dropout = 0:
+ *   x [batch,IN]; every GAT is  n_heads x GraphAttentionLayer(F_in -> HID, concat) then
+ *   out_att (n_heads*HID -> OUT), ELU, log_softmax over the OUT features (models.py:231-237).
+ *   intra: Wi [n_heads,IN,HID]  ai [n_heads,2*HID]  Wio [n_heads*HID,OUT]  aio [2*OUT]
+ *   inter: We [n_heads,OUT,HID] ae [n_heads,2*HID]  Weo [n_heads*HID,OUT]  aeo [2*OUT]
+ *   Wo [FIN,2*OUT] bo [FIN] -> out [batch,FIN].  alpha = LeakyReLU slope.
+ * The reference hard-codes IN=40, HID=72, OUT=16, FIN=24 (models.py:242-244).
+ */
+int64_t sgx_gat_encoder_ws_bytes(int64_t batch, int64_t n_scenes, int32_t n_heads, int32_t IN, int32_t HID,
+                                 int32_t OUT, int32_t FIN);
+int sgx_gat_encoder_fwd(const float* x, const int32_t* leader, const int32_t* group_size, const int32_t* ped_start,
+                        const int32_t* ped_end, int64_t batch, int64_t n_scenes, const float* Wi, const float* ai,
+                        const float* Wio, const float* aio, const float* We, const float* ae, const float* Weo,
+                        const float* aeo, const float* Wo, const float* bo, float alpha, int32_t n_heads, int32_t IN,
+                        int32_t HID, int32_t OUT, int32_t FIN, float* out, void* workspace, int64_t ws_bytes,
+                        void* stream);
+int sgx_gat_encoder_bwd(const float* x, const float* grad_out, const int32_t* leader, const int32_t* group_size,
+                        const int32_t* ped_start, const int32_t* ped_end, int64_t batch, int64_t n_scenes,
+                        const float* Wi, const float* ai, const float* Wio, const float* aio, const float* We,
+                        const float* ae, const float* Weo, const float* aeo, const float* Wo, const float* bo,
+                        float alpha, int32_t n_heads, int32_t IN, int32_t HID, int32_t OUT, int32_t FIN,
+                        float* grad_x, float* grad_Wi, float* grad_ai, float* grad_Wio, float* grad_aio,
+                        float* grad_We, float* grad_ae, float* grad_Weo, float* grad_aeo, float* grad_Wo,
+                        float* grad_bo, void* workspace, int64_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Standalone dense-adjacency layers (API parity for GraphAttentionLayer.forward(h, adj),
+ * sgan/models.py:198-210, and GCN.forward(A, X), models.py:573-580): the masked-softmax rows below
+ * plus sgx_gemm for every product (Wh = h W, att Wh, (A H) W ...).  n x n dense `adj`.
+ */
+/* att[i,:] = softmax_j(adj[i,j] > 0 ? LeakyReLU(st[i,0] + st[j,1]) : -9e15)   st [n,2], adj/att [n,n] */
+int sgx_dense_att_fwd(const float* st, const float* adj, int64_t n, float alpha, float* att, void* stream);
+/* datt_inout: in = dL/d(att), out = dL/d(pre-activation) (0 where adj <= 0);  ds[i] = sum_j of the output row */
+int sgx_dense_att_bwd(const float* st, const float* adj, const float* att, int64_t n, float alpha,
+                      float* datt_inout, float* ds, void* stream);
+/* C[M,N] (+)= op(A) op(B), fp32, generic strides (element strides); used by the dense layers and
+ * by the parameter-gradient reductions.  accumulate != 0 adds into C. */
+int sgx_gemm(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn, float* C,
+             int64_t ldc, int64_t M, int64_t N, int64_t K, int32_t accumulate, int32_t relu, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGX_H_ */

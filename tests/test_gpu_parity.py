@@ -1,0 +1,328 @@
+"""GPU parity: the CUDA path (through the C ABI / torch.library ops) against the golden vectors frozen from
+the reference and against the CPU oracle on seeded inputs.  Tolerances (BASELINE.json north_star):
+group structure bit-exact; pooled features 1e-5 relative (fp32); ADE/FDE 1e-4.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, sse_from_sizes, state_dict_of
+from oracle import sgan_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DEV = 'cuda:0'
+torch.backends.cudnn.allow_tf32 = False   # cuDNN LSTM (Encoder/Decoder) must not drop to TF32 for 1e-5 parity
+
+
+def rel_err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return ((a - b).abs().max() / max(1e-6, b.abs().max())).item()
+
+
+def assert_close(a, b, tol, what='', floor=1e-6):
+    """max |a-b| <= tol * max(|b|_max, floor).  `floor` guards gradients whose true value is ~0 (pure rounding
+    noise in the reference, e.g. d/d(gat_inter.out_att.a) ~ 1e-7 next to O(10) sibling gradients)."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    e = ((a - b).abs().max() / max(floor, b.abs().max())).item()
+    assert e <= tol, '%s: relative error %.3e > %.1e' % (what, e, tol)
+
+
+def grad_floor(g):
+    """1e-2 of the largest parameter gradient of the fixture (cancellation noise scales with the terms, not the sum)."""
+    return 1e-2 * max(float(v.abs().max()) for k, v in g.items() if k.startswith('grad.'))
+
+
+@pytest.fixture(scope='module')
+def sgx():
+    import group_gan_gcn_gat_b200.modules as M
+    import group_gan_gcn_gat_b200.models as MD
+    import group_gan_gcn_gat_b200.ops as ops
+    from group_gan_gcn_gat_b200.schedule import get_schedule
+    return dict(M=M, MD=MD, ops=ops, get_schedule=get_schedule)
+
+
+# ------------------------------------------------------------------ group structure (bit exact)
+def test_group_structure_bit_exact_vs_golden(sgx):
+    g = load_golden('groups')
+    for case in sorted({k.split('.')[0] for k in g}):
+        lab = g[case + '.labels'].reshape(-1)
+        n = lab.numel()
+        sched = sgx['get_schedule'](torch.tensor([[0, n]]), DEV)
+        groups = sgx['ops'].group_ids(lab.to(DEV), sched.ped_start, sched.ped_end, sched.scene_start)
+        M, A, R, Rn = sgx['ops'].group_dense(lab.to(DEV), groups, 0, n)
+        assert torch.equal(M.cpu(), g[case + '.M']), case
+        assert torch.equal(A.cpu(), g[case + '.A']), case          # fl(1/count) bit for bit
+        assert torch.equal(R.cpu(), g[case + '.R']), case
+        assert torch.equal(Rn.cpu(), g[case + '.Rn']), case
+        assert int(groups[3][0]) == g[case + '.R'].shape[0]
+
+
+def test_group_ids_vs_integer_oracle(sgx):
+    rng = np.random.RandomState(7)
+    sizes = list(rng.randint(1, 40, size=300)) + [257, 1]
+    labs = np.concatenate([np.where(rng.rand(n) < 0.15, 0, rng.randint(1, max(2, n // 3 + 1), size=n)) for n in sizes])
+    labs = labs.astype(np.float32)
+    labs[5] = -0.0
+    labs[100] = 2.5
+    sse = sse_from_sizes(sizes)
+    ref = O.group_ids_numpy(labs, sse)
+    sched = sgx['get_schedule'](sse, DEV)
+    leader, gsize, gid, ngrp = sgx['ops'].group_ids(torch.from_numpy(labs).to(DEV), sched.ped_start, sched.ped_end,
+                                                    sched.scene_start)
+    assert np.array_equal(leader.cpu().numpy(), ref['leader'])
+    assert np.array_equal(gsize.cpu().numpy(), ref['group_size'])
+    assert np.array_equal(gid.cpu().numpy(), ref['group_id'])
+    assert np.array_equal(ngrp.cpu().numpy(), ref['n_group'])
+
+
+# ------------------------------------------------------------------ generic gemm
+def test_gemm_matches_torch(sgx):
+    torch.manual_seed(0)
+    for (m, n, k) in [(1, 1, 1), (70, 33, 5), (513, 40, 72), (24, 32, 10000), (3, 2, 70001)]:
+        a = torch.randn(m, k, device=DEV)
+        b = torch.randn(k, n, device=DEV)
+        ref = (a.double() @ b.double()).float()
+        assert_close(sgx['ops'].gemm(a, b), ref, 2e-6, 'gemm %s' % ((m, n, k),))
+        assert_close(sgx['ops'].gemm(a.t().contiguous().t(), b.t().contiguous().t()), ref, 2e-6, 'gemm strided')
+
+
+# ------------------------------------------------------------------ PoolHiddenNet
+def _pool_module(sgx, sd, e_dim, h_dim, bott):
+    m = sgx['M'].PoolHiddenNet(embedding_dim=e_dim, h_dim=h_dim, mlp_dim=64, bottleneck_dim=bott, batch_norm=False)
+    m.load_state_dict(sd, strict=True)
+    return m.to(DEV)
+
+
+@pytest.mark.parametrize('name,dims', [('pool_g', (16, 32, 8)), ('pool_d', (16, 48, 48)), ('pool_g_big', (16, 32, 8))])
+def test_pool_fwd_bwd_vs_golden(sgx, name, dims):
+    g = load_golden(name)
+    m = _pool_module(sgx, state_dict_of(g), *dims)
+    h = g['h'].to(DEV).requires_grad_(True)
+    pos = g['pos'].to(DEV).requires_grad_(True)
+    out = m(h, g['seq_start_end'].to(DEV), pos)
+    assert_close(out, g['out'], 1e-5, name + ' out')
+    (out * g['upstream'].to(DEV)).sum().backward()
+    assert_close(h.grad, g['grad_in.h'], 2e-5, name + ' dh')
+    assert_close(pos.grad, g['grad_in.pos'], 2e-5, name + ' dpos')
+    for k, p in m.named_parameters():
+        assert_close(p.grad, g['grad.' + k], 2e-5, name + ' d' + k, floor=grad_floor(g))
+
+
+@pytest.mark.parametrize('sizes,dims', [([1], (16, 32, 8)), ([2] * 300, (16, 32, 8)), ([129, 3, 200, 64, 65], (16, 32, 8)),
+                                        ([40, 7, 130], (16, 48, 48)), ([5, 9], (8, 20, 24)), ([512], (16, 32, 8))])
+def test_pool_vs_oracle_seeded(sgx, sizes, dims):
+    e_dim, h_dim, bott = dims
+    torch.manual_seed(len(sizes) * 31 + sizes[0])
+    m = sgx['M'].PoolHiddenNet(embedding_dim=e_dim, h_dim=h_dim, mlp_dim=64, bottleneck_dim=bott, batch_norm=False)
+    sse = sse_from_sizes(sizes)
+    b = int(sse[-1, 1])
+    h = torch.randn(1, b, h_dim)
+    pos = torch.rand(b, 2) * 15
+    ref = O.pool_hidden_net(h, sse, pos, m.state_dict())
+    m = m.to(DEV)
+    out = m(h.to(DEV), sse.to(DEV), pos.to(DEV))
+    assert_close(out, ref, 1e-5, 'pool %s' % (sizes[:4],))
+
+
+def test_pool_argmax_points_into_own_scene(sgx):
+    g = load_golden('pool_g')
+    sd = state_dict_of(g)
+    sched = sgx['get_schedule'](g['seq_start_end'], DEV)
+    out, arg = sgx['ops'].pool_fwd(g['h'].reshape(-1, 32).to(DEV), g['pos'].to(DEV), sched.ped_start, sched.ped_end,
+                                   sched.pair_off, sched.tile_first, sched.n_pairs,
+                                   *[sd[k].to(DEV) for k in ('spatial_embedding.weight', 'spatial_embedding.bias',
+                                                             'mlp_pre_pool.0.weight', 'mlp_pre_pool.0.bias',
+                                                             'mlp_pre_pool.2.weight', 'mlp_pre_pool.2.bias')], 0)
+    ref_v, ref_i = O.pool_hidden_net_argmax(g['h'], g['seq_start_end'], g['pos'], sd)
+    arg = arg.cpu()
+    pos_mask = ref_v > 1e-6
+    assert torch.equal(arg[pos_mask].long(), ref_i[pos_mask])
+    for (s, e) in O.scene_bounds(g['seq_start_end']):
+        assert ((arg[s:e] >= s) & (arg[s:e] < e)).all()
+
+
+def test_pool_scene_independence_and_permutation_large(sgx):
+    """Size-independent properties at dense-crowd size (N = 1024): block-diagonality and permutation equivariance."""
+    torch.manual_seed(3)
+    m = sgx['M'].PoolHiddenNet(embedding_dim=16, h_dim=32, mlp_dim=64, bottleneck_dim=8, batch_norm=False).to(DEV)
+    n = 1024
+    h = torch.randn(n + 37, 32, device=DEV)
+    pos = torch.rand(n + 37, 2, device=DEV) * 15
+    both = m(h, sse_from_sizes([n, 37]).to(DEV), pos)
+    alone = m(h[:n], sse_from_sizes([n]).to(DEV), pos[:n])
+    assert torch.equal(both[:n], alone)
+    perm = torch.randperm(n, device=DEV)
+    permuted = m(h[:n][perm], sse_from_sizes([n]).to(DEV), pos[:n][perm])
+    assert_close(permuted, alone[perm], 1e-6, 'permutation equivariance')
+
+
+def test_pool_rejects_bad_segments(sgx):
+    m = sgx['M'].PoolHiddenNet(embedding_dim=16, h_dim=32, mlp_dim=64, bottleneck_dim=8, batch_norm=False).to(DEV)
+    h = torch.randn(5, 32, device=DEV)
+    pos = torch.rand(5, 2, device=DEV)
+    with pytest.raises(ValueError):
+        m(h, torch.tensor([[0, 2], [3, 5]]), pos)      # gap
+    with pytest.raises(ValueError):
+        m(h, torch.tensor([[0, 2], [2, 2], [2, 5]]), pos)  # empty scene
+    with pytest.raises(ValueError):
+        m(h, torch.tensor([[0, 4]]), pos)              # does not cover the batch
+
+
+# ------------------------------------------------------------------ GATEncoder / GCNModule
+@pytest.mark.parametrize('name', ['gat_encoder_h1', 'gat_encoder_h2'])
+def test_gat_encoder_fwd_bwd_vs_golden(sgx, name):
+    g = load_golden(name)
+    m = sgx['M'].GATEncoder(n_units=None, n_heads=int(g['n_heads']), dropout=0, alpha=float(g['alpha']))
+    m.load_state_dict(state_dict_of(g), strict=True)
+    m = m.to(DEV)
+    x = g['x'].to(DEV).requires_grad_(True)
+    out = m(x, g['seq_start_end'].to(DEV), g['pos'].to(DEV), g['labels'].to(DEV))
+    assert_close(out, g['out'], 1e-5, name + ' out')
+    (out * g['upstream'].to(DEV)).sum().backward()
+    assert_close(x.grad, g['grad_in.x'], 5e-5, name + ' dx')
+    for k, p in m.named_parameters():
+        assert_close(p.grad, g['grad.' + k], 5e-5, name + ' d' + k, floor=grad_floor(g))
+
+
+@pytest.mark.parametrize('name,in_dim', [('gcn_module_40', 40), ('gcn_module_32', 32)])
+def test_gcn_module_fwd_bwd_vs_golden(sgx, name, in_dim):
+    g = load_golden(name)
+    m = sgx['M'].GCNModule(input_dim=in_dim, hidden_dim=72, out_dim=16, gcn_layers=2, final_dim=24)
+    m.load_state_dict(state_dict_of(g), strict=True)
+    m = m.to(DEV)
+    x = g['x'].to(DEV).requires_grad_(True)
+    out = m(x, g['seq_start_end'].to(DEV), g['pos'].to(DEV), g['labels'].to(DEV))
+    assert_close(out, g['out'], 1e-5, name + ' out')
+    (out * g['upstream'].to(DEV)).sum().backward()
+    assert_close(x.grad, g['grad_in.x'], 5e-5, name + ' dx')
+    for k, p in m.named_parameters():
+        assert_close(p.grad, g['grad.' + k], 5e-5, name + ' d' + k, floor=grad_floor(g))
+
+
+@pytest.mark.parametrize('kind', ['gat', 'gcn'])
+def test_graph_modules_vs_oracle_seeded(sgx, kind):
+    """Ragged mix incl. singleton scenes, one big scene and one scene that is a single group."""
+    rng = np.random.RandomState(11)
+    torch.manual_seed(11)
+    sizes = [1, 2, 57, 3, 300, 8, 1, 14]
+    sse = sse_from_sizes(sizes)
+    b = int(sse[-1, 1])
+    labs = np.concatenate([np.where(rng.rand(n) < 0.13, 0, rng.randint(1, max(2, n // 3 + 1), size=n)) for n in sizes])
+    labs[sse[5, 0]:sse[5, 1]] = 4          # the 8-ped scene is one group
+    labs = torch.tensor(labs, dtype=torch.float32).view(-1, 1)
+    x = torch.randn(b, 40)
+    pos = torch.rand(b, 2)
+    if kind == 'gat':
+        m = sgx['M'].GATEncoder(n_units=None, n_heads=1, dropout=0, alpha=0.2)
+        ref = O.gat_encoder(x, sse, pos, labs, m.state_dict(), '', 0.2, 1)
+    else:
+        m = sgx['M'].GCNModule(input_dim=40, hidden_dim=72, out_dim=16, gcn_layers=2, final_dim=24)
+        with torch.no_grad():
+            for p in m.parameters():
+                if p.dim() == 2 and p.shape != (24, 32):
+                    p.mul_(0.15)
+        ref = O.gcn_module(x, sse, pos, labs, m.state_dict())
+    out = m.to(DEV)(x.to(DEV), sse.to(DEV), pos.to(DEV), labs.to(DEV))
+    assert_close(out, ref, 1e-5, kind + ' encoder')
+
+
+# ------------------------------------------------------------------ generator / discriminator wiring
+def _generator(sgx, g, wiring):
+    MD = sgx['MD']
+    pet = bool(int(g['pool_every_timestep']))
+    gen = MD.TrajectoryGenerator(obs_len=8, pred_len=int(g['pred_len']), embedding_dim=16, encoder_h_dim=32,
+                                 decoder_h_dim=32, mlp_dim=64, num_layers=1, noise_dim=(8,), noise_type='gaussian',
+                                 noise_mix_type='global', pooling_type='pool_net', pool_every_timestep=pet, dropout=0,
+                                 bottleneck_dim=8, batch_norm=False, n_heads=int(g['n_heads']), dropout1=0,
+                                 alpha=float(g['alpha']), context_type=wiring)
+    missing, unexpected = gen.load_state_dict(state_dict_of(g), strict=False)
+    assert all(k.startswith('gcn_module') for k in unexpected), unexpected   # passenger of the reference class
+    assert all(k.startswith(('mlp_decoder_context', 'gatencoder')) for k in missing), missing
+    return gen.to(DEV).train()
+
+
+@pytest.mark.parametrize('name', ['generator_gat_zara1', 'generator_p_eth', 'generator_gcn_zara1', 'generator_gat_pet'])
+def test_generator_matches_reference(sgx, name):
+    g = load_golden(name)
+    gen = _generator(sgx, g, str(g['wiring']))
+    obs, obs_rel, grp = g['obs_traj'].to(DEV), g['obs_traj_rel'].to(DEV), g['obs_traj_g'].to(DEV)
+    sse = g['seq_start_end'].to(DEV)
+    ades, fdes = [], []
+    with torch.no_grad():
+        for k in range(g['noise'].shape[0]):
+            rel = gen(obs, obs_rel, sse, grp, user_noise=g['noise'][k].to(DEV))
+            assert_close(rel, g['pred_rel'][k], 1e-4, name + ' pred_rel')   # 12 recurrent cuDNN steps; ADE/FDE below is the bar
+            ab = O.relative_to_abs(rel.cpu(), g['obs_traj'][-1])
+            ades.append(O.displacement_error_raw(ab, g['pred_traj_gt']))
+            fdes.append(O.final_displacement_error_raw(ab[-1], g['pred_traj_gt'][-1]))
+    n = obs.shape[1]
+    ade = float(O.best_of_k(ades, g['seq_start_end'])) / (n * int(g['pred_len']))
+    fde = float(O.best_of_k(fdes, g['seq_start_end'])) / n
+    assert abs(ade - float(g['ade'])) < 1e-4 and abs(fde - float(g['fde'])) < 1e-4
+
+
+def test_discriminator_matches_reference(sgx):
+    g = load_golden('discriminator_zara1')
+    d = sgx['MD'].TrajectoryDiscriminator(obs_len=8, pred_len=12, embedding_dim=16, h_dim=48, mlp_dim=64, num_layers=1,
+                                          dropout=0, batch_norm=False, d_type='global')
+    d.load_state_dict(state_dict_of(g), strict=True)
+    d = d.to(DEV)
+    with torch.no_grad():
+        s = d(g['traj'].to(DEV), g['traj_rel'].to(DEV), g['seq_start_end'].to(DEV))
+    assert_close(s, g['scores'], 2e-5, 'D scores')
+
+
+# ------------------------------------------------------------------ standalone dense layers
+def test_dense_gat_layer_and_gat_vs_golden(sgx):
+    M = sgx['M']
+    g = load_golden('gat_layer_dense')
+    layer = M.GraphAttentionLayer(12, 20, dropout=0, alpha=0.2, concat=True)
+    layer.load_state_dict(state_dict_of(g), strict=True)
+    layer = layer.to(DEV)
+    x = g['x'].to(DEV).requires_grad_(True)
+    out = layer(x, g['adj'].to(DEV))
+    assert_close(out, g['out'], 1e-5, 'gat layer out')
+    (out * g['upstream'].to(DEV)).sum().backward()
+    assert_close(x.grad, g['grad_in.x'], 5e-5, 'gat layer dx')
+    for k, p in layer.named_parameters():
+        assert_close(p.grad, g['grad.' + k], 5e-5, 'gat layer d' + k, floor=grad_floor(g))
+    g = load_golden('gat_dense')
+    net = M.GAT(12, 20, 6, dropout=0, alpha=0.2, nheads=3)
+    net.load_state_dict(state_dict_of(g), strict=True)
+    net = net.to(DEV)
+    x = g['x'].to(DEV).requires_grad_(True)
+    out = net(x, g['adj'].to(DEV))
+    assert_close(out, g['out'], 1e-5, 'gat out')
+    (out * g['upstream'].to(DEV)).sum().backward()
+    assert_close(x.grad, g['grad_in.x'], 5e-5, 'gat dx')
+    for k, p in net.named_parameters():
+        assert_close(p.grad, g['grad.' + k], 5e-5, 'gat d' + k, floor=grad_floor(g))
+
+
+def test_dense_gat_fully_masked_row_is_uniform(sgx):
+    """where(adj > 0, e, -9e15) then softmax: a row with no neighbour attends uniformly (models.py:202-204)."""
+    torch.manual_seed(5)
+    layer = sgx['M'].GraphAttentionLayer(6, 4, dropout=0, alpha=0.2, concat=False)
+    x = torch.randn(5, 6)
+    adj = torch.eye(5)
+    adj[2] = 0
+    ref = O.graph_attention_layer(x, adj, layer.W.detach(), layer.a.detach(), 0.2, False)
+    out = layer.to(DEV)(x.to(DEV), adj.to(DEV))
+    assert_close(out, ref, 1e-5, 'fully masked row')
+
+
+def test_dense_gcn_vs_golden(sgx):
+    g = load_golden('gcn_dense')
+    net = sgx['M'].GCN(input_dim=12, hidden_dim=20, out_dim=6, gcn_layers=3)
+    net.load_state_dict(state_dict_of(g), strict=True)
+    net = net.to(DEV)
+    x = g['x'].to(DEV).requires_grad_(True)
+    out = net(g['adj'].to(DEV), x)
+    assert_close(out, g['out'], 1e-5, 'gcn out')
+    (out * g['upstream'].to(DEV)).sum().backward()
+    assert_close(x.grad, g['grad_in.x'], 5e-5, 'gcn dx')
+    for k, p in net.named_parameters():
+        assert_close(p.grad, g['grad.' + k], 5e-5, 'gcn d' + k, floor=grad_floor(g))

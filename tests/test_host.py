@@ -1,0 +1,164 @@
+"""CPU: host-side logic -- the C ABI surface, the scene schedule, the module mirror's state_dict layout,
+and the no-fallback guarantee.  No kernel is launched here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden, sse_from_sizes, state_dict_of
+
+
+@pytest.fixture(scope='module')
+def lib():
+    import __graft_entry__ as ge
+    ge.build()
+    from group_gan_gcn_gat_b200 import _lib
+    return _lib
+
+
+def _declared_functions():
+    """(name, n_params) for every prototype in include/sgx.h."""
+    text = open(os.path.join(ROOT, 'include', 'sgx.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    protos = re.findall(r'\b(?:int|int64_t|const char\*)\s+(sgx_\w+)\s*\(([^;]*?)\)\s*;', text, flags=re.S)
+    out = []
+    for name, params in protos:
+        params = params.strip()
+        n = 0 if params in ('', 'void') else params.count(',') + 1
+        out.append((name, n))
+    return out
+
+
+def test_c_abi_exports_every_declared_symbol(lib):
+    decl = _declared_functions()
+    assert len(decl) >= 18
+    handle = ctypes.CDLL(lib.LIB_PATH)
+    for name, n_params in decl:
+        assert hasattr(handle, name), 'libsgx_b200.so does not export %s' % name
+        assert name in lib.SIGNATURES, 'python binding missing for %s' % name
+        assert len(lib.SIGNATURES[name][1]) == n_params, '%s: header has %d params, binding %d' % (
+            name, n_params, len(lib.SIGNATURES[name][1]))
+    assert set(lib.SIGNATURES) == {n for n, _ in decl}
+    assert lib.lib().sgx_version() >= 100
+
+
+def test_library_carries_sm100a_code(lib):
+    import shutil
+    import subprocess
+    exe = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.isfile(exe):
+        pytest.skip('cuobjdump not available')
+    out = subprocess.run([exe, '-lelf', lib.LIB_PATH], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True).stdout
+    assert 'sm_100a' in out
+
+
+def test_schedule_matches_numpy(lib):
+    from group_gan_gcn_gat_b200.schedule import SceneSchedule
+    rng = np.random.RandomState(0)
+    sizes = [1] + list(rng.randint(1, 70, size=500)) + [300, 2]
+    sse = sse_from_sizes(sizes)
+    s = SceneSchedule(sse, 'cpu')
+    n = np.asarray(sizes)
+    assert s.batch == n.sum() and s.max_n == n.max() and s.n_pairs == (n * n).sum() and s.n_scenes == len(sizes)
+    starts = np.concatenate([[0], np.cumsum(n)])
+    assert np.array_equal(s.scene_start.numpy(), starts)
+    assert np.array_equal(s.ped_start.numpy(), np.repeat(starts[:-1], n))
+    assert np.array_equal(s.ped_end.numpy(), np.repeat(starts[1:], n))
+    per_ped = np.repeat(n, n)
+    off = np.concatenate([[0], np.cumsum(per_ped)])
+    assert np.array_equal(s.pair_off.numpy(), off)
+    # tile t starts at pair 128 t, owned by the last ped whose offset is <= 128 t
+    t = np.arange(s.n_tiles) * 128
+    assert np.array_equal(s.tile_first.numpy(), np.searchsorted(off, t, side='right') - 1)
+
+
+def test_schedule_rejects_what_the_reference_cannot_slice(lib):
+    from group_gan_gcn_gat_b200.schedule import SceneSchedule
+    for bad in ([[0, 2], [3, 5]], [[1, 3]], [[0, 2], [2, 2]], [[0, 3], [2, 5]]):
+        with pytest.raises(ValueError):
+            SceneSchedule(torch.tensor(bad), 'cpu')
+
+
+def test_schedule_cache_follows_tensor_identity_and_version(lib):
+    from group_gan_gcn_gat_b200.schedule import get_schedule
+    a = torch.tensor([[0, 2], [2, 5]])
+    s1 = get_schedule(a, 'cpu')
+    assert get_schedule(a, 'cpu') is s1
+    a[1, 1] = 6
+    s2 = get_schedule(a, 'cpu')
+    assert s2 is not s1 and s2.batch == 6
+    assert get_schedule(a.clone(), 'cpu') is not s2
+
+
+def test_lpt_partition_balances_n_squared(lib):
+    from group_gan_gcn_gat_b200.schedule import SceneSchedule
+    rng = np.random.RandomState(1)
+    sizes = list(rng.randint(2, 60, size=512))
+    s = SceneSchedule(sse_from_sizes(sizes), 'cpu')
+    for world in (1, 2, 8):
+        rank, cost = s.partition(world)
+        assert rank.min() == 0 and rank.max() == world - 1
+        c = np.asarray(sizes) ** 2
+        assert np.array_equal(cost, np.bincount(rank, weights=c, minlength=world).astype(np.int64))
+        assert cost.max() - cost.min() <= c.max()          # LPT bound
+    r1, _ = s.partition(8)
+    r2, _ = s.partition(8)
+    assert np.array_equal(r1, r2)                          # deterministic: every rank computes the same split
+
+
+def test_state_dict_layout_matches_reference_checkpoints(lib):
+    """strict=True loading of the reference's own parameter names."""
+    import group_gan_gcn_gat_b200.models as MD
+    import group_gan_gcn_gat_b200.modules as M
+    g = load_golden('generator_gat_zara1')
+    gen = MD.TrajectoryGenerator(obs_len=8, pred_len=12, embedding_dim=16, encoder_h_dim=32, decoder_h_dim=32, mlp_dim=64,
+                                 noise_dim=(8,), noise_mix_type='global', pooling_type='pool_net',
+                                 pool_every_timestep=False, bottleneck_dim=8, batch_norm=False, n_heads=1)
+    gen.load_state_dict(state_dict_of(g), strict=True)
+    assert sum(p.numel() for p in gen.parameters()) == 56810
+    g = load_golden('discriminator_zara1')
+    d = MD.TrajectoryDiscriminator(obs_len=8, pred_len=12, embedding_dim=16, h_dim=48, mlp_dim=64, batch_norm=False,
+                                   d_type='global')
+    d.load_state_dict(state_dict_of(g), strict=True)
+    assert sum(p.numel() for p in d.parameters()) == 73873
+    g = load_golden('generator_gat_pet')
+    gen = MD.TrajectoryGenerator(obs_len=8, pred_len=12, embedding_dim=16, encoder_h_dim=32, decoder_h_dim=32, mlp_dim=64,
+                                 noise_dim=(8,), noise_mix_type='global', pooling_type='pool_net',
+                                 pool_every_timestep=True, bottleneck_dim=8, batch_norm=False, n_heads=1)
+    gen.load_state_dict(state_dict_of(g), strict=True)                # decoder.pool_net.*, decoder.mlp.*
+    for name, cls, kw in [('gat_encoder_h2', M.GATEncoder, dict(n_units=None, n_heads=2, dropout=0, alpha=0.2)),
+                          ('gcn_module_32', M.GCNModule, dict(input_dim=32, hidden_dim=72, out_dim=16, gcn_layers=2, final_dim=24)),
+                          ('pool_d', M.PoolHiddenNet, dict(embedding_dim=16, h_dim=48, mlp_dim=64, bottleneck_dim=48, batch_norm=False)),
+                          ('gat_dense', M.GAT, dict(nfeat=12, nhid=20, nclass=6, dropout=0, alpha=0.2, nheads=3)),
+                          ('gcn_dense', M.GCN, dict(input_dim=12, hidden_dim=20, out_dim=6, gcn_layers=3))]:
+        cls(**kw).load_state_dict(state_dict_of(load_golden(name)), strict=True)
+
+
+def test_no_cpu_fallback(lib):
+    """The product path must fail loudly without CUDA -- it never routes through the oracle or torch eager."""
+    import group_gan_gcn_gat_b200.modules as M
+    m = M.PoolHiddenNet(embedding_dim=16, h_dim=32, mlp_dim=64, bottleneck_dim=8, batch_norm=False)
+    with pytest.raises(RuntimeError):
+        m(torch.randn(1, 5, 32), torch.tensor([[0, 5]]), torch.rand(5, 2))
+    enc = M.GCNModule()
+    with pytest.raises((RuntimeError, TypeError)):
+        enc(torch.randn(5, 40), torch.tensor([[0, 5]]), torch.rand(5, 2), torch.zeros(5, 1))
+    src = ''
+    pkg = os.path.join(ROOT, 'group_gan_gcn_gat_b200')
+    for fn in os.listdir(pkg):
+        if fn.endswith('.py'):
+            src += open(os.path.join(pkg, fn)).read()
+    assert 'oracle' not in src.replace('the oracle', '')       # the package never imports the checker
+
+
+def test_unsupported_options_raise(lib):
+    import group_gan_gcn_gat_b200.modules as M
+    m = M.PoolHiddenNet(embedding_dim=16, h_dim=32, mlp_dim=64, bottleneck_dim=8, batch_norm=True)
+    with pytest.raises(NotImplementedError):
+        m(torch.randn(1, 5, 32), torch.tensor([[0, 5]]), torch.rand(5, 2))
+    import group_gan_gcn_gat_b200.models as MD
+    with pytest.raises(ValueError):
+        MD.get_noise((2, 2), 'laplace')
