@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- predicted trajectories/sec of the SGAN-GAT generator forward (K = 20 samples) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl sgx|reference] [--scenes S] [--precision fp32|bf16]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], SURVEY.md 8d cfg 2): zara1-shaped synthetic scenes (scene sizes drawn
+from the zara1-test pred-12 histogram, mean 3.74 peds), obs_len 8, pred_len 12, weights of the shipped
+models/sgan-gat-models/zara1_12_model.pt (frozen in tests/golden/generator_gat_zara1.npz), wiring GAT:
+encoder LSTM -> PoolHiddenNet -> GATEncoder -> noise -> decoder LSTM.  One *step* = the K=20 best-of-K generator
+forwards over one batch of S scenes per GPU (the loop of scripts/evaluate_model.py:85-90); every forward is
+complete (nothing is hoisted out of the K loop).  trajectories/step = peds * 20.
+
+Printed JSON line (rank 0): value = whole-job trajectories/sec with inputs resident in HBM; e2e = the same
+through the module API from pinned HOST buffers (schedule build + H2D + 20 forwards + D2H inside the timed
+region); roofline = the PoolHiddenNet pair kernel (CUDA events recorded by the library around that kernel);
+cpu_baseline = the CPU oracle port of the reference timed on this box's host cores on a bounded sample.
+--impl reference times that CPU port alone (the reference itself is Python and cannot travel to the GPU box).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ZARA1_HIST = {2: 212, 3: 136, 4: 109, 5: 55, 6: 32, 7: 10, 8: 20, 9: 8, 10: 12, 11: 4, 12: 1, 13: 2, 14: 1}
+K_SAMPLES = 20
+OBS_LEN, PRED_LEN = 8, 12
+POOL_FLOPS_PER_PAIR = 4 * 16 + 2 * (16 + 32) * 512 + 2 * 512 * 8     # 57 408, as written
+
+
+def synth_batch(n_scenes, seed):
+    """positions U[0,15]^2, per-step displacement N(0,0.3^2), labels 10% zero else U{1..max(1,N//3)}."""
+    rng = np.random.RandomState(seed)
+    sizes_pool = np.array(list(ZARA1_HIST.keys()))
+    probs = np.array(list(ZARA1_HIST.values()), dtype=np.float64)
+    sizes = rng.choice(sizes_pool, size=n_scenes, p=probs / probs.sum())
+    starts = np.concatenate([[0], np.cumsum(sizes)])
+    batch = int(starts[-1])
+    sse = np.stack([starts[:-1], starts[1:]], axis=1).astype(np.int64)
+    disp = rng.normal(0, 0.3, size=(OBS_LEN, batch, 2)).astype(np.float32)
+    disp[0] = 0
+    p0 = rng.uniform(0, 15, size=(1, batch, 2)).astype(np.float32)
+    obs = p0 + np.cumsum(disp, axis=0)
+    hi = np.maximum(1, np.repeat(sizes, sizes) // 3)
+    lab = np.floor(rng.uniform(0, 1, size=batch) * hi).astype(np.float32) + 1
+    lab[rng.uniform(0, 1, size=batch) < 0.10] = 0
+    grp = np.broadcast_to(lab[None, :, None], (OBS_LEN, batch, 1)).copy()
+    return dict(obs_traj=torch.from_numpy(obs.astype(np.float32)), obs_traj_rel=torch.from_numpy(disp),
+                obs_traj_g=torch.from_numpy(grp), seq_start_end=torch.from_numpy(sse), sizes=sizes)
+
+
+def load_weights():
+    z = np.load(os.path.join(ROOT, 'tests', 'golden', 'generator_gat_zara1.npz'))
+    return {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith('sd.')}
+
+
+class ClockSampler:
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.QUERY,
+                                          '--format=csv,noheader,nounits', '-lms', '200'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace('.', '').isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower() == 'active'})
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+def cpu_port_traj_per_sec(n_scenes, k_samples, seed, reps=1):
+    """The CPU oracle port of the reference generator (per-scene python loop, N^2 materialisation), all host threads."""
+    from oracle import sgan_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    data = synth_batch(n_scenes, seed)
+    sd = load_weights()
+    cfg = dict(pred_len=PRED_LEN, wiring='gat', pooling=True, pool_every_timestep=False, alpha=0.2, n_heads=1)
+    gen = torch.Generator().manual_seed(seed)
+    best = None
+    with torch.no_grad():
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            for _k in range(k_samples):
+                z = torch.randn(n_scenes, 8, generator=gen)
+                O.generator_forward(data['obs_traj'], data['obs_traj_rel'], data['seq_start_end'], data['obs_traj_g'],
+                                    sd, cfg, z)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    peds = int(data['seq_start_end'][-1, 1])
+    return peds * k_samples / best, best, peds
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    n_scenes = 256
+    for _ in range(args.warmup):
+        cpu_port_traj_per_sec(16, 2, 1)
+    t0 = time.perf_counter()
+    vals = []
+    for s in range(args.steps):
+        v, dt, peds = cpu_port_traj_per_sec(n_scenes, K_SAMPLES, 1234 + 2 + s)
+        vals.append((v, dt, peds))
+    total_traj = sum(p * K_SAMPLES for _, _, p in vals)
+    total_t = sum(dt for _, dt, _ in vals)
+    value = total_traj / total_t
+    line = {'impl': 'reference', 'metric': 'predicted_trajectories_per_sec', 'value': value, 'unit': 'traj/s',
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total_t / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
+            'config': workload_config(n_scenes, 'cpu'),
+            'cpu_baseline': {'value': value, 'unit': 'traj/s', 'cores': os.cpu_count(), 'kind': 'port',
+                             'sample': '%d zara1-shaped scenes x K=%d generator forwards per step (oracle port of '
+                                       'sgan/models.py, per-scene loop)' % (n_scenes, K_SAMPLES)},
+            'e2e': {'value': value, 'unit': 'traj/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'wall_s': time.perf_counter() - t0}
+    print(json.dumps(line))
+
+
+def workload_config(n_scenes, precision):
+    return {'workload': 'SGAN-GAT generator fwd (PoolHiddenNet+GATEncoder), zara1-shaped synthetic scenes, '
+                        'obs 8 / pred 12, K=20 forwards per step',
+            'scenes_per_gpu': n_scenes, 'k_samples': K_SAMPLES, 'pred_len': PRED_LEN, 'pool_precision': precision,
+            'weights': 'models/sgan-gat-models/zara1_12_model.pt (tests/golden/generator_gat_zara1.npz)',
+            'l2': 'flushed between timed steps (256 MiB write)', 'parallelism': 'scenes sharded by LPT on N^2'}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='sgx', choices=['sgx', 'reference'])
+    ap.add_argument('--scenes', type=int, default=1 << 16, help='scenes per GPU per step')
+    ap.add_argument('--precision', default=os.environ.get('SGX_POOL_PRECISION', 'auto'))
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (the sgx ops have no CPU fallback)'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    torch.backends.cudnn.allow_tf32 = False
+
+    from group_gan_gcn_gat_b200 import _lib, models as MD
+    from group_gan_gcn_gat_b200.schedule import SceneSchedule, get_schedule
+    L = _lib.lib()
+    precision = args.precision
+    if precision == 'auto':
+        precision = 'bf16' if L.sgx_has_tcgen05() else 'fp32'
+
+    # ---- the global scene set, sharded by LPT on N^2 (weak scaling: S scenes per GPU) ----
+    data = synth_batch(args.scenes * world, 1234 + 2)
+    if world > 1:
+        full = SceneSchedule(data['seq_start_end'], 'cpu')
+        rank_of, _ = full.partition(world)
+        mine = np.nonzero(rank_of == rank)[0]
+        sse = data['seq_start_end'].numpy()
+        idx = np.concatenate([np.arange(sse[s, 0], sse[s, 1]) for s in mine])
+        sizes = data['sizes'][mine]
+        st = np.concatenate([[0], np.cumsum(sizes)])
+        data = dict(obs_traj=data['obs_traj'][:, idx], obs_traj_rel=data['obs_traj_rel'][:, idx],
+                    obs_traj_g=data['obs_traj_g'][:, idx],
+                    seq_start_end=torch.from_numpy(np.stack([st[:-1], st[1:]], 1).astype(np.int64)), sizes=sizes)
+    n_scenes = data['seq_start_end'].shape[0]
+    peds = int(data['seq_start_end'][-1, 1])
+    n_pairs = int((data['sizes'].astype(np.int64) ** 2).sum())
+
+    gen = MD.TrajectoryGenerator(obs_len=OBS_LEN, pred_len=PRED_LEN, embedding_dim=16, encoder_h_dim=32, decoder_h_dim=32,
+                                 mlp_dim=64, noise_dim=(8,), noise_mix_type='global', pooling_type='pool_net',
+                                 pool_every_timestep=False, bottleneck_dim=8, batch_norm=False, n_heads=1, alpha=0.2)
+    gen.load_state_dict(load_weights(), strict=True)
+    gen = gen.to(dev).train()          # scripts/evaluate_model.py:54 keeps the generator in train mode
+    gen.pool_net.precision = precision
+
+    host = {k: data[k].pin_memory() for k in ('obs_traj', 'obs_traj_rel', 'obs_traj_g', 'seq_start_end')}
+    dev_in = {k: v.to(dev) for k, v in host.items()}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    noise_gen = torch.Generator(device=dev).manual_seed(7)
+    out_host = torch.empty(K_SAMPLES, PRED_LEN, peds, 2).pin_memory()
+
+    def step_resident():
+        outs = None
+        for _k in range(K_SAMPLES):
+            z = torch.randn(n_scenes, 8, device=dev, generator=noise_gen)
+            outs = gen(dev_in['obs_traj'], dev_in['obs_traj_rel'], dev_in['seq_start_end'], dev_in['obs_traj_g'],
+                       user_noise=z)
+        return outs
+
+    def step_e2e():
+        obs = host['obs_traj'].to(dev, non_blocking=True)
+        obs_rel = host['obs_traj_rel'].to(dev, non_blocking=True)
+        grp = host['obs_traj_g'].to(dev, non_blocking=True)
+        sse = host['seq_start_end'].clone()              # a fresh batch object every step: the schedule is rebuilt
+        for k in range(K_SAMPLES):                       # once per step from the HOST tensor (no D2H sync), then cached
+            rel = gen(obs, obs_rel, sse, grp)            # noise drawn on the CPU generator like the reference
+            out_host[k].copy_(rel, non_blocking=True)
+        torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            step_resident()
+        # ---- timed: resident inputs, CUDA events per step, L2 flushed between steps ----
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        barrier()
+        launches0 = L.sgx_launch_count()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        wall0 = time.perf_counter()
+        for a, b in ev:
+            flush.fill_(1)
+            a.record()
+            step_resident()
+            b.record()
+        barrier()
+        wall = time.perf_counter() - wall0
+        launches = L.sgx_launch_count() - launches0
+        step_ms = [a.elapsed_time(b) for a, b in ev]
+        total_ms = sum(step_ms)
+        clocks = sampler.stop() if rank == 0 else None
+
+        # ---- e2e: host buffers, H2D + schedule + 20 forwards + D2H inside the timed region ----
+        step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+
+        # ---- roofline of the dominant pooling kernel: events recorded by the library around that launch ----
+        import ctypes
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); e1.record(); torch.cuda.synchronize()        # create the underlying cudaEvents
+        L.sgx_profile_events(ctypes.c_void_p(e0.cuda_event), ctypes.c_void_p(e1.cuda_event))
+        h_enc = gen.encoder(dev_in['obs_traj_rel'])
+        kernel_ms = []
+        for _ in range(3 + 10):
+            flush.fill_(1)
+            gen.pool_net(h_enc, dev_in['seq_start_end'], dev_in['obs_traj'][-1])
+            torch.cuda.synchronize()
+            kernel_ms.append(e0.elapsed_time(e1))
+        L.sgx_profile_events(None, None)
+        kernel_ms = kernel_ms[3:]
+
+    t_total = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    work = torch.tensor([float(peds * K_SAMPLES)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_total, op=dist.ReduceOp.MAX)
+        dist.all_reduce(work, op=dist.ReduceOp.SUM)
+    total_ms_max, e2e_ms_max = t_total.tolist()
+    traj_per_step = work.item()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except OSError:
+            pass
+        if precision == 'bf16':
+            peak, peak_src = peaks.get('bf16_tflops_sustained', 1400.0), 'measured bf16 sustained' if peaks else 'fallback'
+        else:
+            peak, peak_src = peaks.get('bf16_tflops_sustained', 1400.0), 'measured bf16 sustained' if peaks else 'fallback'
+        k_ms = statistics.mean(kernel_ms)
+        achieved = POOL_FLOPS_PER_PAIR * n_pairs / (k_ms * 1e-3) / 1e12
+        line = {
+            'metric': 'predicted_trajectories_per_sec', 'value': traj_per_step * args.steps / (total_ms_max * 1e-3),
+            'unit': 'traj/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': total_ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'bf16' if precision == 'bf16' else 'fp32', 'data': 'synthetic',
+            'config': dict(workload_config(n_scenes, precision), peds_per_gpu=peds, pairs_per_gpu=n_pairs),
+            'clocks': clocks,
+            'e2e': {'value': traj_per_step * args.steps / (e2e_ms_max * 1e-3), 'unit': 'traj/s',
+                    'h2d_bytes_per_step': int(sum(host[k].numel() * host[k].element_size()
+                                                  for k in ('obs_traj', 'obs_traj_rel', 'obs_traj_g')) +
+                                              5 * 4 * peds + 8 * peds + K_SAMPLES * n_scenes * 8 * 4),
+                    'd2h_bytes_per_step': int(out_host.numel() * 4)},
+            'gpu_launches': int(launches),
+            'roofline': {'kernel': 'pool_pair_kernel' if precision != 'bf16' else 'pool_tc_kernel', 'bound': 'tensor',
+                         'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
+                         'traffic': None, 'peak_source': peak_src, 'kernel_ms': k_ms,
+                         'algorithmic_flops_per_launch': POOL_FLOPS_PER_PAIR * n_pairs,
+                         'note': 'as-written FLOPs (57408 per ordered pair); the fp32 kernel executes the exactly '
+                                 'factored layer 1 on CUDA cores, see DESIGN.md'},
+            'wall_s_timed_region': wall,
+        }
+        if not args.no_cpu_baseline:
+            v, dt, p = cpu_port_traj_per_sec(256, K_SAMPLES, 1234 + 2)
+            line['cpu_baseline'] = {'value': v, 'unit': 'traj/s', 'cores': os.cpu_count(), 'kind': 'port',
+                                    'sample': '256 zara1-shaped scenes (%d peds) x K=20 forwards, %.1f s' % (p, dt)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -28,6 +28,8 @@ SIGNATURES = {
     'sgx_last_error': (ctypes.c_char_p, []),
     'sgx_version': (ctypes.c_int, []),
     'sgx_has_tcgen05': (ctypes.c_int, []),
+    'sgx_launch_count': (ctypes.c_longlong, []),
+    'sgx_profile_events': (ctypes.c_int, [_P, _P]),
     'sgx_schedule_stats': (ctypes.c_int, [_P, _I64, _P]),
     'sgx_schedule_fill': (ctypes.c_int, [_P, _I64, _P, _P, _P, _P, _P]),
     'sgx_schedule_partition': (ctypes.c_int, [_P, _I64, _I32, _P, _P]),

@@ -4,6 +4,7 @@
 // (sgan/models.py:507-510, 256-262, 639-644): seq_start_end is read ONCE per minibatch on the
 // host and turned into flat per-ped arrays that every kernel indexes without a device sync.
 #include <algorithm>
+#include <atomic>
 #include <numeric>
 #include <queue>
 #include <vector>
@@ -18,7 +19,18 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+static thread_local cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
+void profile_events(cudaEvent_t* start, cudaEvent_t* stop) { *start = g_ev_start; *stop = g_ev_stop; }
 }  // namespace sgx
+
+extern "C" long long sgx_launch_count(void) { return sgx::g_launches.load(); }
+extern "C" int sgx_profile_events(void* ev_start, void* ev_stop) {
+    sgx::g_ev_start = (cudaEvent_t)ev_start;
+    sgx::g_ev_stop = (cudaEvent_t)ev_stop;
+    return SGX_OK;
+}
 
 extern "C" const char* sgx_last_error(void) { return sgx::g_err; }
 extern "C" int sgx_version(void) { return 100; }

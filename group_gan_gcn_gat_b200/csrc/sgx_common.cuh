@@ -11,6 +11,9 @@
 namespace sgx {
 
 void set_error(const char* fmt, ...);
+void count_launch();
+// optional events recorded around the dominant pooling kernel (bench instrumentation); null when unset
+void profile_events(cudaEvent_t* start, cudaEvent_t* stop);
 
 #define SGX_REQUIRE(cond, ...)                 \
     do {                                       \
@@ -38,7 +41,12 @@ void set_error(const char* fmt, ...);
         }                                                                                       \
     } while (0)
 
-#define SGX_LAUNCH_CHECK() SGX_CUDA(cudaGetLastError())
+// every kernel launch of the library is followed by this: counts launches (sgx_launch_count) and surfaces errors
+#define SGX_LAUNCH_CHECK()              \
+    do {                                \
+        sgx::count_launch();            \
+        SGX_CUDA(cudaGetLastError());   \
+    } while (0)
 
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 static inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }

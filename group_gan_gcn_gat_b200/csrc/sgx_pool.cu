@@ -326,6 +326,9 @@ extern "C" int sgx_pool_fwd(const float* h, const float* pos, const int32_t* ped
         // C^T[k][p] = c0[k] + sum_h W1[k][E+h] * h[p][h]
         rc = gemm(W1 + E, E + H, 1, h, 1, H, Ct, ldc, HID, batch, H, 0, 0, st, c0);
         if (rc) return rc;
+        cudaEvent_t ev0, ev1;
+        profile_events(&ev0, &ev1);
+        if (ev0 && ev1) SGX_CUDA(cudaEventRecord(ev0, st));
         if (B % 16 == 0) {
             constexpr int BC = 16, R = 4, T = 256;
             dim3 grid((unsigned)((n_pairs + T * R - 1) / (T * R)), B / BC);
@@ -338,6 +341,7 @@ extern "C" int sgx_pool_fwd(const float* h, const float* pos, const int32_t* ped
                                                            (int)batch, n_pairs, Aeff, W2, b2, B, packed);
         }
         SGX_LAUNCH_CHECK();
+        if (ev0 && ev1) SGX_CUDA(cudaEventRecord(ev1, st));
     }
     pool_unpack_kernel<<<blocks_for(batch * B, 256), 256, 0, st>>>(packed, batch * B, out, argmax);
     SGX_LAUNCH_CHECK();

@@ -40,6 +40,11 @@ const char* sgx_last_error(void);
 int sgx_version(void);
 /* 1 when the loaded binary carries sm_100a code for the tcgen05 pooling kernel */
 int sgx_has_tcgen05(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches evidence) */
+long long sgx_launch_count(void);
+/* bench instrumentation: when both are non-null CUDA events (cudaEvent_t), sgx_pool_fwd records them on its
+ * stream directly around its dominant kernel (the pair kernel); pass nulls to switch off.  Thread local. */
+int sgx_profile_events(void* ev_start, void* ev_stop);
 
 /* ---------------------------------------------------------------------------------------------
  * Scene schedule (host).  Replaces the per-scene `.item()` loop headers of

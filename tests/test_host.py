@@ -23,7 +23,7 @@ def _declared_functions():
     """(name, n_params) for every prototype in include/sgx.h."""
     text = open(os.path.join(ROOT, 'include', 'sgx.h')).read()
     text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
-    protos = re.findall(r'\b(?:int|int64_t|const char\*)\s+(sgx_\w+)\s*\(([^;]*?)\)\s*;', text, flags=re.S)
+    protos = re.findall(r'\b(?:int|int64_t|long long|const char\*)\s+(sgx_\w+)\s*\(([^;]*?)\)\s*;', text, flags=re.S)
     out = []
     for name, params in protos:
         params = params.strip()
