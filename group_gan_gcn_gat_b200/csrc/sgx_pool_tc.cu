@@ -1,0 +1,497 @@
+// PoolHiddenNet forward on the 5th-gen tensor cores: tcgen05.mma + TMEM, bf16 operands, fp32 accumulate.
+//
+// Reference math (sgan/models.py:530-541), per ordered pair (i,j) of a scene:
+//     y = ReLU(W2 ReLU(W1 [We (P_j-P_i)+be ; h_j] + b1) + b2)   ;   out_i = max_j y
+// Tensor-core formulation.  A tile is 128 consecutive ordered pairs of the flat (i,j)-sorted pair list
+// (any mix of scenes).  Per tile:
+//   GEMM1  D1[128 x 512] = X[128 x K] . W1p[512 x K]^T        K = 16 + H  (48 for G, 64 for D)
+//          X row = [dx_hi dx_lo dx_hi dy_hi dy_lo dy_hi 1 1 0.. | bf16(h_j)]
+//          W1p row k = [A0_hi A0_hi A0_lo A1_hi A1_hi A1_lo c_hi c_lo 0.. | bf16(W1[k, E:])]
+//          with Aeff = W1[:, :E] We and c = W1[:, :E] be + b1 folded on the host side of the kernel (exact
+//          algebra; hi/lo bf16 splits keep the position term and the bias at ~16 mantissa bits).
+//          Issued as 4 hidden chunks of N = 128 so the fp32 accumulator (128 TMEM columns) double-buffers.
+//   EPI1   TMEM -> registers (tcgen05.ld 32x32b.x32), ReLU + bf16x2 pack (cvt.rn.relu.bf16x2.f32),
+//          registers -> TMEM (tcgen05.st) as the A operand of GEMM2 -- the 128 x 512 hidden tile never
+//          touches shared or global memory ("ts" mode; "ss" mode stages it in shared memory instead).
+//   GEMM2  D2[128 x N2] += Hc[128 x 128] . W2p[N2 x 128]^T  per hidden chunk  (N2 = 16 for B = 8, 48 for B = 48)
+//   EPI2   TMEM -> registers, + b2, ReLU, segmented warp max over rows that share i, one 64-bit
+//          atomicMax (value bits << 32 | j) per (segment, channel) into the packed output.
+// Weights are pre-swizzled bf16 images (SWIZZLE_128B, K-major) loaded once per persistent CTA with the
+// bulk-copy engine (cp.async.bulk + mbarrier complete_tx).  One CTA per SM, 13 warps:
+//   warp 0      MMA issuer (one elected lane)            warps 1-4   build X tiles / final epilogue
+//   warps 5-8   EPI1 for even hidden chunks              warps 9-12  EPI1 for odd hidden chunks
+#include <cuda_bf16.h>
+#include <stdlib.h>
+
+#include "sgx_common.cuh"
+
+namespace sgx {
+
+constexpr int HID = SGX_POOL_HIDDEN;
+constexpr int TILE = 128;        // pairs per tile = UMMA M
+constexpr int NCHUNK = 4;        // hidden chunks of 128
+constexpr int NST = 3;           // X-tile smem stages
+constexpr int NMETA = 4;         // ring of per-tile (i,j) metadata
+constexpr int LOOKAHEAD = 2;     // tiles built ahead of the final epilogue
+constexpr int NTHREADS = 13 * 32;
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[smem desc] . B[smem desc]
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem desc]
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,"
+        "%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(
+            taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// {hi, lo} -> packed bf16x2 with ReLU (lo in bits 15:0)
+__device__ __forceinline__ uint32_t relu_pack(uint32_t hi_f32_bits, uint32_t lo_f32_bits) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi_f32_bits)), "f"(__uint_as_float(lo_f32_bits)));
+    return d;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (row pitch 128 B, 8-row atoms 1024 B apart)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);   // start address
+    d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major) = 16 B
+    d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset: 1024 B between 8-row groups
+    d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+    return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    // c_format f32 (1<<4) | a_format bf16 (1<<7) | b_format bf16 (1<<10) | K-major A,B | N>>3 @17 | M>>4 @24
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// byte offset of element (row r, 16-byte chunk c) inside a SWIZZLE_128B K-major tile with 128-byte rows
+__host__ __device__ __forceinline__ uint32_t swz(uint32_t r, uint32_t c) { return r * 128u + ((c ^ (r & 7u)) << 4); }
+
+// ---------------------------------------------------------------------------------------------
+// operand preparation: bf16 copy of h, pre-swizzled weight images
+// ---------------------------------------------------------------------------------------------
+__global__ void tc_prep_h_kernel(const float* __restrict__ h, int64_t n, __nv_bfloat16* __restrict__ hb) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) hb[i] = __float2bfloat16_rn(h[i]);
+}
+
+// W1p image: 512 rows x 128 B.   W2p image: 8 K-blocks x N2 rows x 128 B.
+__global__ void tc_prep_w_kernel(const float2* __restrict__ Aeff, const float* __restrict__ c0,
+                                 const float* __restrict__ W1, const float* __restrict__ W2, int E, int H, int B, int N2,
+                                 __nv_bfloat16* __restrict__ W1p, __nv_bfloat16* __restrict__ W2p) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < HID * 64) {
+        int n = t / 64, k = t % 64;
+        float v = 0.f;
+        if (k < 16) {
+            float2 a = Aeff[n];
+            float c = c0[n];
+            float src = (k < 3) ? a.x : (k < 6) ? a.y : c;
+            float hi = __bfloat162float(__float2bfloat16_rn(src));
+            float lo = src - hi;
+            bool want_lo = (k == 2 || k == 5 || k == 7);
+            v = (k < 8) ? (want_lo ? lo : hi) : 0.f;
+        } else if (k - 16 < H) {
+            v = W1[(int64_t)n * (E + H) + E + (k - 16)];
+        }
+        uint32_t off = swz((uint32_t)n, (uint32_t)(k >> 3)) + (k & 7) * 2;
+        W1p[off >> 1] = __float2bfloat16_rn(v);
+    }
+    if (t < 8 * N2 * 64) {
+        int kb = t / (N2 * 64), r = (t / 64) % N2, kk = t % 64;
+        float v = (r < B) ? W2[(int64_t)r * HID + kb * 64 + kk] : 0.f;
+        uint32_t off = (uint32_t)kb * N2 * 128 + swz((uint32_t)r, (uint32_t)(kk >> 3)) + (kk & 7) * 2;
+        W2p[off >> 1] = __float2bfloat16_rn(v);
+    }
+}
+
+__device__ __forceinline__ int find_ped_tc(const int64_t* __restrict__ pair_off, int lo, int hi, int64_t q) {
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (pair_off[mid] <= q) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+struct TcSmem {   // dynamic shared memory layout (offsets from a 1024-aligned base)
+    static constexpr int W1P = 0;                                  // 64 KB
+    static constexpr int X = W1P + HID * 128;                      // NST x 16 KB
+    static constexpr int W2P = X + NST * TILE * 128;               // 8 * N2 * 128
+};
+
+template <int H, int N2, bool TS>
+struct TcCfg {
+    static constexpr int KCH = (16 + H) / 16;                      // k-chunks of GEMM1
+    static constexpr int W2P_BYTES = 8 * N2 * 128;
+    static constexpr int HS = TcSmem::W2P + W2P_BYTES;             // "ss" mode: 2 x 32 KB hidden staging
+    static constexpr int HS_BYTES = TS ? 0 : 2 * TILE * 256;
+    static constexpr int META = HS + HS_BYTES;                     // int2 [NMETA][128]
+    static constexpr int BARS = META + NMETA * TILE * 8;
+    static constexpr int TOTAL = BARS + 256 + 1024;                // + alignment slack
+    static constexpr int D2_STRIDE = (N2 <= 32) ? 32 : 64;         // TMEM columns per D2 buffer
+    static constexpr int TM_D1 = 0, TM_H = 256, TM_D2 = 384;
+};
+
+template <int H, int B, int N2, bool TS>
+__global__ void __launch_bounds__(NTHREADS, 1)
+pool_tc_kernel(const __nv_bfloat16* __restrict__ hb, const float* __restrict__ pos,
+               const int32_t* __restrict__ ped_start, const int64_t* __restrict__ pair_off,
+               const int32_t* __restrict__ tile_first, int64_t n_tiles, int batch, int64_t n_pairs,
+               const __nv_bfloat16* __restrict__ W1p, const __nv_bfloat16* __restrict__ W2p,
+               const float* __restrict__ b2, unsigned long long* __restrict__ packed) {
+    using C = TcCfg<H, N2, TS>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BARS);
+    uint64_t* w_full = bars + 0;
+    uint64_t* x_full = bars + 1;             // [NST]
+    uint64_t* x_free = x_full + NST;         // [NST]
+    uint64_t* d1_full = x_free + NST;        // [2]
+    uint64_t* d1_free = d1_full + 2;         // [2]
+    uint64_t* h_ready = d1_free + 2;         // [2]
+    uint64_t* h_free = h_ready + 2;          // [2]
+    uint64_t* d2_full = h_free + 2;          // [2]
+    uint64_t* d2_free = d2_full + 2;         // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2_free + 2);
+    int2* meta = reinterpret_cast<int2*>(smem + C::META);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (threadIdx.x == 0) {
+        mbar_init(w_full, 1);
+        for (int s = 0; s < NST; ++s) { mbar_init(&x_full[s], 128); mbar_init(&x_free[s], 1); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&d1_full[s], 1); mbar_init(&d1_free[s], 128);
+            mbar_init(&h_ready[s], 128); mbar_init(&h_free[s], 1);
+            mbar_init(&d2_full[s], 1); mbar_init(&d2_free[s], 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 0) {   // TMEM: all 512 columns (one CTA per SM)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ======================= MMA issuer =======================
+        if (lane == 0) {
+            mbar_expect_tx(w_full, HID * 128 + C::W2P_BYTES);
+            bulk_g2s(smem + TcSmem::W1P, W1p, HID * 128, w_full);
+            bulk_g2s(smem + TcSmem::W2P, W2p, C::W2P_BYTES, w_full);
+            mbar_wait(w_full, 0);
+            constexpr uint32_t idesc1 = make_idesc(128, 128), idesc2 = make_idesc(128, N2);
+            const uint32_t w1_s = smem_u32(smem + TcSmem::W1P), w2_s = smem_u32(smem + TcSmem::W2P);
+            const uint32_t x_s = smem_u32(smem + TcSmem::X), hs_s = smem_u32(smem + C::HS);
+            const int64_t n_chunks = my_tiles * NCHUNK;
+            for (int64_t g = 0; g <= n_chunks; ++g) {
+                if (g < n_chunks) {   // ---- GEMM1 of chunk g ----
+                    const int64_t t = g / NCHUNK;
+                    const int c = (int)(g % NCHUNK), st = (int)(t % NST), buf = (int)(g & 1);
+                    if (c == 0) mbar_wait(&x_full[st], (uint32_t)((t / NST) & 1));
+                    mbar_wait(&d1_free[buf], (uint32_t)(((g >> 1) & 1) ^ 1));
+                    tc_fence_after();
+                    const uint32_t d1 = tmem + C::TM_D1 + buf * 128;
+#pragma unroll
+                    for (int kc = 0; kc < C::KCH; ++kc)
+                        mma_ss(d1, make_desc(x_s + st * TILE * 128 + kc * 32), make_desc(w1_s + c * 16384 + kc * 32),
+                               idesc1, kc > 0);
+                    tc_commit(&d1_full[buf]);
+                    if (c == NCHUNK - 1) tc_commit(&x_free[st]);
+                }
+                if (g > 0) {          // ---- GEMM2 of chunk g-1 ----
+                    const int64_t gp = g - 1, t = gp / NCHUNK;
+                    const int c = (int)(gp % NCHUNK), buf = (int)(gp & 1), db = (int)(t & 1);
+                    if (c == 0) mbar_wait(&d2_free[db], (uint32_t)(((t >> 1) & 1) ^ 1));
+                    mbar_wait(&h_ready[buf], (uint32_t)((gp >> 1) & 1));
+                    tc_fence_after();
+                    const uint32_t d2 = tmem + C::TM_D2 + db * C::D2_STRIDE;
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) {
+                        const uint64_t bd = make_desc(w2_s + (c * 2 + (kk >> 2)) * (N2 * 128) + (kk & 3) * 32);
+                        if (TS)
+                            mma_ts(d2, tmem + C::TM_H + buf * 64 + kk * 8, bd, idesc2, (c > 0 || kk > 0));
+                        else
+                            mma_ss(d2, make_desc(hs_s + buf * (TILE * 256) + (kk >> 2) * 16384 + (kk & 3) * 32), bd,
+                                   idesc2, (c > 0 || kk > 0));
+                    }
+                    tc_commit(&h_free[buf]);
+                    if (c == NCHUNK - 1) tc_commit(&d2_full[db]);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp <= 4) {
+        // ======================= row warps: build X tiles, final epilogue =======================
+        const int row = ((warp & 3) << 5) | lane;    // TMEM lane quadrant = warp % 4
+        float bias2[B];
+#pragma unroll
+        for (int b = 0; b < B; ++b) bias2[b] = b2[b];
+        for (int64_t it = 0; it < my_tiles + LOOKAHEAD; ++it) {
+            if (it < my_tiles) {
+                const int64_t tile = blockIdx.x + it * gridDim.x;
+                const int st = (int)(it % NST);
+                mbar_wait(&x_free[st], (uint32_t)(((it / NST) & 1) ^ 1));
+                const int64_t q = tile * TILE + row;
+                uint8_t* xrow = smem + TcSmem::X + st * TILE * 128;
+                int2 ij = make_int2(-1, 0);
+                uint4 c0 = make_uint4(0, 0, 0, 0);
+                if (q < n_pairs) {
+                    const int lo = tile_first[tile];
+                    const int hi = (tile + 1 < n_tiles) ? tile_first[tile + 1] : batch - 1;
+                    const int i = find_ped_tc(pair_off, lo, hi, q);
+                    const int j = ped_start[i] + (int)(q - pair_off[i]);
+                    ij = make_int2(i, j);
+                    const float dx = pos[2 * j] - pos[2 * i], dy = pos[2 * j + 1] - pos[2 * i + 1];
+                    const float dxh = __bfloat162float(__float2bfloat16_rn(dx)), dyh = __bfloat162float(__float2bfloat16_rn(dy));
+                    c0.x = pack_bf16(dxh, dx - dxh);       // slots 0,1
+                    c0.y = pack_bf16(dxh, dyh);            // slots 2,3
+                    c0.z = pack_bf16(dy - dyh, dyh);       // slots 4,5
+                    c0.w = pack_bf16(1.f, 1.f);            // slots 6,7
+                    const uint4* hrow = reinterpret_cast<const uint4*>(hb + (int64_t)j * H);
+#pragma unroll
+                    for (int c = 0; c < H / 8; ++c)
+                        *reinterpret_cast<uint4*>(xrow + swz(row, 2 + c)) = hrow[c];
+                } else {
+#pragma unroll
+                    for (int c = 0; c < H / 8; ++c)
+                        *reinterpret_cast<uint4*>(xrow + swz(row, 2 + c)) = make_uint4(0, 0, 0, 0);
+                }
+                *reinterpret_cast<uint4*>(xrow + swz(row, 0)) = c0;
+                *reinterpret_cast<uint4*>(xrow + swz(row, 1)) = make_uint4(0, 0, 0, 0);
+                meta[(it % NMETA) * TILE + row] = ij;
+                fence_proxy_async();
+                mbar_arrive(&x_full[st]);
+            }
+            if (it >= LOOKAHEAD) {
+                const int64_t t = it - LOOKAHEAD;
+                const int db = (int)(t & 1);
+                mbar_wait(&d2_full[db], (uint32_t)((t >> 1) & 1));
+                tc_fence_after();
+                uint32_t v[16];
+                tmem_ld16(tmem + ((uint32_t)((warp & 3) << 5) << 16) + C::TM_D2 + db * C::D2_STRIDE, v);
+                uint32_t v2[16], v3[16];
+                if (B > 16) {
+                    tmem_ld16(tmem + ((uint32_t)((warp & 3) << 5) << 16) + C::TM_D2 + db * C::D2_STRIDE + 16, v2);
+                    tmem_ld16(tmem + ((uint32_t)((warp & 3) << 5) << 16) + C::TM_D2 + db * C::D2_STRIDE + 32, v3);
+                }
+                tmem_wait_ld();
+                tc_fence_before();
+                mbar_arrive(&d2_free[db]);
+                const int2 ij = meta[(t % NMETA) * TILE + row];
+                const int key = ij.x;
+                const int key_prev = __shfl_up_sync(0xffffffffu, key, 1);
+                const bool head = (lane == 0) || (key_prev != key);
+#pragma unroll
+                for (int b = 0; b < B; ++b) {
+                    const uint32_t raw = (b < 16) ? v[b & 15] : (b < 32) ? v2[b & 15] : v3[b & 15];
+                    float y = fmaxf(__uint_as_float(raw) + bias2[b], 0.f);
+                    unsigned long long pk =
+                        ((unsigned long long)(__float_as_uint(y) & 0x7fffffffu) << 32) | (unsigned)ij.y;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        unsigned long long other = __shfl_down_sync(0xffffffffu, pk, o);
+                        int okey = __shfl_down_sync(0xffffffffu, key, o);
+                        if (lane + o < 32 && okey == key && other > pk) pk = other;
+                    }
+                    if (head && key >= 0) atomicMax(&packed[(int64_t)key * B + b], pk);
+                }
+            }
+        }
+    } else {
+        // ======================= EPI1 warps: D1 -> ReLU -> bf16 -> H =======================
+        const int grp = (warp - 5) >> 2;               // 0: even chunks (buffer 0), 1: odd chunks (buffer 1)
+        const int quad = warp & 3;
+        const int row = (quad << 5) | lane;
+        const uint32_t lane_base = (uint32_t)(quad << 5) << 16;
+        const int64_t n_chunks = my_tiles * NCHUNK;
+        int64_t use = 0;
+        for (int64_t g = grp; g < n_chunks; g += 2, ++use) {
+            mbar_wait(&d1_full[grp], (uint32_t)(use & 1));
+            mbar_wait(&h_free[grp], (uint32_t)((use & 1) ^ 1));
+            tc_fence_after();
+#pragma unroll
+            for (int blk = 0; blk < 4; ++blk) {
+                uint32_t v[32];
+                tmem_ld32(tmem + lane_base + C::TM_D1 + grp * 128 + blk * 32, v);
+                tmem_wait_ld();
+                uint32_t p[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) p[e] = relu_pack(v[2 * e + 1], v[2 * e]);
+                if (TS) {
+                    tmem_st16(tmem + lane_base + C::TM_H + grp * 64 + blk * 16, p);
+                } else {
+                    uint8_t* hs = smem + C::HS + grp * (TILE * 256) + (blk >> 1) * 16384;
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc)
+                        *reinterpret_cast<uint4*>(hs + swz(row, (blk & 1) * 4 + cc)) =
+                            make_uint4(p[4 * cc], p[4 * cc + 1], p[4 * cc + 2], p[4 * cc + 3]);
+                }
+            }
+            if (TS) tmem_wait_st(); else fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(&d1_free[grp]);
+            mbar_arrive(&h_ready[grp]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+    }
+}
+
+template <int H, int B, int N2, bool TS>
+static int launch_tc(const __nv_bfloat16* hb, const float* pos, const int32_t* ped_start, const int64_t* pair_off,
+                     const int32_t* tile_first, int64_t n_tiles, int batch, int64_t n_pairs, const __nv_bfloat16* W1p,
+                     const __nv_bfloat16* W2p, const float* b2, unsigned long long* packed, cudaStream_t st) {
+    using C = TcCfg<H, N2, TS>;
+    auto kern = pool_tc_kernel<H, B, N2, TS>;
+    SGX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
+    int dev = 0, sms = 148;
+    SGX_CUDA(cudaGetDevice(&dev));
+    SGX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    unsigned grid = (unsigned)std::min<int64_t>(n_tiles, sms);
+    cudaEvent_t ev0, ev1;
+    profile_events(&ev0, &ev1);
+    if (ev0 && ev1) SGX_CUDA(cudaEventRecord(ev0, st));
+    kern<<<grid, NTHREADS, C::TOTAL, st>>>(hb, pos, ped_start, pair_off, tile_first, n_tiles, batch, n_pairs, W1p, W2p,
+                                           b2, packed);
+    SGX_LAUNCH_CHECK();
+    if (ev0 && ev1) SGX_CUDA(cudaEventRecord(ev1, st));
+    return SGX_OK;
+}
+
+__global__ void pool_prep_kernel(const float* __restrict__ We, const float* __restrict__ be,
+                                 const float* __restrict__ W1, const float* __restrict__ b1, int E, int H,
+                                 float2* __restrict__ Aeff, float* __restrict__ c0);
+
+}  // namespace sgx
+
+using namespace sgx;
+
+static int n2_for(int B) { return B <= 16 ? 16 : 48; }
+
+int64_t sgx_pool_bf16_ws_bytes(int64_t batch, int E, int H, int B) {
+    (void)E;
+    return align_up(batch * H * 2, 256) + align_up(HID * 128, 256) + align_up(8 * n2_for(B) * 128, 256) +
+           align_up(HID * 8, 256) + align_up(HID * 4, 256);
+}
+
+extern "C" int sgx_has_tcgen05(void) { return 1; }
+
+int sgx_pool_fwd_bf16(const float* h, const float* pos, const int32_t* ped_start, const int64_t* pair_off,
+                      const int32_t* tile_first, int64_t batch, int64_t n_pairs, const float* We, const float* be,
+                      const float* W1, const float* b1, const float* W2, const float* b2, int E, int H, int B,
+                      unsigned long long* packed, void* ws, int64_t ws_bytes, cudaStream_t st) {
+    SGX_UNSUPPORTED(!((H == 32 && B == 8) || (H == 48 && B == 48)),
+                    "bf16 tensor-core pooling is built for (h_dim, bottleneck) in {(32,8), (48,48)}; got (%d,%d) -- "
+                    "use precision fp32", H, B);
+    SGX_REQUIRE(ws_bytes >= sgx_pool_bf16_ws_bytes(batch, E, H, B), "sgx_pool_fwd_bf16: workspace too small");
+    SGX_REQUIRE(n_pairs < ((int64_t)1 << 40), "sgx_pool_fwd_bf16: too many pairs");
+    const int N2 = n2_for(B);
+    Carver c(ws);
+    __nv_bfloat16* hb = c.take<__nv_bfloat16>(batch * H);
+    __nv_bfloat16* W1p = c.take<__nv_bfloat16>(HID * 64);
+    __nv_bfloat16* W2p = c.take<__nv_bfloat16>(8 * N2 * 64);
+    float2* Aeff = c.take<float2>(HID);
+    float* c0 = c.take<float>(HID);
+    pool_prep_kernel<<<2, 256, 0, st>>>(We, be, W1, b1, E, H, Aeff, c0);
+    SGX_LAUNCH_CHECK();
+    tc_prep_w_kernel<<<blocks_for(HID * 64, 256), 256, 0, st>>>(Aeff, c0, W1, W2, E, H, B, N2, W1p, W2p);
+    SGX_LAUNCH_CHECK();
+    tc_prep_h_kernel<<<blocks_for(batch * H, 256), 256, 0, st>>>(h, batch * H, hb);
+    SGX_LAUNCH_CHECK();
+    const int64_t n_tiles = (n_pairs + TILE - 1) / TILE;
+    const char* mode = getenv("SGX_POOL_TC_MODE");
+    const bool ss = mode && mode[0] == 's';
+    if (H == 32) {
+        if (ss) return launch_tc<32, 8, 16, false>(hb, pos, ped_start, pair_off, tile_first, n_tiles, (int)batch, n_pairs,
+                                                   W1p, W2p, b2, packed, st);
+        return launch_tc<32, 8, 16, true>(hb, pos, ped_start, pair_off, tile_first, n_tiles, (int)batch, n_pairs, W1p,
+                                          W2p, b2, packed, st);
+    }
+    return launch_tc<48, 48, 48, true>(hb, pos, ped_start, pair_off, tile_first, n_tiles, (int)batch, n_pairs, W1p, W2p,
+                                       b2, packed, st);
+}
