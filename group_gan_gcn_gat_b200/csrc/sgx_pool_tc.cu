@@ -17,9 +17,11 @@
 //   EPI2   TMEM -> registers, + b2, ReLU, segmented warp max over rows that share i, one 64-bit
 //          atomicMax (value bits << 32 | j) per (segment, channel) into the packed output.
 // Weights are pre-swizzled bf16 images (SWIZZLE_128B, K-major) loaded once per persistent CTA with the
-// bulk-copy engine (cp.async.bulk + mbarrier complete_tx).  One CTA per SM, 13 warps:
-//   warp 0      MMA issuer (one elected lane)            warps 1-4   build X tiles / final epilogue
-//   warps 5-8   EPI1 for even hidden chunks              warps 9-12  EPI1 for odd hidden chunks
+// bulk-copy engine (cp.async.bulk + mbarrier complete_tx).  One CTA per SM, 17 warps:
+//   warp 0       MMA issuer (one elected lane)
+//   warps 1-4    row warps, set 0: build X for even tiles of this CTA, EPI2 for the same tiles
+//   warps 5-8    row warps, set 1: odd tiles (two tile builds in flight hide the dependent-load chain)
+//   warps 9-12   EPI1 for even hidden chunks (TMEM D1 buffer 0)   warps 13-16  EPI1 for odd chunks (buffer 1)
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
@@ -30,16 +32,28 @@ namespace sgx {
 constexpr int HID = SGX_POOL_HIDDEN;
 constexpr int TILE = 128;        // pairs per tile = UMMA M
 constexpr int NCHUNK = 4;        // hidden chunks of 128
-constexpr int NST = 3;           // X-tile smem stages
+constexpr int NST = 4;           // X-tile smem stages (row-warp set s owns stages s and s+2)
 constexpr int NMETA = 4;         // ring of per-tile (i,j) metadata
-constexpr int LOOKAHEAD = 2;     // tiles built ahead of the final epilogue
-constexpr int NTHREADS = 13 * 32;
+constexpr int NTHREADS = 18 * 32;
+constexpr int SLICE = 136;       // per-tile slice of pair_off / ped_start staged in smem for the pair decode
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// true for exactly one lane of the (converged) warp -- the form ptxas recognises for single-thread UTCHMMA issue
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 rx;\n\t"
+        ".reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, px;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -60,6 +74,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "WAIT_DONE:\n\t"
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+#ifdef SGX_TC_STATS
+#define TWAIT(bar, par, slot) do { long long t0__ = clock64(); mbar_wait(bar, par); stats_[slot] += clock64() - t0__; } while (0)
+#else
+#define TWAIT(bar, par, slot) mbar_wait(bar, par)
+#endif
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -112,6 +131,15 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(
             taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
         "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"
+        "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+        "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]),
+        "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]),
+        "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -202,22 +230,34 @@ struct TcCfg {
     static constexpr int HS = TcSmem::W2P + W2P_BYTES;             // "ss" mode: 2 x 32 KB hidden staging
     static constexpr int HS_BYTES = TS ? 0 : 2 * TILE * 256;
     static constexpr int META = HS + HS_BYTES;                     // int2 [NMETA][128]
-    static constexpr int BARS = META + NMETA * TILE * 8;
+    static constexpr int SOFF = META + NMETA * TILE * 8;           // int64 [2][SLICE]
+    static constexpr int SPS = SOFF + 2 * SLICE * 8;               // int32 [2][SLICE]
+    static constexpr int BARS = SPS + 2 * SLICE * 4;
     static constexpr int TOTAL = BARS + 256 + 1024;                // + alignment slack
-    static constexpr int D2_STRIDE = (N2 <= 32) ? 32 : 64;         // TMEM columns per D2 buffer
+    static constexpr int NACC = (N2 <= 16) ? 4 : 1;                // independent GEMM2 accumulators (breaks the
+                                                                   // dependent-accumulate chain of the small-N MMAs)
+    static constexpr int D2_STRIDE = 64;                           // TMEM columns per D2 buffer
     static constexpr int TM_D1 = 0, TM_H = 256, TM_D2 = 384;
 };
 
+// warp roles (18 warps): 0-3 row set 0, 4-7 row set 1, 8-11 EPI1 even chunks, 12-15 EPI1 odd chunks,
+// 16 GEMM1 issuer, 17 GEMM2 issuer.  Two issuer threads because a single thread issuing 44 small MMAs per tile
+// (each ~15 SASS instructions of descriptor set-up on the uniform datapath) was the measured bottleneck.
 template <int H, int B, int N2, bool TS>
 __global__ void __launch_bounds__(NTHREADS, 1)
 pool_tc_kernel(const __nv_bfloat16* __restrict__ hb, const float* __restrict__ pos,
                const int32_t* __restrict__ ped_start, const int64_t* __restrict__ pair_off,
                const int32_t* __restrict__ tile_first, int64_t n_tiles, int batch, int64_t n_pairs,
                const __nv_bfloat16* __restrict__ W1p, const __nv_bfloat16* __restrict__ W2p,
-               const float* __restrict__ b2, unsigned long long* __restrict__ packed) {
+               const float* __restrict__ b2, unsigned long long* __restrict__ packed, int dbg,
+               long long* __restrict__ stats_out) {
     using C = TcCfg<H, N2, TS>;
+    long long stats_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long t_begin_ = clock64();
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // align inside the 32-bit shared window so every derived address stays warp-uniform for the compiler
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (sbase - smem_u32(smem_raw));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BARS);
     uint64_t* w_full = bars + 0;
     uint64_t* x_full = bars + 1;             // [NST]
@@ -232,7 +272,7 @@ pool_tc_kernel(const __nv_bfloat16* __restrict__ hb, const float* __restrict__ p
     int2* meta = reinterpret_cast<int2*>(smem + C::META);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int my_tiles = (n_tiles > blockIdx.x) ? (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
 
     if (threadIdx.x == 0) {
         mbar_init(w_full, 1);
@@ -244,188 +284,262 @@ pool_tc_kernel(const __nv_bfloat16* __restrict__ hb, const float* __restrict__ p
         }
         fence_barrier_init();
     }
-    if (warp == 0) {   // TMEM: all 512 columns (one CTA per SM)
+    if (warp == 16) {   // TMEM: all 512 columns (one CTA per SM) => the allocation starts at lane 0 / column 0
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
+    if (*tmem_slot != 0u) __trap();      // TMEM addresses below are compile-time constants relative to base 0
+    constexpr uint32_t tmem = 0u;
 
-    if (warp == 0) {
-        // ======================= MMA issuer =======================
+    if (warp == 16) {
+        // ======================= GEMM1 issuer =======================
         if (lane == 0) {
             mbar_expect_tx(w_full, HID * 128 + C::W2P_BYTES);
             bulk_g2s(smem + TcSmem::W1P, W1p, HID * 128, w_full);
             bulk_g2s(smem + TcSmem::W2P, W2p, C::W2P_BYTES, w_full);
-            mbar_wait(w_full, 0);
-            constexpr uint32_t idesc1 = make_idesc(128, 128), idesc2 = make_idesc(128, N2);
-            const uint32_t w1_s = smem_u32(smem + TcSmem::W1P), w2_s = smem_u32(smem + TcSmem::W2P);
-            const uint32_t x_s = smem_u32(smem + TcSmem::X), hs_s = smem_u32(smem + C::HS);
-            const int64_t n_chunks = my_tiles * NCHUNK;
-            for (int64_t g = 0; g <= n_chunks; ++g) {
-                if (g < n_chunks) {   // ---- GEMM1 of chunk g ----
-                    const int64_t t = g / NCHUNK;
-                    const int c = (int)(g % NCHUNK), st = (int)(t % NST), buf = (int)(g & 1);
-                    if (c == 0) mbar_wait(&x_full[st], (uint32_t)((t / NST) & 1));
-                    mbar_wait(&d1_free[buf], (uint32_t)(((g >> 1) & 1) ^ 1));
-                    tc_fence_after();
-                    const uint32_t d1 = tmem + C::TM_D1 + buf * 128;
+        }
+        mbar_wait(w_full, 0);
+        constexpr uint32_t idesc1 = make_idesc(128, 128);
+        const uint64_t w1_d = make_desc(sbase + TcSmem::W1P), x_d = make_desc(sbase + TcSmem::X);
+        for (int t = 0; t < my_tiles; ++t) {
+            const int st = t & (NST - 1);
+            TWAIT(&x_full[st], (uint32_t)((t / NST) & 1), 0);
+            const uint64_t xa = x_d + (uint64_t)(st * (TILE * 128 / 16));
+#pragma unroll
+            for (int c = 0; c < NCHUNK; ++c) {
+                TWAIT(&d1_free[c & 1], (uint32_t)(((c >> 1) & 1) ^ 1), 1);
+                tc_fence_after();
+                if (elect_one()) {
 #pragma unroll
                     for (int kc = 0; kc < C::KCH; ++kc)
-                        mma_ss(d1, make_desc(x_s + st * TILE * 128 + kc * 32), make_desc(w1_s + c * 16384 + kc * 32),
-                               idesc1, kc > 0);
-                    tc_commit(&d1_full[buf]);
+                        mma_ss(tmem + C::TM_D1 + (c & 1) * 128, xa + kc * 2, w1_d + (c * 16384 + kc * 32) / 16, idesc1, kc > 0);
+                    tc_commit(&d1_full[c & 1]);
                     if (c == NCHUNK - 1) tc_commit(&x_free[st]);
                 }
-                if (g > 0) {          // ---- GEMM2 of chunk g-1 ----
-                    const int64_t gp = g - 1, t = gp / NCHUNK;
-                    const int c = (int)(gp % NCHUNK), buf = (int)(gp & 1), db = (int)(t & 1);
-                    if (c == 0) mbar_wait(&d2_free[db], (uint32_t)(((t >> 1) & 1) ^ 1));
-                    mbar_wait(&h_ready[buf], (uint32_t)((gp >> 1) & 1));
-                    tc_fence_after();
-                    const uint32_t d2 = tmem + C::TM_D2 + db * C::D2_STRIDE;
-#pragma unroll
-                    for (int kk = 0; kk < 8; ++kk) {
-                        const uint64_t bd = make_desc(w2_s + (c * 2 + (kk >> 2)) * (N2 * 128) + (kk & 3) * 32);
-                        if (TS)
-                            mma_ts(d2, tmem + C::TM_H + buf * 64 + kk * 8, bd, idesc2, (c > 0 || kk > 0));
-                        else
-                            mma_ss(d2, make_desc(hs_s + buf * (TILE * 256) + (kk >> 2) * 16384 + (kk & 3) * 32), bd,
-                                   idesc2, (c > 0 || kk > 0));
-                    }
-                    tc_commit(&h_free[buf]);
-                    if (c == NCHUNK - 1) tc_commit(&d2_full[db]);
-                }
+                __syncwarp();
             }
         }
-        __syncwarp();
-    } else if (warp <= 4) {
+    } else if (warp == 17) {
+        // ======================= GEMM2 issuer =======================
+        mbar_wait(w_full, 0);
+        constexpr uint32_t idesc2 = make_idesc(128, N2);
+        const uint64_t w2_d = make_desc(sbase + TcSmem::W2P), hs_d = make_desc(sbase + C::HS);
+        for (int t = 0; t < my_tiles; ++t) {
+            const int db = t & 1;
+            TWAIT(&d2_free[db], (uint32_t)(((t >> 1) & 1) ^ 1), 2);
+            const uint32_t d2 = tmem + C::TM_D2 + db * C::D2_STRIDE;
+#pragma unroll
+            for (int c = 0; c < NCHUNK; ++c) {
+                TWAIT(&h_ready[c & 1], (uint32_t)((c >> 1) & 1), 3);
+                tc_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) {
+                        const uint64_t bd = w2_d + ((c * 2 + (kk >> 2)) * (N2 * 128) + (kk & 3) * 32) / 16;
+                        const uint32_t d2k = d2 + (kk % C::NACC) * N2;
+                        const uint32_t accf = (c > 0 || kk >= C::NACC);
+                        if (TS)
+                            mma_ts(d2k, tmem + C::TM_H + (c & 1) * 64 + kk * 8, bd, idesc2, accf);
+                        else
+                            mma_ss(d2k, hs_d + ((c & 1) * (TILE * 256) + (kk >> 2) * 16384 + (kk & 3) * 32) / 16, bd, idesc2, accf);
+                    }
+                    tc_commit(&h_free[c & 1]);
+                    if (c == NCHUNK - 1) tc_commit(&d2_full[db]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp < 8) {
         // ======================= row warps: build X tiles, final epilogue =======================
-        const int row = ((warp & 3) << 5) | lane;    // TMEM lane quadrant = warp % 4
+        const int set = warp >> 2;                   // set s handles this CTA's tiles it = 2k + s
+        const int rt = (warp & 3) * 32 + lane;       // thread index inside the set (0..127)
+        const int row = rt;                          // tile row == TMEM lane (quadrant = warp % 4)
+        int64_t* soff = reinterpret_cast<int64_t*>(smem + C::SOFF) + set * SLICE;
+        int32_t* sps = reinterpret_cast<int32_t*>(smem + C::SPS) + set * SLICE;
         float bias2[B];
 #pragma unroll
         for (int b = 0; b < B; ++b) bias2[b] = b2[b];
-        for (int64_t it = 0; it < my_tiles + LOOKAHEAD; ++it) {
+        for (int it = set; it < my_tiles + 2; it += 2) {
             if (it < my_tiles) {
-                const int64_t tile = blockIdx.x + it * gridDim.x;
-                const int st = (int)(it % NST);
-                mbar_wait(&x_free[st], (uint32_t)(((it / NST) & 1) ^ 1));
+                const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
+                const int st = it & (NST - 1);
+                // ---- stage this tile's slice of the ped tables (coalesced), decode (i,j) from shared memory ----
+                const int lo = tile_first[tile];
+                const int hi = (tile + 1 < n_tiles) ? tile_first[tile + 1] : batch - 1;   // hi - lo <= 128
+                if (lo + rt <= hi) { soff[rt] = pair_off[lo + rt]; sps[rt] = ped_start[lo + rt]; }
+                if (rt == 0 && lo + 128 <= hi) { soff[128] = pair_off[lo + 128]; sps[128] = ped_start[lo + 128]; }
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");
                 const int64_t q = tile * TILE + row;
                 uint8_t* xrow = smem + TcSmem::X + st * TILE * 128;
                 int2 ij = make_int2(-1, 0);
-                uint4 c0 = make_uint4(0, 0, 0, 0);
-                if (q < n_pairs) {
-                    const int lo = tile_first[tile];
-                    const int hi = (tile + 1 < n_tiles) ? tile_first[tile + 1] : batch - 1;
-                    const int i = find_ped_tc(pair_off, lo, hi, q);
-                    const int j = ped_start[i] + (int)(q - pair_off[i]);
+                float2 pi = make_float2(0.f, 0.f), pj = make_float2(0.f, 0.f);
+                uint4 hv[H / 8];
+#pragma unroll
+                for (int c = 0; c < H / 8; ++c) hv[c] = make_uint4(0, 0, 0, 0);
+                const bool valid = q < n_pairs;
+                if (valid) {
+                    int a = 0, z = hi - lo;
+                    while (a < z) {
+                        int mid = (a + z + 1) >> 1;
+                        if (soff[mid] <= q) a = mid; else z = mid - 1;
+                    }
+                    const int i = lo + a;
+                    const int j = sps[a] + (int)(q - soff[a]);
                     ij = make_int2(i, j);
-                    const float dx = pos[2 * j] - pos[2 * i], dy = pos[2 * j + 1] - pos[2 * i + 1];
+                    pi = *reinterpret_cast<const float2*>(pos + 2 * (int64_t)i);
+                    pj = *reinterpret_cast<const float2*>(pos + 2 * (int64_t)j);
+                    const uint4* hrow = reinterpret_cast<const uint4*>(hb + (int64_t)j * H);
+#pragma unroll
+                    for (int c = 0; c < H / 8; ++c) hv[c] = hrow[c];
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");   // slice may be overwritten next round
+                TWAIT(&x_free[st], (uint32_t)(((it / NST) & 1) ^ 1), 0);
+                uint4 c0 = make_uint4(0, 0, 0, 0);
+                if (valid) {
+                    const float dx = pj.x - pi.x, dy = pj.y - pi.y;
                     const float dxh = __bfloat162float(__float2bfloat16_rn(dx)), dyh = __bfloat162float(__float2bfloat16_rn(dy));
                     c0.x = pack_bf16(dxh, dx - dxh);       // slots 0,1
                     c0.y = pack_bf16(dxh, dyh);            // slots 2,3
                     c0.z = pack_bf16(dy - dyh, dyh);       // slots 4,5
                     c0.w = pack_bf16(1.f, 1.f);            // slots 6,7
-                    const uint4* hrow = reinterpret_cast<const uint4*>(hb + (int64_t)j * H);
-#pragma unroll
-                    for (int c = 0; c < H / 8; ++c)
-                        *reinterpret_cast<uint4*>(xrow + swz(row, 2 + c)) = hrow[c];
-                } else {
-#pragma unroll
-                    for (int c = 0; c < H / 8; ++c)
-                        *reinterpret_cast<uint4*>(xrow + swz(row, 2 + c)) = make_uint4(0, 0, 0, 0);
                 }
                 *reinterpret_cast<uint4*>(xrow + swz(row, 0)) = c0;
                 *reinterpret_cast<uint4*>(xrow + swz(row, 1)) = make_uint4(0, 0, 0, 0);
-                meta[(it % NMETA) * TILE + row] = ij;
+#pragma unroll
+                for (int c = 0; c < H / 8; ++c) *reinterpret_cast<uint4*>(xrow + swz(row, 2 + c)) = hv[c];
+                meta[(it & (NMETA - 1)) * TILE + row] = ij;
                 fence_proxy_async();
                 mbar_arrive(&x_full[st]);
             }
-            if (it >= LOOKAHEAD) {
-                const int64_t t = it - LOOKAHEAD;
-                const int db = (int)(t & 1);
-                mbar_wait(&d2_full[db], (uint32_t)((t >> 1) & 1));
+            if (it >= 2) {
+                const int t = it - 2;                // the previous tile of this set; D2 buffer = t & 1 = set
+                const int db = set;
+                TWAIT(&d2_full[db], (uint32_t)((t >> 1) & 1), 1);
                 tc_fence_after();
-                uint32_t v[16];
-                tmem_ld16(tmem + ((uint32_t)((warp & 3) << 5) << 16) + C::TM_D2 + db * C::D2_STRIDE, v);
-                uint32_t v2[16], v3[16];
-                if (B > 16) {
-                    tmem_ld16(tmem + ((uint32_t)((warp & 3) << 5) << 16) + C::TM_D2 + db * C::D2_STRIDE + 16, v2);
-                    tmem_ld16(tmem + ((uint32_t)((warp & 3) << 5) << 16) + C::TM_D2 + db * C::D2_STRIDE + 32, v3);
+                const uint32_t d2a = tmem + ((uint32_t)((warp & 3) << 5) << 16) + C::TM_D2 + db * C::D2_STRIDE;
+                uint32_t v[16], v2[16], v3[16];
+                tmem_ld16(d2a, v);
+                if (B > 16) { tmem_ld16(d2a + 16, v2); tmem_ld16(d2a + 32, v3); }
+                if (C::NACC == 4) {       // B <= 16: four partial accumulators of 16 columns each
+                    tmem_ld16(d2a + 16, v2);
+                    tmem_ld16(d2a + 32, v3);
+                    uint32_t v4[16];
+                    tmem_ld16(d2a + 48, v4);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int b = 0; b < 16; ++b)
+                        v[b] = __float_as_uint((__uint_as_float(v[b]) + __uint_as_float(v2[b])) +
+                                               (__uint_as_float(v3[b]) + __uint_as_float(v4[b])));
                 }
                 tmem_wait_ld();
                 tc_fence_before();
                 mbar_arrive(&d2_free[db]);
-                const int2 ij = meta[(t % NMETA) * TILE + row];
+                const int2 ij = meta[(t & (NMETA - 1)) * TILE + row];
                 const int key = ij.x;
                 const int key_prev = __shfl_up_sync(0xffffffffu, key, 1);
                 const bool head = (lane == 0) || (key_prev != key);
+                const bool uniform = __all_sync(0xffffffffu, key == __shfl_sync(0xffffffffu, key, 0));
 #pragma unroll
                 for (int b = 0; b < B; ++b) {
                     const uint32_t raw = (b < 16) ? v[b & 15] : (b < 32) ? v2[b & 15] : v3[b & 15];
-                    float y = fmaxf(__uint_as_float(raw) + bias2[b], 0.f);
-                    unsigned long long pk =
-                        ((unsigned long long)(__float_as_uint(y) & 0x7fffffffu) << 32) | (unsigned)ij.y;
+                    const float y = fmaxf(__uint_as_float(raw) + bias2[b], 0.f);
+                    const uint32_t bits = __float_as_uint(y) & 0x7fffffffu;
+                    if (uniform) {
+                        // the whole warp belongs to one pedestrian i (dense crowd): one REDUX + one atomic
+                        const uint32_t mx = __reduce_max_sync(0xffffffffu, bits);
+                        const uint32_t who = __ballot_sync(0xffffffffu, bits == mx);
+                        const int src = 31 - __clz(who);                       // ties -> larger j
+                        const int jj = __shfl_sync(0xffffffffu, ij.y, src);
+                        if (lane == 0 && key >= 0)
+                            atomicMax(&packed[(int64_t)key * B + b], ((unsigned long long)mx << 32) | (unsigned)jj);
+                    } else {
+                        unsigned long long pk = ((unsigned long long)bits << 32) | (unsigned)ij.y;
 #pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        unsigned long long other = __shfl_down_sync(0xffffffffu, pk, o);
-                        int okey = __shfl_down_sync(0xffffffffu, key, o);
-                        if (lane + o < 32 && okey == key && other > pk) pk = other;
+                        for (int o = 1; o < 32; o <<= 1) {
+                            unsigned long long other = __shfl_down_sync(0xffffffffu, pk, o);
+                            int okey = __shfl_down_sync(0xffffffffu, key, o);
+                            if (lane + o < 32 && okey == key && other > pk) pk = other;
+                        }
+                        if (head && key >= 0) atomicMax(&packed[(int64_t)key * B + b], pk);
                     }
-                    if (head && key >= 0) atomicMax(&packed[(int64_t)key * B + b], pk);
                 }
             }
         }
     } else {
         // ======================= EPI1 warps: D1 -> ReLU -> bf16 -> H =======================
-        const int grp = (warp - 5) >> 2;               // 0: even chunks (buffer 0), 1: odd chunks (buffer 1)
+        const int grp = (warp - 8) >> 2;               // 0: even chunks (buffer 0), 1: odd chunks (buffer 1)
         const int quad = warp & 3;
         const int row = (quad << 5) | lane;
         const uint32_t lane_base = (uint32_t)(quad << 5) << 16;
-        const int64_t n_chunks = my_tiles * NCHUNK;
-        int64_t use = 0;
-        for (int64_t g = grp; g < n_chunks; g += 2, ++use) {
-            mbar_wait(&d1_full[grp], (uint32_t)(use & 1));
-            mbar_wait(&h_free[grp], (uint32_t)((use & 1) ^ 1));
+        const int n_chunks = my_tiles * NCHUNK;
+        int use = 0;
+        for (int g = grp; g < n_chunks; g += 2, ++use) {
+            TWAIT(&d1_full[grp], (uint32_t)(use & 1), 0);
             tc_fence_after();
+            const uint32_t d1a = tmem + lane_base + C::TM_D1 + grp * 128;
 #pragma unroll
-            for (int blk = 0; blk < 4; ++blk) {
-                uint32_t v[32];
-                tmem_ld32(tmem + lane_base + C::TM_D1 + grp * 128 + blk * 32, v);
+            for (int half = 0; half < 2; ++half) {
+                uint32_t va[32], vb[32];
+                tmem_ld32(d1a + half * 64, va);
+                tmem_ld32(d1a + half * 64 + 32, vb);
                 tmem_wait_ld();
-                uint32_t p[16];
+                if (half == 1) {          // all of D1 has been read: the GEMM1 issuer may overwrite this accumulator
+                    tc_fence_before();
+                    mbar_arrive(&d1_free[grp]);
+                }
+                uint32_t p[32];
 #pragma unroll
-                for (int e = 0; e < 16; ++e) p[e] = relu_pack(v[2 * e + 1], v[2 * e]);
+                for (int e = 0; e < 16; ++e) {
+                    p[e] = relu_pack(va[2 * e + 1], va[2 * e]);
+                    p[16 + e] = relu_pack(vb[2 * e + 1], vb[2 * e]);
+                }
+                if (half == 0) {          // GEMM2 of chunk g-2 must have consumed this H buffer
+                    TWAIT(&h_free[grp], (uint32_t)((use & 1) ^ 1), 1);
+                    tc_fence_after();
+                }
                 if (TS) {
-                    tmem_st16(tmem + lane_base + C::TM_H + grp * 64 + blk * 16, p);
+                    tmem_st32(tmem + lane_base + C::TM_H + grp * 64 + half * 32, p);
                 } else {
-                    uint8_t* hs = smem + C::HS + grp * (TILE * 256) + (blk >> 1) * 16384;
+                    uint8_t* hs = smem + C::HS + grp * (TILE * 256) + half * 16384;
 #pragma unroll
-                    for (int cc = 0; cc < 4; ++cc)
-                        *reinterpret_cast<uint4*>(hs + swz(row, (blk & 1) * 4 + cc)) =
+                    for (int cc = 0; cc < 8; ++cc)
+                        *reinterpret_cast<uint4*>(hs + swz(row, cc)) =
                             make_uint4(p[4 * cc], p[4 * cc + 1], p[4 * cc + 2], p[4 * cc + 3]);
                 }
             }
             if (TS) tmem_wait_st(); else fence_proxy_async();
             tc_fence_before();
-            mbar_arrive(&d1_free[grp]);
             mbar_arrive(&h_ready[grp]);
         }
     }
+#ifdef SGX_TC_STATS
+    if (stats_out && blockIdx.x == 0 && lane == 0 && (warp == 16 || warp == 17 || warp == 0 || warp == 8 || warp == 12)) {
+        const int role = warp == 16 ? 0 : warp == 17 ? 1 : warp == 0 ? 2 : warp == 8 ? 3 : 4;
+        for (int k = 0; k < 4; ++k) stats_out[role * 8 + k] = stats_[k];
+        stats_out[role * 8 + 4] = clock64() - t_begin_;
+        stats_out[role * 8 + 5] = my_tiles;
+    }
+#endif
+    (void)dbg; (void)stats_out; (void)t_begin_; (void)stats_;
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) {
+    if (warp == 16) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
     }
 }
 
+long long* g_tc_stats = nullptr;   // debug: device buffer of 40 long longs (SGX_TC_STATS builds)
+
 template <int H, int B, int N2, bool TS>
 static int launch_tc(const __nv_bfloat16* hb, const float* pos, const int32_t* ped_start, const int64_t* pair_off,
                      const int32_t* tile_first, int64_t n_tiles, int batch, int64_t n_pairs, const __nv_bfloat16* W1p,
                      const __nv_bfloat16* W2p, const float* b2, unsigned long long* packed, cudaStream_t st) {
+    const char* dbg_s = getenv("SGX_POOL_TC_DBG");
+    const int dbg = dbg_s ? atoi(dbg_s) : 0;
     using C = TcCfg<H, N2, TS>;
     auto kern = pool_tc_kernel<H, B, N2, TS>;
     SGX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
@@ -437,7 +551,7 @@ static int launch_tc(const __nv_bfloat16* hb, const float* pos, const int32_t* p
     profile_events(&ev0, &ev1);
     if (ev0 && ev1) SGX_CUDA(cudaEventRecord(ev0, st));
     kern<<<grid, NTHREADS, C::TOTAL, st>>>(hb, pos, ped_start, pair_off, tile_first, n_tiles, batch, n_pairs, W1p, W2p,
-                                           b2, packed);
+                                           b2, packed, dbg, g_tc_stats);
     SGX_LAUNCH_CHECK();
     if (ev0 && ev1) SGX_CUDA(cudaEventRecord(ev1, st));
     return SGX_OK;
@@ -460,6 +574,7 @@ int64_t sgx_pool_bf16_ws_bytes(int64_t batch, int E, int H, int B) {
 }
 
 extern "C" int sgx_has_tcgen05(void) { return 1; }
+extern "C" void sgx_debug_tc_stats(void* dev_buf) { sgx::g_tc_stats = (long long*)dev_buf; }
 
 int sgx_pool_fwd_bf16(const float* h, const float* pos, const int32_t* ped_start, const int64_t* pair_off,
                       const int32_t* tile_first, int64_t batch, int64_t n_pairs, const float* We, const float* be,

@@ -1,0 +1,19 @@
+import ctypes, os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from group_gan_gcn_gat_b200 import _lib
+from tools.time_pool import time_case
+L = _lib.lib()
+buf = torch.zeros(40, dtype=torch.int64, device='cuda')
+h = ctypes.CDLL(_lib.LIB_PATH)
+h.sgx_debug_tc_stats.argtypes = [ctypes.c_void_p]
+h.sgx_debug_tc_stats(buf.data_ptr())
+for dbg in (0, 15):
+    os.environ['SGX_POOL_TC_DBG'] = str(dbg)
+    time_case([1024] * 8, (16, 32, 8), 'bf16', reps=3)
+    torch.cuda.synchronize()
+    s = buf.cpu().view(5, 8)
+    names = ['MMA  (x_full, d1_free, d2_free, h_ready)', 'ROW0 (x_free, d2_full)', 'ROW1 (x_free, d2_full)', 'EPI0 (d1_full, h_free)', 'EPI1 (d1_full, h_free)']
+    for r in range(5):
+        n = max(1, int(s[r, 5]))
+        print('dbg', dbg, names[r], 'per-tile wait cycles:', [int(v) // n for v in s[r, :4]], 'total/tile:', int(s[r, 4]) // n, 'tiles', n)
