@@ -1,0 +1,225 @@
+// Fused per-pedestrian LSTM recurrences of the generator / discriminator.
+//
+// Reference: Encoder.forward (sgan/models.py:62-92): Linear(2,E) + single-layer LSTM over obs_len steps;
+//            Decoder.forward (sgan/models.py:142-178) with pool_every_timestep = 0: per step LSTM cell ->
+//            hidden2pos -> spatial_embedding of the predicted displacement -> next step.
+// In both, every pedestrian's recurrence is independent of every other pedestrian, so the whole
+// T-step loop runs in ONE kernel with one thread per pedestrian: h in registers, c / h_next in shared
+// memory columns, W_hh (4H x H, 16 KB for H = 32) broadcast from shared memory as 128-bit loads.  The
+// embedding is folded into the input weights exactly:  W_ih (We d + be) = (W_ih We) d + W_ih be.
+// The reference issues one cuDNN call (plus ~6 small kernels) per decoder step; on the bench workload
+// cuDNN's persistent-RNN kernel took 3.7 ms per call (13 calls = 90 % of the generator forward).
+// Inference only: under autograd the modules keep using nn.LSTM (cuDNN) so training semantics are unchanged.
+#include "sgx_common.cuh"
+
+namespace sgx {
+
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_f(float x) {
+    // 1 - 2/(1+e^{2x}); __expf is ex2.approx (2 ulp), the subtraction is absolutely accurate to ~1e-7
+    const float e = __expf(2.f * x);
+    return 1.f - __fdividef(2.f, 1.f + e);
+}
+
+template <int H, int THREADS>
+struct LstmSmem {
+    float whh[4 * H * H];      // [4H][H]
+    float wx[4 * H * 2];       // (W_ih We) [4H][2]
+    float bx[4 * H];           // W_ih be + b_ih + b_hh
+    float c[H * THREADS];      // cell state, column per thread
+    float hn[H * THREADS];     // next hidden state, column per thread
+    float whp[2 * H + 2];      // hidden2pos (decoder only)
+};
+
+template <int H, int THREADS>
+__device__ __forceinline__ void lstm_load_weights(LstmSmem<H, THREADS>& s, const float* __restrict__ We,
+                                                  const float* __restrict__ be, const float* __restrict__ W_ih,
+                                                  const float* __restrict__ W_hh, const float* __restrict__ b_ih,
+                                                  const float* __restrict__ b_hh, int E) {
+    for (int e = threadIdx.x; e < 4 * H * H; e += THREADS) s.whh[e] = W_hh[e];
+    for (int r = threadIdx.x; r < 4 * H; r += THREADS) {
+        float ax = 0.f, ay = 0.f, b = b_ih[r] + b_hh[r];
+        for (int e = 0; e < E; ++e) {
+            const float w = W_ih[r * E + e];
+            ax = fmaf(w, We[2 * e], ax);
+            ay = fmaf(w, We[2 * e + 1], ay);
+            b = fmaf(w, be[e], b);
+        }
+        s.wx[2 * r] = ax;
+        s.wx[2 * r + 1] = ay;
+        s.bx[r] = b;
+    }
+}
+
+// one LSTM cell update for this thread's pedestrian; input is the 2-vector (dx, dy)
+template <int H, int THREADS>
+__device__ __forceinline__ void lstm_cell(LstmSmem<H, THREADS>& s, float (&h)[H], float dx, float dy) {
+    const int tid = threadIdx.x;
+#pragma unroll 1
+    for (int u = 0; u < H; ++u) {
+        float g[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int r = q * H + u;
+            float acc = fmaf(s.wx[2 * r], dx, fmaf(s.wx[2 * r + 1], dy, s.bx[r]));
+            const float4* w = reinterpret_cast<const float4*>(&s.whh[r * H]);
+#pragma unroll
+            for (int k = 0; k < H / 4; ++k) {
+                const float4 v = w[k];
+                acc = fmaf(v.x, h[4 * k], acc); acc = fmaf(v.y, h[4 * k + 1], acc);
+                acc = fmaf(v.z, h[4 * k + 2], acc); acc = fmaf(v.w, h[4 * k + 3], acc);
+            }
+            g[q] = acc;
+        }
+        const float cn = sigmoid_f(g[1]) * s.c[u * THREADS + tid] + sigmoid_f(g[0]) * tanh_f(g[2]);
+        s.c[u * THREADS + tid] = cn;
+        s.hn[u * THREADS + tid] = sigmoid_f(g[3]) * tanh_f(cn);
+    }
+#pragma unroll
+    for (int u = 0; u < H; ++u) h[u] = s.hn[u * THREADS + tid];
+}
+
+template <int H, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+lstm_encoder_kernel(const float* __restrict__ obs_rel, int T, int batch, const float* __restrict__ We,
+                    const float* __restrict__ be, const float* __restrict__ W_ih, const float* __restrict__ W_hh,
+                    const float* __restrict__ b_ih, const float* __restrict__ b_hh, int E, float* __restrict__ h_out) {
+    extern __shared__ __align__(16) uint8_t raw[];
+    LstmSmem<H, THREADS>& s = *reinterpret_cast<LstmSmem<H, THREADS>*>(raw);
+    lstm_load_weights<H, THREADS>(s, We, be, W_ih, W_hh, b_ih, b_hh, E);
+    __syncthreads();
+    const int tid = threadIdx.x;
+    for (int p0 = blockIdx.x * THREADS; p0 < batch; p0 += gridDim.x * THREADS) {
+        const int p = p0 + tid;
+        const bool live = p < batch;
+        float h[H];
+#pragma unroll
+        for (int u = 0; u < H; ++u) { h[u] = 0.f; s.c[u * THREADS + tid] = 0.f; }
+        for (int t = 0; t < T; ++t) {
+            float2 d = make_float2(0.f, 0.f);
+            if (live) d = *reinterpret_cast<const float2*>(obs_rel + ((int64_t)t * batch + p) * 2);
+            lstm_cell<H, THREADS>(s, h, d.x, d.y);
+        }
+        if (live) {
+#pragma unroll
+            for (int u = 0; u < H; u += 4)
+                *reinterpret_cast<float4*>(h_out + (int64_t)p * H + u) = make_float4(h[u], h[u + 1], h[u + 2], h[u + 3]);
+        }
+    }
+}
+
+template <int H, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+lstm_decoder_kernel(const float* __restrict__ h0, const float* __restrict__ c0, const float* __restrict__ last_pos_rel,
+                    int steps, int batch, const float* __restrict__ We, const float* __restrict__ be,
+                    const float* __restrict__ W_ih, const float* __restrict__ W_hh, const float* __restrict__ b_ih,
+                    const float* __restrict__ b_hh, const float* __restrict__ W_hp, const float* __restrict__ b_hp, int E,
+                    float* __restrict__ pred_rel, float* __restrict__ h_final, float* __restrict__ c_final) {
+    extern __shared__ __align__(16) uint8_t raw[];
+    LstmSmem<H, THREADS>& s = *reinterpret_cast<LstmSmem<H, THREADS>*>(raw);
+    lstm_load_weights<H, THREADS>(s, We, be, W_ih, W_hh, b_ih, b_hh, E);
+    for (int e = threadIdx.x; e < 2 * H; e += THREADS) s.whp[e] = W_hp[e];
+    if (threadIdx.x < 2) s.whp[2 * H + threadIdx.x] = b_hp[threadIdx.x];
+    __syncthreads();
+    const int tid = threadIdx.x;
+    for (int p0 = blockIdx.x * THREADS; p0 < batch; p0 += gridDim.x * THREADS) {
+        const int p = p0 + tid;
+        const bool live = p < batch;
+        float h[H];
+#pragma unroll
+        for (int u = 0; u < H; ++u) {
+            h[u] = live ? h0[(int64_t)p * H + u] : 0.f;
+            s.c[u * THREADS + tid] = (live && c0) ? c0[(int64_t)p * H + u] : 0.f;
+        }
+        float2 d = make_float2(0.f, 0.f);
+        if (live) d = *reinterpret_cast<const float2*>(last_pos_rel + (int64_t)p * 2);
+        for (int t = 0; t < steps; ++t) {
+            lstm_cell<H, THREADS>(s, h, d.x, d.y);
+            float rx = s.whp[2 * H], ry = s.whp[2 * H + 1];
+#pragma unroll
+            for (int u = 0; u < H; ++u) {
+                rx = fmaf(s.whp[u], h[u], rx);
+                ry = fmaf(s.whp[H + u], h[u], ry);
+            }
+            d = make_float2(rx, ry);
+            if (live) *reinterpret_cast<float2*>(pred_rel + ((int64_t)t * batch + p) * 2) = d;
+        }
+        if (live && h_final) {
+#pragma unroll
+            for (int u = 0; u < H; ++u) h_final[(int64_t)p * H + u] = h[u];
+        }
+        if (live && c_final) {
+#pragma unroll
+            for (int u = 0; u < H; ++u) c_final[(int64_t)p * H + u] = s.c[u * THREADS + tid];
+        }
+    }
+}
+
+template <int H>
+static int launch_encoder(const float* obs_rel, int T, int64_t batch, const float* We, const float* be,
+                          const float* W_ih, const float* W_hh, const float* b_ih, const float* b_hh, int E,
+                          float* h_out, cudaStream_t st) {
+    constexpr int THREADS = 128;
+    auto kern = lstm_encoder_kernel<H, THREADS>;
+    const int smem = (int)sizeof(LstmSmem<H, THREADS>);
+    SGX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    unsigned grid = (unsigned)std::min<int64_t>((batch + THREADS - 1) / THREADS, 148 * 4);
+    kern<<<grid, THREADS, smem, st>>>(obs_rel, T, (int)batch, We, be, W_ih, W_hh, b_ih, b_hh, E, h_out);
+    SGX_LAUNCH_CHECK();
+    return SGX_OK;
+}
+
+template <int H>
+static int launch_decoder(const float* h0, const float* c0, const float* last_pos_rel, int steps, int64_t batch,
+                          const float* We, const float* be, const float* W_ih, const float* W_hh, const float* b_ih,
+                          const float* b_hh, const float* W_hp, const float* b_hp, int E, float* pred_rel,
+                          float* h_final, float* c_final, cudaStream_t st) {
+    constexpr int THREADS = 128;
+    auto kern = lstm_decoder_kernel<H, THREADS>;
+    const int smem = (int)sizeof(LstmSmem<H, THREADS>);
+    SGX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    unsigned grid = (unsigned)std::min<int64_t>((batch + THREADS - 1) / THREADS, 148 * 4);
+    kern<<<grid, THREADS, smem, st>>>(h0, c0, last_pos_rel, steps, (int)batch, We, be, W_ih, W_hh, b_ih, b_hh, W_hp,
+                                      b_hp, E, pred_rel, h_final, c_final);
+    SGX_LAUNCH_CHECK();
+    return SGX_OK;
+}
+
+}  // namespace sgx
+
+using namespace sgx;
+
+extern "C" int sgx_lstm_encoder_fwd(const float* obs_rel, int32_t T, int64_t batch, const float* We, const float* be,
+                                    const float* W_ih, const float* W_hh, const float* b_ih, const float* b_hh,
+                                    int32_t E, int32_t H, float* h_out, void* stream) {
+    SGX_REQUIRE(obs_rel && We && be && W_ih && W_hh && b_ih && b_hh && h_out, "sgx_lstm_encoder_fwd: null pointer");
+    SGX_REQUIRE(T >= 1 && batch >= 1 && batch < ((int64_t)1 << 31) && E >= 1, "sgx_lstm_encoder_fwd: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (H == 32) return launch_encoder<32>(obs_rel, T, batch, We, be, W_ih, W_hh, b_ih, b_hh, E, h_out, st);
+    if (H == 48) return launch_encoder<48>(obs_rel, T, batch, We, be, W_ih, W_hh, b_ih, b_hh, E, h_out, st);
+    if (H == 64) return launch_encoder<64>(obs_rel, T, batch, We, be, W_ih, W_hh, b_ih, b_hh, E, h_out, st);
+    sgx::set_error("fused LSTM is built for h_dim in {32, 48, 64}; got %d", H);
+    return SGX_ERR_UNSUPPORTED;
+}
+
+extern "C" int sgx_lstm_decoder_fwd(const float* h0, const float* c0, const float* last_pos_rel, int32_t steps,
+                                    int64_t batch, const float* We, const float* be, const float* W_ih,
+                                    const float* W_hh, const float* b_ih, const float* b_hh, const float* W_hp,
+                                    const float* b_hp, int32_t E, int32_t H, float* pred_rel, float* h_final,
+                                    float* c_final, void* stream) {
+    SGX_REQUIRE(h0 && last_pos_rel && We && be && W_ih && W_hh && b_ih && b_hh && W_hp && b_hp && pred_rel,
+                "sgx_lstm_decoder_fwd: null pointer");
+    SGX_REQUIRE(steps >= 1 && batch >= 1 && batch < ((int64_t)1 << 31) && E >= 1, "sgx_lstm_decoder_fwd: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (H == 32)
+        return launch_decoder<32>(h0, c0, last_pos_rel, steps, batch, We, be, W_ih, W_hh, b_ih, b_hh, W_hp, b_hp, E,
+                                  pred_rel, h_final, c_final, st);
+    if (H == 48)
+        return launch_decoder<48>(h0, c0, last_pos_rel, steps, batch, We, be, W_ih, W_hh, b_ih, b_hh, W_hp, b_hp, E,
+                                  pred_rel, h_final, c_final, st);
+    if (H == 64)
+        return launch_decoder<64>(h0, c0, last_pos_rel, steps, batch, We, be, W_ih, W_hh, b_ih, b_hh, W_hp, b_hp, E,
+                                  pred_rel, h_final, c_final, st);
+    sgx::set_error("fused LSTM is built for h_dim in {32, 48, 64}; got %d", H);
+    return SGX_ERR_UNSUPPORTED;
+}

@@ -11,8 +11,21 @@ instead.  Differences that are not visible in results:
 import torch
 import torch.nn as nn
 
+from . import ops
 from .modules import GATEncoder, GCNModule, PoolHiddenNet, make_mlp
 from .schedule import get_schedule
+
+
+def _fused_lstm_ok(module, lstm, *tensors):
+    """The fused recurrence kernels serve inference; anything that needs autograd stays on nn.LSTM (cuDNN)."""
+    if not all(t.is_cuda and t.dtype == torch.float32 for t in tensors):
+        return False
+    if lstm.num_layers != 1 or lstm.hidden_size not in ops.FUSED_LSTM_H or lstm.bidirectional:
+        return False
+    if torch.is_grad_enabled() and (any(t.requires_grad for t in tensors) or
+                                    any(p.requires_grad for p in module.parameters())):
+        return False
+    return True
 
 
 def get_noise(shape, noise_type, device=None):
@@ -44,6 +57,8 @@ class Encoder(nn.Module):
 
     def forward(self, obs_traj):
         batch = obs_traj.size(1)
+        if _fused_lstm_ok(self, self.encoder, obs_traj):
+            return ops.lstm_encoder(obs_traj, self.spatial_embedding, self.encoder)
         emb = self.spatial_embedding(obs_traj.reshape(-1, 2)).view(-1, batch, self.embedding_dim)
         _, state = self.encoder(emb, self.init_hidden(batch, emb))
         return state[0]
@@ -74,6 +89,8 @@ class Decoder(nn.Module):
 
     def forward(self, last_pos, last_pos_rel, state_tuple, seq_start_end):
         batch = last_pos.size(0)
+        if _fused_lstm_ok(self, self.decoder, last_pos_rel, state_tuple[0], state_tuple[1]):
+            return self._forward_fused(last_pos, last_pos_rel, state_tuple, seq_start_end)
         steps = []
         dec_in = self.spatial_embedding(last_pos_rel).view(1, batch, self.embedding_dim)
         for _ in range(self.seq_len):
@@ -89,6 +106,31 @@ class Decoder(nn.Module):
             steps.append(rel_pos.view(batch, -1))
             last_pos = curr_pos
         return torch.stack(steps, dim=0), state_tuple[0]
+
+
+def _decoder_forward_fused(self, last_pos, last_pos_rel, state_tuple, seq_start_end):
+    """Inference path of Decoder.forward: the whole step loop in one kernel (no per-step pooling), or one fused
+    cell + hidden2pos kernel per step around the pooling op (pool_every_timestep)."""
+    h, c = state_tuple
+    if not self.pool_every_timestep:
+        pred, hf, _ = ops.lstm_decoder(h, c, last_pos_rel, self.seq_len, self.spatial_embedding, self.decoder,
+                                       self.hidden2pos, want_state=True)
+        return pred, hf.unsqueeze(0)
+    h, c = h.reshape(-1, self.h_dim), c.reshape(-1, self.h_dim)
+    rel_in, steps = last_pos_rel, []
+    for _ in range(self.seq_len):
+        rel, h, c = ops.lstm_decoder(h, c, rel_in, 1, self.spatial_embedding, self.decoder, self.hidden2pos,
+                                     want_state=True)
+        rel = rel[0]
+        curr_pos = rel + last_pos
+        pool_h = self.pool_net(h, seq_start_end, curr_pos)
+        h = self.mlp(torch.cat([h, pool_h], dim=1))
+        steps.append(rel)
+        rel_in, last_pos = rel, curr_pos
+    return torch.stack(steps, dim=0), h.unsqueeze(0)
+
+
+Decoder._forward_fused = _decoder_forward_fused
 
 
 class TrajectoryGenerator(nn.Module):

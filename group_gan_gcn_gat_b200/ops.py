@@ -307,3 +307,46 @@ def gemm(a, b, relu=False):
         _lib.check(L.sgx_gemm(_ptr(a), a.stride(0), a.stride(1), _ptr(b), b.stride(0), b.stride(1), _ptr(c), N, M, N, K,
                               0, int(relu), _stream(a)), 'sgx_gemm')
     return c
+
+
+# ---------------------------------------------------------------------------------------------
+# fused LSTM recurrences (inference only; training keeps nn.LSTM / cuDNN under autograd)
+# ---------------------------------------------------------------------------------------------
+FUSED_LSTM_H = (32, 48, 64)
+
+
+def lstm_encoder(obs_rel, emb, lstm):
+    """obs_rel [T,batch,2] -> final hidden state [1,batch,H] (Encoder.forward, sgan/models.py:62-92)."""
+    obs_rel = _f32(obs_rel, 'obs_traj_rel')
+    T, batch, _ = obs_rel.shape
+    H, E = lstm.hidden_size, emb.out_features
+    out = torch.empty(batch, H, dtype=torch.float32, device=obs_rel.device)
+    L = _lib.lib()
+    with torch.cuda.device(obs_rel.device):
+        _lib.check(L.sgx_lstm_encoder_fwd(_ptr(obs_rel), T, batch, _ptr(emb.weight.contiguous()), _ptr(emb.bias.contiguous()),
+                                          _ptr(lstm.weight_ih_l0.contiguous()), _ptr(lstm.weight_hh_l0.contiguous()),
+                                          _ptr(lstm.bias_ih_l0.contiguous()), _ptr(lstm.bias_hh_l0.contiguous()), E, H,
+                                          _ptr(out), _stream(obs_rel)), 'sgx_lstm_encoder_fwd')
+    return out.unsqueeze(0)
+
+
+def lstm_decoder(h0, c0, last_pos_rel, steps, emb, lstm, hidden2pos, want_state=False):
+    """-> pred_rel [steps,batch,2] (and (h,c) [batch,H] when want_state) -- Decoder.forward, models.py:142-178."""
+    h0 = _f32(h0.reshape(-1, lstm.hidden_size), 'decoder_h')
+    c0 = None if c0 is None else _f32(c0.reshape(-1, lstm.hidden_size), 'decoder_c')
+    last_pos_rel = _f32(last_pos_rel, 'last_pos_rel')
+    batch, H = h0.shape
+    E = emb.out_features
+    dev = h0.device
+    pred = torch.empty(steps, batch, 2, dtype=torch.float32, device=dev)
+    hf = torch.empty(batch, H, dtype=torch.float32, device=dev) if want_state else None
+    cf = torch.empty(batch, H, dtype=torch.float32, device=dev) if want_state else None
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        _lib.check(L.sgx_lstm_decoder_fwd(_ptr(h0), _ptr(c0), _ptr(last_pos_rel), steps, batch,
+                                          _ptr(emb.weight.contiguous()), _ptr(emb.bias.contiguous()),
+                                          _ptr(lstm.weight_ih_l0.contiguous()), _ptr(lstm.weight_hh_l0.contiguous()),
+                                          _ptr(lstm.bias_ih_l0.contiguous()), _ptr(lstm.bias_hh_l0.contiguous()),
+                                          _ptr(hidden2pos.weight.contiguous()), _ptr(hidden2pos.bias.contiguous()), E, H,
+                                          _ptr(pred), _ptr(hf), _ptr(cf), _stream(h0)), 'sgx_lstm_decoder_fwd')
+    return (pred, hf, cf) if want_state else pred

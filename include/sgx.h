@@ -161,6 +161,24 @@ int sgx_gat_encoder_bwd(const float* x, const float* grad_out, const int32_t* le
                         float* grad_bo, void* workspace, int64_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Fused per-pedestrian LSTM recurrences (inference), SURVEY.md 8f row f1.
+ * Encoder.forward (sgan/models.py:62-92): obs_rel [T,batch,2] -> Linear(2,E) -> LSTM(E,H) from zero state ->
+ *   h_out [batch,H].  We [E,2] be [E]  W_ih [4H,E] W_hh [4H,H] b_ih,b_hh [4H] (PyTorch gate order i,f,g,o).
+ * Decoder.forward (sgan/models.py:142-178) without per-step pooling: h0 [batch,H], c0 [batch,H] or null (= 0),
+ *   first input = embedding of last_pos_rel [batch,2]; per step LSTM cell -> rel = W_hp h + b_hp -> next input =
+ *   embedding of rel.  pred_rel [steps,batch,2]; h_final / c_final [batch,H] optional (null to skip).
+ *   steps = 1 gives the single cell update used when the caller pools between steps (models.py:162-168).
+ * Built for H in {32, 48, 64}.
+ */
+int sgx_lstm_encoder_fwd(const float* obs_rel, int32_t T, int64_t batch, const float* We, const float* be,
+                         const float* W_ih, const float* W_hh, const float* b_ih, const float* b_hh, int32_t E,
+                         int32_t H, float* h_out, void* stream);
+int sgx_lstm_decoder_fwd(const float* h0, const float* c0, const float* last_pos_rel, int32_t steps, int64_t batch,
+                         const float* We, const float* be, const float* W_ih, const float* W_hh, const float* b_ih,
+                         const float* b_hh, const float* W_hp, const float* b_hp, int32_t E, int32_t H,
+                         float* pred_rel, float* h_final, float* c_final, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Standalone dense-adjacency layers (API parity for GraphAttentionLayer.forward(h, adj),
  * sgan/models.py:198-210, and GCN.forward(A, X), models.py:573-580): the masked-softmax rows below
  * plus sgx_gemm for every product (Wh = h W, att Wh, (A H) W ...).  n x n dense `adj`.

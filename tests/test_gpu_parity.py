@@ -326,3 +326,39 @@ def test_dense_gcn_vs_golden(sgx):
     assert_close(x.grad, g['grad_in.x'], 5e-5, 'gcn dx')
     for k, p in net.named_parameters():
         assert_close(p.grad, g['grad.' + k], 5e-5, 'gcn d' + k, floor=grad_floor(g))
+
+
+# ------------------------------------------------------------------ fused LSTM recurrences
+@pytest.mark.parametrize('h_dim,T', [(32, 8), (48, 20), (64, 3)])
+def test_fused_encoder_matches_cudnn_and_oracle(sgx, h_dim, T):
+    torch.manual_seed(h_dim)
+    enc = sgx['MD'].Encoder(embedding_dim=16, h_dim=h_dim, mlp_dim=64, num_layers=1)
+    x = torch.randn(T, 777, 2) * 0.4
+    sd = {'e.' + k: v for k, v in enc.state_dict().items()}
+    ref = O.encoder(x, sd, 'e.')
+    enc = enc.to(DEV)
+    with torch.no_grad():
+        fused = enc(x.to(DEV))                      # inference -> sgx_lstm_encoder_fwd
+    eager = enc(x.to(DEV).requires_grad_(True))     # autograd -> nn.LSTM
+    assert fused.shape == eager.shape == ref.shape
+    assert_close(fused, ref, 2e-5, 'fused encoder vs CPU oracle')   # ex2.approx-based sigmoid/tanh, T recurrent steps
+    assert_close(fused, eager, 2e-5, 'fused encoder vs cuDNN')
+
+
+@pytest.mark.parametrize('pet', [False, True])
+def test_fused_decoder_matches_autograd_path(sgx, pet):
+    torch.manual_seed(5)
+    dec = sgx['MD'].Decoder(12, embedding_dim=16, h_dim=32, mlp_dim=64, num_layers=1, pool_every_timestep=pet,
+                            bottleneck_dim=8, batch_norm=False).to(DEV)
+    sizes = [3, 5, 2, 40, 1, 9]
+    sse = sse_from_sizes(sizes).to(DEV)
+    n = sum(sizes)
+    last_pos = torch.rand(n, 2, device=DEV) * 10
+    last_rel = torch.randn(n, 2, device=DEV) * 0.3
+    h0 = torch.randn(1, n, 32, device=DEV)
+    c0 = torch.zeros(1, n, 32, device=DEV)
+    with torch.no_grad():
+        fused, hf = dec(last_pos, last_rel, (h0, c0), sse)
+    eager, he = dec(last_pos, last_rel, (h0.clone().requires_grad_(True), c0), sse)
+    assert_close(fused, eager, 1e-5, 'fused decoder pred_rel')
+    assert_close(hf, he, 1e-5, 'fused decoder final h')
