@@ -1,0 +1,137 @@
+"""Scene-sharded data parallelism and the adversarial step of scripts/train.py:395-484.
+
+Inference shards: scenes are independent units (all three operators are block-diagonal over scenes, the K samples
+are independent given the noise), so `shard_batch` splits them across ranks by LPT on N^2 -- computed identically
+on every rank from the host copy of seq_start_end, no communication -- and nothing is exchanged in the forward.
+Training: one flattened all-reduce (sum) per network per optimizer step; BCE terms are means over ALL pedestrians of
+the global batch (sgan/losses.py:21) so the local term is weighted by local_peds / global_peds, the best-of-K L2
+variety term is a SUM over scenes (scripts/train.py:460-466) so local sums simply add; the label-smoothing draws
+come from an identically seeded `random.Random` on every rank; clip_grad_norm_ acts on the reduced gradient.
+"""
+import random
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from .losses import gan_d_loss, gan_g_loss, l2_loss
+from .models import ped_scene_index
+from .schedule import SceneSchedule, get_schedule
+from .utils import relative_to_abs
+
+
+def shard_batch(batch_tensors, seq_start_end, world, rank, ped_dim=1):
+    """Returns (local tensors, local seq_start_end [int64, host], scene indices) for `rank`.
+
+    batch_tensors: dict name -> tensor whose dimension `ped_dim` indexes pedestrians ([T,batch,C] in the reference),
+    or dimension 0 for tensors listed with a leading '0:' in the name (e.g. loss_mask [batch, T]).
+    """
+    sched = seq_start_end if isinstance(seq_start_end, SceneSchedule) else SceneSchedule(seq_start_end, 'cpu')
+    rank_of, _ = sched.partition(world)
+    mine = np.nonzero(rank_of == rank)[0]
+    sse = sched.host_sse
+    sizes = (sse[mine, 1] - sse[mine, 0]).astype(np.int64)
+    idx = np.concatenate([np.arange(sse[s, 0], sse[s, 1]) for s in mine]) if len(mine) else np.zeros(0, np.int64)
+    starts = np.concatenate([[0], np.cumsum(sizes)])
+    local_sse = torch.from_numpy(np.stack([starts[:-1], starts[1:]], axis=1).astype(np.int64))
+    out = {}
+    for name, t in batch_tensors.items():
+        dim = 0 if name.startswith('0:') else ped_dim
+        sel = torch.from_numpy(idx).to(t.device)
+        out[name[2:] if name.startswith('0:') else name] = t.index_select(dim, sel)
+    return out, local_sse, mine
+
+
+def allreduce_gradients(module, group=None):
+    """One flattened all-reduce (sum) over every parameter gradient of `module` (missing grads count as zero)."""
+    params = [p for p in module.parameters() if p.requires_grad]
+    if not params or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return 0
+    for p in params:
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+    flat = torch.cat([p.grad.reshape(-1) for p in params])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for p in params:
+        n = p.numel()
+        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+        off += n
+    return flat.numel() * flat.element_size()
+
+
+def _global_count(n_local, device, group=None):
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return float(n_local)
+    t = torch.tensor([float(n_local)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return float(t.item())
+
+
+def variety_l2(l2_raw_per_sample, loss_mask, sched):
+    """sum over scenes of min_k( sum_{peds of scene} l2[ped,k] ) / sum(loss_mask of scene)  -- the per-scene python
+    loop of scripts/train.py:460-464 as two segmented sums."""
+    seg = ped_scene_index(sched)
+    k = l2_raw_per_sample.shape[1]
+    per_scene = l2_raw_per_sample.new_zeros(sched.n_scenes, k).index_add_(0, seg, l2_raw_per_sample)
+    denom = loss_mask.new_zeros(sched.n_scenes).index_add_(0, seg, loss_mask.sum(dim=1))
+    return (per_scene.min(dim=1).values / denom).sum()
+
+
+def discriminator_step(args, batch, generator, discriminator, optimizer_d, label_rng=None, group=None):
+    """scripts/train.py:395-429 on this rank's shard; gradients are all-reduced before the optimizer step."""
+    (obs_traj, pred_traj_gt, obs_traj_rel, pred_traj_gt_rel, obs_traj_g, loss_mask, seq_start_end) = batch
+    n_local = obs_traj.shape[1]
+    w = n_local / _global_count(n_local, obs_traj.device, group)
+    fake_rel = generator(obs_traj, obs_traj_rel, seq_start_end, obs_traj_g)
+    fake = relative_to_abs(fake_rel, obs_traj[-1])
+    s_fake = discriminator(torch.cat([obs_traj, fake], 0), torch.cat([obs_traj_rel, fake_rel], 0), seq_start_end)
+    s_real = discriminator(torch.cat([obs_traj, pred_traj_gt], 0), torch.cat([obs_traj_rel, pred_traj_gt_rel], 0),
+                           seq_start_end)
+    loss = gan_d_loss(s_real, s_fake, label_rng) * w
+    optimizer_d.zero_grad()
+    loss.backward()
+    allreduce_gradients(discriminator, group)
+    if getattr(args, 'clipping_threshold_d', 0) > 0:
+        nn.utils.clip_grad_norm_(discriminator.parameters(), args.clipping_threshold_d)
+    optimizer_d.step()
+    return {'D_total_loss': float(loss.detach()) / max(w, 1e-12) if w else 0.0}
+
+
+def generator_step(args, batch, generator, discriminator, optimizer_g, label_rng=None, group=None):
+    """scripts/train.py:432-484: best-of-K variety loss + adversarial term on the last sample."""
+    (obs_traj, pred_traj_gt, obs_traj_rel, pred_traj_gt_rel, obs_traj_g, loss_mask, seq_start_end) = batch
+    n_local = obs_traj.shape[1]
+    w = n_local / _global_count(n_local, obs_traj.device, group)
+    sched = get_schedule(seq_start_end, obs_traj.device)
+    mask = loss_mask[:, args.obs_len:]
+    raws = []
+    for _ in range(args.best_k):
+        fake_rel = generator(obs_traj, obs_traj_rel, seq_start_end, obs_traj_g)
+        if args.l2_loss_weight > 0:
+            raws.append(args.l2_loss_weight * l2_loss(fake_rel, pred_traj_gt_rel, mask, mode='raw'))
+    loss = obs_traj.new_zeros(())
+    losses = {}
+    if args.l2_loss_weight > 0:
+        l2 = variety_l2(torch.stack(raws, dim=1), mask, sched)
+        losses['G_l2_loss_rel'] = float(l2.detach())
+        loss = loss + l2
+    fake = relative_to_abs(fake_rel, obs_traj[-1])
+    s_fake = discriminator(torch.cat([obs_traj, fake], 0), torch.cat([obs_traj_rel, fake_rel], 0), seq_start_end)
+    adv = gan_g_loss(s_fake, label_rng)
+    losses['G_discriminator_loss'] = float(adv.detach())
+    loss = loss + adv * w
+    optimizer_g.zero_grad()
+    loss.backward()
+    allreduce_gradients(generator, group)
+    if getattr(args, 'clipping_threshold_g', 0) > 0:
+        nn.utils.clip_grad_norm_(generator.parameters(), args.clipping_threshold_g)
+    optimizer_g.step()
+    losses['G_total_loss'] = float(loss.detach())
+    return losses
+
+
+def make_label_rng(seed, step):
+    """Identical on every rank: the reference draws label smoothing from Python's global RNG (sgan/losses.py:32,45)."""
+    return random.Random(seed * 1000003 + step)

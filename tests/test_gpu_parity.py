@@ -362,3 +362,65 @@ def test_fused_decoder_matches_autograd_path(sgx, pet):
     eager, he = dec(last_pos, last_rel, (h0.clone().requires_grad_(True), c0), sse)
     assert_close(fused, eager, 1e-5, 'fused decoder pred_rel')
     assert_close(hf, he, 1e-5, 'fused decoder final h')
+
+
+# ------------------------------------------------------------------ training step (SURVEY cfg 3 / 5): fwd + bwd parity
+@pytest.mark.parametrize('name', ['generator_gat_zara1', 'generator_gcn_zara1'])
+def test_generator_training_gradients_match_oracle(sgx, name):
+    """Best-of-K variety L2 + adversarial term through the pooled discriminator: every generator gradient on the GPU
+    (sgx backward kernels + cuDNN LSTM) against CPU autograd through the oracle restatement."""
+    from group_gan_gcn_gat_b200 import losses, parallel
+    from group_gan_gcn_gat_b200.utils import relative_to_abs
+    g = load_golden(name)
+    gd = load_golden('discriminator_zara1')
+    wiring = str(g['wiring'])
+    gen = _generator(sgx, g, wiring)
+    disc = sgx['MD'].TrajectoryDiscriminator(obs_len=8, pred_len=12, embedding_dim=16, h_dim=48, mlp_dim=64, num_layers=1,
+                                             dropout=0, batch_norm=False, d_type='global')
+    disc.load_state_dict(state_dict_of(gd), strict=True)
+    disc = disc.to(DEV)
+    obs, obs_rel, grp = g['obs_traj'], g['obs_traj_rel'], g['obs_traj_g']
+    sse, gt = g['seq_start_end'], g['pred_traj_gt']
+    gt_rel = torch.cat([(gt[0] - obs[-1]).unsqueeze(0), gt[1:] - gt[:-1]], 0)
+    mask = torch.ones(obs.shape[1], 12)
+    K = g['noise'].shape[0]
+
+    def total_loss(gen_fn, disc_fn, variety_fn, dev):
+        raws, rel = [], None
+        for k in range(K):
+            rel = gen_fn(g['noise'][k].to(dev))
+            raws.append(losses.l2_loss(rel, gt_rel.to(dev), mask.to(dev), mode='raw'))
+        l2 = variety_fn(torch.stack(raws, 1))
+        fake = relative_to_abs(rel, obs[-1].to(dev))
+        s = disc_fn(torch.cat([obs.to(dev), fake], 0), torch.cat([obs_rel.to(dev), rel], 0))
+        return l2 + losses.bce_loss(s, torch.full_like(s, 0.9))
+
+    # GPU: product path
+    sched = sgx['get_schedule'](sse, DEV)
+    loss_gpu = total_loss(lambda z: gen(obs.to(DEV), obs_rel.to(DEV), sse.to(DEV), grp.to(DEV), user_noise=z),
+                          lambda t, tr: disc(t, tr, sse.to(DEV)), lambda r: parallel.variety_l2(r, mask.to(DEV), sched), DEV)
+    gen.zero_grad()
+    loss_gpu.backward()
+    # CPU: oracle with autograd
+    sd = {k: v.clone().requires_grad_(True) for k, v in state_dict_of(g).items()}
+    sdd = state_dict_of(gd)
+    cfg = dict(pred_len=12, wiring=wiring, pooling=True, pool_every_timestep=False, alpha=float(g['alpha']),
+               n_heads=int(g['n_heads']))
+
+    def variety_cpu(r):
+        tot = 0.0
+        for s, e in sse.tolist():
+            tot = tot + torch.min(r[s:e].sum(0)) / mask[s:e].sum()
+        return tot
+    loss_cpu = total_loss(lambda z: O.generator_forward(obs, obs_rel, sse, grp, sd, cfg, z),
+                          lambda t, tr: O.discriminator_forward(t, tr, sse, sdd), variety_cpu, 'cpu')
+    loss_cpu.backward()
+    assert abs(float(loss_gpu) - float(loss_cpu)) < 1e-4 * max(1.0, abs(float(loss_cpu)))
+    ref_grads = {k: v.grad for k, v in sd.items() if v.grad is not None}
+    floor = 1e-2 * max(float(v.abs().max()) for v in ref_grads.values())
+    checked = 0
+    for k, p in gen.named_parameters():
+        if k in ref_grads and p.grad is not None:
+            assert_close(p.grad, ref_grads[k], 2e-4, name + ' d' + k, floor=floor)
+            checked += 1
+    assert checked >= 20
