@@ -31,6 +31,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ['NCCL_DEBUG'] = os.environ.get('SGX_NCCL_DEBUG', 'WARN')   # keep stdout to the one JSON line
 
 ZARA1_HIST = {2: 212, 3: 136, 4: 109, 5: 55, 6: 32, 7: 10, 8: 20, 9: 8, 10: 12, 11: 4, 12: 1, 13: 2, 14: 1}
 K_SAMPLES = 20
