@@ -119,3 +119,25 @@ extern "C" int sgx_schedule_partition(const int64_t* sse, int64_t S, int32_t wor
         for (int32_t r = 0; r < world; ++r) rank_cost[r] = tot[r];
     return SGX_OK;
 }
+
+// Greedy packing of consecutive whole scenes into chunks of at most `cap` pedestrians (one warp / CTA team per
+// chunk in the fused GAT kernel).  h_chunk_scene [S+1]: scene index where each chunk starts, closed by S.
+// Returns the number of chunks in *h_n_chunks, or SGX_ERR_UNSUPPORTED if a scene exceeds `cap`.
+extern "C" int sgx_schedule_chunks(const int64_t* sse, int64_t S, int32_t cap, int32_t* chunk_scene,
+                                   int64_t* n_chunks) {
+    int64_t batch, mx, pairs;
+    int rc = validate(sse, S, &batch, &mx, &pairs);
+    if (rc) return rc;
+    SGX_REQUIRE(chunk_scene && n_chunks && cap >= 1, "sgx_schedule_chunks: bad arguments");
+    SGX_UNSUPPORTED(mx > cap, "largest scene has %lld pedestrians, chunk capacity is %d", (long long)mx, cap);
+    int64_t c = 0, fill = 0;
+    chunk_scene[0] = 0;
+    for (int64_t s = 0; s < S; ++s) {
+        int64_t n = sse[2 * s + 1] - sse[2 * s];
+        if (fill + n > cap) { chunk_scene[++c] = (int32_t)s; fill = 0; }
+        fill += n;
+    }
+    chunk_scene[++c] = (int32_t)S;
+    *n_chunks = c;
+    return SGX_OK;
+}

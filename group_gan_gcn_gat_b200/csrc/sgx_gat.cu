@@ -405,6 +405,267 @@ static int gat_forward(const float* x, const int32_t* leader, const int32_t* gsi
     return SGX_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Fused forward for batches whose scenes all fit a warp (N <= 32; every ETH/UCY test split except univ):
+// one WARP per chunk of whole scenes (<= 32 peds, lanes <-> peds).  x -> intra GAT -> GPool -> inter GAT ->
+// unpool -> Linear without a single intermediate leaving the SM: per-ped rows ping-pong between two
+// shared-memory row buffers, every linear map is a thread-per-row GEMV with the weights broadcast from
+// shared memory as 128-bit loads, attention gathers neighbour rows from the same buffers.  Only x, the
+// group structure and out touch HBM (260 B/ped).  n_heads = 1 (every shipped checkpoint).
+// ------------------------------------------------------------------------------------------------
+constexpr int RS = 76;                 // row stride (floats) of the per-slot buffers: 16 B aligned, conflict-free STS.128
+constexpr int FUSED_WARPS = 4;
+
+struct FusedW {                        // shared-memory weight block (floats)
+    float Wi[40 * HID], ai[2 * HID], Wio[HID * OUT], aio[2 * OUT];
+    float We[OUT * HID], ae[2 * HID], Weo[HID * OUT], aeo[2 * OUT];
+    float Wo[24 * 2 * OUT], bo[24];
+};
+
+// y[0..NO) = sum_c xrow[c] * W[c][0..NO)   (W row-major [NI][NO] in smem, xrow in smem)
+template <int NI, int NO>
+__device__ __forceinline__ void gemv_rows(const float* __restrict__ xrow, const float* __restrict__ W, float (&y)[NO]) {
+#pragma unroll
+    for (int o = 0; o < NO; ++o) y[o] = 0.f;
+#pragma unroll 2
+    for (int c = 0; c < NI; ++c) {
+        const float xv = xrow[c];
+        const float4* w = reinterpret_cast<const float4*>(W + c * NO);
+#pragma unroll
+        for (int o = 0; o < NO / 4; ++o) {
+            const float4 v = w[o];
+            y[4 * o] = fmaf(xv, v.x, y[4 * o]); y[4 * o + 1] = fmaf(xv, v.y, y[4 * o + 1]);
+            y[4 * o + 2] = fmaf(xv, v.z, y[4 * o + 2]); y[4 * o + 3] = fmaf(xv, v.w, y[4 * o + 3]);
+        }
+    }
+}
+
+// attention of one node over the slots [b,e) of its scene that satisfy `pick`; rows/scores live in shared memory
+template <int F, bool INTER>
+__device__ __forceinline__ void attend_smem(const float* __restrict__ rows, const float2* __restrict__ st,
+                                            const int* __restrict__ lead_slot, int b, int e, int my_lead, float s_i,
+                                            float alpha, float (&hp)[F]) {
+    float m = -INFINITY;
+    for (int q = b; q < e; ++q) {
+        const bool nb = INTER ? (lead_slot[q] == q) : (lead_slot[q] == my_lead);
+        if (nb) m = fmaxf(m, lrelu(s_i + st[q].y, alpha));
+    }
+    float den = 0.f;
+#pragma unroll
+    for (int f = 0; f < F; ++f) hp[f] = 0.f;
+    for (int q = b; q < e; ++q) {
+        const bool nb = INTER ? (lead_slot[q] == q) : (lead_slot[q] == my_lead);
+        if (!nb) continue;
+        const float w = expf(lrelu(s_i + st[q].y, alpha) - m);
+        den += w;
+        const float4* row = reinterpret_cast<const float4*>(rows + q * RS);
+#pragma unroll
+        for (int f = 0; f < F / 4; ++f) {
+            const float4 v = row[f];
+            hp[4 * f] = fmaf(w, v.x, hp[4 * f]); hp[4 * f + 1] = fmaf(w, v.y, hp[4 * f + 1]);
+            hp[4 * f + 2] = fmaf(w, v.z, hp[4 * f + 2]); hp[4 * f + 3] = fmaf(w, v.w, hp[4 * f + 3]);
+        }
+    }
+    const float inv = 1.f / den;
+#pragma unroll
+    for (int f = 0; f < F; ++f) hp[f] *= inv;
+}
+
+template <int F>
+__device__ __forceinline__ void store_row(float* __restrict__ row, const float (&v)[F]) {
+#pragma unroll
+    for (int f = 0; f < F / 4; ++f)
+        reinterpret_cast<float4*>(row)[f] = make_float4(v[4 * f], v[4 * f + 1], v[4 * f + 2], v[4 * f + 3]);
+}
+
+template <int F>
+__device__ __forceinline__ float2 scores(const float (&wh)[F], const float* __restrict__ a) {
+    float s = 0.f, t = 0.f;
+#pragma unroll
+    for (int f = 0; f < F; ++f) { s = fmaf(wh[f], a[f], s); t = fmaf(wh[f], a[F + f], t); }
+    return make_float2(s, t);
+}
+
+template <int F>
+__device__ __forceinline__ void elu_logsoftmax(float (&v)[F]) {
+    float mx = -INFINITY;
+#pragma unroll
+    for (int f = 0; f < F; ++f) { v[f] = elu1(v[f]); mx = fmaxf(mx, v[f]); }
+    float sum = 0.f;
+#pragma unroll
+    for (int f = 0; f < F; ++f) sum += expf(v[f] - mx);
+    const float lse = mx + logf(sum);
+#pragma unroll
+    for (int f = 0; f < F; ++f) v[f] -= lse;
+}
+
+template <int IN, int FIN>
+__global__ void __launch_bounds__(FUSED_WARPS * 32)
+gat_fused_fwd_kernel(const float* __restrict__ x, const int32_t* __restrict__ leader, const int32_t* __restrict__ gsize,
+                     const int32_t* __restrict__ ped_start, const int32_t* __restrict__ ped_end,
+                     const int32_t* __restrict__ scene_start, const int32_t* __restrict__ chunk_scene, int n_chunks,
+                     const float* __restrict__ Wi, const float* __restrict__ ai, const float* __restrict__ Wio,
+                     const float* __restrict__ aio, const float* __restrict__ We, const float* __restrict__ ae,
+                     const float* __restrict__ Weo, const float* __restrict__ aeo, const float* __restrict__ Wo,
+                     const float* __restrict__ bo, float alpha, float* __restrict__ out) {
+    extern __shared__ __align__(16) uint8_t raw[];
+    FusedW& w = *reinterpret_cast<FusedW*>(raw);
+    float* bufs = reinterpret_cast<float*>(raw + sizeof(FusedW));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    {   // weights: one cooperative load per CTA
+        const float* src[10] = {Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo};
+        float* dst[10] = {w.Wi, w.ai, w.Wio, w.aio, w.We, w.ae, w.Weo, w.aeo, w.Wo, w.bo};
+        const int cnt[10] = {IN * HID, 2 * HID, HID * OUT, 2 * OUT, OUT * HID, 2 * HID, HID * OUT, 2 * OUT,
+                             FIN * 2 * OUT, FIN};
+        for (int k = 0; k < 10; ++k)
+            for (int e = threadIdx.x; e < cnt[k]; e += blockDim.x) dst[k][e] = src[k][e];
+    }
+    __syncthreads();
+    // per-warp scratch: two row buffers, X1 rows, scores, leader slots
+    float* A = bufs + warp * (32 * RS * 2 + 32 * 16 + 32 * 2 + 32);
+    float* Bf = A + 32 * RS;
+    float* X1s = Bf + 32 * RS;
+    float2* st = reinterpret_cast<float2*>(X1s + 32 * 16);
+    int* lead_slot = reinterpret_cast<int*>(st + 32);
+
+    const int n_warps_total = gridDim.x * FUSED_WARPS;
+    for (int chunk = blockIdx.x * FUSED_WARPS + warp; chunk < n_chunks; chunk += n_warps_total) {
+        const int p0 = scene_start[chunk_scene[chunk]];
+        const int np = scene_start[chunk_scene[chunk + 1]] - p0;
+        const bool live = lane < np;
+        const int p = p0 + lane;
+        int b = 0, e = 0, my_lead = lane;
+        float inv_g = 1.f;
+        if (live) {
+            b = ped_start[p] - p0; e = ped_end[p] - p0; my_lead = leader[p] - p0;
+            inv_g = __frcp_rn((float)gsize[p]);
+            const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)p * IN);
+#pragma unroll
+            for (int c = 0; c < IN / 4; ++c) reinterpret_cast<float4*>(A + lane * RS)[c] = xr[c];
+        }
+        lead_slot[lane] = live ? my_lead : -1;
+        const bool is_lead = live && (my_lead == lane);
+        __syncwarp();
+        // ---- intra GAT, layer 1 ----
+        if (live) {
+            float wh[HID];
+            gemv_rows<IN, HID>(A + lane * RS, w.Wi, wh);
+            st[lane] = scores<HID>(wh, w.ai);
+            store_row<HID>(Bf + lane * RS, wh);
+        }
+        __syncwarp();
+        if (live) {
+            float hp[HID];
+            attend_smem<HID, false>(Bf, st, lead_slot, b, e, my_lead, st[lane].x, alpha, hp);
+#pragma unroll
+            for (int f = 0; f < HID; ++f) hp[f] = elu1(hp[f]);
+            store_row<HID>(A + lane * RS, hp);              // x1a
+        }
+        __syncwarp();
+        // ---- intra GAT, out_att ----
+        float x1[OUT];
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) x1[o] = 0.f;
+        if (live) {
+            float wh2[OUT];
+            gemv_rows<HID, OUT>(A + lane * RS, w.Wio, wh2);
+            st[lane] = scores<OUT>(wh2, w.aio);
+            store_row<OUT>(Bf + lane * RS, wh2);
+        }
+        __syncwarp();
+        if (live) {
+            attend_smem<OUT, false>(Bf, st, lead_slot, b, e, my_lead, st[lane].x, alpha, x1);
+            elu_logsoftmax<OUT>(x1);
+            store_row<OUT>(X1s + lane * 16, x1);
+        }
+        __syncwarp();
+        // ---- GPool (leaders) + inter GAT layer 1 ----
+        if (is_lead) {
+            float xg[OUT];
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) xg[o] = 0.f;
+            for (int q = lane; q < e; ++q) {
+                if (lead_slot[q] != lane) continue;
+#pragma unroll
+                for (int o = 0; o < OUT; ++o) xg[o] = fmaf(inv_g, X1s[q * 16 + o], xg[o]);
+            }
+            store_row<OUT>(A + lane * RS, xg);
+        }
+        __syncwarp();
+        if (is_lead) {
+            float wh3[HID];
+            gemv_rows<OUT, HID>(A + lane * RS, w.We, wh3);
+            st[lane] = scores<HID>(wh3, w.ae);
+            store_row<HID>(Bf + lane * RS, wh3);
+        }
+        __syncwarp();
+        if (is_lead) {
+            float hp[HID];
+            attend_smem<HID, true>(Bf, st, lead_slot, b, e, my_lead, st[lane].x, alpha, hp);
+#pragma unroll
+            for (int f = 0; f < HID; ++f) hp[f] = elu1(hp[f]);
+            store_row<HID>(A + lane * RS, hp);
+        }
+        __syncwarp();
+        if (is_lead) {
+            float wh4[OUT];
+            gemv_rows<HID, OUT>(A + lane * RS, w.Weo, wh4);
+            st[lane] = scores<OUT>(wh4, w.aeo);
+            store_row<OUT>(Bf + lane * RS, wh4);
+        }
+        __syncwarp();
+        if (is_lead) {
+            float yg[OUT];
+            attend_smem<OUT, true>(Bf, st, lead_slot, b, e, my_lead, st[lane].x, alpha, yg);
+            elu_logsoftmax<OUT>(yg);
+            store_row<OUT>(A + lane * RS, yg);              // Yg at the leader's slot
+        }
+        __syncwarp();
+        // ---- unpool + output Linear ----
+        if (live) {
+            float cat[2 * OUT];
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) { cat[o] = x1[o]; cat[OUT + o] = inv_g * A[my_lead * RS + o]; }
+            float* orow = out + (int64_t)p * FIN;
+#pragma unroll
+            for (int o4 = 0; o4 < FIN / 4; ++o4) {
+                float y[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int o = 4 * o4 + k;
+                    float acc = w.bo[o];
+                    const float4* wr = reinterpret_cast<const float4*>(w.Wo + o * 2 * OUT);
+#pragma unroll
+                    for (int c = 0; c < 2 * OUT / 4; ++c) {
+                        const float4 v = wr[c];
+                        acc = fmaf(cat[4 * c], v.x, acc); acc = fmaf(cat[4 * c + 1], v.y, acc);
+                        acc = fmaf(cat[4 * c + 2], v.z, acc); acc = fmaf(cat[4 * c + 3], v.w, acc);
+                    }
+                    y[k] = acc;
+                }
+                reinterpret_cast<float4*>(orow)[o4] = make_float4(y[0], y[1], y[2], y[3]);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+static int gat_fused_forward(const float* x, const int32_t* leader, const int32_t* gsize, const int32_t* ps,
+                             const int32_t* pe, const int32_t* scene_start, const int32_t* chunk_scene, int n_chunks,
+                             const float* Wi, const float* ai, const float* Wio, const float* aio, const float* We,
+                             const float* ae, const float* Weo, const float* aeo, const float* Wo, const float* bo,
+                             float alpha, float* out, cudaStream_t st) {
+    auto kern = gat_fused_fwd_kernel<40, 24>;
+    const int smem = (int)(sizeof(FusedW) + FUSED_WARPS * (32 * RS * 2 + 32 * 16 + 32 * 2 + 32) * sizeof(float));
+    SGX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int grid = std::min((n_chunks + FUSED_WARPS - 1) / FUSED_WARPS, 148 * 2);
+    kern<<<grid, FUSED_WARPS * 32, smem, st>>>(x, leader, gsize, ps, pe, scene_start, chunk_scene, n_chunks, Wi, ai, Wio,
+                                               aio, We, ae, Weo, aeo, Wo, bo, alpha, out);
+    SGX_LAUNCH_CHECK();
+    return SGX_OK;
+}
+
 }  // namespace sgx
 
 using namespace sgx;
@@ -490,4 +751,22 @@ extern "C" int sgx_gat_encoder_bwd(const float* x, const float* grad_out, const 
                                    w.dX1, grad_x, grad_Wi, grad_ai, grad_Wio, grad_aio, st)))
         return rc;
     return SGX_OK;
+}
+
+// Fused forward for batches whose scenes all have <= 32 peds (chunk_scene: scene index boundaries of chunks of whole
+// scenes with <= 32 peds, built by sgx_schedule_chunks).  n_heads = 1, IN = 40, HID = 72, OUT = 16, FIN = 24.
+extern "C" int sgx_gat_encoder_fused_fwd(const float* x, const int32_t* leader, const int32_t* group_size,
+                                         const int32_t* ped_start, const int32_t* ped_end, const int32_t* scene_start,
+                                         const int32_t* chunk_scene, int64_t n_chunks, const float* Wi, const float* ai,
+                                         const float* Wio, const float* aio, const float* We, const float* ae,
+                                         const float* Weo, const float* aeo, const float* Wo, const float* bo,
+                                         float alpha, int32_t n_heads, int32_t IN, int32_t HID_, int32_t OUT_,
+                                         int32_t FIN, float* out, void* stream) {
+    SGX_REQUIRE(x && leader && group_size && ped_start && ped_end && scene_start && chunk_scene && Wi && ai && Wio &&
+                    aio && We && ae && Weo && aeo && Wo && bo && out, "sgx_gat_encoder_fused_fwd: null pointer");
+    SGX_REQUIRE(n_chunks > 0 && n_chunks < ((int64_t)1 << 31), "sgx_gat_encoder_fused_fwd: bad chunk count");
+    SGX_UNSUPPORTED(n_heads != 1 || IN != 40 || HID_ != HID || OUT_ != OUT || FIN != 24,
+                    "fused GAT encoder is built for n_heads=1, dims 40/72/16/24 (the shipped configuration)");
+    return gat_fused_forward(x, leader, group_size, ped_start, ped_end, scene_start, chunk_scene, (int)n_chunks, Wi, ai,
+                             Wio, aio, We, ae, Weo, aeo, Wo, bo, alpha, out, (cudaStream_t)stream);
 }

@@ -168,9 +168,10 @@ class GATEncoder(nn.Module):
         leader, gsize, _gid, _ng = _groups_for(sched, end_group)
         Wi, ai, Wio, aio = self.gat_intra.stacked()
         We, ae, Weo, aeo = self.gat_inter.stacked()
+        chunk_scene, n_chunks = sched.chunks(32) if self.n_heads == 1 else (sched.scene_start[:0], 0)
         return ops.gat_encoder_fwd(h_states, leader, gsize, sched.ped_start, sched.ped_end, sched.n_scenes, Wi, ai, Wio,
                                    aio, We, ae, Weo, aeo, self.out_embedding.weight, self.out_embedding.bias,
-                                   float(self.alpha))
+                                   float(self.alpha), sched.scene_start, chunk_scene, n_chunks)
 
 
 class GCN(nn.Module):

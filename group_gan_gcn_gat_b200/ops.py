@@ -231,7 +231,9 @@ gcn_module_fwd.register_autograd(_gcn_backward, setup_context=_gcn_setup)
 @torch.library.custom_op('sgx::gat_encoder_fwd', mutates_args=())
 def gat_encoder_fwd(x: Tensor, leader: Tensor, gsize: Tensor, ped_start: Tensor, ped_end: Tensor, n_scenes: int,
                     Wi: Tensor, ai: Tensor, Wio: Tensor, aio: Tensor, We: Tensor, ae: Tensor, Weo: Tensor,
-                    aeo: Tensor, Wo: Tensor, bo: Tensor, alpha: float) -> Tensor:
+                    aeo: Tensor, Wo: Tensor, bo: Tensor, alpha: float, scene_start: Tensor, chunk_scene: Tensor,
+                    n_chunks: int) -> Tensor:
+    """n_chunks > 0 selects the single-launch fused kernel (all scenes <= 32 peds, n_heads = 1, dims 40/72/16/24)."""
     x = _f32(x, 'h_states')
     ps = [_f32(t, 'gat weight') for t in (Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo)]
     batch, IN = x.shape
@@ -239,8 +241,14 @@ def gat_encoder_fwd(x: Tensor, leader: Tensor, gsize: Tensor, ped_start: Tensor,
     OUT, FIN = Wio.shape[1], Wo.shape[0]
     out = torch.empty(batch, FIN, dtype=torch.float32, device=x.device)
     L = _lib.lib()
-    ws = _ws(L.sgx_gat_encoder_ws_bytes(batch, n_scenes, nh, IN, HID, OUT, FIN), x.device)
     with torch.cuda.device(x.device):
+        if n_chunks > 0 and nh == 1 and (IN, HID, OUT, FIN) == (40, 72, 16, 24):
+            _lib.check(L.sgx_gat_encoder_fused_fwd(_ptr(x), _ptr(leader), _ptr(gsize), _ptr(ped_start), _ptr(ped_end),
+                                                   _ptr(scene_start), _ptr(chunk_scene), n_chunks,
+                                                   *[_ptr(p) for p in ps], alpha, nh, IN, HID, OUT, FIN, _ptr(out),
+                                                   _stream(x)), 'sgx_gat_encoder_fused_fwd')
+            return out
+        ws = _ws(L.sgx_gat_encoder_ws_bytes(batch, n_scenes, nh, IN, HID, OUT, FIN), x.device)
         _lib.check(L.sgx_gat_encoder_fwd(_ptr(x), _ptr(leader), _ptr(gsize), _ptr(ped_start), _ptr(ped_end), batch,
                                          n_scenes, *[_ptr(p) for p in ps], alpha, nh, IN, HID, OUT, FIN, _ptr(out),
                                          _ptr(ws), ws.numel(), _stream(x)), 'sgx_gat_encoder_fwd')
@@ -248,7 +256,8 @@ def gat_encoder_fwd(x: Tensor, leader: Tensor, gsize: Tensor, ped_start: Tensor,
 
 
 @gat_encoder_fwd.register_fake
-def _(x, leader, gsize, ped_start, ped_end, n_scenes, Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo, alpha):
+def _(x, leader, gsize, ped_start, ped_end, n_scenes, Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo, alpha, scene_start,
+      chunk_scene, n_chunks):
     return x.new_empty(x.shape[0], Wo.shape[0])
 
 
@@ -278,7 +287,8 @@ def _(x, grad_out, leader, gsize, ped_start, ped_end, n_scenes, Wi, ai, Wio, aio
 
 
 def _gat_setup(ctx, inputs, output):
-    x, leader, gsize, ps, pe, S, *params, alpha = inputs
+    x, leader, gsize, ps, pe, S, *rest = inputs
+    params, alpha = rest[:10], rest[10]
     ctx.save_for_backward(x, leader, gsize, ps, pe, *params)
     ctx.n_scenes, ctx.alpha = S, alpha
 
@@ -286,7 +296,7 @@ def _gat_setup(ctx, inputs, output):
 def _gat_backward(ctx, grad_out):
     x, leader, gsize, ps, pe, *params = ctx.saved_tensors
     g = gat_encoder_bwd(x, grad_out.contiguous(), leader, gsize, ps, pe, ctx.n_scenes, *params, ctx.alpha)
-    return (g[0], None, None, None, None, None, *g[1:], None)
+    return (g[0], None, None, None, None, None, *g[1:], None, None, None, None)
 
 
 gat_encoder_fwd.register_autograd(_gat_backward, setup_context=_gat_setup)

@@ -47,7 +47,23 @@ class SceneSchedule:
         self.ped_end = put(ped_end)
         self.pair_off = put(pair_off)
         self.tile_first = put(tile_first)
-        self._groups = {}
+        self._chunks = {}
+
+    def chunks(self, cap=32):
+        """(chunk_scene int32 device tensor, n_chunks) packing whole scenes into chunks of <= cap peds, or (empty, 0)
+        when a scene is larger than cap (the caller then takes the multi-pass path).  Cached."""
+        hit = self._chunks.get(cap)
+        if hit is None:
+            if self.max_n > cap:
+                hit = (torch.empty(0, dtype=torch.int32, device=self.device), 0)
+            else:
+                buf = np.empty(self.n_scenes + 1, np.int32)
+                n = np.zeros(1, np.int64)
+                _lib.check(_lib.lib().sgx_schedule_chunks(self.host_sse.ctypes.data, self.n_scenes, cap,
+                                                          buf.ctypes.data, n.ctypes.data), 'chunks')
+                hit = (torch.from_numpy(buf[:int(n[0]) + 1].copy()).to(self.device), int(n[0]))
+            self._chunks[cap] = hit
+        return hit
 
     def partition(self, world):
         """LPT split of scenes over ranks by N^2 cost -> (rank_of_scene int32 [S], cost per rank)."""

@@ -70,6 +70,11 @@ int sgx_schedule_fill(const int64_t* h_seq_start_end, int64_t n_scenes, int32_t*
                       int32_t* h_ped_start, int32_t* h_ped_end, int64_t* h_pair_off, int32_t* h_tile_first);
 int sgx_schedule_partition(const int64_t* h_seq_start_end, int64_t n_scenes, int32_t world,
                            int32_t* h_rank_of_scene, int64_t* h_rank_cost);
+/* Greedy packing of consecutive whole scenes into chunks of <= cap pedestrians (fused GAT kernel: one warp per
+ * chunk).  h_chunk_scene int32 [S+1] receives the first scene of every chunk, closed by S; *h_n_chunks the count.
+ * SGX_ERR_UNSUPPORTED when a scene is larger than cap. */
+int sgx_schedule_chunks(const int64_t* h_seq_start_end, int64_t n_scenes, int32_t cap, int32_t* h_chunk_scene,
+                        int64_t* h_n_chunks);
 
 /* ---------------------------------------------------------------------------------------------
  * Group structure.  Replaces sgan/models.py:263-278 (GATEncoder) == 654-680 (GCNModule):
@@ -151,6 +156,14 @@ int sgx_gat_encoder_fwd(const float* x, const int32_t* leader, const int32_t* gr
                         const float* aeo, const float* Wo, const float* bo, float alpha, int32_t n_heads, int32_t IN,
                         int32_t HID, int32_t OUT, int32_t FIN, float* out, void* workspace, int64_t ws_bytes,
                         void* stream);
+/* Same forward in ONE launch for batches whose scenes all have <= 32 pedestrians (chunk_scene / n_chunks from
+ * sgx_schedule_chunks with cap = 32): no intermediate leaves the SM.  n_heads = 1, dims 40/72/16/24 only. */
+int sgx_gat_encoder_fused_fwd(const float* x, const int32_t* leader, const int32_t* group_size,
+                              const int32_t* ped_start, const int32_t* ped_end, const int32_t* scene_start,
+                              const int32_t* chunk_scene, int64_t n_chunks, const float* Wi, const float* ai,
+                              const float* Wio, const float* aio, const float* We, const float* ae, const float* Weo,
+                              const float* aeo, const float* Wo, const float* bo, float alpha, int32_t n_heads,
+                              int32_t IN, int32_t HID, int32_t OUT, int32_t FIN, float* out, void* stream);
 int sgx_gat_encoder_bwd(const float* x, const float* grad_out, const int32_t* leader, const int32_t* group_size,
                         const int32_t* ped_start, const int32_t* ped_end, int64_t batch, int64_t n_scenes,
                         const float* Wi, const float* ai, const float* Wio, const float* aio, const float* We,

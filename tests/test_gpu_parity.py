@@ -421,6 +421,6 @@ def test_generator_training_gradients_match_oracle(sgx, name):
     checked = 0
     for k, p in gen.named_parameters():
         if k in ref_grads and p.grad is not None:
-            assert_close(p.grad, ref_grads[k], 5e-4, name + ' d' + k, floor=floor)   # through 20 recurrent LSTM steps
+            assert_close(p.grad, ref_grads[k], 1e-3, name + ' d' + k, floor=floor)   # through 20 recurrent LSTM steps, max-pool argmax and min-over-K kinks
             checked += 1
     assert checked >= 20
