@@ -70,6 +70,15 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// Blackwell packed fp32 FMA (SASS FFMA2): d = a * b + c on both halves; halves the FMA issue slots of the
+// CUDA-core GEMV loops.  The two halves accumulate even / odd k separately and are added at the end.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                       rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2*>(&rd);
+}
+
 // generic fp32 GEMM used inside the library (same as the exported sgx_gemm)
 // bias_m / bias_n (nullable): per-row / per-column bias added to C (disables split-K)
 int gemm(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn, float* C, int64_t ldc,
