@@ -56,7 +56,9 @@ def synth_batch(n_scenes, seed):
     lab = np.floor(rng.uniform(0, 1, size=batch) * hi).astype(np.float32) + 1
     lab[rng.uniform(0, 1, size=batch) < 0.10] = 0
     grp = np.broadcast_to(lab[None, :, None], (OBS_LEN, batch, 1)).copy()
-    return dict(obs_traj=torch.from_numpy(obs.astype(np.float32)), obs_traj_rel=torch.from_numpy(disp),
+    fut = obs[-1:] + np.cumsum(rng.normal(0, 0.3, size=(PRED_LEN, batch, 2)).astype(np.float32), axis=0)
+    return dict(pred_traj_gt=torch.from_numpy(fut.astype(np.float32)),
+                obs_traj=torch.from_numpy(obs.astype(np.float32)), obs_traj_rel=torch.from_numpy(disp),
                 obs_traj_g=torch.from_numpy(grp), seq_start_end=torch.from_numpy(sse), sizes=sizes)
 
 
@@ -110,10 +112,16 @@ def cpu_port_traj_per_sec(n_scenes, k_samples, seed, reps=1):
     with torch.no_grad():
         for _ in range(reps):
             t0 = time.perf_counter()
-            for _k in range(k_samples):
+            ade, fde = [], []
+            for _k in range(k_samples):              # the loop of scripts/evaluate_model.py:85-95
                 z = torch.randn(n_scenes, 8, generator=gen)
-                O.generator_forward(data['obs_traj'], data['obs_traj_rel'], data['seq_start_end'], data['obs_traj_g'],
-                                    sd, cfg, z)
+                rel = O.generator_forward(data['obs_traj'], data['obs_traj_rel'], data['seq_start_end'],
+                                          data['obs_traj_g'], sd, cfg, z)
+                pred = O.relative_to_abs(rel, data['obs_traj'][-1])
+                ade.append(O.displacement_error_raw(pred, data['pred_traj_gt']))
+                fde.append(O.final_displacement_error_raw(pred[-1], data['pred_traj_gt'][-1]))
+            O.best_of_k(ade, data['seq_start_end'])
+            O.best_of_k(fde, data['seq_start_end'])
             dt = time.perf_counter() - t0
             best = dt if best is None else min(best, dt)
     peds = int(data['seq_start_end'][-1, 1])
@@ -211,11 +219,12 @@ def main():
     gen = gen.to(dev).train()          # scripts/evaluate_model.py:54 keeps the generator in train mode
     gen.pool_net.precision = precision
 
-    host = {k: data[k].pin_memory() for k in ('obs_traj', 'obs_traj_rel', 'obs_traj_g', 'seq_start_end')}
+    host = {k: data[k].pin_memory() for k in ('obs_traj', 'obs_traj_rel', 'obs_traj_g', 'seq_start_end', 'pred_traj_gt')}
     dev_in = {k: v.to(dev) for k, v in host.items()}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     noise_gen = torch.Generator(device=dev).manual_seed(7)
-    out_host = torch.empty(K_SAMPLES, PRED_LEN, peds, 2).pin_memory()
+    out_host = torch.empty(2).pin_memory()
+    from group_gan_gcn_gat_b200.evaluate import evaluate_batch
 
     def step_resident():
         outs = None
@@ -226,13 +235,16 @@ def main():
         return outs
 
     def step_e2e():
+        """The body of scripts/evaluate_model.py:72-99 for one minibatch, from HOST buffers: H2D of the batch, schedule
+        built from the host seq_start_end, K complete generator forwards (noise drawn on the CPU generator like the
+        reference), best-of-K ADE/FDE reduced on the device, D2H of the two sums."""
         obs = host['obs_traj'].to(dev, non_blocking=True)
         obs_rel = host['obs_traj_rel'].to(dev, non_blocking=True)
         grp = host['obs_traj_g'].to(dev, non_blocking=True)
+        gt = host['pred_traj_gt'].to(dev, non_blocking=True)
         sse = host['seq_start_end'].clone()              # a fresh batch object every step: the schedule is rebuilt
-        for k in range(K_SAMPLES):                       # once per step from the HOST tensor (no D2H sync), then cached
-            rel = gen(obs, obs_rel, sse, grp)            # noise drawn on the CPU generator like the reference
-            out_host[k].copy_(rel, non_blocking=True)
+        ade, fde = evaluate_batch(gen, obs, obs_rel, sse, grp, gt, K_SAMPLES)
+        out_host.copy_(torch.stack([ade, fde]), non_blocking=True)
         torch.cuda.synchronize()
 
     def barrier():
@@ -316,9 +328,11 @@ def main():
             'clocks': clocks,
             'e2e': {'value': traj_per_step * args.steps / (e2e_ms_max * 1e-3), 'unit': 'traj/s',
                     'h2d_bytes_per_step': int(sum(host[k].numel() * host[k].element_size()
-                                                  for k in ('obs_traj', 'obs_traj_rel', 'obs_traj_g')) +
-                                              5 * 4 * peds + 8 * peds + K_SAMPLES * n_scenes * 8 * 4),
-                    'd2h_bytes_per_step': int(out_host.numel() * 4)},
+                                                  for k in ('obs_traj', 'obs_traj_rel', 'obs_traj_g', 'pred_traj_gt')) +
+                                              (4 + 4 + 8) * peds + 4 * (n_scenes + 1) + 4 * ((n_pairs + 127) // 128) +
+                                              K_SAMPLES * n_scenes * 8 * 4),
+                    'd2h_bytes_per_step': int(out_host.numel() * 4),
+                    'what': 'evaluate_batch(): H2D batch + schedule + K forwards + best-of-K ADE/FDE on device + D2H of the sums'},
             'gpu_launches': int(launches),
             'roofline': {'kernel': 'pool_pair_kernel' if precision != 'bf16' else 'pool_tc_kernel', 'bound': 'tensor',
                          'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,

@@ -414,8 +414,10 @@ static int gat_forward(const float* x, const int32_t* leader, const int32_t* gsi
 // shared memory as 128-bit loads, attention gathers neighbour rows from the same buffers.  Only x, the
 // group structure and out touch HBM (260 B/ped).  n_heads = 1 (every shipped checkpoint).
 // ------------------------------------------------------------------------------------------------
-constexpr int RS = 76;                 // row stride (floats) of the per-slot buffers: 16 B aligned, conflict-free STS.128
-constexpr int FUSED_WARPS = 4;
+constexpr int RS = 76;                 // row stride (floats) of the 72-wide row buffer: 16 B aligned, conflict-free STS.128
+constexpr int RA = 44;                 // row stride of the 40-wide input buffer (x, Xg, Yg)
+constexpr int FUSED_WARPS = 8;
+constexpr int FUSED_SCRATCH = 32 * RA + 32 * RS + 32 * 16 + 32 * 2 + 32;   // floats per warp
 
 struct FusedW {                        // shared-memory weight block (floats)
     float Wi[40 * HID], ai[2 * HID], Wio[HID * OUT], aio[2 * OUT];
@@ -472,6 +474,23 @@ __device__ __forceinline__ void attend_smem(const float* __restrict__ rows, cons
     for (int f = 0; f < F; ++f) hp[f] *= inv;
 }
 
+// y[0..NO) = sum_c x[c] * W[c][0..NO) with x in registers (fully unrolled; used for the 72 -> 16 maps)
+template <int NI, int NO>
+__device__ __forceinline__ void gemv_regs(const float (&x)[NI], const float* __restrict__ W, float (&y)[NO]) {
+#pragma unroll
+    for (int o = 0; o < NO; ++o) y[o] = 0.f;
+#pragma unroll
+    for (int c = 0; c < NI; ++c) {
+        const float4* w = reinterpret_cast<const float4*>(W + c * NO);
+#pragma unroll
+        for (int o = 0; o < NO / 4; ++o) {
+            const float4 v = w[o];
+            y[4 * o] = fmaf(x[c], v.x, y[4 * o]); y[4 * o + 1] = fmaf(x[c], v.y, y[4 * o + 1]);
+            y[4 * o + 2] = fmaf(x[c], v.z, y[4 * o + 2]); y[4 * o + 3] = fmaf(x[c], v.w, y[4 * o + 3]);
+        }
+    }
+}
+
 template <int F>
 __device__ __forceinline__ void store_row(float* __restrict__ row, const float (&v)[F]) {
 #pragma unroll
@@ -523,8 +542,8 @@ gat_fused_fwd_kernel(const float* __restrict__ x, const int32_t* __restrict__ le
     }
     __syncthreads();
     // per-warp scratch: two row buffers, X1 rows, scores, leader slots
-    float* A = bufs + warp * (32 * RS * 2 + 32 * 16 + 32 * 2 + 32);
-    float* Bf = A + 32 * RS;
+    float* A = bufs + warp * FUSED_SCRATCH;
+    float* Bf = A + 32 * RA;
     float* X1s = Bf + 32 * RS;
     float2* st = reinterpret_cast<float2*>(X1s + 32 * 16);
     int* lead_slot = reinterpret_cast<int*>(st + 32);
@@ -542,7 +561,7 @@ gat_fused_fwd_kernel(const float* __restrict__ x, const int32_t* __restrict__ le
             inv_g = __frcp_rn((float)gsize[p]);
             const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)p * IN);
 #pragma unroll
-            for (int c = 0; c < IN / 4; ++c) reinterpret_cast<float4*>(A + lane * RS)[c] = xr[c];
+            for (int c = 0; c < IN / 4; ++c) reinterpret_cast<float4*>(A + lane * RA)[c] = xr[c];
         }
         lead_slot[lane] = live ? my_lead : -1;
         const bool is_lead = live && (my_lead == lane);
@@ -550,26 +569,25 @@ gat_fused_fwd_kernel(const float* __restrict__ x, const int32_t* __restrict__ le
         // ---- intra GAT, layer 1 ----
         if (live) {
             float wh[HID];
-            gemv_rows<IN, HID>(A + lane * RS, w.Wi, wh);
+            gemv_rows<IN, HID>(A + lane * RA, w.Wi, wh);
             st[lane] = scores<HID>(wh, w.ai);
             store_row<HID>(Bf + lane * RS, wh);
         }
         __syncwarp();
+        float x1[OUT];
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) x1[o] = 0.f;
+        float wh2[OUT];
         if (live) {
             float hp[HID];
             attend_smem<HID, false>(Bf, st, lead_slot, b, e, my_lead, st[lane].x, alpha, hp);
 #pragma unroll
-            for (int f = 0; f < HID; ++f) hp[f] = elu1(hp[f]);
-            store_row<HID>(A + lane * RS, hp);              // x1a
+            for (int f = 0; f < HID; ++f) hp[f] = elu1(hp[f]);      // x1a stays in registers
+            // ---- intra GAT, out_att ----
+            gemv_regs<HID, OUT>(hp, w.Wio, wh2);
         }
-        __syncwarp();
-        // ---- intra GAT, out_att ----
-        float x1[OUT];
-#pragma unroll
-        for (int o = 0; o < OUT; ++o) x1[o] = 0.f;
+        __syncwarp();                                               // every lane is done reading Wh1 rows
         if (live) {
-            float wh2[OUT];
-            gemv_rows<HID, OUT>(A + lane * RS, w.Wio, wh2);
             st[lane] = scores<OUT>(wh2, w.aio);
             store_row<OUT>(Bf + lane * RS, wh2);
         }
@@ -590,27 +608,26 @@ gat_fused_fwd_kernel(const float* __restrict__ x, const int32_t* __restrict__ le
 #pragma unroll
                 for (int o = 0; o < OUT; ++o) xg[o] = fmaf(inv_g, X1s[q * 16 + o], xg[o]);
             }
-            store_row<OUT>(A + lane * RS, xg);
+            store_row<OUT>(A + lane * RA, xg);
         }
         __syncwarp();
         if (is_lead) {
             float wh3[HID];
-            gemv_rows<OUT, HID>(A + lane * RS, w.We, wh3);
+            gemv_rows<OUT, HID>(A + lane * RA, w.We, wh3);
             st[lane] = scores<HID>(wh3, w.ae);
             store_row<HID>(Bf + lane * RS, wh3);
         }
         __syncwarp();
+        float wh4[OUT];
         if (is_lead) {
             float hp[HID];
             attend_smem<HID, true>(Bf, st, lead_slot, b, e, my_lead, st[lane].x, alpha, hp);
 #pragma unroll
             for (int f = 0; f < HID; ++f) hp[f] = elu1(hp[f]);
-            store_row<HID>(A + lane * RS, hp);
+            gemv_regs<HID, OUT>(hp, w.Weo, wh4);
         }
         __syncwarp();
         if (is_lead) {
-            float wh4[OUT];
-            gemv_rows<HID, OUT>(A + lane * RS, w.Weo, wh4);
             st[lane] = scores<OUT>(wh4, w.aeo);
             store_row<OUT>(Bf + lane * RS, wh4);
         }
@@ -619,14 +636,14 @@ gat_fused_fwd_kernel(const float* __restrict__ x, const int32_t* __restrict__ le
             float yg[OUT];
             attend_smem<OUT, true>(Bf, st, lead_slot, b, e, my_lead, st[lane].x, alpha, yg);
             elu_logsoftmax<OUT>(yg);
-            store_row<OUT>(A + lane * RS, yg);              // Yg at the leader's slot
+            store_row<OUT>(A + lane * RA, yg);              // Yg at the leader's slot
         }
         __syncwarp();
         // ---- unpool + output Linear ----
         if (live) {
             float cat[2 * OUT];
 #pragma unroll
-            for (int o = 0; o < OUT; ++o) { cat[o] = x1[o]; cat[OUT + o] = inv_g * A[my_lead * RS + o]; }
+            for (int o = 0; o < OUT; ++o) { cat[o] = x1[o]; cat[OUT + o] = inv_g * A[my_lead * RA + o]; }
             float* orow = out + (int64_t)p * FIN;
 #pragma unroll
             for (int o4 = 0; o4 < FIN / 4; ++o4) {
@@ -657,9 +674,9 @@ static int gat_fused_forward(const float* x, const int32_t* leader, const int32_
                              const float* ae, const float* Weo, const float* aeo, const float* Wo, const float* bo,
                              float alpha, float* out, cudaStream_t st) {
     auto kern = gat_fused_fwd_kernel<40, 24>;
-    const int smem = (int)(sizeof(FusedW) + FUSED_WARPS * (32 * RS * 2 + 32 * 16 + 32 * 2 + 32) * sizeof(float));
+    const int smem = (int)(sizeof(FusedW) + FUSED_WARPS * FUSED_SCRATCH * sizeof(float));
     SGX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int grid = std::min((n_chunks + FUSED_WARPS - 1) / FUSED_WARPS, 148 * 2);
+    const int grid = std::min((n_chunks + FUSED_WARPS - 1) / FUSED_WARPS, 148);
     kern<<<grid, FUSED_WARPS * 32, smem, st>>>(x, leader, gsize, ps, pe, scene_start, chunk_scene, n_chunks, Wi, ai, Wio,
                                                aio, We, ae, Weo, aeo, Wo, bo, alpha, out);
     SGX_LAUNCH_CHECK();

@@ -1,0 +1,34 @@
+"""Best-of-K evaluation of one minibatch -- the loop body of scripts/evaluate_model.py:72-99 without per-scene
+python loops (SURVEY 8f rows f2/f3 stay behind the same API: every sample is a complete generator forward).
+
+    ade_sum, fde_sum = evaluate_batch(generator, obs_traj, obs_traj_rel, seq_start_end, obs_traj_g, pred_traj_gt, K)
+
+ade_sum / (total_traj * pred_len) and fde_sum / total_traj are the numbers the reference prints.
+"""
+import torch
+
+from .losses import displacement_error, final_displacement_error
+from .models import ped_scene_index
+from .schedule import get_schedule
+from .utils import relative_to_abs
+
+
+def best_of_k_sum(per_sample, sched):
+    """evaluate_helper (scripts/evaluate_model.py:58-69): per scene sum over peds, min over the K samples, summed."""
+    seg = ped_scene_index(sched)
+    per_scene = per_sample.new_zeros(sched.n_scenes, per_sample.shape[1]).index_add_(0, seg, per_sample)
+    return per_scene.min(dim=1).values.sum()
+
+
+@torch.no_grad()
+def evaluate_batch(generator, obs_traj, obs_traj_rel, seq_start_end, obs_traj_g, pred_traj_gt, num_samples=20,
+                   noise=None):
+    sched = get_schedule(seq_start_end, obs_traj.device)
+    ade, fde = [], []
+    for k in range(num_samples):
+        rel = generator(obs_traj, obs_traj_rel, seq_start_end, obs_traj_g,
+                        user_noise=None if noise is None else noise[k])
+        pred = relative_to_abs(rel, obs_traj[-1])
+        ade.append(displacement_error(pred, pred_traj_gt, mode='raw'))
+        fde.append(final_displacement_error(pred[-1], pred_traj_gt[-1], mode='raw'))
+    return best_of_k_sum(torch.stack(ade, dim=1), sched), best_of_k_sum(torch.stack(fde, dim=1), sched)

@@ -431,3 +431,16 @@ def test_generator_training_gradients_match_oracle(sgx, name):
             assert_close(p.grad, ref_grads[k], tol, name + ' d' + k, floor=floor)
             checked += 1
     assert checked >= 20
+
+
+def test_evaluate_batch_matches_reference_metrics(sgx):
+    """scripts/evaluate_model.py:72-99 on one batch: best-of-K ADE/FDE (vectorised) against the frozen reference numbers."""
+    from group_gan_gcn_gat_b200.evaluate import evaluate_batch
+    g = load_golden('generator_gat_zara1')
+    gen = _generator(sgx, g, 'gat')
+    t = lambda k: g[k].to(DEV)
+    ade, fde = evaluate_batch(gen, t('obs_traj'), t('obs_traj_rel'), t('seq_start_end'), t('obs_traj_g'), t('pred_traj_gt'),
+                              num_samples=g['noise'].shape[0], noise=t('noise'))
+    n = g['obs_traj'].shape[1]
+    assert abs(float(ade) / (n * 12) - float(g['ade'])) < 1e-4
+    assert abs(float(fde) / n - float(g['fde'])) < 1e-4
