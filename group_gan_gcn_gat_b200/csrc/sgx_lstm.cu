@@ -138,7 +138,7 @@ lstm_encoder_kernel(const float* __restrict__ obs_rel, int T, int batch, const f
 template <int H, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 lstm_decoder_kernel(const float* __restrict__ h0, const float* __restrict__ c0, const float* __restrict__ last_pos_rel,
-                    int steps, int batch, const float* __restrict__ We, const float* __restrict__ be,
+                    const float* __restrict__ z, const int32_t* __restrict__ ped_scene, int nz, int steps, int batch, const float* __restrict__ We, const float* __restrict__ be,
                     const float* __restrict__ W_ih, const float* __restrict__ W_hh, const float* __restrict__ b_ih,
                     const float* __restrict__ b_hh, const float* __restrict__ W_hp, const float* __restrict__ b_hp, int E,
                     float* __restrict__ pred_rel, float* __restrict__ h_final, float* __restrict__ c_final) {
@@ -158,8 +158,14 @@ lstm_decoder_kernel(const float* __restrict__ h0, const float* __restrict__ c0, 
             p[k] = p0 + k * THREADS + tid;
             live[k] = p[k] < batch;
 #pragma unroll
+            // h0 row = [h0[p][0 .. H-nz) | z[ped_scene[p]][0 .. nz)]: the add_noise concat of models.py:837-846 folded in
+            const int hc = H - nz;
+            const int sc = (live[k] && nz > 0) ? ped_scene[p[k]] : 0;
+#pragma unroll
             for (int u = 0; u < H; ++u) {
-                h[k][u] = live[k] ? h0[(int64_t)p[k] * H + u] : 0.f;
+                float v = 0.f;
+                if (live[k]) v = (u < hc) ? h0[(int64_t)p[k] * hc + u] : z[(int64_t)sc * nz + (u - hc)];
+                h[k][u] = v;
                 s.c[(k * H + u) * THREADS + tid] = (live[k] && c0) ? c0[(int64_t)p[k] * H + u] : 0.f;
             }
             float2 d = make_float2(0.f, 0.f);
@@ -210,7 +216,8 @@ static int launch_encoder(const float* obs_rel, int T, int64_t batch, const floa
 }
 
 template <int H>
-static int launch_decoder(const float* h0, const float* c0, const float* last_pos_rel, int steps, int64_t batch,
+static int launch_decoder(const float* h0, const float* c0, const float* last_pos_rel, const float* z,
+                          const int32_t* ped_scene, int nz, int steps, int64_t batch,
                           const float* We, const float* be, const float* W_ih, const float* W_hh, const float* b_ih,
                           const float* b_hh, const float* W_hp, const float* b_hp, int E, float* pred_rel,
                           float* h_final, float* c_final, cudaStream_t st) {
@@ -219,7 +226,7 @@ static int launch_decoder(const float* h0, const float* c0, const float* last_po
     const int smem = (int)sizeof(LstmSmem<H, THREADS>);
     SGX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     unsigned grid = (unsigned)std::min<int64_t>((batch + THREADS * PPT - 1) / (THREADS * PPT), 148 * 4);
-    kern<<<grid, THREADS, smem, st>>>(h0, c0, last_pos_rel, steps, (int)batch, We, be, W_ih, W_hh, b_ih, b_hh, W_hp,
+    kern<<<grid, THREADS, smem, st>>>(h0, c0, last_pos_rel, z, ped_scene, nz, steps, (int)batch, We, be, W_ih, W_hh, b_ih, b_hh, W_hp,
                                       b_hp, E, pred_rel, h_final, c_final);
     SGX_LAUNCH_CHECK();
     return SGX_OK;
@@ -242,23 +249,24 @@ extern "C" int sgx_lstm_encoder_fwd(const float* obs_rel, int32_t T, int64_t bat
     return SGX_ERR_UNSUPPORTED;
 }
 
-extern "C" int sgx_lstm_decoder_fwd(const float* h0, const float* c0, const float* last_pos_rel, int32_t steps,
-                                    int64_t batch, const float* We, const float* be, const float* W_ih,
+extern "C" int sgx_lstm_decoder_fwd(const float* h0, const float* c0, const float* last_pos_rel, const float* z,
+                                    const int32_t* ped_scene, int32_t nz, int32_t steps, int64_t batch, const float* We, const float* be, const float* W_ih,
                                     const float* W_hh, const float* b_ih, const float* b_hh, const float* W_hp,
                                     const float* b_hp, int32_t E, int32_t H, float* pred_rel, float* h_final,
                                     float* c_final, void* stream) {
     SGX_REQUIRE(h0 && last_pos_rel && We && be && W_ih && W_hh && b_ih && b_hh && W_hp && b_hp && pred_rel,
                 "sgx_lstm_decoder_fwd: null pointer");
     SGX_REQUIRE(steps >= 1 && batch >= 1 && batch < ((int64_t)1 << 31) && E >= 1, "sgx_lstm_decoder_fwd: bad shape");
+    SGX_REQUIRE(nz == 0 || (z && ped_scene && nz > 0 && nz < H), "sgx_lstm_decoder_fwd: noise needs z, ped_scene, 0 < nz < H");
     cudaStream_t st = (cudaStream_t)stream;
     if (H == 32)
-        return launch_decoder<32>(h0, c0, last_pos_rel, steps, batch, We, be, W_ih, W_hh, b_ih, b_hh, W_hp, b_hp, E,
+        return launch_decoder<32>(h0, c0, last_pos_rel, z, ped_scene, nz, steps, batch, We, be, W_ih, W_hh, b_ih, b_hh, W_hp, b_hp, E,
                                   pred_rel, h_final, c_final, st);
     if (H == 48)
-        return launch_decoder<48>(h0, c0, last_pos_rel, steps, batch, We, be, W_ih, W_hh, b_ih, b_hh, W_hp, b_hp, E,
+        return launch_decoder<48>(h0, c0, last_pos_rel, z, ped_scene, nz, steps, batch, We, be, W_ih, W_hh, b_ih, b_hh, W_hp, b_hp, E,
                                   pred_rel, h_final, c_final, st);
     if (H == 64)
-        return launch_decoder<64>(h0, c0, last_pos_rel, steps, batch, We, be, W_ih, W_hh, b_ih, b_hh, W_hp, b_hp, E,
+        return launch_decoder<64>(h0, c0, last_pos_rel, z, ped_scene, nz, steps, batch, We, be, W_ih, W_hh, b_ih, b_hh, W_hp, b_hp, E,
                                   pred_rel, h_final, c_final, st);
     sgx::set_error("fused LSTM is built for h_dim in {32, 48, 64}; got %d", H);
     return SGX_ERR_UNSUPPORTED;

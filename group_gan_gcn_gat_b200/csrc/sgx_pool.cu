@@ -120,16 +120,21 @@ pool_pair_kernel(const float* __restrict__ Ct, int64_t ldc, const float* __restr
         const int key = ped_i[r];
         const int key_prev = __shfl_up_sync(0xffffffffu, key, 1);
         const bool head = (lane == 0) || (key_prev != key);
+        bool same[5];
+#pragma unroll
+        for (int sft = 0; sft < 5; ++sft) {
+            const int okey = __shfl_down_sync(0xffffffffu, key, 1 << sft);
+            same[sft] = (lane + (1 << sft) < 32) && (okey == key);
+        }
 #pragma unroll
         for (int c = 0; c < BC; ++c) {
             float y = fmaxf(acc[r][c] + b2[cb + c], 0.f);
             unsigned long long pk =
                 ((unsigned long long)(__float_as_uint(y) & 0x7fffffffu) << 32) | (unsigned)ped_j[r];
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                unsigned long long other = __shfl_down_sync(0xffffffffu, pk, o);
-                int okey = __shfl_down_sync(0xffffffffu, key, o);
-                if (lane + o < 32 && okey == key && other > pk) pk = other;
+            for (int sft = 0; sft < 5; ++sft) {
+                const unsigned long long other = __shfl_down_sync(0xffffffffu, pk, 1 << sft);
+                if (same[sft] && other > pk) pk = other;
             }
             if (head && key >= 0) atomicMax(&packed[(int64_t)key * B + cb + c], pk);
         }

@@ -442,6 +442,12 @@ pool_tc_kernel(const __nv_bfloat16* __restrict__ hb, const float* __restrict__ p
                 const int key_prev = __shfl_up_sync(0xffffffffu, key, 1);
                 const bool head = (lane == 0) || (key_prev != key);
                 const bool uniform = __all_sync(0xffffffffu, key == __shfl_sync(0xffffffffu, key, 0));
+                bool same[5];                           // lane + 2^s belongs to the same pedestrian i (hoisted out of b)
+#pragma unroll
+                for (int sft = 0; sft < 5; ++sft) {
+                    const int okey = __shfl_down_sync(0xffffffffu, key, 1 << sft);
+                    same[sft] = (lane + (1 << sft) < 32) && (okey == key);
+                }
 #pragma unroll
                 for (int b = 0; b < B; ++b) {
                     const uint32_t raw = (b < 16) ? v[b & 15] : (b < 32) ? v2[b & 15] : v3[b & 15];
@@ -458,10 +464,9 @@ pool_tc_kernel(const __nv_bfloat16* __restrict__ hb, const float* __restrict__ p
                     } else {
                         unsigned long long pk = ((unsigned long long)bits << 32) | (unsigned)ij.y;
 #pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            unsigned long long other = __shfl_down_sync(0xffffffffu, pk, o);
-                            int okey = __shfl_down_sync(0xffffffffu, key, o);
-                            if (lane + o < 32 && okey == key && other > pk) pk = other;
+                        for (int sft = 0; sft < 5; ++sft) {
+                            const unsigned long long other = __shfl_down_sync(0xffffffffu, pk, 1 << sft);
+                            if (same[sft] && other > pk) pk = other;
                         }
                         if (head && key >= 0) atomicMax(&packed[(int64_t)key * B + b], pk);
                     }

@@ -224,6 +224,16 @@ class TrajectoryGenerator(nn.Module):
 
     def decode(self, ctx, obs_traj, obs_traj_rel, seq_start_end, user_noise=None):
         batch = obs_traj_rel.size(1)
+        dec = self.decoder
+        if (self.noise_dim and self.noise_mix_type == 'global' and not dec.pool_every_timestep and len(self.noise_dim) == 1
+                and _fused_lstm_ok(dec, dec.decoder, ctx, obs_traj_rel)):
+            # inference fast path: add_noise (models.py:837-846) is folded into the fused decoder kernel
+            sched = get_schedule(seq_start_end, ctx.device)
+            z = user_noise if user_noise is not None else get_noise((sched.n_scenes,) + tuple(self.noise_dim),
+                                                                   self.noise_type, ctx.device)
+            z = z.to(ctx.device).reshape(sched.n_scenes, -1)
+            return ops.lstm_decoder(ctx, None, obs_traj_rel[-1], dec.seq_len, dec.spatial_embedding, dec.decoder,
+                                    dec.hidden2pos, z=z, ped_scene=sched.ped_scene32())
         decoder_h = self.add_noise(ctx, seq_start_end, user_noise=user_noise).unsqueeze(0)
         decoder_c = decoder_h.new_zeros(self.num_layers, batch, self.decoder_h_dim)
         pred_rel, _ = self.decoder(obs_traj[-1], obs_traj_rel[-1], (decoder_h, decoder_c), seq_start_end)

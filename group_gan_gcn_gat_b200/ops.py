@@ -340,12 +340,16 @@ def lstm_encoder(obs_rel, emb, lstm):
     return out.unsqueeze(0)
 
 
-def lstm_decoder(h0, c0, last_pos_rel, steps, emb, lstm, hidden2pos, want_state=False):
-    """-> pred_rel [steps,batch,2] (and (h,c) [batch,H] when want_state) -- Decoder.forward, models.py:142-178."""
-    h0 = _f32(h0.reshape(-1, lstm.hidden_size), 'decoder_h')
+def lstm_decoder(h0, c0, last_pos_rel, steps, emb, lstm, hidden2pos, want_state=False, z=None, ped_scene=None):
+    """-> pred_rel [steps,batch,2] (and (h,c) [batch,H] when want_state) -- Decoder.forward, models.py:142-178.
+    With z [S,nz] and ped_scene int32 [batch], h0 is the noise-free context [batch,H-nz] (add_noise folded in)."""
+    nz = 0 if z is None else int(z.shape[1])
+    h0 = _f32(h0.reshape(-1, lstm.hidden_size - nz), 'decoder_h')
+    if nz:
+        z = _f32(z, 'noise')
     c0 = None if c0 is None else _f32(c0.reshape(-1, lstm.hidden_size), 'decoder_c')
     last_pos_rel = _f32(last_pos_rel, 'last_pos_rel')
-    batch, H = h0.shape
+    batch, H = h0.shape[0], lstm.hidden_size
     E = emb.out_features
     dev = h0.device
     pred = torch.empty(steps, batch, 2, dtype=torch.float32, device=dev)
@@ -353,7 +357,7 @@ def lstm_decoder(h0, c0, last_pos_rel, steps, emb, lstm, hidden2pos, want_state=
     cf = torch.empty(batch, H, dtype=torch.float32, device=dev) if want_state else None
     L = _lib.lib()
     with torch.cuda.device(dev):
-        _lib.check(L.sgx_lstm_decoder_fwd(_ptr(h0), _ptr(c0), _ptr(last_pos_rel), steps, batch,
+        _lib.check(L.sgx_lstm_decoder_fwd(_ptr(h0), _ptr(c0), _ptr(last_pos_rel), _ptr(z), _ptr(ped_scene), nz, steps, batch,
                                           _ptr(emb.weight.contiguous()), _ptr(emb.bias.contiguous()),
                                           _ptr(lstm.weight_ih_l0.contiguous()), _ptr(lstm.weight_hh_l0.contiguous()),
                                           _ptr(lstm.bias_ih_l0.contiguous()), _ptr(lstm.bias_hh_l0.contiguous()),

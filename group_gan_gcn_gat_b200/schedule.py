@@ -48,6 +48,15 @@ class SceneSchedule:
         self.pair_off = put(pair_off)
         self.tile_first = put(tile_first)
         self._chunks = {}
+        self._ped_scene32 = None
+
+    def ped_scene32(self):
+        """int32 [batch] scene index of every pedestrian (device), for the noise fold-in of the fused decoder."""
+        if self._ped_scene32 is None:
+            sizes = (self.host_sse[:, 1] - self.host_sse[:, 0]).astype(np.int64)
+            idx = np.repeat(np.arange(self.n_scenes, dtype=np.int32), sizes)
+            self._ped_scene32 = torch.from_numpy(idx).to(self.device)
+        return self._ped_scene32
 
     def chunks(self, cap=32):
         """(chunk_scene int32 device tensor, n_chunks) packing whole scenes into chunks of <= cap peds, or (empty, 0)
