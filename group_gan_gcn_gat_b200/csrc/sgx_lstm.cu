@@ -10,6 +10,8 @@
 // The reference issues one cuDNN call (plus ~6 small kernels) per decoder step; on the bench workload
 // cuDNN's persistent-RNN kernel took 3.7 ms per call (13 calls = 90 % of the generator forward).
 // Inference only: under autograd the modules keep using nn.LSTM (cuDNN) so training semantics are unchanged.
+#include <stdlib.h>
+
 #include "sgx_common.cuh"
 
 namespace sgx {
@@ -236,12 +238,31 @@ static int launch_decoder(const float* h0, const float* c0, const float* last_po
 
 using namespace sgx;
 
+// tensor-core variant (sgx_lstm_tc.cu): H = 32, large batches
+int64_t sgx_lstm_tc_ws_bytes();
+int sgx_lstm_tc_run(bool decoder, const float* seq_in, const float* h0, const float* c0, const float* z,
+                    const int32_t* ped_scene, int nz, int T, int64_t batch, const float* We, const float* be,
+                    const float* W_ih, const float* W_hh, const float* b_ih, const float* b_hh, const float* W_hp,
+                    const float* b_hp, int E, float* seq_out, float* h_out, void* ws, cudaStream_t st);
+
+static bool use_tc(int H, int T, int64_t batch, const void* ws, int64_t ws_bytes) {
+    const char* off = getenv("SGX_LSTM_TC");
+    if (off && off[0] == '0') return false;
+    return H == 32 && T >= 2 && batch >= 8192 && ws != nullptr && ws_bytes >= sgx_lstm_tc_ws_bytes();
+}
+
+extern "C" int64_t sgx_lstm_ws_bytes(void) { return sgx_lstm_tc_ws_bytes(); }
+
 extern "C" int sgx_lstm_encoder_fwd(const float* obs_rel, int32_t T, int64_t batch, const float* We, const float* be,
                                     const float* W_ih, const float* W_hh, const float* b_ih, const float* b_hh,
-                                    int32_t E, int32_t H, float* h_out, void* stream) {
+                                    int32_t E, int32_t H, float* h_out, void* workspace, int64_t ws_bytes,
+                                    void* stream) {
     SGX_REQUIRE(obs_rel && We && be && W_ih && W_hh && b_ih && b_hh && h_out, "sgx_lstm_encoder_fwd: null pointer");
     SGX_REQUIRE(T >= 1 && batch >= 1 && batch < ((int64_t)1 << 31) && E >= 1, "sgx_lstm_encoder_fwd: bad shape");
     cudaStream_t st = (cudaStream_t)stream;
+    if (use_tc(H, T, batch, workspace, ws_bytes))
+        return sgx_lstm_tc_run(false, obs_rel, nullptr, nullptr, nullptr, nullptr, 0, T, batch, We, be, W_ih, W_hh, b_ih,
+                               b_hh, nullptr, nullptr, E, nullptr, h_out, workspace, st);
     if (H == 32) return launch_encoder<32>(obs_rel, T, batch, We, be, W_ih, W_hh, b_ih, b_hh, E, h_out, st);
     if (H == 48) return launch_encoder<48>(obs_rel, T, batch, We, be, W_ih, W_hh, b_ih, b_hh, E, h_out, st);
     if (H == 64) return launch_encoder<64>(obs_rel, T, batch, We, be, W_ih, W_hh, b_ih, b_hh, E, h_out, st);
@@ -253,12 +274,15 @@ extern "C" int sgx_lstm_decoder_fwd(const float* h0, const float* c0, const floa
                                     const int32_t* ped_scene, int32_t nz, int32_t steps, int64_t batch, const float* We, const float* be, const float* W_ih,
                                     const float* W_hh, const float* b_ih, const float* b_hh, const float* W_hp,
                                     const float* b_hp, int32_t E, int32_t H, float* pred_rel, float* h_final,
-                                    float* c_final, void* stream) {
+                                    float* c_final, void* workspace, int64_t ws_bytes, void* stream) {
     SGX_REQUIRE(h0 && last_pos_rel && We && be && W_ih && W_hh && b_ih && b_hh && W_hp && b_hp && pred_rel,
                 "sgx_lstm_decoder_fwd: null pointer");
     SGX_REQUIRE(steps >= 1 && batch >= 1 && batch < ((int64_t)1 << 31) && E >= 1, "sgx_lstm_decoder_fwd: bad shape");
     SGX_REQUIRE(nz == 0 || (z && ped_scene && nz > 0 && nz < H), "sgx_lstm_decoder_fwd: noise needs z, ped_scene, 0 < nz < H");
     cudaStream_t st = (cudaStream_t)stream;
+    if (!c_final && use_tc(H, steps, batch, workspace, ws_bytes))
+        return sgx_lstm_tc_run(true, last_pos_rel, h0, c0, z, ped_scene, nz, steps, batch, We, be, W_ih, W_hh, b_ih, b_hh,
+                               W_hp, b_hp, E, pred_rel, h_final, workspace, st);
     if (H == 32)
         return launch_decoder<32>(h0, c0, last_pos_rel, z, ped_scene, nz, steps, batch, We, be, W_ih, W_hh, b_ih, b_hh, W_hp, b_hp, E,
                                   pred_rel, h_final, c_final, st);

@@ -24,6 +24,12 @@ def best_of_k_sum(per_sample, sched):
 def evaluate_batch(generator, obs_traj, obs_traj_rel, seq_start_end, obs_traj_g, pred_traj_gt, num_samples=20,
                    noise=None):
     sched = get_schedule(seq_start_end, obs_traj.device)
+    if noise is None and generator.noise_dim and generator.noise_mix_type == 'global':
+        # one draw for all K samples on the device generator.  The reference draws each sample on the CPU generator and
+        # copies it (sgan/models.py:23-29), which costs more host time than the whole forward here; pass `noise=` to
+        # reproduce a CPU-seeded stream.
+        fn = torch.randn if generator.noise_type == 'gaussian' else (lambda *a, **k: torch.rand(*a, **k) * 2 - 1)
+        noise = fn(num_samples, sched.n_scenes, *generator.noise_dim, device=obs_traj.device)
     ade, fde = [], []
     for k in range(num_samples):
         rel = generator(obs_traj, obs_traj_rel, seq_start_end, obs_traj_g,

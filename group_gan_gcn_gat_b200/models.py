@@ -113,8 +113,8 @@ def _decoder_forward_fused(self, last_pos, last_pos_rel, state_tuple, seq_start_
     cell + hidden2pos kernel per step around the pooling op (pool_every_timestep)."""
     h, c = state_tuple
     if not self.pool_every_timestep:
-        pred, hf, _ = ops.lstm_decoder(h, c, last_pos_rel, self.seq_len, self.spatial_embedding, self.decoder,
-                                       self.hidden2pos, want_state=True)
+        pred, hf = ops.lstm_decoder(h, c, last_pos_rel, self.seq_len, self.spatial_embedding, self.decoder,
+                                    self.hidden2pos, want_state='h')
         return pred, hf.unsqueeze(0)
     h, c = h.reshape(-1, self.h_dim), c.reshape(-1, self.h_dim)
     rel_in, steps = last_pos_rel, []

@@ -332,11 +332,12 @@ def lstm_encoder(obs_rel, emb, lstm):
     H, E = lstm.hidden_size, emb.out_features
     out = torch.empty(batch, H, dtype=torch.float32, device=obs_rel.device)
     L = _lib.lib()
+    ws = _ws(L.sgx_lstm_ws_bytes(), obs_rel.device)
     with torch.cuda.device(obs_rel.device):
         _lib.check(L.sgx_lstm_encoder_fwd(_ptr(obs_rel), T, batch, _ptr(emb.weight.contiguous()), _ptr(emb.bias.contiguous()),
                                           _ptr(lstm.weight_ih_l0.contiguous()), _ptr(lstm.weight_hh_l0.contiguous()),
                                           _ptr(lstm.bias_ih_l0.contiguous()), _ptr(lstm.bias_hh_l0.contiguous()), E, H,
-                                          _ptr(out), _stream(obs_rel)), 'sgx_lstm_encoder_fwd')
+                                          _ptr(out), _ptr(ws), ws.numel(), _stream(obs_rel)), 'sgx_lstm_encoder_fwd')
     return out.unsqueeze(0)
 
 
@@ -354,13 +355,16 @@ def lstm_decoder(h0, c0, last_pos_rel, steps, emb, lstm, hidden2pos, want_state=
     dev = h0.device
     pred = torch.empty(steps, batch, 2, dtype=torch.float32, device=dev)
     hf = torch.empty(batch, H, dtype=torch.float32, device=dev) if want_state else None
-    cf = torch.empty(batch, H, dtype=torch.float32, device=dev) if want_state else None
+    cf = torch.empty(batch, H, dtype=torch.float32, device=dev) if want_state is True else None
     L = _lib.lib()
+    ws = _ws(L.sgx_lstm_ws_bytes(), dev)
     with torch.cuda.device(dev):
         _lib.check(L.sgx_lstm_decoder_fwd(_ptr(h0), _ptr(c0), _ptr(last_pos_rel), _ptr(z), _ptr(ped_scene), nz, steps, batch,
                                           _ptr(emb.weight.contiguous()), _ptr(emb.bias.contiguous()),
                                           _ptr(lstm.weight_ih_l0.contiguous()), _ptr(lstm.weight_hh_l0.contiguous()),
                                           _ptr(lstm.bias_ih_l0.contiguous()), _ptr(lstm.bias_hh_l0.contiguous()),
                                           _ptr(hidden2pos.weight.contiguous()), _ptr(hidden2pos.bias.contiguous()), E, H,
-                                          _ptr(pred), _ptr(hf), _ptr(cf), _stream(h0)), 'sgx_lstm_decoder_fwd')
+                                          _ptr(pred), _ptr(hf), _ptr(cf), _ptr(ws), ws.numel(), _stream(h0)), 'sgx_lstm_decoder_fwd')
+    if want_state == 'h':
+        return pred, hf
     return (pred, hf, cf) if want_state else pred

@@ -183,16 +183,20 @@ int sgx_gat_encoder_bwd(const float* x, const float* grad_out, const int32_t* le
  *   steps = 1 gives the single cell update used when the caller pools between steps (models.py:162-168).
  *   nz > 0 folds add_noise (models.py:837-846, 'global' mix) in: h0 is then [batch,H-nz] and the last nz features
  *   of pedestrian p are z[ped_scene[p]] (z [S,nz], ped_scene int32 [batch]); pass z = ped_scene = null, nz = 0 otherwise.
- * Built for H in {32, 48, 64}.
+ * Built for H in {32, 48, 64}.  With a workspace of sgx_lstm_ws_bytes() and H = 32, batch >= 8192, steps >= 2 the
+ * recurrence runs on the tensor cores (tcgen05, 3-way bf16 operand splits = fp32-level accuracy); workspace may be
+ * null (CUDA-core kernel).
  */
+int64_t sgx_lstm_ws_bytes(void);
 int sgx_lstm_encoder_fwd(const float* obs_rel, int32_t T, int64_t batch, const float* We, const float* be,
                          const float* W_ih, const float* W_hh, const float* b_ih, const float* b_hh, int32_t E,
-                         int32_t H, float* h_out, void* stream);
+                         int32_t H, float* h_out, void* workspace, int64_t ws_bytes, void* stream);
 int sgx_lstm_decoder_fwd(const float* h0, const float* c0, const float* last_pos_rel, const float* z,
                          const int32_t* ped_scene, int32_t nz, int32_t steps, int64_t batch,
                          const float* We, const float* be, const float* W_ih, const float* W_hh, const float* b_ih,
                          const float* b_hh, const float* W_hp, const float* b_hp, int32_t E, int32_t H,
-                         float* pred_rel, float* h_final, float* c_final, void* stream);
+                         float* pred_rel, float* h_final, float* c_final, void* workspace, int64_t ws_bytes,
+                         void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Standalone dense-adjacency layers (API parity for GraphAttentionLayer.forward(h, adj),

@@ -444,3 +444,57 @@ def test_evaluate_batch_matches_reference_metrics(sgx):
     n = g['obs_traj'].shape[1]
     assert abs(float(ade) / (n * 12) - float(g['ade'])) < 1e-4
     assert abs(float(fde) / n - float(g['fde'])) < 1e-4
+
+
+# ------------------------------------------------------------------ tensor-core LSTM (3-way bf16 splits, fp32-level accuracy)
+def _with_env(key, val, fn):
+    import os
+    old = os.environ.get(key)
+    os.environ[key] = val
+    try:
+        return fn()
+    finally:
+        if old is None:
+            os.environ.pop(key, None)
+        else:
+            os.environ[key] = old
+
+
+def test_lstm_tensor_core_encoder_matches_cuda_core_and_oracle(sgx):
+    torch.manual_seed(21)
+    enc = sgx['MD'].Encoder(embedding_dim=16, h_dim=32, mlp_dim=64, num_layers=1)
+    n = 128 * 77 + 5                                   # >= 8192 -> tcgen05 path; ragged last tile
+    x = torch.randn(8, n, 2) * 0.4
+    sd = {'e.' + k: v for k, v in enc.state_dict().items()}
+    ref = O.encoder(x[:, :600], sd, 'e.')
+    enc = enc.to(DEV)
+    with torch.no_grad():
+        tc = enc(x.to(DEV))
+        cc = _with_env('SGX_LSTM_TC', '0', lambda: enc(x.to(DEV)))
+    assert_close(tc[:, :600], ref, 2e-5, 'tensor-core encoder vs CPU oracle')
+    assert_close(tc, cc, 2e-5, 'tensor-core encoder vs CUDA-core kernel')
+
+
+def test_lstm_tensor_core_decoder_matches_cuda_core(sgx):
+    g = load_golden('generator_gat_zara1')
+    gen = _generator(sgx, g, 'gat')
+    torch.manual_seed(22)
+    n_scenes = 3000
+    sizes = [int(v) for v in torch.randint(2, 7, (n_scenes,))]
+    sse = sse_from_sizes(sizes).to(DEV)
+    n = sum(sizes)
+    assert n >= 8192
+    ctx = torch.randn(n, 24, device=DEV)
+    obs = torch.rand(8, n, 2, device=DEV) * 10
+    obs_rel = torch.randn(8, n, 2, device=DEV) * 0.3
+    z = torch.randn(n_scenes, 8, device=DEV)
+    with torch.no_grad():
+        tc = gen.decode(ctx, obs, obs_rel, sse, user_noise=z)
+        cc = _with_env('SGX_LSTM_TC', '0', lambda: gen.decode(ctx, obs, obs_rel, sse, user_noise=z))
+    assert tc.shape == (12, n, 2)
+    assert_close(tc, cc, 3e-5, 'tensor-core decoder vs CUDA-core kernel')
+    # and against the autograd (cuDNN) path on a slice of whole scenes
+    k = 200
+    m = int(sse[k - 1, 1])
+    eager = gen.decode(ctx[:m].clone().requires_grad_(True), obs[:, :m], obs_rel[:, :m], sse[:k].clone(), user_noise=z[:k])
+    assert_close(tc[:, :m], eager, 3e-5, 'tensor-core decoder vs cuDNN path')
