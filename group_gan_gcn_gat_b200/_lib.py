@@ -54,6 +54,8 @@ SIGNATURES = {
     'sgx_lstm_ws_bytes': (_I64, []),
     'sgx_lstm_encoder_fwd': (ctypes.c_int, [_P, _I32, _I64, _P, _P, _P, _P, _P, _P, _I32, _I32, _P, _P, _I64, _P]),
     'sgx_lstm_decoder_fwd': (ctypes.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I64] + [_P] * 8 + [_I32, _I32, _P, _P, _P, _P, _I64, _P]),
+    'sgx_displacement_errors': (ctypes.c_int, [_P, _P, _P, _I32, _I64, _P, _P, _I32, _I32, _P]),
+    'sgx_best_of_k': (ctypes.c_int, [_P, _P, _P, _I64, _I32, _P, _P]),
     'sgx_dense_att_fwd': (ctypes.c_int, [_P, _P, _I64, _F32, _P, _P]),
     'sgx_dense_att_bwd': (ctypes.c_int, [_P, _P, _P, _I64, _F32, _P, _P, _P]),
     'sgx_gemm': (ctypes.c_int, [_P, _I64, _I64, _P, _I64, _I64, _P, _I64, _I64, _I64, _I64, _I32, _I32, _P]),

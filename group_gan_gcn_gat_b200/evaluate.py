@@ -30,6 +30,26 @@ def evaluate_batch(generator, obs_traj, obs_traj_rel, seq_start_end, obs_traj_g,
         # reproduce a CPU-seeded stream.
         fn = torch.randn if generator.noise_type == 'gaussian' else (lambda *a, **k: torch.rand(*a, **k) * 2 - 1)
         noise = fn(num_samples, sched.n_scenes, *generator.noise_dim, device=obs_traj.device)
+    dev = obs_traj.device
+    if obs_traj.is_cuda and num_samples <= 32:
+        # fused path: one metrics kernel per sample, one best-of-K kernel (sgx_displacement_errors / sgx_best_of_k)
+        from . import _lib
+        from .ops import _f32, _ptr, _stream
+        L = _lib.lib()
+        batch, T = obs_traj.shape[1], pred_traj_gt.shape[0]
+        ade = torch.empty(batch, num_samples, dtype=torch.float32, device=dev)
+        fde = torch.empty_like(ade)
+        out2 = torch.empty(2, dtype=torch.float32, device=dev)
+        gt, start = _f32(pred_traj_gt, 'pred_traj_gt'), _f32(obs_traj[-1], 'obs_traj')
+        with torch.cuda.device(dev):
+            for k in range(num_samples):
+                rel = generator(obs_traj, obs_traj_rel, seq_start_end, obs_traj_g,
+                                user_noise=None if noise is None else noise[k]).contiguous()
+                _lib.check(L.sgx_displacement_errors(_ptr(rel), _ptr(start), _ptr(gt), T, batch, _ptr(ade), _ptr(fde),
+                                                     num_samples, k, _stream(rel)), 'sgx_displacement_errors')
+            _lib.check(L.sgx_best_of_k(_ptr(ade), _ptr(fde), _ptr(sched.scene_start), sched.n_scenes, num_samples,
+                                       _ptr(out2), _stream(ade)), 'sgx_best_of_k')
+        return out2[0], out2[1]
     ade, fde = [], []
     for k in range(num_samples):
         rel = generator(obs_traj, obs_traj_rel, seq_start_end, obs_traj_g,

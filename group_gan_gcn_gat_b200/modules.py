@@ -85,14 +85,14 @@ class PoolHiddenNet(nn.Module):
         h = h_states.reshape(-1, self.h_dim)
         if h.shape[0] != sched.batch:
             raise ValueError('h_states has %d rows but seq_start_end covers %d pedestrians' % (h.shape[0], sched.batch))
-        out, _ = ops.pool_fwd(h, end_pos, sched.ped_start, sched.ped_end, sched.pair_off, sched.tile_first,
+        out, _ = ops.call(ops.pool_fwd, h, end_pos, sched.ped_start, sched.ped_end, sched.pair_off, sched.tile_first,
                               sched.n_pairs, self.spatial_embedding.weight, self.spatial_embedding.bias,
                               l1.weight, l1.bias, l2.weight, l2.bias, _precision_code(self.precision))
         return out
 
 
 def _groups_for(sched, end_group):
-    return ops.group_ids(end_group.reshape(-1).float(), sched.ped_start, sched.ped_end, sched.scene_start)
+    return ops.call(ops.group_ids, end_group.reshape(-1).float(), sched.ped_start, sched.ped_end, sched.scene_start)
 
 
 class GraphAttentionLayer(nn.Module):
@@ -169,7 +169,7 @@ class GATEncoder(nn.Module):
         Wi, ai, Wio, aio = self.gat_intra.stacked()
         We, ae, Weo, aeo = self.gat_inter.stacked()
         chunk_scene, n_chunks = sched.chunks(32) if self.n_heads == 1 else (sched.scene_start[:0], 0)
-        return ops.gat_encoder_fwd(h_states, leader, gsize, sched.ped_start, sched.ped_end, sched.n_scenes, Wi, ai, Wio,
+        return ops.call(ops.gat_encoder_fwd, h_states, leader, gsize, sched.ped_start, sched.ped_end, sched.n_scenes, Wi, ai, Wio,
                                    aio, We, ae, Weo, aeo, self.out_embedding.weight, self.out_embedding.bias,
                                    float(self.alpha), sched.scene_start, chunk_scene, n_chunks)
 
@@ -214,6 +214,6 @@ class GCNModule(nn.Module):
         if h_states.shape[0] != sched.batch:
             raise ValueError('h_states has %d rows but seq_start_end covers %d pedestrians' % (h_states.shape[0], sched.batch))
         leader, gsize, _gid, ngrp = _groups_for(sched, end_group)
-        return ops.gcn_module_fwd(h_states, leader, gsize, sched.ped_start, sched.ped_end, sched.scene_start, ngrp,
+        return ops.call(ops.gcn_module_fwd, h_states, leader, gsize, sched.ped_start, sched.ped_end, sched.scene_start, ngrp,
                                   self.gcn_intra.W[0], self.gcn_intra.W[1], self.gcn_inter.W[0], self.gcn_inter.W[1],
                                   self.out_embedding.weight, self.out_embedding.bias)

@@ -36,8 +36,27 @@ def _i32(t, name):
     return t.contiguous()
 
 
+_ws_cache = {}
+
+
 def _ws(nbytes, device):
-    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+    """Scratch for one op call.  Reused per (device, current stream): ops on one stream run in order, so the previous
+    user is done before the next kernel touches it; a different stream gets its own buffer."""
+    nbytes = max(int(nbytes), 256)
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes * 1.25), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def call(op, *args):
+    """Dispatch through torch.library only when autograd needs it; otherwise call the op body directly (the
+    dispatcher + custom_op wrapper costs ~100 us per call, more than some of the kernels)."""
+    if torch.is_grad_enabled() and any(torch.is_tensor(a) and a.requires_grad for a in args):
+        return op(*args)
+    return op._init_fn(*args)
 
 
 # ---------------------------------------------------------------------------------------------

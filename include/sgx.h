@@ -199,6 +199,17 @@ int sgx_lstm_decoder_fwd(const float* h0, const float* c0, const float* last_pos
                          void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Displacement metrics + best-of-K reduction: relative_to_abs (sgan/utils.py:83-96) +
+ * displacement_error / final_displacement_error mode='raw' (sgan/losses.py:74-119) for sample k, written to column k
+ * of ade / fde [batch,K]; then evaluate_helper (scripts/evaluate_model.py:58-69): out2[0] = sum over scenes of
+ * min_k sum_{peds} ade[p][k], out2[1] the same for fde.  pred_rel, gt [T,batch,2]; start_pos [batch,2]; K <= 32.
+ */
+int sgx_displacement_errors(const float* pred_rel, const float* start_pos, const float* gt, int32_t T, int64_t batch,
+                            float* ade, float* fde, int32_t K, int32_t k, void* stream);
+int sgx_best_of_k(const float* ade, const float* fde, const int32_t* scene_start, int64_t n_scenes, int32_t K,
+                  float* out2, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Standalone dense-adjacency layers (API parity for GraphAttentionLayer.forward(h, adj),
  * sgan/models.py:198-210, and GCN.forward(A, X), models.py:573-580): the masked-softmax rows below
  * plus sgx_gemm for every product (Wh = h W, att Wh, (A H) W ...).  n x n dense `adj`.

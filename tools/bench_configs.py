@@ -1,0 +1,115 @@
+"""Measurements of the other BASELINE.json configs next to bench.py's headline:
+  cfg 3  GCNModule / GATEncoder op-level forward + backward at S = 2^16 zara1-shaped scenes
+  cfg 4  dense crowds: N in {64..1024}, pool_every_timestep = 1, pred 12 (13 pooling calls per forward)
+One JSON line per measurement (CUDA events, median of reps, L2 flushed between reps)."""
+import json
+import os
+import statistics
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from group_gan_gcn_gat_b200 import models as MD, modules as M  # noqa: E402
+
+dev = torch.device('cuda:0')
+torch.backends.cudnn.allow_tf32 = False
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else {}
+
+
+def timed(fn, reps=7, warm=3):
+    ts = []
+    for i in range(reps + warm):
+        flush.fill_(i)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return statistics.median(ts[warm:])
+
+
+def sse_of(sizes):
+    st = np.concatenate([[0], np.cumsum(sizes)])
+    return torch.from_numpy(np.stack([st[:-1], st[1:]], 1).astype(np.int64))
+
+
+def cfg3():
+    data = bench.synth_batch(1 << 16, 1237)
+    sse = data['seq_start_end'].to(dev)
+    n = int(sse[-1, 1])
+    lab = data['obs_traj_g'][-1].to(dev)
+    pos = data['obs_traj'][-1].to(dev)
+    hbm = peaks.get('hbm_gbs', 6650.0)
+    for name, mod in (('GCNModule', M.GCNModule()), ('GATEncoder', M.GATEncoder(None, 1, 0, 0.2))):
+        mod = mod.to(dev)
+        with torch.no_grad():
+            for p in mod.parameters():
+                if name == 'GCNModule' and p.dim() == 2 and tuple(p.shape) != (24, 32):
+                    p.mul_(0.15)
+        x = torch.randn(n, 40, device=dev)
+        with torch.no_grad():
+            f_ms = timed(lambda: mod(x, sse, pos, lab))
+        xg = x.clone().requires_grad_(True)
+        up = torch.randn(n, 24, device=dev)
+
+        def fb():
+            mod.zero_grad(set_to_none=True)
+            xg.grad = None
+            (mod(xg, sse, pos, lab) * up).sum().backward()
+        fb_ms = timed(fb)
+        fwd_b, bwd_b = 260 * n + 16 * (1 << 16), 420 * n
+        print(json.dumps({'config': 'cfg3 op-level', 'op': name, 'scenes': 1 << 16, 'peds': n, 'fwd_ms': f_ms,
+                          'fwd_bwd_ms': fb_ms, 'fwd_GBps_algorithmic': fwd_b / f_ms / 1e6,
+                          'fwd_frac_hbm': fwd_b / f_ms / 1e6 / hbm,
+                          'fwd_bwd_GBps_algorithmic': (fwd_b + bwd_b) / fb_ms / 1e6,
+                          'fwd_bwd_frac_hbm': (fwd_b + bwd_b) / fb_ms / 1e6 / hbm}))
+
+
+def cfg4():
+    torch.manual_seed(0)
+    gen = MD.TrajectoryGenerator(obs_len=8, pred_len=12, embedding_dim=16, encoder_h_dim=32, decoder_h_dim=32, mlp_dim=64,
+                                 noise_dim=(8,), noise_mix_type='global', pooling_type='pool_net', pool_every_timestep=True,
+                                 bottleneck_dim=8, batch_norm=False, n_heads=1, alpha=0.2).to(dev)
+    for m in gen.modules():
+        if isinstance(m, torch.nn.Linear):
+            torch.nn.init.kaiming_normal_(m.weight)
+    for precision in ('bf16', 'fp32'):
+        gen.pool_net.precision = precision
+        gen.decoder.pool_net.precision = precision
+        for n in (64, 128, 256, 512, 1024):
+            s = max(1, (8 << 20) // (n * n))
+            rng = np.random.RandomState(n)
+            sizes = [n] * s
+            tot = n * s
+            disp = rng.normal(0, 0.3, size=(8, tot, 2)).astype(np.float32)
+            disp[0] = 0
+            obs = rng.uniform(0, 15, size=(1, tot, 2)).astype(np.float32) + np.cumsum(disp, 0)
+            lab = np.floor(rng.uniform(0, 1, tot) * max(1, n // 3)).astype(np.float32) + 1
+            lab[rng.uniform(0, 1, tot) < 0.1] = 0
+            t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+            o, orel = t(obs), t(disp)
+            grp = t(np.broadcast_to(lab[None, :, None], (8, tot, 1)).copy())
+            sse = sse_of(sizes).to(dev)
+            z = torch.randn(s, 8, device=dev)
+            with torch.no_grad():
+                ms = timed(lambda: gen(o, orel, sse, grp, user_noise=z), reps=5, warm=2)
+            pairs = n * n * s
+            flops = 13 * pairs * bench.POOL_FLOPS_PER_PAIR
+            print(json.dumps({'config': 'cfg4 dense crowd, pool_every_timestep=1, pred 12', 'precision': precision, 'N': n,
+                              'scenes': s, 'peds': tot, 'pairs_per_pool_call': pairs, 'forward_ms': ms,
+                              'traj_per_s_one_sample': tot / ms * 1e3,
+                              'pool_as_written_TFLOPs_over_whole_forward': flops / ms / 1e9}))
+
+
+if __name__ == '__main__':
+    which = sys.argv[1:] or ['cfg3', 'cfg4']
+    if 'cfg3' in which:
+        cfg3()
+    if 'cfg4' in which:
+        cfg4()
