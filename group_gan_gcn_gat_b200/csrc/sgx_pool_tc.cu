@@ -227,15 +227,33 @@ pool_tc_kernel(const __nv_bfloat16* __restrict__ hb, const float* __restrict__ p
         float bias2[B];
 #pragma unroll
         for (int b = 0; b < B; ++b) bias2[b] = b2[b];
+        // The per-tile decode needs tile_first -> (pair_off, ped_start) slice -> (pos, hb) gathers: three dependent
+        // global-load levels.  The first two are software-pipelined one tile ahead (registers), so only the gathers'
+        // latency is exposed per tile.
+        int lo = 0, hi = -1, sp = 0, sp_x = 0;
+        int64_t so = 0, so_x = 0;
+        if (set < my_tiles) {
+            const int64_t t0 = blockIdx.x + (int64_t)set * gridDim.x;
+            lo = tile_first[t0];
+            hi = (t0 + 1 < n_tiles) ? tile_first[t0 + 1] : batch - 1;
+            if (lo + rt <= hi) { so = pair_off[lo + rt]; sp = ped_start[lo + rt]; }
+            if (rt == 0 && lo + 128 <= hi) { so_x = pair_off[lo + 128]; sp_x = ped_start[lo + 128]; }
+        }
         for (int it = set; it < my_tiles + 2; it += 2) {
             if (it < my_tiles) {
                 const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
                 const int st = it & (NST - 1);
-                // ---- stage this tile's slice of the ped tables (coalesced), decode (i,j) from shared memory ----
-                const int lo = tile_first[tile];
-                const int hi = (tile + 1 < n_tiles) ? tile_first[tile + 1] : batch - 1;   // hi - lo <= 128
-                if (lo + rt <= hi) { soff[rt] = pair_off[lo + rt]; sps[rt] = ped_start[lo + rt]; }
-                if (rt == 0 && lo + 128 <= hi) { soff[128] = pair_off[lo + 128]; sps[128] = ped_start[lo + 128]; }
+                // ---- publish this tile's slice of the ped tables, decode (i,j) from shared memory ----
+                if (lo + rt <= hi) { soff[rt] = so; sps[rt] = sp; }
+                if (rt == 0 && lo + 128 <= hi) { soff[128] = so_x; sps[128] = sp_x; }
+                const int lo_c = lo, hi_c = hi;
+                const bool has_next = it + 2 < my_tiles;
+                int lo_n = 0, hi_n = -1;
+                if (has_next) {                                  // bounds of this set's next tile
+                    const int64_t tn = blockIdx.x + (int64_t)(it + 2) * gridDim.x;
+                    lo_n = tile_first[tn];
+                    hi_n = (tn + 1 < n_tiles) ? tile_first[tn + 1] : batch - 1;
+                }
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");
                 const int64_t q = tile * TILE + row;
                 uint8_t* xrow = smem + TcSmem::X + st * TILE * 128;
@@ -246,12 +264,12 @@ pool_tc_kernel(const __nv_bfloat16* __restrict__ hb, const float* __restrict__ p
                 for (int c = 0; c < H / 8; ++c) hv[c] = make_uint4(0, 0, 0, 0);
                 const bool valid = q < n_pairs;
                 if (valid) {
-                    int a = 0, z = hi - lo;
+                    int a = 0, z = hi_c - lo_c;
                     while (a < z) {
                         int mid = (a + z + 1) >> 1;
                         if (soff[mid] <= q) a = mid; else z = mid - 1;
                     }
-                    const int i = lo + a;
+                    const int i = lo_c + a;
                     const int j = sps[a] + (int)(q - soff[a]);
                     ij = make_int2(i, j);
                     pi = *reinterpret_cast<const float2*>(pos + 2 * (int64_t)i);
@@ -260,6 +278,9 @@ pool_tc_kernel(const __nv_bfloat16* __restrict__ hb, const float* __restrict__ p
 #pragma unroll
                     for (int c = 0; c < H / 8; ++c) hv[c] = hrow[c];
                 }
+                lo = lo_n; hi = hi_n;                           // next tile's slice -> registers
+                if (lo + rt <= hi) { so = pair_off[lo + rt]; sp = ped_start[lo + rt]; }
+                if (rt == 0 && lo + 128 <= hi) { so_x = pair_off[lo + 128]; sp_x = ped_start[lo + 128]; }
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");   // slice may be overwritten next round
                 TWAIT(&x_free[st], (uint32_t)(((it / NST) & 1) ^ 1), 0);
                 uint4 c0 = make_uint4(0, 0, 0, 0);

@@ -1,6 +1,7 @@
 import ctypes, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench
 from group_gan_gcn_gat_b200 import _lib
 from tools.time_pool import time_case
 L = _lib.lib()
@@ -8,12 +9,11 @@ buf = torch.zeros(40, dtype=torch.int64, device='cuda')
 h = ctypes.CDLL(_lib.LIB_PATH)
 h.sgx_debug_tc_stats.argtypes = [ctypes.c_void_p]
 h.sgx_debug_tc_stats(buf.data_ptr())
-for dbg in (0, 15):
-    os.environ['SGX_POOL_TC_DBG'] = str(dbg)
-    time_case([1024] * 8, (16, 32, 8), 'bf16', reps=3)
+names = ['G1 issuer (x_full, d1_free)', 'G2 issuer (-, -, d2_free, h_ready)', 'ROW0 (x_free, d2_full)', 'EPI0 (d1_full, h_free)', 'EPI1 (d1_full, h_free)']
+for label, sizes in (('dense N=1024 x8', [1024] * 8), ('zara-shaped 65536 scenes', list(bench.synth_batch(1 << 16, 1236)['sizes']))):
+    time_case(sizes, (16, 32, 8), 'bf16', reps=3)
     torch.cuda.synchronize()
     s = buf.cpu().view(5, 8)
-    names = ['MMA  (x_full, d1_free, d2_free, h_ready)', 'ROW0 (x_free, d2_full)', 'ROW1 (x_free, d2_full)', 'EPI0 (d1_full, h_free)', 'EPI1 (d1_full, h_free)']
     for r in range(5):
         n = max(1, int(s[r, 5]))
-        print('dbg', dbg, names[r], 'per-tile wait cycles:', [int(v) // n for v in s[r, :4]], 'total/tile:', int(s[r, 4]) // n, 'tiles', n)
+        print(label, '|', names[r], 'per-tile wait cycles:', [int(v) // n for v in s[r, :4]], 'total/tile:', int(s[r, 4]) // n, 'tiles', n)
