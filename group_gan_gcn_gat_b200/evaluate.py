@@ -22,7 +22,10 @@ def best_of_k_sum(per_sample, sched):
 
 @torch.no_grad()
 def evaluate_batch(generator, obs_traj, obs_traj_rel, seq_start_end, obs_traj_g, pred_traj_gt, num_samples=20,
-                   noise=None):
+                   noise=None, hoist_context=False):
+    """hoist_context=True computes the noise-independent part of the forward (encoder, pooling, graph context:
+    everything before sgan/models.py:909) once instead of num_samples times -- bit-identical results when the
+    decoder does not pool per step.  Off by default: the reference recomputes it per sample."""
     sched = get_schedule(seq_start_end, obs_traj.device)
     if noise is None and generator.noise_dim and generator.noise_mix_type == 'global':
         # one draw for all K samples on the device generator.  The reference draws each sample on the CPU generator and
@@ -41,10 +44,14 @@ def evaluate_batch(generator, obs_traj, obs_traj_rel, seq_start_end, obs_traj_g,
         fde = torch.empty_like(ade)
         out2 = torch.empty(2, dtype=torch.float32, device=dev)
         gt, start = _f32(pred_traj_gt, 'pred_traj_gt'), _f32(obs_traj[-1], 'obs_traj')
+        ctx = generator.context(obs_traj, obs_traj_rel, seq_start_end, obs_traj_g) if hoist_context else None
         with torch.cuda.device(dev):
             for k in range(num_samples):
-                rel = generator(obs_traj, obs_traj_rel, seq_start_end, obs_traj_g,
-                                user_noise=None if noise is None else noise[k]).contiguous()
+                nz = None if noise is None else noise[k]
+                if ctx is not None:
+                    rel = generator.decode(ctx, obs_traj, obs_traj_rel, seq_start_end, user_noise=nz).contiguous()
+                else:
+                    rel = generator(obs_traj, obs_traj_rel, seq_start_end, obs_traj_g, user_noise=nz).contiguous()
                 _lib.check(L.sgx_displacement_errors(_ptr(rel), _ptr(start), _ptr(gt), T, batch, _ptr(ade), _ptr(fde),
                                                      num_samples, k, _stream(rel)), 'sgx_displacement_errors')
             _lib.check(L.sgx_best_of_k(_ptr(ade), _ptr(fde), _ptr(sched.scene_start), sched.n_scenes, num_samples,

@@ -444,6 +444,9 @@ def test_evaluate_batch_matches_reference_metrics(sgx):
     n = g['obs_traj'].shape[1]
     assert abs(float(ade) / (n * 12) - float(g['ade'])) < 1e-4
     assert abs(float(fde) / n - float(g['fde'])) < 1e-4
+    ade_h, fde_h = evaluate_batch(gen, t('obs_traj'), t('obs_traj_rel'), t('seq_start_end'), t('obs_traj_g'),
+                                  t('pred_traj_gt'), num_samples=g['noise'].shape[0], noise=t('noise'), hoist_context=True)
+    assert float(ade_h) == float(ade) and float(fde_h) == float(fde)      # hoisting is bit-identical (row f2)
 
 
 # ------------------------------------------------------------------ tensor-core LSTM (3-way bf16 splits, fp32-level accuracy)
