@@ -428,19 +428,23 @@ struct FusedW {                        // shared-memory weight block (floats)
 // y[0..NO) = sum_c xrow[c] * W[c][0..NO)   (W row-major [NI][NO] in smem, xrow in smem)
 template <int NI, int NO>
 __device__ __forceinline__ void gemv_rows(const float* __restrict__ xrow, const float* __restrict__ W, float (&y)[NO]) {
+    float2 acc[NO / 2];                          // packed FFMA2: (y[2o], y[2o+1]) += (x, x) * (W[c][2o], W[c][2o+1])
 #pragma unroll
-    for (int o = 0; o < NO; ++o) y[o] = 0.f;
+    for (int o = 0; o < NO / 2; ++o) acc[o] = make_float2(0.f, 0.f);
 #pragma unroll 2
     for (int c = 0; c < NI; ++c) {
         const float xv = xrow[c];
+        const float2 xx = make_float2(xv, xv);
         const float4* w = reinterpret_cast<const float4*>(W + c * NO);
 #pragma unroll
         for (int o = 0; o < NO / 4; ++o) {
             const float4 v = w[o];
-            y[4 * o] = fmaf(xv, v.x, y[4 * o]); y[4 * o + 1] = fmaf(xv, v.y, y[4 * o + 1]);
-            y[4 * o + 2] = fmaf(xv, v.z, y[4 * o + 2]); y[4 * o + 3] = fmaf(xv, v.w, y[4 * o + 3]);
+            acc[2 * o] = ffma2(xx, make_float2(v.x, v.y), acc[2 * o]);
+            acc[2 * o + 1] = ffma2(xx, make_float2(v.z, v.w), acc[2 * o + 1]);
         }
     }
+#pragma unroll
+    for (int o = 0; o < NO / 2; ++o) { y[2 * o] = acc[o].x; y[2 * o + 1] = acc[o].y; }
 }
 
 // attention of one node over the slots [b,e) of its scene that satisfy `pick`; rows/scores live in shared memory
@@ -477,18 +481,22 @@ __device__ __forceinline__ void attend_smem(const float* __restrict__ rows, cons
 // y[0..NO) = sum_c x[c] * W[c][0..NO) with x in registers (fully unrolled; used for the 72 -> 16 maps)
 template <int NI, int NO>
 __device__ __forceinline__ void gemv_regs(const float (&x)[NI], const float* __restrict__ W, float (&y)[NO]) {
+    float2 acc[NO / 2];
 #pragma unroll
-    for (int o = 0; o < NO; ++o) y[o] = 0.f;
+    for (int o = 0; o < NO / 2; ++o) acc[o] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int c = 0; c < NI; ++c) {
+        const float2 xx = make_float2(x[c], x[c]);
         const float4* w = reinterpret_cast<const float4*>(W + c * NO);
 #pragma unroll
         for (int o = 0; o < NO / 4; ++o) {
             const float4 v = w[o];
-            y[4 * o] = fmaf(x[c], v.x, y[4 * o]); y[4 * o + 1] = fmaf(x[c], v.y, y[4 * o + 1]);
-            y[4 * o + 2] = fmaf(x[c], v.z, y[4 * o + 2]); y[4 * o + 3] = fmaf(x[c], v.w, y[4 * o + 3]);
+            acc[2 * o] = ffma2(xx, make_float2(v.x, v.y), acc[2 * o]);
+            acc[2 * o + 1] = ffma2(xx, make_float2(v.z, v.w), acc[2 * o + 1]);
         }
     }
+#pragma unroll
+    for (int o = 0; o < NO / 2; ++o) { y[2 * o] = acc[o].x; y[2 * o + 1] = acc[o].y; }
 }
 
 template <int F>
