@@ -31,7 +31,11 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ['NCCL_DEBUG'] = os.environ.get('SGX_NCCL_DEBUG', 'WARN')   # keep stdout to the one JSON line
+# NCCL prints its version banner on STDOUT at any debug level >= VERSION; keep stdout to the one JSON line
+if 'SGX_NCCL_DEBUG' in os.environ:
+    os.environ['NCCL_DEBUG'] = os.environ['SGX_NCCL_DEBUG']
+else:
+    os.environ.pop('NCCL_DEBUG', None)
 
 ZARA1_HIST = {2: 212, 3: 136, 4: 109, 5: 55, 6: 32, 7: 10, 8: 20, 9: 8, 10: 12, 11: 4, 12: 1, 13: 2, 14: 1}
 K_SAMPLES = 20
@@ -213,7 +217,7 @@ def main():
         sizes = data['sizes'][mine]
         st = np.concatenate([[0], np.cumsum(sizes)])
         data = dict(obs_traj=data['obs_traj'][:, idx], obs_traj_rel=data['obs_traj_rel'][:, idx],
-                    obs_traj_g=data['obs_traj_g'][:, idx],
+                    obs_traj_g=data['obs_traj_g'][:, idx], pred_traj_gt=data['pred_traj_gt'][:, idx],
                     seq_start_end=torch.from_numpy(np.stack([st[:-1], st[1:]], 1).astype(np.int64)), sizes=sizes)
     n_scenes = data['seq_start_end'].shape[0]
     peds = int(data['seq_start_end'][-1, 1])
