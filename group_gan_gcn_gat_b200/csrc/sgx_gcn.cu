@@ -387,6 +387,180 @@ static int gcn_forward(const float* x, const int32_t* leader, const int32_t* gsi
     return SGX_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Fused forward for batches whose scenes all fit a warp (N <= 32): one WARP per chunk of whole scenes, lanes <-> peds.
+// Leader lanes run the intra GCN on their group's mean, the first lane of every scene runs the inter GCN on the mean
+// of the scene's group states, every lane writes its output row: one launch, only x / group structure / out in HBM.
+// ------------------------------------------------------------------------------------------------
+constexpr int GF_WARPS = 8;
+constexpr int GF_RA = 44;                                     // stride of the 40-wide x rows (16 B aligned)
+constexpr int GF_SCRATCH = 32 * GF_RA + 32 * 16 * 3 + 32;     // x rows, X1 / Xg / Y rows, leader slots
+
+template <int NI, int NO>
+__device__ __forceinline__ void gemv_regs2(const float (&x)[NI], const float* __restrict__ W /*[NI][NO] smem*/,
+                                           float (&y)[NO]) {
+    float2 acc[NO / 2];
+#pragma unroll
+    for (int o = 0; o < NO / 2; ++o) acc[o] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < NI; ++c) {
+        const float2 xx = make_float2(x[c], x[c]);
+        const float4* w = reinterpret_cast<const float4*>(W + c * NO);
+#pragma unroll
+        for (int o = 0; o < NO / 4; ++o) {
+            const float4 v = w[o];
+            acc[2 * o] = ffma2(xx, make_float2(v.x, v.y), acc[2 * o]);
+            acc[2 * o + 1] = ffma2(xx, make_float2(v.z, v.w), acc[2 * o + 1]);
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < NO / 2; ++o) { y[2 * o] = acc[o].x; y[2 * o + 1] = acc[o].y; }
+}
+
+template <int IN, int HID, int OUT, int FIN>
+__global__ void __launch_bounds__(GF_WARPS * 32)
+gcn_fused_fwd_kernel(const float* __restrict__ x, const int32_t* __restrict__ leader, const int32_t* __restrict__ gsize,
+                     const int32_t* __restrict__ ped_start, const int32_t* __restrict__ ped_end,
+                     const int32_t* __restrict__ scene_start, const int32_t* __restrict__ chunk_scene, int n_chunks,
+                     const float* __restrict__ W0, const float* __restrict__ W1, const float* __restrict__ V0,
+                     const float* __restrict__ V1, const float* __restrict__ Wo, const float* __restrict__ bo,
+                     float* __restrict__ out) {
+    extern __shared__ __align__(16) uint8_t raw[];
+    float* sW0 = reinterpret_cast<float*>(raw);               // [IN][HID]
+    float* sW1 = sW0 + IN * HID;                              // [HID][OUT]
+    float* sV0 = sW1 + HID * OUT;                             // [OUT][HID]
+    float* sV1 = sV0 + OUT * HID;                             // [HID][OUT]
+    float* sWo = sV1 + HID * OUT;                             // [FIN][2*OUT]
+    float* sbo = sWo + FIN * 2 * OUT;                         // [FIN]
+    float* bufs = sbo + ((FIN + 3) / 4) * 4;
+    {
+        const float* src[6] = {W0, W1, V0, V1, Wo, bo};
+        float* dst[6] = {sW0, sW1, sV0, sV1, sWo, sbo};
+        const int cnt[6] = {IN * HID, HID * OUT, OUT * HID, HID * OUT, FIN * 2 * OUT, FIN};
+        for (int k = 0; k < 6; ++k)
+            for (int e = threadIdx.x; e < cnt[k]; e += blockDim.x) dst[k][e] = src[k][e];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* A = bufs + warp * GF_SCRATCH;
+    float* X1s = A + 32 * GF_RA;
+    float* Xgs = X1s + 32 * 16;
+    float* Ys = Xgs + 32 * 16;
+    int* lead_slot = reinterpret_cast<int*>(Ys + 32 * 16);
+    const int n_warps_total = gridDim.x * GF_WARPS;
+    for (int chunk = blockIdx.x * GF_WARPS + warp; chunk < n_chunks; chunk += n_warps_total) {
+        const int p0 = scene_start[chunk_scene[chunk]];
+        const int np = scene_start[chunk_scene[chunk + 1]] - p0;
+        const bool live = lane < np;
+        const int p = p0 + lane;
+        int b = 0, e = 0, my_lead = lane, k = 1;
+        if (live) {
+            b = ped_start[p] - p0; e = ped_end[p] - p0; my_lead = leader[p] - p0; k = gsize[p];
+            const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)p * IN);
+#pragma unroll
+            for (int c = 0; c < IN / 4; ++c) reinterpret_cast<float4*>(A + lane * GF_RA)[c] = xr[c];
+        }
+        lead_slot[lane] = live ? my_lead : -1;
+        const float a = __frcp_rn((float)k);
+        __syncwarp();
+        // ---- intra GCN on the group mean (leader lanes) ----
+        if (live && my_lead == lane) {
+            float m1[IN];
+#pragma unroll
+            for (int c = 0; c < IN; ++c) m1[c] = 0.f;
+            for (int q = lane; q < e; ++q) {
+                if (lead_slot[q] != lane) continue;
+                const float4* row = reinterpret_cast<const float4*>(A + q * GF_RA);
+#pragma unroll
+                for (int c = 0; c < IN / 4; ++c) {
+                    const float4 v = row[c];
+                    m1[4 * c] = fmaf(a, v.x, m1[4 * c]); m1[4 * c + 1] = fmaf(a, v.y, m1[4 * c + 1]);
+                    m1[4 * c + 2] = fmaf(a, v.z, m1[4 * c + 2]); m1[4 * c + 3] = fmaf(a, v.w, m1[4 * c + 3]);
+                }
+            }
+            float h1[HID];
+            gemv_regs2<IN, HID>(m1, sW0, h1);
+#pragma unroll
+            for (int f = 0; f < HID; ++f) h1[f] = repeat_sum(a * fmaxf(h1[f], 0.f), k);      // = M2
+            float x1[OUT];
+            gemv_regs2<HID, OUT>(h1, sW1, x1);
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) {
+                x1[o] = fmaxf(x1[o], 0.f);
+                X1s[lane * 16 + o] = x1[o];
+                Xgs[lane * 16 + o] = repeat_sum(a * x1[o], k);
+            }
+        }
+        __syncwarp();
+        // ---- inter GCN on the mean of the scene's group states (first lane of every scene) ----
+        if (live && lane == b) {
+            int G = 0;
+            for (int q = b; q < e; ++q) G += (lead_slot[q] == q) ? 1 : 0;
+            const float c = __frcp_rn((float)G);
+            float n1[OUT];
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) n1[o] = 0.f;
+            for (int q = b; q < e; ++q) {
+                if (lead_slot[q] != q) continue;
+#pragma unroll
+                for (int o = 0; o < OUT; ++o) n1[o] = fmaf(c, Xgs[q * 16 + o], n1[o]);
+            }
+            float k1[HID];
+            gemv_regs2<OUT, HID>(n1, sV0, k1);
+#pragma unroll
+            for (int f = 0; f < HID; ++f) k1[f] = repeat_sum(c * fmaxf(k1[f], 0.f), G);      // = N2
+            float y[OUT];
+            gemv_regs2<HID, OUT>(k1, sV1, y);
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) Ys[lane * 16 + o] = fmaxf(y[o], 0.f);
+        }
+        __syncwarp();
+        // ---- output Linear on [X1 of my group ; Y of my scene / |group|] ----
+        if (live) {
+            float cat[2 * OUT];
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) { cat[o] = X1s[my_lead * 16 + o]; cat[OUT + o] = a * Ys[b * 16 + o]; }
+            float* orow = out + (int64_t)p * FIN;
+#pragma unroll
+            for (int o4 = 0; o4 < FIN / 4; ++o4) {
+                float yv[4];
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const int o = 4 * o4 + kk;
+                    float acc = sbo[o];
+                    const float4* wr = reinterpret_cast<const float4*>(sWo + o * 2 * OUT);
+#pragma unroll
+                    for (int c = 0; c < 2 * OUT / 4; ++c) {
+                        const float4 v = wr[c];
+                        acc = fmaf(cat[4 * c], v.x, acc); acc = fmaf(cat[4 * c + 1], v.y, acc);
+                        acc = fmaf(cat[4 * c + 2], v.z, acc); acc = fmaf(cat[4 * c + 3], v.w, acc);
+                    }
+                    yv[kk] = acc;
+                }
+                reinterpret_cast<float4*>(orow)[o4] = make_float4(yv[0], yv[1], yv[2], yv[3]);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <int IN, int FIN>
+static int gcn_fused_launch(const float* x, const int32_t* leader, const int32_t* gsize, const int32_t* ps,
+                            const int32_t* pe, const int32_t* scene_start, const int32_t* chunk_scene, int n_chunks,
+                            const float* W0, const float* W1, const float* V0, const float* V1, const float* Wo,
+                            const float* bo, float* out, cudaStream_t st) {
+    auto kern = gcn_fused_fwd_kernel<IN, 72, 16, FIN>;
+    const int wfloats = IN * 72 + 72 * 16 * 3 + FIN * 32 + ((FIN + 3) / 4) * 4;
+    const int smem = (wfloats + GF_WARPS * GF_SCRATCH) * (int)sizeof(float);
+    SGX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int grid = std::min((n_chunks + GF_WARPS - 1) / GF_WARPS, 148);
+    kern<<<grid, GF_WARPS * 32, smem, st>>>(x, leader, gsize, ps, pe, scene_start, chunk_scene, n_chunks, W0, W1, V0, V1,
+                                            Wo, bo, out);
+    SGX_LAUNCH_CHECK();
+    return SGX_OK;
+}
+
 }  // namespace sgx
 
 using namespace sgx;
@@ -487,5 +661,22 @@ extern "C" int sgx_gcn_module_bwd(const float* x, const float* grad_out, const i
     GCN_DISPATCH((rc = gcn_backward<I, 72, 16, F>(x, grad_out, leader, group_size, ped_start, ped_end, scene_start,
                                                   n_group, batch, n_scenes, W0, W1, V0, V1, Wo, bo, grad_x, grad_W0,
                                                   grad_W1, grad_V0, grad_V1, grad_Wo, grad_bo, w, st)));
+    return rc;
+}
+
+// Fused single-launch forward for batches whose scenes all have <= 32 pedestrians (chunk_scene / n_chunks from
+// sgx_schedule_chunks with cap = 32).  Same dims as sgx_gcn_module_fwd with hid = 72, out = 16, final % 4 == 0.
+extern "C" int sgx_gcn_module_fused_fwd(const float* x, const int32_t* leader, const int32_t* group_size,
+                                        const int32_t* ped_start, const int32_t* ped_end, const int32_t* scene_start,
+                                        const int32_t* chunk_scene, int64_t n_chunks, const float* W0, const float* W1,
+                                        const float* V0, const float* V1, const float* Wo, const float* bo, int32_t IN,
+                                        int32_t HID, int32_t OUT, int32_t FIN, float* out, void* stream) {
+    SGX_REQUIRE(x && leader && group_size && ped_start && ped_end && scene_start && chunk_scene && W0 && W1 && V0 && V1 &&
+                    Wo && bo && out, "sgx_gcn_module_fused_fwd: null pointer");
+    SGX_REQUIRE(n_chunks > 0 && n_chunks < ((int64_t)1 << 31), "sgx_gcn_module_fused_fwd: bad chunk count");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = SGX_OK;
+    GCN_DISPATCH((rc = gcn_fused_launch<I, F>(x, leader, group_size, ped_start, ped_end, scene_start, chunk_scene,
+                                              (int)n_chunks, W0, W1, V0, V1, Wo, bo, out, st)));
     return rc;
 }

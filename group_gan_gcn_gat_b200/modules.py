@@ -207,6 +207,15 @@ class GCNModule(nn.Module):
         self.gcn_inter = GCN(input_dim=16, hidden_dim=hidden_dim, out_dim=out_dim, gcn_layers=gcn_layers)
         self.out_embedding = nn.Linear(out_dim * 2, final_dim)
 
+    @staticmethod
+    def _chunks(sched):
+        # The single-launch warp-per-chunk kernel (sgx_gcn_module_fused_fwd) measured SLOWER than the three-kernel path
+        # on B200 (0.45 vs 0.28 ms at 245 k peds: the group / scene MLPs run on ~45 % / ~27 % of the lanes at 8 warps per
+        # SM), so it is opt-in.
+        if os.environ.get('SGX_GCN_FUSED') == '1':
+            return sched.chunks(32)
+        return sched.scene_start[:0], 0
+
     def forward(self, h_states, seq_start_end, end_pos, end_group):
         if self.gcn_layers != 2:
             raise NotImplementedError('GCNModule fused kernel is built for gcn_layers=2 (the reference wiring)')
@@ -216,4 +225,4 @@ class GCNModule(nn.Module):
         leader, gsize, _gid, ngrp = _groups_for(sched, end_group)
         return ops.call(ops.gcn_module_fwd, h_states, leader, gsize, sched.ped_start, sched.ped_end, sched.scene_start, ngrp,
                                   self.gcn_intra.W[0], self.gcn_intra.W[1], self.gcn_inter.W[0], self.gcn_inter.W[1],
-                                  self.out_embedding.weight, self.out_embedding.bias)
+                                  self.out_embedding.weight, self.out_embedding.bias, *self._chunks(sched))

@@ -183,7 +183,8 @@ pool_fwd.register_autograd(_pool_backward, setup_context=_pool_setup)
 # ---------------------------------------------------------------------------------------------
 @torch.library.custom_op('sgx::gcn_module_fwd', mutates_args=())
 def gcn_module_fwd(x: Tensor, leader: Tensor, gsize: Tensor, ped_start: Tensor, ped_end: Tensor, scene_start: Tensor,
-                   n_group: Tensor, W0: Tensor, W1: Tensor, V0: Tensor, V1: Tensor, Wo: Tensor, bo: Tensor) -> Tensor:
+                   n_group: Tensor, W0: Tensor, W1: Tensor, V0: Tensor, V1: Tensor, Wo: Tensor, bo: Tensor,
+                   chunk_scene: Tensor, n_chunks: int) -> Tensor:
     x = _f32(x, 'h_states')
     W0, W1, V0, V1, Wo, bo = (_f32(t, 'gcn weight') for t in (W0, W1, V0, V1, Wo, bo))
     batch, IN = x.shape
@@ -191,6 +192,13 @@ def gcn_module_fwd(x: Tensor, leader: Tensor, gsize: Tensor, ped_start: Tensor, 
     S = scene_start.numel() - 1
     out = torch.empty(batch, FIN, dtype=torch.float32, device=x.device)
     L = _lib.lib()
+    if n_chunks > 0 and HID == 72 and OUT == 16 and IN in (32, 40) and FIN in (24, 32):
+        with torch.cuda.device(x.device):
+            _lib.check(L.sgx_gcn_module_fused_fwd(_ptr(x), _ptr(leader), _ptr(gsize), _ptr(ped_start), _ptr(ped_end),
+                                                  _ptr(scene_start), _ptr(chunk_scene), n_chunks, _ptr(W0), _ptr(W1),
+                                                  _ptr(V0), _ptr(V1), _ptr(Wo), _ptr(bo), IN, HID, OUT, FIN, _ptr(out),
+                                                  _stream(x)), 'sgx_gcn_module_fused_fwd')
+        return out
     ws = _ws(L.sgx_gcn_module_ws_bytes(batch, S, IN, HID, OUT, FIN), x.device)
     with torch.cuda.device(x.device):
         _lib.check(L.sgx_gcn_module_fwd(_ptr(x), _ptr(leader), _ptr(gsize), _ptr(ped_start), _ptr(ped_end),
@@ -201,7 +209,7 @@ def gcn_module_fwd(x: Tensor, leader: Tensor, gsize: Tensor, ped_start: Tensor, 
 
 
 @gcn_module_fwd.register_fake
-def _(x, leader, gsize, ped_start, ped_end, scene_start, n_group, W0, W1, V0, V1, Wo, bo):
+def _(x, leader, gsize, ped_start, ped_end, scene_start, n_group, W0, W1, V0, V1, Wo, bo, chunk_scene, n_chunks):
     return x.new_empty(x.shape[0], Wo.shape[0])
 
 
@@ -232,13 +240,13 @@ def _(x, grad_out, leader, gsize, ped_start, ped_end, scene_start, n_group, W0, 
 
 
 def _gcn_setup(ctx, inputs, output):
-    ctx.save_for_backward(*inputs)
+    ctx.save_for_backward(*inputs[:13])
 
 
 def _gcn_backward(ctx, grad_out):
     x, leader, gsize, ps, pe, ss, ng, W0, W1, V0, V1, Wo, bo = ctx.saved_tensors
     g = gcn_module_bwd(x, grad_out.contiguous(), leader, gsize, ps, pe, ss, ng, W0, W1, V0, V1, Wo, bo)
-    return g[0], None, None, None, None, None, None, g[1], g[2], g[3], g[4], g[5], g[6]
+    return g[0], None, None, None, None, None, None, g[1], g[2], g[3], g[4], g[5], g[6], None, None
 
 
 gcn_module_fwd.register_autograd(_gcn_backward, setup_context=_gcn_setup)

@@ -131,6 +131,12 @@ int sgx_gcn_module_fwd(const float* x, const int32_t* leader, const int32_t* gro
                        int64_t n_scenes, const float* W0, const float* W1, const float* V0, const float* V1,
                        const float* Wo, const float* bo, int32_t IN, int32_t HID, int32_t OUT, int32_t FIN,
                        float* out, void* workspace, int64_t ws_bytes, void* stream);
+/* Same forward in ONE launch for batches whose scenes all have <= 32 pedestrians (chunks from sgx_schedule_chunks). */
+int sgx_gcn_module_fused_fwd(const float* x, const int32_t* leader, const int32_t* group_size,
+                             const int32_t* ped_start, const int32_t* ped_end, const int32_t* scene_start,
+                             const int32_t* chunk_scene, int64_t n_chunks, const float* W0, const float* W1,
+                             const float* V0, const float* V1, const float* Wo, const float* bo, int32_t IN,
+                             int32_t HID, int32_t OUT, int32_t FIN, float* out, void* stream);
 int sgx_gcn_module_bwd(const float* x, const float* grad_out, const int32_t* leader, const int32_t* group_size,
                        const int32_t* ped_start, const int32_t* ped_end, const int32_t* scene_start,
                        const int32_t* n_group, int64_t batch, int64_t n_scenes, const float* W0, const float* W1,

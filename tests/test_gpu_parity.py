@@ -501,3 +501,16 @@ def test_lstm_tensor_core_decoder_matches_cuda_core(sgx):
     m = int(sse[k - 1, 1])
     eager = gen.decode(ctx[:m].clone().requires_grad_(True), obs[:, :m], obs_rel[:, :m], sse[:k].clone(), user_noise=z[:k])
     assert_close(tc[:, :m], eager, 3e-5, 'tensor-core decoder vs cuDNN path')
+
+
+def test_gcn_fused_single_launch_matches_three_kernel_path(sgx):
+    g = load_golden('gcn_module_40')
+    m = sgx['M'].GCNModule(input_dim=40, hidden_dim=72, out_dim=16, gcn_layers=2, final_dim=24)
+    m.load_state_dict(state_dict_of(g), strict=True)
+    m = m.to(DEV)
+    args = (g['x'].to(DEV), g['seq_start_end'].to(DEV), g['pos'].to(DEV), g['labels'].to(DEV))
+    with torch.no_grad():
+        ref = m(*args)
+        fused = _with_env('SGX_GCN_FUSED', '1', lambda: m(*args))
+    assert_close(fused, ref, 2e-6, 'fused GCN vs three-kernel path')
+    assert_close(fused, g['out'], 1e-5, 'fused GCN vs golden')
