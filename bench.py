@@ -371,10 +371,12 @@ def main():
             'gpu_launches': int(launches),
             'roofline': {'kernel': 'pool_pair_kernel' if precision != 'bf16' else 'pool_tc_kernel', 'bound': 'tensor',
                          'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
-                         'traffic': None, 'peak_source': peak_src, 'kernel_ms': k_ms,
+                         'traffic': 36.45e6 if (precision == 'bf16' and args.scenes == 1 << 16) else None,
+                         'traffic_source': 'dram__bytes_read+write per launch, ncu --set full, profiles/r01_pool_tc_ncu_full_raw.csv',
+                         'peak_source': peak_src, 'kernel_ms': k_ms,
                          'algorithmic_flops_per_launch': POOL_FLOPS_PER_PAIR * n_pairs,
-                         'note': 'as-written FLOPs (57408 per ordered pair); the fp32 kernel executes the exactly '
-                                 'factored layer 1 on CUDA cores, see DESIGN.md'},
+                         'note': 'as-written FLOPs (57408 per ordered pair); bf16: tcgen05 GEMM1+GEMM2 with the 2->16 embedding '
+                                 'folded into GEMM1; fp32: exactly factored layer 1 on CUDA cores (DESIGN.md 4.1/4.2)'},
             'wall_s_timed_region': wall,
             'other_kernels': [
                 {'op': 'GATEncoder fwd (group_ids + gat_fused_fwd_kernel)', 'bound': 'hbm', 'ms': gat_ms,

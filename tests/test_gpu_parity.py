@@ -514,3 +514,57 @@ def test_gcn_fused_single_launch_matches_three_kernel_path(sgx):
         fused = _with_env('SGX_GCN_FUSED', '1', lambda: m(*args))
     assert_close(fused, ref, 2e-6, 'fused GCN vs three-kernel path')
     assert_close(fused, g['out'], 1e-5, 'fused GCN vs golden')
+
+
+# ------------------------------------------------------------------ edge cases of the ragged layout
+@pytest.mark.parametrize('sizes', [[32], [32, 32, 1], [33], [31, 2, 32, 1, 1, 30], [1] * 70])
+def test_gat_encoder_chunk_boundaries(sgx, sizes):
+    """Scenes of exactly 32 peds fill a warp-chunk of the fused kernel; 33 falls back to the general path; many
+    singleton scenes share a chunk.  Both paths must agree with the oracle."""
+    rng = np.random.RandomState(sum(sizes))
+    torch.manual_seed(sum(sizes))
+    sse = sse_from_sizes(sizes)
+    n = sum(sizes)
+    labs = torch.tensor(np.where(rng.rand(n) < 0.2, 0, rng.randint(1, 5, size=n)), dtype=torch.float32).view(-1, 1)
+    x, pos = torch.randn(n, 40), torch.rand(n, 2)
+    m = sgx['M'].GATEncoder(n_units=None, n_heads=1, dropout=0, alpha=0.2)
+    ref = O.gat_encoder(x, sse, pos, labs, m.state_dict(), '', 0.2, 1)
+    with torch.no_grad():
+        out = m.to(DEV)(x.to(DEV), sse.to(DEV), pos.to(DEV), labs.to(DEV))
+    assert_close(out, ref, 1e-5, 'gat %s' % sizes[:3])
+
+
+@pytest.mark.parametrize('sizes', [[8] * 2, [16] * 8, [2] * 32, [11, 3], [128], [1]])
+def test_pool_tile_boundaries_both_precisions(sgx, sizes):
+    """Pair counts that are exact multiples of the 128-pair tile, one pair short / over, and a single pair."""
+    torch.manual_seed(len(sizes))
+    m = sgx['M'].PoolHiddenNet(embedding_dim=16, h_dim=32, mlp_dim=64, bottleneck_dim=8, batch_norm=False)
+    sse = sse_from_sizes(sizes)
+    n = sum(sizes)
+    h, pos = torch.randn(n, 32), torch.rand(n, 2) * 15
+    ref = O.pool_hidden_net(h, sse, pos, m.state_dict())
+    m = m.to(DEV)
+    with torch.no_grad():
+        m.precision = 'fp32'
+        assert_close(m(h.to(DEV), sse.to(DEV), pos.to(DEV)), ref, 1e-5, 'fp32 %s' % sizes[:2])
+        m.precision = 'bf16'
+        assert_close(m(h.to(DEV), sse.to(DEV), pos.to(DEV)), ref, 2e-2, 'bf16 %s' % sizes[:2])
+
+
+def test_generator_every_timestep_pooling_bf16_close_to_fp32(sgx):
+    """cfg 4 wiring (decoder pools at every step): the bf16 tensor-core pooling stays within 2e-2 of the fp32 path
+    after 12 recurrent steps on a dense scene."""
+    g = load_golden('generator_gat_pet')
+    gen = _generator(sgx, g, 'gat')
+    torch.manual_seed(3)
+    n = 96
+    sse = sse_from_sizes([n]).to(DEV)
+    obs = torch.rand(8, n, 2, device=DEV) * 10
+    obs_rel = torch.randn(8, n, 2, device=DEV) * 0.2
+    grp = torch.randint(0, 6, (8, n, 1), device=DEV).float()
+    z = torch.randn(1, 8, device=DEV)
+    with torch.no_grad():
+        a = gen(obs, obs_rel, sse, grp, user_noise=z)
+        gen.pool_net.precision = gen.decoder.pool_net.precision = 'bf16'
+        b = gen(obs, obs_rel, sse, grp, user_noise=z)
+    assert_close(b, a, 2e-2, 'per-step pooling bf16 vs fp32')
