@@ -22,7 +22,7 @@ namespace sgx {
 
 constexpr int LH = 32;            // hidden size this kernel is built for
 constexpr int LT = 128;           // pedestrians per tile (UMMA M)
-constexpr int LSLOTS = 2;         // tiles in flight per CTA
+constexpr int LSLOTS = 3;         // tiles in flight per CTA (13 warps => 128 registers per thread)
 constexpr int LTHREADS = (1 + 4 * LSLOTS) * 32;
 
 struct LstmTcSmem {               // byte offsets from the 1024-aligned base
@@ -99,19 +99,19 @@ __device__ __forceinline__ void write_a_rows(uint8_t* blk0, uint8_t* blk1, int r
     c1.x = pack_bf16(yh, yl); c1.y = pack_bf16(ym, yh); c1.z = pack_bf16(1.f, 1.f); c1.w = pack_bf16(1.f, 0.f);
     *reinterpret_cast<uint4*>(blk0 + swz(row, 0)) = c0;
     *reinterpret_cast<uint4*>(blk0 + swz(row, 1)) = c1;
-    uint32_t hi[LH / 2], mi[LH / 2], lo[LH / 2];
 #pragma unroll
-    for (int u = 0; u < LH; u += 2) {
-        float a0, a1, a2, b0, b1, b2;
-        split3(h[u], a0, a1, a2);
-        split3(h[u + 1], b0, b1, b2);
-        hi[u / 2] = pack_bf16(a0, b0); mi[u / 2] = pack_bf16(a1, b1); lo[u / 2] = pack_bf16(a2, b2);
-    }
+    for (int c = 0; c < 4; ++c) {                 // 8 hidden units per 16-byte chunk; nothing wider than that stays live
+        uint32_t hi[4], mi[4], lo[4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        *reinterpret_cast<uint4*>(blk0 + swz(row, 2 + c)) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
-        *reinterpret_cast<uint4*>(blk1 + swz(row, c)) = make_uint4(mi[4 * c], mi[4 * c + 1], mi[4 * c + 2], mi[4 * c + 3]);
-        *reinterpret_cast<uint4*>(blk1 + swz(row, 4 + c)) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+        for (int j = 0; j < 4; ++j) {
+            float a0, a1, a2, b0, b1, b2;
+            split3(h[8 * c + 2 * j], a0, a1, a2);
+            split3(h[8 * c + 2 * j + 1], b0, b1, b2);
+            hi[j] = pack_bf16(a0, b0); mi[j] = pack_bf16(a1, b1); lo[j] = pack_bf16(a2, b2);
+        }
+        *reinterpret_cast<uint4*>(blk0 + swz(row, 2 + c)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(blk1 + swz(row, c)) = make_uint4(mi[0], mi[1], mi[2], mi[3]);
+        *reinterpret_cast<uint4*>(blk1 + swz(row, 4 + c)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
 }
 
@@ -232,25 +232,30 @@ lstm_tc_kernel(const float* __restrict__ seq_in, const float* __restrict__ h0, c
 #ifdef SGX_TC_STATS
                 const long long te0_ = clock64();
 #endif
-                uint32_t v[32];
-                float ig[LH];
-                tmem_ld32(gaddr + 0, v);                       // input gate
-                tmem_wait_ld();
 #pragma unroll
-                for (int u = 0; u < LH; ++u) ig[u] = exp_neg(__uint_as_float(v[u]));
-                tmem_ld32(gaddr + 64, v);                      // cell candidate
-                tmem_wait_ld();
+                for (int half = 0; half < 2; ++half) {         // 16 hidden units at a time keeps the thread under 128 regs
+                    uint32_t v[16];
+                    float ig[16];
+                    tmem_ld16(gaddr + 0 + half * 16, v);       // input gate
+                    tmem_wait_ld();
 #pragma unroll
-                for (int u = 0; u < LH; ++u) ig[u] = sig_tanh(ig[u], __uint_as_float(v[u]));
-                tmem_ld32(gaddr + 32, v);                      // forget gate
-                tmem_wait_ld();
+                    for (int u = 0; u < 16; ++u) ig[u] = exp_neg(__uint_as_float(v[u]));
+                    tmem_ld16(gaddr + 64 + half * 16, v);      // cell candidate
+                    tmem_wait_ld();
 #pragma unroll
-                for (int u = 0; u < LH; ++u) c[u] = fmaf(sig_f(__uint_as_float(v[u])), c[u], ig[u]);
-                tmem_ld32(gaddr + 96, v);                      // output gate
-                tmem_wait_ld();
+                    for (int u = 0; u < 16; ++u) ig[u] = sig_tanh(ig[u], __uint_as_float(v[u]));
+                    tmem_ld16(gaddr + 32 + half * 16, v);      // forget gate
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int u = 0; u < 16; ++u)
+                        c[half * 16 + u] = fmaf(sig_f(__uint_as_float(v[u])), c[half * 16 + u], ig[u]);
+                    tmem_ld16(gaddr + 96 + half * 16, v);      // output gate
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int u = 0; u < 16; ++u)
+                        h[half * 16 + u] = sig_tanh(exp_neg(__uint_as_float(v[u])), c[half * 16 + u]);
+                }
                 tc_fence_before();
-#pragma unroll
-                for (int u = 0; u < LH; ++u) h[u] = sig_tanh(exp_neg(__uint_as_float(v[u])), c[u]);
                 if (DECODER) {
                     float rx = whp[2 * LH], ry = whp[2 * LH + 1];
 #pragma unroll
