@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libsgx_b200.so')
+# SGX_LIB: developer override to A/B a differently-built copy of the same library (tools/ only)
+LIB_PATH = os.environ.get('SGX_LIB') or os.path.join(_HERE, 'lib', 'libsgx_b200.so')
 
 SGX_OK = 0
 SGX_ERR_INVALID = -1

@@ -413,10 +413,14 @@ static int gat_forward(const float* x, const int32_t* leader, const int32_t* gsi
 // shared-memory row buffers, every linear map is a thread-per-row GEMV with the weights broadcast from
 // shared memory as 128-bit loads, attention gathers neighbour rows from the same buffers.  Only x, the
 // group structure and out touch HBM (260 B/ped).  n_heads = 1 (every shipped checkpoint).
+// Bound (ncu, profiles/r01_gat_v2_ncu_full_raw.csv): the shared-memory data pipe.  A broadcast LDS.128 costs two
+// wavefronts and feeds four lane-FMAs, so one weight word per FMA caps the FMA pipe at 50 %; the kernel sits at 65 %
+// of that cap.  The next step is register blocking over two peds per lane (halves the weight wavefronts).
 // ------------------------------------------------------------------------------------------------
 constexpr int RS = 76;                 // row stride (floats) of the 72-wide row buffer: 16 B aligned, conflict-free STS.128
-constexpr int RA = 44;                 // row stride of the 40-wide input buffer (x, Xg, Yg)
-constexpr int FUSED_WARPS = 8;
+constexpr int RA = 20;                 // row stride of the 16-wide leader buffer (Xg, Yg); x itself is staged in the
+                                       // lane's own 72-wide row, which only that lane reads before overwriting it with Wh
+constexpr int FUSED_WARPS = 12;
 constexpr int FUSED_SCRATCH = 32 * RA + 32 * RS + 32 * 16 + 32 * 2 + 32;   // floats per warp
 
 struct FusedW {                        // shared-memory weight block (floats)
@@ -425,22 +429,35 @@ struct FusedW {                        // shared-memory weight block (floats)
     float Wo[24 * 2 * OUT], bo[24];
 };
 
+// ex2.approx based exp / ELU for the fused kernel (2 ulp; the general path keeps expf / expm1f): expm1f alone was
+// ~25 instructions per element, more dynamic instructions than the 40x72 GEMV it follows.
+__device__ __forceinline__ float fexp(float v) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v * 1.4426950408889634f));
+    return r;
+}
+__device__ __forceinline__ float felu(float v) { return v > 0.f ? v : fexp(v) - 1.f; }
+
 // y[0..NO) = sum_c xrow[c] * W[c][0..NO)   (W row-major [NI][NO] in smem, xrow in smem)
 template <int NI, int NO>
 __device__ __forceinline__ void gemv_rows(const float* __restrict__ xrow, const float* __restrict__ W, float (&y)[NO]) {
     float2 acc[NO / 2];                          // packed FFMA2: (y[2o], y[2o+1]) += (x, x) * (W[c][2o], W[c][2o+1])
 #pragma unroll
     for (int o = 0; o < NO / 2; ++o) acc[o] = make_float2(0.f, 0.f);
-#pragma unroll 2
-    for (int c = 0; c < NI; ++c) {
-        const float xv = xrow[c];
-        const float2 xx = make_float2(xv, xv);
-        const float4* w = reinterpret_cast<const float4*>(W + c * NO);
+#pragma unroll 1
+    for (int c4 = 0; c4 < NI / 4; ++c4) {        // rolled on purpose: the whole kernel has to stay inside the I-cache
+        const float4 x4 = reinterpret_cast<const float4*>(xrow)[c4];
+        const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
-        for (int o = 0; o < NO / 4; ++o) {
-            const float4 v = w[o];
-            acc[2 * o] = ffma2(xx, make_float2(v.x, v.y), acc[2 * o]);
-            acc[2 * o + 1] = ffma2(xx, make_float2(v.z, v.w), acc[2 * o + 1]);
+        for (int k = 0; k < 4; ++k) {
+            const float2 xx = make_float2(xs[k], xs[k]);
+            const float4* w = reinterpret_cast<const float4*>(W + (4 * c4 + k) * NO);
+#pragma unroll
+            for (int o = 0; o < NO / 4; ++o) {
+                const float4 v = w[o];
+                acc[2 * o] = ffma2(xx, make_float2(v.x, v.y), acc[2 * o]);
+                acc[2 * o + 1] = ffma2(xx, make_float2(v.z, v.w), acc[2 * o + 1]);
+            }
         }
     }
 #pragma unroll
@@ -463,7 +480,7 @@ __device__ __forceinline__ void attend_smem(const float* __restrict__ rows, cons
     for (int q = b; q < e; ++q) {
         const bool nb = INTER ? (lead_slot[q] == q) : (lead_slot[q] == my_lead);
         if (!nb) continue;
-        const float w = expf(lrelu(s_i + st[q].y, alpha) - m);
+        const float w = fexp(lrelu(s_i + st[q].y, alpha) - m);
         den += w;
         const float4* row = reinterpret_cast<const float4*>(rows + q * RS);
 #pragma unroll
@@ -510,7 +527,11 @@ template <int F>
 __device__ __forceinline__ float2 scores(const float (&wh)[F], const float* __restrict__ a) {
     float s = 0.f, t = 0.f;
 #pragma unroll
-    for (int f = 0; f < F; ++f) { s = fmaf(wh[f], a[f], s); t = fmaf(wh[f], a[F + f], t); }
+    for (int f = 0; f < F / 4; ++f) {
+        const float4 u = reinterpret_cast<const float4*>(a)[f], v = reinterpret_cast<const float4*>(a + F)[f];
+        s = fmaf(wh[4 * f], u.x, s); s = fmaf(wh[4 * f + 1], u.y, s); s = fmaf(wh[4 * f + 2], u.z, s); s = fmaf(wh[4 * f + 3], u.w, s);
+        t = fmaf(wh[4 * f], v.x, t); t = fmaf(wh[4 * f + 1], v.y, t); t = fmaf(wh[4 * f + 2], v.z, t); t = fmaf(wh[4 * f + 3], v.w, t);
+    }
     return make_float2(s, t);
 }
 
@@ -518,10 +539,10 @@ template <int F>
 __device__ __forceinline__ void elu_logsoftmax(float (&v)[F]) {
     float mx = -INFINITY;
 #pragma unroll
-    for (int f = 0; f < F; ++f) { v[f] = elu1(v[f]); mx = fmaxf(mx, v[f]); }
+    for (int f = 0; f < F; ++f) { v[f] = felu(v[f]); mx = fmaxf(mx, v[f]); }
     float sum = 0.f;
 #pragma unroll
-    for (int f = 0; f < F; ++f) sum += expf(v[f] - mx);
+    for (int f = 0; f < F; ++f) sum += fexp(v[f] - mx);
     const float lse = mx + logf(sum);
 #pragma unroll
     for (int f = 0; f < F; ++f) v[f] -= lse;
@@ -569,7 +590,7 @@ gat_fused_fwd_kernel(const float* __restrict__ x, const int32_t* __restrict__ le
             inv_g = __frcp_rn((float)gsize[p]);
             const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)p * IN);
 #pragma unroll
-            for (int c = 0; c < IN / 4; ++c) reinterpret_cast<float4*>(A + lane * RA)[c] = xr[c];
+            for (int c = 0; c < IN / 4; ++c) reinterpret_cast<float4*>(Bf + lane * RS)[c] = xr[c];
         }
         lead_slot[lane] = live ? my_lead : -1;
         const bool is_lead = live && (my_lead == lane);
@@ -577,7 +598,7 @@ gat_fused_fwd_kernel(const float* __restrict__ x, const int32_t* __restrict__ le
         // ---- intra GAT, layer 1 ----
         if (live) {
             float wh[HID];
-            gemv_rows<IN, HID>(A + lane * RA, w.Wi, wh);
+            gemv_rows<IN, HID>(Bf + lane * RS, w.Wi, wh);
             st[lane] = scores<HID>(wh, w.ai);
             store_row<HID>(Bf + lane * RS, wh);
         }
@@ -590,7 +611,7 @@ gat_fused_fwd_kernel(const float* __restrict__ x, const int32_t* __restrict__ le
             float hp[HID];
             attend_smem<HID, false>(Bf, st, lead_slot, b, e, my_lead, st[lane].x, alpha, hp);
 #pragma unroll
-            for (int f = 0; f < HID; ++f) hp[f] = elu1(hp[f]);      // x1a stays in registers
+            for (int f = 0; f < HID; ++f) hp[f] = felu(hp[f]);      // x1a stays in registers
             // ---- intra GAT, out_att ----
             gemv_regs<HID, OUT>(hp, w.Wio, wh2);
         }
@@ -631,7 +652,7 @@ gat_fused_fwd_kernel(const float* __restrict__ x, const int32_t* __restrict__ le
             float hp[HID];
             attend_smem<HID, true>(Bf, st, lead_slot, b, e, my_lead, st[lane].x, alpha, hp);
 #pragma unroll
-            for (int f = 0; f < HID; ++f) hp[f] = elu1(hp[f]);
+            for (int f = 0; f < HID; ++f) hp[f] = felu(hp[f]);
             gemv_regs<HID, OUT>(hp, w.Weo, wh4);
         }
         __syncwarp();
@@ -659,15 +680,15 @@ gat_fused_fwd_kernel(const float* __restrict__ x, const int32_t* __restrict__ le
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int o = 4 * o4 + k;
-                    float acc = w.bo[o];
+                    float2 acc = make_float2(w.bo[o], 0.f);
                     const float4* wr = reinterpret_cast<const float4*>(w.Wo + o * 2 * OUT);
 #pragma unroll
                     for (int c = 0; c < 2 * OUT / 4; ++c) {
                         const float4 v = wr[c];
-                        acc = fmaf(cat[4 * c], v.x, acc); acc = fmaf(cat[4 * c + 1], v.y, acc);
-                        acc = fmaf(cat[4 * c + 2], v.z, acc); acc = fmaf(cat[4 * c + 3], v.w, acc);
+                        acc = ffma2(make_float2(cat[4 * c], cat[4 * c + 1]), make_float2(v.x, v.y), acc);
+                        acc = ffma2(make_float2(cat[4 * c + 2], cat[4 * c + 3]), make_float2(v.z, v.w), acc);
                     }
-                    y[k] = acc;
+                    y[k] = acc.x + acc.y;
                 }
                 reinterpret_cast<float4*>(orow)[o4] = make_float4(y[0], y[1], y[2], y[3]);
             }
