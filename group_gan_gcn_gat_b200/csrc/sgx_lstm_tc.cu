@@ -14,8 +14,8 @@
 //              [axh axh axm axh axm axl | ayh ayh aym ayh aym ayl | bh bm bl | 0]   (embedding + biases folded)
 // = 13 MMAs (M 128, N 128, K 16) per tile-step.  The epilogue (one thread per pedestrian, c and h in registers)
 // reads the gates from TMEM, applies sigmoid/tanh, updates c and h, computes hidden2pos (decoder), splits the new h
-// and writes the next A rows.  Two 128-ped tiles are in flight per CTA so one tile's MMAs overlap the other's
-// epilogue; the kernel is bound by the 320 MUFU operations per pedestrian-step of the gate non-linearities.
+// and writes the next A rows.  Three 128-ped tiles are in flight per CTA so one tile's MMAs overlap the others'
+// epilogues; the kernel is bound by the 256 MUFU operations per pedestrian-step of the gate non-linearities.
 #include "sgx_tc.cuh"
 
 namespace sgx {
@@ -33,6 +33,7 @@ struct LstmTcSmem {               // byte offsets from the 1024-aligned base
     static constexpr int TOTAL = BARS + 256 + 1024;
 };
 
+constexpr float LOG2E = 1.4426950408889634f;
 __device__ __forceinline__ void split3(float v, float& hi, float& mid, float& lo) {
     hi = __bfloat162float(__float2bfloat16_rn(v));
     const float r = v - hi;
@@ -49,9 +50,13 @@ __global__ void lstm_tc_prep_kernel(const float* __restrict__ We, const float* _
     if (t >= 5 * LT * 64) return;
     const int tile = t / (LT * 64), r = (t / 64) % LT, k = t % 64;
     float v = 0.f;
-    auto w3 = [&](int col, int part) {                        // part 0/1/2 = hi/mid/lo of W_hh[r][col]
+    // Gate rows are pre-scaled so that the GEMM delivers the ex2 argument itself: -log2(e) * a for the sigmoid gates
+    // (i, f, o: e^-a = 2^(-a log2 e)), 2 log2(e) * a for the cell candidate (tanh through e^2a).  One rounding per
+    // weight, the same one the multiply in the epilogue would make.
+    const float gs = (r >= 2 * LH && r < 3 * LH) ? 2.f * LOG2E : -LOG2E;
+    auto w3 = [&](int col, int part) {                        // part 0/1/2 = hi/mid/lo of gs * W_hh[r][col]
         float hi, mid, lo;
-        split3(W_hh[r * LH + col], hi, mid, lo);
+        split3(gs * W_hh[r * LH + col], hi, mid, lo);
         return part == 0 ? hi : part == 1 ? mid : lo;
     };
     if (tile == 0) {
@@ -65,9 +70,9 @@ __global__ void lstm_tc_prep_kernel(const float* __restrict__ We, const float* _
             }
             float h3[3];
             const int part_of[6] = {0, 0, 1, 0, 1, 2};        // against d: [h m h l m h]
-            if (k < 6) { split3(ax, h3[0], h3[1], h3[2]); v = h3[part_of[k]]; }
-            else if (k < 12) { split3(ay, h3[0], h3[1], h3[2]); v = h3[part_of[k - 6]]; }
-            else if (k < 15) { split3(b, h3[0], h3[1], h3[2]); v = h3[k - 12]; }
+            if (k < 6) { split3(gs * ax, h3[0], h3[1], h3[2]); v = h3[part_of[k]]; }
+            else if (k < 12) { split3(gs * ay, h3[0], h3[1], h3[2]); v = h3[part_of[k - 6]]; }
+            else if (k < 15) { split3(gs * b, h3[0], h3[1], h3[2]); v = h3[k - 12]; }
         } else if (k < 48) v = w3(k - 16, 0);
     } else if (tile == 1) { if (k >= 16 && k < 48) v = w3(k - 16, 1); }
     else if (tile == 2) { if (k >= 16 && k < 48) v = w3(k - 16, 2); }
@@ -77,23 +82,46 @@ __global__ void lstm_tc_prep_kernel(const float* __restrict__ We, const float* _
     img[off >> 1] = __float2bfloat16_rn(v);
 }
 
-__device__ __forceinline__ float sig_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-// The kernel is MUFU-bound (ex2 + rcp per sigmoid / tanh = 10 MUFU per hidden unit and step).  sigmoid(a) * tanh(b)
+// The kernel is MUFU-bound.  ex2 + rcp per sigmoid / tanh would be 10 MUFU per hidden unit and step; sigmoid(a) * tanh(b)
 // = (E - 1) / ((1 + e)(1 + E)) with e = exp(-a), E = exp(2b) needs 2 ex2 + 1 rcp instead of 4 MUFU, which brings the
-// count to 8.  Arguments are clamped so that neither exponential overflows (tanh / sigmoid are saturated to fp32
-// there anyway); an overflowing product in the denominator gives rcp(inf) = 0, the correct limit.
-__device__ __forceinline__ float exp_neg(float a) { return __expf(fminf(-a, 80.f)); }
-__device__ __forceinline__ float sig_tanh(float e_of_a, float b) {
-    const float E = __expf(fminf(2.f * b, 80.f));
-    return __fdividef(E - 1.f, (1.f + e_of_a) * (1.f + E));
+// count to 8.  The gate pre-activations arrive pre-scaled (see lstm_tc_prep_kernel), so e and E are a clamp and one
+// ex2.approx.ftz each: __expf / __fdividef would add a range check and two multiplies around every MUFU.  Arguments are
+// clamped so that neither exponential overflows (tanh / sigmoid are saturated to fp32 there anyway); an overflowing
+// product in the denominator gives rcp(inf) = 0, the correct limit.
+__device__ __forceinline__ float ex2_clamped(float v) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fminf(v, 115.f)));
+    return r;
+}
+__device__ __forceinline__ float rcp_fast(float v) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+// sigmoid(a) * tanh(b) given e = e^-a and E = e^2b
+__device__ __forceinline__ float sig_tanh(float e, float E) { return (E - 1.f) * rcp_fast((1.f + e) * (1.f + E)); }
+
+// hi/mid/lo bf16 split of TWO values at once, all on the ALU pipe: cvt.rn.bf16x2 (F2FP) rounds both, the rounded values
+// come back as floats by a shift / mask.  The scalar form (F2F.BF16.F32) runs on the XU pipe, which the gate
+// non-linearities already saturate: 136 of the kernel's 392 XU operations per pedestrian-step were these conversions.
+struct Split3x2 { float a[3], b[3]; uint32_t packed[3]; };
+__device__ __forceinline__ Split3x2 split3_pair(float x0, float x1) {
+    Split3x2 r;
+    r.packed[0] = pack_bf16(x0, x1);
+    r.a[0] = __uint_as_float(r.packed[0] << 16); r.b[0] = __uint_as_float(r.packed[0] & 0xFFFF0000u);
+    const float ra = x0 - r.a[0], rb = x1 - r.b[0];
+    r.packed[1] = pack_bf16(ra, rb);
+    r.a[1] = __uint_as_float(r.packed[1] << 16); r.b[1] = __uint_as_float(r.packed[1] & 0xFFFF0000u);
+    r.a[2] = ra - r.a[1]; r.b[2] = rb - r.b[1];
+    r.packed[2] = pack_bf16(r.a[2], r.b[2]);
+    return r;
 }
 
 // write this pedestrian's operand rows for the next step: input chunk + 3-way split of h
 __device__ __forceinline__ void write_a_rows(uint8_t* blk0, uint8_t* blk1, int row, float dx, float dy,
                                              const float (&h)[LH]) {
-    float xh, xm, xl, yh, ym, yl;
-    split3(dx, xh, xm, xl);
-    split3(dy, yh, ym, yl);
+    const Split3x2 d = split3_pair(dx, dy);
+    const float xh = d.a[0], xm = d.a[1], xl = d.a[2], yh = d.b[0], ym = d.b[1], yl = d.b[2];
     uint4 c0, c1;
     c0.x = pack_bf16(xh, xm); c0.y = pack_bf16(xh, xl); c0.z = pack_bf16(xm, xh); c0.w = pack_bf16(yh, ym);
     c1.x = pack_bf16(yh, yl); c1.y = pack_bf16(ym, yh); c1.z = pack_bf16(1.f, 1.f); c1.w = pack_bf16(1.f, 0.f);
@@ -104,10 +132,8 @@ __device__ __forceinline__ void write_a_rows(uint8_t* blk0, uint8_t* blk1, int r
         uint32_t hi[4], mi[4], lo[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            float a0, a1, a2, b0, b1, b2;
-            split3(h[8 * c + 2 * j], a0, a1, a2);
-            split3(h[8 * c + 2 * j + 1], b0, b1, b2);
-            hi[j] = pack_bf16(a0, b0); mi[j] = pack_bf16(a1, b1); lo[j] = pack_bf16(a2, b2);
+            const Split3x2 q = split3_pair(h[8 * c + 2 * j], h[8 * c + 2 * j + 1]);
+            hi[j] = q.packed[0]; mi[j] = q.packed[1]; lo[j] = q.packed[2];
         }
         *reinterpret_cast<uint4*>(blk0 + swz(row, 2 + c)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<uint4*>(blk1 + swz(row, c)) = make_uint4(mi[0], mi[1], mi[2], mi[3]);
@@ -239,21 +265,22 @@ lstm_tc_kernel(const float* __restrict__ seq_in, const float* __restrict__ h0, c
                     tmem_ld16(gaddr + 0 + half * 16, v);       // input gate
                     tmem_wait_ld();
 #pragma unroll
-                    for (int u = 0; u < 16; ++u) ig[u] = exp_neg(__uint_as_float(v[u]));
+                    for (int u = 0; u < 16; ++u) ig[u] = ex2_clamped(__uint_as_float(v[u]));
                     tmem_ld16(gaddr + 64 + half * 16, v);      // cell candidate
                     tmem_wait_ld();
 #pragma unroll
-                    for (int u = 0; u < 16; ++u) ig[u] = sig_tanh(ig[u], __uint_as_float(v[u]));
+                    for (int u = 0; u < 16; ++u) ig[u] = sig_tanh(ig[u], ex2_clamped(__uint_as_float(v[u])));
                     tmem_ld16(gaddr + 32 + half * 16, v);      // forget gate
                     tmem_wait_ld();
 #pragma unroll
                     for (int u = 0; u < 16; ++u)
-                        c[half * 16 + u] = fmaf(sig_f(__uint_as_float(v[u])), c[half * 16 + u], ig[u]);
+                        c[half * 16 + u] = fmaf(rcp_fast(1.f + ex2_clamped(__uint_as_float(v[u]))), c[half * 16 + u], ig[u]);
                     tmem_ld16(gaddr + 96 + half * 16, v);      // output gate
                     tmem_wait_ld();
 #pragma unroll
                     for (int u = 0; u < 16; ++u)
-                        h[half * 16 + u] = sig_tanh(exp_neg(__uint_as_float(v[u])), c[half * 16 + u]);
+                        h[half * 16 + u] = sig_tanh(ex2_clamped(__uint_as_float(v[u])),
+                                                    ex2_clamped(2.f * LOG2E * c[half * 16 + u]));
                 }
                 tc_fence_before();
                 if (DECODER) {
