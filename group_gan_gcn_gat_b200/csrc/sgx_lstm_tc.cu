@@ -82,15 +82,19 @@ __global__ void lstm_tc_prep_kernel(const float* __restrict__ We, const float* _
     img[off >> 1] = __float2bfloat16_rn(v);
 }
 
-// The kernel is MUFU-bound.  ex2 + rcp per sigmoid / tanh would be 10 MUFU per hidden unit and step; sigmoid(a) * tanh(b)
-// = (E - 1) / ((1 + e)(1 + E)) with e = exp(-a), E = exp(2b) needs 2 ex2 + 1 rcp instead of 4 MUFU, which brings the
-// count to 8.  The gate pre-activations arrive pre-scaled (see lstm_tc_prep_kernel), so e and E are a clamp and one
-// ex2.approx.ftz each: __expf / __fdividef would add a range check and two multiplies around every MUFU.  Arguments are
-// clamped so that neither exponential overflows (tanh / sigmoid are saturated to fp32 there anyway); an overflowing
-// product in the denominator gives rcp(inf) = 0, the correct limit.
-__device__ __forceinline__ float ex2_clamped(float v) {
+// The kernel is MUFU-bound (XU pipe > 80 % busy, profiles/r01_lstm_v3_ncu_full_raw.csv).  ex2 + rcp per sigmoid / tanh
+// would be 10 MUFU per hidden unit and step.  With e_x = e^-x and E_x = e^2x:
+//     c' = sigmoid(f) c + sigmoid(i) tanh(g) = [c (1+e_i)(1+E_g) + (E_g-1)(1+e_f)] / [(1+e_f)(1+e_i)(1+E_g)]
+//     h' = sigmoid(o) tanh(c')               = (E_c'-1) / [(1+e_o)(1+E_c')]
+// is 5 ex2 + 2 rcp = 7.  The gate pre-activations arrive pre-scaled (see lstm_tc_prep_kernel), so every exponential is a
+// clamp and one ex2.approx.ftz: __expf / __fdividef would add a range check and two multiplies around every MUFU.
+// Clamps: e <= 2^40 (sigmoid floor 9e-13), E <= 2^30 (tanh = 1 - 2e-9, below fp32 resolution), so the triple product
+// stays finite for |c| < 2^17.  (Moving one of the five exponentials to an FMA-pipe polynomial was tried: no gain, the
+// issue slots it costs are as scarce as the XU cycles it frees.)
+constexpr float E_CLAMP = 40.f, T_CLAMP = 30.f;
+__device__ __forceinline__ float ex2_clamped(float v, float hi) {
     float r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fminf(v, 115.f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fminf(v, hi)));
     return r;
 }
 __device__ __forceinline__ float rcp_fast(float v) {
@@ -98,8 +102,14 @@ __device__ __forceinline__ float rcp_fast(float v) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
     return r;
 }
-// sigmoid(a) * tanh(b) given e = e^-a and E = e^2b
-__device__ __forceinline__ float sig_tanh(float e, float E) { return (E - 1.f) * rcp_fast((1.f + e) * (1.f + E)); }
+__device__ __forceinline__ float cell_update(float c, float e_i, float E_g, float e_f) {
+    const float A = (1.f + e_i) * (1.f + E_g), F = 1.f + e_f;
+    return fmaf(c, A, (E_g - 1.f) * F) * rcp_fast(F * A);
+}
+__device__ __forceinline__ float hidden_out(float e_o, float c) {
+    const float E = ex2_clamped(2.f * LOG2E * c, T_CLAMP);
+    return (E - 1.f) * rcp_fast((1.f + e_o) * (1.f + E));
+}
 
 // hi/mid/lo bf16 split of TWO values at once, all on the ALU pipe: cvt.rn.bf16x2 (F2FP) rounds both, the rounded values
 // come back as floats by a shift / mask.  The scalar form (F2F.BF16.F32) runs on the XU pipe, which the gate
@@ -261,26 +271,26 @@ lstm_tc_kernel(const float* __restrict__ seq_in, const float* __restrict__ h0, c
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {         // 16 hidden units at a time keeps the thread under 128 regs
                     uint32_t v[16];
-                    float ig[16];
-                    tmem_ld16(gaddr + 0 + half * 16, v);       // input gate
+                    float A[16], B[16];
+                    tmem_ld16(gaddr + 0 + half * 16, v);       // input gate -> e_i
                     tmem_wait_ld();
 #pragma unroll
-                    for (int u = 0; u < 16; ++u) ig[u] = ex2_clamped(__uint_as_float(v[u]));
-                    tmem_ld16(gaddr + 64 + half * 16, v);      // cell candidate
+                    for (int u = 0; u < 16; ++u) A[u] = ex2_clamped(__uint_as_float(v[u]), E_CLAMP);
+                    tmem_ld16(gaddr + 64 + half * 16, v);      // cell candidate -> E_g
                     tmem_wait_ld();
 #pragma unroll
-                    for (int u = 0; u < 16; ++u) ig[u] = sig_tanh(ig[u], ex2_clamped(__uint_as_float(v[u])));
+                    for (int u = 0; u < 16; ++u) B[u] = ex2_clamped(__uint_as_float(v[u]), T_CLAMP);
                     tmem_ld16(gaddr + 32 + half * 16, v);      // forget gate
                     tmem_wait_ld();
 #pragma unroll
                     for (int u = 0; u < 16; ++u)
-                        c[half * 16 + u] = fmaf(rcp_fast(1.f + ex2_clamped(__uint_as_float(v[u]))), c[half * 16 + u], ig[u]);
+                        c[half * 16 + u] = cell_update(c[half * 16 + u], A[u], B[u],
+                                                       ex2_clamped(__uint_as_float(v[u]), E_CLAMP));
                     tmem_ld16(gaddr + 96 + half * 16, v);      // output gate
                     tmem_wait_ld();
 #pragma unroll
                     for (int u = 0; u < 16; ++u)
-                        h[half * 16 + u] = sig_tanh(ex2_clamped(__uint_as_float(v[u])),
-                                                    ex2_clamped(2.f * LOG2E * c[half * 16 + u]));
+                        h[half * 16 + u] = hidden_out(ex2_clamped(__uint_as_float(v[u]), E_CLAMP), c[half * 16 + u]);
                 }
                 tc_fence_before();
                 if (DECODER) {
