@@ -65,3 +65,57 @@ def evaluate_batch(generator, obs_traj, obs_traj_rel, seq_start_end, obs_traj_g,
         ade.append(displacement_error(pred, pred_traj_gt, mode='raw'))
         fde.append(final_displacement_error(pred[-1], pred_traj_gt[-1], mode='raw'))
     return best_of_k_sum(torch.stack(ade, dim=1), sched), best_of_k_sum(torch.stack(fde, dim=1), sched)
+
+
+def get_generator(checkpoint, device='cuda', context_type='gat', pool_precision=None):
+    """scripts/evaluate_model.py:26-55: a TrajectoryGenerator built from checkpoint['args'] with checkpoint['g_state']
+    loaded, on `device`, in train mode (:54).  n_units = [40] + hidden_units + [40] as at :23-27 (GATEncoder ignores
+    it); checkpoints written before the GAT arguments existed (sgan-p / sgan-g models) get hidden_units '16',
+    n_heads 1, dropout1 0, alpha 0.2 -- pass context_type='mlp' / 'gcn' for those wirings."""
+    from .models import TrajectoryGenerator
+    args = checkpoint['args']
+    get = (lambda k, d=None: args.get(k, d)) if isinstance(args, dict) else (lambda k, d=None: getattr(args, k, d))
+    hidden = [int(x) for x in str(get('hidden_units', '16')).strip().split(',')]
+    n_heads = get('n_heads', 1)
+    n_heads = n_heads if isinstance(n_heads, int) else int(str(n_heads).strip().split(',')[0])
+    n_units = [40] + hidden + [40]
+    generator = TrajectoryGenerator(
+        obs_len=get('obs_len'), pred_len=get('pred_len'), embedding_dim=get('embedding_dim'),
+        encoder_h_dim=get('encoder_h_dim_g'), decoder_h_dim=get('decoder_h_dim_g'), mlp_dim=get('mlp_dim'),
+        num_layers=get('num_layers'), noise_dim=tuple(get('noise_dim')), noise_type=get('noise_type'),
+        noise_mix_type=get('noise_mix_type'), pooling_type=get('pooling_type'),
+        pool_every_timestep=get('pool_every_timestep'), dropout=get('dropout'), bottleneck_dim=get('bottleneck_dim'),
+        neighborhood_size=get('neighborhood_size'), grid_size=get('grid_size'), batch_norm=get('batch_norm'),
+        n_units=n_units, n_heads=n_heads, dropout1=get('dropout1', 0), alpha=get('alpha', 0.2),
+        context_type=context_type)
+    generator.load_state_dict(checkpoint['g_state'])
+    generator = generator.to(device).train()
+    if pool_precision is not None and getattr(generator, 'pool_net', None) is not None:
+        generator.pool_net.precision = pool_precision
+    return generator
+
+
+@torch.no_grad()
+def evaluate(args, loader, generator, num_samples, noise_for_batch=None, hoist_context=False):
+    """scripts/evaluate_model.py:72-99: best-of-`num_samples` ADE / FDE over a loader of 11-tuples (data.seq_collate /
+    data.DeviceLoader).  Batches already on the generator's device are used as they are; host batches are copied.
+    `noise_for_batch(batch_index, n_scenes) -> [num_samples, n_scenes, *noise_dim]` pins the noise (parity runs)."""
+    device = next(generator.parameters()).device
+    ade_sum = torch.zeros((), dtype=torch.float64, device=device)
+    fde_sum = torch.zeros((), dtype=torch.float64, device=device)
+    total_traj = 0
+    for b, batch in enumerate(loader):
+        batch = [t.to(device, non_blocking=True) for t in batch]
+        obs_traj, pred_traj_gt, obs_traj_rel = batch[0], batch[1], batch[2]
+        obs_traj_g, seq_start_end = batch[6], batch[10]
+        total_traj += pred_traj_gt.size(1)
+        noise = None if noise_for_batch is None else noise_for_batch(b, seq_start_end.size(0)).to(device)
+        a, f = evaluate_batch(generator, obs_traj.contiguous(), obs_traj_rel.contiguous(), seq_start_end,
+                              obs_traj_g.contiguous(), pred_traj_gt.contiguous(), num_samples, noise=noise,
+                              hoist_context=hoist_context)
+        ade_sum += a.double()
+        fde_sum += f.double()
+    pred_len = args['pred_len'] if isinstance(args, dict) else args.pred_len
+    ade = ade_sum / (total_traj * pred_len)
+    fde = fde_sum / total_traj
+    return ade.float(), fde.float()
