@@ -99,8 +99,6 @@ struct TcCfg {
     static constexpr int SPS = SOFF + 2 * SLICE * 8;               // int32 [2][SLICE]
     static constexpr int BARS = SPS + 2 * SLICE * 4;
     static constexpr int TOTAL = BARS + 256 + 1024;                // + alignment slack
-    static constexpr int NACC = (N2 <= 16) ? 4 : 1;                // independent GEMM2 accumulators (breaks the
-                                                                   // dependent-accumulate chain of the small-N MMAs)
     static constexpr int D2_STRIDE = 64;                           // TMEM columns per D2 buffer
     static constexpr int TM_D1 = 0, TM_H = 256, TM_D2 = 384;
 };
@@ -117,6 +115,7 @@ pool_tc_kernel(const __nv_bfloat16* __restrict__ hb, const float* __restrict__ p
                const float* __restrict__ b2, unsigned long long* __restrict__ packed, int dbg,
                long long* __restrict__ stats_out) {
     using C = TcCfg<H, N2, TS>;
+    static_assert(B % 8 == 0, "the final epilogue reduces eight columns at a time");
     long long stats_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long t_begin_ = clock64();
     extern __shared__ uint8_t smem_raw[];
@@ -204,12 +203,11 @@ pool_tc_kernel(const __nv_bfloat16* __restrict__ hb, const float* __restrict__ p
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk) {
                         const uint64_t bd = w2_d + ((c * 2 + (kk >> 2)) * (N2 * 128) + (kk & 3) * 32) / 16;
-                        const uint32_t d2k = d2 + (kk % C::NACC) * N2;
-                        const uint32_t accf = (c > 0 || kk >= C::NACC);
+                        const uint32_t accf = (c > 0 || kk > 0);
                         if (TS)
-                            mma_ts(d2k, tmem + C::TM_H + (c & 1) * 64 + kk * 8, bd, idesc2, accf);
+                            mma_ts(d2, tmem + C::TM_H + (c & 1) * 64 + kk * 8, bd, idesc2, accf);
                         else
-                            mma_ss(d2k, hs_d + ((c & 1) * (TILE * 256) + (kk >> 2) * 16384 + (kk & 3) * 32) / 16, bd, idesc2, accf);
+                            mma_ss(d2, hs_d + ((c & 1) * (TILE * 256) + (kk >> 2) * 16384 + (kk & 3) * 32) / 16, bd, idesc2, accf);
                     }
                     tc_commit(&h_free[c & 1]);
                     if (c == NCHUNK - 1) tc_commit(&d2_full[db]);
@@ -228,60 +226,69 @@ pool_tc_kernel(const __nv_bfloat16* __restrict__ hb, const float* __restrict__ p
 #pragma unroll
         for (int b = 0; b < B; ++b) bias2[b] = b2[b];
         // The per-tile decode needs tile_first -> (pair_off, ped_start) slice -> (pos, hb) gathers: three dependent
-        // global-load levels.  The first two are software-pipelined one tile ahead (registers), so only the gathers'
-        // latency is exposed per tile.
-        int lo = 0, hi = -1, sp = 0, sp_x = 0;
+        // global-load levels.  All three are software-pipelined: the slice one more tile ahead in registers, and the
+        // gathers of the set's NEXT tile are issued before the finalize of its previous tile and consumed at the top of
+        // the next iteration, so no load latency sits on the row warps' critical path (they bound small-scene batches).
+        int lo = 0, hi = -1, sp = 0, sp_x = 0;       // slice of the tile whose rows are decoded next
         int64_t so = 0, so_x = 0;
-        if (set < my_tiles) {
-            const int64_t t0 = blockIdx.x + (int64_t)set * gridDim.x;
-            lo = tile_first[t0];
-            hi = (t0 + 1 < n_tiles) ? tile_first[t0 + 1] : batch - 1;
+        int lo2 = 0, hi2 = -1;                       // bounds of the tile after that (one more level of look-ahead)
+        auto bounds = [&](int itn, int& l, int& h) {
+            l = 0; h = -1;
+            if (itn < my_tiles) {
+                const int64_t tn = blockIdx.x + (int64_t)itn * gridDim.x;
+                l = tile_first[tn];
+                h = (tn + 1 < n_tiles) ? tile_first[tn + 1] : batch - 1;
+            }
+        };
+        bounds(set, lo, hi);
+        bounds(set + 2, lo2, hi2);
+        if (lo + rt <= hi) { so = pair_off[lo + rt]; sp = ped_start[lo + rt]; }
+        if (rt == 0 && lo + 128 <= hi) { so_x = pair_off[lo + 128]; sp_x = ped_start[lo + 128]; }
+        // prefetched row of the set's next tile
+        int2 ij = make_int2(-1, 0);
+        float2 pi = make_float2(0.f, 0.f), pj = make_float2(0.f, 0.f);
+        uint4 hv[H / 8];
+        bool valid = false;
+        auto prefetch = [&](int itn) {
+            const int64_t tile = blockIdx.x + (int64_t)itn * gridDim.x;
+            // ---- publish this tile's slice of the ped tables, decode (i,j) from shared memory ----
+            if (lo + rt <= hi) { soff[rt] = so; sps[rt] = sp; }
+            if (rt == 0 && lo + 128 <= hi) { soff[128] = so_x; sps[128] = sp_x; }
+            const int lo_c = lo, hi_c = hi;
+            int lo3, hi3;
+            bounds(itn + 4, lo3, hi3);                           // consumed two prefetches from now
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");
+            const int64_t q = tile * TILE + row;
+            ij = make_int2(-1, 0);
+            pi = make_float2(0.f, 0.f); pj = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int c = 0; c < H / 8; ++c) hv[c] = make_uint4(0, 0, 0, 0);
+            valid = q < n_pairs;
+            if (valid) {
+                int a = 0, z = hi_c - lo_c;
+                while (a < z) {
+                    int mid = (a + z + 1) >> 1;
+                    if (soff[mid] <= q) a = mid; else z = mid - 1;
+                }
+                const int i = lo_c + a;
+                const int j = sps[a] + (int)(q - soff[a]);
+                ij = make_int2(i, j);
+                pi = *reinterpret_cast<const float2*>(pos + 2 * (int64_t)i);
+                pj = *reinterpret_cast<const float2*>(pos + 2 * (int64_t)j);
+                const uint4* hrow = reinterpret_cast<const uint4*>(hb + (int64_t)j * H);
+#pragma unroll
+                for (int c = 0; c < H / 8; ++c) hv[c] = hrow[c];
+            }
+            lo = lo2; hi = hi2; lo2 = lo3; hi2 = hi3;           // the following tile's slice -> registers
             if (lo + rt <= hi) { so = pair_off[lo + rt]; sp = ped_start[lo + rt]; }
             if (rt == 0 && lo + 128 <= hi) { so_x = pair_off[lo + 128]; sp_x = ped_start[lo + 128]; }
-        }
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");   // slice may be overwritten next round
+        };
+        if (set < my_tiles) prefetch(set);
         for (int it = set; it < my_tiles + 2; it += 2) {
-            if (it < my_tiles) {
-                const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
+            if (it < my_tiles) {                                 // ---- X stage of tile `it` from the prefetched row ----
                 const int st = it & (NST - 1);
-                // ---- publish this tile's slice of the ped tables, decode (i,j) from shared memory ----
-                if (lo + rt <= hi) { soff[rt] = so; sps[rt] = sp; }
-                if (rt == 0 && lo + 128 <= hi) { soff[128] = so_x; sps[128] = sp_x; }
-                const int lo_c = lo, hi_c = hi;
-                const bool has_next = it + 2 < my_tiles;
-                int lo_n = 0, hi_n = -1;
-                if (has_next) {                                  // bounds of this set's next tile
-                    const int64_t tn = blockIdx.x + (int64_t)(it + 2) * gridDim.x;
-                    lo_n = tile_first[tn];
-                    hi_n = (tn + 1 < n_tiles) ? tile_first[tn + 1] : batch - 1;
-                }
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");
-                const int64_t q = tile * TILE + row;
                 uint8_t* xrow = smem + TcSmem::X + st * TILE * 128;
-                int2 ij = make_int2(-1, 0);
-                float2 pi = make_float2(0.f, 0.f), pj = make_float2(0.f, 0.f);
-                uint4 hv[H / 8];
-#pragma unroll
-                for (int c = 0; c < H / 8; ++c) hv[c] = make_uint4(0, 0, 0, 0);
-                const bool valid = q < n_pairs;
-                if (valid) {
-                    int a = 0, z = hi_c - lo_c;
-                    while (a < z) {
-                        int mid = (a + z + 1) >> 1;
-                        if (soff[mid] <= q) a = mid; else z = mid - 1;
-                    }
-                    const int i = lo_c + a;
-                    const int j = sps[a] + (int)(q - soff[a]);
-                    ij = make_int2(i, j);
-                    pi = *reinterpret_cast<const float2*>(pos + 2 * (int64_t)i);
-                    pj = *reinterpret_cast<const float2*>(pos + 2 * (int64_t)j);
-                    const uint4* hrow = reinterpret_cast<const uint4*>(hb + (int64_t)j * H);
-#pragma unroll
-                    for (int c = 0; c < H / 8; ++c) hv[c] = hrow[c];
-                }
-                lo = lo_n; hi = hi_n;                           // next tile's slice -> registers
-                if (lo + rt <= hi) { so = pair_off[lo + rt]; sp = ped_start[lo + rt]; }
-                if (rt == 0 && lo + 128 <= hi) { so_x = pair_off[lo + 128]; sp_x = ped_start[lo + 128]; }
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");   // slice may be overwritten next round
                 TWAIT(&x_free[st], (uint32_t)(((it / NST) & 1) ^ 1), 0);
                 uint4 c0 = make_uint4(0, 0, 0, 0);
                 if (valid) {
@@ -300,31 +307,26 @@ pool_tc_kernel(const __nv_bfloat16* __restrict__ hb, const float* __restrict__ p
                 fence_proxy_async();
                 mbar_arrive(&x_full[st]);
             }
+            if (it + 2 < my_tiles) {                             // gathers in flight across the finalize below
+#ifdef SGX_TC_STATS
+                const long long tp__ = clock64();
+#endif
+                prefetch(it + 2);
+#ifdef SGX_TC_STATS
+                stats_[2] += clock64() - tp__;
+#endif
+            }
             if (it >= 2) {
                 const int t = it - 2;                // the previous tile of this set; D2 buffer = t & 1 = set
                 const int db = set;
                 TWAIT(&d2_full[db], (uint32_t)((t >> 1) & 1), 1);
+#ifdef SGX_TC_STATS
+                const long long tf__ = clock64();
+#endif
                 tc_fence_after();
                 const uint32_t d2a = tmem + ((uint32_t)((warp & 3) << 5) << 16) + C::TM_D2 + db * C::D2_STRIDE;
-                uint32_t v[16], v2[16], v3[16];
-                tmem_ld16(d2a, v);
-                if (B > 16) { tmem_ld16(d2a + 16, v2); tmem_ld16(d2a + 32, v3); }
-                if (C::NACC == 4) {       // B <= 16: four partial accumulators of 16 columns each
-                    tmem_ld16(d2a + 16, v2);
-                    tmem_ld16(d2a + 32, v3);
-                    uint32_t v4[16];
-                    tmem_ld16(d2a + 48, v4);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int b = 0; b < 16; ++b)
-                        v[b] = __float_as_uint((__uint_as_float(v[b]) + __uint_as_float(v2[b])) +
-                                               (__uint_as_float(v3[b]) + __uint_as_float(v4[b])));
-                }
-                tmem_wait_ld();
-                tc_fence_before();
-                mbar_arrive(&d2_free[db]);
-                const int2 ij = meta[(t & (NMETA - 1)) * TILE + row];
-                const int key = ij.x;
+                const int2 mij = meta[(t & (NMETA - 1)) * TILE + row];
+                const int key = mij.x;
                 const int key_prev = __shfl_up_sync(0xffffffffu, key, 1);
                 const bool head = (lane == 0) || (key_prev != key);
                 const bool uniform = __all_sync(0xffffffffu, key == __shfl_sync(0xffffffffu, key, 0));
@@ -334,29 +336,64 @@ pool_tc_kernel(const __nv_bfloat16* __restrict__ hb, const float* __restrict__ p
                     const int okey = __shfl_down_sync(0xffffffffu, key, 1 << sft);
                     same[sft] = (lane + (1 << sft) < 32) && (okey == key);
                 }
+                constexpr int NG = (B + 15) / 16;       // 16 accumulator columns at a time (register budget of the D dims)
 #pragma unroll
-                for (int b = 0; b < B; ++b) {
-                    const uint32_t raw = (b < 16) ? v[b & 15] : (b < 32) ? v2[b & 15] : v3[b & 15];
-                    const float y = fmaxf(__uint_as_float(raw) + bias2[b], 0.f);
-                    const uint32_t bits = __float_as_uint(y) & 0x7fffffffu;
+                for (int g = 0; g < NG; ++g) {
+                    uint32_t v[16];
+                    tmem_ld16(d2a + 16 * g, v);
+                    tmem_wait_ld();
+                    if (g == NG - 1) {                  // all of D2 has been read: GEMM2 may overwrite this buffer
+                        tc_fence_before();
+                        mbar_arrive(&d2_free[db]);
+                    }
+                    auto column_bits = [&](int c) {     // c: column inside the group
+                        return __float_as_uint(fmaxf(__uint_as_float(v[c]) + bias2[16 * g + c], 0.f)) & 0x7fffffffu;
+                    };
+                    // The uniform / segmented choice sits outside the column loops: with the branch inside, every
+                    // column was its own basic block and the dependent shuffle chains ran one after the other.
                     if (uniform) {
-                        // the whole warp belongs to one pedestrian i (dense crowd): one REDUX + one atomic
-                        const uint32_t mx = __reduce_max_sync(0xffffffffu, bits);
-                        const uint32_t who = __ballot_sync(0xffffffffu, bits == mx);
-                        const int src = 31 - __clz(who);                       // ties -> larger j
-                        const int jj = __shfl_sync(0xffffffffu, ij.y, src);
-                        if (lane == 0 && key >= 0)
-                            atomicMax(&packed[(int64_t)key * B + b], ((unsigned long long)mx << 32) | (unsigned)jj);
-                    } else {
-                        unsigned long long pk = ((unsigned long long)bits << 32) | (unsigned)ij.y;
+                        // the whole warp belongs to one pedestrian i (dense crowd): one REDUX + one atomic per column
 #pragma unroll
-                        for (int sft = 0; sft < 5; ++sft) {
-                            const unsigned long long other = __shfl_down_sync(0xffffffffu, pk, 1 << sft);
-                            if (same[sft] && other > pk) pk = other;
+                        for (int c = 0; c < 16; ++c) {
+                            if (16 * g + c < B) {
+                                const uint32_t bits = column_bits(c);
+                                const uint32_t mx = __reduce_max_sync(0xffffffffu, bits);
+                                const uint32_t who = __ballot_sync(0xffffffffu, bits == mx);
+                                const int src = 31 - __clz(who);                       // ties -> larger j
+                                const int jj = __shfl_sync(0xffffffffu, mij.y, src);
+                                if (lane == 0 && key >= 0)
+                                    atomicMax(&packed[(int64_t)key * B + 16 * g + c],
+                                              ((unsigned long long)mx << 32) | (unsigned)jj);
+                            }
                         }
-                        if (head && key >= 0) atomicMax(&packed[(int64_t)key * B + b], pk);
+                    } else {
+#pragma unroll
+                        for (int c0 = 0; c0 < 16; c0 += 8) {       // eight independent scan chains at a time
+                            if (16 * g + c0 < B) {
+                                unsigned long long pk[8];
+#pragma unroll
+                                for (int c = 0; c < 8; ++c)
+                                    pk[c] = ((unsigned long long)column_bits(c0 + c) << 32) | (unsigned)mij.y;
+#pragma unroll
+                                for (int sft = 0; sft < 5; ++sft) {
+#pragma unroll
+                                    for (int c = 0; c < 8; ++c) {
+                                        const unsigned long long other = __shfl_down_sync(0xffffffffu, pk[c], 1 << sft);
+                                        if (same[sft] && other > pk[c]) pk[c] = other;
+                                    }
+                                }
+                                if (head && key >= 0) {
+#pragma unroll
+                                    for (int c = 0; c < 8; ++c)
+                                        atomicMax(&packed[(int64_t)key * B + 16 * g + c0 + c], pk[c]);
+                                }
+                            }
+                        }
                     }
                 }
+#ifdef SGX_TC_STATS
+                stats_[3] += clock64() - tf__;
+#endif
             }
         }
     } else {
