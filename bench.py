@@ -81,10 +81,41 @@ class ClockSampler:
         self.rows, self.proc, self.gpu = [], None, gpu_index
 
     def start(self):
+        """NVML polled every 20 ms from a thread (the timed region of a default run is ~80 ms, shorter than one
+        `nvidia-smi -lms` period); the recipe's nvidia-smi query line is the fallback."""
+        self.stop_flag = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            reasons_fn = getattr(pynvml, 'nvmlDeviceGetCurrentClocksEventReasons', None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = [('hw_slowdown', 0x8), ('hw_thermal_slowdown', 0x40), ('sw_thermal_slowdown', 0x20), ('sw_power_cap', 0x4)]
+            max_sm = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+
+            def poll():
+                while not self.stop_flag.is_set():
+                    try:
+                        sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                        r = reasons_fn(h)
+                        pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                    except pynvml.NVMLError:
+                        break
+                    self.rows.append([time.perf_counter(), str(self.gpu), str(sm), str(max_sm), '%.1f' % pw, hex(r)] +
+                                     ['Active' if r & b else 'Not Active' for _n, b in bits])
+                    self.stop_flag.wait(0.02)
+
+            self.proc = 'nvml'
+            self.source = 'nvml, 20 ms period'
+            threading.Thread(target=poll, daemon=True).start()
+            return
+        except Exception:
+            pass
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.QUERY,
                                           '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
+            self.source = 'nvidia-smi -lms 100'
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
@@ -103,13 +134,16 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        self.proc.terminate()
+        self.stop_flag.set()
+        if self.proc != 'nvml':
+            self.proc.terminate()
         sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace('.', '').isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace('.', '').isdigit()]
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower() == 'active'})
         return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': reasons, 'samples': len(sm), 'note': getattr(self, 'note', '')}
+                'reasons': reasons, 'samples': len(sm), 'note': getattr(self, 'note', ''),
+                'source': getattr(self, 'source', '')}
 
 
 def cpu_port_traj_per_sec(n_scenes, k_samples, seed, reps=1):
