@@ -53,11 +53,36 @@ __device__ __forceinline__ void lstm_load_weights(LstmSmem<H, THREADS>& s, const
     }
 }
 
+// Training tape (backward): everything the backward kernel and the parameter-gradient GEMMs read,
+// unit-major [rows][T][batch] so that thread-per-pedestrian accesses coalesce and the merged (t, ped) index is the
+// contiguous K dimension of the GEMMs.
+struct LstmTape {
+    float* gact;     // [4H][T][B]  i, f, g, o after their non-linearities
+    float* cprev;    // [H][T][B]   cell state entering step t
+    float* tanhc;    // [H][T][B]   tanh of the cell state leaving step t
+    float* hprev;    // [H][T][B]   hidden state entering step t
+    float* hout;     // [H+1][T][B] hidden state leaving step t, last row = 1 (bias column of the hidden2pos gradient)
+    float* xaug;     // [3][T][B]   step input (dx, dy, 1)
+    int T;
+    int64_t B;
+};
+
 // one LSTM cell update for this thread's PPT pedestrians; input of ped k is the 2-vector (dx[k], dy[k])
-template <int H, int THREADS>
+template <int H, int THREADS, bool SAVE = false>
 __device__ __forceinline__ void lstm_cell(LstmSmem<H, THREADS>& s, float (&h)[PPT][H], const float (&dx)[PPT],
-                                          const float (&dy)[PPT]) {
+                                          const float (&dy)[PPT], const LstmTape* tape = nullptr, int t = 0,
+                                          const int* p = nullptr, const bool* live = nullptr) {
     const int tid = threadIdx.x;
+    if (SAVE) {
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+            if (!live[k]) continue;
+            const int64_t at = (int64_t)t * tape->B + p[k], plane = (int64_t)tape->T * tape->B;
+#pragma unroll
+            for (int u = 0; u < H; ++u) tape->hprev[u * plane + at] = h[k][u];
+            tape->xaug[at] = dx[k]; tape->xaug[plane + at] = dy[k]; tape->xaug[2 * plane + at] = 1.f;
+        }
+    }
 #pragma unroll 1
     for (int u = 0; u < H; ++u) {
         float g[PPT][4];
@@ -84,22 +109,47 @@ __device__ __forceinline__ void lstm_cell(LstmSmem<H, THREADS>& s, float (&h)[PP
 #pragma unroll
         for (int k = 0; k < PPT; ++k) {
             const int col = (k * H + u) * THREADS + tid;
-            const float cn = sigmoid_f(g[k][1]) * s.c[col] + sigmoid_f(g[k][0]) * tanh_f(g[k][2]);
-            s.c[col] = cn;
-            s.hn[col] = sigmoid_f(g[k][3]) * tanh_f(cn);
+            if (SAVE) {
+                const float gi = sigmoid_f(g[k][0]), gf = sigmoid_f(g[k][1]), gg = tanh_f(g[k][2]), go = sigmoid_f(g[k][3]);
+                const float cp = s.c[col];
+                const float cn = gf * cp + gi * gg;
+                const float tc = tanh_f(cn);
+                s.c[col] = cn;
+                s.hn[col] = go * tc;
+                if (live[k]) {
+                    const int64_t at = (int64_t)t * tape->B + p[k], plane = (int64_t)tape->T * tape->B;
+                    tape->gact[(0 * H + u) * plane + at] = gi;
+                    tape->gact[(1 * H + u) * plane + at] = gf;
+                    tape->gact[(2 * H + u) * plane + at] = gg;
+                    tape->gact[(3 * H + u) * plane + at] = go;
+                    tape->cprev[u * plane + at] = cp;
+                    tape->tanhc[u * plane + at] = tc;
+                    tape->hout[u * plane + at] = go * tc;
+                }
+            } else {
+                const float cn = sigmoid_f(g[k][1]) * s.c[col] + sigmoid_f(g[k][0]) * tanh_f(g[k][2]);
+                s.c[col] = cn;
+                s.hn[col] = sigmoid_f(g[k][3]) * tanh_f(cn);
+            }
         }
     }
 #pragma unroll
     for (int k = 0; k < PPT; ++k)
 #pragma unroll
         for (int u = 0; u < H; ++u) h[k][u] = s.hn[(k * H + u) * THREADS + tid];
+    if (SAVE) {
+#pragma unroll
+        for (int k = 0; k < PPT; ++k)
+            if (live[k]) tape->hout[H * (int64_t)tape->T * tape->B + (int64_t)t * tape->B + p[k]] = 1.f;
+    }
 }
 
-template <int H, int THREADS>
+template <int H, int THREADS, bool SAVE>
 __global__ void __launch_bounds__(THREADS)
 lstm_encoder_kernel(const float* __restrict__ obs_rel, int T, int batch, const float* __restrict__ We,
                     const float* __restrict__ be, const float* __restrict__ W_ih, const float* __restrict__ W_hh,
-                    const float* __restrict__ b_ih, const float* __restrict__ b_hh, int E, float* __restrict__ h_out) {
+                    const float* __restrict__ b_ih, const float* __restrict__ b_hh, int E, float* __restrict__ h_out,
+                    LstmTape tape) {
     extern __shared__ __align__(16) uint8_t raw[];
     LstmSmem<H, THREADS>& s = *reinterpret_cast<LstmSmem<H, THREADS>*>(raw);
     lstm_load_weights<H, THREADS>(s, We, be, W_ih, W_hh, b_ih, b_hh, E);
@@ -124,7 +174,7 @@ lstm_encoder_kernel(const float* __restrict__ obs_rel, int T, int batch, const f
                 if (live[k]) d = *reinterpret_cast<const float2*>(obs_rel + ((int64_t)t * batch + p[k]) * 2);
                 dx[k] = d.x; dy[k] = d.y;
             }
-            lstm_cell<H, THREADS>(s, h, dx, dy);
+            lstm_cell<H, THREADS, SAVE>(s, h, dx, dy, &tape, t, p, live);
         }
 #pragma unroll
         for (int k = 0; k < PPT; ++k) {
@@ -137,13 +187,14 @@ lstm_encoder_kernel(const float* __restrict__ obs_rel, int T, int batch, const f
     }
 }
 
-template <int H, int THREADS>
+template <int H, int THREADS, bool SAVE>
 __global__ void __launch_bounds__(THREADS)
 lstm_decoder_kernel(const float* __restrict__ h0, const float* __restrict__ c0, const float* __restrict__ last_pos_rel,
                     const float* __restrict__ z, const int32_t* __restrict__ ped_scene, int nz, int steps, int batch, const float* __restrict__ We, const float* __restrict__ be,
                     const float* __restrict__ W_ih, const float* __restrict__ W_hh, const float* __restrict__ b_ih,
                     const float* __restrict__ b_hh, const float* __restrict__ W_hp, const float* __restrict__ b_hp, int E,
-                    float* __restrict__ pred_rel, float* __restrict__ h_final, float* __restrict__ c_final) {
+                    float* __restrict__ pred_rel, float* __restrict__ h_final, float* __restrict__ c_final,
+                    LstmTape tape) {
     extern __shared__ __align__(16) uint8_t raw[];
     LstmSmem<H, THREADS>& s = *reinterpret_cast<LstmSmem<H, THREADS>*>(raw);
     lstm_load_weights<H, THREADS>(s, We, be, W_ih, W_hh, b_ih, b_hh, E);
@@ -175,7 +226,7 @@ lstm_decoder_kernel(const float* __restrict__ h0, const float* __restrict__ c0, 
             dx[k] = d.x; dy[k] = d.y;
         }
         for (int t = 0; t < steps; ++t) {
-            lstm_cell<H, THREADS>(s, h, dx, dy);
+            lstm_cell<H, THREADS, SAVE>(s, h, dx, dy, &tape, t, p, live);
 #pragma unroll
             for (int k = 0; k < PPT; ++k) {
                 float rx = s.whp[2 * H], ry = s.whp[2 * H + 1];
@@ -203,34 +254,171 @@ lstm_decoder_kernel(const float* __restrict__ h0, const float* __restrict__ c0, 
     }
 }
 
-template <int H>
+template <int H, bool SAVE = false>
 static int launch_encoder(const float* obs_rel, int T, int64_t batch, const float* We, const float* be,
                           const float* W_ih, const float* W_hh, const float* b_ih, const float* b_hh, int E,
-                          float* h_out, cudaStream_t st) {
+                          float* h_out, cudaStream_t st, LstmTape tape = LstmTape()) {
     constexpr int THREADS = 128;
-    auto kern = lstm_encoder_kernel<H, THREADS>;
+    auto kern = lstm_encoder_kernel<H, THREADS, SAVE>;
     const int smem = (int)sizeof(LstmSmem<H, THREADS>);
     SGX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     unsigned grid = (unsigned)std::min<int64_t>((batch + THREADS * PPT - 1) / (THREADS * PPT), 148 * 4);
-    kern<<<grid, THREADS, smem, st>>>(obs_rel, T, (int)batch, We, be, W_ih, W_hh, b_ih, b_hh, E, h_out);
+    kern<<<grid, THREADS, smem, st>>>(obs_rel, T, (int)batch, We, be, W_ih, W_hh, b_ih, b_hh, E, h_out, tape);
     SGX_LAUNCH_CHECK();
     return SGX_OK;
 }
 
-template <int H>
+template <int H, bool SAVE = false>
 static int launch_decoder(const float* h0, const float* c0, const float* last_pos_rel, const float* z,
                           const int32_t* ped_scene, int nz, int steps, int64_t batch,
                           const float* We, const float* be, const float* W_ih, const float* W_hh, const float* b_ih,
                           const float* b_hh, const float* W_hp, const float* b_hp, int E, float* pred_rel,
-                          float* h_final, float* c_final, cudaStream_t st) {
+                          float* h_final, float* c_final, cudaStream_t st, LstmTape tape = LstmTape()) {
     constexpr int THREADS = 128;
-    auto kern = lstm_decoder_kernel<H, THREADS>;
+    auto kern = lstm_decoder_kernel<H, THREADS, SAVE>;
     const int smem = (int)sizeof(LstmSmem<H, THREADS>);
     SGX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     unsigned grid = (unsigned)std::min<int64_t>((batch + THREADS * PPT - 1) / (THREADS * PPT), 148 * 4);
     kern<<<grid, THREADS, smem, st>>>(h0, c0, last_pos_rel, z, ped_scene, nz, steps, (int)batch, We, be, W_ih, W_hh, b_ih, b_hh, W_hp,
-                                      b_hp, E, pred_rel, h_final, c_final);
+                                      b_hp, E, pred_rel, h_final, c_final, tape);
     SGX_LAUNCH_CHECK();
+    return SGX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward through the whole recurrence in one kernel (thread per pedestrian, t = T-1 .. 0), reading the tape.
+//   d(pre-activation gates) -> dG [4H][T][B] for the parameter-gradient GEMMs
+//   decoder: the step input is hidden2pos of the previous step, so d(rel_t) = d_pred_rel[t] + Wx^T dG_{t+1} and
+//            dh_t += W_hp^T d(rel_t); d(rel_t) is kept in dRel [2][T][B]; dh_0's carry is d_h0.
+//   encoder: d(seq_in[t]) = Wx^T dG_t (needed when the sequence is a generator output fed to the discriminator).
+// dh lives in the hn columns of shared memory, dc in the c columns, W_hh^T dG accumulates in registers.
+// ------------------------------------------------------------------------------------------------
+template <int H, int THREADS, bool DECODER>
+__global__ void __launch_bounds__(THREADS)
+lstm_bwd_kernel(LstmTape tape, int T, int batch, const float* __restrict__ We, const float* __restrict__ be,
+                const float* __restrict__ W_ih, const float* __restrict__ W_hh, const float* __restrict__ b_ih,
+                const float* __restrict__ b_hh, const float* __restrict__ W_hp, int E,
+                const float* __restrict__ d_seq_out, const float* __restrict__ d_h_last, float* __restrict__ d_seq_in,
+                float* __restrict__ d_h0, float* __restrict__ d_c0, float* __restrict__ dG, float* __restrict__ dRel) {
+    extern __shared__ __align__(16) uint8_t raw[];
+    LstmSmem<H, THREADS>& s = *reinterpret_cast<LstmSmem<H, THREADS>*>(raw);
+    lstm_load_weights<H, THREADS>(s, We, be, W_ih, W_hh, b_ih, b_hh, E);
+    if (DECODER) for (int e = threadIdx.x; e < 2 * H; e += THREADS) s.whp[e] = W_hp[e];
+    __syncthreads();
+    const int tid = threadIdx.x;
+    const int64_t plane = (int64_t)T * batch;
+    for (int p = blockIdx.x * THREADS + tid; p < batch; p += gridDim.x * THREADS) {
+#pragma unroll 4
+        for (int u = 0; u < H; ++u) {
+            s.hn[u * THREADS + tid] = d_h_last ? d_h_last[(int64_t)p * H + u] : 0.f;      // dh
+            s.c[u * THREADS + tid] = 0.f;                                                   // dc
+        }
+        float cx = 0.f, cy = 0.f;                        // Wx^T dG of the step after this one
+        for (int t = T - 1; t >= 0; --t) {
+            const int64_t at = (int64_t)t * batch + p;
+            if (DECODER) {
+                const float2 go = *reinterpret_cast<const float2*>(d_seq_out + at * 2);
+                const float rx = go.x + cx, ry = go.y + cy;
+                dRel[at] = rx;
+                dRel[plane + at] = ry;
+#pragma unroll 4
+                for (int u = 0; u < H; ++u)
+                    s.hn[u * THREADS + tid] += s.whp[u] * rx + s.whp[H + u] * ry;
+            }
+            float dhp[H];
+#pragma unroll
+            for (int j = 0; j < H; ++j) dhp[j] = 0.f;
+            float dx = 0.f, dy = 0.f;
+#pragma unroll 1
+            for (int u = 0; u < H; ++u) {
+                const float gi = tape.gact[(0 * H + u) * plane + at], gf = tape.gact[(1 * H + u) * plane + at];
+                const float gg = tape.gact[(2 * H + u) * plane + at], go = tape.gact[(3 * H + u) * plane + at];
+                const float cp = tape.cprev[u * plane + at], tc = tape.tanhc[u * plane + at];
+                const float dh = s.hn[u * THREADS + tid];
+                const float dc = s.c[u * THREADS + tid] + dh * go * (1.f - tc * tc);
+                float d[4];
+                d[0] = dc * gg * gi * (1.f - gi);
+                d[1] = dc * cp * gf * (1.f - gf);
+                d[2] = dc * gi * (1.f - gg * gg);
+                d[3] = dh * tc * go * (1.f - go);
+                s.c[u * THREADS + tid] = dc * gf;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int r = q * H + u;
+                    dG[r * plane + at] = d[q];
+                    const float4 wi = s.wxb[r];
+                    dx = fmaf(wi.x, d[q], dx);
+                    dy = fmaf(wi.y, d[q], dy);
+                    const float4* w = reinterpret_cast<const float4*>(&s.whh[r * H]);
+#pragma unroll
+                    for (int j = 0; j < H / 4; ++j) {
+                        const float4 v = w[j];
+                        dhp[4 * j] = fmaf(v.x, d[q], dhp[4 * j]);
+                        dhp[4 * j + 1] = fmaf(v.y, d[q], dhp[4 * j + 1]);
+                        dhp[4 * j + 2] = fmaf(v.z, d[q], dhp[4 * j + 2]);
+                        dhp[4 * j + 3] = fmaf(v.w, d[q], dhp[4 * j + 3]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < H; ++j) s.hn[j * THREADS + tid] = dhp[j];
+            if (DECODER) { cx = dx; cy = dy; }
+            else if (d_seq_in) *reinterpret_cast<float2*>(d_seq_in + at * 2) = make_float2(dx, dy);
+        }
+        if (d_h0) {
+#pragma unroll 4
+            for (int u = 0; u < H; ++u) d_h0[(int64_t)p * H + u] = s.hn[u * THREADS + tid];
+        }
+        if (d_c0) {
+#pragma unroll 4
+            for (int u = 0; u < H; ++u) d_c0[(int64_t)p * H + u] = s.c[u * THREADS + tid];
+        }
+    }
+}
+
+static LstmTape carve_tape(float* base, int T, int64_t B, int H) {
+    LstmTape t;
+    const int64_t plane = (int64_t)T * B;
+    t.gact = base;
+    t.cprev = t.gact + 4 * H * plane;
+    t.tanhc = t.cprev + H * plane;
+    t.hprev = t.tanhc + H * plane;
+    t.hout = t.hprev + H * plane;
+    t.xaug = t.hout + (H + 1) * plane;
+    t.T = T;
+    t.B = B;
+    return t;
+}
+
+template <int H>
+static int lstm_backward(bool decoder, LstmTape tape, int T, int64_t batch, const float* We, const float* be,
+                         const float* W_ih, const float* W_hh, const float* b_ih, const float* b_hh, const float* W_hp,
+                         int E, const float* d_seq_out, const float* d_h_last, float* d_seq_in, float* d_h0,
+                         float* d_c0, float* dW_hh, float* dS, float* dW_hp_aug, float* ws, cudaStream_t st) {
+    constexpr int THREADS = 128;
+    const int64_t plane = (int64_t)T * batch;
+    float* dG = ws;
+    float* dRel = ws + 4 * H * plane;
+    const int smem = (int)sizeof(LstmSmem<H, THREADS>);
+    const unsigned grid = (unsigned)std::min<int64_t>((batch + THREADS - 1) / THREADS, 148 * 4);
+    if (decoder) {
+        auto kern = lstm_bwd_kernel<H, THREADS, true>;
+        SGX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        kern<<<grid, THREADS, smem, st>>>(tape, T, (int)batch, We, be, W_ih, W_hh, b_ih, b_hh, W_hp, E, d_seq_out, d_h_last,
+                                          d_seq_in, d_h0, d_c0, dG, dRel);
+    } else {
+        auto kern = lstm_bwd_kernel<H, THREADS, false>;
+        SGX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        kern<<<grid, THREADS, smem, st>>>(tape, T, (int)batch, We, be, W_ih, W_hh, b_ih, b_hh, W_hp, E, d_seq_out, d_h_last,
+                                          d_seq_in, d_h0, d_c0, dG, dRel);
+    }
+    SGX_LAUNCH_CHECK();
+    int rc;
+    // dW_hh [4H,H] = dG [4H, T*B] . hprev [H, T*B]^T ;  dS [4H,3] = dG . (dx, dy, 1)^T  (input weights, embedding, biases)
+    if ((rc = gemm(dG, plane, 1, tape.hprev, 1, plane, dW_hh, H, 4 * H, H, plane, 0, 0, st))) return rc;
+    if ((rc = gemm(dG, plane, 1, tape.xaug, 1, plane, dS, 3, 4 * H, 3, plane, 0, 0, st))) return rc;
+    if (decoder)   // [dW_hp | db_hp] [2, H+1] = dRel [2, T*B] . (hout ; 1) [H+1, T*B]^T
+        if ((rc = gemm(dRel, plane, 1, tape.hout, 1, plane, dW_hp_aug, H + 1, 2, H + 1, plane, 0, 0, st))) return rc;
     return SGX_OK;
 }
 
@@ -294,4 +482,64 @@ extern "C" int sgx_lstm_decoder_fwd(const float* h0, const float* c0, const floa
                                   pred_rel, h_final, c_final, st);
     sgx::set_error("fused LSTM is built for h_dim in {32, 48, 64}; got %d", H);
     return SGX_ERR_UNSUPPORTED;
+}
+
+// ---- training path (forward with tape, backward) -------------------------------------------------
+extern "C" int64_t sgx_lstm_tape_floats(int32_t T, int64_t batch, int32_t H) {
+    return ((int64_t)4 * H + 3 * (int64_t)H + (H + 1) + 3) * T * batch;
+}
+extern "C" int64_t sgx_lstm_bwd_ws_bytes(int32_t T, int64_t batch, int32_t H) {
+    return ((int64_t)4 * H + 2) * T * batch * (int64_t)sizeof(float);
+}
+
+#define SGX_LSTM_DISPATCH_H(H, CALL)                                                         \
+    if (H == 32) { constexpr int HH = 32; return CALL; }                                     \
+    if (H == 48) { constexpr int HH = 48; return CALL; }                                     \
+    if (H == 64) { constexpr int HH = 64; return CALL; }                                     \
+    sgx::set_error("fused LSTM is built for h_dim in {32, 48, 64}; got %d", H);             \
+    return SGX_ERR_UNSUPPORTED;
+
+extern "C" int sgx_lstm_encoder_train_fwd(const float* seq_in, int32_t T, int64_t batch, const float* We,
+                                          const float* be, const float* W_ih, const float* W_hh, const float* b_ih,
+                                          const float* b_hh, int32_t E, int32_t H, float* h_out, float* tape,
+                                          void* stream) {
+    SGX_REQUIRE(seq_in && We && be && W_ih && W_hh && b_ih && b_hh && h_out && tape,
+                "sgx_lstm_encoder_train_fwd: null pointer");
+    SGX_REQUIRE(T >= 1 && batch >= 1 && batch < ((int64_t)1 << 31) && E >= 1, "sgx_lstm_encoder_train_fwd: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    SGX_LSTM_DISPATCH_H(H, (launch_encoder<HH, true>(seq_in, T, batch, We, be, W_ih, W_hh, b_ih, b_hh, E, h_out, st,
+                                                      carve_tape(tape, T, batch, HH))))
+}
+
+extern "C" int sgx_lstm_decoder_train_fwd(const float* h0, const float* c0, const float* last_pos_rel, int32_t steps,
+                                          int64_t batch, const float* We, const float* be, const float* W_ih,
+                                          const float* W_hh, const float* b_ih, const float* b_hh, const float* W_hp,
+                                          const float* b_hp, int32_t E, int32_t H, float* pred_rel, float* h_final,
+                                          float* tape, void* stream) {
+    SGX_REQUIRE(h0 && last_pos_rel && We && be && W_ih && W_hh && b_ih && b_hh && W_hp && b_hp && pred_rel && tape,
+                "sgx_lstm_decoder_train_fwd: null pointer");
+    SGX_REQUIRE(steps >= 1 && batch >= 1 && batch < ((int64_t)1 << 31) && E >= 1, "sgx_lstm_decoder_train_fwd: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    SGX_LSTM_DISPATCH_H(H, (launch_decoder<HH, true>(h0, c0, last_pos_rel, nullptr, nullptr, 0, steps, batch, We, be, W_ih,
+                                                      W_hh, b_ih, b_hh, W_hp, b_hp, E, pred_rel, h_final, nullptr, st,
+                                                      carve_tape(tape, steps, batch, HH))))
+}
+
+// decoder != 0: d_seq_out = d(pred_rel) [T,B,2] (required), d_h0 / d_c0 [B,H] receive d(h0) / d(c0), dW_hp_aug [2,H+1] = [dW_hp | db_hp].
+// decoder == 0: d_seq_in [T,B,2] (nullable) receives d(seq_in); d_seq_out / W_hp / dW_hp_aug unused.
+// dS [4H,3] = dG . (x, y, 1)^T: the caller forms dW_ih = dS[:, :2] We^T + dS[:, 2] be^T, dWe = W_ih^T dS[:, :2],
+// dbe = W_ih^T dS[:, 2], db_ih = db_hh = dS[:, 2]  (the embedding is folded into the input weights in the kernel).
+extern "C" int sgx_lstm_bwd(int32_t decoder, const float* tape, int32_t T, int64_t batch, const float* We,
+                            const float* be, const float* W_ih, const float* W_hh, const float* b_ih,
+                            const float* b_hh, const float* W_hp, int32_t E, int32_t H, const float* d_seq_out,
+                            const float* d_h_last, float* d_seq_in, float* d_h0, float* d_c0, float* dW_hh,
+                            float* dS, float* dW_hp_aug, void* workspace, int64_t ws_bytes, void* stream) {
+    SGX_REQUIRE(tape && We && be && W_ih && W_hh && b_ih && b_hh && dW_hh && dS && workspace, "sgx_lstm_bwd: null pointer");
+    SGX_REQUIRE(!decoder || (W_hp && d_seq_out && dW_hp_aug), "sgx_lstm_bwd: decoder needs W_hp, d_seq_out, dW_hp_aug");
+    SGX_REQUIRE(T >= 1 && batch >= 1 && batch < ((int64_t)1 << 31) && E >= 1, "sgx_lstm_bwd: bad shape");
+    SGX_REQUIRE(ws_bytes >= sgx_lstm_bwd_ws_bytes(T, batch, H), "sgx_lstm_bwd: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    SGX_LSTM_DISPATCH_H(H, (lstm_backward<HH>(decoder != 0, carve_tape(const_cast<float*>(tape), T, batch, HH), T, batch, We,
+                                               be, W_ih, W_hh, b_ih, b_hh, W_hp, E, d_seq_out, d_h_last, d_seq_in, d_h0,
+                                               d_c0, dW_hh, dS, dW_hp_aug, (float*)workspace, st)))
 }

@@ -28,6 +28,20 @@ def _fused_lstm_ok(module, lstm, *tensors):
     return True
 
 
+def _fused_lstm_train_ok(module, lstm, *tensors):
+    """Under autograd the recurrence runs as one forward kernel with a tape + one backward kernel
+    (ops.lstm_encoder_train / lstm_decoder_train) instead of cuDNN + a python step loop.  SGX_LSTM_TRAIN=0 keeps the
+    nn.LSTM path (kept for A/B parity tests)."""
+    import os
+    if os.environ.get('SGX_LSTM_TRAIN', '1') == '0':
+        return False
+    if not all(t is None or (t.is_cuda and t.dtype == torch.float32) for t in tensors):
+        return False
+    if lstm.num_layers != 1 or lstm.hidden_size not in ops.FUSED_LSTM_H or lstm.bidirectional:
+        return False
+    return not (lstm.dropout and module.training)
+
+
 def get_noise(shape, noise_type, device=None):
     """Drawn on the CPU generator then moved, exactly like sgan/models.py:23-29 (seed-compatible)."""
     if noise_type == 'gaussian':
@@ -59,6 +73,8 @@ class Encoder(nn.Module):
         batch = obs_traj.size(1)
         if _fused_lstm_ok(self, self.encoder, obs_traj):
             return ops.lstm_encoder(obs_traj, self.spatial_embedding, self.encoder)
+        if _fused_lstm_train_ok(self, self.encoder, obs_traj):
+            return ops.lstm_encoder_train(obs_traj, self.spatial_embedding, self.encoder)
         emb = self.spatial_embedding(obs_traj.reshape(-1, 2)).view(-1, batch, self.embedding_dim)
         _, state = self.encoder(emb, self.init_hidden(batch, emb))
         return state[0]
@@ -91,6 +107,10 @@ class Decoder(nn.Module):
         batch = last_pos.size(0)
         if _fused_lstm_ok(self, self.decoder, last_pos_rel, state_tuple[0], state_tuple[1]):
             return self._forward_fused(last_pos, last_pos_rel, state_tuple, seq_start_end)
+        if not self.pool_every_timestep and _fused_lstm_train_ok(self, self.decoder, last_pos_rel, *state_tuple):
+            pred, hf = ops.lstm_decoder_train(state_tuple[0], state_tuple[1], last_pos_rel, self.seq_len,
+                                              self.spatial_embedding, self.decoder, self.hidden2pos)
+            return pred, hf.unsqueeze(0)
         steps = []
         dec_in = self.spatial_embedding(last_pos_rel).view(1, batch, self.embedding_dim)
         for _ in range(self.seq_len):

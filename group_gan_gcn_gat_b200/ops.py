@@ -395,3 +395,112 @@ def lstm_decoder(h0, c0, last_pos_rel, steps, emb, lstm, hidden2pos, want_state=
     if want_state == 'h':
         return pred, hf
     return (pred, hf, cf) if want_state else pred
+
+
+# ------------------------------------------------------------------------------------------------
+# Training path of the recurrences: one forward kernel that writes a tape, one backward kernel + reductions
+# (sgx_lstm_*_train_fwd / sgx_lstm_bwd).  The step loop of sgan/models.py:157-175 under autograd is ~45 launches per
+# decoder step forward + backward; this is 2 + 5.
+# ------------------------------------------------------------------------------------------------
+def _lstm_params(emb, lstm):
+    return (emb.weight, emb.bias, lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0)
+
+
+def _lstm_param_grads(dS, dW_hh, We, be, W_ih):
+    """dS [4H,3] -> gradients of (We, be, W_ih, W_hh, b_ih, b_hh); the kernels fold the embedding into W_ih."""
+    dSxy, dSb = dS[:, :2], dS[:, 2]
+    return (W_ih.t() @ dSxy, W_ih.t() @ dSb, dSxy @ We.t() + torch.outer(dSb, be), dW_hh, dSb, dSb.clone())
+
+
+class _LstmEncoderTrain(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, seq_in, We, be, W_ih, W_hh, b_ih, b_hh):
+        seq = _f32(seq_in, 'obs_traj_rel')
+        T, batch, _ = seq.shape
+        H, E = W_hh.shape[1], We.shape[0]
+        L = _lib.lib()
+        out = torch.empty(batch, H, dtype=torch.float32, device=seq.device)
+        tape = torch.empty(L.sgx_lstm_tape_floats(T, batch, H), dtype=torch.float32, device=seq.device)
+        w = [t.contiguous() for t in (We, be, W_ih, W_hh, b_ih, b_hh)]
+        with torch.cuda.device(seq.device):
+            _lib.check(L.sgx_lstm_encoder_train_fwd(_ptr(seq), T, batch, *[_ptr(t) for t in w], E, H, _ptr(out), _ptr(tape),
+                                                    _stream(seq)), 'sgx_lstm_encoder_train_fwd')
+        ctx.save_for_backward(tape, *w)
+        ctx.dims = (T, batch, H, E)
+        ctx.need_dseq = seq_in.requires_grad
+        return out
+
+    @staticmethod
+    def backward(ctx, d_h):
+        tape, We, be, W_ih, W_hh, b_ih, b_hh = ctx.saved_tensors
+        T, batch, H, E = ctx.dims
+        L = _lib.lib()
+        dev = tape.device
+        d_h = d_h.contiguous().float()
+        d_seq = torch.empty(T, batch, 2, dtype=torch.float32, device=dev) if ctx.need_dseq else None
+        dW_hh = torch.empty(4 * H, H, dtype=torch.float32, device=dev)
+        dS = torch.empty(4 * H, 3, dtype=torch.float32, device=dev)
+        ws = _ws(L.sgx_lstm_bwd_ws_bytes(T, batch, H), dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.sgx_lstm_bwd(0, _ptr(tape), T, batch, _ptr(We), _ptr(be), _ptr(W_ih), _ptr(W_hh), _ptr(b_ih),
+                                      _ptr(b_hh), None, E, H, None, _ptr(d_h), _ptr(d_seq), None, None, _ptr(dW_hh),
+                                      _ptr(dS), None, _ptr(ws), ws.numel(), _stream(tape)), 'sgx_lstm_bwd')
+        return (d_seq,) + _lstm_param_grads(dS, dW_hh, We, be, W_ih)
+
+
+class _LstmDecoderTrain(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h0, c0, last_pos_rel, We, be, W_ih, W_hh, b_ih, b_hh, W_hp, b_hp, steps):
+        h0c = _f32(h0, 'decoder_h')
+        c0c = None if c0 is None else _f32(c0, 'decoder_c')
+        rel0 = _f32(last_pos_rel, 'last_pos_rel')
+        batch, H = h0c.shape
+        E = We.shape[0]
+        L = _lib.lib()
+        dev = h0c.device
+        pred = torch.empty(steps, batch, 2, dtype=torch.float32, device=dev)
+        hf = torch.empty(batch, H, dtype=torch.float32, device=dev)
+        tape = torch.empty(L.sgx_lstm_tape_floats(steps, batch, H), dtype=torch.float32, device=dev)
+        w = [t.contiguous() for t in (We, be, W_ih, W_hh, b_ih, b_hh, W_hp, b_hp)]
+        with torch.cuda.device(dev):
+            _lib.check(L.sgx_lstm_decoder_train_fwd(_ptr(h0c), _ptr(c0c), _ptr(rel0), steps, batch, *[_ptr(t) for t in w], E, H,
+                                                    _ptr(pred), _ptr(hf), _ptr(tape), _stream(h0c)),
+                       'sgx_lstm_decoder_train_fwd')
+        ctx.save_for_backward(tape, *w)
+        ctx.dims = (steps, batch, H, E)
+        ctx.need_dh0 = h0.requires_grad
+        ctx.need_dc0 = c0 is not None and c0.requires_grad
+        return pred, hf
+
+    @staticmethod
+    def backward(ctx, d_pred, d_hf):
+        tape, We, be, W_ih, W_hh, b_ih, b_hh, W_hp, b_hp = ctx.saved_tensors
+        T, batch, H, E = ctx.dims
+        L = _lib.lib()
+        dev = tape.device
+        d_pred = torch.zeros(T, batch, 2, dtype=torch.float32, device=dev) if d_pred is None else d_pred.contiguous().float()
+        d_hf = None if d_hf is None else d_hf.contiguous().float()
+        d_h0 = torch.empty(batch, H, dtype=torch.float32, device=dev) if ctx.need_dh0 else None
+        d_c0 = torch.empty(batch, H, dtype=torch.float32, device=dev) if ctx.need_dc0 else None
+        dW_hh = torch.empty(4 * H, H, dtype=torch.float32, device=dev)
+        dS = torch.empty(4 * H, 3, dtype=torch.float32, device=dev)
+        dWhp = torch.empty(2, H + 1, dtype=torch.float32, device=dev)
+        ws = _ws(L.sgx_lstm_bwd_ws_bytes(T, batch, H), dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.sgx_lstm_bwd(1, _ptr(tape), T, batch, _ptr(We), _ptr(be), _ptr(W_ih), _ptr(W_hh), _ptr(b_ih),
+                                      _ptr(b_hh), _ptr(W_hp), E, H, _ptr(d_pred), _ptr(d_hf), None, _ptr(d_h0),
+                                      _ptr(d_c0), _ptr(dW_hh), _ptr(dS), _ptr(dWhp), _ptr(ws), ws.numel(), _stream(tape)), 'sgx_lstm_bwd')
+        return (d_h0, d_c0, None) + _lstm_param_grads(dS, dW_hh, We, be, W_ih) + (dWhp[:, :H].contiguous(), dWhp[:, H].contiguous(), None)
+
+
+def lstm_encoder_train(seq_in, emb, lstm):
+    """Differentiable Encoder.forward (sgan/models.py:62-92): seq_in [T,batch,2] -> final_h [1,batch,H]."""
+    return _LstmEncoderTrain.apply(seq_in, *_lstm_params(emb, lstm)).unsqueeze(0)
+
+
+def lstm_decoder_train(h0, c0, last_pos_rel, steps, emb, lstm, hidden2pos):
+    """Differentiable Decoder.forward without per-step pooling (sgan/models.py:142-178); c0 None = zeros:
+    -> pred_rel [steps,batch,2], final_h [batch,H]."""
+    c0 = None if c0 is None else c0.reshape(-1, lstm.hidden_size)
+    return _LstmDecoderTrain.apply(h0.reshape(-1, lstm.hidden_size), c0, last_pos_rel, *_lstm_params(emb, lstm),
+                                   hidden2pos.weight, hidden2pos.bias, steps)

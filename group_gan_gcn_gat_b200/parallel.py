@@ -99,6 +99,21 @@ def discriminator_step(args, batch, generator, discriminator, optimizer_d, label
     return {'D_total_loss': float(loss.detach()) / max(w, 1e-12) if w else 0.0}
 
 
+def _folded_samples(generator, obs_traj, obs_traj_rel, obs_traj_g, seq_start_end, k):
+    """k generator samples as one forward over k copies of the batch -> fake_rel [pred_len, k * batch, 2] (sample-major)."""
+    from .models import get_noise
+    n, s = obs_traj.shape[1], seq_start_end.shape[0]
+    noise = None
+    if generator.noise_dim:
+        rows = s if generator.noise_mix_type == 'global' else n
+        noise = torch.cat([get_noise((rows,) + tuple(generator.noise_dim), generator.noise_type, obs_traj.device)
+                           for _ in range(k)], dim=0)
+    offs = (torch.arange(k, device=seq_start_end.device, dtype=seq_start_end.dtype) * n).repeat_interleave(s)
+    sse_k = seq_start_end.repeat(k, 1) + offs.unsqueeze(1)
+    return generator(obs_traj.repeat(1, k, 1), obs_traj_rel.repeat(1, k, 1), sse_k, obs_traj_g.repeat(1, k, 1),
+                     user_noise=noise)
+
+
 def generator_step(args, batch, generator, discriminator, optimizer_g, label_rng=None, group=None):
     """scripts/train.py:432-484: best-of-K variety loss + adversarial term on the last sample."""
     (obs_traj, pred_traj_gt, obs_traj_rel, pred_traj_gt_rel, obs_traj_g, loss_mask, seq_start_end) = batch
@@ -107,10 +122,20 @@ def generator_step(args, batch, generator, discriminator, optimizer_g, label_rng
     sched = get_schedule(seq_start_end, obs_traj.device)
     mask = loss_mask[:, args.obs_len:]
     raws = []
-    for _ in range(args.best_k):
-        fake_rel = generator(obs_traj, obs_traj_rel, seq_start_end, obs_traj_g)
-        if args.l2_loss_weight > 0:
-            raws.append(args.l2_loss_weight * l2_loss(fake_rel, pred_traj_gt_rel, mask, mode='raw'))
+    if getattr(args, 'fold_best_k', True) and args.best_k > 1:
+        # The best_k samples share weights and inputs and differ only in the noise: run them as ONE forward / backward
+        # over best_k copies of the batch (SURVEY 8d cfg 4/5: "K folded into the batch dimension").  Same noise stream
+        # as the loop (one get_noise draw per sample, in order), same loss terms, 1/best_k of the launches.
+        fake_all = _folded_samples(generator, obs_traj, obs_traj_rel, obs_traj_g, seq_start_end, args.best_k)
+        for k in range(args.best_k):
+            fake_rel = fake_all[:, k * n_local:(k + 1) * n_local]
+            if args.l2_loss_weight > 0:
+                raws.append(args.l2_loss_weight * l2_loss(fake_rel, pred_traj_gt_rel, mask, mode='raw'))
+    else:
+        for _ in range(args.best_k):
+            fake_rel = generator(obs_traj, obs_traj_rel, seq_start_end, obs_traj_g)
+            if args.l2_loss_weight > 0:
+                raws.append(args.l2_loss_weight * l2_loss(fake_rel, pred_traj_gt_rel, mask, mode='raw'))
     loss = obs_traj.new_zeros(())
     losses = {}
     if args.l2_loss_weight > 0:

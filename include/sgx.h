@@ -204,6 +204,32 @@ int sgx_lstm_decoder_fwd(const float* h0, const float* c0, const float* last_pos
                          float* pred_rel, float* h_final, float* c_final, void* workspace, int64_t ws_bytes,
                          void* stream);
 
+/* Training path of the same recurrences (what autograd does through nn.LSTM + the step loop of sgan/models.py:157-175,
+ * replaced by one forward kernel that writes a tape and one backward kernel + 2-3 reductions):
+ *   tape: sgx_lstm_tape_floats(T, batch, H) floats, caller-owned, kept between forward and backward.
+ *   sgx_lstm_encoder_train_fwd / sgx_lstm_decoder_train_fwd: as the inference entry points (zero initial state for the
+ *     encoder; decoder without noise fold-in -- pass the concatenated [batch,H] state), plus the tape.
+ *   sgx_lstm_bwd: decoder != 0: d_seq_out = d(pred_rel) [T,batch,2], d_h_last = d(h_final) [batch,H] or null;
+ *       outputs d_h0 / d_c0 [batch,H] (null to skip), dW_hp_aug [2,H+1] = [dW_hp | db_hp].
+ *     decoder == 0: d_h_last = d(final_h) [batch,H]; d_seq_in [T,batch,2] receives d(seq_in) (null to skip).
+ *     Both: dW_hh [4H,H]; dS [4H,3] = sum_t dG_t (x_t, y_t, 1)^T, from which the caller forms (the embedding is folded
+ *     into the input weights inside the kernels)  dW_ih = dS[:, :2] We^T + dS[:, 2] be^T,  dWe = W_ih^T dS[:, :2],
+ *     dbe = W_ih^T dS[:, 2],  db_ih = db_hh = dS[:, 2].   workspace: sgx_lstm_bwd_ws_bytes(T, batch, H).
+ */
+int64_t sgx_lstm_tape_floats(int32_t T, int64_t batch, int32_t H);
+int64_t sgx_lstm_bwd_ws_bytes(int32_t T, int64_t batch, int32_t H);
+int sgx_lstm_encoder_train_fwd(const float* seq_in, int32_t T, int64_t batch, const float* We, const float* be,
+                               const float* W_ih, const float* W_hh, const float* b_ih, const float* b_hh, int32_t E,
+                               int32_t H, float* h_out, float* tape, void* stream);
+int sgx_lstm_decoder_train_fwd(const float* h0, const float* c0, const float* last_pos_rel, int32_t steps,
+                               int64_t batch, const float* We, const float* be, const float* W_ih, const float* W_hh,
+                               const float* b_ih, const float* b_hh, const float* W_hp, const float* b_hp, int32_t E,
+                               int32_t H, float* pred_rel, float* h_final, float* tape, void* stream);
+int sgx_lstm_bwd(int32_t decoder, const float* tape, int32_t T, int64_t batch, const float* We, const float* be,
+                 const float* W_ih, const float* W_hh, const float* b_ih, const float* b_hh, const float* W_hp,
+                 int32_t E, int32_t H, const float* d_seq_out, const float* d_h_last, float* d_seq_in, float* d_h0,
+                 float* d_c0, float* dW_hh, float* dS, float* dW_hp_aug, void* workspace, int64_t ws_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Displacement metrics + best-of-K reduction: relative_to_abs (sgan/utils.py:83-96) +
  * displacement_error / final_displacement_error mode='raw' (sgan/losses.py:74-119) for sample k, written to column k

@@ -86,6 +86,17 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             times[name].append(e0.elapsed_time(e1))
+    if os.environ.get('SGX_PROFILE_STEP') and rank == 0:    # kernel / host breakdown of one G step (torch.profiler)
+        rng = parallel.make_label_rng(0, 99)
+        with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA,
+                                                torch.profiler.ProfilerActivity.CPU]) as prof:
+            t0 = time.perf_counter()
+            parallel.generator_step(args, batch, gen, disc, opt_g, label_rng=rng)
+            t1 = time.perf_counter()
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+        print('G step: host issue %.1f ms, drain %.1f ms' % ((t1 - t0) * 1e3, (t2 - t1) * 1e3), file=sys.stderr)
+        print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=45, max_name_column_width=60), file=sys.stderr)
     # parameters must stay bit-identical across ranks after the reduced updates
     flat = torch.cat([p.detach().reshape(-1) for p in gen.parameters()])
     chk = torch.stack([flat.double().sum(), flat.double().abs().sum()])
