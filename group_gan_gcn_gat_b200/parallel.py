@@ -84,11 +84,22 @@ def discriminator_step(args, batch, generator, discriminator, optimizer_d, label
     (obs_traj, pred_traj_gt, obs_traj_rel, pred_traj_gt_rel, obs_traj_g, loss_mask, seq_start_end) = batch
     n_local = obs_traj.shape[1]
     w = n_local / _global_count(n_local, obs_traj.device, group)
-    fake_rel = generator(obs_traj, obs_traj_rel, seq_start_end, obs_traj_g)
-    fake = relative_to_abs(fake_rel, obs_traj[-1])
-    s_fake = discriminator(torch.cat([obs_traj, fake], 0), torch.cat([obs_traj_rel, fake_rel], 0), seq_start_end)
-    s_real = discriminator(torch.cat([obs_traj, pred_traj_gt], 0), torch.cat([obs_traj_rel, pred_traj_gt_rel], 0),
-                           seq_start_end)
+    # The reference leaves the generator graph attached here (scripts/train.py:404-409) and back-propagates the D loss
+    # into generator .grad buffers that optimizer_g.zero_grad() discards before they are ever used; running the
+    # generator without autograd gives the same D gradients and takes the inference kernels.
+    with torch.no_grad():
+        fake_rel = generator(obs_traj, obs_traj_rel, seq_start_end, obs_traj_g)
+        fake = relative_to_abs(fake_rel, obs_traj[-1])
+    if _batch_independent(discriminator):
+        # fake and real trajectories as ONE discriminator batch of 2 x scenes (same weights, independent scenes)
+        traj = torch.cat([torch.cat([obs_traj, fake], 0), torch.cat([obs_traj, pred_traj_gt], 0)], 1)
+        traj_rel = torch.cat([torch.cat([obs_traj_rel, fake_rel], 0), torch.cat([obs_traj_rel, pred_traj_gt_rel], 0)], 1)
+        scores = discriminator(traj, traj_rel, torch.cat([seq_start_end, seq_start_end + n_local], 0))
+        s_fake, s_real = scores[:n_local], scores[n_local:]
+    else:
+        s_fake = discriminator(torch.cat([obs_traj, fake], 0), torch.cat([obs_traj_rel, fake_rel], 0), seq_start_end)
+        s_real = discriminator(torch.cat([obs_traj, pred_traj_gt], 0), torch.cat([obs_traj_rel, pred_traj_gt_rel], 0),
+                               seq_start_end)
     loss = gan_d_loss(s_real, s_fake, label_rng) * w
     optimizer_d.zero_grad()
     loss.backward()
@@ -97,6 +108,17 @@ def discriminator_step(args, batch, generator, discriminator, optimizer_d, label
         nn.utils.clip_grad_norm_(discriminator.parameters(), args.clipping_threshold_d)
     optimizer_d.step()
     return {'D_total_loss': float(loss.detach()) / max(w, 1e-12) if w else 0.0}
+
+
+def _batch_independent(module):
+    """True when every pedestrian / scene is processed independently of the rest of the batch, i.e. stacking batches is
+    exact: no BatchNorm statistics and no active dropout."""
+    for m in module.modules():
+        if isinstance(m, nn.modules.batchnorm._BatchNorm):
+            return False
+        if isinstance(m, nn.Dropout) and m.p > 0 and m.training:
+            return False
+    return True
 
 
 def _folded_samples(generator, obs_traj, obs_traj_rel, obs_traj_g, seq_start_end, k):
@@ -122,7 +144,7 @@ def generator_step(args, batch, generator, discriminator, optimizer_g, label_rng
     sched = get_schedule(seq_start_end, obs_traj.device)
     mask = loss_mask[:, args.obs_len:]
     raws = []
-    if getattr(args, 'fold_best_k', True) and args.best_k > 1:
+    if getattr(args, 'fold_best_k', True) and args.best_k > 1 and _batch_independent(generator):
         # The best_k samples share weights and inputs and differ only in the noise: run them as ONE forward / backward
         # over best_k copies of the batch (SURVEY 8d cfg 4/5: "K folded into the batch dimension").  Same noise stream
         # as the loop (one get_noise draw per sample, in order), same loss terms, 1/best_k of the launches.

@@ -166,3 +166,50 @@ def test_generator_step_with_folded_samples_matches_the_sample_loop():
         moved += int(not torch.equal(b, p0.detach()))
         assert float((a - b).abs().max()) < 2e-5          # Adam step = lr * sign-like update, lr = 1e-3
     assert moved > 20
+
+
+def test_discriminator_step_stacked_batch_matches_two_calls():
+    """parallel.discriminator_step (generator under no_grad, fake + real as one D batch) == the reference's two D calls
+    with the generator graph attached (scripts/train.py:395-429): same loss, same D update."""
+    import copy
+    from types import SimpleNamespace
+    from group_gan_gcn_gat_b200 import models as MD, parallel
+    from group_gan_gcn_gat_b200.losses import gan_d_loss
+    from group_gan_gcn_gat_b200.utils import relative_to_abs
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(31)
+    gen = MD.TrajectoryGenerator(obs_len=8, pred_len=12, embedding_dim=16, encoder_h_dim=32, decoder_h_dim=32, mlp_dim=64,
+                                 noise_dim=(8,), noise_mix_type='global', pooling_type='pool_net',
+                                 pool_every_timestep=False, bottleneck_dim=8, batch_norm=False, n_heads=1).cuda()
+    disc = MD.TrajectoryDiscriminator(obs_len=8, pred_len=12, embedding_dim=16, h_dim=48, mlp_dim=64, batch_norm=False,
+                                      d_type='global').cuda()
+    sizes = [3, 6, 2, 4]
+    n = sum(sizes)
+    ends = torch.tensor(sizes).cumsum(0)
+    sse = torch.stack([ends - torch.tensor(sizes), ends], 1).cuda()
+    rel = torch.randn(20, n, 2, device='cuda') * 0.3
+    rel[0] = 0
+    traj = torch.randn(1, n, 2, device='cuda') * 5 + rel.cumsum(0)
+    grp = torch.randint(0, 3, (1, n, 1), device='cuda').float().expand(8, n, 1).contiguous()
+    batch = (traj[:8], traj[8:], rel[:8], rel[8:], grp, torch.ones(n, 20, device='cuda'), sse)
+    args = SimpleNamespace(obs_len=8, pred_len=12, clipping_threshold_d=0.0)
+    # ours
+    d1 = copy.deepcopy(disc)
+    torch.manual_seed(5)
+    out = parallel.discriminator_step(args, batch, gen, d1, torch.optim.Adam(d1.parameters(), lr=1e-3),
+                                      label_rng=parallel.make_label_rng(0, 0))
+    # the reference's sequence, spelled out
+    d2 = copy.deepcopy(disc)
+    opt = torch.optim.Adam(d2.parameters(), lr=1e-3)
+    torch.manual_seed(5)
+    fake_rel = gen(batch[0], batch[2], sse, grp)
+    fake = relative_to_abs(fake_rel, batch[0][-1])
+    s_fake = d2(torch.cat([batch[0], fake], 0), torch.cat([batch[2], fake_rel], 0), sse)
+    s_real = d2(torch.cat([batch[0], batch[1]], 0), torch.cat([batch[2], batch[3]], 0), sse)
+    loss = gan_d_loss(s_real, s_fake, parallel.make_label_rng(0, 0))
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+    assert abs(out['D_total_loss'] - float(loss)) < 1e-5 * max(1.0, abs(float(loss)))
+    for a, b in zip(d1.parameters(), d2.parameters()):
+        assert float((a - b).abs().max()) < 2e-5
