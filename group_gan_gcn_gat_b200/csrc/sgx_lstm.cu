@@ -9,7 +9,8 @@
 // embedding is folded into the input weights exactly:  W_ih (We d + be) = (W_ih We) d + W_ih be.
 // The reference issues one cuDNN call (plus ~6 small kernels) per decoder step; on the bench workload
 // cuDNN's persistent-RNN kernel took 3.7 ms per call (13 calls = 90 % of the generator forward).
-// Inference only: under autograd the modules keep using nn.LSTM (cuDNN) so training semantics are unchanged.
+// Training: the same kernels with SAVE = true write a tape; lstm_bwd_kernel walks it backwards (one thread per
+// pedestrian) and three tall-skinny GEMMs reduce the parameter gradients (sgx_lstm_*_train_fwd / sgx_lstm_bwd).
 #include <stdlib.h>
 
 #include "sgx_common.cuh"

@@ -17,7 +17,8 @@ from .schedule import get_schedule
 
 
 def _fused_lstm_ok(module, lstm, *tensors):
-    """The fused recurrence kernels serve inference; anything that needs autograd stays on nn.LSTM (cuDNN)."""
+    """The inference kernels (tensor-core LSTM for large batches); anything that needs autograd goes through
+    _fused_lstm_train_ok -> ops.lstm_*_train, or nn.LSTM (cuDNN) as the last resort."""
     if not all(t.is_cuda and t.dtype == torch.float32 for t in tensors):
         return False
     if lstm.num_layers != 1 or lstm.hidden_size not in ops.FUSED_LSTM_H or lstm.bidirectional:
