@@ -14,6 +14,8 @@
 // Backward mirrors it: per attention layer one "row" kernel (recompute softmax stats, d(pre-activation),
 // ds) and one "column" kernel (dt and dWh by gathering over the symmetric neighbourhood), GEMMs for the
 // parameter gradients.  dropout must be 0 (all shipped checkpoints; the module raises otherwise).
+#include <stdlib.h>
+
 #include "sgx_common.cuh"
 
 namespace sgx {
@@ -465,7 +467,7 @@ __device__ __forceinline__ void gemv_rows(const float* __restrict__ xrow, const 
 }
 
 // attention of one node over the slots [b,e) of its scene that satisfy `pick`; rows/scores live in shared memory
-template <int F, bool INTER>
+template <int F, bool INTER, int STRIDE = RS>
 __device__ __forceinline__ void attend_smem(const float* __restrict__ rows, const float2* __restrict__ st,
                                             const int* __restrict__ lead_slot, int b, int e, int my_lead, float s_i,
                                             float alpha, float (&hp)[F]) {
@@ -482,7 +484,35 @@ __device__ __forceinline__ void attend_smem(const float* __restrict__ rows, cons
         if (!nb) continue;
         const float w = fexp(lrelu(s_i + st[q].y, alpha) - m);
         den += w;
-        const float4* row = reinterpret_cast<const float4*>(rows + q * RS);
+        const float4* row = reinterpret_cast<const float4*>(rows + q * STRIDE);
+#pragma unroll
+        for (int f = 0; f < F / 4; ++f) {
+            const float4 v = row[f];
+            hp[4 * f] = fmaf(w, v.x, hp[4 * f]); hp[4 * f + 1] = fmaf(w, v.y, hp[4 * f + 1]);
+            hp[4 * f + 2] = fmaf(w, v.z, hp[4 * f + 2]); hp[4 * f + 3] = fmaf(w, v.w, hp[4 * f + 3]);
+        }
+    }
+    const float inv = 1.f / den;
+#pragma unroll
+    for (int f = 0; f < F; ++f) hp[f] *= inv;
+}
+
+
+// attention of one node over the lanes set in `mask` (its group's members / its scene's leaders), ascending lane order
+// = the order of attend_smem, so the two give bit-identical sums; iterates the neighbours only instead of the scene.
+template <int F, int STRIDE>
+__device__ __forceinline__ void attend_mask(const float* __restrict__ rows, const float2* __restrict__ st, uint32_t mask,
+                                            float s_i, float alpha, float (&hp)[F]) {
+    float m = -INFINITY;
+    for (uint32_t mm = mask; mm; mm &= mm - 1) m = fmaxf(m, lrelu(s_i + st[__ffs(mm) - 1].y, alpha));
+    float den = 0.f;
+#pragma unroll
+    for (int f = 0; f < F; ++f) hp[f] = 0.f;
+    for (uint32_t mm = mask; mm; mm &= mm - 1) {
+        const int q = __ffs(mm) - 1;
+        const float w = fexp(lrelu(s_i + st[q].y, alpha) - m);
+        den += w;
+        const float4* row = reinterpret_cast<const float4*>(rows + q * STRIDE);
 #pragma unroll
         for (int f = 0; f < F / 4; ++f) {
             const float4 v = row[f];
@@ -697,15 +727,274 @@ gat_fused_fwd_kernel(const float* __restrict__ x, const int32_t* __restrict__ le
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Same fused forward with the five linear maps on the tensor cores (warp-level mma.sync m16n8k8, 3xTF32: every
+// operand is split hi + lo with hi = top 19 bits, products hi*hi + lo*hi + hi*lo accumulate in fp32 -> ~7e-7 relative,
+// inside the 1e-5 contract).  The thread-per-row GEMV version is bound by the shared-memory data pipe (one broadcast
+// weight word per FMA); here a warp's 32 x K x N product reads every weight word once per 16 rows.  The attention
+// score projections (Wh a1, Wh a2) ride along as two extra weight columns (W a1, W a2).  The 128-row tcgen05 path does
+// not fit: five weight images with fp32-level splits plus per-tile operand staging exceed the 227 KB of shared memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int SW1 = 88;                // row stride of the [K][72+2 (+pad)] weight blocks: 88 % 32 = 24 -> conflict-free B fragments
+constexpr int SW2 = 24;                // row stride of the [K][16+2 (+pad)] and [32][24] blocks
+struct FusedWm {
+    float Wi[40 * SW1], Wio[HID * SW2], We[OUT * SW1], Weo[HID * SW2], WoT[2 * OUT * SW2], bo[24];
+};
+
+__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(v) & 0xFFFFE000u;
+    lo = __float_as_uint(v - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// C [32 x 8 NT] = A [32 x K] . B [K x 8 NT] for one warp; A rows in shared memory (stride SA floats), B row-major
+// (stride SB).  store(mt, nt, acc) receives the m16n8 accumulator fragment: acc[0..1] = row mt*16 + lane/4, columns
+// nt*8 + 2 (lane%4) + {0,1}; acc[2..3] = the same columns of row + 8.  A __syncwarp precedes the stores of an m-tile,
+// so C may overwrite the A rows of that m-tile.
+template <int K, int NT, int SA, int SB, class Store>
+__device__ __forceinline__ void warp_gemm_3xtf32(const float* __restrict__ A, const float* __restrict__ B, int lane,
+                                                 Store&& store) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll 1
+    for (int mt = 0; mt < 2; ++mt) {
+        float acc[NT][4];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+#pragma unroll 1
+        for (int ks = 0; ks < K / 8; ++ks) {
+            const float* ar = A + (mt * 16 + g) * SA + ks * 8 + t;
+            uint32_t ah[4], al[4];
+            split_tf32(ar[0], ah[0], al[0]);
+            split_tf32(ar[8 * SA], ah[1], al[1]);
+            split_tf32(ar[4], ah[2], al[2]);
+            split_tf32(ar[8 * SA + 4], ah[3], al[3]);
+            const float* br = B + (ks * 8 + t) * SB + g;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                uint32_t bh0, bl0, bh1, bl1;
+                split_tf32(br[nt * 8], bh0, bl0);
+                split_tf32(br[4 * SB + nt * 8], bh1, bl1);
+                mma_tf32(acc[nt], al, bh0, bh1);
+                mma_tf32(acc[nt], ah, bl0, bl1);
+                mma_tf32(acc[nt], ah, bh0, bh1);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) store(mt, nt, acc[nt]);
+    }
+    __syncwarp();
+}
+
+template <int IN, int FIN>
+__global__ void __launch_bounds__(FUSED_WARPS * 32)
+gat_fused_mma_kernel(const float* __restrict__ x, const int32_t* __restrict__ leader, const int32_t* __restrict__ gsize,
+                     const int32_t* __restrict__ ped_start, const int32_t* __restrict__ ped_end,
+                     const int32_t* __restrict__ scene_start, const int32_t* __restrict__ chunk_scene, int n_chunks,
+                     const float* __restrict__ Wi, const float* __restrict__ ai, const float* __restrict__ Wio,
+                     const float* __restrict__ aio, const float* __restrict__ We, const float* __restrict__ ae,
+                     const float* __restrict__ Weo, const float* __restrict__ aeo, const float* __restrict__ Wo,
+                     const float* __restrict__ bo, float alpha, float* __restrict__ out) {
+    static_assert(IN == 40 && FIN == 24, "built for the shipped dims");
+    extern __shared__ __align__(16) uint8_t raw[];
+    FusedWm& w = *reinterpret_cast<FusedWm*>(raw);
+    float* bufs = reinterpret_cast<float*>(raw + sizeof(FusedWm));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    {   // weight blocks [K][N + 2 score columns + zero padding]: column N = W a[:N], N+1 = W a[N:]
+        auto fill = [&](float* dst, int stride, const float* W, const float* a, int K, int N) {
+            for (int e = threadIdx.x; e < K * stride; e += blockDim.x) {
+                const int k = e / stride, n = e % stride;
+                float v = 0.f;
+                if (n < N) v = W[k * N + n];
+                else if (n < N + 2) {
+                    const float* av = a + (n - N) * N;
+                    for (int c = 0; c < N; ++c) v = fmaf(W[k * N + c], av[c], v);
+                }
+                dst[e] = v;
+            }
+        };
+        fill(w.Wi, SW1, Wi, ai, IN, HID);
+        fill(w.Wio, SW2, Wio, aio, HID, OUT);
+        fill(w.We, SW1, We, ae, OUT, HID);
+        fill(w.Weo, SW2, Weo, aeo, HID, OUT);
+        for (int e = threadIdx.x; e < 2 * OUT * SW2; e += blockDim.x) {
+            const int k = e / SW2, n = e % SW2;
+            w.WoT[e] = (n < FIN) ? Wo[n * 2 * OUT + k] : 0.f;
+        }
+        for (int e = threadIdx.x; e < FIN; e += blockDim.x) w.bo[e] = bo[e];
+    }
+    __syncthreads();
+    float* A = bufs + warp * FUSED_SCRATCH;               // [32][RA]  16-wide rows: Wh2 / Xg / Wh4 / Yg
+    float* Bf = A + 32 * RA;                              // [32][RS]  72-wide rows: x / Wh1 / hp / Wh3 / hp / cat
+    float* X1s = Bf + 32 * RS;                            // [32][16]
+    float2* st = reinterpret_cast<float2*>(X1s + 32 * 16);
+    int* lead_slot = reinterpret_cast<int*>(st + 32);
+    const int g = lane >> 2, t = lane & 3;
+
+    // fragment stores: 72(+2)-wide result -> Bf rows + scores; 16(+2)-wide result -> A rows + scores
+    auto store_wide = [&](int mt, int nt, const float (&c)[4]) {
+        const int r = mt * 16 + g;
+        if (nt < HID / 8) {
+            *reinterpret_cast<float2*>(Bf + r * RS + nt * 8 + 2 * t) = make_float2(c[0], c[1]);
+            *reinterpret_cast<float2*>(Bf + (r + 8) * RS + nt * 8 + 2 * t) = make_float2(c[2], c[3]);
+        } else if (t == 0) {
+            st[r] = make_float2(c[0], c[1]);
+            st[r + 8] = make_float2(c[2], c[3]);
+        }
+    };
+    auto store_narrow = [&](int mt, int nt, const float (&c)[4]) {
+        const int r = mt * 16 + g;
+        if (nt < OUT / 8) {
+            *reinterpret_cast<float2*>(A + r * RA + nt * 8 + 2 * t) = make_float2(c[0], c[1]);
+            *reinterpret_cast<float2*>(A + (r + 8) * RA + nt * 8 + 2 * t) = make_float2(c[2], c[3]);
+        } else if (t == 0) {
+            st[r] = make_float2(c[0], c[1]);
+            st[r + 8] = make_float2(c[2], c[3]);
+        }
+    };
+
+    const int n_warps_total = gridDim.x * FUSED_WARPS;
+    for (int chunk = blockIdx.x * FUSED_WARPS + warp; chunk < n_chunks; chunk += n_warps_total) {
+        const int p0 = scene_start[chunk_scene[chunk]];
+        const int np = scene_start[chunk_scene[chunk + 1]] - p0;
+        const bool live = lane < np;
+        const int p = p0 + lane;
+        int b = 0, e = 0, my_lead = lane;
+        float inv_g = 1.f;
+        {
+            float4 xv[IN / 4];
+#pragma unroll
+            for (int c = 0; c < IN / 4; ++c) xv[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live) {
+                b = ped_start[p] - p0; e = ped_end[p] - p0; my_lead = leader[p] - p0;
+                inv_g = __frcp_rn((float)gsize[p]);
+                const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)p * IN);
+#pragma unroll
+                for (int c = 0; c < IN / 4; ++c) xv[c] = xr[c];
+            }
+#pragma unroll
+            for (int c = 0; c < IN / 4; ++c) reinterpret_cast<float4*>(Bf + lane * RS)[c] = xv[c];
+        }
+        lead_slot[lane] = live ? my_lead : -1;
+        const bool is_lead = live && (my_lead == lane);
+        // neighbour sets as lane masks: the members of my group; the leaders of my scene
+        const uint32_t group_mask = __match_any_sync(0xffffffffu, live ? my_lead : 32 + lane);
+        const uint32_t scene_mask = (e >= 32 ? 0xffffffffu : ((1u << e) - 1u)) & ~((1u << b) - 1u);
+        const uint32_t leader_mask = __ballot_sync(0xffffffffu, is_lead) & scene_mask;
+        __syncwarp();
+        // ---- intra GAT, layer 1: Wh1 = x Wi (+ scores), in place over the x rows ----
+        warp_gemm_3xtf32<IN, HID / 8 + 1, RS, SW1>(Bf, w.Wi, lane, store_wide);
+        float x1[OUT];
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) x1[o] = 0.f;
+        {
+            float hp[HID];
+#pragma unroll
+            for (int f = 0; f < HID; ++f) hp[f] = 0.f;
+            if (live) {
+                attend_mask<HID, RS>(Bf, st, group_mask, st[lane].x, alpha, hp);
+#pragma unroll
+                for (int f = 0; f < HID; ++f) hp[f] = felu(hp[f]);
+            }
+            __syncwarp();                                           // every lane is done reading Wh1 rows
+            store_row<HID>(Bf + lane * RS, hp);
+        }
+        __syncwarp();
+        // ---- intra GAT, out_att: Wh2 = x1a Wio (+ scores) -> A rows ----
+        warp_gemm_3xtf32<HID, OUT / 8 + 1, RS, SW2>(Bf, w.Wio, lane, store_narrow);
+        if (live) {
+            attend_mask<OUT, RA>(A, st, group_mask, st[lane].x, alpha, x1);
+            elu_logsoftmax<OUT>(x1);
+            store_row<OUT>(X1s + lane * 16, x1);
+        }
+        __syncwarp();
+        // ---- GPool (leaders): Xg -> A rows ----
+        {
+            float xg[OUT];
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) xg[o] = 0.f;
+            if (is_lead) {
+                for (uint32_t mm = group_mask; mm; mm &= mm - 1) {
+                    const int q = __ffs(mm) - 1;
+#pragma unroll
+                    for (int o = 0; o < OUT; ++o) xg[o] = fmaf(inv_g, X1s[q * 16 + o], xg[o]);
+                }
+            }
+            store_row<OUT>(A + lane * RA, xg);
+        }
+        __syncwarp();
+        // ---- inter GAT, layer 1 over the leader slots: Wh3 = Xg We (+ scores) -> Bf rows ----
+        warp_gemm_3xtf32<OUT, HID / 8 + 1, RA, SW1>(A, w.We, lane, store_wide);
+        {
+            float hp[HID];
+#pragma unroll
+            for (int f = 0; f < HID; ++f) hp[f] = 0.f;
+            if (is_lead) {
+                attend_mask<HID, RS>(Bf, st, leader_mask, st[lane].x, alpha, hp);
+#pragma unroll
+                for (int f = 0; f < HID; ++f) hp[f] = felu(hp[f]);
+            }
+            __syncwarp();
+            store_row<HID>(Bf + lane * RS, hp);
+        }
+        __syncwarp();
+        // ---- inter GAT, out_att: Wh4 = hp Weo (+ scores) -> A rows ----
+        warp_gemm_3xtf32<HID, OUT / 8 + 1, RS, SW2>(Bf, w.Weo, lane, store_narrow);
+        {
+            float yg[OUT];
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) yg[o] = 0.f;
+            if (is_lead) {
+                attend_mask<OUT, RA>(A, st, leader_mask, st[lane].x, alpha, yg);
+                elu_logsoftmax<OUT>(yg);
+            }
+            __syncwarp();                                           // every leader is done reading Wh4 rows
+            store_row<OUT>(A + lane * RA, yg);                      // Yg at the leader's slot
+        }
+        __syncwarp();
+        // ---- unpool: cat = [x1 | Yg[leader] / |group|] -> Bf rows (32 wide), out = cat Wo^T + bo ----
+        {
+            float cat2[OUT];
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) cat2[o] = inv_g * A[my_lead * RA + o];
+            store_row<OUT>(Bf + lane * RS, x1);
+            store_row<OUT>(Bf + lane * RS + OUT, cat2);
+        }
+        __syncwarp();
+        warp_gemm_3xtf32<2 * OUT, FIN / 8, RS, SW2>(Bf, w.WoT, lane, [&](int mt, int nt, const float (&c)[4]) {
+            const int r = mt * 16 + g, col = nt * 8 + 2 * t;
+            const float b0 = w.bo[col], b1 = w.bo[col + 1];
+            if (r < np) *reinterpret_cast<float2*>(out + (int64_t)(p0 + r) * FIN + col) = make_float2(c[0] + b0, c[1] + b1);
+            if (r + 8 < np)
+                *reinterpret_cast<float2*>(out + (int64_t)(p0 + r + 8) * FIN + col) = make_float2(c[2] + b0, c[3] + b1);
+        });
+    }
+}
+
 static int gat_fused_forward(const float* x, const int32_t* leader, const int32_t* gsize, const int32_t* ps,
                              const int32_t* pe, const int32_t* scene_start, const int32_t* chunk_scene, int n_chunks,
                              const float* Wi, const float* ai, const float* Wio, const float* aio, const float* We,
                              const float* ae, const float* Weo, const float* aeo, const float* Wo, const float* bo,
                              float alpha, float* out, cudaStream_t st) {
+    const int grid = std::min((n_chunks + FUSED_WARPS - 1) / FUSED_WARPS, 148);
+    const char* mode = getenv("SGX_GAT_MMA");
+    if (!(mode && mode[0] == '0')) {       // default: linear maps on the tensor cores (SGX_GAT_MMA=0: CUDA-core GEMV)
+        auto kern_m = gat_fused_mma_kernel<40, 24>;
+        const int smem_m = (int)(sizeof(FusedWm) + FUSED_WARPS * FUSED_SCRATCH * sizeof(float));
+        SGX_CUDA(cudaFuncSetAttribute(kern_m, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_m));
+        kern_m<<<grid, FUSED_WARPS * 32, smem_m, st>>>(x, leader, gsize, ps, pe, scene_start, chunk_scene, n_chunks, Wi, ai,
+                                                       Wio, aio, We, ae, Weo, aeo, Wo, bo, alpha, out);
+        SGX_LAUNCH_CHECK();
+        return SGX_OK;
+    }
     auto kern = gat_fused_fwd_kernel<40, 24>;
     const int smem = (int)(sizeof(FusedW) + FUSED_WARPS * FUSED_SCRATCH * sizeof(float));
     SGX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int grid = std::min((n_chunks + FUSED_WARPS - 1) / FUSED_WARPS, 148);
     kern<<<grid, FUSED_WARPS * 32, smem, st>>>(x, leader, gsize, ps, pe, scene_start, chunk_scene, n_chunks, Wi, ai, Wio,
                                                aio, We, ae, Weo, aeo, Wo, bo, alpha, out);
     SGX_LAUNCH_CHECK();
