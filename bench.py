@@ -428,7 +428,7 @@ def main():
                  'achieved': (260 * peds + 16 * n_scenes + 29920) / (gat_ms * 1e-3) / 1e9,
                  'peak': peaks.get('hbm_gbs', 6650.0), 'unit': 'GB/s',
                  'frac': (260 * peds + 16 * n_scenes + 29920) / (gat_ms * 1e-3) / 1e9 / peaks.get('hbm_gbs', 6650.0),
-                 'note': 'HBM-bound by decree (SURVEY 8d); the kernel is CUDA-core bound (6 kFMA/ped), see DESIGN.md'},
+                 'note': 'HBM-bound by decree (SURVEY 8d); the kernel is issue / tensor-pipe bound (3xTF32 mma.sync linear maps + per-ped attention, ~6 kFMA/ped), see DESIGN.md 4.3'},
                 {'op': 'Encoder LSTM 8 steps (lstm_tc_kernel)', 'ms': enc_ms, 'ped_steps_per_s': 8 * peds / (enc_ms * 1e-3)},
                 {'op': 'Decoder LSTM 12 steps + hidden2pos + noise fold-in (lstm_tc_kernel)', 'ms': dec_ms,
                  'ped_steps_per_s': 12 * peds / (dec_ms * 1e-3)},

@@ -774,14 +774,24 @@ __device__ __forceinline__ void warp_gemm_3xtf32(const float* __restrict__ A, co
             split_tf32(ar[4], ah[2], al[2]);
             split_tf32(ar[8 * SA + 4], ah[3], al[3]);
             const float* br = B + (ks * 8 + t) * SB + g;
+            // n-tiles in groups: the three products of one n-tile accumulate into the same fragment, so issuing them
+            // back to back serialises on the MMA latency; interleaving NG n-tiles puts NG independent MMAs between.
+            constexpr int NG = (NT % 5 == 0) ? 5 : 3;
+            static_assert(NT % NG == 0, "n-tile count must be a multiple of the interleave group");
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt) {
-                uint32_t bh0, bl0, bh1, bl1;
-                split_tf32(br[nt * 8], bh0, bl0);
-                split_tf32(br[4 * SB + nt * 8], bh1, bl1);
-                mma_tf32(acc[nt], al, bh0, bh1);
-                mma_tf32(acc[nt], ah, bl0, bl1);
-                mma_tf32(acc[nt], ah, bh0, bh1);
+            for (int n0 = 0; n0 < NT; n0 += NG) {
+                uint32_t bh0[NG], bl0[NG], bh1[NG], bl1[NG];
+#pragma unroll
+                for (int j = 0; j < NG; ++j) {
+                    split_tf32(br[(n0 + j) * 8], bh0[j], bl0[j]);
+                    split_tf32(br[4 * SB + (n0 + j) * 8], bh1[j], bl1[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < NG; ++j) mma_tf32(acc[n0 + j], al, bh0[j], bh1[j]);
+#pragma unroll
+                for (int j = 0; j < NG; ++j) mma_tf32(acc[n0 + j], ah, bl0[j], bl1[j]);
+#pragma unroll
+                for (int j = 0; j < NG; ++j) mma_tf32(acc[n0 + j], ah, bh0[j], bh1[j]);
             }
         }
         __syncwarp();
