@@ -173,11 +173,12 @@ def test_evaluate_over_device_loader_matches_reference_evaluation(golden):
     gen.load_state_dict(_zara1_weights(), strict=True)
     gen = gen.cuda().train()
     ds = _dataset('a')
-    for hoist in (False, True):
+    for hoist, fold in ((False, False), (True, False), (False, True)):     # sample loop, hoisted context, folded samples
         loader = D.DeviceLoader(ds, batch_size=16, shuffle=False, device='cuda:0')
-        ade, fde = E.evaluate(dict(pred_len=12), loader, gen, 4, noise_for_batch=_eval_noise, hoist_context=hoist)
-        assert abs(float(ade) - float(golden['eval.ade'])) < 1e-4, (hoist, float(ade))
-        assert abs(float(fde) - float(golden['eval.fde'])) < 1e-4, (hoist, float(fde))
+        ade, fde = E.evaluate(dict(pred_len=12), loader, gen, 4, noise_for_batch=_eval_noise, hoist_context=hoist,
+                              fold_samples=fold)
+        assert abs(float(ade) - float(golden['eval.ade'])) < 1e-4, (hoist, fold, float(ade))
+        assert abs(float(fde) - float(golden['eval.fde'])) < 1e-4, (hoist, fold, float(fde))
 
 
 def test_get_generator_builds_from_checkpoint_args():

@@ -439,14 +439,16 @@ def test_evaluate_batch_matches_reference_metrics(sgx):
     g = load_golden('generator_gat_zara1')
     gen = _generator(sgx, g, 'gat')
     t = lambda k: g[k].to(DEV)
-    ade, fde = evaluate_batch(gen, t('obs_traj'), t('obs_traj_rel'), t('seq_start_end'), t('obs_traj_g'), t('pred_traj_gt'),
-                              num_samples=g['noise'].shape[0], noise=t('noise'))
     n = g['obs_traj'].shape[1]
-    assert abs(float(ade) / (n * 12) - float(g['ade'])) < 1e-4
-    assert abs(float(fde) / n - float(g['fde'])) < 1e-4
+    for fold in (True, False):          # samples folded into one forward (the small-batch default) / the sample loop
+        ade, fde = evaluate_batch(gen, t('obs_traj'), t('obs_traj_rel'), t('seq_start_end'), t('obs_traj_g'),
+                                  t('pred_traj_gt'), num_samples=g['noise'].shape[0], noise=t('noise'), fold_samples=fold)
+        assert abs(float(ade) / (n * 12) - float(g['ade'])) < 1e-4, fold
+        assert abs(float(fde) / n - float(g['fde'])) < 1e-4, fold
     ade_h, fde_h = evaluate_batch(gen, t('obs_traj'), t('obs_traj_rel'), t('seq_start_end'), t('obs_traj_g'),
                                   t('pred_traj_gt'), num_samples=g['noise'].shape[0], noise=t('noise'), hoist_context=True)
-    assert float(ade_h) == float(ade) and float(fde_h) == float(fde)      # hoisting is bit-identical (row f2)
+    # hoisting gives bit-identical predictions (row f2); the scene sums are float atomics, so compare to rounding
+    assert abs(float(ade_h) - float(ade)) <= 2e-6 * abs(float(ade)) and abs(float(fde_h) - float(fde)) <= 2e-6 * abs(float(fde))
 
 
 # ------------------------------------------------------------------ tensor-core LSTM (3-way bf16 splits, fp32-level accuracy)

@@ -107,8 +107,57 @@ def cfg4():
                               'pool_as_written_TFLOPs_over_whole_forward': flops / ms / 1e9}))
 
 
+def cfg2_small():
+    """cfg 2 at the reference's own batch size: S = 64 zara1-shaped scenes (~240 peds), best-of-20 evaluation of one
+    minibatch (scripts/evaluate_model.py:72-99).  Launch-latency regime: (a) the K forwards one after the other, as the
+    reference issues them, (b) the K samples folded into ONE forward over 20 copies of the batch, (c) (b) replayed from
+    a CUDA graph."""
+    from group_gan_gcn_gat_b200.evaluate import evaluate_batch
+    from group_gan_gcn_gat_b200.parallel import _folded_samples
+    K = 20
+    data = bench.synth_batch(64, 1238)
+    gen = MD.TrajectoryGenerator(obs_len=8, pred_len=12, embedding_dim=16, encoder_h_dim=32, decoder_h_dim=32, mlp_dim=64,
+                                 noise_dim=(8,), noise_mix_type='global', pooling_type='pool_net',
+                                 pool_every_timestep=False, bottleneck_dim=8, batch_norm=False, n_heads=1, alpha=0.2)
+    gen.load_state_dict(bench.load_weights(), strict=True)
+    gen = gen.to(dev).train()
+    d = {k: data[k].to(dev) for k in ('obs_traj', 'obs_traj_rel', 'obs_traj_g', 'seq_start_end', 'pred_traj_gt')}
+    n = int(d['obs_traj'].shape[1])
+    with torch.no_grad():
+        loop_ms = timed(lambda: evaluate_batch(gen, d['obs_traj'], d['obs_traj_rel'], d['seq_start_end'], d['obs_traj_g'],
+                                               d['pred_traj_gt'], K))
+        fold_ms = timed(lambda: _folded_samples(gen, d['obs_traj'], d['obs_traj_rel'], d['obs_traj_g'],
+                                                d['seq_start_end'], K))
+        # CUDA graph of the folded forward (static inputs; noise refreshed into a static buffer before each replay)
+        s64 = d['seq_start_end'].shape[0]
+        offs = (torch.arange(K, device=dev) * n).repeat_interleave(s64)
+        sse_k = d['seq_start_end'].repeat(K, 1) + offs.unsqueeze(1)
+        big = [d[k].repeat(1, K, 1).contiguous() for k in ('obs_traj', 'obs_traj_rel', 'obs_traj_g')]
+        z = torch.randn(K * s64, 8, device=dev)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                gen(big[0], big[1], sse_k, big[2], user_noise=z)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = gen(big[0], big[1], sse_k, big[2], user_noise=z)
+
+        def replay():
+            z.normal_()
+            graph.replay()
+        graph_ms = timed(replay)
+    print(json.dumps({'config': 'cfg2 small batch: 64 zara1-shaped scenes, best-of-20', 'peds': n, 'k_samples': K,
+                      'loop_of_20_forwards_ms': loop_ms, 'folded_one_forward_ms': fold_ms, 'folded_cuda_graph_ms': graph_ms,
+                      'traj_per_s_loop': n * K / loop_ms * 1e3, 'traj_per_s_folded': n * K / fold_ms * 1e3,
+                      'traj_per_s_graph': n * K / graph_ms * 1e3, 'graph_output_finite': bool(torch.isfinite(out).all())}))
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['cfg3', 'cfg4']
+    which = sys.argv[1:] or ['cfg2_small', 'cfg3', 'cfg4']
+    if 'cfg2_small' in which:
+        cfg2_small()
     if 'cfg3' in which:
         cfg3()
     if 'cfg4' in which:
