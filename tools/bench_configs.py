@@ -113,7 +113,6 @@ def cfg2_small():
     reference issues them, (b) the K samples folded into ONE forward over 20 copies of the batch, (c) (b) replayed from
     a CUDA graph."""
     from group_gan_gcn_gat_b200.evaluate import evaluate_batch
-    from group_gan_gcn_gat_b200.parallel import _folded_samples
     K = 20
     data = bench.synth_batch(64, 1238)
     gen = MD.TrajectoryGenerator(obs_len=8, pred_len=12, embedding_dim=16, encoder_h_dim=32, decoder_h_dim=32, mlp_dim=64,
@@ -125,9 +124,9 @@ def cfg2_small():
     n = int(d['obs_traj'].shape[1])
     with torch.no_grad():
         loop_ms = timed(lambda: evaluate_batch(gen, d['obs_traj'], d['obs_traj_rel'], d['seq_start_end'], d['obs_traj_g'],
-                                               d['pred_traj_gt'], K))
-        fold_ms = timed(lambda: _folded_samples(gen, d['obs_traj'], d['obs_traj_rel'], d['obs_traj_g'],
-                                                d['seq_start_end'], K))
+                                               d['pred_traj_gt'], K, fold_samples=False))
+        fold_ms = timed(lambda: evaluate_batch(gen, d['obs_traj'], d['obs_traj_rel'], d['seq_start_end'], d['obs_traj_g'],
+                                               d['pred_traj_gt'], K, fold_samples=True))
         # CUDA graph of the folded forward (static inputs; noise refreshed into a static buffer before each replay)
         s64 = d['seq_start_end'].shape[0]
         offs = (torch.arange(K, device=dev) * n).repeat_interleave(s64)
