@@ -89,8 +89,9 @@ __global__ void lstm_tc_prep_kernel(const float* __restrict__ We, const float* _
 // is 5 ex2 + 2 rcp = 7.  The gate pre-activations arrive pre-scaled (see lstm_tc_prep_kernel), so every exponential is a
 // clamp and one ex2.approx.ftz: __expf / __fdividef would add a range check and two multiplies around every MUFU.
 // Clamps: e <= 2^40 (sigmoid floor 9e-13), E <= 2^30 (tanh = 1 - 2e-9, below fp32 resolution), so the triple product
-// stays finite for |c| < 2^17.  (Moving one of the five exponentials to an FMA-pipe polynomial was tried: no gain, the
-// issue slots it costs are as scarce as the XU cycles it frees.)
+// stays finite for |c| < 2^17.  (Tried, measured, dropped: one of the five exponentials as an FMA-pipe polynomial -- no
+// gain, the issue slots it costs are as scarce as the XU cycles it frees; the bf16 roundings of the operand splits as
+// integer arithmetic instead of cvt.rn.bf16x2 -- 6 % slower.)
 constexpr float E_CLAMP = 40.f, T_CLAMP = 30.f;
 __device__ __forceinline__ float ex2_clamped(float v, float hi) {
     float r;
