@@ -14,7 +14,10 @@
 // Sums over identical rows are performed term by term (k additions of a*v) so the arithmetic stays
 // as close to the dense matmul as a different summation order allows.  Backward reuses the same three
 // levels in reverse; parameter gradients are tall-skinny GEMMs over per-group / per-scene rows.
+#include <stdlib.h>
+
 #include "sgx_common.cuh"
+#include "sgx_warp_mma.cuh"
 
 namespace sgx {
 
@@ -545,11 +548,235 @@ gcn_fused_fwd_kernel(const float* __restrict__ x, const int32_t* __restrict__ le
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// The same single-launch forward with the five linear maps as warp-level tensor-core GEMMs over the chunk's 32 slots
+// (sgx_warp_mma.cuh, 3xTF32 = fp32-level accuracy).  In the GEMV form only the leader lanes (~45 %) and the first lane
+// of every scene (~27 %) worked during the two GCNs; as a 32-row GEMM the slots that are not leaders / scene heads just
+// carry rows nobody reads.  Row-wise steps (group mean, ReLU, the k-fold repeat sums that reproduce the reference's
+// summation, the scene mean) stay lane-per-slot and use lane masks for their neighbour sets.
+// ------------------------------------------------------------------------------------------------
+
+// row[f] <- sum of `times` copies of scale * relu(row[f]) (the reference sums the identical rows of a group / scene one
+// by one), F floats.  ONE loop over `times` with the whole row in registers: a loop per element made 72 divergent
+// loops per row (branch stalls + 87 M instructions per launch).
+template <int F>
+__device__ __forceinline__ void relu_scale_repeat_row(float* __restrict__ row, float scale, int times) {
+    float term[F], acc[F];
+#pragma unroll
+    for (int c = 0; c < F / 4; ++c) {
+        const float4 v = reinterpret_cast<const float4*>(row)[c];
+        term[4 * c] = scale * fmaxf(v.x, 0.f); term[4 * c + 1] = scale * fmaxf(v.y, 0.f);
+        term[4 * c + 2] = scale * fmaxf(v.z, 0.f); term[4 * c + 3] = scale * fmaxf(v.w, 0.f);
+    }
+#pragma unroll
+    for (int f = 0; f < F; ++f) acc[f] = 0.f;
+    for (int t = 0; t < times; ++t) {
+#pragma unroll
+        for (int f = 0; f < F; ++f) acc[f] += term[f];
+    }
+#pragma unroll
+    for (int c = 0; c < F / 4; ++c)
+        reinterpret_cast<float4*>(row)[c] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+}
+
+constexpr int GM_WARPS = 10;
+constexpr int GM_RS = 76;                                     // 72-wide row buffer (group mean of x, hidden rows, cat)
+constexpr int GM_RX = 44;                                     // x rows
+constexpr int GM_RN = 20;                                     // 16-wide rows
+constexpr int GM_SCRATCH = 32 * GM_RS + 32 * GM_RN + 32 * 16 * 3;     // the x rows alias X1s/Xgs/Ys (dead before those are written)
+static_assert(32 * GM_RX <= 32 * 16 * 3, "x rows must fit the aliased region");
+constexpr int GM_SW_WIDE = 72;                                // W0 / V0 [K][72]: 72 % 32 = 8 -> conflict-free B fragments
+constexpr int GM_SW_NARROW = 24;                              // W1 / V1 [72][16] padded to 24
+template <int FIN> struct GmWo { static constexpr int STRIDE = (FIN % 32 == 0) ? FIN + 8 : FIN; };
+
+template <int IN, int HID, int OUT, int FIN>
+__global__ void __launch_bounds__(GM_WARPS * 32)
+gcn_fused_mma_kernel(const float* __restrict__ x, const int32_t* __restrict__ leader, const int32_t* __restrict__ gsize,
+                     const int32_t* __restrict__ ped_start, const int32_t* __restrict__ ped_end,
+                     const int32_t* __restrict__ scene_start, const int32_t* __restrict__ chunk_scene, int n_chunks,
+                     const float* __restrict__ W0, const float* __restrict__ W1, const float* __restrict__ V0,
+                     const float* __restrict__ V1, const float* __restrict__ Wo, const float* __restrict__ bo,
+                     float* __restrict__ out) {
+    static_assert(HID == 72 && OUT == 16 && IN % 8 == 0 && FIN % 8 == 0, "built for hidden 72, out 16");
+    constexpr int SWO = GmWo<FIN>::STRIDE;
+    extern __shared__ __align__(16) uint8_t raw[];
+    float* sW0 = reinterpret_cast<float*>(raw);               // [IN][72]
+    float* sW1 = sW0 + IN * GM_SW_WIDE;                       // [72][24]
+    float* sV0 = sW1 + HID * GM_SW_NARROW;                    // [16][72]
+    float* sV1 = sV0 + OUT * GM_SW_WIDE;                      // [72][24]
+    float* sWoT = sV1 + HID * GM_SW_NARROW;                   // [32][SWO] = Wo^T
+    float* sbo = sWoT + 2 * OUT * SWO;                        // [FIN]
+    float* bufs = sbo + FIN;
+    for (int e = threadIdx.x; e < IN * HID; e += blockDim.x) sW0[e] = W0[e];
+    for (int e = threadIdx.x; e < OUT * HID; e += blockDim.x) sV0[e] = V0[e];
+    for (int e = threadIdx.x; e < HID * GM_SW_NARROW; e += blockDim.x) {
+        const int k = e / GM_SW_NARROW, n = e % GM_SW_NARROW;
+        sW1[e] = n < OUT ? W1[k * OUT + n] : 0.f;
+        sV1[e] = n < OUT ? V1[k * OUT + n] : 0.f;
+    }
+    for (int e = threadIdx.x; e < 2 * OUT * SWO; e += blockDim.x) {
+        const int k = e / SWO, n = e % SWO;
+        sWoT[e] = n < FIN ? Wo[n * 2 * OUT + k] : 0.f;
+    }
+    for (int e = threadIdx.x; e < FIN; e += blockDim.x) sbo[e] = bo[e];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    float* RB = bufs + warp * GM_SCRATCH;                     // [32][GM_RS]
+    float* SB = RB + 32 * GM_RS;                              // [32][GM_RN]
+    float* X1s = SB + 32 * GM_RN;                             // [32][16] ReLU'd intra output of the group (at its leader)
+    float* XB = X1s;                                          // [32][GM_RX] x rows, only until the group means are taken
+    float* Xgs = X1s + 32 * 16;                               // [32][16] pooled group state
+    float* Ys = Xgs + 32 * 16;                                // [32][16] inter output of the scene (at its first slot)
+    auto to_rb = [&](int mt, int nt, const float (&c)[4]) {
+        const int r = mt * 16 + g;
+        *reinterpret_cast<float2*>(RB + r * GM_RS + nt * 8 + 2 * t) = make_float2(c[0], c[1]);
+        *reinterpret_cast<float2*>(RB + (r + 8) * GM_RS + nt * 8 + 2 * t) = make_float2(c[2], c[3]);
+    };
+    auto to_sb = [&](int mt, int nt, const float (&c)[4]) {
+        const int r = mt * 16 + g;
+        *reinterpret_cast<float2*>(SB + r * GM_RN + nt * 8 + 2 * t) = make_float2(c[0], c[1]);
+        *reinterpret_cast<float2*>(SB + (r + 8) * GM_RN + nt * 8 + 2 * t) = make_float2(c[2], c[3]);
+    };
+    const int n_warps_total = gridDim.x * GM_WARPS;
+    for (int chunk = blockIdx.x * GM_WARPS + warp; chunk < n_chunks; chunk += n_warps_total) {
+        const int p0 = scene_start[chunk_scene[chunk]];
+        const int np = scene_start[chunk_scene[chunk + 1]] - p0;
+        const bool live = lane < np;
+        const int p = p0 + lane;
+        int b = 0, e = 0, my_lead = lane, k = 1;
+        {
+            float4 xv[IN / 4];
+#pragma unroll
+            for (int c = 0; c < IN / 4; ++c) xv[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live) {
+                b = ped_start[p] - p0; e = ped_end[p] - p0; my_lead = leader[p] - p0; k = gsize[p];
+                const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)p * IN);
+#pragma unroll
+                for (int c = 0; c < IN / 4; ++c) xv[c] = xr[c];
+            }
+#pragma unroll
+            for (int c = 0; c < IN / 4; ++c) reinterpret_cast<float4*>(XB + lane * GM_RX)[c] = xv[c];
+        }
+        const bool is_lead = live && my_lead == lane;
+        const bool is_head = live && lane == b;
+        const float a = __frcp_rn((float)k);
+        const uint32_t group_mask = __match_any_sync(0xffffffffu, live ? my_lead : 32 + lane);
+        const uint32_t scene_mask = (e >= 32 ? 0xffffffffu : ((1u << e) - 1u)) & ~((1u << b) - 1u);
+        const uint32_t leader_mask = __ballot_sync(0xffffffffu, is_lead) & scene_mask;
+        __syncwarp();
+        // ---- group mean of x at the leader slots -> RB rows ----
+        {
+            float m1[IN];
+#pragma unroll
+            for (int c = 0; c < IN; ++c) m1[c] = 0.f;
+            if (is_lead) {
+                for (uint32_t mm = group_mask; mm; mm &= mm - 1) {
+                    const float4* row = reinterpret_cast<const float4*>(XB + (__ffs(mm) - 1) * GM_RX);
+#pragma unroll
+                    for (int c = 0; c < IN / 4; ++c) {
+                        const float4 v = row[c];
+                        m1[4 * c] = fmaf(a, v.x, m1[4 * c]); m1[4 * c + 1] = fmaf(a, v.y, m1[4 * c + 1]);
+                        m1[4 * c + 2] = fmaf(a, v.z, m1[4 * c + 2]); m1[4 * c + 3] = fmaf(a, v.w, m1[4 * c + 3]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < IN / 4; ++c)
+                reinterpret_cast<float4*>(RB + lane * GM_RS)[c] = make_float4(m1[4 * c], m1[4 * c + 1], m1[4 * c + 2], m1[4 * c + 3]);
+        }
+        __syncwarp();
+        // ---- intra GCN: H1 = M1 W0 (in place), M2 = k-fold sum of relu(H1)/k, X1 = relu(M2 W1) ----
+        warp_gemm_3xtf32<IN, HID / 8, GM_RS, GM_SW_WIDE>(RB, sW0, lane, to_rb);
+        {
+            relu_scale_repeat_row<HID>(RB + lane * GM_RS, a, k);
+        }
+        __syncwarp();
+        warp_gemm_3xtf32<HID, OUT / 8, GM_RS, GM_SW_NARROW>(RB, sW1, lane, to_sb);
+        {
+            const float4* row = reinterpret_cast<const float4*>(SB + lane * GM_RN);
+#pragma unroll
+            for (int c = 0; c < OUT / 4; ++c) {
+                float4 v = row[c];
+                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                reinterpret_cast<float4*>(X1s + lane * 16)[c] = v;
+                reinterpret_cast<float4*>(Xgs + lane * 16)[c] = make_float4(repeat_sum(a * v.x, k), repeat_sum(a * v.y, k),
+                                                                            repeat_sum(a * v.z, k), repeat_sum(a * v.w, k));
+            }
+        }
+        __syncwarp();
+        // ---- inter GCN at the scene heads: N1 = mean of the scene's group states ----
+        const int G = __popc(leader_mask);
+        const float cg = __frcp_rn((float)(G > 0 ? G : 1));
+        {
+            float n1[OUT];
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) n1[o] = 0.f;
+            if (is_head) {
+                for (uint32_t mm = leader_mask; mm; mm &= mm - 1) {
+                    const int q = __ffs(mm) - 1;
+#pragma unroll
+                    for (int o = 0; o < OUT; ++o) n1[o] = fmaf(cg, Xgs[q * 16 + o], n1[o]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < OUT / 4; ++c)
+                reinterpret_cast<float4*>(SB + lane * GM_RN)[c] = make_float4(n1[4 * c], n1[4 * c + 1], n1[4 * c + 2], n1[4 * c + 3]);
+        }
+        __syncwarp();
+        warp_gemm_3xtf32<OUT, HID / 8, GM_RN, GM_SW_WIDE>(SB, sV0, lane, to_rb);
+        {
+            relu_scale_repeat_row<HID>(RB + lane * GM_RS, cg, is_head ? G : 1);   // rows of the other slots are never read
+        }
+        __syncwarp();
+        warp_gemm_3xtf32<HID, OUT / 8, GM_RS, GM_SW_NARROW>(RB, sV1, lane, to_sb);
+        {
+            const float4* row = reinterpret_cast<const float4*>(SB + lane * GM_RN);
+#pragma unroll
+            for (int c = 0; c < OUT / 4; ++c) {
+                const float4 v = row[c];
+                reinterpret_cast<float4*>(Ys + lane * 16)[c] =
+                    make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+            }
+        }
+        __syncwarp();
+        // ---- cat = [X1 of my group ; Y of my scene / |group|] -> RB rows, out = cat Wo^T + bo ----
+#pragma unroll
+        for (int c = 0; c < OUT / 4; ++c) {
+            const float4 u = reinterpret_cast<const float4*>(X1s + my_lead * 16)[c];
+            const float4 v = reinterpret_cast<const float4*>(Ys + b * 16)[c];
+            reinterpret_cast<float4*>(RB + lane * GM_RS)[c] = u;
+            reinterpret_cast<float4*>(RB + lane * GM_RS + OUT)[c] = make_float4(a * v.x, a * v.y, a * v.z, a * v.w);
+        }
+        __syncwarp();
+        warp_gemm_3xtf32<2 * OUT, FIN / 8, GM_RS, SWO>(RB, sWoT, lane, [&](int mt, int nt, const float (&c)[4]) {
+            const int r = mt * 16 + g, col = nt * 8 + 2 * t;
+            const float b0 = sbo[col], b1 = sbo[col + 1];
+            if (r < np) *reinterpret_cast<float2*>(out + (int64_t)(p0 + r) * FIN + col) = make_float2(c[0] + b0, c[1] + b1);
+            if (r + 8 < np)
+                *reinterpret_cast<float2*>(out + (int64_t)(p0 + r + 8) * FIN + col) = make_float2(c[2] + b0, c[3] + b1);
+        });
+    }
+}
+
 template <int IN, int FIN>
 static int gcn_fused_launch(const float* x, const int32_t* leader, const int32_t* gsize, const int32_t* ps,
                             const int32_t* pe, const int32_t* scene_start, const int32_t* chunk_scene, int n_chunks,
                             const float* W0, const float* W1, const float* V0, const float* V1, const float* Wo,
                             const float* bo, float* out, cudaStream_t st) {
+    const char* mode = getenv("SGX_GCN_MMA");
+    if (!(mode && mode[0] == '0')) {       // default: linear maps on the tensor cores (SGX_GCN_MMA=0: CUDA-core GEMV)
+        auto kern_m = gcn_fused_mma_kernel<IN, 72, 16, FIN>;
+        const int wf = IN * GM_SW_WIDE + 2 * 72 * GM_SW_NARROW + 16 * GM_SW_WIDE + 32 * GmWo<FIN>::STRIDE + FIN;
+        const int smem_m = (wf + GM_WARPS * GM_SCRATCH) * (int)sizeof(float);
+        SGX_CUDA(cudaFuncSetAttribute(kern_m, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_m));
+        const int grid_m = std::min((n_chunks + GM_WARPS - 1) / GM_WARPS, 148);
+        kern_m<<<grid_m, GM_WARPS * 32, smem_m, st>>>(x, leader, gsize, ps, pe, scene_start, chunk_scene, n_chunks, W0, W1,
+                                                      V0, V1, Wo, bo, out);
+        SGX_LAUNCH_CHECK();
+        return SGX_OK;
+    }
     auto kern = gcn_fused_fwd_kernel<IN, 72, 16, FIN>;
     const int wfloats = IN * 72 + 72 * 16 * 3 + FIN * 32 + ((FIN + 3) / 4) * 4;
     const int smem = (wfloats + GF_WARPS * GF_SCRATCH) * (int)sizeof(float);

@@ -1,0 +1,68 @@
+// Warp-level fp32-accurate GEMM on the tensor cores for the per-scene-chunk graph kernels (sgx_gat.cu, sgx_gcn.cu):
+// mma.sync m16n8k8 TF32 with every operand split hi + lo (hi = top 19 bits), hi*hi + lo*hi + hi*lo accumulated in fp32
+// (~7e-7 relative).  One warp multiplies its chunk's 32 rows; rows are independent, so rows of dead lanes may hold
+// anything.
+#pragma once
+#include <stdint.h>
+
+namespace sgx {
+
+__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(v) & 0xFFFFE000u;
+    lo = __float_as_uint(v - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// C [32 x 8 NT] = A [32 x K] . B [K x 8 NT] for one warp; A rows in shared memory (stride SA floats), B row-major
+// (stride SB).  store(mt, nt, acc) receives the m16n8 accumulator fragment: acc[0..1] = row mt*16 + lane/4, columns
+// nt*8 + 2 (lane%4) + {0,1}; acc[2..3] = the same columns of row + 8.  A __syncwarp precedes the stores of an m-tile,
+// so C may overwrite the A rows of that m-tile.
+template <int K, int NT, int SA, int SB, class Store>
+__device__ __forceinline__ void warp_gemm_3xtf32(const float* __restrict__ A, const float* __restrict__ B, int lane,
+                                                 Store&& store) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll 1
+    for (int mt = 0; mt < 2; ++mt) {
+        float acc[NT][4];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+#pragma unroll 1
+        for (int ks = 0; ks < K / 8; ++ks) {
+            const float* ar = A + (mt * 16 + g) * SA + ks * 8 + t;
+            uint32_t ah[4], al[4];
+            split_tf32(ar[0], ah[0], al[0]);
+            split_tf32(ar[8 * SA], ah[1], al[1]);
+            split_tf32(ar[4], ah[2], al[2]);
+            split_tf32(ar[8 * SA + 4], ah[3], al[3]);
+            const float* br = B + (ks * 8 + t) * SB + g;
+            // n-tiles in groups: the three products of one n-tile accumulate into the same fragment, so issuing them
+            // back to back serialises on the MMA latency; interleaving NG n-tiles puts NG independent MMAs between.
+            constexpr int NG = (NT % 5 == 0) ? 5 : (NT % 4 == 0) ? 4 : (NT % 3 == 0) ? 3 : (NT % 2 == 0) ? 2 : 1;
+#pragma unroll
+            for (int n0 = 0; n0 < NT; n0 += NG) {
+                uint32_t bh0[NG], bl0[NG], bh1[NG], bl1[NG];
+#pragma unroll
+                for (int j = 0; j < NG; ++j) {
+                    split_tf32(br[(n0 + j) * 8], bh0[j], bl0[j]);
+                    split_tf32(br[4 * SB + (n0 + j) * 8], bh1[j], bl1[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < NG; ++j) mma_tf32(acc[n0 + j], al, bh0[j], bh1[j]);
+#pragma unroll
+                for (int j = 0; j < NG; ++j) mma_tf32(acc[n0 + j], ah, bl0[j], bl1[j]);
+#pragma unroll
+                for (int j = 0; j < NG; ++j) mma_tf32(acc[n0 + j], ah, bh0[j], bh1[j]);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) store(mt, nt, acc[nt]);
+    }
+    __syncwarp();
+}
+
+}  // namespace sgx

@@ -209,10 +209,10 @@ class GCNModule(nn.Module):
 
     @staticmethod
     def _chunks(sched):
-        # The single-launch warp-per-chunk kernel (sgx_gcn_module_fused_fwd) measured SLOWER than the three-kernel path
-        # on B200 (0.45 vs 0.28 ms at 245 k peds: the group / scene MLPs run on ~45 % / ~27 % of the lanes at 8 warps per
-        # SM), so it is opt-in.
-        if os.environ.get('SGX_GCN_FUSED') == '1':
+        # Scenes of <= 32 peds (every ETH/UCY split but univ) take the single-launch warp-per-chunk kernel with the linear
+        # maps on the tensor cores (0.13 ms at 245 k peds against 0.22 ms for the three-kernel path, which stays the
+        # general path and what SGX_GCN_FUSED=0 selects).
+        if os.environ.get('SGX_GCN_FUSED', '1') != '0':
             return sched.chunks(32)
         return sched.scene_start[:0], 0
 

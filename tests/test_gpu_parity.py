@@ -512,9 +512,11 @@ def test_gcn_fused_single_launch_matches_three_kernel_path(sgx):
     m = m.to(DEV)
     args = (g['x'].to(DEV), g['seq_start_end'].to(DEV), g['pos'].to(DEV), g['labels'].to(DEV))
     with torch.no_grad():
-        ref = m(*args)
-        fused = _with_env('SGX_GCN_FUSED', '1', lambda: m(*args))
-    assert_close(fused, ref, 2e-6, 'fused GCN vs three-kernel path')
+        ref = _with_env('SGX_GCN_FUSED', '0', lambda: m(*args))
+        fused = m(*args)                                                    # default: tensor-core single launch
+        gemv = _with_env('SGX_GCN_MMA', '0', lambda: m(*args))              # CUDA-core single launch
+    assert_close(fused, ref, 5e-6, 'fused GCN (mma) vs three-kernel path')
+    assert_close(gemv, ref, 2e-6, 'fused GCN (gemv) vs three-kernel path')
     assert_close(fused, g['out'], 1e-5, 'fused GCN vs golden')
 
 
@@ -534,6 +536,28 @@ def test_gat_encoder_chunk_boundaries(sgx, sizes):
     with torch.no_grad():
         out = m.to(DEV)(x.to(DEV), sse.to(DEV), pos.to(DEV), labs.to(DEV))
     assert_close(out, ref, 1e-5, 'gat %s' % sizes[:3])
+
+
+@pytest.mark.parametrize('sizes,in_dim,final', [([32], 40, 24), ([32, 32, 1], 32, 24), ([33], 40, 24),
+                                                ([31, 2, 32, 1, 1, 30], 40, 32), ([1] * 70, 32, 32)])
+def test_gcn_module_chunk_boundaries(sgx, sizes, in_dim, final):
+    """the same layout edge cases through the single-launch tensor-core GCN kernel (and its fallback for N = 33), for
+    every built (input_dim, final_dim) instance"""
+    rng = np.random.RandomState(sum(sizes) + in_dim)
+    torch.manual_seed(sum(sizes) + final)
+    sse = sse_from_sizes(sizes)
+    n = sum(sizes)
+    labs = torch.tensor(np.where(rng.rand(n) < 0.2, 0, rng.randint(1, 5, size=n)), dtype=torch.float32).view(-1, 1)
+    x, pos = torch.randn(n, in_dim), torch.rand(n, 2)
+    m = sgx['M'].GCNModule(input_dim=in_dim, hidden_dim=72, out_dim=16, gcn_layers=2, final_dim=final)
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.dim() == 2 and p.shape[0] != final:
+                p.mul_(0.15)                                   # plain randn GCN weights: keep activations O(1)
+    ref = O.gcn_module(x, sse, pos, labs, m.state_dict(), '')
+    with torch.no_grad():
+        out = m.to(DEV)(x.to(DEV), sse.to(DEV), pos.to(DEV), labs.to(DEV))
+    assert_close(out, ref, 1e-5, 'gcn %s' % sizes[:3])
 
 
 @pytest.mark.parametrize('sizes', [[8] * 2, [16] * 8, [2] * 32, [11, 3], [128], [1]])
