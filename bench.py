@@ -416,7 +416,7 @@ def main():
             'roofline': {'kernel': 'pool_pair_kernel' if precision != 'bf16' else 'pool_tc_kernel', 'bound': 'tensor',
                          'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
                          'traffic': 36.45e6 if (precision == 'bf16' and args.scenes == 1 << 16) else None,
-                         'traffic_source': 'dram__bytes_read+write per launch, ncu --set full, profiles/r01_final_pool_tc_ncu_full_raw.csv',
+                         'traffic_source': 'dram__bytes_read+write per launch, ncu --set full, profiles/r01_final_forward_top_kernels_ncu_full_raw.csv',
                          'peak_source': peak_src, 'kernel_ms': k_ms,
                          'algorithmic_flops_per_launch': POOL_FLOPS_PER_PAIR * n_pairs,
                          'note': 'as-written FLOPs (57408 per ordered pair); bf16: tcgen05 GEMM1+GEMM2 with the 2->16 embedding '
