@@ -33,6 +33,7 @@ SIGNATURES = {
     'sgx_profile_events': (ctypes.c_int, [_P, _P]),
     'sgx_schedule_stats': (ctypes.c_int, [_P, _I64, _P]),
     'sgx_schedule_fill': (ctypes.c_int, [_P, _I64, _P, _P, _P, _P, _P]),
+    'sgx_schedule_build': (ctypes.c_int, [_P, _I64, _P, _P, _P, _P, _P, _P, _I32, _P, _P]),
     'sgx_schedule_partition': (ctypes.c_int, [_P, _I64, _I32, _P, _P]),
     'sgx_schedule_chunks': (ctypes.c_int, [_P, _I64, _I32, _P, _P]),
     'sgx_group_ids': (ctypes.c_int, [_P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P]),

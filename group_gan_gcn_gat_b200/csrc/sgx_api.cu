@@ -92,6 +92,41 @@ extern "C" int sgx_schedule_fill(const int64_t* sse, int64_t S, int32_t* scene_s
     return SGX_OK;
 }
 
+// sgx_schedule_fill + the per-pedestrian scene index + (when every scene fits `chunk_cap`) the chunk boundaries of
+// sgx_schedule_chunks, in ONE pass over the scenes: what the host side builds per minibatch.
+extern "C" int sgx_schedule_build(const int64_t* sse, int64_t S, int32_t* scene_start, int32_t* ped_start,
+                                  int32_t* ped_end, int64_t* pair_off, int32_t* tile_first, int32_t* ped_scene,
+                                  int32_t chunk_cap, int32_t* chunk_scene, int64_t* n_chunks) {
+    int64_t batch, mx, pairs;
+    int rc = validate(sse, S, &batch, &mx, &pairs);
+    if (rc) return rc;
+    SGX_REQUIRE(scene_start && ped_start && ped_end && pair_off && tile_first && ped_scene, "null output array");
+    const bool chunks = chunk_scene != nullptr && n_chunks != nullptr && chunk_cap >= 1 && mx <= chunk_cap;
+    int64_t acc = 0, next_tile = 0, c = 0, fill = 0;
+    if (chunks) chunk_scene[0] = 0;
+    for (int64_t s = 0; s < S; ++s) {
+        const int64_t a = sse[2 * s], b = sse[2 * s + 1], n = b - a;
+        scene_start[s] = (int32_t)a;
+        if (chunks) {
+            if (fill + n > chunk_cap) { chunk_scene[++c] = (int32_t)s; fill = 0; }
+            fill += n;
+        }
+        for (int64_t i = a; i < b; ++i) {
+            ped_start[i] = (int32_t)a;
+            ped_end[i] = (int32_t)b;
+            ped_scene[i] = (int32_t)s;
+            pair_off[i] = acc;
+            while (next_tile * 128 < acc + n) tile_first[next_tile++] = (int32_t)i;
+            acc += n;
+        }
+    }
+    scene_start[S] = (int32_t)batch;
+    pair_off[batch] = acc;
+    if (chunks) chunk_scene[++c] = (int32_t)S;
+    if (n_chunks) *n_chunks = chunks ? c : 0;
+    return SGX_OK;
+}
+
 // Longest-processing-time-first partition of scenes over ranks, cost = N^2 (pairwise pooling).
 extern "C" int sgx_schedule_partition(const int64_t* sse, int64_t S, int32_t world, int32_t* rank_of_scene,
                                       int64_t* rank_cost) {
