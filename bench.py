@@ -423,12 +423,21 @@ def main():
                                  'folded into GEMM1; fp32: exactly factored layer 1 on CUDA cores (DESIGN.md 4.1/4.2)'},
             'wall_s_timed_region': wall,
             'other_kernels': [
-                {'op': 'GATEncoder fwd (group_ids + gat_fused_fwd_kernel)', 'bound': 'hbm', 'ms': gat_ms,
+                {'op': 'GATEncoder fwd (group_ids + gat_fused_mma_kernel)', 'bound': 'hbm', 'ms': gat_ms,
                  'algorithmic_bytes': 260 * peds + 16 * n_scenes + 29920,
                  'achieved': (260 * peds + 16 * n_scenes + 29920) / (gat_ms * 1e-3) / 1e9,
                  'peak': peaks.get('hbm_gbs', 6650.0), 'unit': 'GB/s',
                  'frac': (260 * peds + 16 * n_scenes + 29920) / (gat_ms * 1e-3) / 1e9 / peaks.get('hbm_gbs', 6650.0),
-                 'note': 'HBM-bound by decree (SURVEY 8d); the kernel is issue / tensor-pipe bound (3xTF32 mma.sync linear maps + per-ped attention, ~6 kFMA/ped), see DESIGN.md 4.3'},
+                 'algorithmic_flops': 190 * n_pairs + 8400 * peds,
+                 'achieved_tflops': (190 * n_pairs + 8400 * peds) / (gat_ms * 1e-3) / 1e12,
+                 'fp32_cuda_core_peak_tflops': 148 * 128 * 2 * 1.965e-3,
+                 'note': 'HBM-bound by decree (SURVEY 8d: 260 B/ped, 190 N^2 + 8.4k N FLOP per scene = 35 FLOP/B, above the '
+                         '11.5 FLOP/B ridge of the fp32 CUDA cores): the kernel is issue / tensor-pipe bound (3xTF32 mma.sync '
+                         'linear maps + per-ped attention), see DESIGN.md 4.3'},
+                {'op': 'Encoder + decoder LSTM', 'bound': 'xu (MUFU)', 'ms': enc_ms + dec_ms,
+                 'mufu_per_ped_step': 7 * 32, 'achieved_gmufu_s': 224 * 20 * peds / ((enc_ms + dec_ms) * 1e-3) / 1e9,
+                 'peak_gmufu_s': 148 * 16 * 1.965, 'frac': 224 * 20 * peds / ((enc_ms + dec_ms) * 1e-3) / 1e9 / (148 * 16 * 1.965),
+                 'note': '7 transcendental operations per hidden unit and step on 16 MUFU lanes per SM at 1.965 GHz (DESIGN.md 4.6)'},
                 {'op': 'Encoder LSTM 8 steps (lstm_tc_kernel)', 'ms': enc_ms, 'ped_steps_per_s': 8 * peds / (enc_ms * 1e-3)},
                 {'op': 'Decoder LSTM 12 steps + hidden2pos + noise fold-in (lstm_tc_kernel)', 'ms': dec_ms,
                  'ped_steps_per_s': 12 * peds / (dec_ms * 1e-3)},

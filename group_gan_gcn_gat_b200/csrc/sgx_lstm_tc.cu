@@ -93,7 +93,8 @@ __global__ void lstm_tc_prep_kernel(const float* __restrict__ We, const float* _
 // gain, the issue slots it costs are as scarce as the XU cycles it frees; the bf16 roundings of the operand splits as
 // integer arithmetic instead of cvt.rn.bf16x2 -- 6 % slower; truncating splits (mask + byte-permute, no cvt at all) -- no
 // change; software-pipelined TMEM loads -- no change; four tiles in flight (17 warps => 96 registers, 250 B of spills)
-// -- 20 % slower.  Per-phase counters (tools/lstm_stats.py): of 6 590 cycles per tile-step the gate math holds the warp
+// -- 20 % slower; the two reciprocals as integer seed + two Halley steps on the FMA pipe -- 1 % slower.
+// Per-phase counters (tools/lstm_stats.py): of 6 590 cycles per tile-step the gate math holds the warp
 // for 4 090 with three warps sharing each SMSP's XU unit: 3 x 224 MUFU x 8 cycles = 5 376 = 82 % of the step.)
 constexpr float E_CLAMP = 40.f, T_CLAMP = 30.f;
 __device__ __forceinline__ float ex2_clamped(float v, float hi) {
