@@ -594,3 +594,51 @@ def test_generator_every_timestep_pooling_bf16_close_to_fp32(sgx):
         gen.pool_net.precision = gen.decoder.pool_net.precision = 'bf16'
         b = gen(obs, obs_rel, sse, grp, user_noise=z)
     assert_close(b, a, 2e-2, 'per-step pooling bf16 vs fp32')
+
+
+def test_generator_block_diagonal_over_scenes_at_bench_size(sgx):
+    """Size-independent property at BASELINE's full size (65 536 zara1-shaped scenes, 245 k peds): the generator is
+    block-diagonal over scenes, so the forward of the whole batch equals the concatenated forwards of its two halves,
+    in both pooling precisions, and the LPT shards of `parallel.shard_batch` reassemble to the same predictions."""
+    import sys
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from group_gan_gcn_gat_b200 import parallel
+    data = bench.synth_batch(1 << 16, 4321)
+    g = load_golden('generator_gat_zara1')
+    gen = _generator(sgx, g, 'gat')
+    sse = data['seq_start_end']
+    S = sse.shape[0]
+    n = int(sse[-1, 1])
+    z = torch.randn(S, 8, generator=torch.Generator().manual_seed(5))
+    dev = lambda t: t.to(DEV)
+
+    def forward(scenes_lo, scenes_hi):
+        p0, p1 = int(sse[scenes_lo, 0]), int(sse[scenes_hi - 1, 1])
+        part = sse[scenes_lo:scenes_hi] - p0
+        with torch.no_grad():
+            return gen(dev(data['obs_traj'][:, p0:p1]), dev(data['obs_traj_rel'][:, p0:p1]), dev(part),
+                       dev(data['obs_traj_g'][:, p0:p1]), user_noise=dev(z[scenes_lo:scenes_hi]))
+
+    for precision, tol in (('bf16', 1e-6), ('fp32', 1e-6)):
+        gen.pool_net.precision = precision
+        whole = forward(0, S)
+        assert whole.shape == (12, n, 2) and bool(torch.isfinite(whole).all())
+        halves = torch.cat([forward(0, S // 2 + 7), forward(S // 2 + 7, S)], dim=1)
+        assert_close(halves, whole, tol, 'halves vs whole (%s)' % precision)
+    # LPT shards over 3 ranks: every pedestrian appears exactly once and keeps its prediction
+    gen.pool_net.precision = 'bf16'
+    whole = forward(0, S)
+    seen = torch.zeros(n, dtype=torch.bool)
+    for rank in range(3):
+        loc, sse_r, mine = parallel.shard_batch({'obs_traj': data['obs_traj'], 'obs_traj_rel': data['obs_traj_rel'],
+                                                 'obs_traj_g': data['obs_traj_g']}, sse, 3, rank)
+        mine = torch.as_tensor(mine)
+        with torch.no_grad():
+            out = gen(dev(loc['obs_traj']), dev(loc['obs_traj_rel']), dev(sse_r), dev(loc['obs_traj_g']), user_noise=dev(z[mine]))
+        idx = torch.cat([torch.arange(int(sse[s, 0]), int(sse[s, 1])) for s in mine.tolist()])
+        assert not seen[idx].any()
+        seen[idx] = True
+        assert_close(out, whole[:, idx.to(DEV)], 1e-6, 'LPT shard %d' % rank)
+    assert bool(seen.all())
