@@ -39,9 +39,12 @@ constexpr int SLICE = 136;       // per-tile slice of pair_off / ped_start stage
 // ---------------------------------------------------------------------------------------------
 // operand preparation: bf16 copy of h, pre-swizzled weight images
 // ---------------------------------------------------------------------------------------------
-__global__ void tc_prep_h_kernel(const float* __restrict__ h, int64_t n, __nv_bfloat16* __restrict__ hb) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) hb[i] = __float2bfloat16_rn(h[i]);
+__global__ void tc_prep_h_kernel(const float* __restrict__ h, int64_t n8, __nv_bfloat16* __restrict__ hb) {
+    // eight values per thread: two 16-byte loads, one 16-byte store (n = 8 n8; H is a multiple of 8)
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n8) return;
+    const float4 a = reinterpret_cast<const float4*>(h)[2 * i], b = reinterpret_cast<const float4*>(h)[2 * i + 1];
+    reinterpret_cast<uint4*>(hb)[i] = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
 }
 
 // W1p image: 512 rows x 128 B.   W2p image: 8 K-blocks x N2 rows x 128 B.
@@ -524,7 +527,7 @@ int sgx_pool_fwd_bf16(const float* h, const float* pos, const int32_t* ped_start
     SGX_LAUNCH_CHECK();
     tc_prep_w_kernel<<<blocks_for(HID * 64, 256), 256, 0, st>>>(Aeff, c0, W1, W2, E, H, B, N2, W1p, W2p);
     SGX_LAUNCH_CHECK();
-    tc_prep_h_kernel<<<blocks_for(batch * H, 256), 256, 0, st>>>(h, batch * H, hb);
+    tc_prep_h_kernel<<<blocks_for(batch * H / 8, 256), 256, 0, st>>>(h, batch * H / 8, hb);
     SGX_LAUNCH_CHECK();
     const int64_t n_tiles = (n_pairs + TILE - 1) / TILE;
     const char* mode = getenv("SGX_POOL_TC_MODE");
