@@ -115,7 +115,7 @@ pool_tc_kernel(const __nv_bfloat16* __restrict__ hb, const float* __restrict__ p
                const int32_t* __restrict__ ped_start, const int64_t* __restrict__ pair_off,
                const int32_t* __restrict__ tile_first, int64_t n_tiles, int batch, int64_t n_pairs,
                const __nv_bfloat16* __restrict__ W1p, const __nv_bfloat16* __restrict__ W2p,
-               const float* __restrict__ b2, unsigned long long* __restrict__ packed, int dbg,
+               const float* __restrict__ b2, unsigned long long* __restrict__ packed,
                long long* __restrict__ stats_out) {
     using C = TcCfg<H, N2, TS>;
     static_assert(B % 8 == 0, "the final epilogue reduces eight columns at a time");
@@ -454,7 +454,7 @@ pool_tc_kernel(const __nv_bfloat16* __restrict__ hb, const float* __restrict__ p
         stats_out[role * 8 + 5] = my_tiles;
     }
 #endif
-    (void)dbg; (void)stats_out; (void)t_begin_; (void)stats_;
+    (void)stats_out; (void)t_begin_; (void)stats_;
     tc_fence_before();
     __syncthreads();
     if (warp == 16) {
@@ -469,8 +469,6 @@ template <int H, int B, int N2, bool TS>
 static int launch_tc(const __nv_bfloat16* hb, const float* pos, const int32_t* ped_start, const int64_t* pair_off,
                      const int32_t* tile_first, int64_t n_tiles, int batch, int64_t n_pairs, const __nv_bfloat16* W1p,
                      const __nv_bfloat16* W2p, const float* b2, unsigned long long* packed, cudaStream_t st) {
-    const char* dbg_s = getenv("SGX_POOL_TC_DBG");
-    const int dbg = dbg_s ? atoi(dbg_s) : 0;
     using C = TcCfg<H, N2, TS>;
     auto kern = pool_tc_kernel<H, B, N2, TS>;
     SGX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
@@ -482,7 +480,7 @@ static int launch_tc(const __nv_bfloat16* hb, const float* pos, const int32_t* p
     profile_events(&ev0, &ev1);
     if (ev0 && ev1) SGX_CUDA(cudaEventRecord(ev0, st));
     kern<<<grid, NTHREADS, C::TOTAL, st>>>(hb, pos, ped_start, pair_off, tile_first, n_tiles, batch, n_pairs, W1p, W2p,
-                                           b2, packed, dbg, g_tc_stats);
+                                           b2, packed, g_tc_stats);
     SGX_LAUNCH_CHECK();
     if (ev0 && ev1) SGX_CUDA(cudaEventRecord(ev1, st));
     return SGX_OK;
