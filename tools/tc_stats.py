@@ -9,7 +9,7 @@ buf = torch.zeros(40, dtype=torch.int64, device='cuda')
 h = ctypes.CDLL(_lib.LIB_PATH)
 h.sgx_debug_tc_stats.argtypes = [ctypes.c_void_p]
 h.sgx_debug_tc_stats(buf.data_ptr())
-names = ['G1 issuer (x_full, d1_free)', 'G2 issuer (-, -, d2_free, h_ready)', 'ROW0 (x_free, d2_full)', 'EPI0 (d1_full, h_free)', 'EPI1 (d1_full, h_free)']
+names = ['G1 issuer (x_full, d1_free)', 'G2 issuer (-, -, d2_free, h_ready)', 'ROW0 (wait x_free, wait d2_full, prefetch cycles, finalize cycles)', 'EPI0 (d1_full, h_free)', 'EPI1 (d1_full, h_free)']
 for label, sizes in (('dense N=1024 x8', [1024] * 8), ('zara-shaped 65536 scenes', list(bench.synth_batch(1 << 16, 1236)['sizes']))):
     time_case(sizes, (16, 32, 8), 'bf16', reps=3)
     torch.cuda.synchronize()
