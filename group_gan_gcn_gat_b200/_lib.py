@@ -51,7 +51,7 @@ SIGNATURES = {
     'sgx_gat_encoder_ws_bytes': (_I64, [_I64, _I64, _I32, _I32, _I32, _I32, _I32]),
     'sgx_gat_encoder_fwd': (ctypes.c_int, [_P] * 5 + [_I64, _I64] + [_P] * 10 + [_F32] + [_I32] * 5 +
                             [_P, _P, _I64, _P]),
-    'sgx_gat_encoder_fused_fwd': (ctypes.c_int, [_P] * 7 + [_I64] + [_P] * 10 + [_F32] + [_I32] * 5 + [_P, _P]),
+    'sgx_gat_encoder_fused_fwd': (ctypes.c_int, [_P] * 7 + [_I64, _I32] + [_P] * 10 + [_F32] + [_I32] * 5 + [_P, _P]),
     'sgx_gat_encoder_bwd': (ctypes.c_int, [_P] * 6 + [_I64, _I64] + [_P] * 10 + [_F32] + [_I32] * 5 + [_P] * 11 +
                             [_P, _I64, _P]),
     'sgx_lstm_ws_bytes': (_I64, []),

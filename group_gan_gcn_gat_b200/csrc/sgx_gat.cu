@@ -743,21 +743,14 @@ struct FusedWm {
     float Wi[40 * SW1], Wio[HID * SW2], We[OUT * SW1], Weo[HID * SW2], WoT[2 * OUT * SW2], bo[24];
 };
 
+// weight blocks [K][N + 2 score columns + zero padding]: column N = W a[:N], N+1 = W a[N:]; Wo transposed
 template <int IN, int FIN>
-__global__ void __launch_bounds__(FUSED_WARPS * 32)
-gat_fused_mma_kernel(const float* __restrict__ x, const int32_t* __restrict__ leader, const int32_t* __restrict__ gsize,
-                     const int32_t* __restrict__ ped_start, const int32_t* __restrict__ ped_end,
-                     const int32_t* __restrict__ scene_start, const int32_t* __restrict__ chunk_scene, int n_chunks,
-                     const float* __restrict__ Wi, const float* __restrict__ ai, const float* __restrict__ Wio,
-                     const float* __restrict__ aio, const float* __restrict__ We, const float* __restrict__ ae,
-                     const float* __restrict__ Weo, const float* __restrict__ aeo, const float* __restrict__ Wo,
-                     const float* __restrict__ bo, float alpha, float* __restrict__ out) {
-    static_assert(IN == 40 && FIN == 24, "built for the shipped dims");
-    extern __shared__ __align__(16) uint8_t raw[];
-    FusedWm& w = *reinterpret_cast<FusedWm*>(raw);
-    float* bufs = reinterpret_cast<float*>(raw + sizeof(FusedWm));
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    {   // weight blocks [K][N + 2 score columns + zero padding]: column N = W a[:N], N+1 = W a[N:]
+__device__ __forceinline__ void fused_load_weights(FusedWm& w, const float* __restrict__ Wi, const float* __restrict__ ai,
+                                                   const float* __restrict__ Wio, const float* __restrict__ aio,
+                                                   const float* __restrict__ We, const float* __restrict__ ae,
+                                                   const float* __restrict__ Weo, const float* __restrict__ aeo,
+                                                   const float* __restrict__ Wo, const float* __restrict__ bo) {
+    {
         auto fill = [&](float* dst, int stride, const float* W, const float* a, int K, int N) {
             for (int e = threadIdx.x; e < K * stride; e += blockDim.x) {
                 const int k = e / stride, n = e % stride;
@@ -780,6 +773,23 @@ gat_fused_mma_kernel(const float* __restrict__ x, const int32_t* __restrict__ le
         }
         for (int e = threadIdx.x; e < FIN; e += blockDim.x) w.bo[e] = bo[e];
     }
+}
+
+template <int IN, int FIN>
+__global__ void __launch_bounds__(FUSED_WARPS * 32)
+gat_fused_mma_kernel(const float* __restrict__ x, const int32_t* __restrict__ leader, const int32_t* __restrict__ gsize,
+                     const int32_t* __restrict__ ped_start, const int32_t* __restrict__ ped_end,
+                     const int32_t* __restrict__ scene_start, const int32_t* __restrict__ chunk_scene, int n_chunks,
+                     const float* __restrict__ Wi, const float* __restrict__ ai, const float* __restrict__ Wio,
+                     const float* __restrict__ aio, const float* __restrict__ We, const float* __restrict__ ae,
+                     const float* __restrict__ Weo, const float* __restrict__ aeo, const float* __restrict__ Wo,
+                     const float* __restrict__ bo, float alpha, float* __restrict__ out) {
+    static_assert(IN == 40 && FIN == 24, "built for the shipped dims");
+    extern __shared__ __align__(16) uint8_t raw[];
+    FusedWm& w = *reinterpret_cast<FusedWm*>(raw);
+    float* bufs = reinterpret_cast<float*>(raw + sizeof(FusedWm));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    fused_load_weights<IN, FIN>(w, Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo);
     __syncthreads();
     float* A = bufs + warp * FUSED_SCRATCH;               // [32][RA]  16-wide rows: Wh2 / Xg / Wh4 / Yg
     float* Bf = A + 32 * RA;                              // [32][RS]  72-wide rows: x / Wh1 / hp / Wh3 / hp / cat
@@ -928,11 +938,246 @@ gat_fused_mma_kernel(const float* __restrict__ x, const int32_t* __restrict__ le
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Chunks of up to 64 pedestrians (scenes of 33..64: 28 % of the univ test windows, ~10 % of every training split, and
+// one such scene sends the whole minibatch down the multi-pass path otherwise): the same kernel with TWO slots per
+// lane (lane and lane + 32), four m-tiles per warp GEMM, 64-bit neighbour masks built once per chunk by scanning the
+// scene's leader slots.  Twice the per-warp scratch => 6 warps per SM; only used when a scene exceeds 32.
+// ------------------------------------------------------------------------------------------------
+constexpr int F64_WARPS = 6;
+constexpr int F64_SCRATCH = 64 * RA + 64 * RS + 64 * 16 + 64 * 2 + 64;   // floats per warp
+
+template <int F, int STRIDE>
+__device__ __forceinline__ void attend_mask64(const float* __restrict__ rows, const float2* __restrict__ st,
+                                              unsigned long long mask, float s_i, float alpha, float (&hp)[F]) {
+    float m = -INFINITY;
+    for (unsigned long long mm = mask; mm; mm &= mm - 1) m = fmaxf(m, lrelu(s_i + st[__ffsll(mm) - 1].y, alpha));
+    float den = 0.f;
+#pragma unroll
+    for (int f = 0; f < F; ++f) hp[f] = 0.f;
+    for (unsigned long long mm = mask; mm; mm &= mm - 1) {
+        const int q = __ffsll(mm) - 1;
+        const float w = fexp(lrelu(s_i + st[q].y, alpha) - m);
+        den += w;
+        const float4* row = reinterpret_cast<const float4*>(rows + q * STRIDE);
+#pragma unroll
+        for (int f = 0; f < F / 4; ++f) {
+            const float4 v = row[f];
+            hp[4 * f] = fmaf(w, v.x, hp[4 * f]); hp[4 * f + 1] = fmaf(w, v.y, hp[4 * f + 1]);
+            hp[4 * f + 2] = fmaf(w, v.z, hp[4 * f + 2]); hp[4 * f + 3] = fmaf(w, v.w, hp[4 * f + 3]);
+        }
+    }
+    const float inv = 1.f / den;
+#pragma unroll
+    for (int f = 0; f < F; ++f) hp[f] *= inv;
+}
+
+template <int IN, int FIN>
+__global__ void __launch_bounds__(F64_WARPS * 32)
+gat_fused_mma64_kernel(const float* __restrict__ x, const int32_t* __restrict__ leader, const int32_t* __restrict__ gsize,
+                       const int32_t* __restrict__ ped_start, const int32_t* __restrict__ ped_end,
+                       const int32_t* __restrict__ scene_start, const int32_t* __restrict__ chunk_scene, int n_chunks,
+                       const float* __restrict__ Wi, const float* __restrict__ ai, const float* __restrict__ Wio,
+                       const float* __restrict__ aio, const float* __restrict__ We, const float* __restrict__ ae,
+                       const float* __restrict__ Weo, const float* __restrict__ aeo, const float* __restrict__ Wo,
+                       const float* __restrict__ bo, float alpha, float* __restrict__ out) {
+    static_assert(IN == 40 && FIN == 24, "built for the shipped dims");
+    extern __shared__ __align__(16) uint8_t raw[];
+    FusedWm& w = *reinterpret_cast<FusedWm*>(raw);
+    float* bufs = reinterpret_cast<float*>(raw + sizeof(FusedWm));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    fused_load_weights<IN, FIN>(w, Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo);
+    __syncthreads();
+    float* A = bufs + warp * F64_SCRATCH;                 // [64][RA]
+    float* Bf = A + 64 * RA;                              // [64][RS]
+    float* X1s = Bf + 64 * RS;                            // [64][16]
+    float2* st = reinterpret_cast<float2*>(X1s + 64 * 16);
+    int* lead_slot = reinterpret_cast<int*>(st + 64);
+    const int g = lane >> 2, t = lane & 3;
+    auto store_wide = [&](int mt, int nt, const float (&c)[4]) {
+        const int r = mt * 16 + g;
+        if (nt < HID / 8) {
+            *reinterpret_cast<float2*>(Bf + r * RS + nt * 8 + 2 * t) = make_float2(c[0], c[1]);
+            *reinterpret_cast<float2*>(Bf + (r + 8) * RS + nt * 8 + 2 * t) = make_float2(c[2], c[3]);
+        } else if (t == 0) {
+            st[r] = make_float2(c[0], c[1]);
+            st[r + 8] = make_float2(c[2], c[3]);
+        }
+    };
+    auto store_narrow = [&](int mt, int nt, const float (&c)[4]) {
+        const int r = mt * 16 + g;
+        if (nt < OUT / 8) {
+            *reinterpret_cast<float2*>(A + r * RA + nt * 8 + 2 * t) = make_float2(c[0], c[1]);
+            *reinterpret_cast<float2*>(A + (r + 8) * RA + nt * 8 + 2 * t) = make_float2(c[2], c[3]);
+        } else if (t == 0) {
+            st[r] = make_float2(c[0], c[1]);
+            st[r + 8] = make_float2(c[2], c[3]);
+        }
+    };
+    const int n_warps_total = gridDim.x * F64_WARPS;
+    for (int chunk = blockIdx.x * F64_WARPS + warp; chunk < n_chunks; chunk += n_warps_total) {
+        const int p0 = scene_start[chunk_scene[chunk]];
+        const int np = scene_start[chunk_scene[chunk + 1]] - p0;
+        bool live[2], is_lead[2];
+        int b[2], e[2], my_lead[2];
+        float inv_g[2];
+        unsigned long long group_mask[2], leader_mask[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int slot = lane + 32 * r, p = p0 + slot;
+            live[r] = slot < np;
+            b[r] = 0; e[r] = 0; my_lead[r] = slot; inv_g[r] = 1.f;
+            float4 xv[IN / 4];
+#pragma unroll
+            for (int c = 0; c < IN / 4; ++c) xv[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live[r]) {
+                b[r] = ped_start[p] - p0; e[r] = ped_end[p] - p0; my_lead[r] = leader[p] - p0;
+                inv_g[r] = __frcp_rn((float)gsize[p]);
+                const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)p * IN);
+#pragma unroll
+                for (int c = 0; c < IN / 4; ++c) xv[c] = xr[c];
+            }
+#pragma unroll
+            for (int c = 0; c < IN / 4; ++c) reinterpret_cast<float4*>(Bf + slot * RS)[c] = xv[c];
+            lead_slot[slot] = live[r] ? my_lead[r] : -1;
+            is_lead[r] = live[r] && my_lead[r] == slot;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {                     // neighbour sets: members of my group, leaders of my scene
+            group_mask[r] = 0ull; leader_mask[r] = 0ull;
+            for (int q = b[r]; q < e[r]; ++q) {
+                const int l = lead_slot[q];
+                if (l == my_lead[r]) group_mask[r] |= 1ull << q;
+                if (l == q) leader_mask[r] |= 1ull << q;
+            }
+        }
+        // ---- intra GAT, layer 1 ----
+        warp_gemm_3xtf32<IN, HID / 8 + 1, RS, SW1, 4>(Bf, w.Wi, lane, store_wide);
+        {
+            float hp[2][HID];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+#pragma unroll
+                for (int f = 0; f < HID; ++f) hp[r][f] = 0.f;
+                if (live[r]) {
+                    attend_mask64<HID, RS>(Bf, st, group_mask[r], st[lane + 32 * r].x, alpha, hp[r]);
+#pragma unroll
+                    for (int f = 0; f < HID; ++f) hp[r][f] = felu(hp[r][f]);
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 2; ++r) store_row<HID>(Bf + (lane + 32 * r) * RS, hp[r]);
+        }
+        __syncwarp();
+        // ---- intra GAT, out_att ----
+        warp_gemm_3xtf32<HID, OUT / 8 + 1, RS, SW2, 4>(Bf, w.Wio, lane, store_narrow);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            float x1[OUT];
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) x1[o] = 0.f;
+            if (live[r]) {
+                attend_mask64<OUT, RA>(A, st, group_mask[r], st[lane + 32 * r].x, alpha, x1);
+                elu_logsoftmax<OUT>(x1);
+            }
+            store_row<OUT>(X1s + (lane + 32 * r) * 16, x1);
+        }
+        __syncwarp();
+        // ---- GPool (leaders) ----
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            float xg[OUT];
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) xg[o] = 0.f;
+            if (is_lead[r]) {
+                for (unsigned long long mm = group_mask[r]; mm; mm &= mm - 1) {
+                    const int q = __ffsll(mm) - 1;
+#pragma unroll
+                    for (int o = 0; o < OUT; ++o) xg[o] = fmaf(inv_g[r], X1s[q * 16 + o], xg[o]);
+                }
+            }
+            store_row<OUT>(A + (lane + 32 * r) * RA, xg);
+        }
+        __syncwarp();
+        // ---- inter GAT ----
+        warp_gemm_3xtf32<OUT, HID / 8 + 1, RA, SW1, 4>(A, w.We, lane, store_wide);
+        {
+            float hp[2][HID];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+#pragma unroll
+                for (int f = 0; f < HID; ++f) hp[r][f] = 0.f;
+                if (is_lead[r]) {
+                    attend_mask64<HID, RS>(Bf, st, leader_mask[r], st[lane + 32 * r].x, alpha, hp[r]);
+#pragma unroll
+                    for (int f = 0; f < HID; ++f) hp[r][f] = felu(hp[r][f]);
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 2; ++r) store_row<HID>(Bf + (lane + 32 * r) * RS, hp[r]);
+        }
+        __syncwarp();
+        warp_gemm_3xtf32<HID, OUT / 8 + 1, RS, SW2, 4>(Bf, w.Weo, lane, store_narrow);
+        {
+            float yg[2][OUT];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+#pragma unroll
+                for (int o = 0; o < OUT; ++o) yg[r][o] = 0.f;
+                if (is_lead[r]) {
+                    attend_mask64<OUT, RA>(A, st, leader_mask[r], st[lane + 32 * r].x, alpha, yg[r]);
+                    elu_logsoftmax<OUT>(yg[r]);
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 2; ++r) store_row<OUT>(A + (lane + 32 * r) * RA, yg[r]);
+        }
+        __syncwarp();
+        // ---- unpool + output Linear ----
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int slot = lane + 32 * r;
+#pragma unroll
+            for (int c = 0; c < OUT / 4; ++c) {
+                const float4 u = reinterpret_cast<const float4*>(X1s + slot * 16)[c];
+                const float4 v = reinterpret_cast<const float4*>(A + my_lead[r] * RA)[c];
+                reinterpret_cast<float4*>(Bf + slot * RS)[c] = u;
+                reinterpret_cast<float4*>(Bf + slot * RS + OUT)[c] =
+                    make_float4(inv_g[r] * v.x, inv_g[r] * v.y, inv_g[r] * v.z, inv_g[r] * v.w);
+            }
+        }
+        __syncwarp();
+        warp_gemm_3xtf32<2 * OUT, FIN / 8, RS, SW2, 4>(Bf, w.WoT, lane, [&](int mt, int nt, const float (&c)[4]) {
+            const int r = mt * 16 + g, col = nt * 8 + 2 * t;
+            const float b0 = w.bo[col], b1 = w.bo[col + 1];
+            if (r < np) *reinterpret_cast<float2*>(out + (int64_t)(p0 + r) * FIN + col) = make_float2(c[0] + b0, c[1] + b1);
+            if (r + 8 < np)
+                *reinterpret_cast<float2*>(out + (int64_t)(p0 + r + 8) * FIN + col) = make_float2(c[2] + b0, c[3] + b1);
+        });
+    }
+}
+
 static int gat_fused_forward(const float* x, const int32_t* leader, const int32_t* gsize, const int32_t* ps,
                              const int32_t* pe, const int32_t* scene_start, const int32_t* chunk_scene, int n_chunks,
+                             int chunk_cap,
                              const float* Wi, const float* ai, const float* Wio, const float* aio, const float* We,
                              const float* ae, const float* Weo, const float* aeo, const float* Wo, const float* bo,
                              float alpha, float* out, cudaStream_t st) {
+    if (chunk_cap > 32) {                  // chunks of up to 64 pedestrians: two slots per lane
+        auto kern64 = gat_fused_mma64_kernel<40, 24>;
+        const int smem64 = (int)(sizeof(FusedWm) + F64_WARPS * F64_SCRATCH * sizeof(float));
+        SGX_CUDA(cudaFuncSetAttribute(kern64, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64));
+        const int grid64 = std::min((n_chunks + F64_WARPS - 1) / F64_WARPS, 148);
+        kern64<<<grid64, F64_WARPS * 32, smem64, st>>>(x, leader, gsize, ps, pe, scene_start, chunk_scene, n_chunks, Wi, ai,
+                                                       Wio, aio, We, ae, Weo, aeo, Wo, bo, alpha, out);
+        SGX_LAUNCH_CHECK();
+        return SGX_OK;
+    }
     const int grid = std::min((n_chunks + FUSED_WARPS - 1) / FUSED_WARPS, 148);
     const char* mode = getenv("SGX_GAT_MMA");
     if (!(mode && mode[0] == '0')) {       // default: linear maps on the tensor cores (SGX_GAT_MMA=0: CUDA-core GEMV)
@@ -1040,20 +1285,21 @@ extern "C" int sgx_gat_encoder_bwd(const float* x, const float* grad_out, const 
     return SGX_OK;
 }
 
-// Fused forward for batches whose scenes all have <= 32 peds (chunk_scene: scene index boundaries of chunks of whole
-// scenes with <= 32 peds, built by sgx_schedule_chunks).  n_heads = 1, IN = 40, HID = 72, OUT = 16, FIN = 24.
+// Fused forward for batches whose scenes all have <= chunk_cap (32 or 64) peds (chunk_scene: scene index boundaries of
+// chunks of whole scenes with <= chunk_cap peds, built by sgx_schedule_chunks).  n_heads = 1, IN = 40, HID = 72, OUT = 16, FIN = 24.
 extern "C" int sgx_gat_encoder_fused_fwd(const float* x, const int32_t* leader, const int32_t* group_size,
                                          const int32_t* ped_start, const int32_t* ped_end, const int32_t* scene_start,
-                                         const int32_t* chunk_scene, int64_t n_chunks, const float* Wi, const float* ai,
-                                         const float* Wio, const float* aio, const float* We, const float* ae,
-                                         const float* Weo, const float* aeo, const float* Wo, const float* bo,
-                                         float alpha, int32_t n_heads, int32_t IN, int32_t HID_, int32_t OUT_,
-                                         int32_t FIN, float* out, void* stream) {
+                                         const int32_t* chunk_scene, int64_t n_chunks, int32_t chunk_cap,
+                                         const float* Wi, const float* ai, const float* Wio, const float* aio,
+                                         const float* We, const float* ae, const float* Weo, const float* aeo,
+                                         const float* Wo, const float* bo, float alpha, int32_t n_heads, int32_t IN,
+                                         int32_t HID_, int32_t OUT_, int32_t FIN, float* out, void* stream) {
     SGX_REQUIRE(x && leader && group_size && ped_start && ped_end && scene_start && chunk_scene && Wi && ai && Wio &&
                     aio && We && ae && Weo && aeo && Wo && bo && out, "sgx_gat_encoder_fused_fwd: null pointer");
     SGX_REQUIRE(n_chunks > 0 && n_chunks < ((int64_t)1 << 31), "sgx_gat_encoder_fused_fwd: bad chunk count");
+    SGX_REQUIRE(chunk_cap == 32 || chunk_cap == 64, "sgx_gat_encoder_fused_fwd: chunk capacity must be 32 or 64");
     SGX_UNSUPPORTED(n_heads != 1 || IN != 40 || HID_ != HID || OUT_ != OUT || FIN != 24,
                     "fused GAT encoder is built for n_heads=1, dims 40/72/16/24 (the shipped configuration)");
-    return gat_fused_forward(x, leader, group_size, ped_start, ped_end, scene_start, chunk_scene, (int)n_chunks, Wi, ai,
+    return gat_fused_forward(x, leader, group_size, ped_start, ped_end, scene_start, chunk_scene, (int)n_chunks, chunk_cap, Wi, ai,
                              Wio, aio, We, ae, Weo, aeo, Wo, bo, alpha, out, (cudaStream_t)stream);
 }

@@ -17,16 +17,16 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// C [32 x 8 NT] = A [32 x K] . B [K x 8 NT] for one warp; A rows in shared memory (stride SA floats), B row-major
+// C [16 MT x 8 NT] = A [16 MT x K] . B [K x 8 NT] for one warp (MT = 2: the 32 slots of a warp chunk); A rows in shared memory (stride SA floats), B row-major
 // (stride SB).  store(mt, nt, acc) receives the m16n8 accumulator fragment: acc[0..1] = row mt*16 + lane/4, columns
 // nt*8 + 2 (lane%4) + {0,1}; acc[2..3] = the same columns of row + 8.  A __syncwarp precedes the stores of an m-tile,
 // so C may overwrite the A rows of that m-tile.
-template <int K, int NT, int SA, int SB, class Store>
+template <int K, int NT, int SA, int SB, int MT = 2, class Store>
 __device__ __forceinline__ void warp_gemm_3xtf32(const float* __restrict__ A, const float* __restrict__ B, int lane,
                                                  Store&& store) {
     const int g = lane >> 2, t = lane & 3;
 #pragma unroll 1
-    for (int mt = 0; mt < 2; ++mt) {
+    for (int mt = 0; mt < MT; ++mt) {
         float acc[NT][4];
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }

@@ -168,10 +168,12 @@ class GATEncoder(nn.Module):
         leader, gsize, _gid, _ng = _groups_for(sched, end_group)
         Wi, ai, Wio, aio = self.gat_intra.stacked()
         We, ae, Weo, aeo = self.gat_inter.stacked()
-        chunk_scene, n_chunks = sched.chunks(32) if self.n_heads == 1 else (sched.scene_start[:0], 0)
+        # single-launch kernel: warp chunks of <= 32 peds, or <= 64 (two slots per lane) when a scene exceeds 32
+        cap = 32 if sched.max_n <= 32 else 64
+        chunk_scene, n_chunks = sched.chunks(cap) if self.n_heads == 1 else (sched.scene_start[:0], 0)
         return ops.call(ops.gat_encoder_fwd, h_states, leader, gsize, sched.ped_start, sched.ped_end, sched.n_scenes, Wi, ai, Wio,
                                    aio, We, ae, Weo, aeo, self.out_embedding.weight, self.out_embedding.bias,
-                                   float(self.alpha), sched.scene_start, chunk_scene, n_chunks)
+                                   float(self.alpha), sched.scene_start, chunk_scene, n_chunks, cap)
 
 
 class GCN(nn.Module):

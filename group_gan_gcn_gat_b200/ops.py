@@ -259,8 +259,9 @@ gcn_module_fwd.register_autograd(_gcn_backward, setup_context=_gcn_setup)
 def gat_encoder_fwd(x: Tensor, leader: Tensor, gsize: Tensor, ped_start: Tensor, ped_end: Tensor, n_scenes: int,
                     Wi: Tensor, ai: Tensor, Wio: Tensor, aio: Tensor, We: Tensor, ae: Tensor, Weo: Tensor,
                     aeo: Tensor, Wo: Tensor, bo: Tensor, alpha: float, scene_start: Tensor, chunk_scene: Tensor,
-                    n_chunks: int) -> Tensor:
-    """n_chunks > 0 selects the single-launch fused kernel (all scenes <= 32 peds, n_heads = 1, dims 40/72/16/24)."""
+                    n_chunks: int, chunk_cap: int = 32) -> Tensor:
+    """n_chunks > 0 selects the single-launch fused kernel (all scenes <= chunk_cap = 32 or 64 peds, n_heads = 1,
+    dims 40/72/16/24)."""
     x = _f32(x, 'h_states')
     ps = [_f32(t, 'gat weight') for t in (Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo)]
     batch, IN = x.shape
@@ -271,7 +272,7 @@ def gat_encoder_fwd(x: Tensor, leader: Tensor, gsize: Tensor, ped_start: Tensor,
     with torch.cuda.device(x.device):
         if n_chunks > 0 and nh == 1 and (IN, HID, OUT, FIN) == (40, 72, 16, 24):
             _lib.check(L.sgx_gat_encoder_fused_fwd(_ptr(x), _ptr(leader), _ptr(gsize), _ptr(ped_start), _ptr(ped_end),
-                                                   _ptr(scene_start), _ptr(chunk_scene), n_chunks,
+                                                   _ptr(scene_start), _ptr(chunk_scene), n_chunks, chunk_cap,
                                                    *[_ptr(p) for p in ps], alpha, nh, IN, HID, OUT, FIN, _ptr(out),
                                                    _stream(x)), 'sgx_gat_encoder_fused_fwd')
             return out
@@ -284,7 +285,7 @@ def gat_encoder_fwd(x: Tensor, leader: Tensor, gsize: Tensor, ped_start: Tensor,
 
 @gat_encoder_fwd.register_fake
 def _(x, leader, gsize, ped_start, ped_end, n_scenes, Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo, alpha, scene_start,
-      chunk_scene, n_chunks):
+      chunk_scene, n_chunks, chunk_cap=32):
     return x.new_empty(x.shape[0], Wo.shape[0])
 
 
@@ -323,7 +324,7 @@ def _gat_setup(ctx, inputs, output):
 def _gat_backward(ctx, grad_out):
     x, leader, gsize, ps, pe, *params = ctx.saved_tensors
     g = gat_encoder_bwd(x, grad_out.contiguous(), leader, gsize, ps, pe, ctx.n_scenes, *params, ctx.alpha)
-    return (g[0], None, None, None, None, None, *g[1:], None, None, None, None)
+    return (g[0], None, None, None, None, None, *g[1:], None, None, None, None, None)
 
 
 gat_encoder_fwd.register_autograd(_gat_backward, setup_context=_gat_setup)

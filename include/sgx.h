@@ -168,14 +168,16 @@ int sgx_gat_encoder_fwd(const float* x, const int32_t* leader, const int32_t* gr
                         const float* aeo, const float* Wo, const float* bo, float alpha, int32_t n_heads, int32_t IN,
                         int32_t HID, int32_t OUT, int32_t FIN, float* out, void* workspace, int64_t ws_bytes,
                         void* stream);
-/* Same forward in ONE launch for batches whose scenes all have <= 32 pedestrians (chunk_scene / n_chunks from
- * sgx_schedule_chunks with cap = 32): no intermediate leaves the SM.  n_heads = 1, dims 40/72/16/24 only. */
+/* Same forward in ONE launch for batches whose scenes all have <= chunk_cap pedestrians, chunk_cap = 32 or 64
+ * (chunk_scene / n_chunks from sgx_schedule_chunks with that cap; every ETH/UCY window has <= 57): no intermediate
+ * leaves the SM.  n_heads = 1, dims 40/72/16/24 only. */
 int sgx_gat_encoder_fused_fwd(const float* x, const int32_t* leader, const int32_t* group_size,
                               const int32_t* ped_start, const int32_t* ped_end, const int32_t* scene_start,
-                              const int32_t* chunk_scene, int64_t n_chunks, const float* Wi, const float* ai,
-                              const float* Wio, const float* aio, const float* We, const float* ae, const float* Weo,
-                              const float* aeo, const float* Wo, const float* bo, float alpha, int32_t n_heads,
-                              int32_t IN, int32_t HID, int32_t OUT, int32_t FIN, float* out, void* stream);
+                              const int32_t* chunk_scene, int64_t n_chunks, int32_t chunk_cap, const float* Wi,
+                              const float* ai, const float* Wio, const float* aio, const float* We, const float* ae,
+                              const float* Weo, const float* aeo, const float* Wo, const float* bo, float alpha,
+                              int32_t n_heads, int32_t IN, int32_t HID, int32_t OUT, int32_t FIN, float* out,
+                              void* stream);
 int sgx_gat_encoder_bwd(const float* x, const float* grad_out, const int32_t* leader, const int32_t* group_size,
                         const int32_t* ped_start, const int32_t* ped_end, int64_t batch, int64_t n_scenes,
                         const float* Wi, const float* ai, const float* Wio, const float* aio, const float* We,

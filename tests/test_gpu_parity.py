@@ -521,10 +521,12 @@ def test_gcn_fused_single_launch_matches_three_kernel_path(sgx):
 
 
 # ------------------------------------------------------------------ edge cases of the ragged layout
-@pytest.mark.parametrize('sizes', [[32], [32, 32, 1], [33], [31, 2, 32, 1, 1, 30], [1] * 70])
+@pytest.mark.parametrize('sizes', [[32], [32, 32, 1], [33], [31, 2, 32, 1, 1, 30], [1] * 70, [64], [57, 3, 40, 24, 1],
+                                   [64, 64, 1, 63], [65], [20, 70, 5]])
 def test_gat_encoder_chunk_boundaries(sgx, sizes):
-    """Scenes of exactly 32 peds fill a warp-chunk of the fused kernel; 33 falls back to the general path; many
-    singleton scenes share a chunk.  Both paths must agree with the oracle."""
+    """Scenes of exactly 32 peds fill a warp-chunk of the fused kernel; 33..64 take the two-slots-per-lane kernel
+    (chunks of <= 64); 65 falls back to the general path; many singleton scenes share a chunk.  All paths must
+    agree with the oracle."""
     rng = np.random.RandomState(sum(sizes))
     torch.manual_seed(sum(sizes))
     sse = sse_from_sizes(sizes)
