@@ -485,9 +485,9 @@ def main():
             ],
         }
         if not args.no_cpu_baseline:
-            v, dt, p = cpu_port_traj_per_sec(256, K_SAMPLES, 1234 + 2)
+            v, dt, p = cpu_port_traj_per_sec(1536, K_SAMPLES, 1234 + 2)      # ~11 s of CPU work on 16 cores
             line['cpu_baseline'] = {'value': v, 'unit': 'traj/s', 'cores': os.cpu_count(), 'kind': 'port',
-                                    'sample': '256 zara1-shaped scenes (%d peds) x K=20 forwards, %.1f s' % (p, dt)}
+                                    'sample': '1536 zara1-shaped scenes (%d peds) x K=20 forwards, %.1f s' % (p, dt)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
