@@ -484,7 +484,7 @@ def main():
                  'ped_steps_per_s': 12 * peds / (dec_ms * 1e-3)},
             ],
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:          # the CPU port is timed next to the 1-GPU number only
             v, dt, p = cpu_port_traj_per_sec(1536, K_SAMPLES, 1234 + 2)      # ~11 s of CPU work on 16 cores
             line['cpu_baseline'] = {'value': v, 'unit': 'traj/s', 'cores': os.cpu_count(), 'kind': 'port',
                                     'sample': '1536 zara1-shaped scenes (%d peds) x K=20 forwards, %.1f s' % (p, dt)}
