@@ -737,6 +737,8 @@ gat_fused_fwd_kernel(const float* __restrict__ x, const int32_t* __restrict__ le
 // score projections (Wh a1, Wh a2) ride along as two extra weight columns (W a1, W a2).  The 128-row tcgen05 path does
 // not fit: five weight images with fp32-level splits plus per-tile operand staging exceed the 227 KB of shared memory.
 // ------------------------------------------------------------------------------------------------
+constexpr int FUSEDM_WARPS = 14;       // tensor-core kernel: x1 rows alias the wide row buffer => 12.7 KB per warp; 14 warps per SM (15: slower)
+constexpr int FUSEDM_SCRATCH = 32 * RA + 32 * RS + 32 * 2 + 32;
 constexpr int SW1 = 88;                // row stride of the [K][72+2 (+pad)] weight blocks: 88 % 32 = 24 -> conflict-free B fragments
 constexpr int SW2 = 24;                // row stride of the [K][16+2 (+pad)] and [32][24] blocks
 struct FusedWm {
@@ -776,7 +778,7 @@ __device__ __forceinline__ void fused_load_weights(FusedWm& w, const float* __re
 }
 
 template <int IN, int FIN>
-__global__ void __launch_bounds__(FUSED_WARPS * 32)
+__global__ void __launch_bounds__(FUSEDM_WARPS * 32)
 gat_fused_mma_kernel(const float* __restrict__ x, const int32_t* __restrict__ leader, const int32_t* __restrict__ gsize,
                      const int32_t* __restrict__ ped_start, const int32_t* __restrict__ ped_end,
                      const int32_t* __restrict__ scene_start, const int32_t* __restrict__ chunk_scene, int n_chunks,
@@ -791,10 +793,9 @@ gat_fused_mma_kernel(const float* __restrict__ x, const int32_t* __restrict__ le
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     fused_load_weights<IN, FIN>(w, Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo);
     __syncthreads();
-    float* A = bufs + warp * FUSED_SCRATCH;               // [32][RA]  16-wide rows: Wh2 / Xg / Wh4 / Yg
+    float* A = bufs + warp * FUSEDM_SCRATCH;              // [32][RA]  16-wide rows: Wh2 / Xg / Wh4 / Yg
     float* Bf = A + 32 * RA;                              // [32][RS]  72-wide rows: x / Wh1 / hp / Wh3 / hp / cat
-    float* X1s = Bf + 32 * RS;                            // [32][16]
-    float2* st = reinterpret_cast<float2*>(X1s + 32 * 16);
+    float2* st = reinterpret_cast<float2*>(Bf + 32 * RS);  // x1 rows for the group pooling live in Bf (idle then)
     int* lead_slot = reinterpret_cast<int*>(st + 32);
     const int g = lane >> 2, t = lane & 3;
 
@@ -820,8 +821,8 @@ gat_fused_mma_kernel(const float* __restrict__ x, const int32_t* __restrict__ le
         }
     };
 
-    const int n_warps_total = gridDim.x * FUSED_WARPS;
-    for (int chunk = blockIdx.x * FUSED_WARPS + warp; chunk < n_chunks; chunk += n_warps_total) {
+    const int n_warps_total = gridDim.x * FUSEDM_WARPS;
+    for (int chunk = blockIdx.x * FUSEDM_WARPS + warp; chunk < n_chunks; chunk += n_warps_total) {
         const int p0 = scene_start[chunk_scene[chunk]];
         const int np = scene_start[chunk_scene[chunk + 1]] - p0;
         const bool live = lane < np;
@@ -872,7 +873,7 @@ gat_fused_mma_kernel(const float* __restrict__ x, const int32_t* __restrict__ le
         if (live) {
             attend_mask<OUT, RA>(A, st, group_mask, st[lane].x, alpha, x1);
             elu_logsoftmax<OUT>(x1);
-            store_row<OUT>(X1s + lane * 16, x1);
+            store_row<OUT>(Bf + lane * RS, x1);
         }
         __syncwarp();
         // ---- GPool (leaders): Xg -> A rows ----
@@ -884,7 +885,7 @@ gat_fused_mma_kernel(const float* __restrict__ x, const int32_t* __restrict__ le
                 for (uint32_t mm = group_mask; mm; mm &= mm - 1) {
                     const int q = __ffs(mm) - 1;
 #pragma unroll
-                    for (int o = 0; o < OUT; ++o) xg[o] = fmaf(inv_g, X1s[q * 16 + o], xg[o]);
+                    for (int o = 0; o < OUT; ++o) xg[o] = fmaf(inv_g, Bf[q * RS + o], xg[o]);
                 }
             }
             store_row<OUT>(A + lane * RA, xg);
@@ -1182,9 +1183,10 @@ static int gat_fused_forward(const float* x, const int32_t* leader, const int32_
     const char* mode = getenv("SGX_GAT_MMA");
     if (!(mode && mode[0] == '0')) {       // default: linear maps on the tensor cores (SGX_GAT_MMA=0: CUDA-core GEMV)
         auto kern_m = gat_fused_mma_kernel<40, 24>;
-        const int smem_m = (int)(sizeof(FusedWm) + FUSED_WARPS * FUSED_SCRATCH * sizeof(float));
+        const int smem_m = (int)(sizeof(FusedWm) + FUSEDM_WARPS * FUSEDM_SCRATCH * sizeof(float));
         SGX_CUDA(cudaFuncSetAttribute(kern_m, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_m));
-        kern_m<<<grid, FUSED_WARPS * 32, smem_m, st>>>(x, leader, gsize, ps, pe, scene_start, chunk_scene, n_chunks, Wi, ai,
+        const int grid_m = std::min((n_chunks + FUSEDM_WARPS - 1) / FUSEDM_WARPS, 148);
+        kern_m<<<grid_m, FUSEDM_WARPS * 32, smem_m, st>>>(x, leader, gsize, ps, pe, scene_start, chunk_scene, n_chunks, Wi, ai,
                                                        Wio, aio, We, ae, Weo, aeo, Wo, bo, alpha, out);
         SGX_LAUNCH_CHECK();
         return SGX_OK;
