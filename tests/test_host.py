@@ -181,3 +181,47 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
     assert line['e2e'] == {'value': line['value'], 'unit': line['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert 'workload' in line['config']
+
+
+def test_schedule_build_matches_the_separate_passes():
+    """sgx_schedule_build (one pass, what SceneSchedule uses) == sgx_schedule_fill + per-ped scene index +
+    sgx_schedule_chunks, on ragged layouts with and without a scene above the chunk capacity."""
+    from group_gan_gcn_gat_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.RandomState(3)
+    for sizes in ([1], [32, 1, 31, 2], list(rng.randint(1, 15, size=500)), [5, 33, 2], [64] * 3 + [1]):
+        st = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        sse = np.ascontiguousarray(np.stack([st[:-1], st[1:]], 1))
+        S, B = len(sizes), int(st[-1])
+        stats = np.zeros(8, np.int64)
+        assert L.sgx_schedule_stats(sse.ctypes.data, S, stats.ctypes.data) == 0
+        T = max(int(stats[3]), 1)
+        mk = lambda: (np.full(S + 1, -7, np.int32), np.full(B, -7, np.int32), np.full(B, -7, np.int32),
+                      np.full(B + 1, -7, np.int64), np.full(T, -7, np.int32))
+        a, b = mk(), mk()
+        assert L.sgx_schedule_fill(sse.ctypes.data, S, *[x.ctypes.data for x in a]) == 0
+        ped_scene, chunks, n = np.full(B, -7, np.int32), np.full(S + 1, -7, np.int32), np.zeros(1, np.int64)
+        assert L.sgx_schedule_build(sse.ctypes.data, S, *[x.ctypes.data for x in b], ped_scene.ctypes.data, 32,
+                                    chunks.ctypes.data, n.ctypes.data) == 0
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+        assert np.array_equal(ped_scene, np.repeat(np.arange(S, dtype=np.int32), sizes))
+        if max(sizes) <= 32:
+            ref, m = np.full(S + 1, -7, np.int32), np.zeros(1, np.int64)
+            assert L.sgx_schedule_chunks(sse.ctypes.data, S, 32, ref.ctypes.data, m.ctypes.data) == 0
+            assert n[0] == m[0] and np.array_equal(chunks[:n[0] + 1], ref[:m[0] + 1])
+            fill = np.add.reduceat(np.asarray(sizes), chunks[:n[0]])
+            assert fill.max() <= 32
+        else:
+            assert n[0] == 0 and (chunks == -7).all()          # a scene exceeds the capacity: untouched
+
+
+def test_batch_independence_guard_of_the_folded_steps():
+    """parallel._batch_independent: folding samples / stacking fake + real is only exact without batch statistics"""
+    import torch.nn as nn
+    from group_gan_gcn_gat_b200.parallel import _batch_independent
+    assert _batch_independent(nn.Sequential(nn.Linear(4, 4), nn.ReLU(), nn.Dropout(0.0)))
+    assert not _batch_independent(nn.Sequential(nn.Linear(4, 4), nn.BatchNorm1d(4)))
+    drop = nn.Sequential(nn.Linear(4, 4), nn.Dropout(0.5))
+    assert not _batch_independent(drop.train())
+    assert _batch_independent(drop.eval())
