@@ -348,7 +348,7 @@ def gemm(a, b, relu=False):
 
 
 # ---------------------------------------------------------------------------------------------
-# fused LSTM recurrences (inference only; training keeps nn.LSTM / cuDNN under autograd)
+# fused LSTM recurrences: inference entry points (tensor-core kernel for large batches); the training path is further down
 # ---------------------------------------------------------------------------------------------
 FUSED_LSTM_H = (32, 48, 64)
 
