@@ -459,6 +459,10 @@ def main():
                          'traffic': 36.45e6 if (precision == 'bf16' and args.scenes == 1 << 16) else None,
                          'traffic_source': 'dram__bytes_read+write per launch, ncu --set full, profiles/r01_final_forward_top_kernels_ncu_full_raw.csv',
                          'peak_source': peak_src, 'kernel_ms': k_ms,
+                         'share_of_step': k_ms * K_SAMPLES / (total_ms_max / args.steps),
+                         'why_this_kernel': 'the operator SURVEY 8d gives a tensor roofline (as-written pair-MLP FLOPs); the '
+                                            'largest share of the step is the XU-bound LSTM recurrence, whose roofline '
+                                            '(MUFU/s) is in other_kernels next to the HBM-by-decree GAT',
                          'algorithmic_flops_per_launch': POOL_FLOPS_PER_PAIR * n_pairs,
                          'note': 'as-written FLOPs (57408 per ordered pair); bf16: tcgen05 GEMM1+GEMM2 with the 2->16 embedding '
                                  'folded into GEMM1; fp32: exactly factored layer 1 on CUDA cores (DESIGN.md 4.1/4.2)'},
