@@ -348,23 +348,24 @@ def main():
         out_pipe = torch.empty(args.steps + args.warmup, 2).pin_memory()
         keys = ('obs_traj', 'obs_traj_rel', 'obs_traj_g', 'pred_traj_gt')
 
-        def stage():
-            side.wait_stream(main)
+        slots = [{k: torch.empty_like(dev_in[k]) for k in keys} for _ in range(2)]    # double buffer, no allocation per step
+
+        def stage(i):
+            side.wait_stream(main)                   # slot i % 2 was last read by step i - 2, already enqueued on main
             with torch.cuda.stream(side):
-                tensors = {k: host[k].to(dev, non_blocking=True) for k in keys}
+                for k in keys:
+                    slots[i % 2][k].copy_(host[k], non_blocking=True)
                 done = torch.cuda.Event()
                 done.record(side)
-            return tensors, done
+            return slots[i % 2], done
 
         def run_pipelined(n, offset):
-            nxt = stage()
+            nxt = stage(0)
             for i in range(n):
                 cur, done = nxt
                 main.wait_event(done)
-                for t in cur.values():
-                    t.record_stream(main)
                 if i + 1 < n:
-                    nxt = stage()
+                    nxt = stage(i + 1)
                 sse = host['seq_start_end'].clone()
                 ade, fde = evaluate_batch(gen, cur['obs_traj'], cur['obs_traj_rel'], sse, cur['obs_traj_g'],
                                           cur['pred_traj_gt'], K_SAMPLES)
