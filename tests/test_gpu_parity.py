@@ -480,6 +480,40 @@ def test_lstm_tensor_core_encoder_matches_cuda_core_and_oracle(sgx):
     assert_close(tc, cc, 2e-5, 'tensor-core encoder vs CUDA-core kernel')
 
 
+def test_lstm_tensor_core_saturated_gates(sgx):
+    """The tensor-core kernel evaluates the cell update as a rational function of exponentials with clamped arguments:
+    drive the gates deep into saturation (pre-activations of a few hundred, cell states of tens) and compare with
+    torch's own LSTM on the CPU.  No NaN / Inf, same values."""
+    torch.manual_seed(23)
+    enc = sgx['MD'].Encoder(embedding_dim=16, h_dim=32, mlp_dim=64, num_layers=1)
+    with torch.no_grad():
+        for p in enc.encoder.parameters():
+            p.mul_(12.0)
+        enc.spatial_embedding.weight.mul_(6.0)
+    n = 128 * 70 + 17
+    x = torch.randn(8, n, 2) * 25.0
+    x[:, ::7] = 0.0                                      # and some exactly-zero tracks
+    import copy
+    with torch.no_grad():
+        e64 = copy.deepcopy(enc).double()
+        emb = e64.spatial_embedding(x.double().reshape(-1, 2)).view(8, n, 16)
+        ref = e64.encoder(emb)[1][0].float()             # float64 nn.LSTM on the CPU: the true value
+        emb32 = enc.spatial_embedding(x.reshape(-1, 2)).view(8, n, 16)
+        cpu32 = enc.encoder(emb32)[1][0]                 # torch's own fp32 result, for scale
+        pre = emb.abs().max()
+    assert float(pre) > 100
+    enc = enc.to(DEV)
+    with torch.no_grad():
+        tc = enc(x.to(DEV))
+        cc = _with_env('SGX_LSTM_TC', '0', lambda: enc(x.to(DEV)))
+    assert bool(torch.isfinite(tc).all()) and bool(torch.isfinite(cc).all())
+    # Unsaturated gates are differences of terms of magnitude ~300 here, so ANY fp32 evaluation carries ~1e-4 of rounding
+    # (torch's fp32 CPU LSTM included): the bar is "as accurate as fp32 gets", not the well-conditioned 2e-5.
+    e_tc, e_cc = float((tc.cpu() - ref).abs().max()), float((cc.cpu() - ref).abs().max())
+    e_cpu32 = float((cpu32 - ref).abs().max())
+    assert e_tc < 3e-4 and e_cc < 3e-4 and e_tc < 4 * max(e_cpu32, 2e-5), (e_tc, e_cc, e_cpu32)
+
+
 def test_lstm_tensor_core_decoder_matches_cuda_core(sgx):
     g = load_golden('generator_gat_zara1')
     gen = _generator(sgx, g, 'gat')
