@@ -574,6 +574,34 @@ def test_gat_encoder_chunk_boundaries(sgx, sizes):
     assert_close(out, ref, 1e-5, 'gat %s' % sizes[:3])
 
 
+@pytest.mark.parametrize('scale', [1e-3, 30.0])
+def test_graph_kernels_tensor_core_splits_at_extreme_magnitudes(sgx, scale):
+    """The single-launch GAT / GCN forwards run their linear maps as 3xTF32 tensor-core GEMMs (operands split hi + lo):
+    tiny and large activations (softmax saturation, log-softmax of large logits, ReLU sums of large terms) must still
+    match the fp32 oracle to the 1e-5 contract relative to the output scale."""
+    rng = np.random.RandomState(9)
+    torch.manual_seed(9)
+    sizes = [3, 32, 7, 1, 19, 12, 28, 4]
+    sse = sse_from_sizes(sizes)
+    n = sum(sizes)
+    labs = torch.tensor(np.where(rng.rand(n) < 0.2, 0, rng.randint(1, 4, size=n)), dtype=torch.float32).view(-1, 1)
+    x, pos = torch.randn(n, 40) * scale, torch.rand(n, 2)
+    gat = sgx['M'].GATEncoder(n_units=None, n_heads=1, dropout=0, alpha=0.2)
+    gcn = sgx['M'].GCNModule(input_dim=40, hidden_dim=72, out_dim=16, gcn_layers=2, final_dim=24)
+    with torch.no_grad():
+        for p in gcn.parameters():
+            if p.dim() == 2 and p.shape[0] != 24:
+                p.mul_(0.15)
+    ref_gat = O.gat_encoder(x, sse, pos, labs, gat.state_dict(), '', 0.2, 1)
+    ref_gcn = O.gcn_module(x, sse, pos, labs, gcn.state_dict(), '')
+    with torch.no_grad():
+        out_gat = gat.to(DEV)(x.to(DEV), sse.to(DEV), pos.to(DEV), labs.to(DEV))
+        out_gcn = gcn.to(DEV)(x.to(DEV), sse.to(DEV), pos.to(DEV), labs.to(DEV))
+    assert bool(torch.isfinite(out_gat).all()) and bool(torch.isfinite(out_gcn).all())
+    assert_close(out_gat, ref_gat, 1e-5, 'gat at scale %g' % scale)
+    assert_close(out_gcn, ref_gcn, 1e-5, 'gcn at scale %g' % scale)
+
+
 @pytest.mark.parametrize('sizes,in_dim,final', [([32], 40, 24), ([32, 32, 1], 32, 24), ([33], 40, 24),
                                                 ([31, 2, 32, 1, 1, 30], 40, 32), ([1] * 70, 32, 32)])
 def test_gcn_module_chunk_boundaries(sgx, sizes, in_dim, final):
