@@ -68,7 +68,8 @@ int sgx_profile_events(void* ev_start, void* ev_stop);
 int sgx_schedule_stats(const int64_t* h_seq_start_end, int64_t n_scenes, int64_t* h_stats);
 int sgx_schedule_fill(const int64_t* h_seq_start_end, int64_t n_scenes, int32_t* h_scene_start,
                       int32_t* h_ped_start, int32_t* h_ped_end, int64_t* h_pair_off, int32_t* h_tile_first);
-/* sgx_schedule_fill + h_ped_scene int32 [batch] (scene index of every pedestrian) + the chunk boundaries of
+/* sgx_schedule_fill + h_ped_scene int32 [batch] (scene index of every pedestrian: the per-scene -> per-ped repeat of
+ * add_noise, sgan/models.py:837-846, and of evaluate_helper, scripts/evaluate_model.py:58-69) + the chunk boundaries of
  * sgx_schedule_chunks(cap = chunk_cap) in one pass; *h_n_chunks = 0 (chunk_scene untouched) when a scene exceeds
  * chunk_cap or h_chunk_scene is null. */
 int sgx_schedule_build(const int64_t* h_seq_start_end, int64_t n_scenes, int32_t* h_scene_start,
