@@ -177,7 +177,7 @@ def cpu_port_traj_per_sec(n_scenes, k_samples, seed, reps=1):
 def run_reference(args, rank):
     if rank != 0:
         return
-    n_scenes = 256
+    n_scenes = args.ref_scenes
     for _ in range(args.warmup):
         cpu_port_traj_per_sec(16, 2, 1)
     t0 = time.perf_counter()
@@ -217,6 +217,7 @@ def main():
     ap.add_argument('--scenes', type=int, default=1 << 16, help='scenes per GPU per step')
     ap.add_argument('--precision', default=os.environ.get('SGX_POOL_PRECISION', 'auto'))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--ref-scenes', type=int, default=256, help='scenes per step of the --impl reference arm')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
