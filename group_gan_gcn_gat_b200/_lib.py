@@ -18,6 +18,7 @@ SGX_ERR_CUDA = -3
 
 PRECISION_FP32 = 0
 PRECISION_BF16 = 1
+PRECISION_TC32 = 2
 
 _P = ctypes.c_void_p
 _I64 = ctypes.c_int64
@@ -41,6 +42,11 @@ SIGNATURES = {
     'sgx_pool_ws_bytes': (_I64, [_I64, _I32, _I32, _I32, _I32]),
     'sgx_pool_fwd': (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32,
                                     _I32, _P, _P, _P, _I64, _P]),
+    'sgx_pool_prep_bytes': (_I64, [_I32, _I32, _I32, _I32]),
+    'sgx_pool_prep': (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P, _I64, _P]),
+    'sgx_pool_fwd_prepped': (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32,
+                                            _I32, _P, _P, _P, _P, _I64, _P]),
+    'sgx_pool_tc32_available': (ctypes.c_int, [_I32, _I32, _I32]),
     'sgx_pool_bwd_ws_bytes': (_I64, [_I64, _I32, _I32, _I32]),
     'sgx_pool_bwd': (ctypes.c_int, [_P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _P, _P, _P,
                                     _P, _P, _P, _P, _P, _P, _I64, _P]),

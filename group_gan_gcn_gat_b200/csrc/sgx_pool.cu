@@ -108,7 +108,7 @@ pool_pair_kernel(const float* __restrict__ Ct, int64_t ldc, const float* __restr
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             float z = fmaf(a.x, dx[r], fmaf(a.y, dy[r], __ldg(cptr[r] + (int64_t)k * ldc)));
-            z = fmaxf(z, 0.f);
+            asm("max.NaN.f32 %0, %0, 0f00000000;" : "+f"(z));     // ReLU that keeps a NaN (FMNMX.NAN), like torch.relu
 #pragma unroll
             for (int c = 0; c < BC; ++c) acc[r][c] = fmaf(w[c], z, acc[r][c]);
         }
@@ -128,9 +128,10 @@ pool_pair_kernel(const float* __restrict__ Ct, int64_t ldc, const float* __restr
         }
 #pragma unroll
         for (int c = 0; c < BC; ++c) {
-            float y = fmaxf(acc[r][c] + b2[cb + c], 0.f);
-            unsigned long long pk =
-                ((unsigned long long)(__float_as_uint(y) & 0x7fffffffu) << 32) | (unsigned)ped_j[r];
+            // a NaN keeps its (canonical) bit pattern: it orders above every finite value, like torch.max
+            const float y = acc[r][c] + b2[cb + c];
+            const unsigned ybits = (y != y) ? 0x7fc00000u : (__float_as_uint(fmaxf(y, 0.f)) & 0x7fffffffu);
+            unsigned long long pk = ((unsigned long long)ybits << 32) | (unsigned)ped_j[r];
 #pragma unroll
             for (int sft = 0; sft < 5; ++sft) {
                 const unsigned long long other = __shfl_down_sync(0xffffffffu, pk, 1 << sft);
@@ -286,48 +287,105 @@ static int64_t ldc_for(int64_t batch) { return align_up(batch, 32); }
 
 using namespace sgx;
 
-// implemented in sgx_pool_tc.cu
-int sgx_pool_fwd_bf16(const float* h, const float* pos, const int32_t* ped_start, const int64_t* pair_off,
-                      const int32_t* tile_first, int64_t batch, int64_t n_pairs, const float* We, const float* be,
-                      const float* W1, const float* b1, const float* W2, const float* b2, int E, int H, int B,
-                      unsigned long long* packed, void* ws, int64_t ws_bytes, cudaStream_t st);
+// implemented in sgx_pool_tc.cu (bf16 operands) and sgx_pool_tc32.cu (fp16 hi/lo operand splits)
+int64_t sgx_pool_bf16_prep_bytes(int E, int H, int B);
 int64_t sgx_pool_bf16_ws_bytes(int64_t batch, int E, int H, int B);
+int sgx_pool_bf16_prep(const float* We, const float* be, const float* W1, const float* b1, const float* W2, int E, int H,
+                       int B, void* prep, cudaStream_t st);
+int sgx_pool_fwd_bf16(const float* h, const float* pos, const int32_t* ped_start, const int64_t* pair_off,
+                      const int32_t* tile_first, int64_t batch, int64_t n_pairs, const void* prep, const float* b2, int E,
+                      int H, int B, unsigned long long* packed, void* ws, cudaStream_t st);
+bool sgx_pool_tc32_supported(int E, int H, int B);
+int64_t sgx_pool_tc32_prep_bytes(int E, int H, int B);
+int64_t sgx_pool_tc32_ws_bytes(int64_t batch, int H);
+int sgx_pool_tc32_prep(const float* We, const float* be, const float* W1, const float* b1, const float* W2, int E, int H,
+                       int B, void* prep, cudaStream_t st);
+int sgx_pool_fwd_tc32(const float* h, const float* pos, const int32_t* ped_start, const int64_t* pair_off,
+                      const int32_t* tile_first, int64_t batch, int64_t n_pairs, const void* prep, const float* b2, int E,
+                      int H, int B, unsigned long long* packed, void* ws, cudaStream_t st);
 
-extern "C" int64_t sgx_pool_ws_bytes(int64_t batch, int32_t E, int32_t H, int32_t B, int32_t precision) {
-    int64_t packed = align_up(batch * B * 8, 256);
-    if (precision == SGX_PRECISION_BF16) return packed + sgx_pool_bf16_ws_bytes(batch, E, H, B);
-    return packed + align_up(ldc_for(batch) * HID * 4, 256) + align_up(HID * 8, 256) + align_up(HID * 4, 256);
+// Prepared weights: everything that depends on the parameters only (folded first layer, operand images of the
+// tensor-core kernels).  Built once per weight version by sgx_pool_prep; sgx_pool_fwd builds it into its workspace.
+extern "C" int64_t sgx_pool_prep_bytes(int32_t E, int32_t H, int32_t B, int32_t precision) {
+    if (precision == SGX_PRECISION_BF16) return sgx_pool_bf16_prep_bytes(E, H, B);
+    if (precision == SGX_PRECISION_TC32) return sgx_pool_tc32_prep_bytes(E, H, B);
+    return align_up(HID * 8, 256) + align_up(HID * 4, 256);
 }
 
-extern "C" int sgx_pool_fwd(const float* h, const float* pos, const int32_t* ped_start, const int32_t* ped_end,
-                            const int64_t* pair_off, const int32_t* tile_first, int64_t batch, int64_t n_pairs,
-                            const float* We, const float* be, const float* W1, const float* b1, const float* W2,
-                            const float* b2, int32_t E, int32_t H, int32_t B, int32_t precision, float* out,
-                            int32_t* argmax, void* workspace, int64_t ws_bytes, void* stream) {
+extern "C" int sgx_pool_prep(const float* We, const float* be, const float* W1, const float* b1, const float* W2,
+                             const float* b2, int32_t E, int32_t H, int32_t B, int32_t precision, void* prep,
+                             int64_t prep_bytes, void* stream) {
+    (void)b2;
+    SGX_REQUIRE(We && be && W1 && b1 && W2 && prep, "sgx_pool_prep: null pointer");
+    int rc = check_dims(E, H, B);
+    if (rc) return rc;
+    SGX_REQUIRE(precision >= SGX_PRECISION_FP32 && precision <= SGX_PRECISION_TC32, "sgx_pool_prep: unknown precision %d",
+                precision);
+    SGX_REQUIRE(prep_bytes >= sgx_pool_prep_bytes(E, H, B, precision), "sgx_pool_prep: buffer too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (precision == SGX_PRECISION_BF16) return sgx_pool_bf16_prep(We, be, W1, b1, W2, E, H, B, prep, st);
+    if (precision == SGX_PRECISION_TC32) return sgx_pool_tc32_prep(We, be, W1, b1, W2, E, H, B, prep, st);
+    Carver c(prep);
+    float2* Aeff = c.take<float2>(HID);
+    float* c0 = c.take<float>(HID);
+    pool_prep_kernel<<<2, 256, 0, st>>>(We, be, W1, b1, E, H, Aeff, c0);
+    SGX_LAUNCH_CHECK();
+    return SGX_OK;
+}
+
+// workspace: [packed | 256 B of per-call statistics (zeroed with packed) | precision-specific | room for prepared weights]
+static int64_t pool_call_ws(int64_t batch, int E, int H, int B, int precision) {
+    int64_t n = align_up(batch * B * 8, 256) + 256;
+    if (precision == SGX_PRECISION_BF16) return n + sgx_pool_bf16_ws_bytes(batch, E, H, B);
+    if (precision == SGX_PRECISION_TC32) return n + sgx_pool_tc32_ws_bytes(batch, H) - 256;
+    return n + align_up(ldc_for(batch) * HID * 4, 256);
+}
+
+extern "C" int64_t sgx_pool_ws_bytes(int64_t batch, int32_t E, int32_t H, int32_t B, int32_t precision) {
+    return pool_call_ws(batch, E, H, B, precision) + sgx_pool_prep_bytes(E, H, B, precision);
+}
+
+extern "C" int sgx_pool_fwd_prepped(const float* h, const float* pos, const int32_t* ped_start, const int32_t* ped_end,
+                                    const int64_t* pair_off, const int32_t* tile_first, int64_t batch, int64_t n_pairs,
+                                    const float* We, const float* be, const float* W1, const float* b1, const float* W2,
+                                    const float* b2, int32_t E, int32_t H, int32_t B, int32_t precision,
+                                    const void* prep, float* out, int32_t* argmax, void* workspace, int64_t ws_bytes,
+                                    void* stream) {
     (void)ped_end;
     SGX_REQUIRE(h && pos && ped_start && pair_off && tile_first && We && be && W1 && b1 && W2 && b2 && out && workspace,
                 "sgx_pool_fwd: null pointer");
     SGX_REQUIRE(batch > 0 && n_pairs >= batch, "sgx_pool_fwd: bad batch/n_pairs");
     int rc = check_dims(E, H, B);
     if (rc) return rc;
-    SGX_REQUIRE(ws_bytes >= sgx_pool_ws_bytes(batch, E, H, B, precision), "sgx_pool_fwd: workspace too small");
+    SGX_REQUIRE(precision >= SGX_PRECISION_FP32 && precision <= SGX_PRECISION_TC32, "sgx_pool_fwd: unknown precision %d",
+                precision);
+    SGX_REQUIRE(ws_bytes >= pool_call_ws(batch, E, H, B, precision) + (prep ? 0 : sgx_pool_prep_bytes(E, H, B, precision)),
+                "sgx_pool_fwd: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     Carver ws(workspace);
     unsigned long long* packed = ws.take<unsigned long long>(batch * B);
-    SGX_CUDA(cudaMemsetAsync(packed, 0, (size_t)batch * B * 8, st));
+    unsigned* stat = ws.take<unsigned>(64);
+    SGX_CUDA(cudaMemsetAsync(packed, 0, (size_t)((char*)stat - (char*)packed) + 256, st));
+    if (!prep) {   // weights not prepared by the caller: build the images behind the per-call regions
+        void* own = ws.base + pool_call_ws(batch, E, H, B, precision);
+        rc = sgx_pool_prep(We, be, W1, b1, W2, b2, E, H, B, precision, own, sgx_pool_prep_bytes(E, H, B, precision), stream);
+        if (rc) return rc;
+        prep = own;
+    }
     const int64_t n_tiles128 = (n_pairs + 127) / 128;
     if (precision == SGX_PRECISION_BF16) {
-        rc = sgx_pool_fwd_bf16(h, pos, ped_start, pair_off, tile_first, batch, n_pairs, We, be, W1, b1, W2, b2, E, H, B,
-                               packed, ws.base + ws.off, ws_bytes - ws.off, st);
+        rc = sgx_pool_fwd_bf16(h, pos, ped_start, pair_off, tile_first, batch, n_pairs, prep, b2, E, H, B, packed,
+                               ws.base + ws.off, st);
+        if (rc) return rc;
+    } else if (precision == SGX_PRECISION_TC32) {
+        rc = sgx_pool_fwd_tc32(h, pos, ped_start, pair_off, tile_first, batch, n_pairs, prep, b2, E, H, B, packed, stat, st);
         if (rc) return rc;
     } else {
-        SGX_REQUIRE(precision == SGX_PRECISION_FP32, "sgx_pool_fwd: unknown precision %d", precision);
         const int64_t ldc = ldc_for(batch);
         float* Ct = ws.take<float>(ldc * HID);
-        float2* Aeff = ws.take<float2>(HID);
-        float* c0 = ws.take<float>(HID);
-        pool_prep_kernel<<<2, 256, 0, st>>>(We, be, W1, b1, E, H, Aeff, c0);
-        SGX_LAUNCH_CHECK();
+        Carver pc(const_cast<void*>(prep));
+        const float2* Aeff = pc.take<float2>(HID);
+        const float* c0 = pc.take<float>(HID);
         // C^T[k][p] = c0[k] + sum_h W1[k][E+h] * h[p][h]
         rc = gemm(W1 + E, E + H, 1, h, 1, H, Ct, ldc, HID, batch, H, 0, 0, st, c0);
         if (rc) return rc;
@@ -351,6 +409,20 @@ extern "C" int sgx_pool_fwd(const float* h, const float* pos, const int32_t* ped
     pool_unpack_kernel<<<blocks_for(batch * B, 256), 256, 0, st>>>(packed, batch * B, out, argmax);
     SGX_LAUNCH_CHECK();
     return SGX_OK;
+}
+
+extern "C" int sgx_pool_fwd(const float* h, const float* pos, const int32_t* ped_start, const int32_t* ped_end,
+                            const int64_t* pair_off, const int32_t* tile_first, int64_t batch, int64_t n_pairs,
+                            const float* We, const float* be, const float* W1, const float* b1, const float* W2,
+                            const float* b2, int32_t E, int32_t H, int32_t B, int32_t precision, float* out,
+                            int32_t* argmax, void* workspace, int64_t ws_bytes, void* stream) {
+    return sgx_pool_fwd_prepped(h, pos, ped_start, ped_end, pair_off, tile_first, batch, n_pairs, We, be, W1, b1, W2, b2,
+                                E, H, B, precision, nullptr, out, argmax, workspace, ws_bytes, stream);
+}
+
+/* 1 when precision TC32 has a kernel for these dims on the current device */
+extern "C" int sgx_pool_tc32_available(int32_t E, int32_t H, int32_t B) {
+    return (sgx_has_tcgen05() && sgx_pool_tc32_supported(E, H, B)) ? 1 : 0;
 }
 
 extern "C" int64_t sgx_pool_bwd_ws_bytes(int64_t batch, int32_t E, int32_t H, int32_t B) {

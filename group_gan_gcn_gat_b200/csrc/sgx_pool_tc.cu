@@ -350,7 +350,9 @@ pool_tc_kernel(const __nv_bfloat16* __restrict__ hb, const float* __restrict__ p
                         mbar_arrive(&d2_free[db]);
                     }
                     auto column_bits = [&](int c) {     // c: column inside the group
-                        return __float_as_uint(fmaxf(__uint_as_float(v[c]) + bias2[16 * g + c], 0.f)) & 0x7fffffffu;
+                        // a NaN keeps its (canonical) bit pattern: it orders above every finite value, like torch.max
+                        const float y = __uint_as_float(v[c]) + bias2[16 * g + c];
+                        return (y != y) ? 0x7fc00000u : (__float_as_uint(fmaxf(y, 0.f)) & 0x7fffffffu);
                     };
                     // The uniform / segmented choice sits outside the column loops: with the branch inside, every
                     // column was its own basic block and the dependent shuffle chains ran one after the other.
@@ -496,27 +498,34 @@ using namespace sgx;
 
 static int n2_for(int B) { return B <= 16 ? 16 : 48; }
 
+// prepared weights (per weight version): [W1p | W2p | Aeff | c0]
+int64_t sgx_pool_bf16_prep_bytes(int E, int H, int B) {
+    (void)E; (void)H;
+    return align_up(HID * 128, 256) + align_up(8 * n2_for(B) * 128, 256) + align_up(HID * 8, 256) + align_up(HID * 4, 256);
+}
 int64_t sgx_pool_bf16_ws_bytes(int64_t batch, int E, int H, int B) {
-    (void)E;
-    return align_up(batch * H * 2, 256) + align_up(HID * 128, 256) + align_up(8 * n2_for(B) * 128, 256) +
-           align_up(HID * 8, 256) + align_up(HID * 4, 256);
+    (void)E; (void)B;
+    return align_up(batch * H * 2, 256);
 }
 
-extern "C" int sgx_has_tcgen05(void) { return 1; }
+// 1 when the current device can run the tcgen05 kernels of this build (compute capability 10.x)
+extern "C" int sgx_has_tcgen05(void) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+    return major == 10 ? 1 : 0;
+}
 extern "C" void sgx_debug_tc_stats(void* dev_buf) { sgx::g_tc_stats = (long long*)dev_buf; }
 
-int sgx_pool_fwd_bf16(const float* h, const float* pos, const int32_t* ped_start, const int64_t* pair_off,
-                      const int32_t* tile_first, int64_t batch, int64_t n_pairs, const float* We, const float* be,
-                      const float* W1, const float* b1, const float* W2, const float* b2, int E, int H, int B,
-                      unsigned long long* packed, void* ws, int64_t ws_bytes, cudaStream_t st) {
-    SGX_UNSUPPORTED(!((H == 32 && B == 8) || (H == 48 && B == 48)),
+static bool bf16_supported(int H, int B) { return (H == 32 && B == 8) || (H == 48 && B == 48); }
+
+int sgx_pool_bf16_prep(const float* We, const float* be, const float* W1, const float* b1, const float* W2, int E, int H,
+                       int B, void* prep, cudaStream_t st) {
+    SGX_UNSUPPORTED(!bf16_supported(H, B),
                     "bf16 tensor-core pooling is built for (h_dim, bottleneck) in {(32,8), (48,48)}; got (%d,%d) -- "
                     "use precision fp32", H, B);
-    SGX_REQUIRE(ws_bytes >= sgx_pool_bf16_ws_bytes(batch, E, H, B), "sgx_pool_fwd_bf16: workspace too small");
-    SGX_REQUIRE(n_pairs < ((int64_t)1 << 40), "sgx_pool_fwd_bf16: too many pairs");
     const int N2 = n2_for(B);
-    Carver c(ws);
-    __nv_bfloat16* hb = c.take<__nv_bfloat16>(batch * H);
+    Carver c(prep);
     __nv_bfloat16* W1p = c.take<__nv_bfloat16>(HID * 64);
     __nv_bfloat16* W2p = c.take<__nv_bfloat16>(8 * N2 * 64);
     float2* Aeff = c.take<float2>(HID);
@@ -525,14 +534,33 @@ int sgx_pool_fwd_bf16(const float* h, const float* pos, const int32_t* ped_start
     SGX_LAUNCH_CHECK();
     tc_prep_w_kernel<<<blocks_for(HID * 64, 256), 256, 0, st>>>(Aeff, c0, W1, W2, E, H, B, N2, W1p, W2p);
     SGX_LAUNCH_CHECK();
+    return SGX_OK;
+}
+
+int sgx_pool_fwd_bf16(const float* h, const float* pos, const int32_t* ped_start, const int64_t* pair_off,
+                      const int32_t* tile_first, int64_t batch, int64_t n_pairs, const void* prep, const float* b2, int E,
+                      int H, int B, unsigned long long* packed, void* ws, cudaStream_t st) {
+    (void)E;
+    SGX_UNSUPPORTED(!bf16_supported(H, B),
+                    "bf16 tensor-core pooling is built for (h_dim, bottleneck) in {(32,8), (48,48)}; got (%d,%d) -- "
+                    "use precision fp32", H, B);
+    SGX_REQUIRE(n_pairs < ((int64_t)1 << 40), "sgx_pool_fwd_bf16: too many pairs");
+    const int N2 = n2_for(B);
+    Carver pc(const_cast<void*>(prep));
+    const __nv_bfloat16* W1p = pc.take<__nv_bfloat16>(HID * 64);
+    const __nv_bfloat16* W2p = pc.take<__nv_bfloat16>(8 * N2 * 64);
+    Carver c(ws);
+    __nv_bfloat16* hb = c.take<__nv_bfloat16>(batch * H);
     tc_prep_h_kernel<<<blocks_for(batch * H / 8, 256), 256, 0, st>>>(h, batch * H / 8, hb);
     SGX_LAUNCH_CHECK();
     const int64_t n_tiles = (n_pairs + TILE - 1) / TILE;
-    const char* mode = getenv("SGX_POOL_TC_MODE");
-    const bool ss = mode && mode[0] == 's';
     if (H == 32) {
-        if (ss) return launch_tc<32, 8, 16, false>(hb, pos, ped_start, pair_off, tile_first, n_tiles, (int)batch, n_pairs,
-                                                   W1p, W2p, b2, packed, st);
+#ifdef SGX_AB_VARIANTS   // A/B build only: GEMM2 A operand staged in shared memory instead of TMEM
+        const char* mode = getenv("SGX_POOL_TC_MODE");
+        if (mode && mode[0] == 's')
+            return launch_tc<32, 8, 16, false>(hb, pos, ped_start, pair_off, tile_first, n_tiles, (int)batch, n_pairs,
+                                               W1p, W2p, b2, packed, st);
+#endif
         return launch_tc<32, 8, 16, true>(hb, pos, ped_start, pair_off, tile_first, n_tiles, (int)batch, n_pairs, W1p,
                                           W2p, b2, packed, st);
     }

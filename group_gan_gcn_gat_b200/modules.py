@@ -40,20 +40,37 @@ def make_mlp(dim_list, activation='relu', batch_norm=True, dropout=0):
     return nn.Sequential(*mods)
 
 
-def _precision_code(name):
+POOL_PRECISIONS = ('fp32', 'fp32-simt', 'tc32', 'bf16')
+
+
+def resolve_pool_precision(name, embedding_dim, h_dim, bottleneck_dim):
+    """Precision name -> code of include/sgx.h.
+
+    'fp32' (the default, 1e-5 contract): the tcgen05 kernel with fp16 hi/lo operand splits ('tc32') where it is built
+    for the dims -- (h_dim, bottleneck_dim) = (32, 8), the generator's pool_net of every shipped checkpoint -- and
+    the CUDA-core kernel otherwise; 'fp32-simt' forces the CUDA-core kernel, 'tc32' the tensor-core one (raises for
+    other dims); 'bf16' (2e-2 pooled features) is the bf16-operand tensor-core kernel.
+    """
     name = (name or 'fp32').lower()
     if name in ('fp32', 'float32'):
+        from . import _lib
+        ok = _lib.lib().sgx_pool_tc32_available(int(embedding_dim), int(h_dim), int(bottleneck_dim))
+        return ops.PRECISION_TC32 if ok else ops.PRECISION_FP32
+    if name in ('fp32-simt', 'fp32_simt', 'simt'):
         return ops.PRECISION_FP32
+    if name in ('tc32', 'fp32-tc', 'split'):
+        return ops.PRECISION_TC32
     if name in ('bf16', 'bfloat16'):
         return ops.PRECISION_BF16
-    raise ValueError('unknown pooling precision %r (fp32 | bf16)' % (name,))
+    raise ValueError('unknown pooling precision %r (%s)' % (name, ' | '.join(POOL_PRECISIONS)))
 
 
 class PoolHiddenNet(nn.Module):
     """Pairwise social pooling (sgan/models.py:458-549), fused: no N^2 x 512 tensor is materialised.
 
-    ``precision``: 'fp32' (CUDA cores, 1e-5 parity, default) or 'bf16' (tcgen05 tensor cores, 2e-2);
-    can also be set process-wide with SGX_POOL_PRECISION.
+    ``precision``: 'fp32' (default; 1e-5 parity -- tensor cores with fp16 hi/lo operand splits for the generator
+    dims, CUDA cores otherwise), 'fp32-simt', 'tc32' or 'bf16' (tcgen05 with bf16 operands, 2e-2); see
+    ``resolve_pool_precision``.  Can also be set process-wide with SGX_POOL_PRECISION.
     """
 
     def __init__(self, embedding_dim=64, h_dim=64, mlp_dim=1024, bottleneck_dim=1024, activation='relu',
@@ -85,10 +102,23 @@ class PoolHiddenNet(nn.Module):
         h = h_states.reshape(-1, self.h_dim)
         if h.shape[0] != sched.batch:
             raise ValueError('h_states has %d rows but seq_start_end covers %d pedestrians' % (h.shape[0], sched.batch))
+        params = (self.spatial_embedding.weight, self.spatial_embedding.bias, l1.weight, l1.bias, l2.weight, l2.bias)
+        code = resolve_pool_precision(self.precision, self.embedding_dim, self.h_dim, self.bottleneck_dim)
         out, _ = ops.call(ops.pool_fwd, h, end_pos, sched.ped_start, sched.ped_end, sched.pair_off, sched.tile_first,
-                              sched.n_pairs, self.spatial_embedding.weight, self.spatial_embedding.bias,
-                              l1.weight, l1.bias, l2.weight, l2.bias, _precision_code(self.precision))
+                          sched.n_pairs, *params, code, self._prepared(params, code))
         return out
+
+    def _prepared(self, params, code):
+        """Folded first layer + tensor-core operand images, rebuilt only when a parameter changed (version counter /
+        storage) -- three small launches per call otherwise, 13 calls per forward with per-step pooling."""
+        key = (code,) + tuple((p.data_ptr(), p._version, p.device) for p in params)
+        cached = getattr(self, '_prep_cache', None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        with torch.no_grad():
+            buf = ops.pool_prep(*params, code, out=None if cached is None else cached[1])
+        object.__setattr__(self, '_prep_cache', (key, buf))
+        return buf
 
 
 def _groups_for(sched, end_group):

@@ -5,13 +5,13 @@ device pointers + the current CUDA stream to libsgx_b200.so and returns.  Autogr
 with ``register_autograd`` and calls the matching ``*_bwd`` entry point.  There is no eager/CPU
 fallback: tensors must be CUDA fp32 and the library must be present.
 """
-from typing import List, Tuple
+from typing import List, Optional, Tuple
 
 import torch
 from torch import Tensor
 
 from . import _lib
-from ._lib import PRECISION_BF16, PRECISION_FP32  # noqa: F401
+from ._lib import PRECISION_BF16, PRECISION_FP32, PRECISION_TC32  # noqa: F401
 
 
 def _ptr(t):
@@ -51,18 +51,30 @@ def _ws(nbytes, device):
     return buf
 
 
+_DIRECT = {}
+
+
+def _custom_op(name):
+    """torch.library.custom_op that also remembers the plain python body of the op (see ``call``)."""
+    def deco(fn):
+        op = torch.library.custom_op(name, mutates_args=())(fn)
+        _DIRECT[op] = fn
+        return op
+    return deco
+
+
 def call(op, *args):
     """Dispatch through torch.library only when autograd needs it; otherwise call the op body directly (the
     dispatcher + custom_op wrapper costs ~100 us per call, more than some of the kernels)."""
     if torch.is_grad_enabled() and any(torch.is_tensor(a) and a.requires_grad for a in args):
         return op(*args)
-    return op._init_fn(*args)
+    return _DIRECT[op](*args)
 
 
 # ---------------------------------------------------------------------------------------------
 # group structure
 # ---------------------------------------------------------------------------------------------
-@torch.library.custom_op('sgx::group_ids', mutates_args=())
+@_custom_op('sgx::group_ids')
 def group_ids(labels: Tensor, ped_start: Tensor, ped_end: Tensor, scene_start: Tensor) -> List[Tensor]:
     """-> [leader, group_size, group_id, n_group] (int32).  sgan/models.py:263-278."""
     labels = _f32(labels.reshape(-1), 'labels')
@@ -108,10 +120,25 @@ def group_dense(labels, groups, start, end):
 # ---------------------------------------------------------------------------------------------
 # PoolHiddenNet
 # ---------------------------------------------------------------------------------------------
-@torch.library.custom_op('sgx::pool_fwd', mutates_args=())
+def pool_prep(We, be, W1, b1, W2, b2, precision, out=None):
+    """Prepared weights of PoolHiddenNet for one precision (folded first layer, tensor-core operand images): a uint8
+    buffer to pass as ``prep`` to pool_fwd while the parameters stay unchanged.  ``out``: buffer to refill."""
+    ws = [_f32(t.detach(), n) for t, n in zip((We, be, W1, b1, W2, b2), ('We', 'be', 'W1', 'b1', 'W2', 'b2'))]
+    E, B, H = We.shape[0], W2.shape[0], W1.shape[1] - We.shape[0]
+    L = _lib.lib()
+    nbytes = L.sgx_pool_prep_bytes(E, H, B, precision)
+    if out is None or out.numel() < nbytes or out.device != We.device:
+        out = torch.empty(nbytes, dtype=torch.uint8, device=We.device)
+    with torch.cuda.device(We.device):
+        _lib.check(L.sgx_pool_prep(*[_ptr(t) for t in ws], E, H, B, precision, _ptr(out), out.numel(), _stream(We)),
+                   'sgx_pool_prep')
+    return out
+
+
+@_custom_op('sgx::pool_fwd')
 def pool_fwd(h: Tensor, pos: Tensor, ped_start: Tensor, ped_end: Tensor, pair_off: Tensor, tile_first: Tensor,
              n_pairs: int, We: Tensor, be: Tensor, W1: Tensor, b1: Tensor, W2: Tensor, b2: Tensor,
-             precision: int) -> Tuple[Tensor, Tensor]:
+             precision: int, prep: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
     h, pos = _f32(h, 'h_states'), _f32(pos, 'end_pos')
     We, be, W1, b1, W2, b2 = (_f32(t, n) for t, n in zip((We, be, W1, b1, W2, b2), ('We', 'be', 'W1', 'b1', 'W2', 'b2')))
     batch, H = h.shape
@@ -124,21 +151,24 @@ def pool_fwd(h: Tensor, pos: Tensor, ped_start: Tensor, ped_end: Tensor, pair_of
     out = torch.empty(batch, B, dtype=torch.float32, device=dev)
     arg = torch.empty(batch, B, dtype=torch.int32, device=dev)
     L = _lib.lib()
+    if prep is not None and prep.numel() < L.sgx_pool_prep_bytes(E, H, B, precision):
+        raise ValueError('pool_fwd: prepared-weight buffer too small for these dims / precision')
     nbytes = L.sgx_pool_ws_bytes(batch, E, H, B, precision)
     ws = _ws(nbytes, dev)
     with torch.cuda.device(dev):
-        _lib.check(L.sgx_pool_fwd(_ptr(h), _ptr(pos), _ptr(ped_start), _ptr(ped_end), _ptr(pair_off), _ptr(tile_first),
-                                  batch, n_pairs, _ptr(We), _ptr(be), _ptr(W1), _ptr(b1), _ptr(W2), _ptr(b2), E, H, B,
-                                  precision, _ptr(out), _ptr(arg), _ptr(ws), ws.numel(), _stream(h)), 'sgx_pool_fwd')
+        _lib.check(L.sgx_pool_fwd_prepped(_ptr(h), _ptr(pos), _ptr(ped_start), _ptr(ped_end), _ptr(pair_off),
+                                          _ptr(tile_first), batch, n_pairs, _ptr(We), _ptr(be), _ptr(W1), _ptr(b1),
+                                          _ptr(W2), _ptr(b2), E, H, B, precision, _ptr(prep), _ptr(out), _ptr(arg),
+                                          _ptr(ws), ws.numel(), _stream(h)), 'sgx_pool_fwd')
     return out, arg
 
 
 @pool_fwd.register_fake
-def _(h, pos, ped_start, ped_end, pair_off, tile_first, n_pairs, We, be, W1, b1, W2, b2, precision):
+def _(h, pos, ped_start, ped_end, pair_off, tile_first, n_pairs, We, be, W1, b1, W2, b2, precision, prep=None):
     return (h.new_empty(h.shape[0], W2.shape[0]), torch.empty(h.shape[0], W2.shape[0], dtype=torch.int32, device=h.device))
 
 
-@torch.library.custom_op('sgx::pool_bwd', mutates_args=())
+@_custom_op('sgx::pool_bwd')
 def pool_bwd(h: Tensor, pos: Tensor, out: Tensor, argmax: Tensor, grad_out: Tensor, We: Tensor, be: Tensor,
              W1: Tensor, b1: Tensor, W2: Tensor, b2: Tensor) -> List[Tensor]:
     h, pos, out, grad_out = _f32(h, 'h'), _f32(pos, 'pos'), _f32(out, 'out'), _f32(grad_out, 'grad_out')
@@ -164,7 +194,7 @@ def _(h, pos, out, argmax, grad_out, We, be, W1, b1, W2, b2):
 
 
 def _pool_setup(ctx, inputs, output):
-    h, pos, _ps, _pe, _po, _tf, _np, We, be, W1, b1, W2, b2, _prec = inputs
+    h, pos, _ps, _pe, _po, _tf, _np, We, be, W1, b1, W2, b2, _prec, _prep = inputs
     out, arg = output
     ctx.save_for_backward(h, pos, out, arg, We, be, W1, b1, W2, b2)
 
@@ -172,7 +202,7 @@ def _pool_setup(ctx, inputs, output):
 def _pool_backward(ctx, grad_out, _grad_arg):
     h, pos, out, arg, We, be, W1, b1, W2, b2 = ctx.saved_tensors
     gh, gpos, gWe, gbe, gW1, gb1, gW2, gb2 = pool_bwd(h, pos, out, arg, grad_out.contiguous(), We, be, W1, b1, W2, b2)
-    return gh, gpos, None, None, None, None, None, gWe, gbe, gW1, gb1, gW2, gb2, None
+    return gh, gpos, None, None, None, None, None, gWe, gbe, gW1, gb1, gW2, gb2, None, None
 
 
 pool_fwd.register_autograd(_pool_backward, setup_context=_pool_setup)
@@ -181,7 +211,7 @@ pool_fwd.register_autograd(_pool_backward, setup_context=_pool_setup)
 # ---------------------------------------------------------------------------------------------
 # GCNModule
 # ---------------------------------------------------------------------------------------------
-@torch.library.custom_op('sgx::gcn_module_fwd', mutates_args=())
+@_custom_op('sgx::gcn_module_fwd')
 def gcn_module_fwd(x: Tensor, leader: Tensor, gsize: Tensor, ped_start: Tensor, ped_end: Tensor, scene_start: Tensor,
                    n_group: Tensor, W0: Tensor, W1: Tensor, V0: Tensor, V1: Tensor, Wo: Tensor, bo: Tensor,
                    chunk_scene: Tensor, n_chunks: int) -> Tensor:
@@ -213,7 +243,7 @@ def _(x, leader, gsize, ped_start, ped_end, scene_start, n_group, W0, W1, V0, V1
     return x.new_empty(x.shape[0], Wo.shape[0])
 
 
-@torch.library.custom_op('sgx::gcn_module_bwd', mutates_args=())
+@_custom_op('sgx::gcn_module_bwd')
 def gcn_module_bwd(x: Tensor, grad_out: Tensor, leader: Tensor, gsize: Tensor, ped_start: Tensor, ped_end: Tensor,
                    scene_start: Tensor, n_group: Tensor, W0: Tensor, W1: Tensor, V0: Tensor, V1: Tensor, Wo: Tensor,
                    bo: Tensor) -> List[Tensor]:
@@ -255,7 +285,7 @@ gcn_module_fwd.register_autograd(_gcn_backward, setup_context=_gcn_setup)
 # ---------------------------------------------------------------------------------------------
 # GATEncoder
 # ---------------------------------------------------------------------------------------------
-@torch.library.custom_op('sgx::gat_encoder_fwd', mutates_args=())
+@_custom_op('sgx::gat_encoder_fwd')
 def gat_encoder_fwd(x: Tensor, leader: Tensor, gsize: Tensor, ped_start: Tensor, ped_end: Tensor, n_scenes: int,
                     Wi: Tensor, ai: Tensor, Wio: Tensor, aio: Tensor, We: Tensor, ae: Tensor, Weo: Tensor,
                     aeo: Tensor, Wo: Tensor, bo: Tensor, alpha: float, scene_start: Tensor, chunk_scene: Tensor,
@@ -289,7 +319,7 @@ def _(x, leader, gsize, ped_start, ped_end, n_scenes, Wi, ai, Wio, aio, We, ae, 
     return x.new_empty(x.shape[0], Wo.shape[0])
 
 
-@torch.library.custom_op('sgx::gat_encoder_bwd', mutates_args=())
+@_custom_op('sgx::gat_encoder_bwd')
 def gat_encoder_bwd(x: Tensor, grad_out: Tensor, leader: Tensor, gsize: Tensor, ped_start: Tensor, ped_end: Tensor,
                     n_scenes: int, Wi: Tensor, ai: Tensor, Wio: Tensor, aio: Tensor, We: Tensor, ae: Tensor,
                     Weo: Tensor, aeo: Tensor, Wo: Tensor, bo: Tensor, alpha: float) -> List[Tensor]:

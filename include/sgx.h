@@ -32,13 +32,15 @@ extern "C" {
 #define SGX_ERR_CUDA (-3)        /* a CUDA runtime call failed                               */
 
 #define SGX_PRECISION_FP32 0     /* CUDA-core path, 1e-5 relative parity                     */
-#define SGX_PRECISION_BF16 1     /* tcgen05/TMEM path, 2e-2 parity                           */
+#define SGX_PRECISION_BF16 1     /* tcgen05/TMEM path, bf16 operands, 2e-2 parity            */
+#define SGX_PRECISION_TC32 2     /* tcgen05/TMEM path, fp16 hi+lo operand splits with fp32    */
+                                 /* accumulation: 1e-5 relative parity (the fp32 contract)   */
 
 #define SGX_POOL_HIDDEN 512      /* hard-coded mid width of mlp_pre_pool, sgan/models.py:473 */
 
 const char* sgx_last_error(void);
 int sgx_version(void);
-/* 1 when the loaded binary carries sm_100a code for the tcgen05 pooling kernel */
+/* 1 when the current CUDA device can run the tcgen05 kernels of this build (compute capability 10.x) */
 int sgx_has_tcgen05(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches evidence) */
 long long sgx_launch_count(void);
@@ -107,9 +109,15 @@ int sgx_group_dense(const float* labels, const int32_t* leader, const int32_t* g
  *   out[i,b] = max_j ReLU(b2[b] + W2[b,:] . ReLU(b1 + W1 [We (P_j - P_i) + be ; h_j]))   j in scene(i)
  *   h [batch,H]  pos [batch,2]  We [E,2] be [E]  W1 [512,E+H] b1 [512]  W2 [B,512] b2 [B]
  *   out fp32 [batch,B]   argmax int32 [batch,B] (global index j attaining the max; ties -> larger j)
- * precision: SGX_PRECISION_FP32 (any E<=64, H<=128, B<=64 multiple of 8) or
- *            SGX_PRECISION_BF16 (tcgen05; (E,H,B) in {(16,32,8),(16,48,48)} ... see DESIGN.md).
- * workspace: sgx_pool_ws_bytes(batch, H, B, precision).
+ * precision: SGX_PRECISION_FP32 (CUDA cores; any E, H, B multiple of 8),
+ *            SGX_PRECISION_TC32 (tcgen05, fp32-grade; (H,B) = (32,8): sgx_pool_tc32_available) or
+ *            SGX_PRECISION_BF16 (tcgen05; (H,B) in {(32,8),(48,48)}) ... see DESIGN.md.
+ * workspace: sgx_pool_ws_bytes(batch, E, H, B, precision).
+ * Prepared weights: everything that depends only on the parameters (the folded first layer
+ *   Aeff = W1[:, :E] We, c = W1[:, :E] be + b1, and the operand images of the tensor-core kernels) can be built
+ *   once per weight version with sgx_pool_prep into a caller-owned buffer of sgx_pool_prep_bytes() and passed
+ *   to sgx_pool_fwd_prepped (prep = NULL: built per call inside the workspace, which is what sgx_pool_fwd does).
+ * A NaN in any pair's output makes out[i,b] NaN (like torch.max).
  * Backward (argmax-sparse, fp32): grads of sum(out*grad_out) w.r.t. every input; gradient
  * buffers are OVERWRITTEN (not accumulated).  Reference: autograd through models.py:516-541.
  */
@@ -119,6 +127,16 @@ int sgx_pool_fwd(const float* h, const float* pos, const int32_t* ped_start, con
                  const float* We, const float* be, const float* W1, const float* b1, const float* W2,
                  const float* b2, int32_t E, int32_t H, int32_t B, int32_t precision, float* out,
                  int32_t* argmax, void* workspace, int64_t ws_bytes, void* stream);
+int64_t sgx_pool_prep_bytes(int32_t E, int32_t H, int32_t B, int32_t precision);
+int sgx_pool_prep(const float* We, const float* be, const float* W1, const float* b1, const float* W2,
+                  const float* b2, int32_t E, int32_t H, int32_t B, int32_t precision, void* prep,
+                  int64_t prep_bytes, void* stream);
+int sgx_pool_fwd_prepped(const float* h, const float* pos, const int32_t* ped_start, const int32_t* ped_end,
+                         const int64_t* pair_off, const int32_t* tile_first, int64_t batch, int64_t n_pairs,
+                         const float* We, const float* be, const float* W1, const float* b1, const float* W2,
+                         const float* b2, int32_t E, int32_t H, int32_t B, int32_t precision, const void* prep,
+                         float* out, int32_t* argmax, void* workspace, int64_t ws_bytes, void* stream);
+int sgx_pool_tc32_available(int32_t E, int32_t H, int32_t B);
 int64_t sgx_pool_bwd_ws_bytes(int64_t batch, int32_t E, int32_t H, int32_t B);
 int sgx_pool_bwd(const float* h, const float* pos, const float* out, const int32_t* argmax, const float* grad_out,
                  int64_t batch, const float* We, const float* be, const float* W1, const float* b1,

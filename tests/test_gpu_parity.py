@@ -244,10 +244,20 @@ def _generator(sgx, g, wiring):
     return gen.to(DEV).train()
 
 
+def _set_pool_precision(gen, precision):
+    for m in gen.modules():
+        if isinstance(m, type(gen.pool_net)):
+            m.precision = precision
+
+
+# 'fp32' is what every module defaults to: the tensor-core kernel with fp16 hi/lo operand splits ('tc32') for the
+# generator's pool_net dims; 'fp32-simt' pins the CUDA-core kernel.  Both must meet the ADE/FDE 1e-4 contract.
+@pytest.mark.parametrize('precision', ['fp32', 'tc32', 'fp32-simt'])
 @pytest.mark.parametrize('name', ['generator_gat_zara1', 'generator_p_eth', 'generator_gcn_zara1', 'generator_gat_pet'])
-def test_generator_matches_reference(sgx, name):
+def test_generator_matches_reference(sgx, name, precision):
     g = load_golden(name)
     gen = _generator(sgx, g, str(g['wiring']))
+    _set_pool_precision(gen, precision)
     obs, obs_rel, grp = g['obs_traj'].to(DEV), g['obs_traj_rel'].to(DEV), g['obs_traj_g'].to(DEV)
     sse = g['seq_start_end'].to(DEV)
     ades, fdes = [], []
@@ -262,6 +272,30 @@ def test_generator_matches_reference(sgx, name):
     ade = float(O.best_of_k(ades, g['seq_start_end'])) / (n * int(g['pred_len']))
     fde = float(O.best_of_k(fdes, g['seq_start_end'])) / n
     assert abs(ade - float(g['ade'])) < 1e-4 and abs(fde - float(g['fde'])) < 1e-4
+
+
+@pytest.mark.parametrize('name', ['generator_gat_zara1', 'generator_p_eth', 'generator_gcn_zara1', 'generator_gat_pet'])
+def test_generator_bf16_pooling_is_outside_the_ade_contract_but_bounded(sgx, name):
+    """precision='bf16' (bf16 operands, 2e-2 pooled features) is NOT a contract mode for ADE/FDE: on the real
+    checkpoints it moves ADE/FDE by ~1e-3.  It is kept as an explicit opt-in; this pins how far it is from the frozen
+    reference numbers (bound 5e-3) so the documentation stays honest.  bench.py's headline runs 'fp32'."""
+    g = load_golden(name)
+    gen = _generator(sgx, g, str(g['wiring']))
+    _set_pool_precision(gen, 'bf16')
+    obs, obs_rel, grp = g['obs_traj'].to(DEV), g['obs_traj_rel'].to(DEV), g['obs_traj_g'].to(DEV)
+    sse = g['seq_start_end'].to(DEV)
+    ades, fdes = [], []
+    with torch.no_grad():
+        for k in range(g['noise'].shape[0]):
+            rel = gen(obs, obs_rel, sse, grp, user_noise=g['noise'][k].to(DEV))
+            ab = O.relative_to_abs(rel.cpu(), g['obs_traj'][-1])
+            ades.append(O.displacement_error_raw(ab, g['pred_traj_gt']))
+            fdes.append(O.final_displacement_error_raw(ab[-1], g['pred_traj_gt'][-1]))
+    n = obs.shape[1]
+    ade = float(O.best_of_k(ades, g['seq_start_end'])) / (n * int(g['pred_len']))
+    fde = float(O.best_of_k(fdes, g['seq_start_end'])) / n
+    print('bf16 pooling %s: |dADE| %.2e |dFDE| %.2e' % (name, abs(ade - float(g['ade'])), abs(fde - float(g['fde']))))
+    assert abs(ade - float(g['ade'])) < 5e-3 and abs(fde - float(g['fde'])) < 1e-2
 
 
 def test_discriminator_matches_reference(sgx):
@@ -635,8 +669,9 @@ def test_pool_tile_boundaries_both_precisions(sgx, sizes):
     ref = O.pool_hidden_net(h, sse, pos, m.state_dict())
     m = m.to(DEV)
     with torch.no_grad():
-        m.precision = 'fp32'
-        assert_close(m(h.to(DEV), sse.to(DEV), pos.to(DEV)), ref, 1e-5, 'fp32 %s' % sizes[:2])
+        for precision in ('fp32', 'fp32-simt', 'tc32'):
+            m.precision = precision
+            assert_close(m(h.to(DEV), sse.to(DEV), pos.to(DEV)), ref, 1e-5, '%s %s' % (precision, sizes[:2]))
         m.precision = 'bf16'
         assert_close(m(h.to(DEV), sse.to(DEV), pos.to(DEV)), ref, 2e-2, 'bf16 %s' % sizes[:2])
 
@@ -685,7 +720,7 @@ def test_generator_block_diagonal_over_scenes_at_bench_size(sgx):
             return gen(dev(data['obs_traj'][:, p0:p1]), dev(data['obs_traj_rel'][:, p0:p1]), dev(part),
                        dev(data['obs_traj_g'][:, p0:p1]), user_noise=dev(z[scenes_lo:scenes_hi]))
 
-    for precision, tol in (('bf16', 1e-6), ('fp32', 1e-6)):
+    for precision, tol in (('bf16', 1e-6), ('fp32', 1e-6), ('fp32-simt', 1e-6)):
         gen.pool_net.precision = precision
         whole = forward(0, S)
         assert whole.shape == (12, n, 2) and bool(torch.isfinite(whole).all())

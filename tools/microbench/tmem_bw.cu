@@ -1,5 +1,6 @@
 // TMEM -> register (tcgen05.ld) and register -> TMEM (tcgen05.st) throughput per SM on sm_100a.
-// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tmem_bw tmem_bw.cu && ./tmem_bw
+// nvcc -gencode arch=compute_100a,code=sm_100a --cudart shared -O3 -o /tmp/tmem_bw tmem_bw.cu && /tmp/tmem_bw
+// (dynamic cudart, binary kept out of the repo tree)
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>

@@ -38,16 +38,18 @@ def time_case(sizes, dims, precision, reps=10):
     pairs = int((np.asarray(sizes, dtype=np.int64) ** 2).sum())
     flops = pairs * (4 * e + 2 * (e + h_dim) * 512 + 2 * 512 * b)
     med = ts[len(ts) // 2]
-    print('%-28s %-5s pairs=%-10d kernel_ms med=%.4f min=%.4f  as-written TFLOP/s=%.1f  Gpairs/s=%.2f' % (
+    print('%-28s %-9s pairs=%-10d kernel_ms med=%.4f min=%.4f  as-written TFLOP/s=%.1f  Gpairs/s=%.2f' % (
         'N=%s x%d' % (sizes[0], len(sizes)), precision, pairs, med, ts[0], flops / med / 1e9, pairs / med / 1e6))
 
 
 if __name__ == '__main__':
     G, D = (16, 32, 8), (16, 48, 48)
-    for prec in ('fp32', 'bf16'):
+    precs = sys.argv[1:] or ('fp32-simt', 'tc32', 'bf16')
+    for prec in precs:
         time_case([1024] * 8, G, prec)
         time_case([256] * 64, G, prec)
         time_case([64] * 512, G, prec)
         z = bench.synth_batch(1 << 16, 1236)['sizes']
         time_case(list(z), G, prec)
-        time_case([1024] * 4, D, prec)
+        if prec != 'tc32':
+            time_case([1024] * 4, D, prec)
