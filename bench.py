@@ -1,21 +1,28 @@
 #!/usr/bin/env python
-"""bench.py -- predicted trajectories/sec of the SGAN-GAT generator forward (K = 20 samples) on B200.
+"""bench.py -- predicted trajectories/sec of the sgan generator forward (K = 20 samples) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl sgx|reference] [--scenes S] [--precision fp32|bf16]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl sgx|reference] [--config sgan_p|sgan_gat]
+                    [--scenes S] [--precision fp32|fp32-simt|tc32|bf16]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1], SURVEY.md 8d cfg 2): zara1-shaped synthetic scenes (scene sizes drawn
-from the zara1-test pred-12 histogram, mean 3.74 peds), obs_len 8, pred_len 12, weights of the shipped
-models/sgan-gat-models/zara1_12_model.pt (frozen in tests/golden/generator_gat_zara1.npz), wiring GAT:
-encoder LSTM -> PoolHiddenNet -> GATEncoder -> noise -> decoder LSTM.  One *step* = the K=20 best-of-K generator
-forwards over one batch of S scenes per GPU (the loop of scripts/evaluate_model.py:85-90); every forward is
-complete (nothing is hoisted out of the K loop).  trajectories/step = peds * 20.
+Workloads (BASELINE.json `metric` is quoted on "SGAN-P fwd, K=20" = configs[0]; SURVEY.md 8d cfg 1 / cfg 2):
+  sgan_p   (default) SGAN-P generator: encoder LSTM -> PoolHiddenNet -> mlp_decoder_context -> noise -> decoder LSTM
+           (the upstream wiring, sgan/models.py:796-804,898), weights of models/sgan-p-models/eth_8_model.pt (frozen in
+           tests/golden/generator_p_eth.npz), obs 8 / pred 8, scene sizes from the ETH-test histogram tiled to S = 2^16
+           scenes per GPU (SURVEY 8d cfg 1 scale-up).
+  sgan_gat SGAN-GAT generator (PoolHiddenNet + GATEncoder), zara1-test histogram, obs 8 / pred 12,
+           models/sgan-gat-models/zara1_12_model.pt (tests/golden/generator_gat_zara1.npz).
+One *step* = the K=20 best-of-K generator forwards over one batch of S scenes per GPU (the loop of
+scripts/evaluate_model.py:85-90); every forward is complete (nothing is hoisted out of the K loop).
+trajectories/step = peds * 20.  Pooling runs in the default 'fp32' mode -- the mode whose ADE/FDE <= 1e-4 tests are
+green (tests/test_gpu_parity.py::test_generator_matches_reference): the tcgen05 kernel with fp16 hi/lo operand splits.
 
 Printed JSON line (rank 0): value = whole-job trajectories/sec with inputs resident in HBM; e2e = the same
 through the module API from pinned HOST buffers (schedule build + H2D + 20 forwards + D2H inside the timed
 region); roofline = the PoolHiddenNet pair kernel (CUDA events recorded by the library around that kernel);
 cpu_baseline = the CPU oracle port of the reference timed on this box's host cores on a bounded sample.
---impl reference times that CPU port alone (the reference itself is Python and cannot travel to the GPU box).
+--impl reference times that CPU port alone (the reference itself is Python and cannot travel to the GPU box), on the
+same config: each step is a bounded sample (--ref-scenes scenes of the same histogram) of the workload.
 """
 import argparse
 import gc
@@ -32,23 +39,36 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# NCCL prints its version banner on STDOUT at any debug level >= VERSION; keep stdout to the one JSON line
-if 'SGX_NCCL_DEBUG' in os.environ:
-    os.environ['NCCL_DEBUG'] = os.environ['SGX_NCCL_DEBUG']
-else:
-    os.environ.pop('NCCL_DEBUG', None)
 
 ZARA1_HIST = {2: 212, 3: 136, 4: 109, 5: 55, 6: 32, 7: 10, 8: 20, 9: 8, 10: 12, 11: 4, 12: 1, 13: 2, 14: 1}
+ETH_HIST = {2: 89, 3: 53, 4: 22, 5: 19, 6: 7, 7: 1, 8: 1, 12: 2, 13: 1}          # SURVEY 8d cfg 1 / A.3 (eth test, pred 8)
 K_SAMPLES = 20
-OBS_LEN, PRED_LEN = 8, 12
+OBS_LEN, PRED_LEN = 8, 12            # sgan_gat defaults (kept as module constants for tools/ and tests/)
 POOL_FLOPS_PER_PAIR = 4 * 16 + 2 * (16 + 32) * 512 + 2 * 512 * 8     # 57 408, as written
+# tensor-pipe FLOPs actually issued per ordered pair (padded N, operand-split K): DESIGN.md 4.1 / 4.1b
+POOL_EXECUTED_FLOPS = {'bf16': 2 * 512 * 48 + 2 * 16 * 512, 'tc32': 2 * 512 * 112 + 2 * 16 * 1024,
+                       'fp32-simt': 512 * (2 * 2 + 1 + 2 * 8)}
+
+CONFIGS = {
+    'sgan_p': dict(hist=ETH_HIST, pred_len=8, wiring='mlp', golden='generator_p_eth',
+                   what='SGAN-P generator fwd (encoder LSTM, PoolHiddenNet, mlp_decoder_context, decoder LSTM), '
+                        'ETH-test scene-size histogram tiled, obs 8 / pred 8, K=20 forwards per step',
+                   weights='models/sgan-p-models/eth_8_model.pt (tests/golden/generator_p_eth.npz)'),
+    'sgan_gat': dict(hist=ZARA1_HIST, pred_len=12, wiring='gat', golden='generator_gat_zara1',
+                     what='SGAN-GAT generator fwd (PoolHiddenNet+GATEncoder), zara1-shaped synthetic scenes, '
+                          'obs 8 / pred 12, K=20 forwards per step',
+                     weights='models/sgan-gat-models/zara1_12_model.pt (tests/golden/generator_gat_zara1.npz)'),
+}
 
 
-def synth_batch(n_scenes, seed):
-    """SURVEY 8d: positions U[0,15]^2, per-step displacement N(0,0.3^2), labels 10% zero else U{1..max(1,N//3)}."""
+def synth_batch(n_scenes, seed, config='sgan_gat'):
+    """SURVEY 8d: positions U[0,15]^2, per-step displacement N(0,0.3^2), labels 10% zero else U{1..max(1,N//3)};
+    scene sizes drawn from the config's histogram (ETH test for sgan_p, zara1 test for sgan_gat)."""
+    cfg = CONFIGS[config]
+    pred_len = cfg['pred_len']
     rng = np.random.RandomState(seed)
-    sizes_pool = np.array(list(ZARA1_HIST.keys()))
-    probs = np.array(list(ZARA1_HIST.values()), dtype=np.float64)
+    sizes_pool = np.array(list(cfg['hist'].keys()))
+    probs = np.array(list(cfg['hist'].values()), dtype=np.float64)
     sizes = rng.choice(sizes_pool, size=n_scenes, p=probs / probs.sum())
     starts = np.concatenate([[0], np.cumsum(sizes)])
     batch = int(starts[-1])
@@ -61,15 +81,56 @@ def synth_batch(n_scenes, seed):
     lab = np.floor(rng.uniform(0, 1, size=batch) * hi).astype(np.float32) + 1
     lab[rng.uniform(0, 1, size=batch) < 0.10] = 0
     grp = np.broadcast_to(lab[None, :, None], (OBS_LEN, batch, 1)).copy()
-    fut = obs[-1:] + np.cumsum(rng.normal(0, 0.3, size=(PRED_LEN, batch, 2)).astype(np.float32), axis=0)
+    fut = obs[-1:] + np.cumsum(rng.normal(0, 0.3, size=(pred_len, batch, 2)).astype(np.float32), axis=0)
     return dict(pred_traj_gt=torch.from_numpy(fut.astype(np.float32)),
                 obs_traj=torch.from_numpy(obs.astype(np.float32)), obs_traj_rel=torch.from_numpy(disp),
                 obs_traj_g=torch.from_numpy(grp), seq_start_end=torch.from_numpy(sse), sizes=sizes)
 
 
-def load_weights():
-    z = np.load(os.path.join(ROOT, 'tests', 'golden', 'generator_gat_zara1.npz'))
+def load_weights(config='sgan_gat'):
+    z = np.load(os.path.join(ROOT, 'tests', 'golden', CONFIGS[config]['golden'] + '.npz'))
     return {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith('sd.')}
+
+
+def build_generator(config, dev):
+    """The generator of the config with the shipped checkpoint's weights, in train mode (scripts/evaluate_model.py:54)."""
+    from group_gan_gcn_gat_b200 import models as MD
+    cfg = CONFIGS[config]
+    gen = MD.TrajectoryGenerator(obs_len=OBS_LEN, pred_len=cfg['pred_len'], embedding_dim=16, encoder_h_dim=32,
+                                 decoder_h_dim=32, mlp_dim=64, noise_dim=(8,), noise_mix_type='global',
+                                 pooling_type='pool_net', pool_every_timestep=False, bottleneck_dim=8, batch_norm=False,
+                                 n_heads=1, alpha=0.2, context_type=cfg['wiring'])
+    sd = load_weights(config)
+    if cfg['wiring'] == 'gat':
+        gen.load_state_dict(sd, strict=True)
+    else:   # older checkpoint generation: the reference class's passenger gcn_module is not part of this wiring
+        missing, unexpected = gen.load_state_dict(sd, strict=False)
+        assert not missing and all(k.startswith('gcn_module') for k in unexpected), (missing, unexpected)
+    return gen.to(dev).train()
+
+
+def bind_to_gpu_numa(local_rank):
+    """Pin this rank's host threads to the NUMA node of its GPU (H2D staging and the schedule build are host work)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        node = int(open('/sys/bus/pci/devices/%s/numa_node' % bus[-12:].lower()).read())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open('/sys/devices/system/node/node%d/cpulist' % node).read().strip().split(','):
+            a, _, b = part.partition('-')
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        return None
+    return None
 
 
 class ClockSampler:
@@ -146,13 +207,14 @@ class ClockSampler:
                 'source': getattr(self, 'source', '')}
 
 
-def cpu_port_traj_per_sec(n_scenes, k_samples, seed, reps=1):
+def cpu_port_traj_per_sec(n_scenes, k_samples, seed, reps=1, config='sgan_gat'):
     """The CPU oracle port of the reference generator (per-scene python loop, N^2 materialisation), all host threads."""
     from oracle import sgan_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
-    data = synth_batch(n_scenes, seed)
-    sd = load_weights()
-    cfg = dict(pred_len=PRED_LEN, wiring='gat', pooling=True, pool_every_timestep=False, alpha=0.2, n_heads=1)
+    cfgd = CONFIGS[config]
+    data = synth_batch(n_scenes, seed, config)
+    sd = load_weights(config)
+    cfg = dict(pred_len=cfgd['pred_len'], wiring=cfgd['wiring'], pooling=True, pool_every_timestep=False, alpha=0.2, n_heads=1)
     gen = torch.Generator().manual_seed(seed)
     best = None
     with torch.no_grad():
@@ -174,16 +236,24 @@ def cpu_port_traj_per_sec(n_scenes, k_samples, seed, reps=1):
     return peds * k_samples / best, best, peds
 
 
+def workload_config(config, n_scenes):
+    """Identical for both arms: the reference arm runs bounded samples of THIS workload (see its cpu_baseline.sample)."""
+    cfg = CONFIGS[config]
+    return {'workload': cfg['what'], 'name': config, 'scenes_per_gpu': n_scenes, 'k_samples': K_SAMPLES,
+            'obs_len': OBS_LEN, 'pred_len': cfg['pred_len'], 'pool_precision': 'fp32', 'weights': cfg['weights'],
+            'l2': 'flushed between timed steps (256 MiB write)', 'parallelism': 'scenes sharded by LPT on N^2'}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
     n_scenes = args.ref_scenes
     for _ in range(args.warmup):
-        cpu_port_traj_per_sec(16, 2, 1)
+        cpu_port_traj_per_sec(16, 2, 1, config=args.config)
     t0 = time.perf_counter()
     vals = []
     for s in range(args.steps):
-        v, dt, peds = cpu_port_traj_per_sec(n_scenes, K_SAMPLES, 1234 + 2 + s)
+        v, dt, peds = cpu_port_traj_per_sec(n_scenes, K_SAMPLES, 1234 + 2 + s, config=args.config)
         vals.append((v, dt, peds))
     total_traj = sum(p * K_SAMPLES for _, _, p in vals)
     total_t = sum(dt for _, dt, _ in vals)
@@ -191,21 +261,30 @@ def run_reference(args, rank):
     line = {'impl': 'reference', 'metric': 'predicted_trajectories_per_sec', 'value': value, 'unit': 'traj/s',
             'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total_t / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
-            'config': workload_config(n_scenes, 'cpu'),
+            'config': workload_config(args.config, args.scenes),
             'cpu_baseline': {'value': value, 'unit': 'traj/s', 'cores': os.cpu_count(), 'kind': 'port',
-                             'sample': '%d zara1-shaped scenes x K=%d generator forwards per step (oracle port of '
-                                       'sgan/models.py, per-scene loop)' % (n_scenes, K_SAMPLES)},
+                             'sample': 'each step = %d scenes of the config\'s histogram x K=%d complete generator forwards '
+                                       '(oracle port of sgan/models.py, per-scene loop, fp32, torch threads = all cores); '
+                                       'the reference has no batching across scenes, so traj/s does not depend on the '
+                                       'sample size' % (n_scenes, K_SAMPLES)},
             'e2e': {'value': value, 'unit': 'traj/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'wall_s': time.perf_counter() - t0}
     print(json.dumps(line))
 
 
-def workload_config(n_scenes, precision):
-    return {'workload': 'SGAN-GAT generator fwd (PoolHiddenNet+GATEncoder), zara1-shaped synthetic scenes, '
-                        'obs 8 / pred 12, K=20 forwards per step',
-            'scenes_per_gpu': n_scenes, 'k_samples': K_SAMPLES, 'pred_len': PRED_LEN, 'pool_precision': precision,
-            'weights': 'models/sgan-gat-models/zara1_12_model.pt (tests/golden/generator_gat_zara1.npz)',
-            'l2': 'flushed between timed steps (256 MiB write)', 'parallelism': 'scenes sharded by LPT on N^2'}
+def pool_kernel_name(code):
+    return {0: 'pool_pair_kernel', 1: 'pool_tc_kernel', 2: 'pool_tc32_kernel'}[code]
+
+
+def measured_traffic(config, kernel, scenes):
+    """dram bytes per launch of the dominant kernel from the committed ncu summary (profiles/pool_traffic.json, written
+    by tools/ncu_traffic.py from an `ncu --set full` capture of this command); None when no capture matches."""
+    try:
+        table = json.load(open(os.path.join(ROOT, 'profiles', 'pool_traffic.json')))
+    except (OSError, ValueError):
+        return None, None
+    e = table.get('%s/%s/%d' % (config, kernel, scenes))
+    return (e['dram_bytes_per_launch'], e['source']) if e else (None, None)
 
 
 def main():
@@ -214,10 +293,14 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='sgx', choices=['sgx', 'reference'])
+    ap.add_argument('--config', default='sgan_p', choices=sorted(CONFIGS))
     ap.add_argument('--scenes', type=int, default=1 << 16, help='scenes per GPU per step')
-    ap.add_argument('--precision', default=os.environ.get('SGX_POOL_PRECISION', 'auto'))
+    ap.add_argument('--precision', default=os.environ.get('SGX_POOL_PRECISION', 'fp32'),
+                    help="pooling precision: fp32 (default, contract mode) | fp32-simt | tc32 | bf16 (outside the ADE contract)")
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--ref-scenes', type=int, default=256, help='scenes per step of the --impl reference arm')
+    ap.add_argument('--no-train', action='store_true', help='skip the cfg-5 training-step sub-measurement')
+    ap.add_argument('--ref-scenes', type=int, default=256,
+                    help='scenes per step of the --impl reference arm (a bounded sample of the same workload)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -226,24 +309,28 @@ def main():
         run_reference(args, rank)
         return
     args.warmup = max(args.warmup, 3)
+    cfg = CONFIGS[args.config]
+    pred_len = cfg['pred_len']
 
     import torch.distributed as dist
     assert torch.cuda.is_available(), 'bench.py needs a CUDA device (the sgx ops have no CPU fallback)'
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    numa = bind_to_gpu_numa(local_rank)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     torch.backends.cudnn.allow_tf32 = False
 
-    from group_gan_gcn_gat_b200 import _lib, models as MD
-    from group_gan_gcn_gat_b200.schedule import SceneSchedule, get_schedule
+    from group_gan_gcn_gat_b200 import _lib, modules as M
+    from group_gan_gcn_gat_b200.schedule import SceneSchedule
     L = _lib.lib()
     precision = args.precision
-    if precision == 'auto':
-        precision = 'bf16' if L.sgx_has_tcgen05() else 'fp32'
+    pool_code = M.resolve_pool_precision(precision, 16, 32, 8)
+    kernel = pool_kernel_name(pool_code)
+    pool_mode = {0: 'fp32-simt', 1: 'bf16', 2: 'tc32'}[pool_code]
 
     # ---- the global scene set, sharded by LPT on N^2 (weak scaling: S scenes per GPU) ----
-    data = synth_batch(args.scenes * world, 1234 + 2)
+    data = synth_batch(args.scenes * world, 1234 + 2, args.config)
     if world > 1:
         full = SceneSchedule(data['seq_start_end'], 'cpu')
         rank_of, _ = full.partition(world)
@@ -259,11 +346,7 @@ def main():
     peds = int(data['seq_start_end'][-1, 1])
     n_pairs = int((data['sizes'].astype(np.int64) ** 2).sum())
 
-    gen = MD.TrajectoryGenerator(obs_len=OBS_LEN, pred_len=PRED_LEN, embedding_dim=16, encoder_h_dim=32, decoder_h_dim=32,
-                                 mlp_dim=64, noise_dim=(8,), noise_mix_type='global', pooling_type='pool_net',
-                                 pool_every_timestep=False, bottleneck_dim=8, batch_norm=False, n_heads=1, alpha=0.2)
-    gen.load_state_dict(load_weights(), strict=True)
-    gen = gen.to(dev).train()          # scripts/evaluate_model.py:54 keeps the generator in train mode
+    gen = build_generator(args.config, dev)
     gen.pool_net.precision = precision
 
     host = {k: data[k].pin_memory() for k in ('obs_traj', 'obs_traj_rel', 'obs_traj_g', 'seq_start_end', 'pred_traj_gt')}
@@ -283,14 +366,14 @@ def main():
 
     def step_e2e():
         """The body of scripts/evaluate_model.py:72-99 for one minibatch, from HOST buffers: H2D of the batch, schedule
-        built from the host seq_start_end, K complete generator forwards (noise drawn on the CPU generator like the
-        reference), best-of-K ADE/FDE reduced on the device, D2H of the two sums."""
+        built from the host seq_start_end, K complete generator forwards, best-of-K ADE/FDE reduced on the device,
+        D2H of the two sums."""
         obs = host['obs_traj'].to(dev, non_blocking=True)
         obs_rel = host['obs_traj_rel'].to(dev, non_blocking=True)
         grp = host['obs_traj_g'].to(dev, non_blocking=True)
         gt = host['pred_traj_gt'].to(dev, non_blocking=True)
         sse = host['seq_start_end'].clone()              # a fresh batch object every step: the schedule is rebuilt
-        ade, fde = evaluate_batch(gen, obs, obs_rel, sse, grp, gt, K_SAMPLES)
+        ade, fde = evaluate_batch(gen, obs, obs_rel, sse, grp, gt, K_SAMPLES, fold_samples=False)
         out_host.copy_(torch.stack([ade, fde]), non_blocking=True)
         torch.cuda.synchronize()
 
@@ -329,8 +412,8 @@ def main():
         clocks = sampler.stop() if rank == 0 else None
 
         # ---- e2e: host buffers, H2D + schedule + 20 forwards + D2H inside the timed region ----
-        for _ in range(args.warmup):                     # same W as the resident arm: the first e2e steps grow the
-            step_e2e()                                   # caching allocator (cudaMalloc of the 109 MB batch buffers)
+        for _ in range(args.warmup + 2):                 # the first e2e steps grow the caching allocator and the pinned
+            step_e2e()                                   # staging buffers of the schedule; keep that out of the timing
         barrier()
         t0 = time.perf_counter()
         e2e_steps = []
@@ -345,14 +428,13 @@ def main():
         # stream while batch k computes, results go back with an async D2H per step, ONE synchronisation at the end --
         # the reference's evaluate() does not synchronise per minibatch either (scripts/evaluate_model.py:72-99).
         side = torch.cuda.Stream(dev)
-        main = torch.cuda.current_stream(dev)
+        main_stream = torch.cuda.current_stream(dev)
         out_pipe = torch.empty(args.steps + args.warmup, 2).pin_memory()
         keys = ('obs_traj', 'obs_traj_rel', 'obs_traj_g', 'pred_traj_gt')
-
         slots = [{k: torch.empty_like(dev_in[k]) for k in keys} for _ in range(2)]    # double buffer, no allocation per step
 
         def stage(i):
-            side.wait_stream(main)                   # slot i % 2 was last read by step i - 2, already enqueued on main
+            side.wait_stream(main_stream)            # slot i % 2 was last read by step i - 2, already enqueued on main
             with torch.cuda.stream(side):
                 for k in keys:
                     slots[i % 2][k].copy_(host[k], non_blocking=True)
@@ -364,12 +446,12 @@ def main():
             nxt = stage(0)
             for i in range(n):
                 cur, done = nxt
-                main.wait_event(done)
+                main_stream.wait_event(done)
                 if i + 1 < n:
                     nxt = stage(i + 1)
                 sse = host['seq_start_end'].clone()
                 ade, fde = evaluate_batch(gen, cur['obs_traj'], cur['obs_traj_rel'], sse, cur['obs_traj_g'],
-                                          cur['pred_traj_gt'], K_SAMPLES)
+                                          cur['pred_traj_gt'], K_SAMPLES, fold_samples=False)
                 out_pipe[offset + i].copy_(torch.stack([ade, fde]), non_blocking=True)
 
         run_pipelined(args.warmup, 0)
@@ -406,15 +488,35 @@ def main():
                 torch.cuda.synchronize()
                 ts.append(a.elapsed_time(b))
             return statistics.mean(ts[3:])
-        pool_h = gen.pool_net(h_enc, dev_in['seq_start_end'], dev_in['obs_traj'][-1])
+        end_pos = dev_in['obs_traj'][-1]
+        pool_ms = time_call(lambda: gen.pool_net(h_enc, dev_in['seq_start_end'], end_pos))
+        pool_h = gen.pool_net(h_enc, dev_in['seq_start_end'], end_pos)
         ctx_in = torch.cat([h_enc.view(-1, 32), pool_h], dim=1)
         end_grp = dev_in['obs_traj_g'][-1]
-        gat_ms = time_call(lambda: gen.gatencoder(ctx_in, dev_in['seq_start_end'], dev_in['obs_traj'][-1], end_grp))
+        if cfg['wiring'] == 'gat':
+            ctx_fn = lambda: gen.gatencoder(ctx_in, dev_in['seq_start_end'], end_pos, end_grp)
+        else:
+            ctx_fn = lambda: gen.mlp_decoder_context(ctx_in)
+        ctx_ms = time_call(ctx_fn)
         enc_ms = time_call(lambda: gen.encoder(dev_in['obs_traj_rel']))
-        ctx24 = gen.gatencoder(ctx_in, dev_in['seq_start_end'], dev_in['obs_traj'][-1], end_grp)
+        ctx24 = ctx_fn()
         z0 = torch.randn(n_scenes, 8, device=dev)
         dec_ms = time_call(lambda: gen.decode(ctx24, dev_in['obs_traj'], dev_in['obs_traj_rel'], dev_in['seq_start_end'],
                                               user_noise=z0))
+        other_modes = {}
+        for alt in ('bf16', 'fp32-simt'):                    # the same pooling call in the other modes, for the record
+            if alt == pool_mode:
+                continue
+            gen.pool_net.precision = alt
+            other_modes[alt] = time_call(lambda: gen.pool_net(h_enc, dev_in['seq_start_end'], end_pos), reps=5)
+        gen.pool_net.precision = precision
+
+    train = None
+    if not args.no_train:
+        try:
+            train = train_step_numbers(dev, rank, world)
+        except Exception as e:                               # the headline must not depend on the sub-measurement
+            train = {'error': repr(e)[:200]}
 
     t_total = torch.tensor([total_ms, e2e_s * 1e3, pipe_s * 1e3], dtype=torch.float64, device=dev)
     work = torch.tensor([float(peds * K_SAMPLES)], dtype=torch.float64, device=dev)
@@ -430,24 +532,48 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
         except OSError:
             pass
-        if precision == 'bf16':
-            peak, peak_src = peaks.get('bf16_tflops_sustained', 1400.0), 'measured bf16 sustained' if peaks else 'fallback'
-        else:
-            peak, peak_src = peaks.get('bf16_tflops_sustained', 1400.0), 'measured bf16 sustained' if peaks else 'fallback'
+        cuda_core_peak = 148 * 128 * 2 * 1.965e-3                      # fp32 FMA lanes x 2 FLOP x GHz -> TFLOP/s
+        if pool_mode == 'fp32-simt':
+            peak, peak_src = cuda_core_peak, 'fp32 CUDA-core peak (148 SMs x 128 FMA lanes x 1.965 GHz); no fp32 tensor-core MMA exists'
+        else:   # fp16 and bf16 operands run at the same tcgen05 rate
+            peak = peaks.get('bf16_tflops_sustained', 1400.0)
+            peak_src = 'MEASURED_PEAKS.json bf16 sustained (kernel timed inside a long step)' if peaks else 'fallback 1400 (B200_PROFILING.md)'
         k_ms = statistics.mean(kernel_ms)
         achieved = POOL_FLOPS_PER_PAIR * n_pairs / (k_ms * 1e-3) / 1e12
+        executed = POOL_EXECUTED_FLOPS[pool_mode] * n_pairs / (k_ms * 1e-3) / 1e12
+        traffic, traffic_src = measured_traffic(args.config, kernel, args.scenes)
+        h2d = int(sum(host[k].numel() * host[k].element_size() for k in ('obs_traj', 'obs_traj_rel', 'obs_traj_g', 'pred_traj_gt')) +
+                  (4 + 4 + 8) * peds + 4 * (n_scenes + 1) + 4 * ((n_pairs + 127) // 128))
+        hbm = peaks.get('hbm_gbs', 6650.0)
+        if cfg['wiring'] == 'gat':
+            ctx_bytes = 260 * peds + 16 * n_scenes + 29920
+            ctx_entry = {'op': 'GATEncoder fwd (group_ids + gat_fused_mma_kernel)', 'bound': 'hbm', 'ms': ctx_ms,
+                         'algorithmic_bytes': ctx_bytes, 'achieved': ctx_bytes / (ctx_ms * 1e-3) / 1e9, 'peak': hbm,
+                         'unit': 'GB/s', 'frac': ctx_bytes / (ctx_ms * 1e-3) / 1e9 / hbm,
+                         'algorithmic_flops': 190 * n_pairs + 8400 * peds,
+                         'achieved_tflops': (190 * n_pairs + 8400 * peds) / (ctx_ms * 1e-3) / 1e12,
+                         'fp32_cuda_core_peak_tflops': cuda_core_peak,
+                         'note': 'HBM-bound by decree (SURVEY 8d: 260 B/ped); in practice issue / tensor-pipe bound, DESIGN.md 4.3'}
+        else:
+            ctx_bytes = (40 + 24) * 4 * peds
+            ctx_entry = {'op': 'mlp_decoder_context 40->64->24 (+ReLU)', 'bound': 'hbm', 'ms': ctx_ms,
+                         'algorithmic_bytes': ctx_bytes, 'achieved': ctx_bytes / (ctx_ms * 1e-3) / 1e9, 'peak': hbm,
+                         'unit': 'GB/s', 'frac': ctx_bytes / (ctx_ms * 1e-3) / 1e9 / hbm}
         line = {
             'metric': 'predicted_trajectories_per_sec', 'value': traj_per_step * args.steps / (total_ms_max * 1e-3),
             'unit': 'traj/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': total_ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'bf16' if precision == 'bf16' else 'fp32', 'data': 'synthetic',
-            'config': dict(workload_config(n_scenes, precision), peds_per_gpu=peds, pairs_per_gpu=n_pairs),
+            'dtype': 'bf16' if pool_mode == 'bf16' else 'fp32', 'data': 'synthetic',
+            'config': dict(workload_config(args.config, args.scenes), pool_precision=precision),
+            'run': {'peds_per_gpu': peds, 'pairs_per_gpu': n_pairs, 'scenes_this_rank': n_scenes, 'pool_kernel': kernel,
+                    'pool_mode': pool_mode, 'numa_node_rank0': numa,
+                    'pool_mode_note': 'fp32 contract mode (ADE/FDE <= 1e-4, pooled features 1e-5): tcgen05 kind::f16 on '
+                                      'fp16 hi+lo operand splits, fp32 accumulate' if pool_mode == 'tc32' else
+                                      ('bf16 operands: pooled features 2e-2, ADE/FDE ~1e-3 -- outside the ADE contract'
+                                       if pool_mode == 'bf16' else 'fp32 CUDA cores')},
             'clocks': clocks,
             'e2e': {'value': traj_per_step * args.steps / (e2e_ms_max * 1e-3), 'unit': 'traj/s',
-                    'h2d_bytes_per_step': int(sum(host[k].numel() * host[k].element_size()
-                                                  for k in ('obs_traj', 'obs_traj_rel', 'obs_traj_g', 'pred_traj_gt')) +
-                                              (4 + 4 + 8) * peds + 4 * (n_scenes + 1) + 4 * ((n_pairs + 127) // 128)),
-                    'd2h_bytes_per_step': int(out_host.numel() * 4),
+                    'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': int(out_host.numel() * 4),
                     'ms_per_step': e2e_ms_max / args.steps, 'ms_per_step_median_rank0': statistics.median(e2e_steps),
                     'ms_per_step_max_rank0': max(e2e_steps),
                     'pipelined': {'value': traj_per_step * args.steps / (pipe_ms_max * 1e-3), 'unit': 'traj/s',
@@ -456,47 +582,77 @@ def main():
                                           'step, one synchronisation at the end (evaluate() over a prefetching loader)'},
                     'what': 'evaluate_batch(): H2D batch + schedule + K forwards + best-of-K ADE/FDE on device + D2H of the sums'},
             'gpu_launches': int(launches),
-            'roofline': {'kernel': 'pool_pair_kernel' if precision != 'bf16' else 'pool_tc_kernel', 'bound': 'tensor',
+            'roofline': {'kernel': kernel, 'bound': 'tensor' if pool_mode != 'fp32-simt' else 'fp32 cuda cores',
                          'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
-                         'traffic': 36.45e6 if (precision == 'bf16' and args.scenes == 1 << 16) else None,
-                         'traffic_source': 'dram__bytes_read+write per launch, ncu --set full, profiles/r01_final_forward_top_kernels_ncu_full_raw.csv',
+                         'executed_tflops': executed, 'frac_executed': executed / peak,
+                         'traffic': traffic, 'traffic_source': traffic_src,
                          'peak_source': peak_src, 'kernel_ms': k_ms,
                          'share_of_step': k_ms * K_SAMPLES / (total_ms_max / args.steps),
-                         'why_this_kernel': 'the operator SURVEY 8d gives a tensor roofline (as-written pair-MLP FLOPs); the '
-                                            'largest share of the step is the XU-bound LSTM recurrence, whose roofline '
-                                            '(MUFU/s) is in other_kernels next to the HBM-by-decree GAT',
                          'algorithmic_flops_per_launch': POOL_FLOPS_PER_PAIR * n_pairs,
-                         'note': 'as-written FLOPs (57408 per ordered pair); bf16: tcgen05 GEMM1+GEMM2 with the 2->16 embedding '
-                                 'folded into GEMM1; fp32: exactly factored layer 1 on CUDA cores (DESIGN.md 4.1/4.2)'},
+                         'executed_flops_per_launch': POOL_EXECUTED_FLOPS[pool_mode] * n_pairs,
+                         'note': 'achieved/frac: as-written FLOPs (57408 per ordered pair, SURVEY 8d); executed: the MMA FLOPs '
+                                 'the kernel issues (tc32: K = 16 + 3 x 32 for GEMM1, hidden hi+lo against [W2_hi; W2_lo] '
+                                 'for GEMM2; the N = 16 GEMM2 MMAs are A-operand-fetch bound at 32 cycles each, DESIGN.md 4.1b)',
+                         'same_call_other_modes_ms': other_modes, 'op_ms_with_prep_and_unpack': pool_ms},
             'wall_s_timed_region': wall,
             'other_kernels': [
-                {'op': 'GATEncoder fwd (group_ids + gat_fused_mma_kernel)', 'bound': 'hbm', 'ms': gat_ms,
-                 'algorithmic_bytes': 260 * peds + 16 * n_scenes + 29920,
-                 'achieved': (260 * peds + 16 * n_scenes + 29920) / (gat_ms * 1e-3) / 1e9,
-                 'peak': peaks.get('hbm_gbs', 6650.0), 'unit': 'GB/s',
-                 'frac': (260 * peds + 16 * n_scenes + 29920) / (gat_ms * 1e-3) / 1e9 / peaks.get('hbm_gbs', 6650.0),
-                 'algorithmic_flops': 190 * n_pairs + 8400 * peds,
-                 'achieved_tflops': (190 * n_pairs + 8400 * peds) / (gat_ms * 1e-3) / 1e12,
-                 'fp32_cuda_core_peak_tflops': 148 * 128 * 2 * 1.965e-3,
-                 'note': 'HBM-bound by decree (SURVEY 8d: 260 B/ped, 190 N^2 + 8.4k N FLOP per scene = 35 FLOP/B, above the '
-                         '11.5 FLOP/B ridge of the fp32 CUDA cores): the kernel is issue / tensor-pipe bound (3xTF32 mma.sync '
-                         'linear maps + per-ped attention), see DESIGN.md 4.3'},
+                ctx_entry,
                 {'op': 'Encoder + decoder LSTM', 'bound': 'xu (MUFU)', 'ms': enc_ms + dec_ms,
-                 'mufu_per_ped_step': 7 * 32, 'achieved_gmufu_s': 224 * 20 * peds / ((enc_ms + dec_ms) * 1e-3) / 1e9,
-                 'peak_gmufu_s': 148 * 16 * 1.965, 'frac': 224 * 20 * peds / ((enc_ms + dec_ms) * 1e-3) / 1e9 / (148 * 16 * 1.965),
+                 'mufu_per_ped_step': 7 * 32,
+                 'achieved_gmufu_s': 224 * (OBS_LEN + pred_len) * peds / ((enc_ms + dec_ms) * 1e-3) / 1e9,
+                 'peak_gmufu_s': 148 * 16 * 1.965,
+                 'frac': 224 * (OBS_LEN + pred_len) * peds / ((enc_ms + dec_ms) * 1e-3) / 1e9 / (148 * 16 * 1.965),
                  'note': '7 transcendental operations per hidden unit and step on 16 MUFU lanes per SM at 1.965 GHz (DESIGN.md 4.6)'},
-                {'op': 'Encoder LSTM 8 steps (lstm_tc_kernel)', 'ms': enc_ms, 'ped_steps_per_s': 8 * peds / (enc_ms * 1e-3)},
-                {'op': 'Decoder LSTM 12 steps + hidden2pos + noise fold-in (lstm_tc_kernel)', 'ms': dec_ms,
-                 'ped_steps_per_s': 12 * peds / (dec_ms * 1e-3)},
+                {'op': 'Encoder LSTM 8 steps (lstm_tc_kernel)', 'ms': enc_ms, 'ped_steps_per_s': OBS_LEN * peds / (enc_ms * 1e-3)},
+                {'op': 'Decoder LSTM %d steps + hidden2pos + noise fold-in (lstm_tc_kernel)' % pred_len, 'ms': dec_ms,
+                 'ped_steps_per_s': pred_len * peds / (dec_ms * 1e-3)},
             ],
         }
+        if train is not None:
+            line['train_step'] = train
         if not args.no_cpu_baseline and world == 1:          # the CPU port is timed next to the 1-GPU number only
-            v, dt, p = cpu_port_traj_per_sec(1536, K_SAMPLES, 1234 + 2)      # ~11 s of CPU work on 16 cores
+            v, dt, p = cpu_port_traj_per_sec(2048, K_SAMPLES, 1234 + 2, config=args.config)   # ~10-20 s of CPU work
             line['cpu_baseline'] = {'value': v, 'unit': 'traj/s', 'cores': os.cpu_count(), 'kind': 'port',
-                                    'sample': '1536 zara1-shaped scenes (%d peds) x K=20 forwards, %.1f s' % (p, dt)}
-        print(json.dumps(line))
+                                    'sample': '2048 scenes of the config\'s histogram (%d peds) x K=20 forwards, %.1f s' % (p, dt)}
+        sys.stdout.flush()
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def train_step_numbers(dev, rank, world):
+    """SURVEY cfg 5 next to the headline: one adversarial iteration (D step + G step, best_k = 20) on 64 zara1-train-shaped
+    scenes per rank, data-parallel with the gradient all-reduce of group_gan_gcn_gat_b200.parallel; device time per
+    step, max over ranks.  The driver's scaling run therefore also records the training step at N = 1, 2, 4, 8."""
+    import torch.distributed as dist
+    from tools import train_step_dp as T
+    from group_gan_gcn_gat_b200 import parallel
+    args, gen, disc, opt_g, opt_d, batch = T.setup(dev, rank, world)
+    times = {'d': [], 'g': []}
+    for it in range(6):
+        rng = parallel.make_label_rng(0, it)
+        torch.manual_seed(100 + it * world + rank)
+        for name, fn, opt in (('d', parallel.discriminator_step, opt_d), ('g', parallel.generator_step, opt_g)):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0.record()
+            fn(args, batch, gen, disc, opt, label_rng=rng, n_global=args.n_global)
+            e1.record()
+            torch.cuda.synchronize()
+            times[name].append(e0.elapsed_time(e1))
+    t = torch.tensor([statistics.median(times['d'][2:]), statistics.median(times['g'][2:])], device=dev, dtype=torch.float64)
+    n = torch.tensor([float(batch[0].shape[1])], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(n, op=dist.ReduceOp.SUM)
+    d_ms, g_ms = t.tolist()
+    return {'workload': 'cfg5 adversarial step: 64 zara1-train-shaped scenes per rank, best_k=20, SGAN-GAT G + global D, Adam',
+            'd_step_ms': d_ms, 'g_step_ms': g_ms, 'peds_global': int(n.item()), 'scenes_global': 64 * world,
+            'scenes_per_s': 64 * world / ((d_ms + g_ms) * 1e-3),
+            'allreduce_bytes': {'G': sum(p.numel() for p in gen.parameters()) * 4,
+                                'D': sum(p.numel() for p in disc.parameters()) * 4}}
 
 
 if __name__ == '__main__':

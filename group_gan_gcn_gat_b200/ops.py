@@ -211,12 +211,37 @@ pool_fwd.register_autograd(_pool_backward, setup_context=_pool_setup)
 # ---------------------------------------------------------------------------------------------
 # GCNModule
 # ---------------------------------------------------------------------------------------------
+def _check_gcn_shapes(x, W0, W1, V0, V1, Wo, bo):
+    """Shape contract of GCNModule (sgan/models.py:583-712): a mismatch raises like the reference's matmul would,
+    instead of letting a kernel index a weight out of bounds."""
+    IN, HID, OUT, FIN = x.shape[1], W0.shape[1], W1.shape[1], Wo.shape[0]
+    if (W0.shape[0] != IN or W1.shape[0] != HID or V0.shape != (OUT, HID) or V1.shape != (HID, OUT) or
+            Wo.shape[1] != 2 * OUT or bo.shape != (FIN,)):
+        raise ValueError('GCNModule: inconsistent shapes x%s W0%s W1%s V0%s V1%s Wo%s bo%s' % tuple(
+            tuple(t.shape) for t in (x, W0, W1, V0, V1, Wo, bo)))
+
+
+def _check_gat_shapes(x, Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo):
+    """Shape contract of GATEncoder (sgan/models.py:239-294): the reference raises a matmul size error when
+    encoder_h_dim + bottleneck_dim != 40; so does this, before any kernel runs."""
+    IN = x.shape[1]
+    nh, _, HID = Wi.shape
+    OUT, FIN = Wio.shape[1], Wo.shape[0]
+    ok = (Wi.shape[1] == IN and tuple(ai.shape) == (nh, 2 * HID) and Wio.shape[0] == nh * HID and aio.numel() == 2 * OUT and
+          tuple(We.shape) == (nh, OUT, HID) and tuple(ae.shape) == (nh, 2 * HID) and tuple(Weo.shape) == (nh * HID, OUT) and
+          aeo.numel() == 2 * OUT and Wo.shape[1] == 2 * OUT and bo.numel() == FIN)
+    if not ok:
+        raise ValueError('GATEncoder: inconsistent shapes x%s Wi%s ai%s Wio%s aio%s We%s ae%s Weo%s aeo%s Wo%s bo%s' % tuple(
+            tuple(t.shape) for t in (x, Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo)))
+
+
 @_custom_op('sgx::gcn_module_fwd')
 def gcn_module_fwd(x: Tensor, leader: Tensor, gsize: Tensor, ped_start: Tensor, ped_end: Tensor, scene_start: Tensor,
                    n_group: Tensor, W0: Tensor, W1: Tensor, V0: Tensor, V1: Tensor, Wo: Tensor, bo: Tensor,
                    chunk_scene: Tensor, n_chunks: int) -> Tensor:
     x = _f32(x, 'h_states')
     W0, W1, V0, V1, Wo, bo = (_f32(t, 'gcn weight') for t in (W0, W1, V0, V1, Wo, bo))
+    _check_gcn_shapes(x, W0, W1, V0, V1, Wo, bo)
     batch, IN = x.shape
     HID, OUT, FIN = W0.shape[1], W1.shape[1], Wo.shape[0]
     S = scene_start.numel() - 1
@@ -249,6 +274,7 @@ def gcn_module_bwd(x: Tensor, grad_out: Tensor, leader: Tensor, gsize: Tensor, p
                    bo: Tensor) -> List[Tensor]:
     x, grad_out = _f32(x, 'x'), _f32(grad_out, 'grad_out')
     W0, W1, V0, V1, Wo, bo = (t.contiguous() for t in (W0, W1, V0, V1, Wo, bo))
+    _check_gcn_shapes(x, W0, W1, V0, V1, Wo, bo)
     batch, IN = x.shape
     HID, OUT, FIN = W0.shape[1], W1.shape[1], Wo.shape[0]
     S = scene_start.numel() - 1
@@ -294,6 +320,7 @@ def gat_encoder_fwd(x: Tensor, leader: Tensor, gsize: Tensor, ped_start: Tensor,
     dims 40/72/16/24)."""
     x = _f32(x, 'h_states')
     ps = [_f32(t, 'gat weight') for t in (Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo)]
+    _check_gat_shapes(x, *ps)
     batch, IN = x.shape
     nh, _, HID = Wi.shape
     OUT, FIN = Wio.shape[1], Wo.shape[0]
@@ -325,6 +352,7 @@ def gat_encoder_bwd(x: Tensor, grad_out: Tensor, leader: Tensor, gsize: Tensor, 
                     Weo: Tensor, aeo: Tensor, Wo: Tensor, bo: Tensor, alpha: float) -> List[Tensor]:
     x, grad_out = _f32(x, 'x'), _f32(grad_out, 'grad_out')
     ps = [t.contiguous() for t in (Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo)]
+    _check_gat_shapes(x, *ps)
     batch, IN = x.shape
     nh, _, HID = Wi.shape
     OUT, FIN = Wio.shape[1], Wo.shape[0]

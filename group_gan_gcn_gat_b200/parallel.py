@@ -26,6 +26,9 @@ def shard_batch(batch_tensors, seq_start_end, world, rank, ped_dim=1):
 
     batch_tensors: dict name -> tensor whose dimension `ped_dim` indexes pedestrians ([T,batch,C] in the reference),
     or dimension 0 for tensors listed with a leading '0:' in the name (e.g. loss_mask [batch, T]).
+    A rank can come out EMPTY (fewer scenes than ranks: the last minibatch of an epoch, the reference loader has no
+    drop_last): its tensors have zero pedestrians and its seq_start_end zero rows; the step functions below skip the
+    forward on such a rank but still join every collective.
     """
     sched = seq_start_end if isinstance(seq_start_end, SceneSchedule) else SceneSchedule(seq_start_end, 'cpu')
     rank_of, _ = sched.partition(world)
@@ -43,30 +46,58 @@ def shard_batch(batch_tensors, seq_start_end, world, rank, ped_dim=1):
     return out, local_sse, mine
 
 
-def allreduce_gradients(module, group=None):
-    """One flattened all-reduce (sum) over every parameter gradient of `module` (missing grads count as zero)."""
+def global_ped_count(seq_start_end):
+    """Pedestrians of the GLOBAL minibatch, known on every rank without communication (each rank holds the host copy of
+    the global seq_start_end it sharded from): pass it as `n_global` to the step functions."""
+    sse = seq_start_end.host_sse if isinstance(seq_start_end, SceneSchedule) else np.asarray(seq_start_end)
+    return int(sse[-1, 1]) if len(sse) else 0
+
+
+def allreduce_gradients(module, group=None, ran_forward=True):
+    """One all-reduce (sum) over every parameter gradient of `module`: ONE `cat` into a flat bucket, the collective,
+    and the parameters' .grad re-pointed at views of the reduced bucket (no copy back).
+
+    Parameters without a gradient (e.g. the passenger gcn_module of the 'gat' wiring) contribute zeros and get
+    grad = None back, so an optimizer with weight decay / momentum skips them exactly as the reference's does.  The set
+    of such parameters is a property of the wiring, identical on every rank that ran a forward; a rank with an EMPTY
+    shard (`ran_forward=False`) contributes zeros for everything and reuses the set it saw on its last real step.
+    Returns the number of bytes reduced (0 when there is nothing to do)."""
     params = [p for p in module.parameters() if p.requires_grad]
     if not params or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return 0
-    for p in params:
-        if p.grad is None:
-            p.grad = torch.zeros_like(p)
-    flat = torch.cat([p.grad.reshape(-1) for p in params])
+    if ran_forward:
+        none_set = frozenset(i for i, p in enumerate(params) if p.grad is None)
+        module._sgx_grad_none = none_set
+    else:
+        none_set = getattr(module, '_sgx_grad_none', frozenset())
+    zeros = getattr(module, '_sgx_zero_grads', None)
+    n_max = max(p.numel() for p in params)
+    if zeros is None or zeros.numel() < n_max or zeros.device != params[0].device:
+        zeros = torch.zeros(n_max, dtype=params[0].dtype, device=params[0].device)
+        module._sgx_zero_grads = zeros
+    pieces = [(p.grad.reshape(-1) if (ran_forward and p.grad is not None) else zeros[:p.numel()]) for p in params]
+    flat = torch.cat(pieces)
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     off = 0
-    for p in params:
+    for i, p in enumerate(params):
         n = p.numel()
-        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+        p.grad = None if i in none_set else flat[off:off + n].view_as(p)
         off += n
     return flat.numel() * flat.element_size()
 
 
 def _global_count(n_local, device, group=None):
+    """Fallback when the caller did not pass n_global: one extra (blocking) all-reduce per step."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return float(n_local)
     t = torch.tensor([float(n_local)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return float(t.item())
+
+
+def _weight(n_local, n_global, device, group):
+    total = float(n_global) if n_global else _global_count(n_local, device, group)
+    return n_local / max(total, 1.0)
 
 
 def variety_l2(l2_raw_per_sample, loss_mask, sched):
@@ -79,11 +110,22 @@ def variety_l2(l2_raw_per_sample, loss_mask, sched):
     return (per_scene.min(dim=1).values / denom).sum()
 
 
-def discriminator_step(args, batch, generator, discriminator, optimizer_d, label_rng=None, group=None):
-    """scripts/train.py:395-429 on this rank's shard; gradients are all-reduced before the optimizer step."""
+def discriminator_step(args, batch, generator, discriminator, optimizer_d, label_rng=None, group=None, n_global=None):
+    """scripts/train.py:395-429 on this rank's shard; gradients are all-reduced before the optimizer step.
+    n_global: pedestrians of the global minibatch (global_ped_count); without it one extra blocking all-reduce finds it."""
     (obs_traj, pred_traj_gt, obs_traj_rel, pred_traj_gt_rel, obs_traj_g, loss_mask, seq_start_end) = batch
     n_local = obs_traj.shape[1]
-    w = n_local / _global_count(n_local, obs_traj.device, group)
+    w = _weight(n_local, n_global, obs_traj.device, group)
+    if n_local == 0:                   # empty shard: no forward, zero gradients, every collective still joined
+        if label_rng is not None:      # keep the label-smoothing stream aligned with the other ranks (gan_d_loss: 2 draws)
+            label_rng.uniform(0.7, 1.2)
+            label_rng.uniform(0, 0.3)
+        optimizer_d.zero_grad()
+        allreduce_gradients(discriminator, group, ran_forward=False)
+        if getattr(args, 'clipping_threshold_d', 0) > 0:
+            nn.utils.clip_grad_norm_(discriminator.parameters(), args.clipping_threshold_d)
+        optimizer_d.step()
+        return {'D_total_loss': 0.0}
     # The reference leaves the generator graph attached here (scripts/train.py:404-409) and back-propagates the D loss
     # into generator .grad buffers that optimizer_g.zero_grad() discards before they are ever used; running the
     # generator without autograd gives the same D gradients and takes the inference kernels.
@@ -107,7 +149,9 @@ def discriminator_step(args, batch, generator, discriminator, optimizer_d, label
     if getattr(args, 'clipping_threshold_d', 0) > 0:
         nn.utils.clip_grad_norm_(discriminator.parameters(), args.clipping_threshold_d)
     optimizer_d.step()
-    return {'D_total_loss': float(loss.detach()) / max(w, 1e-12) if w else 0.0}
+    # 0-dim tensors, not floats: converting here would synchronise the host with the device every step (the reference
+    # only reads its losses every print_every iterations, scripts/train.py:316-330)
+    return {'D_total_loss': loss.detach() / max(w, 1e-12)}
 
 
 def _batch_independent(module):
@@ -136,11 +180,20 @@ def _folded_samples(generator, obs_traj, obs_traj_rel, obs_traj_g, seq_start_end
                      user_noise=noise)
 
 
-def generator_step(args, batch, generator, discriminator, optimizer_g, label_rng=None, group=None):
+def generator_step(args, batch, generator, discriminator, optimizer_g, label_rng=None, group=None, n_global=None):
     """scripts/train.py:432-484: best-of-K variety loss + adversarial term on the last sample."""
     (obs_traj, pred_traj_gt, obs_traj_rel, pred_traj_gt_rel, obs_traj_g, loss_mask, seq_start_end) = batch
     n_local = obs_traj.shape[1]
-    w = n_local / _global_count(n_local, obs_traj.device, group)
+    w = _weight(n_local, n_global, obs_traj.device, group)
+    if n_local == 0:                   # empty shard (see discriminator_step)
+        if label_rng is not None:
+            label_rng.uniform(0.7, 1.2)
+        optimizer_g.zero_grad()
+        allreduce_gradients(generator, group, ran_forward=False)
+        if getattr(args, 'clipping_threshold_g', 0) > 0:
+            nn.utils.clip_grad_norm_(generator.parameters(), args.clipping_threshold_g)
+        optimizer_g.step()
+        return {'G_total_loss': 0.0}
     sched = get_schedule(seq_start_end, obs_traj.device)
     mask = loss_mask[:, args.obs_len:]
     raws = []
@@ -162,12 +215,12 @@ def generator_step(args, batch, generator, discriminator, optimizer_g, label_rng
     losses = {}
     if args.l2_loss_weight > 0:
         l2 = variety_l2(torch.stack(raws, dim=1), mask, sched)
-        losses['G_l2_loss_rel'] = float(l2.detach())
+        losses['G_l2_loss_rel'] = l2.detach()
         loss = loss + l2
     fake = relative_to_abs(fake_rel, obs_traj[-1])
     s_fake = discriminator(torch.cat([obs_traj, fake], 0), torch.cat([obs_traj_rel, fake_rel], 0), seq_start_end)
     adv = gan_g_loss(s_fake, label_rng)
-    losses['G_discriminator_loss'] = float(adv.detach())
+    losses['G_discriminator_loss'] = adv.detach()
     loss = loss + adv * w
     optimizer_g.zero_grad()
     loss.backward()
@@ -175,7 +228,7 @@ def generator_step(args, batch, generator, discriminator, optimizer_g, label_rng
     if getattr(args, 'clipping_threshold_g', 0) > 0:
         nn.utils.clip_grad_norm_(generator.parameters(), args.clipping_threshold_g)
     optimizer_g.step()
-    losses['G_total_loss'] = float(loss.detach())
+    losses['G_total_loss'] = loss.detach()
     return losses
 
 

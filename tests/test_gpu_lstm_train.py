@@ -160,7 +160,7 @@ def test_generator_step_with_folded_samples_matches_the_sample_loop():
         losses = parallel.generator_step(args, batch, g, d, opt, label_rng=parallel.make_label_rng(0, 0))
         out[fold] = (losses, [p.detach().clone() for p in g.parameters()])
     for k in out[True][0]:
-        assert abs(out[True][0][k] - out[False][0][k]) < 1e-4 * max(1.0, abs(out[False][0][k])), k
+        assert abs(float(out[True][0][k]) - float(out[False][0][k])) < 1e-4 * max(1.0, abs(float(out[False][0][k]))), k
     moved = 0
     for a, b, p0 in zip(out[True][1], out[False][1], gen.parameters()):
         moved += int(not torch.equal(b, p0.detach()))
@@ -210,7 +210,7 @@ def test_discriminator_step_stacked_batch_matches_two_calls():
     opt.zero_grad()
     loss.backward()
     opt.step()
-    assert abs(out['D_total_loss'] - float(loss)) < 1e-5 * max(1.0, abs(float(loss)))
+    assert abs(float(out['D_total_loss']) - float(loss)) < 1e-5 * max(1.0, abs(float(loss)))
     for a, b in zip(d1.parameters(), d2.parameters()):
         assert float((a - b).abs().max()) < 2e-5
 

@@ -171,6 +171,22 @@ def test_pool_rejects_bad_segments(sgx):
         m(h, torch.tensor([[0, 4]]), pos)              # does not cover the batch
 
 
+def test_graph_modules_reject_mismatched_feature_dims(sgx):
+    """GATEncoder hard-codes GAT(40, ...) (sgan/models.py:242-244): a wiring with encoder_h_dim + bottleneck_dim != 40
+    is a matmul size error in the reference and must be a ValueError here, not an out-of-bounds read in a kernel."""
+    sse = sse_from_sizes([4, 3]).to(DEV)
+    pos, labs = torch.rand(7, 2, device=DEV), torch.zeros(7, 1, device=DEV)
+    gat = sgx['M'].GATEncoder(n_units=None, n_heads=1, dropout=0, alpha=0.2).to(DEV)
+    for width in (32, 48):
+        with pytest.raises(ValueError):
+            gat(torch.randn(7, width, device=DEV), sse, pos, labs)
+        with pytest.raises(ValueError):
+            gat(torch.randn(7, width, device=DEV, requires_grad=True), sse, pos, labs)
+    gcn = sgx['M'].GCNModule(input_dim=40, hidden_dim=72, out_dim=16, gcn_layers=2, final_dim=24).to(DEV)
+    with pytest.raises(ValueError):
+        gcn(torch.randn(7, 32, device=DEV), sse, pos, labs)
+
+
 # ------------------------------------------------------------------ GATEncoder / GCNModule
 @pytest.mark.parametrize('name', ['gat_encoder_h1', 'gat_encoder_h2'])
 def test_gat_encoder_fwd_bwd_vs_golden(sgx, name):

@@ -57,6 +57,37 @@ def _worker(rank, world, port, q):
         assert nbytes == sum(p.numel() for p in net.parameters()) * 4
         for p, g in zip(net.parameters(), full_grads):
             assert torch.allclose(p.grad, g, atol=1e-6), (p.grad - g).abs().max()
+        # (2b) no blocking count exchange needed: the global ped count comes from the global seq_start_end
+        assert parallel.global_ped_count(sse.numpy()) == n
+        assert abs(parallel._weight(n_local, n, 'cpu', None) - w) < 1e-12
+        # (2c) fewer scenes than ranks: rank 1 gets an EMPTY shard, skips its forward, still joins the all-reduce and
+        # ends with the same reduced gradients; a parameter nobody touched keeps grad = None on both ranks
+        one = sse_from_sizes([5])
+        loc1, sse1, mine1 = parallel.shard_batch({'x': x[:, :5]}, one, world, rank)
+        assert (loc1['x'].shape[1], sse1.shape[0], len(mine1)) == ((5, 1, 1) if rank == 0 else (0, 0, 0))
+
+        class Net(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.used = torch.nn.Linear(2, 3)
+                self.passenger = torch.nn.Linear(2, 2)           # like gcn_module in the 'gat' wiring
+        torch.manual_seed(5)
+        net2 = Net()
+        net2.zero_grad()
+        if rank == 0:
+            net2.used(loc1['x'][-1]).square().sum().backward()
+            expect = [net2.used.weight.grad.clone(), net2.used.bias.grad.clone()]
+            parallel.allreduce_gradients(net2)
+        else:
+            net2._sgx_grad_none = frozenset({2, 3})              # what this rank saw on its last non-empty step
+            parallel.allreduce_gradients(net2, ran_forward=False)
+            expect = None
+        both = [None] * world
+        dist.all_gather_object(both, [net2.used.weight.grad, net2.used.bias.grad])
+        assert torch.equal(both[0][0], both[1][0]) and torch.equal(both[0][1], both[1][1])
+        if rank == 0:
+            assert torch.allclose(net2.used.weight.grad, expect[0]) and torch.allclose(net2.used.bias.grad, expect[1])
+        assert net2.passenger.weight.grad is None and net2.passenger.bias.grad is None
         # (3) identically seeded label RNG
         vals = [None] * world
         dist.all_gather_object(vals, parallel.make_label_rng(7, 3).uniform(0.7, 1.2))

@@ -42,14 +42,9 @@ def synth(n_scenes, seed):
                 seq_start_end=t(np.stack([st[:-1], st[1:]], 1).astype(np.int64)))
 
 
-def main():
-    rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
-    local = int(os.environ.get('LOCAL_RANK', 0))
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
-    torch.backends.cudnn.allow_tf32 = False
+def setup(dev, rank, world, scenes_per_rank=64):
+    """-> (args, generator, discriminator, optimizer_g, optimizer_d, batch) for this rank; args.n_global = pedestrians of
+    the global minibatch (no collective needed to find it)."""
     args = SimpleNamespace(obs_len=8, pred_len=12, best_k=20, l2_loss_weight=1.0, clipping_threshold_g=2.0,
                            clipping_threshold_d=0.0)
     torch.manual_seed(0)                                   # identical initial weights on every rank
@@ -66,12 +61,25 @@ def main():
             p.mul_(0.1)
     opt_g = torch.optim.Adam(gen.parameters(), lr=1e-4)
     opt_d = torch.optim.Adam(disc.parameters(), lr=1e-3)
-    data = synth(64 * world, 1239)
+    data = synth(scenes_per_rank * world, 1239)
     tensors = {k: data[k] for k in ('obs_traj', 'pred_traj_gt', 'obs_traj_rel', 'pred_traj_gt_rel', 'obs_traj_g')}
     tensors['0:loss_mask'] = data['loss_mask']
     loc, sse, mine = parallel.shard_batch(tensors, data['seq_start_end'], world, rank)
+    args.n_global = parallel.global_ped_count(data['seq_start_end'].numpy())
     batch = tuple(loc[k].to(dev) for k in ('obs_traj', 'pred_traj_gt', 'obs_traj_rel', 'pred_traj_gt_rel', 'obs_traj_g',
                                            'loss_mask')) + (sse.to(dev),)
+    return args, gen, disc, opt_g, opt_d, batch
+
+
+def main():
+    rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    torch.backends.cudnn.allow_tf32 = False
+    args, gen, disc, opt_g, opt_d, batch = setup(dev, rank, world)
     times = {'d': [], 'g': []}
     for it in range(4):
         rng = parallel.make_label_rng(0, it)
@@ -82,7 +90,7 @@ def main():
                 dist.barrier()
             torch.cuda.synchronize()
             e0.record()
-            losses = fn(args, batch, gen, disc, opt, label_rng=rng)
+            losses = fn(args, batch, gen, disc, opt, label_rng=rng, n_global=args.n_global)
             e1.record()
             torch.cuda.synchronize()
             times[name].append(e0.elapsed_time(e1))
@@ -91,7 +99,7 @@ def main():
         with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA,
                                                 torch.profiler.ProfilerActivity.CPU]) as prof:
             t0 = time.perf_counter()
-            parallel.generator_step(args, batch, gen, disc, opt_g, label_rng=rng)
+            parallel.generator_step(args, batch, gen, disc, opt_g, label_rng=rng, n_global=args.n_global)
             t1 = time.perf_counter()
             torch.cuda.synchronize()
             t2 = time.perf_counter()
@@ -116,7 +124,7 @@ def main():
                           'allreduce_bytes': {'G': sum(p.numel() for p in gen.parameters()) * 4,
                                               'D': sum(p.numel() for p in disc.parameters()) * 4},
                           'params_in_sync': in_sync, 'finite': bool(torch.isfinite(flat).all()),
-                          'last_losses': losses}))
+                          'last_losses': {k: float(v) for k, v in losses.items()}}))
     if world > 1:
         dist.destroy_process_group()
 
