@@ -495,8 +495,9 @@ def main():
         end_grp = dev_in['obs_traj_g'][-1]
         if cfg['wiring'] == 'gat':
             ctx_fn = lambda: gen.gatencoder(ctx_in, dev_in['seq_start_end'], end_pos, end_grp)
-        else:
-            ctx_fn = lambda: gen.mlp_decoder_context(ctx_in)
+        else:   # the path TrajectoryGenerator.context() takes: cat + Linear + ReLU + Linear + ReLU in one launch
+            from group_gan_gcn_gat_b200 import ops as _ops
+            ctx_fn = lambda: _ops.mlp2(gen.mlp_decoder_context, h_enc.view(-1, 32), pool_h)
         ctx_ms = time_call(ctx_fn)
         enc_ms = time_call(lambda: gen.encoder(dev_in['obs_traj_rel']))
         ctx24 = ctx_fn()
@@ -556,7 +557,7 @@ def main():
                          'note': 'HBM-bound by decree (SURVEY 8d: 260 B/ped); in practice issue / tensor-pipe bound, DESIGN.md 4.3'}
         else:
             ctx_bytes = (40 + 24) * 4 * peds
-            ctx_entry = {'op': 'mlp_decoder_context 40->64->24 (+ReLU)', 'bound': 'hbm', 'ms': ctx_ms,
+            ctx_entry = {'op': 'cat + mlp_decoder_context 40->64->24 (mlp2_fused_kernel)', 'bound': 'hbm', 'ms': ctx_ms,
                          'algorithmic_bytes': ctx_bytes, 'achieved': ctx_bytes / (ctx_ms * 1e-3) / 1e9, 'peak': hbm,
                          'unit': 'GB/s', 'frac': ctx_bytes / (ctx_ms * 1e-3) / 1e9 / hbm}
         line = {

@@ -145,7 +145,8 @@ def _decoder_forward_fused(self, last_pos, last_pos_rel, state_tuple, seq_start_
         rel = rel[0]
         curr_pos = rel + last_pos
         pool_h = self.pool_net(h, seq_start_end, curr_pos)
-        h = self.mlp(torch.cat([h, pool_h], dim=1))
+        fused = ops.mlp2(self.mlp, h, pool_h)                       # cat + mlp (models.py:165-166) in one launch
+        h = fused if fused is not None else self.mlp(torch.cat([h, pool_h], dim=1))
         steps.append(rel)
         rel_in, last_pos = rel, curr_pos
     return torch.stack(steps, dim=0), h.unsqueeze(0)
@@ -232,6 +233,11 @@ class TrajectoryGenerator(nn.Module):
         end_pos = obs_traj[-1, :, :]
         if self.pooling_type:
             pool_h = self.pool_net(final_encoder_h, seq_start_end, end_pos)
+            if self.context_type == 'mlp' and self.mlp_decoder_needed():
+                # SGAN-P wiring (models.py:886,898): cat + the two Linear+ReLU layers as one launch at inference
+                fused = ops.mlp2(self.mlp_decoder_context, final_encoder_h.view(-1, self.encoder_h_dim), pool_h)
+                if fused is not None:
+                    return fused
             ctx_in = torch.cat([final_encoder_h.view(-1, self.encoder_h_dim), pool_h], dim=1)
         else:
             ctx_in = final_encoder_h.view(-1, self.encoder_h_dim)
@@ -241,7 +247,8 @@ class TrajectoryGenerator(nn.Module):
             return self.gatencoder(ctx_in, seq_start_end, end_pos, obs_traj_g[-1, :, :])
         if self.context_type == 'gcn':
             return self.gcn_module(ctx_in, seq_start_end, end_pos, obs_traj_g[-1, :, :])
-        return self.mlp_decoder_context(ctx_in)
+        fused = ops.mlp2(self.mlp_decoder_context, ctx_in)
+        return fused if fused is not None else self.mlp_decoder_context(ctx_in)
 
     def decode(self, ctx, obs_traj, obs_traj_rel, seq_start_end, user_noise=None):
         batch = obs_traj_rel.size(1)
@@ -299,4 +306,5 @@ class TrajectoryDiscriminator(nn.Module):
             classifier_input = final_h.squeeze()
         else:
             classifier_input = self.pool_net(final_h.squeeze(), seq_start_end, traj[0])
-        return self.real_classifier(classifier_input)
+        fused = ops.mlp2(self.real_classifier, classifier_input) if classifier_input.dim() == 2 else None
+        return fused if fused is not None else self.real_classifier(classifier_input)

@@ -209,6 +209,51 @@ pool_fwd.register_autograd(_pool_backward, setup_context=_pool_setup)
 
 
 # ---------------------------------------------------------------------------------------------
+# context MLPs (make_mlp with relu, no batch norm, no dropout): one fused launch at inference
+# ---------------------------------------------------------------------------------------------
+def mlp2_plan(seq):
+    """(linear1, linear2) when `seq` is exactly [Linear, ReLU, Linear, ReLU] (what make_mlp builds for batch_norm 0 /
+    dropout 0 / relu) with dims the fused kernel is built for, else None."""
+    import torch.nn as nn
+    mods = list(seq)
+    if len(mods) != 4 or not (isinstance(mods[0], nn.Linear) and isinstance(mods[1], nn.ReLU) and
+                              isinstance(mods[2], nn.Linear) and isinstance(mods[3], nn.ReLU)):
+        return None
+    l1, l2 = mods[0], mods[2]
+    if l1.bias is None or l2.bias is None or l1.weight.dtype != torch.float32 or not l1.weight.is_cuda:
+        return None
+    if not _lib.lib().sgx_mlp2_supported(l1.in_features, l1.out_features, l2.out_features):
+        return None
+    return l1, l2
+
+
+def mlp2(seq, xa, xb=None):
+    """seq(cat([xa, xb], 1)) through sgx_mlp2_fwd, or None when the fused kernel does not apply (autograd needed,
+    unsupported structure / dims): the caller then runs the nn.Sequential itself."""
+    if torch.is_grad_enabled() and (xa.requires_grad or (xb is not None and xb.requires_grad) or
+                                    any(p.requires_grad for p in seq.parameters())):
+        return None
+    if not (xa.is_cuda and xa.dtype == torch.float32 and xa.dim() == 2):
+        return None
+    plan = mlp2_plan(seq)
+    da, db = xa.shape[1], (0 if xb is None else xb.shape[1])
+    if plan is None or da + db != plan[0].in_features or da % 4 or db % 4:
+        return None
+    l1, l2 = plan
+    xa = xa.contiguous()
+    xb = None if xb is None else _f32(xb, 'xb')
+    out = torch.empty(xa.shape[0], l2.out_features, dtype=torch.float32, device=xa.device)
+    if xa.shape[0] == 0:
+        return out
+    L = _lib.lib()
+    with torch.cuda.device(xa.device):
+        _lib.check(L.sgx_mlp2_fwd(_ptr(xa), da, _ptr(xb), db, xa.shape[0], _ptr(l1.weight.contiguous()), _ptr(l1.bias),
+                                  _ptr(l2.weight.contiguous()), _ptr(l2.bias), l1.out_features, l2.out_features,
+                                  _ptr(out), _stream(xa)), 'sgx_mlp2_fwd')
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
 # GCNModule
 # ---------------------------------------------------------------------------------------------
 def _check_gcn_shapes(x, W0, W1, V0, V1, Wo, bo):

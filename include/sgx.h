@@ -145,6 +145,19 @@ int sgx_pool_bwd(const float* h, const float* pos, const float* out, const int32
                  float* grad_W2, float* grad_b2, void* workspace, int64_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * make_mlp([in, mid, out], activation relu, batch_norm 0, dropout 0) forward (sgan/models.py:7-20) in one launch,
+ * inference only:   out = ReLU(W2 ReLU(W1 [xa ; xb] + b1) + b2)
+ * at its call sites sgan/models.py:898 (mlp_decoder_context(cat(final_encoder_h, pool_h)), the SGAN-P wiring),
+ * :165-166 (decoder.mlp(cat(decoder_h, pool_h))) and :990 (real_classifier).  xa [batch,da], xb [batch,db] or NULL with
+ * db = 0 (the concatenation is folded into the load), W1 [HID,da+db] b1 [HID] W2 [OUT,HID] b2 [OUT] (nn.Linear layout),
+ * out [batch,OUT].  Built for da+db in {32,40,48}, HID 64, OUT in {1,24,32}: sgx_mlp2_supported.
+ */
+int sgx_mlp2_supported(int32_t IN, int32_t HID, int32_t OUT);
+int sgx_mlp2_fwd(const float* xa, int32_t da, const float* xb, int32_t db, int64_t batch, const float* W1,
+                 const float* b1, const float* W2, const float* b2, int32_t HID, int32_t OUT, float* out,
+                 void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * GCNModule.forward (sgan/models.py:628-712) with gcn_layers = 2:
  *   x [batch,IN]  W0 [IN,HID] W1 [HID,OUT] (intra)  V0 [OUT,HID] V1 [HID,OUT] (inter)
  *   Wo [FIN,2*OUT] bo [FIN]  ->  out [batch,FIN]

@@ -757,3 +757,33 @@ def test_generator_block_diagonal_over_scenes_at_bench_size(sgx):
         seen[idx] = True
         assert_close(out, whole[:, idx.to(DEV)], 1e-6, 'LPT shard %d' % rank)
     assert bool(seen.all())
+
+
+# ------------------------------------------------------------------ fused context MLP (make_mlp at models.py:898, 165-166, 990)
+@pytest.mark.parametrize('dims', [(32, 8, 64, 24), (32, 8, 64, 32), (32, 0, 64, 24), (48, 0, 64, 1), (40, 8, 64, 32), (24, 8, 64, 1)])
+@pytest.mark.parametrize('batch', [1, 31, 32, 33, 1000, 70001])
+def test_fused_mlp_matches_sequential(sgx, dims, batch):
+    """ops.mlp2 == make_mlp([...])(cat([xa, xb], 1)) (Linear, ReLU, Linear, ReLU; sgan/models.py:7-20) to 1e-5, for every
+    built (in, mid, out), batches around the 32-row warp chunk, with and without the folded concatenation."""
+    da, db, hid, out = dims
+    torch.manual_seed(da + db + out + batch)
+    seq = sgx['M'].make_mlp([da + db, hid, out], activation='relu', batch_norm=False, dropout=0).to(DEV)
+    xa = torch.randn(batch, da, device=DEV)
+    xb = torch.randn(batch, db, device=DEV) if db else None
+    with torch.no_grad():
+        ref = seq(xa if xb is None else torch.cat([xa, xb], 1))
+        got = sgx['ops'].mlp2(seq, xa, xb)
+    assert got is not None and got.shape == ref.shape
+    assert_close(got, ref.double(), 1e-5, 'mlp2 %s' % (dims,))
+
+
+def test_fused_mlp_declines_what_it_cannot_do(sgx):
+    M, ops = sgx['M'], sgx['ops']
+    x = torch.randn(10, 40, device=DEV)
+    assert ops.mlp2(M.make_mlp([40, 64, 24], batch_norm=True).to(DEV), x) is None            # BatchNorm inside
+    assert ops.mlp2(M.make_mlp([40, 128, 24], batch_norm=False).to(DEV), x) is None          # mid width not built
+    assert ops.mlp2(M.make_mlp([40, 64, 24], activation='leakyrelu', batch_norm=False).to(DEV), x) is None
+    seq = M.make_mlp([40, 64, 24], batch_norm=False).to(DEV)
+    assert ops.mlp2(seq, x.clone().requires_grad_(True)) is None                             # autograd -> torch path
+    with torch.no_grad():
+        assert ops.mlp2(seq, x) is not None
