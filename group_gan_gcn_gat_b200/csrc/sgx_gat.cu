@@ -17,6 +17,7 @@
 #include <stdlib.h>
 
 #include "sgx_common.cuh"
+#include "sgx_gat_fused.cuh"
 #include "sgx_warp_mma.cuh"
 
 namespace sgx {
@@ -34,7 +35,6 @@ template <int MODE>
 __device__ __forceinline__ bool is_neighbour(const int32_t* __restrict__ leader, int li, int q) {
     return MODE == INTRA ? (leader[q] == li) : (leader[q] == q);
 }
-__device__ __forceinline__ float lrelu(float v, float alpha) { return v > 0.f ? v : alpha * v; }
 __device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : expm1f(v); }
 
 // one thread per node: hp_i = sum_j softmax_j(lrelu(s_i + t_j)) Wh_j  over the node's neighbourhood
@@ -299,7 +299,6 @@ __global__ void gat_pool_bwd_kernel(const float* __restrict__ dcat, const float*
     dX1[idx] = dcat[(int64_t)p * 2 * OUT + o] + __frcp_rn((float)gsize[p]) * dXg[(int64_t)leader[p] * OUT + o];
 }
 
-constexpr int HID = 72, OUT = 16;
 
 struct Level {   // buffers of one GAT (intra or inter)
     float *Wh1, *st1, *x1a, *Wh2, *st2, *U, *Xo;
@@ -420,9 +419,6 @@ static int gat_forward(const float* x, const int32_t* leader, const int32_t* gsi
 // wavefronts and feeds four lane-FMAs, so one weight word per FMA caps the FMA pipe at 50 %; the kernel sits at 65 %
 // of that cap.  The next step is register blocking over two peds per lane (halves the weight wavefronts).
 // ------------------------------------------------------------------------------------------------
-constexpr int RS = 76;                 // row stride (floats) of the 72-wide row buffer: 16 B aligned, conflict-free STS.128
-constexpr int RA = 20;                 // row stride of the 16-wide leader buffer (Xg, Yg); x itself is staged in the
-                                       // lane's own 72-wide row, which only that lane reads before overwriting it with Wh
 constexpr int FUSED_WARPS = 12;
 constexpr int FUSED_SCRATCH = 32 * RA + 32 * RS + 32 * 16 + 32 * 2 + 32;   // floats per warp
 
@@ -432,14 +428,6 @@ struct FusedW {                        // shared-memory weight block (floats)
     float Wo[24 * 2 * OUT], bo[24];
 };
 
-// ex2.approx based exp / ELU for the fused kernel (2 ulp; the general path keeps expf / expm1f): expm1f alone was
-// ~25 instructions per element, more dynamic instructions than the 40x72 GEMV it follows.
-__device__ __forceinline__ float fexp(float v) {
-    float r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v * 1.4426950408889634f));
-    return r;
-}
-__device__ __forceinline__ float felu(float v) { return v > 0.f ? v : fexp(v) - 1.f; }
 
 // y[0..NO) = sum_c xrow[c] * W[c][0..NO)   (W row-major [NI][NO] in smem, xrow in smem)
 template <int NI, int NO>
@@ -498,34 +486,6 @@ __device__ __forceinline__ void attend_smem(const float* __restrict__ rows, cons
     for (int f = 0; f < F; ++f) hp[f] *= inv;
 }
 
-
-// attention of one node over the lanes set in `mask` (its group's members / its scene's leaders), ascending lane order
-// = the order of attend_smem, so the two give bit-identical sums; iterates the neighbours only instead of the scene.
-template <int F, int STRIDE>
-__device__ __forceinline__ void attend_mask(const float* __restrict__ rows, const float2* __restrict__ st, uint32_t mask,
-                                            float s_i, float alpha, float (&hp)[F]) {
-    float m = -INFINITY;
-    for (uint32_t mm = mask; mm; mm &= mm - 1) m = fmaxf(m, lrelu(s_i + st[__ffs(mm) - 1].y, alpha));
-    float den = 0.f;
-#pragma unroll
-    for (int f = 0; f < F; ++f) hp[f] = 0.f;
-    for (uint32_t mm = mask; mm; mm &= mm - 1) {
-        const int q = __ffs(mm) - 1;
-        const float w = fexp(lrelu(s_i + st[q].y, alpha) - m);
-        den += w;
-        const float4* row = reinterpret_cast<const float4*>(rows + q * STRIDE);
-#pragma unroll
-        for (int f = 0; f < F / 4; ++f) {
-            const float4 v = row[f];
-            hp[4 * f] = fmaf(w, v.x, hp[4 * f]); hp[4 * f + 1] = fmaf(w, v.y, hp[4 * f + 1]);
-            hp[4 * f + 2] = fmaf(w, v.z, hp[4 * f + 2]); hp[4 * f + 3] = fmaf(w, v.w, hp[4 * f + 3]);
-        }
-    }
-    const float inv = 1.f / den;
-#pragma unroll
-    for (int f = 0; f < F; ++f) hp[f] *= inv;
-}
-
 // y[0..NO) = sum_c x[c] * W[c][0..NO) with x in registers (fully unrolled; used for the 72 -> 16 maps)
 template <int NI, int NO>
 __device__ __forceinline__ void gemv_regs(const float (&x)[NI], const float* __restrict__ W, float (&y)[NO]) {
@@ -548,13 +508,6 @@ __device__ __forceinline__ void gemv_regs(const float (&x)[NI], const float* __r
 }
 
 template <int F>
-__device__ __forceinline__ void store_row(float* __restrict__ row, const float (&v)[F]) {
-#pragma unroll
-    for (int f = 0; f < F / 4; ++f)
-        reinterpret_cast<float4*>(row)[f] = make_float4(v[4 * f], v[4 * f + 1], v[4 * f + 2], v[4 * f + 3]);
-}
-
-template <int F>
 __device__ __forceinline__ float2 scores(const float (&wh)[F], const float* __restrict__ a) {
     float s = 0.f, t = 0.f;
 #pragma unroll
@@ -564,19 +517,6 @@ __device__ __forceinline__ float2 scores(const float (&wh)[F], const float* __re
         t = fmaf(wh[4 * f], v.x, t); t = fmaf(wh[4 * f + 1], v.y, t); t = fmaf(wh[4 * f + 2], v.z, t); t = fmaf(wh[4 * f + 3], v.w, t);
     }
     return make_float2(s, t);
-}
-
-template <int F>
-__device__ __forceinline__ void elu_logsoftmax(float (&v)[F]) {
-    float mx = -INFINITY;
-#pragma unroll
-    for (int f = 0; f < F; ++f) { v[f] = felu(v[f]); mx = fmaxf(mx, v[f]); }
-    float sum = 0.f;
-#pragma unroll
-    for (int f = 0; f < F; ++f) sum += fexp(v[f] - mx);
-    const float lse = mx + logf(sum);
-#pragma unroll
-    for (int f = 0; f < F; ++f) v[f] -= lse;
 }
 
 template <int IN, int FIN>
@@ -739,44 +679,6 @@ gat_fused_fwd_kernel(const float* __restrict__ x, const int32_t* __restrict__ le
 // ------------------------------------------------------------------------------------------------
 constexpr int FUSEDM_WARPS = 14;       // tensor-core kernel: x1 rows alias the wide row buffer => 12.7 KB per warp; 14 warps per SM (15: slower)
 constexpr int FUSEDM_SCRATCH = 32 * RA + 32 * RS + 32 * 2 + 32;
-constexpr int SW1 = 88;                // row stride of the [K][72+2 (+pad)] weight blocks: 88 % 32 = 24 -> conflict-free B fragments
-constexpr int SW2 = 24;                // row stride of the [K][16+2 (+pad)] and [32][24] blocks
-struct FusedWm {
-    float Wi[40 * SW1], Wio[HID * SW2], We[OUT * SW1], Weo[HID * SW2], WoT[2 * OUT * SW2], bo[24];
-};
-
-// weight blocks [K][N + 2 score columns + zero padding]: column N = W a[:N], N+1 = W a[N:]; Wo transposed
-template <int IN, int FIN>
-__device__ __forceinline__ void fused_load_weights(FusedWm& w, const float* __restrict__ Wi, const float* __restrict__ ai,
-                                                   const float* __restrict__ Wio, const float* __restrict__ aio,
-                                                   const float* __restrict__ We, const float* __restrict__ ae,
-                                                   const float* __restrict__ Weo, const float* __restrict__ aeo,
-                                                   const float* __restrict__ Wo, const float* __restrict__ bo) {
-    {
-        auto fill = [&](float* dst, int stride, const float* W, const float* a, int K, int N) {
-            for (int e = threadIdx.x; e < K * stride; e += blockDim.x) {
-                const int k = e / stride, n = e % stride;
-                float v = 0.f;
-                if (n < N) v = W[k * N + n];
-                else if (n < N + 2) {
-                    const float* av = a + (n - N) * N;
-                    for (int c = 0; c < N; ++c) v = fmaf(W[k * N + c], av[c], v);
-                }
-                dst[e] = v;
-            }
-        };
-        fill(w.Wi, SW1, Wi, ai, IN, HID);
-        fill(w.Wio, SW2, Wio, aio, HID, OUT);
-        fill(w.We, SW1, We, ae, OUT, HID);
-        fill(w.Weo, SW2, Weo, aeo, HID, OUT);
-        for (int e = threadIdx.x; e < 2 * OUT * SW2; e += blockDim.x) {
-            const int k = e / SW2, n = e % SW2;
-            w.WoT[e] = (n < FIN) ? Wo[n * 2 * OUT + k] : 0.f;
-        }
-        for (int e = threadIdx.x; e < FIN; e += blockDim.x) w.bo[e] = bo[e];
-    }
-}
-
 template <int IN, int FIN>
 __global__ void __launch_bounds__(FUSEDM_WARPS * 32)
 gat_fused_mma_kernel(const float* __restrict__ x, const int32_t* __restrict__ leader, const int32_t* __restrict__ gsize,

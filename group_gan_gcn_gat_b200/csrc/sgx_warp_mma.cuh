@@ -65,4 +65,96 @@ __device__ __forceinline__ void warp_gemm_3xtf32(const float* __restrict__ A, co
     __syncwarp();
 }
 
+
+// C [32 x 8 NT] = A [32 x K] . Bt  with Bt(k, n) = B[n * SB + k]: the right operand is a row-major block whose ROWS are
+// indexed by the output column (dX = dY W^T read straight from the forward's [K_in][N_out] weight block).  Same
+// fragment conventions as warp_gemm_3xtf32.  B fragment loads are 2-way bank conflicted for SB = 24 / 88 (g and g + 4).
+template <int K, int NT, int SA, int SB, int MT = 2, class Store>
+__device__ __forceinline__ void warp_gemm_3xtf32_bt(const float* __restrict__ A, const float* __restrict__ B, int lane,
+                                                    Store&& store) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll 1
+    for (int mt = 0; mt < MT; ++mt) {
+        float acc[NT][4];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+#pragma unroll 1
+        for (int ks = 0; ks < K / 8; ++ks) {
+            const float* ar = A + (mt * 16 + g) * SA + ks * 8 + t;
+            uint32_t ah[4], al[4];
+            split_tf32(ar[0], ah[0], al[0]);
+            split_tf32(ar[8 * SA], ah[1], al[1]);
+            split_tf32(ar[4], ah[2], al[2]);
+            split_tf32(ar[8 * SA + 4], ah[3], al[3]);
+            const float* br = B + g * SB + ks * 8 + t;
+            constexpr int NG = (NT % 5 == 0) ? 5 : (NT % 4 == 0) ? 4 : (NT % 3 == 0) ? 3 : (NT % 2 == 0) ? 2 : 1;
+#pragma unroll
+            for (int n0 = 0; n0 < NT; n0 += NG) {
+                uint32_t bh0[NG], bl0[NG], bh1[NG], bl1[NG];
+#pragma unroll
+                for (int j = 0; j < NG; ++j) {
+                    split_tf32(br[(n0 + j) * 8 * SB], bh0[j], bl0[j]);
+                    split_tf32(br[(n0 + j) * 8 * SB + 4], bh1[j], bl1[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < NG; ++j) mma_tf32(acc[n0 + j], al, bh0[j], bh1[j]);
+#pragma unroll
+                for (int j = 0; j < NG; ++j) mma_tf32(acc[n0 + j], ah, bl0[j], bl1[j]);
+#pragma unroll
+                for (int j = 0; j < NG; ++j) mma_tf32(acc[n0 + j], ah, bh0[j], bh1[j]);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) store(mt, nt, acc[nt]);
+    }
+    __syncwarp();
+}
+
+// C [M x 8 NT] = A^T . B over the warp's 32 rows (K = 32): A [32][SA] (columns 0..M-1 used), B [32][SB] -- the
+// per-chunk parameter gradient dW = input^T dY.  store(m0, nt, acc): acc[0..1] = rows m0 + lane/4, columns
+// nt*8 + 2 (lane%4) + {0,1}; acc[2..3] = row + 8.  Rows >= M of the last m-tile are computed from clamped columns and
+// must be dropped by the caller.  Every one of the 32 rows of A and B must be finite (zero for dead lanes).
+template <int M, int NT, int SA, int SB, class Store>
+__device__ __forceinline__ void warp_gemm_3xtf32_at(const float* __restrict__ A, const float* __restrict__ B, int lane,
+                                                    Store&& store) {
+    const int g = lane >> 2, t = lane & 3;
+    constexpr int MT = (M + 15) / 16;
+#pragma unroll 1
+    for (int mt = 0; mt < MT; ++mt) {
+        float acc[NT][4];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+        const int m_lo = (mt * 16 + g) < M ? (mt * 16 + g) : (M - 1), m_hi = (mt * 16 + g + 8) < M ? (mt * 16 + g + 8) : (M - 1);
+#pragma unroll 1
+        for (int ks = 0; ks < 4; ++ks) {
+            const float* ar = A + (ks * 8 + t) * SA;
+            uint32_t ah[4], al[4];
+            split_tf32(ar[m_lo], ah[0], al[0]);
+            split_tf32(ar[m_hi], ah[1], al[1]);
+            split_tf32(ar[4 * SA + m_lo], ah[2], al[2]);
+            split_tf32(ar[4 * SA + m_hi], ah[3], al[3]);
+            const float* br = B + (ks * 8 + t) * SB + g;
+            constexpr int NG = (NT % 3 == 0) ? 3 : (NT % 2 == 0) ? 2 : 1;
+#pragma unroll
+            for (int n0 = 0; n0 < NT; n0 += NG) {
+                uint32_t bh0[NG], bl0[NG], bh1[NG], bl1[NG];
+#pragma unroll
+                for (int j = 0; j < NG; ++j) {
+                    split_tf32(br[(n0 + j) * 8], bh0[j], bl0[j]);
+                    split_tf32(br[4 * SB + (n0 + j) * 8], bh1[j], bl1[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < NG; ++j) mma_tf32(acc[n0 + j], al, bh0[j], bh1[j]);
+#pragma unroll
+                for (int j = 0; j < NG; ++j) mma_tf32(acc[n0 + j], ah, bl0[j], bl1[j]);
+#pragma unroll
+                for (int j = 0; j < NG; ++j) mma_tf32(acc[n0 + j], ah, bh0[j], bh1[j]);
+            }
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) store(mt * 16, nt, acc[nt]);
+    }
+}
+
 }  // namespace sgx

@@ -394,7 +394,10 @@ def _(x, leader, gsize, ped_start, ped_end, n_scenes, Wi, ai, Wio, aio, We, ae, 
 @_custom_op('sgx::gat_encoder_bwd')
 def gat_encoder_bwd(x: Tensor, grad_out: Tensor, leader: Tensor, gsize: Tensor, ped_start: Tensor, ped_end: Tensor,
                     n_scenes: int, Wi: Tensor, ai: Tensor, Wio: Tensor, aio: Tensor, We: Tensor, ae: Tensor,
-                    Weo: Tensor, aeo: Tensor, Wo: Tensor, bo: Tensor, alpha: float) -> List[Tensor]:
+                    Weo: Tensor, aeo: Tensor, Wo: Tensor, bo: Tensor, alpha: float, scene_start: Tensor,
+                    chunk_scene: Tensor, n_chunks: int, chunk_cap: int) -> List[Tensor]:
+    """n_chunks > 0 with chunk_cap 32 (every scene <= 32 peds, n_heads 1, dims 40/72/16/24) selects the single-launch
+    backward (forward recomputed inside the kernel); otherwise the general multi-pass path."""
     x, grad_out = _f32(x, 'x'), _f32(grad_out, 'grad_out')
     ps = [t.contiguous() for t in (Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo)]
     _check_gat_shapes(x, *ps)
@@ -403,8 +406,16 @@ def gat_encoder_bwd(x: Tensor, grad_out: Tensor, leader: Tensor, gsize: Tensor, 
     OUT, FIN = Wio.shape[1], Wo.shape[0]
     grads = [torch.empty_like(t) for t in [x] + ps]
     L = _lib.lib()
-    ws = _ws(L.sgx_gat_encoder_ws_bytes(batch, n_scenes, nh, IN, HID, OUT, FIN), x.device)
     with torch.cuda.device(x.device):
+        if n_chunks > 0 and chunk_cap == 32 and nh == 1 and (IN, HID, OUT, FIN) == (40, 72, 16, 24):
+            ws = _ws(L.sgx_gat_encoder_fused_bwd_ws_bytes(), x.device)
+            _lib.check(L.sgx_gat_encoder_fused_bwd(_ptr(x), _ptr(grad_out), _ptr(leader), _ptr(gsize), _ptr(ped_start),
+                                                   _ptr(ped_end), _ptr(scene_start), _ptr(chunk_scene), n_chunks,
+                                                   *[_ptr(p) for p in ps], alpha, nh, IN, HID, OUT, FIN,
+                                                   *[_ptr(g) for g in grads], _ptr(ws), ws.numel(), _stream(x)),
+                       'sgx_gat_encoder_fused_bwd')
+            return grads
+        ws = _ws(L.sgx_gat_encoder_ws_bytes(batch, n_scenes, nh, IN, HID, OUT, FIN), x.device)
         _lib.check(L.sgx_gat_encoder_bwd(_ptr(x), _ptr(grad_out), _ptr(leader), _ptr(gsize), _ptr(ped_start),
                                          _ptr(ped_end), batch, n_scenes, *[_ptr(p) for p in ps], alpha, nh, IN, HID,
                                          OUT, FIN, *[_ptr(g) for g in grads], _ptr(ws), ws.numel(), _stream(x)),
@@ -413,20 +424,24 @@ def gat_encoder_bwd(x: Tensor, grad_out: Tensor, leader: Tensor, gsize: Tensor, 
 
 
 @gat_encoder_bwd.register_fake
-def _(x, grad_out, leader, gsize, ped_start, ped_end, n_scenes, Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo, alpha):
+def _(x, grad_out, leader, gsize, ped_start, ped_end, n_scenes, Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo, alpha,
+      scene_start, chunk_scene, n_chunks, chunk_cap):
     return [torch.empty_like(t) for t in (x, Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo)]
 
 
 def _gat_setup(ctx, inputs, output):
     x, leader, gsize, ps, pe, S, *rest = inputs
     params, alpha = rest[:10], rest[10]
-    ctx.save_for_backward(x, leader, gsize, ps, pe, *params)
-    ctx.n_scenes, ctx.alpha = S, alpha
+    scene_start, chunk_scene, n_chunks = rest[11], rest[12], rest[13]
+    chunk_cap = rest[14] if len(rest) > 14 else 32
+    ctx.save_for_backward(x, leader, gsize, ps, pe, scene_start, chunk_scene, *params)
+    ctx.n_scenes, ctx.alpha, ctx.n_chunks, ctx.chunk_cap = S, alpha, n_chunks, chunk_cap
 
 
 def _gat_backward(ctx, grad_out):
-    x, leader, gsize, ps, pe, *params = ctx.saved_tensors
-    g = gat_encoder_bwd(x, grad_out.contiguous(), leader, gsize, ps, pe, ctx.n_scenes, *params, ctx.alpha)
+    x, leader, gsize, ps, pe, scene_start, chunk_scene, *params = ctx.saved_tensors
+    g = gat_encoder_bwd(x, grad_out.contiguous(), leader, gsize, ps, pe, ctx.n_scenes, *params, ctx.alpha, scene_start,
+                        chunk_scene, ctx.n_chunks, ctx.chunk_cap)
     return (g[0], None, None, None, None, None, *g[1:], None, None, None, None, None)
 
 

@@ -219,6 +219,21 @@ int sgx_gat_encoder_bwd(const float* x, const float* grad_out, const int32_t* le
                         float* grad_We, float* grad_ae, float* grad_Weo, float* grad_aeo, float* grad_Wo,
                         float* grad_bo, void* workspace, int64_t ws_bytes, void* stream);
 
+/* GATEncoder backward in one launch (+ a 30 KB reduction) for the batches sgx_gat_encoder_fused_fwd with chunk_cap 32
+ * covers (every scene <= 32 peds, n_heads 1, dims 40/72/16/24): the forward is recomputed per chunk inside the kernel,
+ * nothing but x, grad_out and grad_x touches HBM.  Gradient buffers are overwritten.  workspace:
+ * sgx_gat_encoder_fused_bwd_ws_bytes() (per-CTA gradient blocks). */
+int64_t sgx_gat_encoder_fused_bwd_ws_bytes(void);
+int sgx_gat_encoder_fused_bwd(const float* x, const float* grad_out, const int32_t* leader, const int32_t* group_size,
+                              const int32_t* ped_start, const int32_t* ped_end, const int32_t* scene_start,
+                              const int32_t* chunk_scene, int64_t n_chunks, const float* Wi, const float* ai,
+                              const float* Wio, const float* aio, const float* We, const float* ae, const float* Weo,
+                              const float* aeo, const float* Wo, const float* bo, float alpha, int32_t n_heads,
+                              int32_t IN, int32_t HID, int32_t OUT, int32_t FIN, float* grad_x, float* grad_Wi,
+                              float* grad_ai, float* grad_Wio, float* grad_aio, float* grad_We, float* grad_ae,
+                              float* grad_Weo, float* grad_aeo, float* grad_Wo, float* grad_bo, void* workspace,
+                              int64_t ws_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Fused per-pedestrian LSTM recurrences (inference), SURVEY.md 8f row f1.
  * Encoder.forward (sgan/models.py:62-92): obs_rel [T,batch,2] -> Linear(2,E) -> LSTM(E,H) from zero state ->

@@ -787,3 +787,46 @@ def test_fused_mlp_declines_what_it_cannot_do(sgx):
     assert ops.mlp2(seq, x.clone().requires_grad_(True)) is None                             # autograd -> torch path
     with torch.no_grad():
         assert ops.mlp2(seq, x) is not None
+
+
+# ------------------------------------------------------------------ single-launch GATEncoder backward
+@pytest.mark.parametrize('sizes', [[32], [32, 32, 1], [31, 2, 32, 1, 1, 30], [1] * 70, [3, 2, 7, 13, 4, 1], [2] * 500, [14, 9, 1, 27]])
+def test_gat_encoder_fused_backward_vs_oracle_autograd(sgx, sizes):
+    """Scenes <= 32 peds take gat_fused_bwd_kernel (forward recomputed per warp chunk, 3xTF32 warp GEMMs for dX and dW,
+    per-CTA gradient blocks): every gradient against torch autograd through the CPU oracle of sgan/models.py:254-294,
+    and against the general multi-pass backward."""
+    rng = np.random.RandomState(sum(sizes) + len(sizes))
+    torch.manual_seed(sum(sizes))
+    sse = sse_from_sizes(sizes)
+    n = sum(sizes)
+    labs = torch.tensor(np.where(rng.rand(n) < 0.2, 0, rng.randint(1, 5, size=n)), dtype=torch.float32).view(-1, 1)
+    x, pos, up = torch.randn(n, 40), torch.rand(n, 2), torch.randn(n, 24)
+    m = sgx['M'].GATEncoder(n_units=None, n_heads=1, dropout=0, alpha=0.2)
+    sd = {k: v.clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    xr = x.clone().requires_grad_(True)
+    (O.gat_encoder(xr, sse, pos, labs, sd, '', 0.2, 1) * up).sum().backward()
+    m = m.to(DEV)
+    xg = x.to(DEV).requires_grad_(True)
+    out = m(xg, sse.to(DEV), pos.to(DEV), labs.to(DEV))
+    (out * up.to(DEV)).sum().backward()
+    floor = 1e-2 * max(float(v.grad.abs().max()) for v in sd.values())
+    assert_close(xg.grad, xr.grad, 5e-5, "dx %s" % sizes[:3], floor=floor)
+    for k, p in m.named_parameters():
+        # the attention vectors' gradients are sums of terms that cancel to ~1e-3 of their size (the reference's own
+        # fp32 result moves by this much under a different summation order): 1e-4 of the largest gradient for those
+        assert_close(p.grad, sd[k].grad, 1e-4 if k.endswith('.a') else 5e-5, 'd%s %s' % (k, sizes[:3]), floor=floor)
+    # the general path on the same inputs (n_chunks = 0)
+    from group_gan_gcn_gat_b200.schedule import get_schedule
+    sched = get_schedule(sse, DEV)
+    groups = sgx['ops'].group_ids(labs.to(DEV).reshape(-1), sched.ped_start, sched.ped_end, sched.scene_start)
+    Wi, ai, Wio, aio = m.gat_intra.stacked()
+    We, ae, Weo, aeo = m.gat_inter.stacked()
+    ps = [t.detach() for t in (Wi, ai, Wio, aio, We, ae, Weo, aeo, m.out_embedding.weight, m.out_embedding.bias)]
+    chunk_scene, n_chunks = sched.chunks(32)
+    args = (xg.detach(), up.to(DEV), groups[0], groups[1], sched.ped_start, sched.ped_end, sched.n_scenes, *ps, 0.2,
+            sched.scene_start, chunk_scene)
+    fused = sgx['ops'].gat_encoder_bwd(*args, n_chunks, 32)
+    general = sgx['ops'].gat_encoder_bwd(*args, 0, 32)
+    assert n_chunks > 0
+    for a, b in zip(fused, general):
+        assert_close(a, b, 1e-4, 'fused vs general backward', floor=floor)

@@ -79,7 +79,7 @@ def cfg4():
     for m in gen.modules():
         if isinstance(m, torch.nn.Linear):
             torch.nn.init.kaiming_normal_(m.weight)
-    for precision in ('bf16', 'fp32'):
+    for precision in ('fp32', 'bf16', 'fp32-simt'):      # fp32 = the tcgen05 kernel with fp16 hi/lo operand splits
         gen.pool_net.precision = precision
         gen.decoder.pool_net.precision = precision
         for n in (64, 128, 256, 512, 1024):
