@@ -110,7 +110,8 @@ def variety_l2(l2_raw_per_sample, loss_mask, sched):
     return (per_scene.min(dim=1).values / denom).sum()
 
 
-def discriminator_step(args, batch, generator, discriminator, optimizer_d, label_rng=None, group=None, n_global=None):
+def discriminator_step(args, batch, generator, discriminator, optimizer_d, label_rng=None, group=None, n_global=None,
+                       noise=None):
     """scripts/train.py:395-429 on this rank's shard; gradients are all-reduced before the optimizer step.
     n_global: pedestrians of the global minibatch (global_ped_count); without it one extra blocking all-reduce finds it."""
     (obs_traj, pred_traj_gt, obs_traj_rel, pred_traj_gt_rel, obs_traj_g, loss_mask, seq_start_end) = batch
@@ -129,8 +130,8 @@ def discriminator_step(args, batch, generator, discriminator, optimizer_d, label
     # The reference leaves the generator graph attached here (scripts/train.py:404-409) and back-propagates the D loss
     # into generator .grad buffers that optimizer_g.zero_grad() discards before they are ever used; running the
     # generator without autograd gives the same D gradients and takes the inference kernels.
-    with torch.no_grad():
-        fake_rel = generator(obs_traj, obs_traj_rel, seq_start_end, obs_traj_g)
+    with torch.no_grad():    # noise: optional [rows, *noise_dim] for this rank's scenes (parity runs under sharding)
+        fake_rel = generator(obs_traj, obs_traj_rel, seq_start_end, obs_traj_g, user_noise=noise)
         fake = relative_to_abs(fake_rel, obs_traj[-1])
     if _batch_independent(discriminator):
         # fake and real trajectories as ONE discriminator batch of 2 x scenes (same weights, independent scenes)
@@ -165,12 +166,14 @@ def _batch_independent(module):
     return True
 
 
-def _folded_samples(generator, obs_traj, obs_traj_rel, obs_traj_g, seq_start_end, k):
-    """k generator samples as one forward over k copies of the batch -> fake_rel [pred_len, k * batch, 2] (sample-major)."""
+def _folded_samples(generator, obs_traj, obs_traj_rel, obs_traj_g, seq_start_end, k, noise=None):
+    """k generator samples as one forward over k copies of the batch -> fake_rel [pred_len, k * batch, 2] (sample-major).
+    noise: optional [k, rows, *noise_dim] (rows = scenes for 'global' mixing) instead of k get_noise draws."""
     from .models import get_noise
     n, s = obs_traj.shape[1], seq_start_end.shape[0]
-    noise = None
-    if generator.noise_dim:
+    if noise is not None:
+        noise = noise.reshape(-1, *noise.shape[2:]).to(obs_traj.device)
+    elif generator.noise_dim:
         rows = s if generator.noise_mix_type == 'global' else n
         noise = torch.cat([get_noise((rows,) + tuple(generator.noise_dim), generator.noise_type, obs_traj.device)
                            for _ in range(k)], dim=0)
@@ -180,7 +183,8 @@ def _folded_samples(generator, obs_traj, obs_traj_rel, obs_traj_g, seq_start_end
                      user_noise=noise)
 
 
-def generator_step(args, batch, generator, discriminator, optimizer_g, label_rng=None, group=None, n_global=None):
+def generator_step(args, batch, generator, discriminator, optimizer_g, label_rng=None, group=None, n_global=None,
+                   noise=None):
     """scripts/train.py:432-484: best-of-K variety loss + adversarial term on the last sample."""
     (obs_traj, pred_traj_gt, obs_traj_rel, pred_traj_gt_rel, obs_traj_g, loss_mask, seq_start_end) = batch
     n_local = obs_traj.shape[1]
@@ -201,14 +205,15 @@ def generator_step(args, batch, generator, discriminator, optimizer_g, label_rng
         # The best_k samples share weights and inputs and differ only in the noise: run them as ONE forward / backward
         # over best_k copies of the batch (SURVEY 8d cfg 4/5: "K folded into the batch dimension").  Same noise stream
         # as the loop (one get_noise draw per sample, in order), same loss terms, 1/best_k of the launches.
-        fake_all = _folded_samples(generator, obs_traj, obs_traj_rel, obs_traj_g, seq_start_end, args.best_k)
+        fake_all = _folded_samples(generator, obs_traj, obs_traj_rel, obs_traj_g, seq_start_end, args.best_k, noise)
         for k in range(args.best_k):
             fake_rel = fake_all[:, k * n_local:(k + 1) * n_local]
             if args.l2_loss_weight > 0:
                 raws.append(args.l2_loss_weight * l2_loss(fake_rel, pred_traj_gt_rel, mask, mode='raw'))
     else:
-        for _ in range(args.best_k):
-            fake_rel = generator(obs_traj, obs_traj_rel, seq_start_end, obs_traj_g)
+        for k in range(args.best_k):     # noise: optional [best_k, rows, *noise_dim] (parity runs under sharding)
+            fake_rel = generator(obs_traj, obs_traj_rel, seq_start_end, obs_traj_g,
+                                 user_noise=None if noise is None else noise[k])
             if args.l2_loss_weight > 0:
                 raws.append(args.l2_loss_weight * l2_loss(fake_rel, pred_traj_gt_rel, mask, mode='raw'))
     loss = obs_traj.new_zeros(())
