@@ -442,8 +442,13 @@ def main():
                 done.record(side)
             return slots[i % 2], done
 
+        pipe_marks = []
+
         def run_pipelined(n, offset):
             nxt = stage(0)
+            first = torch.cuda.Event(enable_timing=True)
+            first.record(main_stream)
+            pipe_marks[:] = [(time.perf_counter(), first)]
             for i in range(n):
                 cur, done = nxt
                 main_stream.wait_event(done)
@@ -453,6 +458,9 @@ def main():
                 ade, fde = evaluate_batch(gen, cur['obs_traj'], cur['obs_traj_rel'], sse, cur['obs_traj_g'],
                                           cur['pred_traj_gt'], K_SAMPLES, fold_samples=False)
                 out_pipe[offset + i].copy_(torch.stack([ade, fde]), non_blocking=True)
+                mark = torch.cuda.Event(enable_timing=True)
+                mark.record(main_stream)
+                pipe_marks.append((time.perf_counter(), mark))
 
         run_pipelined(args.warmup, 0)
         barrier()
@@ -460,6 +468,8 @@ def main():
         run_pipelined(args.steps, args.warmup)
         barrier()
         pipe_s = time.perf_counter() - t0
+        pipe_dev_ms = [a[1].elapsed_time(b[1]) for a, b in zip(pipe_marks, pipe_marks[1:])]
+        pipe_host_ms = [(b[0] - a[0]) * 1e3 for a, b in zip(pipe_marks, pipe_marks[1:])]
 
         # ---- roofline of the dominant pooling kernel: events recorded by the library around that launch ----
         import ctypes
@@ -511,6 +521,12 @@ def main():
             gen.pool_net.precision = alt
             other_modes[alt] = time_call(lambda: gen.pool_net(h_enc, dev_in['seq_start_end'], end_pos), reps=5)
         gen.pool_net.precision = precision
+
+    small = None
+    try:
+        small = small_batch_numbers(gen, args.config, dev, rank, world)
+    except Exception as e:
+        small = {'error': repr(e)[:200]}
 
     train = None
     if not args.no_train:
@@ -579,6 +595,8 @@ def main():
                     'ms_per_step_max_rank0': max(e2e_steps),
                     'pipelined': {'value': traj_per_step * args.steps / (pipe_ms_max * 1e-3), 'unit': 'traj/s',
                                   'ms_per_step': pipe_ms_max / args.steps,
+                                  'device_ms_per_step_rank0': [round(v, 3) for v in pipe_dev_ms],
+                                  'host_issue_ms_per_step_rank0': [round(v, 3) for v in pipe_host_ms],
                                   'what': 'same steps, next batch copied on a side stream during compute, async D2H per '
                                           'step, one synchronisation at the end (evaluate() over a prefetching loader)'},
                     'what': 'evaluate_batch(): H2D batch + schedule + K forwards + best-of-K ADE/FDE on device + D2H of the sums'},
@@ -609,6 +627,8 @@ def main():
                  'ped_steps_per_s': pred_len * peds / (dec_ms * 1e-3)},
             ],
         }
+        if small is not None:
+            line['small_batch'] = small
         if train is not None:
             line['train_step'] = train
         if not args.no_cpu_baseline and world == 1:          # the CPU port is timed next to the 1-GPU number only
@@ -619,6 +639,46 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def small_batch_numbers(gen, config, dev, rank, world, scenes=64, reps=20):
+    """ONE minibatch at the reference's own batch size (64 scenes, scripts/evaluate_model.py:72-99), best-of-20: the
+    launch-latency regime where scene sharding runs dry.  N = 1: the K samples folded into one forward; N > 1: the
+    (sample, scene) pairs sharded over the ranks by LPT + one all-reduce of the [K, S] error sums."""
+    import torch.distributed as dist
+    from group_gan_gcn_gat_b200 import parallel
+    from group_gan_gcn_gat_b200.evaluate import evaluate_batch
+    data = synth_batch(scenes, 4242, config)
+    d = {k: data[k].to(dev) for k in ('obs_traj', 'obs_traj_rel', 'obs_traj_g', 'pred_traj_gt')}
+    sse = data['seq_start_end']
+    noise = torch.randn(K_SAMPLES, scenes, 8, generator=torch.Generator().manual_seed(11)).to(dev)
+    peds = int(sse[-1, 1])
+
+    def run():
+        if world == 1:
+            return evaluate_batch(gen, d['obs_traj'], d['obs_traj_rel'], sse, d['obs_traj_g'], d['pred_traj_gt'], K_SAMPLES,
+                                  noise=noise, fold_samples=True)
+        return parallel.evaluate_batch_sample_sharded(gen, d['obs_traj'], d['obs_traj_rel'], sse, d['obs_traj_g'],
+                                                      d['pred_traj_gt'], K_SAMPLES, noise, world, rank)
+    ts = []
+    with torch.no_grad():
+        for i in range(reps + 5):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            a, f = run()
+            torch.cuda.synchronize()
+            ts.append((time.perf_counter() - t0) * 1e3)
+    t = torch.tensor([statistics.median(ts[5:])], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    return {'workload': 'one %d-scene minibatch (%d peds), best-of-%d, wall clock incl. host issue, median of %d, max over ranks'
+                        % (scenes, peds, K_SAMPLES, reps),
+            'mode': 'K samples folded into one forward' if world == 1 else
+                    '(sample, scene) pairs LPT-sharded over %d ranks + all-reduce of the [K,S] sums' % world,
+            'ms': ms, 'traj_per_s': peds * K_SAMPLES / (ms * 1e-3), 'ade_sum': float(a), 'fde_sum': float(f)}
 
 
 def train_step_numbers(dev, rank, world):

@@ -53,6 +53,81 @@ def global_ped_count(seq_start_end):
     return int(sse[-1, 1]) if len(sse) else 0
 
 
+def partition_samples(seq_start_end, num_samples, world):
+    """LPT split of the (sample k, scene s) PAIRS of one minibatch over `world` ranks by cost N_s^2 ("by
+    scenes ... and by the K = 20 best-of-K samples"): where one 64-scene minibatch cannot feed 8 GPUs by scenes alone,
+    its 20 x 64 (sample, scene) pairs can.  -> rank_of_pair int32 [num_samples, S]; identical on every rank (computed from
+    the host copy of seq_start_end, no communication)."""
+    sched = seq_start_end if isinstance(seq_start_end, SceneSchedule) else SceneSchedule(seq_start_end, 'cpu')
+    sse = sched.host_sse
+    sizes = (sse[:, 1] - sse[:, 0]).astype(np.int64)
+    tiled = np.tile(sizes, num_samples)                      # virtual scene list: pair (k, s) = scene k * S + s
+    ends = np.cumsum(tiled)
+    virt = np.stack([ends - tiled, ends], axis=1).astype(np.int64)
+    rank_of, _ = SceneSchedule(virt, 'cpu').partition(world)
+    return rank_of.reshape(num_samples, len(sizes))
+
+
+def _sample_shard_plan(sched, K, world, rank, dev):
+    """This rank's (sample, scene) pairs of a minibatch as gather indices, cached on the schedule (one minibatch layout is
+    evaluated many times: the plan costs more host time than the forward it feeds).  None for an empty shard."""
+    cache = sched.__dict__.setdefault('_sample_shards', {})
+    key = (K, world, rank, str(dev))
+    if key not in cache:
+        sse = sched.host_sse
+        S = sched.n_scenes
+        mine_k, mine_s = np.nonzero(partition_samples(sched, K, world) == rank)      # sample-major order
+        if not len(mine_k):
+            cache[key] = None
+        else:
+            sizes = (sse[mine_s, 1] - sse[mine_s, 0]).astype(np.int64)
+            idx = torch.from_numpy(np.concatenate([np.arange(sse[s, 0], sse[s, 1]) for s in mine_s])).to(dev)
+            ends = np.cumsum(sizes)
+            sse_l = torch.from_numpy(np.stack([ends - sizes, ends], axis=1).astype(np.int64))
+            pair_of_ped = torch.from_numpy(np.repeat(mine_k * S + mine_s, sizes)).to(dev)
+            cache[key] = (idx, sse_l, torch.from_numpy(mine_k).to(dev), torch.from_numpy(mine_s).to(dev), pair_of_ped)
+    return cache[key]
+
+
+@torch.no_grad()
+def evaluate_batch_sample_sharded(generator, obs_traj, obs_traj_rel, seq_start_end, obs_traj_g, pred_traj_gt, num_samples,
+                                  noise, world=None, rank=None, group=None):
+    """Best-of-K ADE / FDE sums of ONE minibatch (scripts/evaluate_model.py:72-99) with the K samples sharded across
+    ranks: every rank runs its (sample, scene) pairs as one folded forward, the [K, S] per-scene error sums are
+    all-reduced (10 KB for K = 20, S = 64) and the min over K / sum over scenes is taken on every rank.
+    noise [K, S, *noise_dim] must be the same tensor on every rank (draw it from a common seed).  Every rank holds the
+    whole minibatch (it is a few hundred pedestrians).  Same result as evaluate.evaluate_batch up to summation order."""
+    from . import _lib
+    from .ops import _f32, _ptr, _stream
+    world = world if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
+    rank = rank if rank is not None else (dist.get_rank(group) if dist.is_initialized() else 0)
+    dev = obs_traj.device
+    sched = get_schedule(seq_start_end, dev)
+    sse = sched.host_sse
+    S, K, T = sched.n_scenes, int(num_samples), pred_traj_gt.shape[0]
+    plan = _sample_shard_plan(sched, K, world, rank, dev)
+    sums = torch.zeros(2, K, S, dtype=torch.float32, device=dev)
+    if plan is not None:
+        idx, sse_l, sel_k, sel_s, pair_of_ped = plan
+        z = noise.to(dev)[sel_k, sel_s]
+        rel = generator(obs_traj.index_select(1, idx), obs_traj_rel.index_select(1, idx), sse_l,
+                        obs_traj_g.index_select(1, idx), user_noise=z).contiguous()
+        n_l = int(idx.numel())
+        gt = _f32(pred_traj_gt.index_select(1, idx), 'pred_traj_gt')
+        start = _f32(obs_traj[-1].index_select(0, idx), 'obs_traj')
+        ade = torch.empty(n_l, 1, dtype=torch.float32, device=dev)
+        fde = torch.empty_like(ade)
+        L = _lib.lib()
+        with torch.cuda.device(dev):
+            _lib.check(L.sgx_displacement_errors(_ptr(rel), _ptr(start), _ptr(gt), T, n_l, _ptr(ade), _ptr(fde), 1, 0,
+                                                 _stream(rel)), 'sgx_displacement_errors')
+        sums.view(2, K * S).index_add_(1, pair_of_ped, torch.stack([ade.view(-1), fde.view(-1)], 0))
+    if world > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    best = sums.min(dim=1).values.sum(dim=1)
+    return best[0], best[1]
+
+
 def allreduce_gradients(module, group=None, ran_forward=True):
     """One all-reduce (sum) over every parameter gradient of `module`: ONE `cat` into a flat bucket, the collective,
     and the parameters' .grad re-pointed at views of the reduced bucket (no copy back).

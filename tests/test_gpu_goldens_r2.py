@@ -202,3 +202,57 @@ def test_full_split_best_of_20_matches_reference(name, precision):
         assert float((rel.cpu() - g['pred_rel_k0'][:, p0:p1]).abs().max()) < 1e-4
     ade, fde = ade_sum / (n * pred_len), fde_sum / n
     assert abs(ade - float(g['ade'])) < 1e-4 and abs(fde - float(g['fde'])) < 1e-4, (ade, fde, float(g['ade']), float(g['fde']))
+
+
+def _ksharded_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        torch.cuda.set_device(0)
+        from group_gan_gcn_gat_b200 import models as MD, parallel
+        from group_gan_gcn_gat_b200.evaluate import evaluate_batch
+        torch.backends.cudnn.allow_tf32 = False
+        g = load_golden('eval_gat_zara1_full')
+        gen = MD.TrajectoryGenerator(obs_len=8, pred_len=12, embedding_dim=16, encoder_h_dim=32, decoder_h_dim=32, mlp_dim=64,
+                                     num_layers=1, noise_dim=(8,), noise_type='gaussian', noise_mix_type='global',
+                                     pooling_type='pool_net', pool_every_timestep=False, dropout=0, bottleneck_dim=8,
+                                     batch_norm=False, n_heads=1, dropout1=0, alpha=float(g['alpha']), context_type='gat')
+        gen.load_state_dict({k[3:]: v for k, v in g.items() if k.startswith('sd.')}, strict=True)
+        gen = gen.to(DEV).train()
+        sse = g['seq_start_end']
+        s1 = 64                                                 # ONE 64-scene minibatch of the zara1 test split
+        p1 = int(sse[s1 - 1, 1])
+        t = lambda k: g[k][:, :p1].contiguous().to(DEV)
+        noise = g['noise'][:, :s1].to(DEV)
+        a, f = parallel.evaluate_batch_sample_sharded(gen, t('obs_traj'), t('obs_traj_rel'), sse[:s1], t('obs_traj_g'),
+                                                      t('pred_traj_gt'), noise.shape[0], noise, world, rank)
+        a1, f1 = evaluate_batch(gen, t('obs_traj'), t('obs_traj_rel'), sse[:s1].to(DEV), t('obs_traj_g'), t('pred_traj_gt'),
+                                num_samples=noise.shape[0], noise=noise, fold_samples=False)
+        assert abs(float(a) - float(a1)) <= 2e-6 * float(a1) and abs(float(f) - float(f1)) <= 2e-6 * float(f1), (a, a1, f, f1)
+        # and against the frozen per-pedestrian errors of the reference for these 64 scenes
+        ref_a = sum(float(torch.min(g['ade_raw'][s:e].sum(0))) for s, e in sse[:s1].tolist())
+        ref_f = sum(float(torch.min(g['fde_raw'][s:e].sum(0))) for s, e in sse[:s1].tolist())
+        assert abs(float(a) - ref_a) < 1e-4 * p1 * 12 and abs(float(f) - ref_f) < 1e-4 * p1
+        q.put((rank, 'ok'))
+    except Exception:      # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()[-1500:]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_best_of_k_sharded_over_samples_matches_single_rank():
+    """SURVEY 8e / north_star: "partitioned ... by the K = 20 best-of-K samples".  Two ranks each run half of the
+    (sample, scene) pairs of one 64-scene minibatch; the all-reduced [K, S] sums give the single-rank best-of-K result."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ksharded_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == 'ok' for r in results), results

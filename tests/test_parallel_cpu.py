@@ -151,3 +151,25 @@ def test_losses_match_oracle_definitions():
     r = random.Random(1)
     a = losses.gan_d_loss(x, -x, r)
     assert torch.isfinite(a)
+
+
+def test_sample_pair_partition_is_balanced_and_complete():
+    """K-sample sharding: the (sample, scene) pairs of one 64-scene minibatch over 8 ranks -- every pair
+    exactly once, N^2 cost balanced to within one large scene, identical for every caller."""
+    import __graft_entry__ as ge
+    ge.build()
+    from group_gan_gcn_gat_b200 import parallel
+    rng = np.random.RandomState(5)
+    sizes = rng.randint(2, 40, size=64)
+    sse = sse_from_sizes(list(sizes))
+    K, world = 20, 8
+    r = parallel.partition_samples(sse, K, world)
+    assert r.shape == (K, 64) and r.min() == 0 and r.max() == world - 1
+    assert np.array_equal(r, parallel.partition_samples(sse, K, world))
+    cost = np.array([(np.tile(sizes.astype(np.int64) ** 2, (K, 1)) * (r == w)).sum() for w in range(world)])
+    assert cost.sum() == K * (sizes.astype(np.int64) ** 2).sum()
+    assert cost.max() - cost.min() <= int(sizes.max()) ** 2
+    # scene sharding alone would leave the same batch unbalanced by far more
+    r1 = parallel.partition_samples(sse, 1, world)
+    cost1 = np.array([((sizes.astype(np.int64) ** 2) * (r1[0] == w)).sum() for w in range(world)])
+    assert (cost.max() / cost.mean()) <= (cost1.max() / cost1.mean()) + 1e-9
