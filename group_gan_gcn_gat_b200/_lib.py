@@ -62,6 +62,10 @@ SIGNATURES = {
     'sgx_gat_encoder_fused_fwd': (ctypes.c_int, [_P] * 7 + [_I64, _I32] + [_P] * 10 + [_F32] + [_I32] * 5 + [_P, _P]),
     'sgx_gat_encoder_bwd': (ctypes.c_int, [_P] * 6 + [_I64, _I64] + [_P] * 10 + [_F32] + [_I32] * 5 + [_P] * 11 +
                             [_P, _I64, _P]),
+    'sgx_gat_encoder_fwd_dense': (ctypes.c_int, [_P] * 6 + [_I64, _I64, _I32] + [_P] * 10 + [_F32] + [_I32] * 5 +
+                                  [_P, _P, _I64, _P]),
+    'sgx_gat_encoder_bwd_dense': (ctypes.c_int, [_P] * 7 + [_I64, _I64, _I32] + [_P] * 10 + [_F32] + [_I32] * 5 + [_P] * 11 +
+                                  [_P, _I64, _P]),
     'sgx_gat_encoder_fused_bwd_ws_bytes': (_I64, []),
     'sgx_gat_encoder_fused_bwd': (ctypes.c_int, [_P] * 8 + [_I64] + [_P] * 10 + [_F32] + [_I32] * 5 + [_P] * 11 +
                                   [_P, _I64, _P]),

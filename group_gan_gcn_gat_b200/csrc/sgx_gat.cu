@@ -106,6 +106,168 @@ att_fwd_kernel(const float* __restrict__ Wh, int ldw, const float* __restrict__ 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Dense-crowd attention forward (scenes of 65 .. 2048 pedestrians; BASELINE.json configs[3]): att_fwd_kernel gives one
+// THREAD per node a serial walk over the whole scene -- 64 scenes of 1024 leave 3 warps per SM busy for 0.7 ms.
+// Here a CTA owns 32 rows of ONE scene, a warp four of them, lanes <-> features (warp-per-row masked softmax):
+//   * the scene's candidate list (its pedestrians with their group leader for the intra level, the compacted list of
+//     its group leaders for the inter level) and their t scores are staged in shared memory once per CTA;
+//   * pass 1: row maxima, lanes strided over the candidates; pass 2: the candidates in tiles of 32 -- for the inter
+//     level (all-to-all among the leaders) the tile's Wh rows are staged in shared memory by the whole CTA with
+//     coalesced 16-byte loads and reused by its 32 rows; for the intra level (groups are small) only the matching
+//     rows are read, straight from L2;
+//   * ELU / ELU + log_softmax epilogue with warp shuffles.  Same outputs as att_fwd_kernel up to summation order.
+// ------------------------------------------------------------------------------------------------
+constexpr int DENSE_NMAX = 2048;       // candidates per scene held in shared memory
+constexpr int DENSE_ROWS = 32;         // rows per CTA (8 warps x 4)
+
+template <int F, int MODE, int POST>
+__global__ void __launch_bounds__(256)
+att_fwd_scene_kernel(const float* __restrict__ Wh, int ldw, const float* __restrict__ st, int lds,
+                     const int32_t* __restrict__ leader, const int32_t* __restrict__ scene_start, float alpha,
+                     float* __restrict__ out, int ldo, float* __restrict__ U) {
+    constexpr int NU = (F + 31) / 32;                 // features per lane
+    constexpr int TS = F + 4;                         // tile row stride
+    __shared__ int cand[DENSE_NMAX];                  // scene-local index of every candidate
+    __shared__ int lead_s[MODE == INTRA ? DENSE_NMAX : 1];
+    __shared__ float t_s[DENSE_NMAX];
+    __shared__ __align__(16) float tile[MODE == INTER ? 32 * TS : 4];
+    __shared__ int warp_cnt[8];
+    // blockIdx.y = scene, blockIdx.x = block of 32 rows
+    const int b = scene_start[blockIdx.y], e = scene_start[blockIdx.y + 1], n = e - b;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int C = n;
+    if (MODE == INTRA) {
+        if ((int)blockIdx.x * DENSE_ROWS >= n) return;
+        for (int q = threadIdx.x; q < n; q += 256) { lead_s[q] = leader[b + q] - b; t_s[q] = st[(int64_t)(b + q) * lds + 1]; }
+    } else {
+        int base = 0;                                 // ordered compaction of the scene's leaders
+        for (int q0 = 0; q0 < n; q0 += 256) {
+            const int q = q0 + threadIdx.x;
+            const bool is = q < n && leader[b + q] == b + q;
+            const uint32_t m = __ballot_sync(0xffffffffu, is);
+            if (lane == 0) warp_cnt[warp] = __popc(m);
+            __syncthreads();
+            int off = base, tot = 0;
+            for (int w = 0; w < 8; ++w) { if (w < warp) off += warp_cnt[w]; tot += warp_cnt[w]; }
+            if (is) {
+                const int pos = off + __popc(m & ((1u << lane) - 1u));
+                cand[pos] = q;
+                t_s[pos] = st[(int64_t)(b + q) * lds + 1];
+            }
+            base += tot;
+            __syncthreads();
+        }
+        C = base;
+        if ((int)blockIdx.x * DENSE_ROWS >= C) return;
+    }
+    __syncthreads();
+    // ---- this warp's four rows ----
+    int row_i[4];
+    float s_i[4], m_i[4], den[4], acc[4][NU];
+    int my_lead[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = blockIdx.x * DENSE_ROWS + warp * 4 + k;
+        row_i[k] = (r < C) ? (MODE == INTRA ? r : cand[r]) : -1;
+        s_i[k] = row_i[k] >= 0 ? st[(int64_t)(b + row_i[k]) * lds] : 0.f;
+        my_lead[k] = (MODE == INTRA && row_i[k] >= 0) ? lead_s[row_i[k]] : -1;
+        m_i[k] = -INFINITY;
+        den[k] = 0.f;
+#pragma unroll
+        for (int u = 0; u < NU; ++u) acc[k][u] = 0.f;
+    }
+    // ---- pass 1: row maxima ----
+    for (int q = lane; q < C; q += 32) {
+        const float tq = t_s[q];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const bool nb = MODE == INTER ? true : (lead_s[q] == my_lead[k]);
+            if (nb && row_i[k] >= 0) m_i[k] = fmaxf(m_i[k], lrelu(s_i[k] + tq, alpha));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m_i[k] = fmaxf(m_i[k], __shfl_xor_sync(0xffffffffu, m_i[k], o));
+    // ---- pass 2: weights and the weighted sum of the neighbours' rows ----
+    for (int t0 = 0; t0 < C; t0 += 32) {
+        const int q = t0 + lane;
+        if (MODE == INTER) {
+            __syncthreads();                          // the previous tile has been consumed by every warp
+            for (int idx = threadIdx.x; idx < 32 * (F / 4); idx += 256) {
+                const int j = idx / (F / 4), c4 = idx % (F / 4);
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (t0 + j < C) v = *reinterpret_cast<const float4*>(Wh + (int64_t)(b + cand[t0 + j]) * ldw + 4 * c4);
+                *reinterpret_cast<float4*>(tile + j * TS + 4 * c4) = v;
+            }
+            __syncthreads();
+        }
+        float w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const bool nb = q < C && row_i[k] >= 0 && (MODE == INTER ? true : (lead_s[q] == my_lead[k]));
+            w[k] = nb ? expf(lrelu(s_i[k] + t_s[q], alpha) - m_i[k]) : 0.f;
+            den[k] += w[k];
+        }
+        if (MODE == INTER) {
+            const int lim = (C - t0) < 32 ? (C - t0) : 32;
+            for (int j = 0; j < lim; ++j) {
+                float v[NU];
+#pragma unroll
+                for (int u = 0; u < NU; ++u) v[u] = (lane + 32 * u < F) ? tile[j * TS + lane + 32 * u] : 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float wj = __shfl_sync(0xffffffffu, w[k], j);
+#pragma unroll
+                    for (int u = 0; u < NU; ++u) acc[k][u] = fmaf(wj, v[u], acc[k][u]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                for (uint32_t mm = __ballot_sync(0xffffffffu, w[k] != 0.f); mm; mm &= mm - 1) {
+                    const int j = __ffs(mm) - 1;
+                    const float wj = __shfl_sync(0xffffffffu, w[k], j);
+                    const float* row = Wh + (int64_t)(b + t0 + j) * ldw;
+#pragma unroll
+                    for (int u = 0; u < NU; ++u)
+                        if (lane + 32 * u < F) acc[k][u] = fmaf(wj, row[lane + 32 * u], acc[k][u]);
+                }
+            }
+        }
+    }
+    // ---- epilogue ----
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (row_i[k] < 0) continue;                   // warp-uniform
+        float d = den[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        const float inv = 1.f / d;
+        const int64_t i = b + row_i[k];
+        if (POST == POST_ELU) {
+#pragma unroll
+            for (int u = 0; u < NU; ++u)
+                if (lane + 32 * u < F) out[i * ldo + lane + 32 * u] = elu1(acc[k][u] * inv);
+        } else {
+            static_assert(POST == POST_ELU || F <= 32, "log_softmax epilogue: one feature per lane");
+            const float uval = lane < F ? elu1(acc[k][0] * inv) : -INFINITY;
+            float mx = uval;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            float sum = lane < F ? expf(uval - mx) : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            const float lse = mx + logf(sum);
+            if (lane < F) {
+                if (U) U[i * F + lane] = uval;
+                out[i * ldo + lane] = uval - lse;
+            }
+        }
+    }
+}
+
 // Row role of the backward: recompute the node's softmax statistics and hp, turn the upstream gradient
 // into d(hp), and reduce ds_i = sum_j d(pre_ij).  stats[i] = (m_i, den_i, c_i = dhp_i . hp_i).
 template <int F, int MODE, int POST>
@@ -324,12 +486,21 @@ static int64_t carve_gat(Carver& c, GatWs& w, int64_t n, int nh) {
     return c.off;
 }
 
+// dense != nullptr: scene_start of a batch whose scenes all fit the warp-per-row kernels (65 .. DENSE_NMAX peds)
+struct DenseInfo { const int32_t* scene_start; int n_scenes; int max_scene; };
+
 template <int MODE>
 static int gat_level_fwd(const float* feat, int fin, const float* W, const float* a, const float* Wout,
                          const float* aout, int nh, float alpha, const int32_t* leader, const int32_t* ps,
-                         const int32_t* pe, int64_t n, Level& L, cudaStream_t st) {
+                         const int32_t* pe, int64_t n, Level& L, cudaStream_t st, const DenseInfo* dense = nullptr) {
     int rc;
     const int ldh = nh * HID;
+    const dim3 dgrid(dense ? (unsigned)((dense->max_scene + DENSE_ROWS - 1) / DENSE_ROWS) : 1u, dense ? (unsigned)dense->n_scenes : 1u);
+    if (dense && MODE == INTER) {      // rows that are not group leaders stay zero (the thread kernels write those zeros)
+        SGX_CUDA(cudaMemsetAsync(L.x1a, 0, (size_t)n * ldh * sizeof(float), st));
+        SGX_CUDA(cudaMemsetAsync(L.Xo, 0, (size_t)n * OUT * sizeof(float), st));
+        SGX_CUDA(cudaMemsetAsync(L.U, 0, (size_t)n * OUT * sizeof(float), st));
+    }
     for (int k = 0; k < nh; ++k) {
         // Wh1[:, k] = feat W_k ;  st1[:, k] = Wh1[:, k] [a1 a2]
         if ((rc = gemm(feat, fin, 1, W + (int64_t)k * fin * HID, HID, 1, L.Wh1 + k * HID, ldh, n, HID, fin, 0, 0, st)))
@@ -337,14 +508,23 @@ static int gat_level_fwd(const float* feat, int fin, const float* W, const float
         if ((rc = gemm(L.Wh1 + k * HID, ldh, 1, a + (int64_t)k * 2 * HID, 1, HID, L.st1 + 2 * k, 2 * nh, n, 2, HID, 0, 0,
                        st)))
             return rc;
-        att_fwd_kernel<HID, MODE, POST_ELU><<<blocks_for(n, 128), 128, 0, st>>>(
-            L.Wh1 + k * HID, ldh, L.st1 + 2 * k, 2 * nh, leader, ps, pe, (int)n, alpha, L.x1a + k * HID, ldh, nullptr);
+        if (dense)
+            att_fwd_scene_kernel<HID, MODE, POST_ELU><<<dgrid, 256, 0, st>>>(L.Wh1 + k * HID, ldh, L.st1 + 2 * k, 2 * nh, leader,
+                                                                            dense->scene_start, alpha, L.x1a + k * HID,
+                                                                            ldh, nullptr);
+        else
+            att_fwd_kernel<HID, MODE, POST_ELU><<<blocks_for(n, 128), 128, 0, st>>>(
+                L.Wh1 + k * HID, ldh, L.st1 + 2 * k, 2 * nh, leader, ps, pe, (int)n, alpha, L.x1a + k * HID, ldh, nullptr);
         SGX_LAUNCH_CHECK();
     }
     if ((rc = gemm(L.x1a, ldh, 1, Wout, OUT, 1, L.Wh2, OUT, n, OUT, ldh, 0, 0, st))) return rc;
     if ((rc = gemm(L.Wh2, OUT, 1, aout, 1, OUT, L.st2, 2, n, 2, OUT, 0, 0, st))) return rc;
-    att_fwd_kernel<OUT, MODE, POST_ELU_LOGSOFTMAX><<<blocks_for(n, 128), 128, 0, st>>>(
-        L.Wh2, OUT, L.st2, 2, leader, ps, pe, (int)n, alpha, L.Xo, OUT, L.U);
+    if (dense)
+        att_fwd_scene_kernel<OUT, MODE, POST_ELU_LOGSOFTMAX><<<dgrid, 256, 0, st>>>(L.Wh2, OUT, L.st2, 2, leader,
+                                                                                   dense->scene_start, alpha, L.Xo, OUT, L.U);
+    else
+        att_fwd_kernel<OUT, MODE, POST_ELU_LOGSOFTMAX><<<blocks_for(n, 128), 128, 0, st>>>(
+            L.Wh2, OUT, L.st2, 2, leader, ps, pe, (int)n, alpha, L.Xo, OUT, L.U);
     SGX_LAUNCH_CHECK();
     return SGX_OK;
 }
@@ -392,12 +572,12 @@ static int gat_forward(const float* x, const int32_t* leader, const int32_t* gsi
                        const int32_t* pe, int64_t n, const float* Wi, const float* ai, const float* Wio,
                        const float* aio, const float* We, const float* ae, const float* Weo, const float* aeo,
                        const float* Wo, const float* bo, float alpha, int nh, int IN, int FIN, float* out, GatWs& w,
-                       cudaStream_t st) {
+                       cudaStream_t st, const DenseInfo* dense = nullptr) {
     int rc;
-    if ((rc = gat_level_fwd<INTRA>(x, IN, Wi, ai, Wio, aio, nh, alpha, leader, ps, pe, n, w.intra, st))) return rc;
+    if ((rc = gat_level_fwd<INTRA>(x, IN, Wi, ai, Wio, aio, nh, alpha, leader, ps, pe, n, w.intra, st, dense))) return rc;
     gat_pool_kernel<OUT><<<blocks_for(n, 128), 128, 0, st>>>(w.intra.Xo, leader, gsize, pe, (int)n, w.Xg);
     SGX_LAUNCH_CHECK();
-    if ((rc = gat_level_fwd<INTER>(w.Xg, OUT, We, ae, Weo, aeo, nh, alpha, leader, ps, pe, n, w.inter, st))) return rc;
+    if ((rc = gat_level_fwd<INTER>(w.Xg, OUT, We, ae, Weo, aeo, nh, alpha, leader, ps, pe, n, w.inter, st, dense))) return rc;
     gat_cat_kernel<OUT><<<blocks_for(n * OUT, 256), 256, 0, st>>>(w.intra.Xo, w.inter.Xo, leader, gsize, (int)n, w.cat);
     SGX_LAUNCH_CHECK();
     if (out) {
@@ -1122,13 +1302,13 @@ static int gat_check(int nh, int IN, int HID_, int OUT_, int FIN) {
     return SGX_OK;
 }
 
-extern "C" int sgx_gat_encoder_fwd(const float* x, const int32_t* leader, const int32_t* group_size,
-                                   const int32_t* ped_start, const int32_t* ped_end, int64_t batch, int64_t n_scenes,
-                                   const float* Wi, const float* ai, const float* Wio, const float* aio,
-                                   const float* We, const float* ae, const float* Weo, const float* aeo,
-                                   const float* Wo, const float* bo, float alpha, int32_t n_heads, int32_t IN,
-                                   int32_t HID_, int32_t OUT_, int32_t FIN, float* out, void* workspace,
-                                   int64_t ws_bytes, void* stream) {
+static int gat_encoder_fwd_impl(const float* x, const int32_t* leader, const int32_t* group_size,
+                                const int32_t* ped_start, const int32_t* ped_end, int64_t batch, int64_t n_scenes,
+                                const float* Wi, const float* ai, const float* Wio, const float* aio,
+                                const float* We, const float* ae, const float* Weo, const float* aeo,
+                                const float* Wo, const float* bo, float alpha, int32_t n_heads, int32_t IN,
+                                int32_t HID_, int32_t OUT_, int32_t FIN, float* out, void* workspace,
+                                int64_t ws_bytes, void* stream, const DenseInfo* dense) {
     SGX_REQUIRE(x && leader && group_size && ped_start && ped_end && Wi && ai && Wio && aio && We && ae && Weo && aeo &&
                     Wo && bo && out && workspace, "sgx_gat_encoder_fwd: null pointer");
     SGX_REQUIRE(batch > 0, "sgx_gat_encoder_fwd: empty batch");
@@ -1140,10 +1320,40 @@ extern "C" int sgx_gat_encoder_fwd(const float* x, const int32_t* leader, const 
     GatWs w;
     carve_gat(c, w, batch, n_heads);
     return gat_forward(x, leader, group_size, ped_start, ped_end, batch, Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo,
-                       alpha, n_heads, IN, FIN, out, w, (cudaStream_t)stream);
+                       alpha, n_heads, IN, FIN, out, w, (cudaStream_t)stream, dense);
 }
 
-extern "C" int sgx_gat_encoder_bwd(const float* x, const float* grad_out, const int32_t* leader,
+extern "C" int sgx_gat_encoder_fwd(const float* x, const int32_t* leader, const int32_t* group_size,
+                                   const int32_t* ped_start, const int32_t* ped_end, int64_t batch, int64_t n_scenes,
+                                   const float* Wi, const float* ai, const float* Wio, const float* aio,
+                                   const float* We, const float* ae, const float* Weo, const float* aeo,
+                                   const float* Wo, const float* bo, float alpha, int32_t n_heads, int32_t IN,
+                                   int32_t HID_, int32_t OUT_, int32_t FIN, float* out, void* workspace,
+                                   int64_t ws_bytes, void* stream) {
+    return gat_encoder_fwd_impl(x, leader, group_size, ped_start, ped_end, batch, n_scenes, Wi, ai, Wio, aio, We, ae, Weo,
+                                aeo, Wo, bo, alpha, n_heads, IN, HID_, OUT_, FIN, out, workspace, ws_bytes, stream, nullptr);
+}
+
+// true when the warp-per-row scene kernels apply: scenes of 65 .. DENSE_NMAX pedestrians, at most 65535 scenes (grid.y)
+static bool dense_ok(const int32_t* scene_start, int64_t n_scenes, int32_t max_scene) {
+    return scene_start != nullptr && max_scene > 64 && max_scene <= DENSE_NMAX && n_scenes <= 65535;
+}
+
+extern "C" int sgx_gat_encoder_fwd_dense(const float* x, const int32_t* leader, const int32_t* group_size,
+                                         const int32_t* ped_start, const int32_t* ped_end, const int32_t* scene_start,
+                                         int64_t batch, int64_t n_scenes, int32_t max_scene, const float* Wi,
+                                         const float* ai, const float* Wio, const float* aio, const float* We,
+                                         const float* ae, const float* Weo, const float* aeo, const float* Wo,
+                                         const float* bo, float alpha, int32_t n_heads, int32_t IN, int32_t HID_,
+                                         int32_t OUT_, int32_t FIN, float* out, void* workspace, int64_t ws_bytes,
+                                         void* stream) {
+    DenseInfo d{scene_start, (int)n_scenes, max_scene};
+    return gat_encoder_fwd_impl(x, leader, group_size, ped_start, ped_end, batch, n_scenes, Wi, ai, Wio, aio, We, ae, Weo,
+                                aeo, Wo, bo, alpha, n_heads, IN, HID_, OUT_, FIN, out, workspace, ws_bytes, stream,
+                                dense_ok(scene_start, n_scenes, max_scene) ? &d : nullptr);
+}
+
+static int gat_encoder_bwd_impl(const DenseInfo* dense, const float* x, const float* grad_out, const int32_t* leader,
                                    const int32_t* group_size, const int32_t* ped_start, const int32_t* ped_end,
                                    int64_t batch, int64_t n_scenes, const float* Wi, const float* ai, const float* Wio,
                                    const float* aio, const float* We, const float* ae, const float* Weo,
@@ -1168,7 +1378,7 @@ extern "C" int sgx_gat_encoder_bwd(const float* x, const float* grad_out, const 
     const int64_t n = batch;
     // recompute the forward intermediates (cheaper than keeping ~2 KB per ped alive between fwd and bwd)
     if ((rc = gat_forward(x, leader, group_size, ped_start, ped_end, n, Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo, alpha,
-                          n_heads, IN, FIN, nullptr, w, st)))
+                          n_heads, IN, FIN, nullptr, w, st, dense)))
         return rc;
     // final Linear: dcat = gout Wo ; dWo = gout^T cat ; dbo = colsum(gout)
     if ((rc = gemm(grad_out, FIN, 1, Wo, 2 * OUT, 1, w.dcat, 2 * OUT, n, 2 * OUT, FIN, 0, 0, st))) return rc;
@@ -1187,6 +1397,32 @@ extern "C" int sgx_gat_encoder_bwd(const float* x, const float* grad_out, const 
                                    w.dX1, grad_x, grad_Wi, grad_ai, grad_Wio, grad_aio, st)))
         return rc;
     return SGX_OK;
+}
+
+#define SGX_GAT_BWD_PARAMS                                                                                          \
+    const float *x, const float *grad_out, const int32_t *leader, const int32_t *group_size, const int32_t *ped_start, \
+        const int32_t *ped_end
+#define SGX_GAT_BWD_TAIL                                                                                             \
+    const float *Wi, const float *ai, const float *Wio, const float *aio, const float *We, const float *ae,           \
+        const float *Weo, const float *aeo, const float *Wo, const float *bo, float alpha, int32_t n_heads, int32_t IN, \
+        int32_t HID_, int32_t OUT_, int32_t FIN, float *grad_x, float *grad_Wi, float *grad_ai, float *grad_Wio,      \
+        float *grad_aio, float *grad_We, float *grad_ae, float *grad_Weo, float *grad_aeo, float *grad_Wo,            \
+        float *grad_bo, void *workspace, int64_t ws_bytes, void *stream
+#define SGX_GAT_BWD_ARGS                                                                                             \
+    Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo, alpha, n_heads, IN, HID_, OUT_, FIN, grad_x, grad_Wi, grad_ai, grad_Wio, \
+        grad_aio, grad_We, grad_ae, grad_Weo, grad_aeo, grad_Wo, grad_bo, workspace, ws_bytes, stream
+
+extern "C" int sgx_gat_encoder_bwd(SGX_GAT_BWD_PARAMS, int64_t batch, int64_t n_scenes, SGX_GAT_BWD_TAIL) {
+    return gat_encoder_bwd_impl(nullptr, x, grad_out, leader, group_size, ped_start, ped_end, batch, n_scenes,
+                                SGX_GAT_BWD_ARGS);
+}
+
+// same, with the forward recompute on the dense-crowd kernels when the scenes qualify (see sgx_gat_encoder_fwd_dense)
+extern "C" int sgx_gat_encoder_bwd_dense(SGX_GAT_BWD_PARAMS, const int32_t* scene_start, int64_t batch, int64_t n_scenes,
+                                         int32_t max_scene, SGX_GAT_BWD_TAIL) {
+    DenseInfo d{scene_start, (int)n_scenes, max_scene};
+    return gat_encoder_bwd_impl(dense_ok(scene_start, n_scenes, max_scene) ? &d : nullptr, x, grad_out, leader, group_size,
+                                ped_start, ped_end, batch, n_scenes, SGX_GAT_BWD_ARGS);
 }
 
 // Fused forward for batches whose scenes all have <= chunk_cap (32 or 64) peds (chunk_scene: scene index boundaries of

@@ -203,7 +203,7 @@ class GATEncoder(nn.Module):
         chunk_scene, n_chunks = sched.chunks(cap) if self.n_heads == 1 else (sched.scene_start[:0], 0)
         return ops.call(ops.gat_encoder_fwd, h_states, leader, gsize, sched.ped_start, sched.ped_end, sched.n_scenes, Wi, ai, Wio,
                                    aio, We, ae, Weo, aeo, self.out_embedding.weight, self.out_embedding.bias,
-                                   float(self.alpha), sched.scene_start, chunk_scene, n_chunks, cap)
+                                   float(self.alpha), sched.scene_start, chunk_scene, n_chunks, cap, int(sched.max_n))
 
 
 class GCN(nn.Module):

@@ -360,9 +360,10 @@ gcn_module_fwd.register_autograd(_gcn_backward, setup_context=_gcn_setup)
 def gat_encoder_fwd(x: Tensor, leader: Tensor, gsize: Tensor, ped_start: Tensor, ped_end: Tensor, n_scenes: int,
                     Wi: Tensor, ai: Tensor, Wio: Tensor, aio: Tensor, We: Tensor, ae: Tensor, Weo: Tensor,
                     aeo: Tensor, Wo: Tensor, bo: Tensor, alpha: float, scene_start: Tensor, chunk_scene: Tensor,
-                    n_chunks: int, chunk_cap: int = 32) -> Tensor:
+                    n_chunks: int, chunk_cap: int = 32, max_scene: int = 0) -> Tensor:
     """n_chunks > 0 selects the single-launch fused kernel (all scenes <= chunk_cap = 32 or 64 peds, n_heads = 1,
-    dims 40/72/16/24)."""
+    dims 40/72/16/24); otherwise the general path, with the dense-crowd attention kernels when max_scene (largest
+    scene of the batch) is in 65 .. 2048."""
     x = _f32(x, 'h_states')
     ps = [_f32(t, 'gat weight') for t in (Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo)]
     _check_gat_shapes(x, *ps)
@@ -379,15 +380,16 @@ def gat_encoder_fwd(x: Tensor, leader: Tensor, gsize: Tensor, ped_start: Tensor,
                                                    _stream(x)), 'sgx_gat_encoder_fused_fwd')
             return out
         ws = _ws(L.sgx_gat_encoder_ws_bytes(batch, n_scenes, nh, IN, HID, OUT, FIN), x.device)
-        _lib.check(L.sgx_gat_encoder_fwd(_ptr(x), _ptr(leader), _ptr(gsize), _ptr(ped_start), _ptr(ped_end), batch,
-                                         n_scenes, *[_ptr(p) for p in ps], alpha, nh, IN, HID, OUT, FIN, _ptr(out),
-                                         _ptr(ws), ws.numel(), _stream(x)), 'sgx_gat_encoder_fwd')
+        _lib.check(L.sgx_gat_encoder_fwd_dense(_ptr(x), _ptr(leader), _ptr(gsize), _ptr(ped_start), _ptr(ped_end),
+                                               _ptr(scene_start), batch, n_scenes, max_scene, *[_ptr(p) for p in ps],
+                                               alpha, nh, IN, HID, OUT, FIN, _ptr(out), _ptr(ws), ws.numel(),
+                                               _stream(x)), 'sgx_gat_encoder_fwd')
     return out
 
 
 @gat_encoder_fwd.register_fake
 def _(x, leader, gsize, ped_start, ped_end, n_scenes, Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo, alpha, scene_start,
-      chunk_scene, n_chunks, chunk_cap=32):
+      chunk_scene, n_chunks, chunk_cap=32, max_scene=0):
     return x.new_empty(x.shape[0], Wo.shape[0])
 
 
@@ -395,7 +397,7 @@ def _(x, leader, gsize, ped_start, ped_end, n_scenes, Wi, ai, Wio, aio, We, ae, 
 def gat_encoder_bwd(x: Tensor, grad_out: Tensor, leader: Tensor, gsize: Tensor, ped_start: Tensor, ped_end: Tensor,
                     n_scenes: int, Wi: Tensor, ai: Tensor, Wio: Tensor, aio: Tensor, We: Tensor, ae: Tensor,
                     Weo: Tensor, aeo: Tensor, Wo: Tensor, bo: Tensor, alpha: float, scene_start: Tensor,
-                    chunk_scene: Tensor, n_chunks: int, chunk_cap: int) -> List[Tensor]:
+                    chunk_scene: Tensor, n_chunks: int, chunk_cap: int, max_scene: int = 0) -> List[Tensor]:
     """n_chunks > 0 with chunk_cap 32 (every scene <= 32 peds, n_heads 1, dims 40/72/16/24) selects the single-launch
     backward (forward recomputed inside the kernel); otherwise the general multi-pass path."""
     x, grad_out = _f32(x, 'x'), _f32(grad_out, 'grad_out')
@@ -416,16 +418,17 @@ def gat_encoder_bwd(x: Tensor, grad_out: Tensor, leader: Tensor, gsize: Tensor, 
                        'sgx_gat_encoder_fused_bwd')
             return grads
         ws = _ws(L.sgx_gat_encoder_ws_bytes(batch, n_scenes, nh, IN, HID, OUT, FIN), x.device)
-        _lib.check(L.sgx_gat_encoder_bwd(_ptr(x), _ptr(grad_out), _ptr(leader), _ptr(gsize), _ptr(ped_start),
-                                         _ptr(ped_end), batch, n_scenes, *[_ptr(p) for p in ps], alpha, nh, IN, HID,
-                                         OUT, FIN, *[_ptr(g) for g in grads], _ptr(ws), ws.numel(), _stream(x)),
+        _lib.check(L.sgx_gat_encoder_bwd_dense(_ptr(x), _ptr(grad_out), _ptr(leader), _ptr(gsize), _ptr(ped_start),
+                                               _ptr(ped_end), _ptr(scene_start), batch, n_scenes, max_scene,
+                                               *[_ptr(p) for p in ps], alpha, nh, IN, HID, OUT, FIN,
+                                               *[_ptr(g) for g in grads], _ptr(ws), ws.numel(), _stream(x)),
                    'sgx_gat_encoder_bwd')
     return grads
 
 
 @gat_encoder_bwd.register_fake
 def _(x, grad_out, leader, gsize, ped_start, ped_end, n_scenes, Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo, alpha,
-      scene_start, chunk_scene, n_chunks, chunk_cap):
+      scene_start, chunk_scene, n_chunks, chunk_cap, max_scene=0):
     return [torch.empty_like(t) for t in (x, Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo)]
 
 
@@ -434,6 +437,7 @@ def _gat_setup(ctx, inputs, output):
     params, alpha = rest[:10], rest[10]
     scene_start, chunk_scene, n_chunks = rest[11], rest[12], rest[13]
     chunk_cap = rest[14] if len(rest) > 14 else 32
+    ctx.max_scene = rest[15] if len(rest) > 15 else 0
     ctx.save_for_backward(x, leader, gsize, ps, pe, scene_start, chunk_scene, *params)
     ctx.n_scenes, ctx.alpha, ctx.n_chunks, ctx.chunk_cap = S, alpha, n_chunks, chunk_cap
 
@@ -441,8 +445,8 @@ def _gat_setup(ctx, inputs, output):
 def _gat_backward(ctx, grad_out):
     x, leader, gsize, ps, pe, scene_start, chunk_scene, *params = ctx.saved_tensors
     g = gat_encoder_bwd(x, grad_out.contiguous(), leader, gsize, ps, pe, ctx.n_scenes, *params, ctx.alpha, scene_start,
-                        chunk_scene, ctx.n_chunks, ctx.chunk_cap)
-    return (g[0], None, None, None, None, None, *g[1:], None, None, None, None, None)
+                        chunk_scene, ctx.n_chunks, ctx.chunk_cap, ctx.max_scene)
+    return (g[0], None, None, None, None, None, *g[1:], None, None, None, None, None, None)
 
 
 gat_encoder_fwd.register_autograd(_gat_backward, setup_context=_gat_setup)

@@ -219,6 +219,27 @@ int sgx_gat_encoder_bwd(const float* x, const float* grad_out, const int32_t* le
                         float* grad_We, float* grad_ae, float* grad_Weo, float* grad_aeo, float* grad_Wo,
                         float* grad_bo, void* workspace, int64_t ws_bytes, void* stream);
 
+/* Dense crowds (BASELINE.json configs[3]: scenes of 64-1024 pedestrians): the same forward / backward with the attention
+ * layers on warp-per-row scene kernels (a CTA per 32 rows of one scene, candidates and their scores staged in shared
+ * memory, the inter-level Wh tiles staged by the whole CTA) when every scene has 65 .. 2048 pedestrians; otherwise
+ * identical to sgx_gat_encoder_fwd / _bwd.  scene_start int32 [n_scenes+1]; max_scene = largest scene of the batch. */
+int sgx_gat_encoder_fwd_dense(const float* x, const int32_t* leader, const int32_t* group_size,
+                              const int32_t* ped_start, const int32_t* ped_end, const int32_t* scene_start,
+                              int64_t batch, int64_t n_scenes, int32_t max_scene, const float* Wi, const float* ai,
+                              const float* Wio, const float* aio, const float* We, const float* ae, const float* Weo,
+                              const float* aeo, const float* Wo, const float* bo, float alpha, int32_t n_heads,
+                              int32_t IN, int32_t HID, int32_t OUT, int32_t FIN, float* out, void* workspace,
+                              int64_t ws_bytes, void* stream);
+int sgx_gat_encoder_bwd_dense(const float* x, const float* grad_out, const int32_t* leader, const int32_t* group_size,
+                              const int32_t* ped_start, const int32_t* ped_end, const int32_t* scene_start,
+                              int64_t batch, int64_t n_scenes, int32_t max_scene, const float* Wi, const float* ai,
+                              const float* Wio, const float* aio, const float* We, const float* ae, const float* Weo,
+                              const float* aeo, const float* Wo, const float* bo, float alpha, int32_t n_heads,
+                              int32_t IN, int32_t HID, int32_t OUT, int32_t FIN, float* grad_x, float* grad_Wi,
+                              float* grad_ai, float* grad_Wio, float* grad_aio, float* grad_We, float* grad_ae,
+                              float* grad_Weo, float* grad_aeo, float* grad_Wo, float* grad_bo, void* workspace,
+                              int64_t ws_bytes, void* stream);
+
 /* GATEncoder backward in one launch (+ a 30 KB reduction) for the batches sgx_gat_encoder_fused_fwd with chunk_cap 32
  * covers (every scene <= 32 peds, n_heads 1, dims 40/72/16/24): the forward is recomputed per chunk inside the kernel,
  * nothing but x, grad_out and grad_x touches HBM.  Gradient buffers are overwritten.  workspace:

@@ -1,6 +1,6 @@
 """Round-2 golden vectors frozen from the UNMODIFIED reference (run in the build container only):
 
-    python oracle/make_golden_r2.py        # writes tests/golden/{train_step_gat,eval_p_eth_full,eval_gat_zara1_full}.npz
+    python oracle/make_golden_r2.py        # writes tests/golden/{train_step_gat,eval_*_full,pool_g_N,gat_encoder_N,gcn_module_N}.npz
 
   train_step_gat        one discriminator_step + one generator_step of scripts/train.py:395-484 (imported as they are)
                         on one minibatch, from fixed initial weights, fixed noise (torch.manual_seed before each step)
@@ -152,7 +152,34 @@ def main():
     make_train_step(R, seed)
     make_full_split(R, 'eval_p_eth_full', 'models/sgan-p-models/eth_8_model.pt', 'mlp', 'eth', 20, seed=601)
     make_full_split(R, 'eval_gat_zara1_full', 'models/sgan-gat-models/zara1_12_model.pt', 'gat', 'zara1', 20, seed=602)
+    make_dense(R)
 
 
 if __name__ == '__main__':
     main()
+
+
+def make_dense(R):
+    """Dense-crowd fixtures (BASELINE.json configs[3]: scenes of 64-1024 pedestrians): the reference modules on ONE large
+    scene -- PoolHiddenNet materialises N^2 x 512, GATEncoder [N,N,144] (604 MB at N = 1024).  Forward outputs only."""
+    from oracle.make_golden import labels_for, sse_from_sizes, sd_arrays
+    for n in (256, 1024):
+        torch.manual_seed(700 + n)
+        rng = np.random.RandomState(700 + n)
+        sse = sse_from_sizes([n])
+        with torch.no_grad():
+            m = R.PoolHiddenNet(embedding_dim=16, h_dim=32, mlp_dim=64, bottleneck_dim=8, batch_norm=False)
+            h = torch.randn(1, n, 32)
+            pos = torch.rand(n, 2) * 15
+            save('pool_g_%d' % n, seq_start_end=sse, h=h, pos=pos, out=m(h, sse, pos), **sd_arrays(m))
+            x = torch.randn(n, 40)
+            lab = labels_for([n], rng, p_zero=0.1)
+            gat = R.GATEncoder(n_units=None, n_heads=1, dropout=0, alpha=0.2)
+            save('gat_encoder_%d' % n, seq_start_end=sse, x=x, pos=pos, labels=lab, out=gat(x, sse, pos, lab), n_heads=1,
+                 alpha=0.2, **sd_arrays(gat))
+            gcn = R.GCNModule(input_dim=40, hidden_dim=72, out_dim=16, gcn_layers=2, final_dim=24)
+            for p in gcn.parameters():
+                if p.dim() == 2 and p.shape[0] in (40, 72, 16) and p.shape[1] in (72, 16):
+                    p.mul_(0.15)
+            save('gcn_module_%d' % n, seq_start_end=sse, x=x, pos=pos, labels=lab, out=gcn(x, sse, pos, lab),
+                 **sd_arrays(gcn))

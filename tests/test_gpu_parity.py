@@ -830,3 +830,61 @@ def test_gat_encoder_fused_backward_vs_oracle_autograd(sgx, sizes):
     assert n_chunks > 0
     for a, b in zip(fused, general):
         assert_close(a, b, 1e-4, 'fused vs general backward', floor=floor)
+
+
+# ------------------------------------------------------------------ dense crowds (BASELINE.json configs[3])
+@pytest.mark.parametrize('n', [256, 1024])
+def test_dense_crowd_modules_vs_reference_goldens(sgx, n):
+    """ONE scene of 256 / 1024 pedestrians through the unmodified reference modules (PoolHiddenNet materialises
+    N^2 x 512, GATEncoder [N,N,144]) frozen by oracle/make_golden_r2.py: pooled features (tensor-core and CUDA-core
+    kernels), GATEncoder (warp-per-row scene kernels) and GCNModule outputs within 1e-5."""
+    g = load_golden('pool_g_%d' % n)
+    m = _pool_module(sgx, state_dict_of(g), 16, 32, 8)
+    with torch.no_grad():
+        for precision in ('fp32', 'fp32-simt'):
+            m.precision = precision
+            assert_close(m(g['h'].to(DEV), g['seq_start_end'].to(DEV), g['pos'].to(DEV)), g['out'], 1e-5,
+                         'pool N=%d %s' % (n, precision))
+        m.precision = 'bf16'
+        assert_close(m(g['h'].to(DEV), g['seq_start_end'].to(DEV), g['pos'].to(DEV)), g['out'], 2e-2, 'pool bf16 N=%d' % n)
+    g = load_golden('gat_encoder_%d' % n)
+    gat = sgx['M'].GATEncoder(n_units=None, n_heads=1, dropout=0, alpha=0.2)
+    gat.load_state_dict(state_dict_of(g), strict=True)
+    with torch.no_grad():
+        out = gat.to(DEV)(g['x'].to(DEV), g['seq_start_end'].to(DEV), g['pos'].to(DEV), g['labels'].to(DEV))
+    assert_close(out, g['out'], 1e-5, 'GATEncoder N=%d' % n)
+    g = load_golden('gcn_module_%d' % n)
+    gcn = sgx['M'].GCNModule(input_dim=40, hidden_dim=72, out_dim=16, gcn_layers=2, final_dim=24)
+    gcn.load_state_dict(state_dict_of(g), strict=True)
+    with torch.no_grad():
+        out = gcn.to(DEV)(g['x'].to(DEV), g['seq_start_end'].to(DEV), g['pos'].to(DEV), g['labels'].to(DEV))
+    assert_close(out, g['out'], 1e-5, 'GCNModule N=%d' % n)
+
+
+@pytest.mark.parametrize('sizes', [[65], [200, 70, 129], [300, 3, 2000], [97] * 9])
+def test_dense_crowd_gat_scene_kernels_vs_thread_kernels(sgx, sizes):
+    """The warp-per-row scene kernels (max scene 65 .. 2048) against the thread-per-node general path on the same
+    inputs, forward and backward (the backward's forward recompute takes the scene kernels too), mixed scene sizes."""
+    rng = np.random.RandomState(sum(sizes))
+    torch.manual_seed(sum(sizes))
+    from group_gan_gcn_gat_b200.schedule import get_schedule
+    sse = sse_from_sizes(sizes)
+    n = sum(sizes)
+    labs = torch.tensor(np.where(rng.rand(n) < 0.15, 0, rng.randint(1, max(2, max(sizes) // 3), size=n)),
+                        dtype=torch.float32).view(-1, 1).to(DEV)
+    x, up = torch.randn(n, 40, device=DEV), torch.randn(n, 24, device=DEV)
+    m = sgx['M'].GATEncoder(n_units=None, n_heads=1, dropout=0, alpha=0.2).to(DEV)
+    sched = get_schedule(sse, DEV)
+    groups = sgx['ops'].group_ids(labs.reshape(-1), sched.ped_start, sched.ped_end, sched.scene_start)
+    Wi, ai, Wio, aio = m.gat_intra.stacked()
+    We, ae, Weo, aeo = m.gat_inter.stacked()
+    ps = [t.detach() for t in (Wi, ai, Wio, aio, We, ae, Weo, aeo, m.out_embedding.weight, m.out_embedding.bias)]
+    empty = sched.scene_start[:0]
+    fwd = lambda max_scene: sgx['ops'].gat_encoder_fwd(x, groups[0], groups[1], sched.ped_start, sched.ped_end, sched.n_scenes,
+                                                       *ps, 0.2, sched.scene_start, empty, 0, 32, max_scene)
+    bwd = lambda max_scene: sgx['ops'].gat_encoder_bwd(x, up, groups[0], groups[1], sched.ped_start, sched.ped_end,
+                                                       sched.n_scenes, *ps, 0.2, sched.scene_start, empty, 0, 32, max_scene)
+    with torch.no_grad():
+        assert_close(fwd(int(sched.max_n)), fwd(0), 1e-5, 'dense fwd %s' % sizes[:3])
+        for a, b in zip(bwd(int(sched.max_n)), bwd(0)):
+            assert_close(a, b, 5e-5, 'dense bwd %s' % sizes[:3], floor=1e-2 * float(b.abs().max()) + 1e-6)

@@ -107,6 +107,43 @@ def cfg4():
                               'pool_as_written_TFLOPs_over_whole_forward': flops / ms / 1e9}))
 
 
+def cfg4_ops():
+    """Op-level GATEncoder / GCNModule / PoolHiddenNet at dense-crowd scene sizes (SURVEY 8d cfg 4): forward and
+    forward+backward, algorithmic GB/s and FLOP/s (GAT: 190 N^2 + 8.4k N FLOP per scene, 260 B/ped fwd, 420 B/ped bwd)."""
+    hbm = peaks.get('hbm_gbs', 6650.0)
+    for n in (64, 128, 256, 512, 1024):
+        s = max(1, 65536 // n)
+        tot = n * s
+        rng = np.random.RandomState(n)
+        lab = np.floor(rng.uniform(0, 1, tot) * max(1, n // 3)).astype(np.float32) + 1
+        lab[rng.uniform(0, 1, tot) < 0.1] = 0
+        lab = torch.from_numpy(lab).view(-1, 1).to(dev)
+        sse = sse_of([n] * s).to(dev)
+        pos = torch.rand(tot, 2, device=dev) * 15
+        for name, mod in (('GATEncoder', M.GATEncoder(None, 1, 0, 0.2)), ('GCNModule', M.GCNModule())):
+            mod = mod.to(dev)
+            with torch.no_grad():
+                for p in mod.parameters():
+                    if name == 'GCNModule' and p.dim() == 2 and tuple(p.shape) != (24, 32):
+                        p.mul_(0.15)
+            x = torch.randn(tot, 40, device=dev)
+            with torch.no_grad():
+                f_ms = timed(lambda: mod(x, sse, pos, lab), reps=5, warm=2)
+            xg = x.clone().requires_grad_(True)
+            up = torch.randn(tot, 24, device=dev)
+
+            def fb():
+                mod.zero_grad(set_to_none=True)
+                xg.grad = None
+                (mod(xg, sse, pos, lab) * up).sum().backward()
+            fb_ms = timed(fb, reps=5, warm=2)
+            flops = s * (190 * n * n + 8400 * n) if name == 'GATEncoder' else s * 8100 * n
+            print(json.dumps({'config': 'cfg4 op-level', 'op': name, 'N': n, 'scenes': s, 'peds': tot, 'fwd_ms': f_ms,
+                              'fwd_bwd_ms': fb_ms, 'fwd_GBps_algorithmic': 260 * tot / f_ms / 1e6,
+                              'fwd_frac_hbm': 260 * tot / f_ms / 1e6 / hbm, 'fwd_GFLOPs_algorithmic': flops / f_ms / 1e6,
+                              'fwd_bwd_GBps_algorithmic': 680 * tot / fb_ms / 1e6}))
+
+
 def cfg2_small():
     """cfg 2 at the reference's own batch size: S = 64 zara1-shaped scenes (~240 peds), best-of-20 evaluation of one
     minibatch (scripts/evaluate_model.py:72-99).  Launch-latency regime: (a) the K forwards one after the other, as the
@@ -159,5 +196,7 @@ if __name__ == '__main__':
         cfg2_small()
     if 'cfg3' in which:
         cfg3()
+    if 'cfg4_ops' in which:
+        cfg4_ops()
     if 'cfg4' in which:
         cfg4()
