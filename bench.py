@@ -142,7 +142,7 @@ class ClockSampler:
         self.rows, self.proc, self.gpu = [], None, gpu_index
 
     def start(self):
-        """NVML polled every 20 ms from a thread (the timed region of a default run is ~80 ms, shorter than one
+        """NVML polled every 8 ms from a thread (the timed region of a default run is ~200 ms, about one
         `nvidia-smi -lms` period); the recipe's nvidia-smi query line is the fallback."""
         self.stop_flag = threading.Event()
         try:
@@ -164,10 +164,10 @@ class ClockSampler:
                         break
                     self.rows.append([time.perf_counter(), str(self.gpu), str(sm), str(max_sm), '%.1f' % pw, hex(r)] +
                                      ['Active' if r & b else 'Not Active' for _n, b in bits])
-                    self.stop_flag.wait(0.02)
+                    self.stop_flag.wait(0.008)
 
             self.proc = 'nvml'
-            self.source = 'nvml, 20 ms period'
+            self.source = 'nvml, 8 ms period'
             threading.Thread(target=poll, daemon=True).start()
             return
         except Exception:
@@ -290,7 +290,7 @@ def measured_traffic(config, kernel, scenes):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='sgx', choices=['sgx', 'reference'])
     ap.add_argument('--config', default='sgan_p', choices=sorted(CONFIGS))
@@ -632,9 +632,9 @@ def main():
         if train is not None:
             line['train_step'] = train
         if not args.no_cpu_baseline and world == 1:          # the CPU port is timed next to the 1-GPU number only
-            v, dt, p = cpu_port_traj_per_sec(2048, K_SAMPLES, 1234 + 2, config=args.config)   # ~10-20 s of CPU work
+            v, dt, p = cpu_port_traj_per_sec(8192, K_SAMPLES, 1234 + 2, config=args.config)   # ~10-20 s of CPU work
             line['cpu_baseline'] = {'value': v, 'unit': 'traj/s', 'cores': os.cpu_count(), 'kind': 'port',
-                                    'sample': '2048 scenes of the config\'s histogram (%d peds) x K=20 forwards, %.1f s' % (p, dt)}
+                                    'sample': '8192 scenes of the config\'s histogram (%d peds) x K=20 forwards, %.1f s' % (p, dt)}
         sys.stdout.flush()
         print(json.dumps(line), flush=True)
     if world > 1:

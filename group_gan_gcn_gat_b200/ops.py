@@ -316,7 +316,8 @@ def _(x, leader, gsize, ped_start, ped_end, scene_start, n_group, W0, W1, V0, V1
 @_custom_op('sgx::gcn_module_bwd')
 def gcn_module_bwd(x: Tensor, grad_out: Tensor, leader: Tensor, gsize: Tensor, ped_start: Tensor, ped_end: Tensor,
                    scene_start: Tensor, n_group: Tensor, W0: Tensor, W1: Tensor, V0: Tensor, V1: Tensor, Wo: Tensor,
-                   bo: Tensor) -> List[Tensor]:
+                   bo: Tensor, chunk_scene: Tensor, n_chunks: int) -> List[Tensor]:
+    """n_chunks > 0 (every scene <= 32 peds, built dims) selects the single-launch backward."""
     x, grad_out = _f32(x, 'x'), _f32(grad_out, 'grad_out')
     W0, W1, V0, V1, Wo, bo = (t.contiguous() for t in (W0, W1, V0, V1, Wo, bo))
     _check_gcn_shapes(x, W0, W1, V0, V1, Wo, bo)
@@ -325,8 +326,16 @@ def gcn_module_bwd(x: Tensor, grad_out: Tensor, leader: Tensor, gsize: Tensor, p
     S = scene_start.numel() - 1
     grads = [torch.empty_like(t) for t in (x, W0, W1, V0, V1, Wo, bo)]
     L = _lib.lib()
-    ws = _ws(L.sgx_gcn_module_ws_bytes(batch, S, IN, HID, OUT, FIN), x.device)
     with torch.cuda.device(x.device):
+        if n_chunks > 0 and HID == 72 and OUT == 16 and IN in (32, 40) and FIN in (24, 32):
+            ws = _ws(L.sgx_gcn_module_fused_bwd_ws_bytes(), x.device)
+            _lib.check(L.sgx_gcn_module_fused_bwd(_ptr(x), _ptr(grad_out), _ptr(leader), _ptr(gsize), _ptr(ped_start),
+                                                  _ptr(ped_end), _ptr(scene_start), _ptr(chunk_scene), n_chunks, _ptr(W0),
+                                                  _ptr(W1), _ptr(V0), _ptr(V1), _ptr(Wo), _ptr(bo), IN, HID, OUT, FIN,
+                                                  *[_ptr(g) for g in grads], _ptr(ws), ws.numel(), _stream(x)),
+                       'sgx_gcn_module_fused_bwd')
+            return grads
+        ws = _ws(L.sgx_gcn_module_ws_bytes(batch, S, IN, HID, OUT, FIN), x.device)
         _lib.check(L.sgx_gcn_module_bwd(_ptr(x), _ptr(grad_out), _ptr(leader), _ptr(gsize), _ptr(ped_start),
                                         _ptr(ped_end), _ptr(scene_start), _ptr(n_group), batch, S, _ptr(W0), _ptr(W1),
                                         _ptr(V0), _ptr(V1), _ptr(Wo), _ptr(bo), IN, HID, OUT, FIN,
@@ -336,17 +345,19 @@ def gcn_module_bwd(x: Tensor, grad_out: Tensor, leader: Tensor, gsize: Tensor, p
 
 
 @gcn_module_bwd.register_fake
-def _(x, grad_out, leader, gsize, ped_start, ped_end, scene_start, n_group, W0, W1, V0, V1, Wo, bo):
+def _(x, grad_out, leader, gsize, ped_start, ped_end, scene_start, n_group, W0, W1, V0, V1, Wo, bo, chunk_scene, n_chunks):
     return [torch.empty_like(t) for t in (x, W0, W1, V0, V1, Wo, bo)]
 
 
 def _gcn_setup(ctx, inputs, output):
-    ctx.save_for_backward(*inputs[:13])
+    ctx.save_for_backward(*inputs[:14])
+    ctx.n_chunks = inputs[14]
 
 
 def _gcn_backward(ctx, grad_out):
-    x, leader, gsize, ps, pe, ss, ng, W0, W1, V0, V1, Wo, bo = ctx.saved_tensors
-    g = gcn_module_bwd(x, grad_out.contiguous(), leader, gsize, ps, pe, ss, ng, W0, W1, V0, V1, Wo, bo)
+    x, leader, gsize, ps, pe, ss, ng, W0, W1, V0, V1, Wo, bo, chunk_scene = ctx.saved_tensors
+    g = gcn_module_bwd(x, grad_out.contiguous(), leader, gsize, ps, pe, ss, ng, W0, W1, V0, V1, Wo, bo, chunk_scene,
+                       ctx.n_chunks)
     return g[0], None, None, None, None, None, None, g[1], g[2], g[3], g[4], g[5], g[6], None, None
 
 

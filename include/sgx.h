@@ -183,6 +183,18 @@ int sgx_gcn_module_bwd(const float* x, const float* grad_out, const int32_t* lea
                        float* grad_V1, float* grad_Wo, float* grad_bo, void* workspace, int64_t ws_bytes,
                        void* stream);
 
+/* GCNModule backward in one launch (+ a 30 KB reduction) for the batches sgx_gcn_module_fused_fwd covers (every scene <= 32
+ * peds; input 32|40, hidden 72, out 16, final 24|32): the forward is recomputed per chunk inside the kernel, nothing but x,
+ * grad_out and grad_x touches HBM.  Gradient buffers are overwritten.  workspace: sgx_gcn_module_fused_bwd_ws_bytes(). */
+int64_t sgx_gcn_module_fused_bwd_ws_bytes(void);
+int sgx_gcn_module_fused_bwd(const float* x, const float* grad_out, const int32_t* leader, const int32_t* group_size,
+                             const int32_t* ped_start, const int32_t* ped_end, const int32_t* scene_start,
+                             const int32_t* chunk_scene, int64_t n_chunks, const float* W0, const float* W1,
+                             const float* V0, const float* V1, const float* Wo, const float* bo, int32_t IN, int32_t HID,
+                             int32_t OUT, int32_t FIN, float* grad_x, float* grad_W0, float* grad_W1, float* grad_V0,
+                             float* grad_V1, float* grad_Wo, float* grad_bo, void* workspace, int64_t ws_bytes,
+                             void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * GATEncoder.forward (sgan/models.py:254-294), dropout = 0:
  *   x [batch,IN]; every GAT is  n_heads x GraphAttentionLayer(F_in -> HID, concat) then
