@@ -30,6 +30,7 @@ SIGNATURES = {
     'sgx_last_error': (ctypes.c_char_p, []),
     'sgx_version': (ctypes.c_int, []),
     'sgx_has_tcgen05': (ctypes.c_int, []),
+    'sgx_set_option': (ctypes.c_int, [ctypes.c_char_p, _I32]),
     'sgx_launch_count': (ctypes.c_longlong, []),
     'sgx_profile_events': (ctypes.c_int, [_P, _P]),
     'sgx_schedule_stats': (ctypes.c_int, [_P, _I64, _P]),
@@ -115,7 +116,16 @@ def lib():
     if missing:
         raise SgxError('libsgx_b200.so lacks symbols declared in include/sgx.h: %s' % ', '.join(missing))
     _lib = handle
+    # switches are resolved HERE, once, and handed to the library as options (no getenv on any call path)
+    for env, opt in (('SGX_LSTM_TC', b'lstm_tc'), ('SGX_GAT_MMA', b'gat_mma'), ('SGX_GCN_MMA', b'gcn_mma')):
+        if env in os.environ:
+            handle.sgx_set_option(opt, 0 if os.environ[env] == '0' else 1)      # unknown in this build: ignored
     return _lib
+
+
+def set_option(name, value):
+    """sgx_set_option: 'lstm_tc' (and 'gat_mma' / 'gcn_mma' in -DSGX_AB_VARIANTS builds)."""
+    check(lib().sgx_set_option(name.encode(), int(value)), 'sgx_set_option')
 
 
 def last_error():

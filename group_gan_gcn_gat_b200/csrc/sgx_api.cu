@@ -7,6 +7,7 @@
 #include <atomic>
 #include <numeric>
 #include <queue>
+#include <string>
 #include <vector>
 
 #include "sgx_common.cuh"
@@ -24,6 +25,30 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 static thread_local cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
 void profile_events(cudaEvent_t* start, cudaEvent_t* stop) { *start = g_ev_start; *stop = g_ev_stop; }
 }  // namespace sgx
+
+namespace sgx {
+// Process-wide switches, set ONCE by the host side at load time (group_gan_gcn_gat_b200/_lib.py resolves the SGX_*
+// environment variables) or by a test through sgx_set_option -- no getenv on any call path.
+static std::atomic<int> g_opt_lstm_tc{1};
+bool opt_lstm_tc() { return g_opt_lstm_tc.load(std::memory_order_relaxed) != 0; }
+#ifdef SGX_AB_VARIANTS
+static std::atomic<int> g_opt_gat_mma{1}, g_opt_gcn_mma{1};
+bool opt_gat_mma() { return g_opt_gat_mma.load(std::memory_order_relaxed) != 0; }
+bool opt_gcn_mma() { return g_opt_gcn_mma.load(std::memory_order_relaxed) != 0; }
+#endif
+}  // namespace sgx
+
+extern "C" int sgx_set_option(const char* name, int32_t value) {
+    SGX_REQUIRE(name != nullptr, "sgx_set_option: null name");
+    const std::string n(name);
+    if (n == "lstm_tc") { sgx::g_opt_lstm_tc.store(value); return SGX_OK; }
+#ifdef SGX_AB_VARIANTS
+    if (n == "gat_mma") { sgx::g_opt_gat_mma.store(value); return SGX_OK; }
+    if (n == "gcn_mma") { sgx::g_opt_gcn_mma.store(value); return SGX_OK; }
+#endif
+    sgx::set_error("sgx_set_option: unknown option '%s' in this build", name);
+    return SGX_ERR_UNSUPPORTED;
+}
 
 extern "C" long long sgx_launch_count(void) { return sgx::g_launches.load(); }
 extern "C" int sgx_profile_events(void* ev_start, void* ev_stop) {

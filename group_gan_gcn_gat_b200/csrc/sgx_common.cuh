@@ -14,6 +14,12 @@ void set_error(const char* fmt, ...);
 void count_launch();
 // optional events recorded around the dominant pooling kernel (bench instrumentation); null when unset
 void profile_events(cudaEvent_t* start, cudaEvent_t* stop);
+// process-wide switches (sgx_set_option; resolved once by the host side, never getenv on a call path)
+bool opt_lstm_tc();
+#ifdef SGX_AB_VARIANTS
+bool opt_gat_mma();
+bool opt_gcn_mma();
+#endif
 
 #define SGX_REQUIRE(cond, ...)                 \
     do {                                       \

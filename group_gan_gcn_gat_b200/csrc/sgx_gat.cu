@@ -1261,9 +1261,12 @@ static int gat_fused_forward(const float* x, const int32_t* leader, const int32_
         SGX_LAUNCH_CHECK();
         return SGX_OK;
     }
-    const int grid = std::min((n_chunks + FUSED_WARPS - 1) / FUSED_WARPS, 148);
-    const char* mode = getenv("SGX_GAT_MMA");
-    if (!(mode && mode[0] == '0')) {       // default: linear maps on the tensor cores (SGX_GAT_MMA=0: CUDA-core GEMV)
+#ifdef SGX_AB_VARIANTS
+    const bool mma = opt_gat_mma();        // A/B builds only: sgx_set_option("gat_mma", 0) selects the CUDA-core GEMV kernel
+#else
+    constexpr bool mma = true;
+#endif
+    if (mma) {                             // linear maps on the tensor cores
         auto kern_m = gat_fused_mma_kernel<40, 24>;
         const int smem_m = (int)(sizeof(FusedWm) + FUSEDM_WARPS * FUSEDM_SCRATCH * sizeof(float));
         SGX_CUDA(cudaFuncSetAttribute(kern_m, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_m));
@@ -1273,12 +1276,15 @@ static int gat_fused_forward(const float* x, const int32_t* leader, const int32_
         SGX_LAUNCH_CHECK();
         return SGX_OK;
     }
+#ifdef SGX_AB_VARIANTS
+    const int grid = std::min((n_chunks + FUSED_WARPS - 1) / FUSED_WARPS, 148);
     auto kern = gat_fused_fwd_kernel<40, 24>;
     const int smem = (int)(sizeof(FusedW) + FUSED_WARPS * FUSED_SCRATCH * sizeof(float));
     SGX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     kern<<<grid, FUSED_WARPS * 32, smem, st>>>(x, leader, gsize, ps, pe, scene_start, chunk_scene, n_chunks, Wi, ai, Wio,
                                                aio, We, ae, Weo, aeo, Wo, bo, alpha, out);
     SGX_LAUNCH_CHECK();
+#endif
     return SGX_OK;
 }
 

@@ -828,8 +828,12 @@ static int gcn_fused_launch(const float* x, const int32_t* leader, const int32_t
                             const int32_t* pe, const int32_t* scene_start, const int32_t* chunk_scene, int n_chunks,
                             const float* W0, const float* W1, const float* V0, const float* V1, const float* Wo,
                             const float* bo, float* out, cudaStream_t st) {
-    const char* mode = getenv("SGX_GCN_MMA");
-    if (!(mode && mode[0] == '0')) {       // default: linear maps on the tensor cores (SGX_GCN_MMA=0: CUDA-core GEMV)
+#ifdef SGX_AB_VARIANTS
+    const bool mma = opt_gcn_mma();        // A/B builds only: sgx_set_option("gcn_mma", 0) selects the CUDA-core GEMV kernel
+#else
+    constexpr bool mma = true;
+#endif
+    if (mma) {                             // linear maps on the tensor cores
         auto kern_m = gcn_fused_mma_kernel<IN, 72, 16, FIN>;
         const int wf = IN * GM_SW_WIDE + 2 * 72 * GM_SW_NARROW + 16 * GM_SW_WIDE + 32 * GmWo<FIN>::STRIDE + FIN;
         const int smem_m = (wf + GM_WARPS * GM_SCRATCH) * (int)sizeof(float);
@@ -840,6 +844,7 @@ static int gcn_fused_launch(const float* x, const int32_t* leader, const int32_t
         SGX_LAUNCH_CHECK();
         return SGX_OK;
     }
+#ifdef SGX_AB_VARIANTS
     auto kern = gcn_fused_fwd_kernel<IN, 72, 16, FIN>;
     const int wfloats = IN * 72 + 72 * 16 * 3 + FIN * 32 + ((FIN + 3) / 4) * 4;
     const int smem = (wfloats + GF_WARPS * GF_SCRATCH) * (int)sizeof(float);
@@ -848,6 +853,7 @@ static int gcn_fused_launch(const float* x, const int32_t* leader, const int32_t
     kern<<<grid, GF_WARPS * 32, smem, st>>>(x, leader, gsize, ps, pe, scene_start, chunk_scene, n_chunks, W0, W1, V0, V1,
                                             Wo, bo, out);
     SGX_LAUNCH_CHECK();
+#endif
     return SGX_OK;
 }
 

@@ -437,8 +437,7 @@ int sgx_lstm_tc_run(bool decoder, const float* seq_in, const float* h0, const fl
                     const float* b_hp, int E, float* seq_out, float* h_out, void* ws, cudaStream_t st);
 
 static bool use_tc(int H, int T, int64_t batch, const void* ws, int64_t ws_bytes) {
-    const char* off = getenv("SGX_LSTM_TC");
-    if (off && off[0] == '0') return false;
+    if (!opt_lstm_tc()) return false;      // sgx_set_option("lstm_tc", 0): CUDA-core kernels for every batch (parity tests)
     return H == 32 && T >= 2 && batch >= 8192 && ws != nullptr && ws_bytes >= sgx_lstm_tc_ws_bytes();
 }
 

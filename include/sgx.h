@@ -42,6 +42,11 @@ const char* sgx_last_error(void);
 int sgx_version(void);
 /* 1 when the current CUDA device can run the tcgen05 kernels of this build (compute capability 10.x) */
 int sgx_has_tcgen05(void);
+/* Process-wide switches, meant to be set once at load time (the Python host side resolves the SGX_* environment
+ * variables there; nothing in the library reads the environment).  "lstm_tc" (default 1): tcgen05 recurrence kernels
+ * for large inference batches, 0 = CUDA-core kernels for every batch.  Builds with -DSGX_AB_VARIANTS also know
+ * "gat_mma" / "gcn_mma" (0 = the CUDA-core GEMV single-launch kernels kept for A/B timing). */
+int sgx_set_option(const char* name, int32_t value);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches evidence) */
 long long sgx_launch_count(void);
 /* bench instrumentation: when both are non-null CUDA events (cudaEvent_t), sgx_pool_fwd records them on its
