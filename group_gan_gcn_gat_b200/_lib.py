@@ -117,14 +117,14 @@ def lib():
         raise SgxError('libsgx_b200.so lacks symbols declared in include/sgx.h: %s' % ', '.join(missing))
     _lib = handle
     # switches are resolved HERE, once, and handed to the library as options (no getenv on any call path)
-    for env, opt in (('SGX_LSTM_TC', b'lstm_tc'), ('SGX_GAT_MMA', b'gat_mma'), ('SGX_GCN_MMA', b'gcn_mma')):
+    for env, opt in (('SGX_LSTM_TC', b'lstm_tc'), ('SGX_GRAPH_TC', b'graph_tc'), ('SGX_GAT_MMA', b'gat_mma'), ('SGX_GCN_MMA', b'gcn_mma')):
         if env in os.environ:
             handle.sgx_set_option(opt, 0 if os.environ[env] == '0' else 1)      # unknown in this build: ignored
     return _lib
 
 
 def set_option(name, value):
-    """sgx_set_option: 'lstm_tc' (and 'gat_mma' / 'gcn_mma' in -DSGX_AB_VARIANTS builds)."""
+    """sgx_set_option: 'lstm_tc', 'graph_tc' (and 'gat_mma' / 'gcn_mma' in -DSGX_AB_VARIANTS builds)."""
     check(lib().sgx_set_option(name.encode(), int(value)), 'sgx_set_option')
 
 

@@ -31,6 +31,8 @@ namespace sgx {
 // environment variables) or by a test through sgx_set_option -- no getenv on any call path.
 static std::atomic<int> g_opt_lstm_tc{1};
 bool opt_lstm_tc() { return g_opt_lstm_tc.load(std::memory_order_relaxed) != 0; }
+static std::atomic<int> g_opt_graph_tc{1};
+bool opt_graph_tc() { return g_opt_graph_tc.load(std::memory_order_relaxed) != 0; }
 #ifdef SGX_AB_VARIANTS
 static std::atomic<int> g_opt_gat_mma{1}, g_opt_gcn_mma{1};
 bool opt_gat_mma() { return g_opt_gat_mma.load(std::memory_order_relaxed) != 0; }
@@ -42,6 +44,7 @@ extern "C" int sgx_set_option(const char* name, int32_t value) {
     SGX_REQUIRE(name != nullptr, "sgx_set_option: null name");
     const std::string n(name);
     if (n == "lstm_tc") { sgx::g_opt_lstm_tc.store(value); return SGX_OK; }
+    if (n == "graph_tc") { sgx::g_opt_graph_tc.store(value); return SGX_OK; }
 #ifdef SGX_AB_VARIANTS
     if (n == "gat_mma") { sgx::g_opt_gat_mma.store(value); return SGX_OK; }
     if (n == "gcn_mma") { sgx::g_opt_gcn_mma.store(value); return SGX_OK; }

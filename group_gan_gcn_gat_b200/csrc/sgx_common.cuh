@@ -16,6 +16,7 @@ void count_launch();
 void profile_events(cudaEvent_t* start, cudaEvent_t* stop);
 // process-wide switches (sgx_set_option; resolved once by the host side, never getenv on a call path)
 bool opt_lstm_tc();
+bool opt_graph_tc();      // tcgen05 GATEncoder / GCNModule forwards (default 1); 0: the mma.sync kernels (parity tests)
 #ifdef SGX_AB_VARIANTS
 bool opt_gat_mma();
 bool opt_gcn_mma();

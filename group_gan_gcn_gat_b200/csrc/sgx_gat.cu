@@ -1245,6 +1245,12 @@ gat_fused_mma64_kernel(const float* __restrict__ x, const int32_t* __restrict__ 
     }
 }
 
+int gat_fused_tc_forward(const float* x, const int32_t* leader, const int32_t* gsize, const int32_t* ps, const int32_t* pe,
+                         const int32_t* scene_start, const int32_t* chunk_scene, int n_chunks, const float* Wi,
+                         const float* ai, const float* Wio, const float* aio, const float* We, const float* ae,
+                         const float* Weo, const float* aeo, const float* Wo, const float* bo, float alpha, float* out,
+                         cudaStream_t st);   // sgx_gat_tc.cu
+
 static int gat_fused_forward(const float* x, const int32_t* leader, const int32_t* gsize, const int32_t* ps,
                              const int32_t* pe, const int32_t* scene_start, const int32_t* chunk_scene, int n_chunks,
                              int chunk_cap,
@@ -1261,6 +1267,9 @@ static int gat_fused_forward(const float* x, const int32_t* leader, const int32_
         SGX_LAUNCH_CHECK();
         return SGX_OK;
     }
+    if (opt_graph_tc())                    // linear maps on tcgen05 (sgx_gat_tc.cu)
+        return gat_fused_tc_forward(x, leader, gsize, ps, pe, scene_start, chunk_scene, n_chunks, Wi, ai, Wio, aio, We, ae,
+                                    Weo, aeo, Wo, bo, alpha, out, st);
 #ifdef SGX_AB_VARIANTS
     const bool mma = opt_gat_mma();        // A/B builds only: sgx_set_option("gat_mma", 0) selects the CUDA-core GEMV kernel
 #else

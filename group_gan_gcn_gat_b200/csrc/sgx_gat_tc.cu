@@ -1,0 +1,574 @@
+// GATEncoder forward (sgan/models.py:254-294; GraphAttentionLayer 198-220, GAT 231-237) with the five linear maps on
+// the 5th-gen tensor cores (tcgen05.mma kind::f16, accumulators in TMEM) -- the single-launch path for batches whose
+// scenes fit a warp chunk (<= 32 pedestrians), n_heads = 1, dims 40 / 72 / 16 / 24.
+//
+// The mma.sync kernel (sgx_gat.cu, gat_fused_mma_kernel) spends ~40 % of its instruction stream on the warp-level GEMMs
+// (fragment loads, 3xTF32 splits, 816 HMMA per chunk) and is issue bound.  Here a TILE is 128 pedestrians = four warp
+// chunks; a tile GROUP of four warps (thread = pedestrian = TMEM lane) walks the layer chain
+//     x -> [Wi] -> attention (group) -> ELU -> [Wio] -> attention -> ELU, log_softmax = x1 -> mean over the group = Xg
+//       -> [We] -> attention (leaders of the scene) -> ELU -> [Weo] -> attention -> ELU, log_softmax = Yg
+//       -> cat(x1, Yg[leader] / |group|) -> [Wo] + bo
+// and every [W] is ONE batch of tcgen05.mma over the tile's 128 rows:
+//   * fp32-grade accuracy from fp16 operand splits, v = hi + lo (11 + 11 significant bits), three products
+//     lo.hi + hi.lo + hi.hi accumulated in fp32 (~7e-7 relative, the level of the 3xTF32 kernel it replaces).  fp16 has a
+//     narrow exponent range, so every activation ROW is multiplied by its own power of two (row maximum -> [2^13, 2^14))
+//     before the split and every weight matrix by one power of two; both are undone exactly on the way out of TMEM.
+//   * operands in the no-swizzle K-major canonical layout: K core kc (8 halves = 16 bytes) of row r at kc * 2048 + r * 16.
+//     The SAME 40 KB buffer is, alternately, the A operand of a layer (fp16 cores) and the fp32 row buffer the attention
+//     reads its neighbours' Wh rows from (feature quad f of row r at f * 2048 + r * 16): a layer's A operand is dead once
+//     its MMAs have completed, and the Wh rows are dead once the tile's warps have built the next A operand.  Both uses
+//     touch only the 512-byte pieces of the pedestrian's own warp, so the hand-over needs a __syncwarp, not a barrier.
+//   * the attention scores ride along as two extra weight columns (W a1, W a2), as in the mma.sync kernel.
+//   * per layer: build the operand rows, fence.proxy.async, a 128-thread named barrier, one elected thread issues
+//     3 K/16 MMAs + tcgen05.commit, the group waits on its mbarrier, tcgen05.ld brings the thread's own row back.
+// One CTA per SM holds FOUR tile groups (16 warps) that share one 44 KB set of weight images and interleave their MMA
+// round trips; TMEM: 128 columns per group.  Every member of a group computes its group's rows of the inter level
+// (identical operand rows give identical accumulator rows), so no lane is ever predicated off and nothing is zeroed.  The weight images are built in-kernel from the fp32 parameters (a few
+// microseconds per CTA, overlapped across SMs) so the entry point keeps its stateless signature.
+#include "sgx_gat_fused.cuh"
+#include "sgx_tc.cuh"
+
+namespace sgx {
+namespace gtc {
+
+#ifndef GTC_GROUPS
+#define GTC_GROUPS 3
+#endif
+#ifndef GTC_FASTPATH
+#define GTC_FASTPATH 1
+#endif
+constexpr int GROUPS = GTC_GROUPS;
+constexpr int NTHREADS = GROUPS * 128;
+constexpr int IN = 40, FIN = 24;
+constexpr int CORE = 2048;               // bytes of one K core (16 B) over the 128 rows of a tile
+
+// weight images [hi cores | lo cores], core kc of output column n at kc * N * 16 + n * 16
+constexpr int N1 = 80, K1 = 48;          // Wi  + 2 score columns: 40 (padded to 48) -> 72 + 2
+constexpr int N2 = 32, K2 = 80;          // Wio + 2 score columns: 72 (padded to 80) -> 16 + 2
+constexpr int N3 = 80, K3 = 16;          // We
+constexpr int N4 = 32, K4 = 80;          // Weo
+constexpr int N5 = 32, K5 = 32;          // Wo^T: cat(32) -> 24
+constexpr int OFF_W1 = 0;
+constexpr int OFF_W2 = OFF_W1 + 4 * K1 * N1;
+constexpr int OFF_W3 = OFF_W2 + 4 * K2 * N2;
+constexpr int OFF_W4 = OFF_W3 + 4 * K3 * N3;
+constexpr int OFF_W5 = OFF_W4 + 4 * K4 * N4;
+constexpr int OFF_BO = OFF_W5 + 4 * K5 * N5;          // float[32]: bo
+constexpr int OFF_WS = OFF_BO + 128;                  // float[8]: inverse weight scales; uint[8]: max |w| bits
+constexpr int OFF_BAR = OFF_WS + 64;                  // GROUPS mbarriers + the TMEM base slot
+constexpr int OFF_GRP = OFF_BAR + 64;
+constexpr int ABUF = 20 * CORE;                       // A operand (K <= 80: 10 hi + 10 lo cores) / 72-wide fp32 rows
+constexpr int NCORE = 16;                             // the 16-wide fp32 rows (Wh2 / x1 / Wh4) live in cores 16..19
+constexpr int GRP_BYTES = ABUF + 128 * 8;             // + (s, t) per row
+constexpr int SMEM_TOTAL = OFF_GRP + GROUPS * GRP_BYTES + 128;
+constexpr int STAGE_FLOATS = N1 * K1 + N2 * K2 + N3 * K3 + N4 * K4 + N5 * K5;
+static_assert(OFF_GRP % 128 == 0 && GRP_BYTES % 128 == 0, "operand buffers must stay 128-byte aligned");
+static_assert(STAGE_FLOATS * 4 <= GROUPS * GRP_BYTES, "the fp32 staging of the weight prep lives in the group buffers");
+static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory");
+
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t (&v)[2]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+}
+
+// power-of-two scale that brings a maximum of magnitude `m` into [2^13, 2^14) -- or exactly 1 when m is already in
+// [2^-2, 2^15) (or zero): fp16 hi + lo then carries >= 22 significant bits of the row maximum without any scaling
+__device__ __forceinline__ bool scale_free(float m) { return (m >= 0.25f && m < 32768.f) || m == 0.f; }
+__device__ __forceinline__ void pow2_scale(float m, float& s, float& inv) {
+    const int e = (int)((__float_as_uint(m) >> 23) & 0xffu);
+    const int se = min(267 - e, 253);
+    s = __uint_as_float((uint32_t)se << 23);
+    inv = __uint_as_float((uint32_t)(254 - se) << 23);
+}
+
+template <int K, int KP, bool SCALED>
+__device__ __forceinline__ void write_cores(uint8_t* __restrict__ arow, const float (&v)[K], float s) {
+    constexpr int KC = KP / 8;
+#pragma unroll
+    for (int kc = 0; kc < KC; ++kc) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k0 = kc * 8 + 2 * j;
+            float a0 = (k0 < K) ? v[k0 < K ? k0 : 0] : 0.f;
+            float a1 = (k0 + 1 < K) ? v[k0 + 1 < K ? k0 + 1 : 0] : 0.f;
+            if (SCALED) { a0 *= s; a1 *= s; }
+            const uint32_t h = pack_f16_rn(a0, a1);
+            float l0, l1;
+            sub_f16x2(h, a0, a1, l0, l1);
+            hi[j] = h;
+            lo[j] = pack_f16_rn(l0, l1);
+        }
+        *reinterpret_cast<uint4*>(arow + kc * CORE) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(arow + (KC + kc) * CORE) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+// One activation row -> fp16 hi / lo K cores of the A operand; returns the factor that undoes the row's scale.  The
+// rows of a warp take the unscaled path together when every row maximum is inside the scale-free range (the usual case).
+template <int K, int KP>
+__device__ __forceinline__ float row_to_operand(uint8_t* __restrict__ arow, const float (&v)[K]) {
+    float m = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) m = fmaxf(m, fabsf(v[k]));
+#if GTC_FASTPATH
+    if (__all_sync(0xffffffffu, scale_free(m))) {
+        write_cores<K, KP, false>(arow, v, 1.f);
+        return 1.f;
+    }
+#endif
+    float s, inv;
+    pow2_scale(m, s, inv);
+    write_cores<K, KP, true>(arow, v, s);
+    return inv;
+}
+
+// D[128 x N] = A . B^T for one tile: 3 K/16 MMAs (lo.hi, hi.lo, hi.hi) + commit; called by ONE thread
+template <int KP, int N>
+__device__ __forceinline__ void issue_layer(uint32_t d_tmem, uint32_t a_s, uint32_t b_s, uint64_t* bar) {
+    constexpr int KC = KP / 8, KS = KP / 16;
+    constexpr uint32_t idesc = make_idesc_f16(128, N);
+    const uint64_t a_hi = make_desc_ns(a_s, CORE, 128), a_lo = make_desc_ns(a_s + KC * CORE, CORE, 128);
+    const uint64_t b_hi = make_desc_ns(b_s, N * 16, 128), b_lo = make_desc_ns(b_s + KC * N * 16, N * 16, 128);
+#pragma unroll
+    for (int s = 0; s < KS; ++s)
+        mma_ss(d_tmem, a_lo + (uint64_t)(s * (2 * CORE / 16)), b_hi + (uint64_t)(s * (2 * N * 16 / 16)), idesc, s > 0);
+#pragma unroll
+    for (int s = 0; s < KS; ++s)
+        mma_ss(d_tmem, a_hi + (uint64_t)(s * (2 * CORE / 16)), b_lo + (uint64_t)(s * (2 * N * 16 / 16)), idesc, 1);
+#pragma unroll
+    for (int s = 0; s < KS; ++s)
+        mma_ss(d_tmem, a_hi + (uint64_t)(s * (2 * CORE / 16)), b_hi + (uint64_t)(s * (2 * N * 16 / 16)), idesc, 1);
+    tc_commit(bar);
+}
+
+// attention of one node over the lanes set in `mask`; neighbour rows in the core layout (quad f of lane q at
+// f * CORE + q * 16 from `wrows`, the first row of this warp), scores (s, t) per lane in `st`.  Same term order as
+// attend_mask (sgx_gat_fused.cuh).
+template <int F>
+__device__ __forceinline__ void attend_core(const uint8_t* __restrict__ wrows, const float2* __restrict__ st, uint32_t mask,
+                                            float s_i, float alpha, float (&hp)[F]) {
+    float m = -INFINITY;
+    for (uint32_t mm = mask; mm; mm &= mm - 1) m = fmaxf(m, lrelu(s_i + st[__ffs(mm) - 1].y, alpha));
+    float den = 0.f;
+#pragma unroll
+    for (int f = 0; f < F; ++f) hp[f] = 0.f;
+    for (uint32_t mm = mask; mm; mm &= mm - 1) {
+        const int q = __ffs(mm) - 1;
+        const float w = fexp(lrelu(s_i + st[q].y, alpha) - m);
+        den += w;
+        const uint8_t* row = wrows + q * 16;
+#pragma unroll
+        for (int f = 0; f < F / 4; ++f) {
+            const float4 v = *reinterpret_cast<const float4*>(row + f * CORE);
+            hp[4 * f] = fmaf(w, v.x, hp[4 * f]); hp[4 * f + 1] = fmaf(w, v.y, hp[4 * f + 1]);
+            hp[4 * f + 2] = fmaf(w, v.z, hp[4 * f + 2]); hp[4 * f + 3] = fmaf(w, v.w, hp[4 * f + 3]);
+        }
+    }
+    const float inv = 1.f / den;
+#pragma unroll
+    for (int f = 0; f < F; ++f) hp[f] *= inv;
+}
+
+template <int F>
+__device__ __forceinline__ void store_core_row(uint8_t* __restrict__ row, const float (&v)[F]) {
+#pragma unroll
+    for (int f = 0; f < F / 4; ++f)
+        *reinterpret_cast<float4*>(row + f * CORE) = make_float4(v[4 * f], v[4 * f + 1], v[4 * f + 2], v[4 * f + 3]);
+}
+
+// the thread's accumulator row (72 + 2 columns) out of TMEM -> fp32 quads of its own row + (s, t)
+__device__ __forceinline__ void wide_from_tmem(uint32_t d_mine, float sc, uint8_t* __restrict__ arow, float2& sv) {
+    uint32_t v0[32], v1[32], v2[8], v3[2];
+    tmem_ld32(d_mine, v0);
+    tmem_ld32(d_mine + 32, v1);
+    tmem_ld8(d_mine + 64, v2);
+    tmem_ld2(d_mine + 72, v3);
+    tmem_wait_ld();
+    if (GTC_FASTPATH && __all_sync(0xffffffffu, sc == 1.f)) {
+#pragma unroll
+        for (int f = 0; f < 8; ++f) *reinterpret_cast<uint4*>(arow + f * CORE) = make_uint4(v0[4 * f], v0[4 * f + 1], v0[4 * f + 2], v0[4 * f + 3]);
+#pragma unroll
+        for (int f = 0; f < 8; ++f) *reinterpret_cast<uint4*>(arow + (8 + f) * CORE) = make_uint4(v1[4 * f], v1[4 * f + 1], v1[4 * f + 2], v1[4 * f + 3]);
+#pragma unroll
+        for (int f = 0; f < 2; ++f) *reinterpret_cast<uint4*>(arow + (16 + f) * CORE) = make_uint4(v2[4 * f], v2[4 * f + 1], v2[4 * f + 2], v2[4 * f + 3]);
+        sv = make_float2(__uint_as_float(v3[0]), __uint_as_float(v3[1]));
+    } else {
+#pragma unroll
+        for (int f = 0; f < 8; ++f)
+            *reinterpret_cast<float4*>(arow + f * CORE) =
+                make_float4(__uint_as_float(v0[4 * f]) * sc, __uint_as_float(v0[4 * f + 1]) * sc,
+                            __uint_as_float(v0[4 * f + 2]) * sc, __uint_as_float(v0[4 * f + 3]) * sc);
+#pragma unroll
+        for (int f = 0; f < 8; ++f)
+            *reinterpret_cast<float4*>(arow + (8 + f) * CORE) =
+                make_float4(__uint_as_float(v1[4 * f]) * sc, __uint_as_float(v1[4 * f + 1]) * sc,
+                            __uint_as_float(v1[4 * f + 2]) * sc, __uint_as_float(v1[4 * f + 3]) * sc);
+#pragma unroll
+        for (int f = 0; f < 2; ++f)
+            *reinterpret_cast<float4*>(arow + (16 + f) * CORE) =
+                make_float4(__uint_as_float(v2[4 * f]) * sc, __uint_as_float(v2[4 * f + 1]) * sc,
+                            __uint_as_float(v2[4 * f + 2]) * sc, __uint_as_float(v2[4 * f + 3]) * sc);
+        sv = make_float2(__uint_as_float(v3[0]) * sc, __uint_as_float(v3[1]) * sc);
+    }
+}
+// ... (16 + 2 columns) -> fp32 quads NCORE.. of its own row + (s, t)
+__device__ __forceinline__ void narrow_from_tmem(uint32_t d_mine, float sc, uint8_t* __restrict__ nrow, float2& sv) {
+    uint32_t v0[16], v3[2];
+    tmem_ld16(d_mine, v0);
+    tmem_ld2(d_mine + 16, v3);
+    tmem_wait_ld();
+#pragma unroll
+    for (int f = 0; f < 4; ++f)
+        *reinterpret_cast<float4*>(nrow + f * CORE) =
+            make_float4(__uint_as_float(v0[4 * f]) * sc, __uint_as_float(v0[4 * f + 1]) * sc,
+                        __uint_as_float(v0[4 * f + 2]) * sc, __uint_as_float(v0[4 * f + 3]) * sc);
+    sv = make_float2(__uint_as_float(v3[0]) * sc, __uint_as_float(v3[1]) * sc);
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+gat_fused_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ leader, const int32_t* __restrict__ gsize,
+                    const int32_t* __restrict__ ped_start, const int32_t* __restrict__ ped_end,
+                    const int32_t* __restrict__ scene_start, const int32_t* __restrict__ chunk_scene, int n_chunks,
+                    const float* __restrict__ Wi, const float* __restrict__ ai, const float* __restrict__ Wio,
+                    const float* __restrict__ aio, const float* __restrict__ We, const float* __restrict__ ae,
+                    const float* __restrict__ Weo, const float* __restrict__ aeo, const float* __restrict__ Wo,
+                    const float* __restrict__ bo, float alpha, float* __restrict__ out) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
+    uint8_t* smem = smem_raw + (sbase - smem_u32(smem_raw));
+    float* s_bo = reinterpret_cast<float*>(smem + OFF_BO);
+    float* s_winv = reinterpret_cast<float*>(smem + OFF_WS);
+    uint32_t* s_wmax = reinterpret_cast<uint32_t*>(smem + OFF_WS + 32);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + GROUPS);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = warp >> 2, wq = warp & 3;
+    const int n_tiles = (n_chunks + 3) >> 2;
+    const int tile_step = gridDim.x * GROUPS;
+
+    // the first tile's metadata is fetched before the weight prep so that its latency hides behind it
+    int tile = blockIdx.x * GROUPS + grp;
+    int p0 = 0, p1 = 0;                                      // first pedestrian of the chunk, one past its last
+    if (tile < n_tiles && tile * 4 + wq < n_chunks) {
+        p0 = scene_start[chunk_scene[tile * 4 + wq]];
+        p1 = scene_start[chunk_scene[tile * 4 + wq + 1]];
+    }
+    int cs0 = 0, cs1 = 0;                                    // scene bounds of the NEXT tile's chunk (loaded one tile ahead)
+    if (tile + tile_step < n_tiles && (tile + tile_step) * 4 + wq < n_chunks) {
+        cs0 = chunk_scene[(tile + tile_step) * 4 + wq];
+        cs1 = chunk_scene[(tile + tile_step) * 4 + wq + 1];
+    }
+
+    if (threadIdx.x == 0) {
+        for (int g = 0; g < GROUPS; ++g) mbar_init(&bars[g], 1);
+        fence_barrier_init();
+    }
+    if (threadIdx.x < 8) s_wmax[threadIdx.x] = 0u;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    // ---------------- weight prep: fp32 staging [n][k] (in the group buffers), per-matrix scale, hi/lo images ----------------
+    {
+        float* stage = reinterpret_cast<float*>(smem + OFF_GRP);
+        constexpr int S1 = 0, S2 = S1 + N1 * K1, S3 = S2 + N2 * K2, S4 = S3 + N3 * K3, S5 = S4 + N4 * K4;
+        for (int e = threadIdx.x; e < STAGE_FLOATS; e += NTHREADS) stage[e] = 0.f;
+        __syncthreads();
+        uint32_t mx[5] = {0u, 0u, 0u, 0u, 0u};
+        auto put = [&](int q, int idx, float v) {
+            stage[idx] = v;
+            const uint32_t b = __float_as_uint(v) & 0x7fffffffu;
+#pragma unroll
+            for (int qq = 0; qq < 5; ++qq) if (qq == q) mx[qq] = max(mx[qq], b);
+        };
+        // plain entries, global reads coalesced along the parameter's rows
+#pragma unroll 8
+        for (int e = threadIdx.x; e < IN * HID; e += NTHREADS) put(0, S1 + (e % HID) * K1 + e / HID, Wi[e]);
+#pragma unroll 4
+        for (int e = threadIdx.x; e < HID * OUT; e += NTHREADS) put(1, S2 + (e % OUT) * K2 + e / OUT, Wio[e]);
+#pragma unroll 4
+        for (int e = threadIdx.x; e < OUT * HID; e += NTHREADS) put(2, S3 + (e % HID) * K3 + e / HID, We[e]);
+#pragma unroll 4
+        for (int e = threadIdx.x; e < HID * OUT; e += NTHREADS) put(3, S4 + (e % OUT) * K4 + e / OUT, Weo[e]);
+#pragma unroll 2
+        for (int e = threadIdx.x; e < FIN * 2 * OUT; e += NTHREADS) put(4, S5 + e, Wo[e]);     // [n][k] already
+        // score columns W a1, W a2: the 72-long dots by warps, the 16-long ones by threads
+        for (int d = warp; d < 2 * (IN + OUT); d += NTHREADS / 32) {
+            const bool first = d < 2 * IN;
+            const int k = (first ? d : d - 2 * IN) >> 1, which = d & 1;
+            const float* wrow = (first ? Wi : We) + k * HID;
+            const float* av = (first ? ai : ae) + which * HID;
+            float part = 0.f;
+#pragma unroll
+            for (int c = lane; c < HID; c += 32) part = fmaf(wrow[c], av[c], part);
+            part = warp_sum(part);
+            if (lane == 0) put(first ? 0 : 2, (first ? S1 + (HID + which) * K1 : S3 + (HID + which) * K3) + k, part);
+        }
+        for (int d = threadIdx.x; d < 4 * HID; d += NTHREADS) {
+            const bool first = d < 2 * HID;
+            const int k = (first ? d : d - 2 * HID) >> 1, which = d & 1;
+            const float* wrow = (first ? Wio : Weo) + k * OUT;
+            const float* av = (first ? aio : aeo) + which * OUT;
+            float v = 0.f;
+#pragma unroll
+            for (int c = 0; c < OUT; ++c) v = fmaf(wrow[c], av[c], v);
+            put(first ? 1 : 3, (first ? S2 + (OUT + which) * K2 : S4 + (OUT + which) * K4) + k, v);
+        }
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            const uint32_t r = __reduce_max_sync(0xffffffffu, mx[q]);
+            if (lane == 0 && r) atomicMax(&s_wmax[q], r);
+        }
+        if (threadIdx.x < FIN) s_bo[threadIdx.x] = bo[threadIdx.x];
+        __syncthreads();
+        // units of one (matrix, column n, K core kc): 8 values -> one hi and one lo 16-byte core
+        constexpr int U1 = 0, U2 = U1 + N1 * K1 / 8, U3 = U2 + N2 * K2 / 8, U4 = U3 + N3 * K3 / 8, U5 = U4 + N4 * K4 / 8,
+                      UE = U5 + N5 * K5 / 8;
+        for (int u = threadIdx.x; u < UE; u += NTHREADS) {
+            int q, N, K, off, sb, ub;
+            if (u < U2) { q = 0; N = N1; K = K1; off = OFF_W1; sb = S1; ub = U1; }
+            else if (u < U3) { q = 1; N = N2; K = K2; off = OFF_W2; sb = S2; ub = U2; }
+            else if (u < U4) { q = 2; N = N3; K = K3; off = OFF_W3; sb = S3; ub = U3; }
+            else if (u < U5) { q = 3; N = N4; K = K4; off = OFF_W4; sb = S4; ub = U4; }
+            else { q = 4; N = N5; K = K5; off = OFF_W5; sb = S5; ub = U5; }
+            const int KC = K / 8;
+            const int kc = (u - ub) / N, n = (u - ub) % N;
+            const float wm = __uint_as_float(s_wmax[q]);
+            float s = 1.f, inv = 1.f;
+            if (!scale_free(wm)) pow2_scale(wm, s, inv);
+            const float* src = stage + sb + n * K + kc * 8;
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float a0 = src[2 * j] * s, a1 = src[2 * j + 1] * s;
+                const uint32_t h = pack_f16_rn(a0, a1);
+                float l0, l1;
+                sub_f16x2(h, a0, a1, l0, l1);
+                hi[j] = h;
+                lo[j] = pack_f16_rn(l0, l1);
+            }
+            *reinterpret_cast<uint4*>(smem + off + kc * N * 16 + n * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(smem + off + (KC + kc) * N * 16 + n * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            if (n == 0 && kc == 0) s_winv[q] = inv;
+        }
+        fence_proxy_async();
+        __syncthreads();
+    }
+
+    // ---------------- tile groups ----------------
+    uint8_t* abuf = smem + OFF_GRP + grp * GRP_BYTES;        // A operand / fp32 rows of the group's tile
+    float2* st = reinterpret_cast<float2*>(abuf + ABUF) + wq * 32;
+    const int row = wq * 32 + lane;                          // row of the tile = TMEM lane
+    uint8_t* arow = abuf + row * 16;                         // this pedestrian's 16 bytes of every core
+    uint8_t* nrow = arow + NCORE * CORE;
+    const uint8_t* wrows_a = abuf + wq * 512;                // first row of this warp, per core
+    const uint8_t* wrows_n = wrows_a + NCORE * CORE;
+    uint64_t* bar = &bars[grp];
+    const uint32_t a_s = sbase + OFF_GRP + grp * GRP_BYTES;
+    const uint32_t d_tmem = tmem + (uint32_t)grp * 128u;
+    const uint32_t d_mine = d_tmem + ((uint32_t)(wq * 32) << 16);
+    uint32_t parity = 0;
+    const float winv1 = s_winv[0], winv2 = s_winv[1], winv3 = s_winv[2], winv4 = s_winv[3], winv5 = s_winv[4];
+
+    // hand the operand rows to the tensor core, wait for the accumulator
+    auto run_layer = [&](auto issue) {
+        fence_proxy_async();
+        tc_fence_before();
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+        if (wq == 0) {
+            tc_fence_after();
+            if (elect_one()) issue();
+            __syncwarp();
+        }
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+        tc_fence_after();
+    };
+
+    // per-lane metadata and the x row of a chunk; lanes past the chunk get an all-zero row and a one-lane neighbourhood
+    // (raw values: nothing is computed from a prefetched word before the tile that uses it, a dependent instruction
+    // would stall the in-order warp on the load)
+    struct Meta { int b, e, lead, gs; };
+    auto load_meta = [&](int p0_, int np_) {
+        Meta m{p0_, p0_, p0_ + lane, 1};
+        if (lane < np_) {
+            const int p = p0_ + lane;
+            m.b = ped_start[p]; m.e = ped_end[p]; m.lead = leader[p]; m.gs = gsize[p];
+        }
+        return m;
+    };
+    float4 xq[IN / 4];
+    auto load_x = [&](int p0_, int np_) {
+#pragma unroll
+        for (int c = 0; c < IN / 4; ++c) xq[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane < np_) {
+            const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)(p0_ + lane) * IN);
+#pragma unroll
+            for (int c = 0; c < IN / 4; ++c) xq[c] = xr[c];
+        }
+    };
+    Meta mt = load_meta(p0, p1 - p0);
+    load_x(p0, p1 - p0);
+
+    for (; tile < n_tiles; tile += tile_step) {
+        const int np = p1 - p0;
+        const bool live = lane < np;
+        const int p = p0 + lane;
+        const float inv_g = __frcp_rn((float)mt.gs);
+        const int my_lead = mt.lead - p0, sb = mt.b - p0, se = mt.e - p0;
+        const bool is_lead = live && (my_lead == lane);
+        const uint32_t group_mask = __match_any_sync(0xffffffffu, live ? my_lead : 32 + lane);
+        const uint32_t scene_mask = (se >= 32 ? 0xffffffffu : ((1u << se) - 1u)) & ~((1u << sb) - 1u);
+        const uint32_t lead_ballot = __ballot_sync(0xffffffffu, is_lead);
+        const uint32_t leader_mask = live ? (lead_ballot & scene_mask) : (1u << lane);
+        float sc;
+        {
+            float xv[IN];
+#pragma unroll
+            for (int c = 0; c < IN / 4; ++c) { xv[4 * c] = xq[c].x; xv[4 * c + 1] = xq[c].y; xv[4 * c + 2] = xq[c].z; xv[4 * c + 3] = xq[c].w; }
+            sc = row_to_operand<IN, K1>(arow, xv) * winv1;
+        }
+        // the next tile's chunk bounds (its scene indices were loaded during the previous tile) and the scene indices of
+        // the tile after it: no load address depends on a word still in flight
+        const int ntile = tile + tile_step, nntile = ntile + tile_step;
+        int p0n = 0, p1n = 0;
+        if (ntile < n_tiles && ntile * 4 + wq < n_chunks) {
+            p0n = scene_start[cs0];
+            p1n = scene_start[cs1];
+        }
+        if (nntile < n_tiles && nntile * 4 + wq < n_chunks) {
+            cs0 = chunk_scene[nntile * 4 + wq];
+            cs1 = chunk_scene[nntile * 4 + wq + 1];
+        }
+
+        // ---- intra GAT, layer 1: Wh1 = x Wi (+ scores) ----
+        run_layer([&]() { issue_layer<K1, N1>(d_tmem, a_s, sbase + OFF_W1, bar); });
+        float2 sv;
+        wide_from_tmem(d_mine, sc, arow, sv);
+        st[lane] = sv;
+        __syncwarp();
+        {
+            float hp[HID];
+            attend_core<HID>(wrows_a, st, group_mask, sv.x, alpha, hp);
+#pragma unroll
+            for (int f = 0; f < HID; ++f) hp[f] = felu(hp[f]);
+            __syncwarp();                                    // every lane is done reading the Wh1 rows
+            sc = row_to_operand<HID, K2>(arow, hp) * winv2;
+        }
+        // ---- intra GAT, out_att: Wh2 = x1a Wio (+ scores) ----
+        run_layer([&]() { issue_layer<K2, N2>(d_tmem, a_s, sbase + OFF_W2, bar); });
+        narrow_from_tmem(d_mine, sc, nrow, sv);
+        st[lane] = sv;
+        __syncwarp();
+        float x1[OUT];
+        attend_core<OUT>(wrows_n, st, group_mask, sv.x, alpha, x1);
+        elu_logsoftmax<OUT>(x1);
+        __syncwarp();                                        // every lane is done reading the Wh2 rows
+        store_core_row<OUT>(nrow, x1);
+        __syncwarp();
+        // ---- GPool: Xg = mean of x1 over the group (every member computes its group's row) ----
+        {
+            float xg[OUT];
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) xg[o] = 0.f;
+            for (uint32_t mm = group_mask; mm; mm &= mm - 1) {
+                const int q = __ffs(mm) - 1;
+#pragma unroll
+                for (int f = 0; f < OUT / 4; ++f) {
+                    const float4 v = *reinterpret_cast<const float4*>(wrows_n + f * CORE + q * 16);
+                    xg[4 * f] = fmaf(inv_g, v.x, xg[4 * f]); xg[4 * f + 1] = fmaf(inv_g, v.y, xg[4 * f + 1]);
+                    xg[4 * f + 2] = fmaf(inv_g, v.z, xg[4 * f + 2]); xg[4 * f + 3] = fmaf(inv_g, v.w, xg[4 * f + 3]);
+                }
+            }
+            sc = row_to_operand<OUT, K3>(arow, xg) * winv3;
+        }
+        // ---- inter GAT, layer 1: Wh3 = Xg We (+ scores); the attention reads the LEADER rows of the scene, every member
+        //      of a group holds its leader's row and computes the same result ----
+        run_layer([&]() { issue_layer<K3, N3>(d_tmem, a_s, sbase + OFF_W3, bar); });
+        wide_from_tmem(d_mine, sc, arow, sv);
+        st[lane] = sv;
+        __syncwarp();
+        {
+            float hp[HID];
+            attend_core<HID>(wrows_a, st, leader_mask, sv.x, alpha, hp);
+#pragma unroll
+            for (int f = 0; f < HID; ++f) hp[f] = felu(hp[f]);
+            __syncwarp();
+            sc = row_to_operand<HID, K4>(arow, hp) * winv4;
+        }
+        // ---- inter GAT, out_att: Wh4 = hp Weo (+ scores) ----
+        run_layer([&]() { issue_layer<K4, N4>(d_tmem, a_s, sbase + OFF_W4, bar); });
+        narrow_from_tmem(d_mine, sc, nrow, sv);
+        st[lane] = sv;
+        __syncwarp();
+        // ---- unpool: cat = [x1 | Yg / |group|] (Yg of the own group, computed by every member), out = cat Wo^T + bo ----
+        {
+            float cat[2 * OUT], yg[OUT];
+            attend_core<OUT>(wrows_n, st, leader_mask, sv.x, alpha, yg);
+            elu_logsoftmax<OUT>(yg);
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) { cat[o] = x1[o]; cat[OUT + o] = inv_g * yg[o]; }
+            __syncwarp();                                    // the Wh4 rows (cores 16..19) are dead: cat may not overlap,
+            sc = row_to_operand<2 * OUT, K5>(arow, cat) * winv5;   // but the next tile's operand will
+        }
+        // the next tile's metadata and x row: in flight during the last round trip and the output stores
+        const Meta mtn = load_meta(p0n, p1n - p0n);
+        load_x(p0n, p1n - p0n);
+        run_layer([&]() { issue_layer<K5, N5>(d_tmem, a_s, sbase + OFF_W5, bar); });
+        {
+            uint32_t v0[32];
+            tmem_ld32(d_mine, v0);
+            tmem_wait_ld();
+            if (live) {
+                float4* orow = reinterpret_cast<float4*>(out + (int64_t)p * FIN);
+#pragma unroll
+                for (int f = 0; f < FIN / 4; ++f)
+                    orow[f] = make_float4(fmaf(__uint_as_float(v0[4 * f]), sc, s_bo[4 * f]),
+                                          fmaf(__uint_as_float(v0[4 * f + 1]), sc, s_bo[4 * f + 1]),
+                                          fmaf(__uint_as_float(v0[4 * f + 2]), sc, s_bo[4 * f + 2]),
+                                          fmaf(__uint_as_float(v0[4 * f + 3]), sc, s_bo[4 * f + 3]));
+            }
+        }
+        p0 = p0n; p1 = p1n; mt = mtn;
+        // the next tile's first operand overwrites the buffer: every warp of the group has read its accumulator (the
+        // tcgen05.wait::ld above) before it reaches the next barrier, and the fp32 rows / st are warp-private
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+    }
+}
+
+}  // namespace gtc
+
+int gat_fused_tc_forward(const float* x, const int32_t* leader, const int32_t* gsize, const int32_t* ps, const int32_t* pe,
+                         const int32_t* scene_start, const int32_t* chunk_scene, int n_chunks, const float* Wi,
+                         const float* ai, const float* Wio, const float* aio, const float* We, const float* ae,
+                         const float* Weo, const float* aeo, const float* Wo, const float* bo, float alpha, float* out,
+                         cudaStream_t st) {
+    auto kern = gtc::gat_fused_tc_kernel;
+    SGX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gtc::SMEM_TOTAL));
+    int dev = 0, sms = 148;
+    SGX_CUDA(cudaGetDevice(&dev));
+    SGX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int n_tiles = (n_chunks + 3) / 4;
+    const int grid = std::min((n_tiles + gtc::GROUPS - 1) / gtc::GROUPS, sms);
+    kern<<<grid, gtc::NTHREADS, gtc::SMEM_TOTAL, st>>>(x, leader, gsize, ps, pe, scene_start, chunk_scene, n_chunks, Wi, ai,
+                                                       Wio, aio, We, ae, Weo, aeo, Wo, bo, alpha, out);
+    SGX_LAUNCH_CHECK();
+    return SGX_OK;
+}
+
+}  // namespace sgx

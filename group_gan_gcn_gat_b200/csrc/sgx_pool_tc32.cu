@@ -65,41 +65,6 @@ struct Cfg {
     static constexpr int KSTEPS_H = H / 16;
 };
 
-// no-swizzle K-major descriptor: 8-row x 16-byte core matrices; lbo = byte distance between the two K cores of one
-// MMA K-step, sbo = byte distance between 8-row groups
-__device__ __forceinline__ uint64_t make_desc_ns(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-    d |= (uint64_t)(lbo >> 4) << 16;
-    d |= (uint64_t)(sbo >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    return d;
-}
-__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
-    // c_format f32 (1<<4), a_format = b_format = f16 (0), K-major A and B, N>>3 @17, M>>4 @24
-    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ uint32_t pack_f16_rn(float lo, float hi) {
-    uint32_t d;
-    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-    return d;
-}
-__device__ __forceinline__ uint32_t pack_f16_rz_relu(float lo, float hi) {
-    uint32_t d;
-    asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-    return d;
-}
-__device__ __forceinline__ uint32_t pack_f16_rn_relu(float lo, float hi) {
-    uint32_t d;
-    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-    return d;
-}
-// l0 = x0 - f32(h2.lo), l1 = x1 - f32(h2.hi): sm_100 mixed-precision FMA (f16 x f16 + f32, SASS FHFMA), exact
-__device__ __forceinline__ void sub_f16x2(uint32_t h2, float x0, float x1, float& l0, float& l1) {
-    asm("{\n\t.reg .b16 a, b, m1;\n\tmov.b32 {a, b}, %2;\n\tmov.b16 m1, 0xBC00;\n\t"
-        "fma.rn.f32.f16 %0, a, m1, %3;\n\tfma.rn.f32.f16 %1, b, m1, %4;\n\t}"
-        : "=f"(l0), "=f"(l1) : "r"(h2), "f"(x0), "f"(x1));
-}
 __device__ __forceinline__ float f16_round(float v) { return __half2float(__float2half_rn(v)); }
 
 // ---------------------------------------------------------------------------------------------

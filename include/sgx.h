@@ -44,7 +44,8 @@ int sgx_version(void);
 int sgx_has_tcgen05(void);
 /* Process-wide switches, meant to be set once at load time (the Python host side resolves the SGX_* environment
  * variables there; nothing in the library reads the environment).  "lstm_tc" (default 1): tcgen05 recurrence kernels
- * for large inference batches, 0 = CUDA-core kernels for every batch.  Builds with -DSGX_AB_VARIANTS also know
+ * for large inference batches, 0 = CUDA-core kernels for every batch.  "graph_tc" (default 1): tcgen05 kernels for the
+ * single-launch GATEncoder / GCNModule forwards, 0 = the warp-level mma.sync kernels (parity tests).  Builds with -DSGX_AB_VARIANTS also know
  * "gat_mma" / "gcn_mma" (0 = the CUDA-core GEMV single-launch kernels kept for A/B timing). */
 int sgx_set_option(const char* name, int32_t value);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches evidence) */
