@@ -56,6 +56,7 @@ SIGNATURES = {
     'sgx_gcn_module_ws_bytes': (_I64, [_I64, _I64, _I32, _I32, _I32, _I32]),
     'sgx_gcn_module_fwd': (ctypes.c_int, [_P] * 7 + [_I64, _I64] + [_P] * 6 + [_I32] * 4 + [_P, _P, _I64, _P]),
     'sgx_gcn_module_fused_fwd': (ctypes.c_int, [_P] * 7 + [_I64] + [_P] * 6 + [_I32] * 4 + [_P, _P]),
+    'sgx_gcn_module_fused_fwd_labels': (ctypes.c_int, [_P] * 6 + [_I64] + [_P] * 6 + [_I32] * 4 + [_P, _P]),
     'sgx_gcn_module_bwd': (ctypes.c_int, [_P] * 8 + [_I64, _I64] + [_P] * 6 + [_I32] * 4 + [_P] * 7 + [_P, _I64, _P]),
     'sgx_gcn_module_fused_bwd_ws_bytes': (_I64, []),
     'sgx_gcn_module_fused_bwd': (ctypes.c_int, [_P] * 8 + [_I64] + [_P] * 6 + [_I32] * 4 + [_P] * 7 + [_P, _I64, _P]),
@@ -63,6 +64,7 @@ SIGNATURES = {
     'sgx_gat_encoder_fwd': (ctypes.c_int, [_P] * 5 + [_I64, _I64] + [_P] * 10 + [_F32] + [_I32] * 5 +
                             [_P, _P, _I64, _P]),
     'sgx_gat_encoder_fused_fwd': (ctypes.c_int, [_P] * 7 + [_I64, _I32] + [_P] * 10 + [_F32] + [_I32] * 5 + [_P, _P]),
+    'sgx_gat_encoder_fused_fwd_labels': (ctypes.c_int, [_P] * 6 + [_I64] + [_P] * 10 + [_F32] + [_I32] * 5 + [_P, _P]),
     'sgx_gat_encoder_bwd': (ctypes.c_int, [_P] * 6 + [_I64, _I64] + [_P] * 10 + [_F32] + [_I32] * 5 + [_P] * 11 +
                             [_P, _I64, _P]),
     'sgx_gat_encoder_fwd_dense': (ctypes.c_int, [_P] * 6 + [_I64, _I64, _I32] + [_P] * 10 + [_F32] + [_I32] * 5 +
@@ -119,13 +121,24 @@ def lib():
     # switches are resolved HERE, once, and handed to the library as options (no getenv on any call path)
     for env, opt in (('SGX_LSTM_TC', b'lstm_tc'), ('SGX_GRAPH_TC', b'graph_tc'), ('SGX_GAT_MMA', b'gat_mma'), ('SGX_GCN_MMA', b'gcn_mma')):
         if env in os.environ:
-            handle.sgx_set_option(opt, 0 if os.environ[env] == '0' else 1)      # unknown in this build: ignored
+            val = 0 if os.environ[env] == '0' else 1
+            if handle.sgx_set_option(opt, val) == SGX_OK:                      # unknown in this build: ignored
+                OPTIONS[opt.decode()] = val
     return _lib
+
+
+OPTIONS = {'lstm_tc': 1, 'graph_tc': 1}      # host-side mirror of the library switches (defaults of the build)
 
 
 def set_option(name, value):
     """sgx_set_option: 'lstm_tc', 'graph_tc' (and 'gat_mma' / 'gcn_mma' in -DSGX_AB_VARIANTS builds)."""
     check(lib().sgx_set_option(name.encode(), int(value)), 'sgx_set_option')
+    OPTIONS[name] = int(value)
+
+
+def option(name):
+    lib()
+    return OPTIONS.get(name, 1)
 
 
 def last_error():

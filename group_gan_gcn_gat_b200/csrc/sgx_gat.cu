@@ -1245,7 +1245,7 @@ gat_fused_mma64_kernel(const float* __restrict__ x, const int32_t* __restrict__ 
     }
 }
 
-int gat_fused_tc_forward(const float* x, const int32_t* leader, const int32_t* gsize, const int32_t* ps, const int32_t* pe,
+int gat_fused_tc_forward(const float* x, const int32_t* leader, const int32_t* gsize, const float* labels, const int32_t* ps, const int32_t* pe,
                          const int32_t* scene_start, const int32_t* chunk_scene, int n_chunks, const float* Wi,
                          const float* ai, const float* Wio, const float* aio, const float* We, const float* ae,
                          const float* Weo, const float* aeo, const float* Wo, const float* bo, float alpha, float* out,
@@ -1268,7 +1268,7 @@ static int gat_fused_forward(const float* x, const int32_t* leader, const int32_
         return SGX_OK;
     }
     if (opt_graph_tc())                    // linear maps on tcgen05 (sgx_gat_tc.cu)
-        return gat_fused_tc_forward(x, leader, gsize, ps, pe, scene_start, chunk_scene, n_chunks, Wi, ai, Wio, aio, We, ae,
+        return gat_fused_tc_forward(x, leader, gsize, nullptr, ps, pe, scene_start, chunk_scene, n_chunks, Wi, ai, Wio, aio, We, ae,
                                     Weo, aeo, Wo, bo, alpha, out, st);
 #ifdef SGX_AB_VARIANTS
     const bool mma = opt_gat_mma();        // A/B builds only: sgx_set_option("gat_mma", 0) selects the CUDA-core GEMV kernel
@@ -1457,4 +1457,22 @@ extern "C" int sgx_gat_encoder_fused_fwd(const float* x, const int32_t* leader, 
                     "fused GAT encoder is built for n_heads=1, dims 40/72/16/24 (the shipped configuration)");
     return gat_fused_forward(x, leader, group_size, ped_start, ped_end, scene_start, chunk_scene, (int)n_chunks, chunk_cap, Wi, ai,
                              Wio, aio, We, ae, Weo, aeo, Wo, bo, alpha, out, (cudaStream_t)stream);
+}
+
+// The same forward with the group structure derived inside the kernel from the datasets_group labels (no sgx_group_ids
+// pass, no leader / size arrays): scenes <= 32 pedestrians, tcgen05 kernel.
+extern "C" int sgx_gat_encoder_fused_fwd_labels(const float* x, const float* labels, const int32_t* ped_start,
+                                                const int32_t* ped_end, const int32_t* scene_start,
+                                                const int32_t* chunk_scene, int64_t n_chunks, const float* Wi,
+                                                const float* ai, const float* Wio, const float* aio, const float* We,
+                                                const float* ae, const float* Weo, const float* aeo, const float* Wo,
+                                                const float* bo, float alpha, int32_t n_heads, int32_t IN, int32_t HID_,
+                                                int32_t OUT_, int32_t FIN, float* out, void* stream) {
+    SGX_REQUIRE(x && labels && ped_start && ped_end && scene_start && chunk_scene && Wi && ai && Wio && aio && We && ae &&
+                    Weo && aeo && Wo && bo && out, "sgx_gat_encoder_fused_fwd_labels: null pointer");
+    SGX_REQUIRE(n_chunks > 0 && n_chunks < ((int64_t)1 << 31), "sgx_gat_encoder_fused_fwd_labels: bad chunk count");
+    SGX_UNSUPPORTED(n_heads != 1 || IN != 40 || HID_ != HID || OUT_ != OUT || FIN != 24,
+                    "fused GAT encoder is built for n_heads=1, dims 40/72/16/24 (the shipped configuration)");
+    return gat_fused_tc_forward(x, nullptr, nullptr, labels, ped_start, ped_end, scene_start, chunk_scene, (int)n_chunks, Wi,
+                                ai, Wio, aio, We, ae, Weo, aeo, Wo, bo, alpha, out, (cudaStream_t)stream);
 }

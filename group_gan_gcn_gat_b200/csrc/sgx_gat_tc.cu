@@ -26,7 +26,7 @@
 // (identical operand rows give identical accumulator rows), so no lane is ever predicated off and nothing is zeroed.  The weight images are built in-kernel from the fp32 parameters (a few
 // microseconds per CTA, overlapped across SMs) so the entry point keeps its stateless signature.
 #include "sgx_gat_fused.cuh"
-#include "sgx_tc.cuh"
+#include "sgx_graph_tc.cuh"
 
 namespace sgx {
 namespace gtc {
@@ -40,7 +40,7 @@ namespace gtc {
 constexpr int GROUPS = GTC_GROUPS;
 constexpr int NTHREADS = GROUPS * 128;
 constexpr int IN = 40, FIN = 24;
-constexpr int CORE = 2048;               // bytes of one K core (16 B) over the 128 rows of a tile
+using namespace gtile;
 
 // weight images [hi cores | lo cores], core kc of output column n at kc * N * 16 + n * 16
 constexpr int N1 = 80, K1 = 48;          // Wi  + 2 score columns: 40 (padded to 48) -> 72 + 2
@@ -65,86 +65,6 @@ constexpr int STAGE_FLOATS = N1 * K1 + N2 * K2 + N3 * K3 + N4 * K4 + N5 * K5;
 static_assert(OFF_GRP % 128 == 0 && GRP_BYTES % 128 == 0, "operand buffers must stay 128-byte aligned");
 static_assert(STAGE_FLOATS * 4 <= GROUPS * GRP_BYTES, "the fp32 staging of the weight prep lives in the group buffers");
 static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory");
-
-__device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t (&v)[2]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                 : "r"(taddr));
-}
-
-// power-of-two scale that brings a maximum of magnitude `m` into [2^13, 2^14) -- or exactly 1 when m is already in
-// [2^-2, 2^15) (or zero): fp16 hi + lo then carries >= 22 significant bits of the row maximum without any scaling
-__device__ __forceinline__ bool scale_free(float m) { return (m >= 0.25f && m < 32768.f) || m == 0.f; }
-__device__ __forceinline__ void pow2_scale(float m, float& s, float& inv) {
-    const int e = (int)((__float_as_uint(m) >> 23) & 0xffu);
-    const int se = min(267 - e, 253);
-    s = __uint_as_float((uint32_t)se << 23);
-    inv = __uint_as_float((uint32_t)(254 - se) << 23);
-}
-
-template <int K, int KP, bool SCALED>
-__device__ __forceinline__ void write_cores(uint8_t* __restrict__ arow, const float (&v)[K], float s) {
-    constexpr int KC = KP / 8;
-#pragma unroll
-    for (int kc = 0; kc < KC; ++kc) {
-        uint32_t hi[4], lo[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int k0 = kc * 8 + 2 * j;
-            float a0 = (k0 < K) ? v[k0 < K ? k0 : 0] : 0.f;
-            float a1 = (k0 + 1 < K) ? v[k0 + 1 < K ? k0 + 1 : 0] : 0.f;
-            if (SCALED) { a0 *= s; a1 *= s; }
-            const uint32_t h = pack_f16_rn(a0, a1);
-            float l0, l1;
-            sub_f16x2(h, a0, a1, l0, l1);
-            hi[j] = h;
-            lo[j] = pack_f16_rn(l0, l1);
-        }
-        *reinterpret_cast<uint4*>(arow + kc * CORE) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(arow + (KC + kc) * CORE) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    }
-}
-
-// One activation row -> fp16 hi / lo K cores of the A operand; returns the factor that undoes the row's scale.  The
-// rows of a warp take the unscaled path together when every row maximum is inside the scale-free range (the usual case).
-template <int K, int KP>
-__device__ __forceinline__ float row_to_operand(uint8_t* __restrict__ arow, const float (&v)[K]) {
-    float m = 0.f;
-#pragma unroll
-    for (int k = 0; k < K; ++k) m = fmaxf(m, fabsf(v[k]));
-#if GTC_FASTPATH
-    if (__all_sync(0xffffffffu, scale_free(m))) {
-        write_cores<K, KP, false>(arow, v, 1.f);
-        return 1.f;
-    }
-#endif
-    float s, inv;
-    pow2_scale(m, s, inv);
-    write_cores<K, KP, true>(arow, v, s);
-    return inv;
-}
-
-// D[128 x N] = A . B^T for one tile: 3 K/16 MMAs (lo.hi, hi.lo, hi.hi) + commit; called by ONE thread
-template <int KP, int N>
-__device__ __forceinline__ void issue_layer(uint32_t d_tmem, uint32_t a_s, uint32_t b_s, uint64_t* bar) {
-    constexpr int KC = KP / 8, KS = KP / 16;
-    constexpr uint32_t idesc = make_idesc_f16(128, N);
-    const uint64_t a_hi = make_desc_ns(a_s, CORE, 128), a_lo = make_desc_ns(a_s + KC * CORE, CORE, 128);
-    const uint64_t b_hi = make_desc_ns(b_s, N * 16, 128), b_lo = make_desc_ns(b_s + KC * N * 16, N * 16, 128);
-#pragma unroll
-    for (int s = 0; s < KS; ++s)
-        mma_ss(d_tmem, a_lo + (uint64_t)(s * (2 * CORE / 16)), b_hi + (uint64_t)(s * (2 * N * 16 / 16)), idesc, s > 0);
-#pragma unroll
-    for (int s = 0; s < KS; ++s)
-        mma_ss(d_tmem, a_hi + (uint64_t)(s * (2 * CORE / 16)), b_lo + (uint64_t)(s * (2 * N * 16 / 16)), idesc, 1);
-#pragma unroll
-    for (int s = 0; s < KS; ++s)
-        mma_ss(d_tmem, a_hi + (uint64_t)(s * (2 * CORE / 16)), b_hi + (uint64_t)(s * (2 * N * 16 / 16)), idesc, 1);
-    tc_commit(bar);
-}
 
 // attention of one node over the lanes set in `mask`; neighbour rows in the core layout (quad f of lane q at
 // f * CORE + q * 16 from `wrows`, the first row of this warp), scores (s, t) per lane in `st`.  Same term order as
@@ -172,13 +92,6 @@ __device__ __forceinline__ void attend_core(const uint8_t* __restrict__ wrows, c
     const float inv = 1.f / den;
 #pragma unroll
     for (int f = 0; f < F; ++f) hp[f] *= inv;
-}
-
-template <int F>
-__device__ __forceinline__ void store_core_row(uint8_t* __restrict__ row, const float (&v)[F]) {
-#pragma unroll
-    for (int f = 0; f < F / 4; ++f)
-        *reinterpret_cast<float4*>(row + f * CORE) = make_float4(v[4 * f], v[4 * f + 1], v[4 * f + 2], v[4 * f + 3]);
 }
 
 // the thread's accumulator row (72 + 2 columns) out of TMEM -> fp32 quads of its own row + (s, t)
@@ -232,7 +145,7 @@ __device__ __forceinline__ void narrow_from_tmem(uint32_t d_mine, float sc, uint
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 gat_fused_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ leader, const int32_t* __restrict__ gsize,
-                    const int32_t* __restrict__ ped_start, const int32_t* __restrict__ ped_end,
+                    const float* __restrict__ labels, const int32_t* __restrict__ ped_start, const int32_t* __restrict__ ped_end,
                     const int32_t* __restrict__ scene_start, const int32_t* __restrict__ chunk_scene, int n_chunks,
                     const float* __restrict__ Wi, const float* __restrict__ ai, const float* __restrict__ Wio,
                     const float* __restrict__ aio, const float* __restrict__ We, const float* __restrict__ ae,
@@ -403,7 +316,9 @@ gat_fused_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ lea
         Meta m{p0_, p0_, p0_ + lane, 1};
         if (lane < np_) {
             const int p = p0_ + lane;
-            m.b = ped_start[p]; m.e = ped_end[p]; m.lead = leader[p]; m.gs = gsize[p];
+            m.b = ped_start[p]; m.e = ped_end[p];
+            if (labels != nullptr) m.lead = __float_as_int(labels[p]);      // group structure derived in the kernel
+            else { m.lead = leader[p]; m.gs = gsize[p]; }
         }
         return m;
     };
@@ -424,10 +339,12 @@ gat_fused_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ lea
         const int np = p1 - p0;
         const bool live = lane < np;
         const int p = p0 + lane;
-        const float inv_g = __frcp_rn((float)mt.gs);
-        const int my_lead = mt.lead - p0, sb = mt.b - p0, se = mt.e - p0;
+        const int sb = mt.b - p0, se = mt.e - p0;
+        int my_lead, gs;
+        uint32_t group_mask;
+        group_structure(labels != nullptr, live, lane, mt.lead, mt.gs, mt.b, p0, my_lead, gs, group_mask);
+        const float inv_g = __frcp_rn((float)gs);
         const bool is_lead = live && (my_lead == lane);
-        const uint32_t group_mask = __match_any_sync(0xffffffffu, live ? my_lead : 32 + lane);
         const uint32_t scene_mask = (se >= 32 ? 0xffffffffu : ((1u << se) - 1u)) & ~((1u << sb) - 1u);
         const uint32_t lead_ballot = __ballot_sync(0xffffffffu, is_lead);
         const uint32_t leader_mask = live ? (lead_ballot & scene_mask) : (1u << lane);
@@ -553,7 +470,7 @@ gat_fused_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ lea
 
 }  // namespace gtc
 
-int gat_fused_tc_forward(const float* x, const int32_t* leader, const int32_t* gsize, const int32_t* ps, const int32_t* pe,
+int gat_fused_tc_forward(const float* x, const int32_t* leader, const int32_t* gsize, const float* labels, const int32_t* ps, const int32_t* pe,
                          const int32_t* scene_start, const int32_t* chunk_scene, int n_chunks, const float* Wi,
                          const float* ai, const float* Wio, const float* aio, const float* We, const float* ae,
                          const float* Weo, const float* aeo, const float* Wo, const float* bo, float alpha, float* out,
@@ -565,7 +482,7 @@ int gat_fused_tc_forward(const float* x, const int32_t* leader, const int32_t* g
     SGX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int n_tiles = (n_chunks + 3) / 4;
     const int grid = std::min((n_tiles + gtc::GROUPS - 1) / gtc::GROUPS, sms);
-    kern<<<grid, gtc::NTHREADS, gtc::SMEM_TOTAL, st>>>(x, leader, gsize, ps, pe, scene_start, chunk_scene, n_chunks, Wi, ai,
+    kern<<<grid, gtc::NTHREADS, gtc::SMEM_TOTAL, st>>>(x, leader, gsize, labels, ps, pe, scene_start, chunk_scene, n_chunks, Wi, ai,
                                                        Wio, aio, We, ae, Weo, aeo, Wo, bo, alpha, out);
     SGX_LAUNCH_CHECK();
     return SGX_OK;

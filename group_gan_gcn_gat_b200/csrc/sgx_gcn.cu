@@ -824,10 +824,19 @@ gcn_fused_mma_kernel(const float* __restrict__ x, const int32_t* __restrict__ le
 }
 
 template <int IN, int FIN>
+int gcn_fused_tc_forward(const float* x, const int32_t* leader, const int32_t* gsize, const float* labels, const int32_t* ps, const int32_t* pe,
+                         const int32_t* scene_start, const int32_t* chunk_scene, int n_chunks, const float* W0,
+                         const float* W1, const float* V0, const float* V1, const float* Wo, const float* bo, float* out,
+                         cudaStream_t st);   // sgx_gcn_tc.cu
+
+template <int IN, int FIN>
 static int gcn_fused_launch(const float* x, const int32_t* leader, const int32_t* gsize, const int32_t* ps,
                             const int32_t* pe, const int32_t* scene_start, const int32_t* chunk_scene, int n_chunks,
                             const float* W0, const float* W1, const float* V0, const float* V1, const float* Wo,
                             const float* bo, float* out, cudaStream_t st) {
+    if (opt_graph_tc())                    // linear maps on tcgen05 (sgx_gcn_tc.cu)
+        return gcn_fused_tc_forward<IN, FIN>(x, leader, gsize, nullptr, ps, pe, scene_start, chunk_scene, n_chunks, W0, W1, V0, V1,
+                                             Wo, bo, out, st);
 #ifdef SGX_AB_VARIANTS
     const bool mma = opt_gcn_mma();        // A/B builds only: sgx_set_option("gcn_mma", 0) selects the CUDA-core GEMV kernel
 #else
@@ -974,5 +983,23 @@ extern "C" int sgx_gcn_module_fused_fwd(const float* x, const int32_t* leader, c
     int rc = SGX_OK;
     GCN_DISPATCH((rc = gcn_fused_launch<I, F>(x, leader, group_size, ped_start, ped_end, scene_start, chunk_scene,
                                               (int)n_chunks, W0, W1, V0, V1, Wo, bo, out, st)));
+    return rc;
+}
+
+// The same forward with the group structure derived inside the kernel from the datasets_group labels (no sgx_group_ids
+// pass, no leader / size / n_group arrays): scenes <= 32 pedestrians, tcgen05 kernel.
+extern "C" int sgx_gcn_module_fused_fwd_labels(const float* x, const float* labels, const int32_t* ped_start,
+                                               const int32_t* ped_end, const int32_t* scene_start,
+                                               const int32_t* chunk_scene, int64_t n_chunks, const float* W0,
+                                               const float* W1, const float* V0, const float* V1, const float* Wo,
+                                               const float* bo, int32_t IN, int32_t HID, int32_t OUT, int32_t FIN,
+                                               float* out, void* stream) {
+    SGX_REQUIRE(x && labels && ped_start && ped_end && scene_start && chunk_scene && W0 && W1 && V0 && V1 && Wo && bo && out,
+                "sgx_gcn_module_fused_fwd_labels: null pointer");
+    SGX_REQUIRE(n_chunks > 0 && n_chunks < ((int64_t)1 << 31), "sgx_gcn_module_fused_fwd_labels: bad chunk count");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = SGX_OK;
+    GCN_DISPATCH((rc = sgx::gcn_fused_tc_forward<I, F>(x, nullptr, nullptr, labels, ped_start, ped_end, scene_start, chunk_scene,
+                                                       (int)n_chunks, W0, W1, V0, V1, Wo, bo, out, st)));
     return rc;
 }

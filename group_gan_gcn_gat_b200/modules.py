@@ -19,7 +19,7 @@ import os
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import _lib, ops
 from .schedule import get_schedule
 
 
@@ -121,6 +121,10 @@ class PoolHiddenNet(nn.Module):
         return buf
 
 
+def _needs_grad(*tensors):
+    return torch.is_grad_enabled() and any(t.requires_grad for t in tensors)
+
+
 def _groups_for(sched, end_group):
     return ops.call(ops.group_ids, end_group.reshape(-1).float(), sched.ped_start, sched.ped_end, sched.scene_start)
 
@@ -173,6 +177,8 @@ class GAT(nn.Module):
     def stacked(self):
         """-> (W [heads,in,hid], a [heads,2*hid], Wout [heads*hid,out], aout [2*out]) for the fused encoder op."""
         atts = self.attentions
+        if len(atts) == 1:                                  # views: no stacking kernels on the single-head path
+            return atts[0].W.unsqueeze(0), atts[0].a.reshape(1, -1), self.out_att.W, self.out_att.a.reshape(-1)
         return (torch.stack([l.W for l in atts], 0), torch.stack([l.a.reshape(-1) for l in atts], 0),
                 self.out_att.W, self.out_att.a.reshape(-1))
 
@@ -195,9 +201,16 @@ class GATEncoder(nn.Module):
         sched = get_schedule(seq_start_end, h_states.device)
         if h_states.shape[0] != sched.batch:
             raise ValueError('h_states has %d rows but seq_start_end covers %d pedestrians' % (h_states.shape[0], sched.batch))
-        leader, gsize, _gid, _ng = _groups_for(sched, end_group)
         Wi, ai, Wio, aio = self.gat_intra.stacked()
         We, ae, Weo, aeo = self.gat_inter.stacked()
+        if (self.n_heads == 1 and sched.max_n <= 32 and _lib.option('graph_tc') and
+                not _needs_grad(h_states, Wi, ai, Wio, aio, We, ae, Weo, aeo, self.out_embedding.weight, self.out_embedding.bias)):
+            # inference: the tcgen05 kernel derives the group structure from the labels itself (no sgx_group_ids pass)
+            chunk_scene, n_chunks = sched.chunks(32)
+            return ops.gat_encoder_fwd_labels(h_states, end_group, sched.ped_start, sched.ped_end, Wi, ai, Wio, aio, We, ae,
+                                              Weo, aeo, self.out_embedding.weight, self.out_embedding.bias,
+                                              float(self.alpha), sched.scene_start, chunk_scene, n_chunks)
+        leader, gsize, _gid, _ng = _groups_for(sched, end_group)
         # single-launch kernel: warp chunks of <= 32 peds, or <= 64 (two slots per lane) when a scene exceeds 32
         cap = 32 if sched.max_n <= 32 else 64
         chunk_scene, n_chunks = sched.chunks(cap) if self.n_heads == 1 else (sched.scene_start[:0], 0)
@@ -254,7 +267,15 @@ class GCNModule(nn.Module):
         sched = get_schedule(seq_start_end, h_states.device)
         if h_states.shape[0] != sched.batch:
             raise ValueError('h_states has %d rows but seq_start_end covers %d pedestrians' % (h_states.shape[0], sched.batch))
+        chunk_scene, n_chunks = self._chunks(sched)
+        ws = (self.gcn_intra.W[0], self.gcn_intra.W[1], self.gcn_inter.W[0], self.gcn_inter.W[1], self.out_embedding.weight,
+              self.out_embedding.bias)
+        if (n_chunks > 0 and _lib.option('graph_tc') and ws[0].shape[1] == 72 and ws[1].shape[1] == 16 and
+                ws[0].shape[0] in (32, 40) and ws[4].shape[0] in (24, 32) and not _needs_grad(h_states, *ws)):
+            # inference: the tcgen05 kernel derives the group structure from the labels itself (no sgx_group_ids pass)
+            return ops.gcn_module_fwd_labels(h_states, end_group, sched.ped_start, sched.ped_end, sched.scene_start, *ws,
+                                             chunk_scene, n_chunks)
         leader, gsize, _gid, ngrp = _groups_for(sched, end_group)
         return ops.call(ops.gcn_module_fwd, h_states, leader, gsize, sched.ped_start, sched.ped_end, sched.scene_start, ngrp,
                                   self.gcn_intra.W[0], self.gcn_intra.W[1], self.gcn_inter.W[0], self.gcn_inter.W[1],
-                                  self.out_embedding.weight, self.out_embedding.bias, *self._chunks(sched))
+                                  self.out_embedding.weight, self.out_embedding.bias, chunk_scene, n_chunks)

@@ -313,6 +313,26 @@ def _(x, leader, gsize, ped_start, ped_end, scene_start, n_group, W0, W1, V0, V1
     return x.new_empty(x.shape[0], Wo.shape[0])
 
 
+def gcn_module_fwd_labels(x, labels, ped_start, ped_end, scene_start, W0, W1, V0, V1, Wo, bo, chunk_scene, n_chunks):
+    """Inference-only GCNModule forward with the group structure derived inside the tcgen05 kernel from the labels
+    (sgx_gcn_module_fused_fwd_labels): scenes <= 32 pedestrians, built dims.  No autograd."""
+    x = _f32(x, 'h_states')
+    labels = _f32(labels.reshape(-1), 'labels')
+    W0, W1, V0, V1, Wo, bo = (_f32(t, 'gcn weight') for t in (W0, W1, V0, V1, Wo, bo))
+    _check_gcn_shapes(x, W0, W1, V0, V1, Wo, bo)
+    if labels.numel() != x.shape[0]:
+        raise ValueError('labels has %d entries for %d pedestrians' % (labels.numel(), x.shape[0]))
+    batch, IN = x.shape
+    HID, OUT, FIN = W0.shape[1], W1.shape[1], Wo.shape[0]
+    out = torch.empty(batch, FIN, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().sgx_gcn_module_fused_fwd_labels(
+            _ptr(x), _ptr(labels), _ptr(ped_start), _ptr(ped_end), _ptr(scene_start), _ptr(chunk_scene), n_chunks, _ptr(W0),
+            _ptr(W1), _ptr(V0), _ptr(V1), _ptr(Wo), _ptr(bo), IN, HID, OUT, FIN, _ptr(out), _stream(x)),
+            'sgx_gcn_module_fused_fwd_labels')
+    return out
+
+
 @_custom_op('sgx::gcn_module_bwd')
 def gcn_module_bwd(x: Tensor, grad_out: Tensor, leader: Tensor, gsize: Tensor, ped_start: Tensor, ped_end: Tensor,
                    scene_start: Tensor, n_group: Tensor, W0: Tensor, W1: Tensor, V0: Tensor, V1: Tensor, Wo: Tensor,
@@ -402,6 +422,27 @@ def gat_encoder_fwd(x: Tensor, leader: Tensor, gsize: Tensor, ped_start: Tensor,
 def _(x, leader, gsize, ped_start, ped_end, n_scenes, Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo, alpha, scene_start,
       chunk_scene, n_chunks, chunk_cap=32, max_scene=0):
     return x.new_empty(x.shape[0], Wo.shape[0])
+
+
+def gat_encoder_fwd_labels(x, labels, ped_start, ped_end, Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo, alpha, scene_start,
+                           chunk_scene, n_chunks):
+    """Inference-only GATEncoder forward with the group structure derived inside the tcgen05 kernel from the labels
+    (sgx_gat_encoder_fused_fwd_labels): scenes <= 32 pedestrians, n_heads 1, dims 40/72/16/24.  No autograd."""
+    x = _f32(x, 'h_states')
+    labels = _f32(labels.reshape(-1), 'labels')
+    ps = [_f32(t, 'gat weight') for t in (Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo)]
+    _check_gat_shapes(x, *ps)
+    if labels.numel() != x.shape[0]:
+        raise ValueError('labels has %d entries for %d pedestrians' % (labels.numel(), x.shape[0]))
+    batch, IN = x.shape
+    nh, _, HID = Wi.shape
+    OUT, FIN = Wio.shape[1], Wo.shape[0]
+    out = torch.empty(batch, FIN, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().sgx_gat_encoder_fused_fwd_labels(
+            _ptr(x), _ptr(labels), _ptr(ped_start), _ptr(ped_end), _ptr(scene_start), _ptr(chunk_scene), n_chunks,
+            *[_ptr(p) for p in ps], alpha, nh, IN, HID, OUT, FIN, _ptr(out), _stream(x)), 'sgx_gat_encoder_fused_fwd_labels')
+    return out
 
 
 @_custom_op('sgx::gat_encoder_bwd')

@@ -1,0 +1,155 @@
+"""GPU parity of the tcgen05 GATEncoder / GCNModule forwards (csrc/sgx_gat_tc.cu, csrc/sgx_gcn_tc.cu): against the CPU
+oracle (fp32 and fp64 evaluation of sgan/models.py:254-294, 583-712), against the mma.sync kernels they replace
+(library switch graph_tc = 0), and the in-kernel group structure (labels entry points) against sgx_group_ids.
+Contract: 1e-5 of the largest output."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import sse_from_sizes
+from oracle import sgan_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def close(a, b, tol, what):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    assert a.shape == b.shape
+    e = ((a - b).abs().max() / max(1e-6, b.abs().max())).item()
+    assert e <= tol, '%s: relative error %.3e > %.1e' % (what, e, tol)
+
+
+def modules(in_dim=40, final=24):
+    import group_gan_gcn_gat_b200.modules as M
+    gat = M.GATEncoder(n_units=None, n_heads=1, dropout=0, alpha=0.2)
+    gcn = M.GCNModule(input_dim=in_dim, hidden_dim=72, out_dim=16, gcn_layers=2, final_dim=final)
+    with torch.no_grad():
+        for p in gcn.parameters():
+            if p.dim() == 2 and p.shape[0] != final:
+                p.mul_(0.15)                                   # plain randn GCN weights: keep activations O(1)
+    return gat, gcn
+
+
+def with_option(name, val, fn):
+    from group_gan_gcn_gat_b200 import _lib
+    _lib.set_option(name, val)
+    try:
+        return fn()
+    finally:
+        _lib.set_option(name, 1)
+
+
+def batch_of(sizes, seed, in_dim=40, label_hi=5):
+    rng = np.random.RandomState(seed)
+    torch.manual_seed(seed)
+    n = sum(sizes)
+    labs = torch.tensor(np.where(rng.rand(n) < 0.2, 0, rng.randint(1, label_hi, size=n)), dtype=torch.float32).view(-1, 1)
+    return sse_from_sizes(sizes), torch.randn(n, in_dim), torch.rand(n, 2), labs
+
+
+LAYOUTS = [[1], [32], [32, 32, 1], [31, 2, 32, 1, 1, 30], [1] * 70, [3, 5, 2] * 40, [7] * 18 + [32] * 3 + [1] * 5,
+           list(range(1, 33)) * 2]
+
+
+@pytest.mark.parametrize('sizes', LAYOUTS)
+def test_tc_forwards_vs_oracle_and_mma(sizes):
+    """every tile shape: a lone pedestrian, full chunks, partial tiles (fewer than four chunks), several tiles per group"""
+    sse, x, pos, labs = batch_of(sizes, sum(sizes) + len(sizes))
+    gat, gcn = modules()
+    ref_gat = O.gat_encoder(x, sse, pos, labs, gat.state_dict(), '', 0.2, 1)
+    ref_gcn = O.gcn_module(x, sse, pos, labs, gcn.state_dict(), '')
+    args = (x.to(DEV), sse.to(DEV), pos.to(DEV), labs.to(DEV))
+    for name, mod, ref in (('gat', gat.to(DEV), ref_gat), ('gcn', gcn.to(DEV), ref_gcn)):
+        with torch.no_grad():
+            out_labels = mod(*args)                                       # inference: group structure inside the kernel
+            out_mma = with_option('graph_tc', 0, lambda: mod(*args))
+        xg = args[0].clone().requires_grad_(True)
+        out_arrays = mod(xg, *args[1:])                                   # autograd: leader / size arrays from sgx_group_ids
+        close(out_labels, ref, 1e-5, '%s tcgen05 (labels) vs oracle' % name)
+        close(out_mma, ref, 1e-5, '%s mma.sync vs oracle' % name)
+        close(out_labels, out_mma, 5e-6, '%s tcgen05 vs mma.sync' % name)
+        assert torch.equal(out_labels, out_arrays.detach()), '%s: in-kernel group structure differs from sgx_group_ids' % name
+
+
+@pytest.mark.parametrize('in_dim,final', [(32, 24), (32, 32), (40, 32)])
+def test_gcn_tc_every_built_instance(in_dim, final):
+    sizes = [4, 32, 9, 1, 1, 17, 30, 2, 2, 8]
+    sse, x, pos, labs = batch_of(sizes, 17 + in_dim + final, in_dim)
+    _gat, gcn = modules(in_dim, final)
+    ref = O.gcn_module(x, sse, pos, labs, gcn.state_dict(), '')
+    with torch.no_grad():
+        out = gcn.to(DEV)(x.to(DEV), sse.to(DEV), pos.to(DEV), labs.to(DEV))
+    close(out, ref, 1e-5, 'gcn %d/%d' % (in_dim, final))
+
+
+def test_in_kernel_group_structure_label_edge_cases():
+    """float == semantics of the reference (sgan/models.py:263-267): +0.0 / -0.0 / NaN labels stand alone, fractional and
+    negative labels group by value, equal labels in DIFFERENT scenes of one chunk stay apart."""
+    sizes = [6, 6, 5, 7, 8]
+    sse, x, pos, _ = batch_of(sizes, 3)
+    nan = float('nan')
+    labs = torch.tensor([1, 1, 0.0, -0.0, 2.5, 2.5,
+                         1, 1, 2.5, nan, nan, -3,
+                         -3, -3, 0, 1, 1e-30,
+                         1e-30, 7, 7, 7, 7, 7, 7,
+                         5, 0, 5, 0, 5, -0.0, 5, nan], dtype=torch.float32).view(-1, 1)
+    gat, gcn = modules()
+    from group_gan_gcn_gat_b200.schedule import get_schedule
+    from group_gan_gcn_gat_b200 import ops
+    sched = get_schedule(sse.to(DEV), torch.device(DEV))
+    leader, gsize, _gid, _ng = ops.group_ids(labs.to(DEV), sched.ped_start, sched.ped_end, sched.scene_start)
+    assert gsize.tolist() == [2, 2, 1, 1, 2, 2, 2, 2, 1, 1, 1, 1, 2, 2, 1, 1, 1, 1, 6, 6, 6, 6, 6, 6, 4, 1, 4, 1, 4, 1, 4, 1]
+    args = (x.to(DEV), sse.to(DEV), pos.to(DEV), labs.to(DEV))
+    for name, mod in (('gat', gat.to(DEV)), ('gcn', gcn.to(DEV))):
+        with torch.no_grad():
+            out_labels = mod(*args)
+        out_arrays = mod(args[0].clone().requires_grad_(True), *args[1:]).detach()
+        assert bool(torch.isfinite(out_labels).all())
+        assert torch.equal(out_labels, out_arrays), name
+
+
+@pytest.mark.parametrize('scale', [1e-6, 1e-3, 30.0, 1e3, 1e5])
+def test_tc_operand_scaling_extreme_magnitudes(scale):
+    """fp16 operand splits need the per-row power-of-two scaling outside [2^-2, 2^15): tiny and huge activations against an
+    fp64 evaluation of the reference (softmax saturation at large scales amplifies any rounding of the scores, so the bar
+    is the error of the fp32 reference itself, with a floor at the 1e-5 contract)."""
+    sizes = [3, 32, 7, 1, 19, 12, 28, 4]
+    sse, x, pos, labs = batch_of(sizes, 9, label_hi=4)
+    x = x * scale
+    gat, gcn = modules()
+    d = lambda sd: {k: v.double() for k, v in sd.items()}
+    ref_gat64 = O.gat_encoder(x.double(), sse, pos.double(), labs.double(), d(gat.state_dict()), '', 0.2, 1)
+    ref_gcn64 = O.gcn_module(x.double(), sse, pos.double(), labs.double(), d(gcn.state_dict()), '')
+    ref_gat32 = O.gat_encoder(x, sse, pos, labs, gat.state_dict(), '', 0.2, 1)
+    ref_gcn32 = O.gcn_module(x, sse, pos, labs, gcn.state_dict(), '')
+    args = (x.to(DEV), sse.to(DEV), pos.to(DEV), labs.to(DEV))
+    for name, mod, r64, r32 in (('gat', gat.to(DEV), ref_gat64, ref_gat32), ('gcn', gcn.to(DEV), ref_gcn64, ref_gcn32)):
+        with torch.no_grad():
+            out = mod(*args)
+        assert bool(torch.isfinite(out).all())
+        ref_err = ((r32.double() - r64).abs().max() / r64.abs().max()).item()
+        close(out, r64, max(1e-5, 4 * ref_err), '%s at scale %g (fp32 reference itself: %.2e)' % (name, scale, ref_err))
+
+
+def test_tc_nan_and_inf_rows_stay_local():
+    """a NaN / inf input row poisons its own scene only (rows of other scenes share the MMA tile but not the result)"""
+    sizes = [4, 5, 3, 6]
+    sse, x, pos, labs = batch_of(sizes, 11)
+    x[5, 3] = float('nan')          # scene 1
+    x[13, 0] = float('inf')         # scene 3
+    gat, gcn = modules()
+    args = (x.to(DEV), sse.to(DEV), pos.to(DEV), labs.to(DEV))
+    clean = [0, 1, 2, 3, 9, 10, 11]
+    xc = x.clone()
+    xc[5, 3] = 0.0
+    xc[13, 0] = 0.0
+    for name, mod in (('gat', gat.to(DEV)), ('gcn', gcn.to(DEV))):
+        with torch.no_grad():
+            out = mod(*args)
+            ref = mod(xc.to(DEV), *args[1:])
+        assert bool(torch.isfinite(out[clean]).all()), name
+        # (not bit-equal: a non-finite row maximum sends its WARP through the scaled operand path, whose fp16 split of
+        # the other rows rounds differently in the last bits)
+        close(out[clean], ref[clean], 2e-6, name)
+        assert not bool(torch.isfinite(out[4:9]).all()), name          # the reference propagates the NaN through the scene

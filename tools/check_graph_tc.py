@@ -33,7 +33,11 @@ def main():
     enc = M.GATEncoder(n_units=[40, 72, 16], n_heads=1, dropout=0, alpha=0.2)
     enc.load_state_dict(sd, strict=True)
     enc = enc.to(dev)
-    gcn = None   # filled in once the GCN tcgen05 kernel exists
+    gcn = M.GCNModule().to(dev)
+    with torch.no_grad():
+        for prm in gcn.parameters():
+            if prm.dim() == 2 and tuple(prm.shape) != (24, 32):
+                prm.mul_(0.15)
     sse = data['seq_start_end'].to(dev)
     batch = int(data['obs_traj'].shape[1])
     g = torch.Generator(device='cpu').manual_seed(1)
