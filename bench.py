@@ -272,6 +272,21 @@ def run_reference(args, rank):
     print(json.dumps(line))
 
 
+def nccl_evidence(path):
+    """what NCCL itself logged about the communicator of this rank: rank count, NVLS, transport"""
+    if not path:
+        return {'log': None, 'note': 'NCCL_DEBUG was set by the caller; its log is wherever the caller sent it'}
+    try:
+        text = open(path, errors='replace').read()
+    except OSError:
+        return {'log': os.path.relpath(path, ROOT), 'note': 'log not found'}
+    import re
+    nranks = sorted({int(m) for m in re.findall(r'nranks (\d+)', text)})
+    return {'log': os.path.relpath(path, ROOT), 'nranks': nranks[-1] if nranks else None,
+            'nvls': ('NVLS' in text), 'p2p_nvlink': ('via P2P' in text or 'NVL' in text),
+            'version': (re.findall(r'NCCL version ([0-9.+a-z]+)', text) or [None])[0]}
+
+
 def pool_kernel_name(code):
     return {0: 'pool_pair_kernel', 1: 'pool_tc_kernel', 2: 'pool_tc32_kernel'}[code]
 
@@ -297,6 +312,9 @@ def main():
     ap.add_argument('--scenes', type=int, default=1 << 16, help='scenes per GPU per step')
     ap.add_argument('--precision', default=os.environ.get('SGX_POOL_PRECISION', 'fp32'),
                     help="pooling precision: fp32 (default, contract mode) | fp32-simt | tc32 | bf16 (outside the ADE contract)")
+    ap.add_argument('--mode', default='infer', choices=['infer', 'train'],
+                    help="infer (default): the headline best-of-K generator forwards; train: SURVEY cfg 5, the adversarial "
+                         "D + G iteration data-parallel over scenes as its own JSON line")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-train', action='store_true', help='skip the cfg-5 training-step sub-measurement')
     ap.add_argument('--ref-scenes', type=int, default=256,
@@ -317,13 +335,27 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     numa = bind_to_gpu_numa(local_rank)
+    nccl_log = None
     if world > 1:
+        # NCCL's own account of the communicator (ranks, NVLS) goes to a file per rank -- never to stdout, which carries
+        # the JSON line; a caller's own NCCL_DEBUG settings are left alone
+        if 'NCCL_DEBUG' not in os.environ:
+            os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+            nccl_log = os.path.join(ROOT, 'gpurun_out', 'nccl_n%d_pid%d.log' % (world, os.getpid()))
+            os.environ['NCCL_DEBUG'] = 'INFO'
+            os.environ['NCCL_DEBUG_SUBSYS'] = 'INIT,GRAPH'
+            os.environ['NCCL_DEBUG_FILE'] = nccl_log
         dist.init_process_group('nccl', device_id=dev)
     torch.backends.cudnn.allow_tf32 = False
 
     from group_gan_gcn_gat_b200 import _lib, modules as M
     from group_gan_gcn_gat_b200.schedule import SceneSchedule
     L = _lib.lib()
+    if args.mode == 'train':
+        run_train_mode(args, dev, rank, world, local_rank, nccl_log, L)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     precision = args.precision
     pool_code = M.resolve_pool_precision(precision, 16, 32, 8)
     kernel = pool_kernel_name(pool_code)
@@ -522,6 +554,14 @@ def main():
             other_modes[alt] = time_call(lambda: gen.pool_net(h_enc, dev_in['seq_start_end'], end_pos), reps=5)
         gen.pool_net.precision = precision
 
+    hot_ops = None
+    if rank == 0:
+        try:
+            hot_ops = hot_path_op_numbers(dev, args.scenes, json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))).get(
+                'hbm_gbs', 6650.0) if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else 6650.0, flush)
+        except Exception as e:                               # the headline must not depend on the sub-measurement
+            hot_ops = [{'error': repr(e)[:200]}]
+
     small = None
     try:
         small = small_batch_numbers(gen, args.config, dev, rank, world)
@@ -564,13 +604,13 @@ def main():
         hbm = peaks.get('hbm_gbs', 6650.0)
         if cfg['wiring'] == 'gat':
             ctx_bytes = 260 * peds + 16 * n_scenes + 29920
-            ctx_entry = {'op': 'GATEncoder fwd (group_ids + gat_fused_mma_kernel)', 'bound': 'hbm', 'ms': ctx_ms,
+            ctx_entry = {'op': 'GATEncoder fwd (gat_fused_tc_kernel: tcgen05 linear maps, group structure in-kernel)', 'bound': 'hbm', 'ms': ctx_ms,
                          'algorithmic_bytes': ctx_bytes, 'achieved': ctx_bytes / (ctx_ms * 1e-3) / 1e9, 'peak': hbm,
                          'unit': 'GB/s', 'frac': ctx_bytes / (ctx_ms * 1e-3) / 1e9 / hbm,
                          'algorithmic_flops': 190 * n_pairs + 8400 * peds,
                          'achieved_tflops': (190 * n_pairs + 8400 * peds) / (ctx_ms * 1e-3) / 1e12,
                          'fp32_cuda_core_peak_tflops': cuda_core_peak,
-                         'note': 'HBM-bound by decree (SURVEY 8d: 260 B/ped); in practice issue / tensor-pipe bound, DESIGN.md 4.3'}
+                         'note': 'HBM-bound by decree (SURVEY 8d: 260 B/ped); in practice bound by per-warp instruction latency, DESIGN.md 4.3'}
         else:
             ctx_bytes = (40 + 24) * 4 * peds
             ctx_entry = {'op': 'cat + mlp_decoder_context 40->64->24 (mlp2_fused_kernel)', 'bound': 'hbm', 'ms': ctx_ms,
@@ -627,6 +667,10 @@ def main():
                  'ped_steps_per_s': pred_len * peds / (dec_ms * 1e-3)},
             ],
         }
+        if hot_ops is not None:
+            line['hot_path_ops'] = hot_ops
+        if world > 1:
+            line['nccl'] = nccl_evidence(nccl_log)
         if small is not None:
             line['small_batch'] = small
         if train is not None:
@@ -639,6 +683,70 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def hot_path_op_numbers(dev, n_scenes, hbm, flush):
+    """The other hot-path operators of north_star next to the pooling kernel, op-level (module call, CUDA events, L2
+    flushed), on zara1-shaped scenes of the bench size: GATEncoder / GCNModule forward (tcgen05 kernels) and
+    forward+backward (single-launch backward kernels), PoolHiddenNet backward (argmax-sparse).  Algorithmic bytes per
+    pedestrian: SURVEY 8d (260 B forward, 420 B backward for the graph operators)."""
+    from group_gan_gcn_gat_b200 import modules as M
+    data = synth_batch(n_scenes, 1237, 'sgan_gat')
+    sse = data['seq_start_end'].to(dev)
+    n = int(sse[-1, 1])
+    lab, pos = data['obs_traj_g'][-1].to(dev), data['obs_traj'][-1].to(dev)
+
+    def timed(fn, reps=7, warm=3):
+        ts = []
+        for i in range(reps + warm):
+            flush.fill_(i)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return statistics.median(ts[warm:])
+    rows = []
+    torch.manual_seed(0)
+    for name, mod, kern in (('GATEncoder', M.GATEncoder(None, 1, 0, 0.2), 'gat_fused_tc_kernel'),
+                            ('GCNModule', M.GCNModule(), 'gcn_fused_tc_kernel')):
+        mod = mod.to(dev)
+        with torch.no_grad():
+            for p in mod.parameters():
+                if name == 'GCNModule' and p.dim() == 2 and tuple(p.shape) != (24, 32):
+                    p.mul_(0.15)
+        x = torch.randn(n, 40, device=dev)
+        with torch.no_grad():
+            f_ms = timed(lambda: mod(x, sse, pos, lab))
+        xg = x.clone().requires_grad_(True)
+        up = torch.randn(n, 24, device=dev)
+
+        def fb():
+            mod.zero_grad(set_to_none=True)
+            xg.grad = None
+            (mod(xg, sse, pos, lab) * up).sum().backward()
+        fb_ms = timed(fb)
+        fwd_b, bwd_b = 260 * n + 16 * n_scenes, 420 * n
+        rows.append({'op': name + ' fwd (%s, group structure in-kernel)' % kern, 'bound': 'hbm', 'peds': n, 'ms': f_ms,
+                     'algorithmic_bytes': fwd_b, 'achieved': fwd_b / f_ms / 1e6, 'peak': hbm, 'unit': 'GB/s',
+                     'frac': fwd_b / f_ms / 1e6 / hbm})
+        rows.append({'op': name + ' fwd + bwd (autograd: forward, group_ids, single-launch backward, reduction)',
+                     'bound': 'hbm', 'peds': n, 'ms': fb_ms, 'algorithmic_bytes': fwd_b + bwd_b,
+                     'achieved': (fwd_b + bwd_b) / fb_ms / 1e6, 'peak': hbm, 'unit': 'GB/s',
+                     'frac': (fwd_b + bwd_b) / fb_ms / 1e6 / hbm})
+    # PoolHiddenNet backward: gradients flow through the argmax pair of every (pedestrian, channel) only
+    pool = M.PoolHiddenNet(embedding_dim=16, h_dim=32, mlp_dim=64, bottleneck_dim=8, batch_norm=False).to(dev)
+    h = torch.randn(n, 32, device=dev, requires_grad=True)
+    out = pool(h, sse, pos)
+    go = torch.randn_like(out)
+    params = [h] + list(pool.parameters())
+    b_ms = timed(lambda: torch.autograd.grad(out, params, go, retain_graph=True))
+    pool_bwd_b = n * (8 * 4 + 8 * 4 + 2 * 4 + 2 * 32 * 4)      # grad_out, argmax, position, h read + grad_h written
+    rows.append({'op': 'PoolHiddenNet bwd (sgx_pool_bwd, argmax-sparse: 8 pairs per pedestrian)', 'bound': 'hbm', 'peds': n,
+                 'ms': b_ms, 'algorithmic_bytes': pool_bwd_b, 'achieved': pool_bwd_b / b_ms / 1e6, 'peak': hbm,
+                 'unit': 'GB/s', 'frac': pool_bwd_b / b_ms / 1e6 / hbm})
+    return rows
 
 
 def small_batch_numbers(gen, config, dev, rank, world, scenes=64, reps=20):
@@ -679,6 +787,86 @@ def small_batch_numbers(gen, config, dev, rank, world, scenes=64, reps=20):
             'mode': 'K samples folded into one forward' if world == 1 else
                     '(sample, scene) pairs LPT-sharded over %d ranks + all-reduce of the [K,S] sums' % world,
             'ms': ms, 'traj_per_s': peds * K_SAMPLES / (ms * 1e-3), 'ade_sum': float(a), 'fde_sum': float(f)}
+
+
+def run_train_mode(args, dev, rank, world, local_rank, nccl_log, L):
+    """bench.py --mode train: SURVEY cfg 5 as the line's own metric.  One step = one adversarial iteration (discriminator
+    step + generator step with best_k = 20, Adam, gradient all-reduce over NCCL) on 64 zara1-train-shaped scenes per rank
+    (weak scaling).  value: batch resident in HBM; e2e: the batch copied from pinned host memory every step and the
+    losses read back."""
+    import torch.distributed as dist
+    from tools import train_step_dp as T
+    from group_gan_gcn_gat_b200 import parallel
+    targs, gen, disc, opt_g, opt_d, batch = T.setup(dev, rank, world)
+    host = tuple(t.cpu().pin_memory() for t in batch)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(it, b):
+        rng = parallel.make_label_rng(0, it)
+        torch.manual_seed(100 + it * world + rank)
+        parallel.discriminator_step(targs, b, gen, disc, opt_d, label_rng=rng, n_global=targs.n_global)
+        return parallel.generator_step(targs, b, gen, disc, opt_g, label_rng=rng, n_global=targs.n_global)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for it in range(args.warmup):
+        step(it, batch)
+    barrier()
+    launches0 = L.sgx_launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    wall0 = time.perf_counter()
+    for it, (a, b) in enumerate(ev):
+        a.record()
+        step(args.warmup + it, batch)
+        b.record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = L.sgx_launch_count() - launches0
+    if rank == 0:
+        sampler.window(wall0, wall0 + wall)
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    out_host = torch.empty(1).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    for it in range(args.steps):
+        b = tuple(h.to(dev, non_blocking=True) for h in host)
+        losses = step(args.warmup + args.steps + it, b)
+        out_host.copy_(torch.as_tensor(losses['G_total_loss'], device=dev).reshape(1), non_blocking=True)
+        torch.cuda.synchronize()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = t.tolist()
+    if rank == 0:
+        scenes = 64 * world
+        line = {'metric': 'training_scenes_per_sec', 'value': scenes * args.steps / (total_ms * 1e-3), 'unit': 'scenes/s',
+                'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps,
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
+                'config': {'workload': 'SURVEY cfg 5: adversarial step (D step + G step, best_k = 20, Adam) of SGAN-GAT G + '
+                                       'global pooled D, 64 zara1-train-shaped scenes per rank, gradient all-reduce',
+                           'scenes_per_gpu': 64, 'peds_global': int(targs.n_global), 'best_k': 20,
+                           'l2': 'working set (< 10 MB) is L2 resident by nature of the workload: one minibatch',
+                           'parallelism': 'scenes sharded by LPT on N^2, NCCL all-reduce of G and D gradients'},
+                'clocks': clocks,
+                'e2e': {'value': scenes * args.steps / (e2e_ms * 1e-3), 'unit': 'scenes/s',
+                        'h2d_bytes_per_step': int(sum(h.numel() * h.element_size() for h in host)), 'd2h_bytes_per_step': 4,
+                        'ms_per_step': e2e_ms / args.steps},
+                'gpu_launches': int(launches),
+                'roofline': {'kernel': 'launch-latency bound step (hundreds of launches of < 10 us on 800 pedestrians)',
+                             'bound': 'hbm', 'achieved': None, 'peak': None, 'unit': 'GB/s', 'frac': None, 'traffic': None},
+                'allreduce_bytes': {'G': sum(p.numel() for p in gen.parameters()) * 4,
+                                    'D': sum(p.numel() for p in disc.parameters()) * 4}}
+        if world > 1:
+            line['nccl'] = nccl_evidence(nccl_log)
+        print(json.dumps(line), flush=True)
 
 
 def train_step_numbers(dev, rank, world):

@@ -141,9 +141,12 @@ def get_schedule(seq_start_end, device):
         hit = _cache.get(id(seq_start_end))
         if hit is not None and hit[0]() is seq_start_end and hit[1] == key:
             return hit[2]
+        # drop the schedules of batches that no longer exist BEFORE building the new one: their device buffers go back to
+        # the caching allocator and are reused right away.  (Evicting only every 64 misses let the reserved memory of an
+        # evaluation loop grow by one schedule per minibatch, i.e. a cudaMalloc -- 10 .. 150 ms of host stall -- every
+        # few steps.)
+        _evict_dead()
         sched = SceneSchedule(seq_start_end, device)
-        if len(_cache) > 64:
-            _evict_dead()
         _cache[id(seq_start_end)] = (weakref.ref(seq_start_end), key, sched)
         return sched
     return SceneSchedule(seq_start_end, device)
