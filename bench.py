@@ -743,7 +743,7 @@ def hot_path_op_numbers(dev, n_scenes, hbm, flush):
     params = [h] + list(pool.parameters())
     b_ms = timed(lambda: torch.autograd.grad(out, params, go, retain_graph=True))
     pool_bwd_b = n * (8 * 4 + 8 * 4 + 2 * 4 + 2 * 32 * 4)      # grad_out, argmax, position, h read + grad_h written
-    rows.append({'op': 'PoolHiddenNet bwd (sgx_pool_bwd, argmax-sparse: 8 pairs per pedestrian)', 'bound': 'hbm', 'peds': n,
+    rows.append({'op': 'PoolHiddenNet bwd (sgx_pool_bwd_scenes: scene-owned event kernel + 3 tensor-core GEMMs over the [batch,512] hidden gradient; argmax-sparse, 8 pairs per pedestrian)', 'bound': 'hbm', 'peds': n,
                  'ms': b_ms, 'algorithmic_bytes': pool_bwd_b, 'achieved': pool_bwd_b / b_ms / 1e6, 'peak': hbm,
                  'unit': 'GB/s', 'frac': pool_bwd_b / b_ms / 1e6 / hbm})
     return rows

@@ -51,6 +51,8 @@ SIGNATURES = {
     'sgx_pool_bwd_ws_bytes': (_I64, [_I64, _I32, _I32, _I32]),
     'sgx_pool_bwd': (ctypes.c_int, [_P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _P, _P, _P,
                                     _P, _P, _P, _P, _P, _P, _I64, _P]),
+    'sgx_pool_bwd_scenes': (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _P, _P,
+                                           _P, _P, _P, _P, _P, _P, _P, _I64, _P]),
     'sgx_mlp2_supported': (ctypes.c_int, [_I32, _I32, _I32]),
     'sgx_mlp2_fwd': (ctypes.c_int, [_P, _I32, _P, _I32, _I64, _P, _P, _P, _P, _I32, _I32, _P, _P]),
     'sgx_gcn_module_ws_bytes': (_I64, [_I64, _I64, _I32, _I32, _I32, _I32]),

@@ -239,6 +239,156 @@ pool_bwd_event_kernel(const float* __restrict__ Cr /*[batch][512]*/, const float
         if (sdb2[e] != 0.f) atomicAdd(&db2[e], sdb2[e]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Backward events without global atomics (round 2).  pool_bwd_event_kernel above scatters every event's 512 hidden-unit
+// gradients into dC[j*] with atomicAdd: 10^9 L2 atomics per call at 245 k pedestrians, 3.0 ms of the 5.2 ms backward.
+// Here a CTA owns whole scenes -- block b = the scenes whose first pedestrian lies in [16 b, 16 b + 16) -- and thread k
+// owns hidden unit k: the block's rows of Cr are staged in shared memory once, the events of the block's pedestrians
+// (argmax pairs never leave a scene) accumulate into a shared dC tile that only thread k touches in column k, and the
+// tile is written once with plain stores.  dW2 / dAeff / dc0 live in registers for the whole kernel (dc0 = the column
+// sums of dC: no separate pass over the 500 MB matrix).  A block spanning more than PB_ROWS rows (a scene > 33) zeroes its
+// own rows and falls back to atomics.
+// ------------------------------------------------------------------------------------------------
+constexpr int PB_IB = 16;            // pedestrians whose scenes start in one block
+constexpr int PB_ROWS = 48;          // rows of a block held in shared memory (15 + largest scene <= 48)
+
+template <int B, bool DPOS>
+__global__ void __launch_bounds__(HID, 1)
+pool_bwd_block_kernel(const float* __restrict__ Cr /*[batch][512]*/, const float* __restrict__ pos,
+                      const float* __restrict__ out, const int32_t* __restrict__ argmax,
+                      const float* __restrict__ gout, const int32_t* __restrict__ ped_start,
+                      const int32_t* __restrict__ ped_end, int batch, const float2* __restrict__ Aeff,
+                      const float* __restrict__ W2, float* __restrict__ dC /*[batch][512]*/, float* __restrict__ dW2,
+                      float* __restrict__ db2, float* __restrict__ dAeff /*[512][2]*/, float* __restrict__ dc0,
+                      float* __restrict__ dpos) {
+    extern __shared__ __align__(16) float pb_smem[];
+    float* sCr = pb_smem;                                 // [PB_ROWS][512]
+    float* sdC = sCr + PB_ROWS * HID;                     // [PB_ROWS][512]
+    float2* spos = reinterpret_cast<float2*>(sdC + PB_ROWS * HID);   // [PB_ROWS]
+    float* sdpos = reinterpret_cast<float*>(spos + PB_ROWS);         // [PB_ROWS][2]
+    float* ev_g = sdpos + 2 * PB_ROWS;                    // [PB_ROWS * B]
+    int* ev_j = reinterpret_cast<int*>(ev_g + PB_ROWS * B);          // [PB_ROWS * B]  row of j* inside the block, -1: no gradient
+    float* s_db2 = reinterpret_cast<float*>(ev_j + PB_ROWS * B);     // [B]
+    const int k = threadIdx.x, lane = threadIdx.x & 31;
+    const float2 a = Aeff[k];
+    float w2[B], dw2[B];
+#pragma unroll
+    for (int b = 0; b < B; ++b) { w2[b] = W2[(int64_t)b * HID + k]; dw2[b] = 0.f; }
+    float dax = 0.f, day = 0.f, dc0k = 0.f;
+    if (k < B) s_db2[k] = 0.f;
+    const int n_blocks = (batch + PB_IB - 1) / PB_IB;
+    for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        // rows of this block: from the first scene start >= 16 blk to the first scene start >= 16 (blk + 1)
+        const int i0 = blk * PB_IB, i1 = i0 + PB_IB;
+        const int lo = (ped_start[i0] == i0) ? i0 : ped_end[i0];
+        const int hi = (i1 >= batch) ? batch : ((ped_start[i1] == i1) ? i1 : ped_end[i1]);
+        const int rows = hi - lo;
+        if (rows <= 0) continue;
+        if (rows > PB_ROWS) {
+            // ---- a scene too large for the tile: zero the block's rows, then the atomic scatter of the general kernel ----
+            for (int r = 0; r < rows; ++r) dC[(int64_t)(lo + r) * HID + k] = 0.f;
+            __syncthreads();
+            for (int i = lo; i < hi; ++i) {
+                const float2 pi = *reinterpret_cast<const float2*>(pos + 2 * (int64_t)i);
+#pragma unroll
+                for (int b = 0; b < B; ++b) {
+                    const float g = gout[(int64_t)i * B + b];
+                    if (!(out[(int64_t)i * B + b] > 0.f) || g == 0.f) continue;
+                    const int j = argmax[(int64_t)i * B + b];
+                    const float2 pj = *reinterpret_cast<const float2*>(pos + 2 * (int64_t)j);
+                    const float ddx = pj.x - pi.x, ddy = pj.y - pi.y;
+                    const float z = fmaf(a.x, ddx, fmaf(a.y, ddy, Cr[(int64_t)j * HID + k]));
+                    if (k == 0) atomicAdd(&s_db2[b], g);
+                    float dz = 0.f;
+                    if (z > 0.f) {
+                        dw2[b] = fmaf(g, z, dw2[b]);
+                        dz = g * w2[b];
+                        atomicAdd(&dC[(int64_t)j * HID + k], dz);
+                        dc0k += dz;
+                        dax = fmaf(dz, ddx, dax);
+                        day = fmaf(dz, ddy, day);
+                    }
+                    if (DPOS) {
+                        const float sx = warp_sum(dz * a.x), sy = warp_sum(dz * a.y);
+                        if (lane == 0 && (sx != 0.f || sy != 0.f)) {
+                            atomicAdd(&dpos[2 * j], sx); atomicAdd(&dpos[2 * j + 1], sy);
+                            atomicAdd(&dpos[2 * i], -sx); atomicAdd(&dpos[2 * i + 1], -sy);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            continue;
+        }
+        // ---- stage the block: Cr rows, positions, the event list; zero the dC tile ----
+        __syncthreads();                                  // the previous block's tile has been written out
+        for (int r = 0; r < rows; ++r) {
+            sCr[r * HID + k] = Cr[(int64_t)(lo + r) * HID + k];
+            sdC[r * HID + k] = 0.f;
+        }
+        if (k < rows) {
+            spos[k] = *reinterpret_cast<const float2*>(pos + 2 * (int64_t)(lo + k));
+            if (DPOS) { sdpos[2 * k] = 0.f; sdpos[2 * k + 1] = 0.f; }
+        }
+        for (int idx = k; idx < rows * B; idx += HID) {
+            const int64_t src = (int64_t)lo * B + idx;    // rows are contiguous: [lo*B, hi*B)
+            const float g = gout[src];
+            const bool act = (out[src] > 0.f) && (g != 0.f);
+            ev_g[idx] = g;
+            ev_j[idx] = act ? (argmax[src] - lo) : -1;
+            if (act) atomicAdd(&s_db2[idx % B], g);
+        }
+        __syncthreads();
+        // ---- events: channel b outermost so that the per-channel registers are indexed statically.  (Loading four rows'
+        //      metadata and Cr values up front did not help, 1.68 -> 1.86 ms: the loop is issue bound -- 16 warps x ~20
+        //      instructions per event -- not latency bound.) ----
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            for (int r = 0; r < rows; ++r) {
+                const int jr = ev_j[r * B + b];
+                if (jr < 0) continue;
+                const float g = ev_g[r * B + b];
+                const float2 pi = spos[r], pj = spos[jr];
+                const float ddx = pj.x - pi.x, ddy = pj.y - pi.y;
+                const float z = fmaf(a.x, ddx, fmaf(a.y, ddy, sCr[jr * HID + k]));
+                float dz = 0.f;
+                if (z > 0.f) {
+                    dw2[b] = fmaf(g, z, dw2[b]);
+                    dz = g * w2[b];
+                    sdC[jr * HID + k] += dz;
+                    dax = fmaf(dz, ddx, dax);
+                    day = fmaf(dz, ddy, day);
+                }
+                if (DPOS) {
+                    const float sx = warp_sum(dz * a.x), sy = warp_sum(dz * a.y);
+                    if (lane == 0 && (sx != 0.f || sy != 0.f)) {
+                        atomicAdd(&sdpos[2 * jr], sx); atomicAdd(&sdpos[2 * jr + 1], sy);
+                        atomicAdd(&sdpos[2 * r], -sx); atomicAdd(&sdpos[2 * r + 1], -sy);
+                    }
+                }
+            }
+        }
+        // ---- the tile, once ----
+        for (int r = 0; r < rows; ++r) {
+            const float v = sdC[r * HID + k];
+            dC[(int64_t)(lo + r) * HID + k] = v;
+            dc0k += v;
+        }
+        if (DPOS) {
+            __syncthreads();
+            if (k < 2 * rows) dpos[2 * (int64_t)lo + k] = sdpos[k];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < B; ++b)
+        if (dw2[b] != 0.f) atomicAdd(&dW2[(int64_t)b * HID + k], dw2[b]);
+    if (dax != 0.f) atomicAdd(&dAeff[2 * k], dax);
+    if (day != 0.f) atomicAdd(&dAeff[2 * k + 1], day);
+    if (dc0k != 0.f) atomicAdd(&dc0[k], dc0k);
+    if (k < B && s_db2[k] != 0.f) atomicAdd(&db2[k], s_db2[k]);
+}
+
 // dc0[k] = sum_p dC[p][k]
 __global__ void colsum512_kernel(const float* __restrict__ dC, int batch, float* __restrict__ dc0) {
     int k = threadIdx.x + (blockIdx.x % 2) * 256;
@@ -431,19 +581,19 @@ extern "C" int64_t sgx_pool_bwd_ws_bytes(int64_t batch, int32_t E, int32_t H, in
     return 2 * align_up(batch * HID * 4, 256) + 2 * align_up(HID * 8, 256) + 2 * align_up(HID * 4, 256);
 }
 
-extern "C" int sgx_pool_bwd(const float* h, const float* pos, const float* out, const int32_t* argmax,
-                            const float* grad_out, int64_t batch, const float* We, const float* be, const float* W1,
-                            const float* b1, const float* W2, const float* b2, int32_t E, int32_t H, int32_t B,
-                            float* grad_h, float* grad_pos, float* grad_We, float* grad_be, float* grad_W1,
-                            float* grad_b1, float* grad_W2, float* grad_b2, void* workspace, int64_t ws_bytes,
-                            void* stream) {
-    (void)b2;
-    SGX_REQUIRE(h && pos && out && argmax && grad_out && We && be && W1 && b1 && W2 && grad_h && grad_pos && grad_We &&
+static int pool_bwd_impl(const float* h, const float* pos, const float* out, const int32_t* argmax,
+                         const float* grad_out, const int32_t* ped_start, const int32_t* ped_end, int64_t batch,
+                         const float* We, const float* be, const float* W1, const float* b1, const float* W2, int32_t E,
+                         int32_t H, int32_t B, float* grad_h, float* grad_pos, float* grad_We, float* grad_be,
+                         float* grad_W1, float* grad_b1, float* grad_W2, float* grad_b2, void* workspace, int64_t ws_bytes,
+                         void* stream) {
+    SGX_REQUIRE(h && pos && out && argmax && grad_out && We && be && W1 && b1 && W2 && grad_h && grad_We &&
                     grad_be && grad_W1 && grad_b1 && grad_W2 && grad_b2 && workspace,
                 "sgx_pool_bwd: null pointer");
     int rc = check_dims(E, H, B);
     if (rc) return rc;
     SGX_REQUIRE(ws_bytes >= sgx_pool_bwd_ws_bytes(batch, E, H, B), "sgx_pool_bwd: workspace too small");
+    SGX_REQUIRE(batch > 0 && batch < ((int64_t)1 << 31), "sgx_pool_bwd: bad batch");
     cudaStream_t st = (cudaStream_t)stream;
     Carver ws(workspace);
     float* Cr = ws.take<float>(batch * HID);
@@ -452,27 +602,46 @@ extern "C" int sgx_pool_bwd(const float* h, const float* pos, const float* out, 
     float* dAeff = ws.take<float>(2 * HID);
     float* c0 = ws.take<float>(HID);
     float* dc0 = ws.take<float>(HID);
-    SGX_CUDA(cudaMemsetAsync(dC, 0, (size_t)batch * HID * 4, st));
+    // the scene-owned kernel (no global atomics) needs the scene bounds and has instances for the shipped bottlenecks
+    const bool blocks = ped_start && ped_end && (B == 8 || B == 48);
+    if (!blocks) SGX_CUDA(cudaMemsetAsync(dC, 0, (size_t)batch * HID * 4, st));
     SGX_CUDA(cudaMemsetAsync(dAeff, 0, 2 * HID * 4, st));
     SGX_CUDA(cudaMemsetAsync(dc0, 0, HID * 4, st));
     SGX_CUDA(cudaMemsetAsync(grad_W2, 0, (size_t)B * HID * 4, st));
     SGX_CUDA(cudaMemsetAsync(grad_b2, 0, (size_t)B * 4, st));
-    SGX_CUDA(cudaMemsetAsync(grad_pos, 0, (size_t)batch * 2 * 4, st));
+    if (grad_pos) SGX_CUDA(cudaMemsetAsync(grad_pos, 0, (size_t)batch * 2 * 4, st));
     pool_prep_kernel<<<2, 256, 0, st>>>(We, be, W1, b1, E, H, Aeff, c0);
     SGX_LAUNCH_CHECK();
     // Cr[p][k] = c0[k] + sum_h h[p][h] W1[k][E+h]   (row-major: a warp reads one ped's 512 values coalesced)
     rc = gemm(h, H, 1, W1 + E, 1, E + H, Cr, HID, batch, HID, H, 0, 0, st, nullptr, c0);
     if (rc) return rc;
-    const size_t smem = ((size_t)B * HID + 2 * HID + B) * sizeof(float);
-    SGX_UNSUPPORTED(smem > 200 * 1024, "sgx_pool_bwd: bottleneck_dim=%d too large for the backward kernel (max 96)", B);
-    SGX_CUDA(cudaFuncSetAttribute(pool_bwd_event_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = (int)std::min<int64_t>((batch + 7) / 8, 148 * 2);
-    pool_bwd_event_kernel<<<grid, 256, smem, st>>>(Cr, pos, out, argmax, grad_out, (int)batch, B, Aeff, W2, dC, grad_W2,
-                                                  grad_b2, dAeff, grad_pos);
-    SGX_LAUNCH_CHECK();
-    int nchunk = (int)std::min<int64_t>(batch, 128);
-    colsum512_kernel<<<2 * nchunk, 256, 0, st>>>(dC, (int)batch, dc0);
-    SGX_LAUNCH_CHECK();
+    if (blocks) {
+        const size_t smem = ((size_t)2 * PB_ROWS * HID + 4 * PB_ROWS + 2 * (size_t)PB_ROWS * B + B) * sizeof(float);
+        const int grid = (int)std::min<int64_t>((batch + PB_IB - 1) / PB_IB, 148);
+#define SGX_PB_LAUNCH(BB, DP)                                                                                              \
+    do {                                                                                                                   \
+        SGX_CUDA(cudaFuncSetAttribute(pool_bwd_block_kernel<BB, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        pool_bwd_block_kernel<BB, DP><<<grid, HID, smem, st>>>(Cr, pos, out, argmax, grad_out, ped_start, ped_end,          \
+                                                               (int)batch, Aeff, W2, dC, grad_W2, grad_b2, dAeff, dc0,      \
+                                                               grad_pos);                                                   \
+    } while (0)
+        if (B == 8) { if (grad_pos) SGX_PB_LAUNCH(8, true); else SGX_PB_LAUNCH(8, false); }
+        else { if (grad_pos) SGX_PB_LAUNCH(48, true); else SGX_PB_LAUNCH(48, false); }
+#undef SGX_PB_LAUNCH
+        SGX_LAUNCH_CHECK();
+    } else {
+        SGX_REQUIRE(grad_pos != nullptr, "sgx_pool_bwd: grad_pos is optional only with scene bounds and bottleneck 8 / 48");
+        const size_t smem = ((size_t)B * HID + 2 * HID + B) * sizeof(float);
+        SGX_UNSUPPORTED(smem > 200 * 1024, "sgx_pool_bwd: bottleneck_dim=%d too large for the backward kernel (max 96)", B);
+        SGX_CUDA(cudaFuncSetAttribute(pool_bwd_event_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int grid = (int)std::min<int64_t>((batch + 7) / 8, 148 * 2);
+        pool_bwd_event_kernel<<<grid, 256, smem, st>>>(Cr, pos, out, argmax, grad_out, (int)batch, B, Aeff, W2, dC, grad_W2,
+                                                      grad_b2, dAeff, grad_pos);
+        SGX_LAUNCH_CHECK();
+        int nchunk = (int)std::min<int64_t>(batch, 128);
+        colsum512_kernel<<<2 * nchunk, 256, 0, st>>>(dC, (int)batch, dc0);
+        SGX_LAUNCH_CHECK();
+    }
     // dW1[:, E:] = dC^T h     (K = batch: split-K inside gemm)
     rc = gemm(dC, 1, HID, h, H, 1, grad_W1 + E, E + H, HID, H, batch, 0, 0, st);
     if (rc) return rc;
@@ -483,4 +652,31 @@ extern "C" int sgx_pool_bwd(const float* h, const float* pos, const float* out, 
                                                                      grad_We, grad_be);
     SGX_LAUNCH_CHECK();
     return SGX_OK;
+}
+
+extern "C" int sgx_pool_bwd(const float* h, const float* pos, const float* out, const int32_t* argmax,
+                            const float* grad_out, int64_t batch, const float* We, const float* be, const float* W1,
+                            const float* b1, const float* W2, const float* b2, int32_t E, int32_t H, int32_t B,
+                            float* grad_h, float* grad_pos, float* grad_We, float* grad_be, float* grad_W1,
+                            float* grad_b1, float* grad_W2, float* grad_b2, void* workspace, int64_t ws_bytes,
+                            void* stream) {
+    (void)b2;
+    SGX_REQUIRE(grad_pos != nullptr, "sgx_pool_bwd: null pointer");
+    return pool_bwd_impl(h, pos, out, argmax, grad_out, nullptr, nullptr, batch, We, be, W1, b1, W2, E, H, B, grad_h, grad_pos,
+                         grad_We, grad_be, grad_W1, grad_b1, grad_W2, grad_b2, workspace, ws_bytes, stream);
+}
+
+// The same backward with the scene bounds of every pedestrian (ped_start / ped_end from sgx_schedule_fill): the events
+// are accumulated scene by scene in shared memory instead of with global atomics.  grad_pos may be null (positions that
+// need no gradient: the generator's pooling on observed positions) -- the per-event position reduction is then skipped.
+extern "C" int sgx_pool_bwd_scenes(const float* h, const float* pos, const float* out, const int32_t* argmax,
+                                   const float* grad_out, const int32_t* ped_start, const int32_t* ped_end, int64_t batch,
+                                   const float* We, const float* be, const float* W1, const float* b1, const float* W2,
+                                   const float* b2, int32_t E, int32_t H, int32_t B, float* grad_h, float* grad_pos,
+                                   float* grad_We, float* grad_be, float* grad_W1, float* grad_b1, float* grad_W2,
+                                   float* grad_b2, void* workspace, int64_t ws_bytes, void* stream) {
+    (void)b2;
+    SGX_REQUIRE(ped_start && ped_end, "sgx_pool_bwd_scenes: null pointer");
+    return pool_bwd_impl(h, pos, out, argmax, grad_out, ped_start, ped_end, batch, We, be, W1, b1, W2, E, H, B, grad_h,
+                         grad_pos, grad_We, grad_be, grad_W1, grad_b1, grad_W2, grad_b2, workspace, ws_bytes, stream);
 }

@@ -11,6 +11,14 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
     hi = __float_as_uint(v) & 0xFFFFE000u;
     lo = __float_as_uint(v - __uint_as_float(hi));
 }
+// round-to-nearest variant: hi and lo are both rounded (cvt.rna), so the residual error is unbiased and 4x smaller
+// (2^-22 per operand).  The truncating split above leaves a one-sided 2^-20 error that adds up linearly over very long
+// reductions (K = 10^4 .. 10^6 in the split-K parameter-gradient GEMMs).
+__device__ __forceinline__ void split_tf32_rn(float v, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
+    const float r = v - __uint_as_float(hi);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])

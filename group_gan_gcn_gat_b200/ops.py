@@ -169,40 +169,46 @@ def _(h, pos, ped_start, ped_end, pair_off, tile_first, n_pairs, We, be, W1, b1,
 
 
 @_custom_op('sgx::pool_bwd')
-def pool_bwd(h: Tensor, pos: Tensor, out: Tensor, argmax: Tensor, grad_out: Tensor, We: Tensor, be: Tensor,
-             W1: Tensor, b1: Tensor, W2: Tensor, b2: Tensor) -> List[Tensor]:
+def pool_bwd(h: Tensor, pos: Tensor, out: Tensor, argmax: Tensor, grad_out: Tensor, ped_start: Tensor, ped_end: Tensor,
+             We: Tensor, be: Tensor, W1: Tensor, b1: Tensor, W2: Tensor, b2: Tensor, need_pos: bool = True) -> List[Tensor]:
+    """sgx_pool_bwd_scenes.  need_pos = False skips the position gradient (returned as zeros of shape [0])."""
     h, pos, out, grad_out = _f32(h, 'h'), _f32(pos, 'pos'), _f32(out, 'out'), _f32(grad_out, 'grad_out')
     We, be, W1, b1, W2, b2 = (t.contiguous() for t in (We, be, W1, b1, W2, b2))
     batch, H = h.shape
     E, B = We.shape[0], W2.shape[0]
     dev = h.device
-    gh, gpos = torch.empty_like(h), torch.empty_like(pos)
+    gh = torch.empty_like(h)
+    gpos = torch.empty_like(pos) if need_pos else pos.new_empty(0)
     gWe, gbe, gW1, gb1, gW2, gb2 = (torch.empty_like(t) for t in (We, be, W1, b1, W2, b2))
     L = _lib.lib()
     ws = _ws(L.sgx_pool_bwd_ws_bytes(batch, E, H, B), dev)
     with torch.cuda.device(dev):
-        _lib.check(L.sgx_pool_bwd(_ptr(h), _ptr(pos), _ptr(out), _ptr(argmax.contiguous()), _ptr(grad_out), batch,
-                                  _ptr(We), _ptr(be), _ptr(W1), _ptr(b1), _ptr(W2), _ptr(b2), E, H, B, _ptr(gh),
-                                  _ptr(gpos), _ptr(gWe), _ptr(gbe), _ptr(gW1), _ptr(gb1), _ptr(gW2), _ptr(gb2),
-                                  _ptr(ws), ws.numel(), _stream(h)), 'sgx_pool_bwd')
+        _lib.check(L.sgx_pool_bwd_scenes(_ptr(h), _ptr(pos), _ptr(out), _ptr(argmax.contiguous()), _ptr(grad_out),
+                                         _ptr(ped_start), _ptr(ped_end), batch, _ptr(We), _ptr(be), _ptr(W1), _ptr(b1),
+                                         _ptr(W2), _ptr(b2), E, H, B, _ptr(gh), _ptr(gpos) if need_pos else 0, _ptr(gWe),
+                                         _ptr(gbe), _ptr(gW1), _ptr(gb1), _ptr(gW2), _ptr(gb2), _ptr(ws), ws.numel(),
+                                         _stream(h)), 'sgx_pool_bwd_scenes')
     return [gh, gpos, gWe, gbe, gW1, gb1, gW2, gb2]
 
 
 @pool_bwd.register_fake
-def _(h, pos, out, argmax, grad_out, We, be, W1, b1, W2, b2):
-    return [torch.empty_like(t) for t in (h, pos, We, be, W1, b1, W2, b2)]
+def _(h, pos, out, argmax, grad_out, ped_start, ped_end, We, be, W1, b1, W2, b2, need_pos=True):
+    return [torch.empty_like(h), torch.empty_like(pos) if need_pos else pos.new_empty(0)] + \
+        [torch.empty_like(t) for t in (We, be, W1, b1, W2, b2)]
 
 
 def _pool_setup(ctx, inputs, output):
-    h, pos, _ps, _pe, _po, _tf, _np, We, be, W1, b1, W2, b2, _prec, _prep = inputs
+    h, pos, ps, pe, _po, _tf, _np, We, be, W1, b1, W2, b2, _prec, _prep = inputs
     out, arg = output
-    ctx.save_for_backward(h, pos, out, arg, We, be, W1, b1, W2, b2)
+    ctx.save_for_backward(h, pos, out, arg, ps, pe, We, be, W1, b1, W2, b2)
 
 
 def _pool_backward(ctx, grad_out, _grad_arg):
-    h, pos, out, arg, We, be, W1, b1, W2, b2 = ctx.saved_tensors
-    gh, gpos, gWe, gbe, gW1, gb1, gW2, gb2 = pool_bwd(h, pos, out, arg, grad_out.contiguous(), We, be, W1, b1, W2, b2)
-    return gh, gpos, None, None, None, None, None, gWe, gbe, gW1, gb1, gW2, gb2, None, None
+    h, pos, out, arg, ps, pe, We, be, W1, b1, W2, b2 = ctx.saved_tensors
+    need_pos = bool(ctx.needs_input_grad[1])
+    gh, gpos, gWe, gbe, gW1, gb1, gW2, gb2 = pool_bwd(h, pos, out, arg, grad_out.contiguous(), ps, pe, We, be, W1, b1, W2,
+                                                      b2, need_pos)
+    return gh, (gpos if need_pos else None), None, None, None, None, None, gWe, gbe, gW1, gb1, gW2, gb2, None, None
 
 
 pool_fwd.register_autograd(_pool_backward, setup_context=_pool_setup)

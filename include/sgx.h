@@ -149,6 +149,16 @@ int sgx_pool_bwd(const float* h, const float* pos, const float* out, const int32
                  const float* W2, const float* b2, int32_t E, int32_t H, int32_t B, float* grad_h,
                  float* grad_pos, float* grad_We, float* grad_be, float* grad_W1, float* grad_b1,
                  float* grad_W2, float* grad_b2, void* workspace, int64_t ws_bytes, void* stream);
+/* The same backward given the scene bounds of every pedestrian (ped_start / ped_end, as for sgx_pool_fwd): the argmax
+ * pairs never leave a scene, so the hidden-layer gradients are accumulated scene by scene in shared memory and written
+ * once instead of scattered with global atomics (bottleneck 8 or 48; other dims take the path of sgx_pool_bwd).
+ * grad_pos may be NULL when the positions need no gradient (PoolHiddenNet on observed positions). */
+int sgx_pool_bwd_scenes(const float* h, const float* pos, const float* out, const int32_t* argmax,
+                        const float* grad_out, const int32_t* ped_start, const int32_t* ped_end, int64_t batch,
+                        const float* We, const float* be, const float* W1, const float* b1, const float* W2,
+                        const float* b2, int32_t E, int32_t H, int32_t B, float* grad_h, float* grad_pos,
+                        float* grad_We, float* grad_be, float* grad_W1, float* grad_b1, float* grad_W2,
+                        float* grad_b2, void* workspace, int64_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * make_mlp([in, mid, out], activation relu, batch_norm 0, dropout 0) forward (sgan/models.py:7-20) in one launch,

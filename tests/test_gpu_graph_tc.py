@@ -153,3 +153,58 @@ def test_tc_nan_and_inf_rows_stay_local():
         # the other rows rounds differently in the last bits)
         close(out[clean], ref[clean], 2e-6, name)
         assert not bool(torch.isfinite(out[4:9]).all()), name          # the reference propagates the NaN through the scene
+
+
+# ------------------------------------------------------------------ pooling backward: scene-owned kernel vs atomic kernel
+def _pool_bwd_both(sizes, dims, seed, need_pos):
+    """(new scene-owned path through the op, old atomic path through sgx_pool_bwd) on the same forward"""
+    import ctypes  # noqa: F401
+    import group_gan_gcn_gat_b200.modules as M
+    from group_gan_gcn_gat_b200 import _lib, ops
+    from group_gan_gcn_gat_b200.schedule import get_schedule
+    E, H, B = dims
+    torch.manual_seed(seed)
+    sse = sse_from_sizes(sizes).to(DEV)
+    n = sum(sizes)
+    pool = M.PoolHiddenNet(embedding_dim=E, h_dim=H, mlp_dim=64, bottleneck_dim=B, batch_norm=False).to(DEV)
+    h = torch.randn(n, H, device=DEV, requires_grad=True)
+    pos = (torch.rand(n, 2, device=DEV) * 10).requires_grad_(need_pos)
+    out = pool(h, sse, pos)
+    go = torch.randn_like(out)
+    params = list(pool.parameters())
+    new = torch.autograd.grad(out, [h] + ([pos] if need_pos else []) + params, go)
+    # the atomic kernel, straight through the C ABI
+    sched = get_schedule(sse, torch.device(DEV))
+    sd = {k: v.detach() for k, v in pool.named_parameters()}
+    We, be = sd['spatial_embedding.weight'], sd['spatial_embedding.bias']
+    W1, b1, W2, b2 = (sd['mlp_pre_pool.0.weight'], sd['mlp_pre_pool.0.bias'], sd['mlp_pre_pool.2.weight'],
+                      sd['mlp_pre_pool.2.bias'])
+    with torch.no_grad():
+        o2, arg = ops._DIRECT[ops.pool_fwd](h.detach(), pos.detach(), sched.ped_start, sched.ped_end, sched.pair_off,
+                                            sched.tile_first, sched.n_pairs, We, be, W1, b1, W2, b2,
+                                            M.resolve_pool_precision(pool.precision, E, H, B), None)
+    L = _lib.lib()
+    g = [torch.empty_like(t) for t in (h, pos, We, be, W1, b1, W2, b2)]
+    ws = torch.empty(L.sgx_pool_bwd_ws_bytes(n, E, H, B), dtype=torch.uint8, device=DEV)
+    p = lambda t: t.data_ptr()
+    _lib.check(L.sgx_pool_bwd(p(h.detach()), p(pos.detach()), p(o2), p(arg), p(go.contiguous()), n, p(We), p(be), p(W1), p(b1),
+                              p(W2), p(b2), E, H, B, *[p(t) for t in g], p(ws), ws.numel(),
+                              torch.cuda.current_stream().cuda_stream), 'sgx_pool_bwd')
+    torch.cuda.synchronize()
+    old = [g[0]] + ([g[1]] if need_pos else []) + [g[2], g[3], g[4], g[5], g[6], g[7]]
+    return new, old
+
+
+@pytest.mark.parametrize('sizes', [[1], [2, 3], [16] * 3, [33, 1, 15], [14, 2, 34, 3, 9], [1] * 40 + [33], [64, 5, 5], [7] * 30,
+                                   [48], [49, 1]])
+@pytest.mark.parametrize('dims', [(16, 32, 8), (16, 48, 48)])
+@pytest.mark.parametrize('need_pos', [False, True])
+def test_pool_backward_scene_kernel_matches_atomic_kernel(sizes, dims, need_pos):
+    """blocks of whole scenes (<= 48 rows in shared memory), blocks with no scene start, scenes too large for the tile
+    (atomic fall-back inside the kernel), generator and discriminator dims, with and without the position gradient"""
+    new, old = _pool_bwd_both(sizes, dims, sum(sizes) + dims[2], need_pos)
+    scale = max(float(t.abs().max()) for t in old)
+    for i, (a, b) in enumerate(zip(new, old)):
+        assert a.shape == b.shape
+        err = float((a - b).abs().max())
+        assert err <= 2e-5 * max(scale, 1e-6), 'gradient %d: %.3e vs scale %.3e' % (i, err, scale)
