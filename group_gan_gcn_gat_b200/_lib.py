@@ -58,7 +58,9 @@ SIGNATURES = {
     'sgx_gcn_module_ws_bytes': (_I64, [_I64, _I64, _I32, _I32, _I32, _I32]),
     'sgx_gcn_module_fwd': (ctypes.c_int, [_P] * 7 + [_I64, _I64] + [_P] * 6 + [_I32] * 4 + [_P, _P, _I64, _P]),
     'sgx_gcn_module_fused_fwd': (ctypes.c_int, [_P] * 7 + [_I64] + [_P] * 6 + [_I32] * 4 + [_P, _P]),
-    'sgx_gcn_module_fused_fwd_labels': (ctypes.c_int, [_P] * 6 + [_I64] + [_P] * 6 + [_I32] * 4 + [_P, _P]),
+    'sgx_gcn_module_fused_fwd_labels': (ctypes.c_int, [_P] * 6 + [_I64] + [_P] * 6 + [_I32] * 4 + [_P, _P, _P]),
+    'sgx_gcn_module_tc_prep_bytes': (_I64, [_I32] * 4),
+    'sgx_gcn_module_tc_prep': (ctypes.c_int, [_P] * 6 + [_I32] * 4 + [_P, _P]),
     'sgx_gcn_module_bwd': (ctypes.c_int, [_P] * 8 + [_I64, _I64] + [_P] * 6 + [_I32] * 4 + [_P] * 7 + [_P, _I64, _P]),
     'sgx_gcn_module_fused_bwd_ws_bytes': (_I64, []),
     'sgx_gcn_module_fused_bwd': (ctypes.c_int, [_P] * 8 + [_I64] + [_P] * 6 + [_I32] * 4 + [_P] * 7 + [_P, _I64, _P]),
@@ -66,7 +68,9 @@ SIGNATURES = {
     'sgx_gat_encoder_fwd': (ctypes.c_int, [_P] * 5 + [_I64, _I64] + [_P] * 10 + [_F32] + [_I32] * 5 +
                             [_P, _P, _I64, _P]),
     'sgx_gat_encoder_fused_fwd': (ctypes.c_int, [_P] * 7 + [_I64, _I32] + [_P] * 10 + [_F32] + [_I32] * 5 + [_P, _P]),
-    'sgx_gat_encoder_fused_fwd_labels': (ctypes.c_int, [_P] * 6 + [_I64] + [_P] * 10 + [_F32] + [_I32] * 5 + [_P, _P]),
+    'sgx_gat_encoder_fused_fwd_labels': (ctypes.c_int, [_P] * 6 + [_I64] + [_P] * 10 + [_F32] + [_I32] * 5 + [_P, _P, _P]),
+    'sgx_gat_encoder_tc_prep_bytes': (_I64, []),
+    'sgx_gat_encoder_tc_prep': (ctypes.c_int, [_P] * 10 + [_I32] * 5 + [_P, _P]),
     'sgx_gat_encoder_bwd': (ctypes.c_int, [_P] * 6 + [_I64, _I64] + [_P] * 10 + [_F32] + [_I32] * 5 + [_P] * 11 +
                             [_P, _I64, _P]),
     'sgx_gat_encoder_fwd_dense': (ctypes.c_int, [_P] * 6 + [_I64, _I64, _I32] + [_P] * 10 + [_F32] + [_I32] * 5 +

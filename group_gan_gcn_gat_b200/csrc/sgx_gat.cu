@@ -1249,7 +1249,8 @@ int gat_fused_tc_forward(const float* x, const int32_t* leader, const int32_t* g
                          const int32_t* scene_start, const int32_t* chunk_scene, int n_chunks, const float* Wi,
                          const float* ai, const float* Wio, const float* aio, const float* We, const float* ae,
                          const float* Weo, const float* aeo, const float* Wo, const float* bo, float alpha, float* out,
-                         cudaStream_t st);   // sgx_gat_tc.cu
+                         cudaStream_t st, const void* prep = nullptr, void* prep_out = nullptr);   // sgx_gat_tc.cu
+int64_t gat_tc_prep_bytes();
 
 static int gat_fused_forward(const float* x, const int32_t* leader, const int32_t* gsize, const int32_t* ps,
                              const int32_t* pe, const int32_t* scene_start, const int32_t* chunk_scene, int n_chunks,
@@ -1460,19 +1461,33 @@ extern "C" int sgx_gat_encoder_fused_fwd(const float* x, const int32_t* leader, 
 }
 
 // The same forward with the group structure derived inside the kernel from the datasets_group labels (no sgx_group_ids
-// pass, no leader / size arrays): scenes <= 32 pedestrians, tcgen05 kernel.
+// pass, no leader / size arrays): scenes <= 32 pedestrians, tcgen05 kernel.  prep (nullable): the weight images of
+// sgx_gat_encoder_tc_prep for THESE weights; without it the kernel builds them itself (~8 us per launch).
 extern "C" int sgx_gat_encoder_fused_fwd_labels(const float* x, const float* labels, const int32_t* ped_start,
                                                 const int32_t* ped_end, const int32_t* scene_start,
                                                 const int32_t* chunk_scene, int64_t n_chunks, const float* Wi,
                                                 const float* ai, const float* Wio, const float* aio, const float* We,
                                                 const float* ae, const float* Weo, const float* aeo, const float* Wo,
                                                 const float* bo, float alpha, int32_t n_heads, int32_t IN, int32_t HID_,
-                                                int32_t OUT_, int32_t FIN, float* out, void* stream) {
+                                                int32_t OUT_, int32_t FIN, const void* prep, float* out, void* stream) {
     SGX_REQUIRE(x && labels && ped_start && ped_end && scene_start && chunk_scene && Wi && ai && Wio && aio && We && ae &&
                     Weo && aeo && Wo && bo && out, "sgx_gat_encoder_fused_fwd_labels: null pointer");
     SGX_REQUIRE(n_chunks > 0 && n_chunks < ((int64_t)1 << 31), "sgx_gat_encoder_fused_fwd_labels: bad chunk count");
     SGX_UNSUPPORTED(n_heads != 1 || IN != 40 || HID_ != HID || OUT_ != OUT || FIN != 24,
                     "fused GAT encoder is built for n_heads=1, dims 40/72/16/24 (the shipped configuration)");
     return gat_fused_tc_forward(x, nullptr, nullptr, labels, ped_start, ped_end, scene_start, chunk_scene, (int)n_chunks, Wi,
-                                ai, Wio, aio, We, ae, Weo, aeo, Wo, bo, alpha, out, (cudaStream_t)stream);
+                                ai, Wio, aio, We, ae, Weo, aeo, Wo, bo, alpha, out, (cudaStream_t)stream, prep, nullptr);
+}
+
+extern "C" int64_t sgx_gat_encoder_tc_prep_bytes(void) { return gat_tc_prep_bytes(); }
+
+extern "C" int sgx_gat_encoder_tc_prep(const float* Wi, const float* ai, const float* Wio, const float* aio, const float* We,
+                                       const float* ae, const float* Weo, const float* aeo, const float* Wo, const float* bo,
+                                       int32_t n_heads, int32_t IN, int32_t HID_, int32_t OUT_, int32_t FIN, void* prep,
+                                       void* stream) {
+    SGX_REQUIRE(Wi && ai && Wio && aio && We && ae && Weo && aeo && Wo && bo && prep, "sgx_gat_encoder_tc_prep: null pointer");
+    SGX_UNSUPPORTED(n_heads != 1 || IN != 40 || HID_ != HID || OUT_ != OUT || FIN != 24,
+                    "fused GAT encoder is built for n_heads=1, dims 40/72/16/24 (the shipped configuration)");
+    return gat_fused_tc_forward(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, Wi, ai, Wio, aio, We,
+                                ae, Weo, aeo, Wo, bo, 0.f, nullptr, (cudaStream_t)stream, nullptr, prep);
 }

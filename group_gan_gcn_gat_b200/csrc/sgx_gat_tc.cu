@@ -65,6 +65,7 @@ constexpr int STAGE_FLOATS = N1 * K1 + N2 * K2 + N3 * K3 + N4 * K4 + N5 * K5;
 static_assert(OFF_GRP % 128 == 0 && GRP_BYTES % 128 == 0, "operand buffers must stay 128-byte aligned");
 static_assert(STAGE_FLOATS * 4 <= GROUPS * GRP_BYTES, "the fp32 staging of the weight prep lives in the group buffers");
 static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory");
+static_assert(OFF_BAR % 16 == 0, "the prepared blob is copied in 16-byte words");
 
 // attention of one node over the lanes set in `mask`; neighbour rows in the core layout (quad f of lane q at
 // f * CORE + q * 16 from `wrows`, the first row of this warp), scores (s, t) per lane in `st`.  Same term order as
@@ -150,7 +151,8 @@ gat_fused_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ lea
                     const float* __restrict__ Wi, const float* __restrict__ ai, const float* __restrict__ Wio,
                     const float* __restrict__ aio, const float* __restrict__ We, const float* __restrict__ ae,
                     const float* __restrict__ Weo, const float* __restrict__ aeo, const float* __restrict__ Wo,
-                    const float* __restrict__ bo, float alpha, float* __restrict__ out) {
+                    const float* __restrict__ bo, float alpha, float* __restrict__ out,
+                    const uint8_t* __restrict__ prep, uint8_t* __restrict__ prep_out) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
     uint8_t* smem = smem_raw + (sbase - smem_u32(smem_raw));
@@ -191,8 +193,14 @@ gat_fused_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ lea
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    // ---------------- weight prep: fp32 staging [n][k] (in the group buffers), per-matrix scale, hi/lo images ----------------
-    {
+    // ---------------- weight images: copied from a prepared blob (sgx_gat_encoder_tc_prep, cached per weight version by
+    // the host side), or built here: fp32 staging [n][k] (in the group buffers), per-matrix scale, hi/lo split ----------------
+    if (prep != nullptr) {
+        for (int e = threadIdx.x; e < OFF_BAR / 16; e += NTHREADS)
+            reinterpret_cast<uint4*>(smem)[e] = reinterpret_cast<const uint4*>(prep)[e];
+        fence_proxy_async();
+        __syncthreads();
+    } else {
         float* stage = reinterpret_cast<float*>(smem + OFF_GRP);
         constexpr int S1 = 0, S2 = S1 + N1 * K1, S3 = S2 + N2 * K2, S4 = S3 + N3 * K3, S5 = S4 + N4 * K4;
         for (int e = threadIdx.x; e < STAGE_FLOATS; e += NTHREADS) stage[e] = 0.f;
@@ -277,6 +285,10 @@ gat_fused_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ lea
         fence_proxy_async();
         __syncthreads();
     }
+
+    if (prep_out != nullptr)                                 // prep launch: hand the images out (no tiles: n_chunks = 0)
+        for (int e = threadIdx.x; e < OFF_BAR / 16; e += NTHREADS)
+            reinterpret_cast<uint4*>(prep_out)[e] = reinterpret_cast<const uint4*>(smem)[e];
 
     // ---------------- tile groups ----------------
     uint8_t* abuf = smem + OFF_GRP + grp * GRP_BYTES;        // A operand / fp32 rows of the group's tile
@@ -470,20 +482,24 @@ gat_fused_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ lea
 
 }  // namespace gtc
 
+int64_t gat_tc_prep_bytes() { return gtc::OFF_BAR; }
+
+// labels == nullptr: group structure from leader / gsize; prep (nullable): blob of gat_tc_prep; prep_out: build-only launch
 int gat_fused_tc_forward(const float* x, const int32_t* leader, const int32_t* gsize, const float* labels, const int32_t* ps, const int32_t* pe,
                          const int32_t* scene_start, const int32_t* chunk_scene, int n_chunks, const float* Wi,
                          const float* ai, const float* Wio, const float* aio, const float* We, const float* ae,
                          const float* Weo, const float* aeo, const float* Wo, const float* bo, float alpha, float* out,
-                         cudaStream_t st) {
+                         cudaStream_t st, const void* prep, void* prep_out) {
     auto kern = gtc::gat_fused_tc_kernel;
     SGX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gtc::SMEM_TOTAL));
     int dev = 0, sms = 148;
     SGX_CUDA(cudaGetDevice(&dev));
     SGX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int n_tiles = (n_chunks + 3) / 4;
-    const int grid = std::min((n_tiles + gtc::GROUPS - 1) / gtc::GROUPS, sms);
+    const int grid = std::max(1, std::min((n_tiles + gtc::GROUPS - 1) / gtc::GROUPS, sms));
     kern<<<grid, gtc::NTHREADS, gtc::SMEM_TOTAL, st>>>(x, leader, gsize, labels, ps, pe, scene_start, chunk_scene, n_chunks, Wi, ai,
-                                                       Wio, aio, We, ae, Weo, aeo, Wo, bo, alpha, out);
+                                                       Wio, aio, We, ae, Weo, aeo, Wo, bo, alpha, out,
+                                                       (const uint8_t*)prep, (uint8_t*)prep_out);
     SGX_LAUNCH_CHECK();
     return SGX_OK;
 }

@@ -827,7 +827,9 @@ template <int IN, int FIN>
 int gcn_fused_tc_forward(const float* x, const int32_t* leader, const int32_t* gsize, const float* labels, const int32_t* ps, const int32_t* pe,
                          const int32_t* scene_start, const int32_t* chunk_scene, int n_chunks, const float* W0,
                          const float* W1, const float* V0, const float* V1, const float* Wo, const float* bo, float* out,
-                         cudaStream_t st);   // sgx_gcn_tc.cu
+                         cudaStream_t st, const void* prep = nullptr, void* prep_out = nullptr);   // sgx_gcn_tc.cu
+template <int IN, int FIN>
+int64_t gcn_tc_prep_bytes();
 
 template <int IN, int FIN>
 static int gcn_fused_launch(const float* x, const int32_t* leader, const int32_t* gsize, const int32_t* ps,
@@ -987,19 +989,42 @@ extern "C" int sgx_gcn_module_fused_fwd(const float* x, const int32_t* leader, c
 }
 
 // The same forward with the group structure derived inside the kernel from the datasets_group labels (no sgx_group_ids
-// pass, no leader / size / n_group arrays): scenes <= 32 pedestrians, tcgen05 kernel.
+// pass, no leader / size / n_group arrays): scenes <= 32 pedestrians, tcgen05 kernel.  prep (nullable): the weight images
+// of sgx_gcn_module_tc_prep for THESE weights; without it the kernel builds them itself (~8 us per launch).
 extern "C" int sgx_gcn_module_fused_fwd_labels(const float* x, const float* labels, const int32_t* ped_start,
                                                const int32_t* ped_end, const int32_t* scene_start,
                                                const int32_t* chunk_scene, int64_t n_chunks, const float* W0,
                                                const float* W1, const float* V0, const float* V1, const float* Wo,
                                                const float* bo, int32_t IN, int32_t HID, int32_t OUT, int32_t FIN,
-                                               float* out, void* stream) {
+                                               const void* prep, float* out, void* stream) {
     SGX_REQUIRE(x && labels && ped_start && ped_end && scene_start && chunk_scene && W0 && W1 && V0 && V1 && Wo && bo && out,
                 "sgx_gcn_module_fused_fwd_labels: null pointer");
     SGX_REQUIRE(n_chunks > 0 && n_chunks < ((int64_t)1 << 31), "sgx_gcn_module_fused_fwd_labels: bad chunk count");
     cudaStream_t st = (cudaStream_t)stream;
     int rc = SGX_OK;
     GCN_DISPATCH((rc = sgx::gcn_fused_tc_forward<I, F>(x, nullptr, nullptr, labels, ped_start, ped_end, scene_start, chunk_scene,
-                                                       (int)n_chunks, W0, W1, V0, V1, Wo, bo, out, st)));
+                                                       (int)n_chunks, W0, W1, V0, V1, Wo, bo, out, st, prep, nullptr)));
+    return rc;
+}
+
+extern "C" int64_t sgx_gcn_module_tc_prep_bytes(int32_t IN, int32_t HID, int32_t OUT, int32_t FIN) {
+    int64_t n = -1;
+    if (HID == 72 && OUT == 16) {
+        if (IN == 40 && FIN == 24) n = sgx::gcn_tc_prep_bytes<40, 24>();
+        else if (IN == 32 && FIN == 24) n = sgx::gcn_tc_prep_bytes<32, 24>();
+        else if (IN == 40 && FIN == 32) n = sgx::gcn_tc_prep_bytes<40, 32>();
+        else if (IN == 32 && FIN == 32) n = sgx::gcn_tc_prep_bytes<32, 32>();
+    }
+    return n;
+}
+
+extern "C" int sgx_gcn_module_tc_prep(const float* W0, const float* W1, const float* V0, const float* V1, const float* Wo,
+                                      const float* bo, int32_t IN, int32_t HID, int32_t OUT, int32_t FIN, void* prep,
+                                      void* stream) {
+    SGX_REQUIRE(W0 && W1 && V0 && V1 && Wo && bo && prep, "sgx_gcn_module_tc_prep: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = SGX_OK;
+    GCN_DISPATCH((rc = sgx::gcn_fused_tc_forward<I, F>(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0,
+                                                       W0, W1, V0, V1, Wo, bo, nullptr, st, nullptr, prep)));
     return rc;
 }

@@ -51,6 +51,7 @@ struct Cfg {
                          STAGE_FLOATS = S5 + N5 * K5;
     static_assert(STAGE_FLOATS * 4 <= GROUPS * GRP_BYTES, "the fp32 staging of the weight prep lives in the group buffers");
     static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory");
+    static_assert(OFF_BAR % 16 == 0, "the prepared blob is copied in 16-byte words");
     static_assert(FIN <= 32 && FIN % 4 == 0 && IN % 4 == 0 && IN <= 48, "dims");
 };
 
@@ -113,7 +114,7 @@ gcn_fused_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ lea
                     const int32_t* __restrict__ scene_start, const int32_t* __restrict__ chunk_scene, int n_chunks,
                     const float* __restrict__ W0, const float* __restrict__ W1, const float* __restrict__ V0,
                     const float* __restrict__ V1, const float* __restrict__ Wo, const float* __restrict__ bo,
-                    float* __restrict__ out) {
+                    float* __restrict__ out, const uint8_t* __restrict__ prep, uint8_t* __restrict__ prep_out) {
     using C = Cfg<IN, FIN>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
@@ -155,8 +156,14 @@ gcn_fused_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ lea
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    // ---------------- weight prep: fp32 staging [n][k] (in the group buffers), per-matrix scale, hi/lo images ----------------
-    {
+    // ---------------- weight images: copied from a prepared blob (sgx_gcn_module_tc_prep, cached per weight version by
+    // the host side), or built here: fp32 staging [n][k] (in the group buffers), per-matrix scale, hi/lo split ----------------
+    if (prep != nullptr) {
+        for (int e = threadIdx.x; e < C::OFF_BAR / 16; e += NTHREADS)
+            reinterpret_cast<uint4*>(smem)[e] = reinterpret_cast<const uint4*>(prep)[e];
+        fence_proxy_async();
+        __syncthreads();
+    } else {
         float* stage = reinterpret_cast<float*>(smem + C::OFF_GRP);
         for (int e = threadIdx.x; e < C::STAGE_FLOATS; e += NTHREADS) stage[e] = 0.f;
         __syncthreads();
@@ -192,6 +199,10 @@ gcn_fused_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ lea
         fence_proxy_async();
         __syncthreads();
     }
+
+    if (prep_out != nullptr)                                 // prep launch: hand the images out (no tiles: n_chunks = 0)
+        for (int e = threadIdx.x; e < C::OFF_BAR / 16; e += NTHREADS)
+            reinterpret_cast<uint4*>(prep_out)[e] = reinterpret_cast<const uint4*>(smem)[e];
 
     // ---------------- tile groups ----------------
     uint8_t* abuf = smem + C::OFF_GRP + grp * GRP_BYTES;     // A operand / fp32 rows of the group's tile
@@ -376,10 +387,13 @@ gcn_fused_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ lea
 }  // namespace gctc
 
 template <int IN, int FIN>
+int64_t gcn_tc_prep_bytes() { return gctc::Cfg<IN, FIN>::OFF_BAR; }
+
+template <int IN, int FIN>
 int gcn_fused_tc_forward(const float* x, const int32_t* leader, const int32_t* gsize, const float* labels, const int32_t* ps, const int32_t* pe,
                          const int32_t* scene_start, const int32_t* chunk_scene, int n_chunks, const float* W0,
                          const float* W1, const float* V0, const float* V1, const float* Wo, const float* bo, float* out,
-                         cudaStream_t st) {
+                         cudaStream_t st, const void* prep, void* prep_out) {
     using C = gctc::Cfg<IN, FIN>;
     auto kern = gctc::gcn_fused_tc_kernel<IN, FIN>;
     SGX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_TOTAL));
@@ -387,17 +401,19 @@ int gcn_fused_tc_forward(const float* x, const int32_t* leader, const int32_t* g
     SGX_CUDA(cudaGetDevice(&dev));
     SGX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int n_tiles = (n_chunks + 3) / 4;
-    const int grid = std::min((n_tiles + gctc::GROUPS - 1) / gctc::GROUPS, sms);
+    const int grid = std::max(1, std::min((n_tiles + gctc::GROUPS - 1) / gctc::GROUPS, sms));
     kern<<<grid, gctc::NTHREADS, C::SMEM_TOTAL, st>>>(x, leader, gsize, labels, ps, pe, scene_start, chunk_scene, n_chunks, W0, W1,
-                                                      V0, V1, Wo, bo, out);
+                                                      V0, V1, Wo, bo, out, (const uint8_t*)prep, (uint8_t*)prep_out);
     SGX_LAUNCH_CHECK();
     return SGX_OK;
 }
 
 #define GCN_TC_INST(I, F)                                                                                                    \
-    template int gcn_fused_tc_forward<I, F>(const float*, const int32_t*, const int32_t*, const float*, const int32_t*, const int32_t*,   \
-                                            const int32_t*, const int32_t*, int, const float*, const float*, const float*,  \
-                                            const float*, const float*, const float*, float*, cudaStream_t);
+    template int64_t gcn_tc_prep_bytes<I, F>();                                                                              \
+    template int gcn_fused_tc_forward<I, F>(const float*, const int32_t*, const int32_t*, const float*, const int32_t*,     \
+                                            const int32_t*, const int32_t*, const int32_t*, int, const float*, const float*, \
+                                            const float*, const float*, const float*, const float*, float*, cudaStream_t,   \
+                                            const void*, void*);
 GCN_TC_INST(32, 24)
 GCN_TC_INST(32, 32)
 GCN_TC_INST(40, 24)

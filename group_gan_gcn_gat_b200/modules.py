@@ -207,9 +207,11 @@ class GATEncoder(nn.Module):
                 not _needs_grad(h_states, Wi, ai, Wio, aio, We, ae, Weo, aeo, self.out_embedding.weight, self.out_embedding.bias)):
             # inference: the tcgen05 kernel derives the group structure from the labels itself (no sgx_group_ids pass)
             chunk_scene, n_chunks = sched.chunks(32)
+            prep = ops.gat_tc_prep(Wi, ai, Wio, aio, We, ae, Weo, aeo, self.out_embedding.weight, self.out_embedding.bias,
+                                   cache=self.__dict__.setdefault('_tc_prep', {}))
             return ops.gat_encoder_fwd_labels(h_states, end_group, sched.ped_start, sched.ped_end, Wi, ai, Wio, aio, We, ae,
                                               Weo, aeo, self.out_embedding.weight, self.out_embedding.bias,
-                                              float(self.alpha), sched.scene_start, chunk_scene, n_chunks)
+                                              float(self.alpha), sched.scene_start, chunk_scene, n_chunks, prep)
         leader, gsize, _gid, _ng = _groups_for(sched, end_group)
         # single-launch kernel: warp chunks of <= 32 peds, or <= 64 (two slots per lane) when a scene exceeds 32
         cap = 32 if sched.max_n <= 32 else 64
@@ -273,8 +275,9 @@ class GCNModule(nn.Module):
         if (n_chunks > 0 and _lib.option('graph_tc') and ws[0].shape[1] == 72 and ws[1].shape[1] == 16 and
                 ws[0].shape[0] in (32, 40) and ws[4].shape[0] in (24, 32) and not _needs_grad(h_states, *ws)):
             # inference: the tcgen05 kernel derives the group structure from the labels itself (no sgx_group_ids pass)
+            prep = ops.gcn_tc_prep(*ws, cache=self.__dict__.setdefault('_tc_prep', {}))
             return ops.gcn_module_fwd_labels(h_states, end_group, sched.ped_start, sched.ped_end, sched.scene_start, *ws,
-                                             chunk_scene, n_chunks)
+                                             chunk_scene, n_chunks, prep)
         leader, gsize, _gid, ngrp = _groups_for(sched, end_group)
         return ops.call(ops.gcn_module_fwd, h_states, leader, gsize, sched.ped_start, sched.ped_end, sched.scene_start, ngrp,
                                   self.gcn_intra.W[0], self.gcn_intra.W[1], self.gcn_inter.W[0], self.gcn_inter.W[1],

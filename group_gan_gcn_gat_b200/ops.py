@@ -319,7 +319,48 @@ def _(x, leader, gsize, ped_start, ped_end, scene_start, n_group, W0, W1, V0, V1
     return x.new_empty(x.shape[0], Wo.shape[0])
 
 
-def gcn_module_fwd_labels(x, labels, ped_start, ped_end, scene_start, W0, W1, V0, V1, Wo, bo, chunk_scene, n_chunks):
+def _weights_key(ws):
+    return tuple((t.data_ptr(), t._version) for t in ws)
+
+
+def gcn_tc_prep(W0, W1, V0, V1, Wo, bo, cache=None):
+    """fp16 hi/lo weight images of the tcgen05 GCNModule kernel (sgx_gcn_module_tc_prep); `cache`: a dict owned by the
+    module, the blob is rebuilt only when a parameter was reassigned or updated in place (data_ptr / version counter)."""
+    ws = [_f32(t.detach(), 'gcn weight') for t in (W0, W1, V0, V1, Wo, bo)]
+    key = _weights_key(ws)
+    if cache is not None and cache.get('key') == key:
+        return cache['blob']
+    IN, HID, OUT, FIN = W0.shape[0], W0.shape[1], W1.shape[1], Wo.shape[0]
+    L = _lib.lib()
+    blob = torch.empty(L.sgx_gcn_module_tc_prep_bytes(IN, HID, OUT, FIN), dtype=torch.uint8, device=W0.device)
+    with torch.cuda.device(W0.device):
+        _lib.check(L.sgx_gcn_module_tc_prep(*[_ptr(t) for t in ws], IN, HID, OUT, FIN, _ptr(blob), _stream(W0)),
+                   'sgx_gcn_module_tc_prep')
+    if cache is not None:
+        cache['key'], cache['blob'] = key, blob
+    return blob
+
+
+def gat_tc_prep(Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo, cache=None):
+    """fp16 hi/lo weight images of the tcgen05 GATEncoder kernel (sgx_gat_encoder_tc_prep), cached like gcn_tc_prep."""
+    ws = [_f32(t.detach(), 'gat weight') for t in (Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo)]
+    key = _weights_key(ws)
+    if cache is not None and cache.get('key') == key:
+        return cache['blob']
+    nh, IN, HID = Wi.shape
+    OUT, FIN = Wio.shape[1], Wo.shape[0]
+    L = _lib.lib()
+    blob = torch.empty(L.sgx_gat_encoder_tc_prep_bytes(), dtype=torch.uint8, device=Wi.device)
+    with torch.cuda.device(Wi.device):
+        _lib.check(L.sgx_gat_encoder_tc_prep(*[_ptr(t) for t in ws], nh, IN, HID, OUT, FIN, _ptr(blob), _stream(Wi)),
+                   'sgx_gat_encoder_tc_prep')
+    if cache is not None:
+        cache['key'], cache['blob'] = key, blob
+    return blob
+
+
+def gcn_module_fwd_labels(x, labels, ped_start, ped_end, scene_start, W0, W1, V0, V1, Wo, bo, chunk_scene, n_chunks,
+                          prep=None):
     """Inference-only GCNModule forward with the group structure derived inside the tcgen05 kernel from the labels
     (sgx_gcn_module_fused_fwd_labels): scenes <= 32 pedestrians, built dims.  No autograd."""
     x = _f32(x, 'h_states')
@@ -334,7 +375,7 @@ def gcn_module_fwd_labels(x, labels, ped_start, ped_end, scene_start, W0, W1, V0
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib().sgx_gcn_module_fused_fwd_labels(
             _ptr(x), _ptr(labels), _ptr(ped_start), _ptr(ped_end), _ptr(scene_start), _ptr(chunk_scene), n_chunks, _ptr(W0),
-            _ptr(W1), _ptr(V0), _ptr(V1), _ptr(Wo), _ptr(bo), IN, HID, OUT, FIN, _ptr(out), _stream(x)),
+            _ptr(W1), _ptr(V0), _ptr(V1), _ptr(Wo), _ptr(bo), IN, HID, OUT, FIN, _ptr(prep), _ptr(out), _stream(x)),
             'sgx_gcn_module_fused_fwd_labels')
     return out
 
@@ -431,7 +472,7 @@ def _(x, leader, gsize, ped_start, ped_end, n_scenes, Wi, ai, Wio, aio, We, ae, 
 
 
 def gat_encoder_fwd_labels(x, labels, ped_start, ped_end, Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo, alpha, scene_start,
-                           chunk_scene, n_chunks):
+                           chunk_scene, n_chunks, prep=None):
     """Inference-only GATEncoder forward with the group structure derived inside the tcgen05 kernel from the labels
     (sgx_gat_encoder_fused_fwd_labels): scenes <= 32 pedestrians, n_heads 1, dims 40/72/16/24.  No autograd."""
     x = _f32(x, 'h_states')
@@ -447,7 +488,8 @@ def gat_encoder_fwd_labels(x, labels, ped_start, ped_end, Wi, ai, Wio, aio, We, 
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib().sgx_gat_encoder_fused_fwd_labels(
             _ptr(x), _ptr(labels), _ptr(ped_start), _ptr(ped_end), _ptr(scene_start), _ptr(chunk_scene), n_chunks,
-            *[_ptr(p) for p in ps], alpha, nh, IN, HID, OUT, FIN, _ptr(out), _stream(x)), 'sgx_gat_encoder_fused_fwd_labels')
+            *[_ptr(p) for p in ps], alpha, nh, IN, HID, OUT, FIN, _ptr(prep), _ptr(out), _stream(x)),
+            'sgx_gat_encoder_fused_fwd_labels')
     return out
 
 

@@ -192,12 +192,18 @@ int sgx_gcn_module_fused_fwd(const float* x, const int32_t* leader, const int32_
                              const float* V0, const float* V1, const float* Wo, const float* bo, int32_t IN,
                              int32_t HID, int32_t OUT, int32_t FIN, float* out, void* stream);
 /* ... with the group structure derived in the kernel from the datasets_group labels [batch] (what sgx_group_ids would
- * compute, sgan/models.py:654-680, bit for bit): no leader / size arrays, no extra pass.  tcgen05 kernel. */
+ * compute, sgan/models.py:654-680, bit for bit): no leader / size arrays, no extra pass.  tcgen05 kernel.
+ * prep: NULL, or the fp16 hi/lo weight images built by sgx_gcn_module_tc_prep for exactly these weights
+ * (sgx_gcn_module_tc_prep_bytes bytes, device memory; -1 for dims without a kernel instance) -- the host side caches it
+ * per weight version; without it every launch rebuilds the images (~8 us). */
 int sgx_gcn_module_fused_fwd_labels(const float* x, const float* labels, const int32_t* ped_start,
                                     const int32_t* ped_end, const int32_t* scene_start, const int32_t* chunk_scene,
                                     int64_t n_chunks, const float* W0, const float* W1, const float* V0,
                                     const float* V1, const float* Wo, const float* bo, int32_t IN, int32_t HID,
-                                    int32_t OUT, int32_t FIN, float* out, void* stream);
+                                    int32_t OUT, int32_t FIN, const void* prep, float* out, void* stream);
+int64_t sgx_gcn_module_tc_prep_bytes(int32_t IN, int32_t HID, int32_t OUT, int32_t FIN);
+int sgx_gcn_module_tc_prep(const float* W0, const float* W1, const float* V0, const float* V1, const float* Wo,
+                           const float* bo, int32_t IN, int32_t HID, int32_t OUT, int32_t FIN, void* prep, void* stream);
 int sgx_gcn_module_bwd(const float* x, const float* grad_out, const int32_t* leader, const int32_t* group_size,
                        const int32_t* ped_start, const int32_t* ped_end, const int32_t* scene_start,
                        const int32_t* n_group, int64_t batch, int64_t n_scenes, const float* W0, const float* W1,
@@ -246,13 +252,20 @@ int sgx_gat_encoder_fused_fwd(const float* x, const int32_t* leader, const int32
                               int32_t n_heads, int32_t IN, int32_t HID, int32_t OUT, int32_t FIN, float* out,
                               void* stream);
 /* ... with the group structure derived in the kernel from the datasets_group labels [batch] (what sgx_group_ids would
- * compute, sgan/models.py:263-267, bit for bit); scenes <= 32 pedestrians.  tcgen05 kernel. */
+ * compute, sgan/models.py:263-267, bit for bit); scenes <= 32 pedestrians.  tcgen05 kernel.
+ * prep: NULL, or the fp16 hi/lo weight images built by sgx_gat_encoder_tc_prep for exactly these weights
+ * (sgx_gat_encoder_tc_prep_bytes bytes, device memory) -- cached per weight version by the host side. */
 int sgx_gat_encoder_fused_fwd_labels(const float* x, const float* labels, const int32_t* ped_start,
                                      const int32_t* ped_end, const int32_t* scene_start, const int32_t* chunk_scene,
                                      int64_t n_chunks, const float* Wi, const float* ai, const float* Wio,
                                      const float* aio, const float* We, const float* ae, const float* Weo,
                                      const float* aeo, const float* Wo, const float* bo, float alpha, int32_t n_heads,
-                                     int32_t IN, int32_t HID, int32_t OUT, int32_t FIN, float* out, void* stream);
+                                     int32_t IN, int32_t HID, int32_t OUT, int32_t FIN, const void* prep, float* out,
+                                     void* stream);
+int64_t sgx_gat_encoder_tc_prep_bytes(void);
+int sgx_gat_encoder_tc_prep(const float* Wi, const float* ai, const float* Wio, const float* aio, const float* We,
+                            const float* ae, const float* Weo, const float* aeo, const float* Wo, const float* bo,
+                            int32_t n_heads, int32_t IN, int32_t HID, int32_t OUT, int32_t FIN, void* prep, void* stream);
 int sgx_gat_encoder_bwd(const float* x, const float* grad_out, const int32_t* leader, const int32_t* group_size,
                         const int32_t* ped_start, const int32_t* ped_end, int64_t batch, int64_t n_scenes,
                         const float* Wi, const float* ai, const float* Wio, const float* aio, const float* We,

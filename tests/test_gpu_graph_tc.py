@@ -208,3 +208,26 @@ def test_pool_backward_scene_kernel_matches_atomic_kernel(sizes, dims, need_pos)
         assert a.shape == b.shape
         err = float((a - b).abs().max())
         assert err <= 2e-5 * max(scale, 1e-6), 'gradient %d: %.3e vs scale %.3e' % (i, err, scale)
+
+
+def test_tc_weight_images_follow_parameter_updates():
+    """the cached fp16 weight images (sgx_*_tc_prep) are rebuilt after an in-place update (optimizer step, load_state_dict)
+    and after a parameter is reassigned"""
+    sizes = [5, 9, 2, 14]
+    sse, x, pos, labs = batch_of(sizes, 21)
+    gat, gcn = modules()
+    args = (x.to(DEV), sse.to(DEV), pos.to(DEV), labs.to(DEV))
+    for name, mod, oracle in (('gat', gat.to(DEV), lambda m: O.gat_encoder(x, sse, pos, labs, {k: v.cpu() for k, v in m.state_dict().items()}, '', 0.2, 1)),
+                              ('gcn', gcn.to(DEV), lambda m: O.gcn_module(x, sse, pos, labs, {k: v.cpu() for k, v in m.state_dict().items()}, ''))):
+        with torch.no_grad():
+            out0 = mod(*args).clone()
+            assert torch.equal(mod(*args), out0)                      # second call: cached images, same bits
+            close(out0, oracle(mod), 1e-5, name)
+            for p in mod.parameters():
+                p.mul_(0.9)                                           # in-place update (version counter)
+            out1 = mod(*args).clone()
+            close(out1, oracle(mod), 1e-5, name + ' after in-place update')
+            assert not torch.equal(out0, out1)
+            first = next(mod.parameters())
+            first.data = first.data * 1.1                             # reassigned storage (data_ptr)
+            close(mod(*args), oracle(mod), 1e-5, name + ' after reassignment')
