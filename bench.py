@@ -275,7 +275,8 @@ def run_reference(args, rank):
 def nccl_evidence(path):
     """what NCCL itself logged about the communicator of this rank: rank count, NVLS, transport"""
     if not path:
-        return {'log': None, 'note': 'NCCL_DEBUG was set by the caller; its log is wherever the caller sent it'}
+        return {'log': None, 'note': 'NCCL_DEBUG=%s was set by the caller; its log is wherever the caller sent it (%s)'
+                             % (os.environ.get('NCCL_DEBUG'), os.environ.get('NCCL_DEBUG_FILE', 'stdout'))}
     try:
         text = open(path, errors='replace').read()
     except OSError:
@@ -339,7 +340,7 @@ def main():
     if world > 1:
         # NCCL's own account of the communicator (ranks, NVLS) goes to a file per rank -- never to stdout, which carries
         # the JSON line; a caller's own NCCL_DEBUG settings are left alone
-        if 'NCCL_DEBUG' not in os.environ:
+        if os.environ.get('NCCL_DEBUG', '').upper() not in ('INFO', 'TRACE'):      # unset, or VERSION / WARN from the image
             os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
             nccl_log = os.path.join(ROOT, 'gpurun_out', 'nccl_n%d_pid%d.log' % (world, os.getpid()))
             os.environ['NCCL_DEBUG'] = 'INFO'
@@ -613,7 +614,7 @@ def main():
                          'note': 'HBM-bound by decree (SURVEY 8d: 260 B/ped); in practice bound by per-warp instruction latency, DESIGN.md 4.3'}
         else:
             ctx_bytes = (40 + 24) * 4 * peds
-            ctx_entry = {'op': 'cat + mlp_decoder_context 40->64->24 (mlp2_fused_kernel)', 'bound': 'hbm', 'ms': ctx_ms,
+            ctx_entry = {'op': 'cat + mlp_decoder_context 40->64->24 (mlp2_tc_kernel: both linear maps on tcgen05)', 'bound': 'hbm', 'ms': ctx_ms,
                          'algorithmic_bytes': ctx_bytes, 'achieved': ctx_bytes / (ctx_ms * 1e-3) / 1e9, 'peak': hbm,
                          'unit': 'GB/s', 'frac': ctx_bytes / (ctx_ms * 1e-3) / 1e9 / hbm}
         line = {
@@ -679,10 +680,15 @@ def main():
             v, dt, p = cpu_port_traj_per_sec(8192, K_SAMPLES, 1234 + 2, config=args.config)   # ~10-20 s of CPU work
             line['cpu_baseline'] = {'value': v, 'unit': 'traj/s', 'cores': os.cpu_count(), 'kind': 'port',
                                     'sample': '8192 scenes of the config\'s histogram (%d peds) x K=20 forwards, %.1f s' % (p, dt)}
-        sys.stdout.flush()
-        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if rank == 0:
+        # after the process group is gone and the other ranks had time to finish writing: a line > 4 KB is not written
+        # atomically to a pipe the ranks share
+        if world > 1:
+            time.sleep(0.5)
+        sys.stdout.flush()
+        print(json.dumps(line), flush=True)
 
 
 def hot_path_op_numbers(dev, n_scenes, hbm, flush):

@@ -113,6 +113,10 @@ static int launch_mlp2(const float* xa, int da, const float* xb, int db, int64_t
     return SGX_OK;
 }
 
+template <int IN, int OUTP>
+int mlp2_tc_forward(const float* xa, int da, const float* xb, int db, int64_t batch, const float* W1, const float* b1,
+                    const float* W2, const float* b2, int OUT, float* out, cudaStream_t st);   // sgx_mlp_tc.cu
+
 }  // namespace sgx
 
 using namespace sgx;
@@ -133,7 +137,9 @@ extern "C" int sgx_mlp2_fwd(const float* xa, int32_t da, const float* xb, int32_
                     IN, HID, OUT);
     cudaStream_t st = (cudaStream_t)stream;
 #define SGX_MLP_CASE(I, O, OP)                                                                                        \
-    if (IN == I && OUT == O) return launch_mlp2<I, 64, OP>(xa, da, xb, db, batch, W1, b1, W2, b2, OUT, out, st);
+    if (IN == I && OUT == O)                                                                                          \
+        return opt_graph_tc() ? mlp2_tc_forward<I, OP>(xa, da, xb, db, batch, W1, b1, W2, b2, OUT, out, st)           \
+                              : launch_mlp2<I, 64, OP>(xa, da, xb, db, batch, W1, b1, W2, b2, OUT, out, st);
     SGX_MLP_CASE(32, 24, 24) SGX_MLP_CASE(40, 24, 24) SGX_MLP_CASE(48, 24, 24)
     SGX_MLP_CASE(32, 32, 32) SGX_MLP_CASE(40, 32, 32) SGX_MLP_CASE(48, 32, 32)
     SGX_MLP_CASE(32, 1, 8) SGX_MLP_CASE(40, 1, 8) SGX_MLP_CASE(48, 1, 8)
