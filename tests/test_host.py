@@ -190,7 +190,9 @@ def test_schedule_build_matches_the_separate_passes():
     from group_gan_gcn_gat_b200 import _lib
     L = _lib.lib()
     rng = np.random.RandomState(3)
-    for sizes in ([1], [32, 1, 31, 2], list(rng.randint(1, 15, size=500)), [5, 33, 2], [64] * 3 + [1]):
+    # (>= 8192 scenes: the per-pedestrian pass runs on several host threads)
+    for sizes in ([1], [32, 1, 31, 2], list(rng.randint(1, 15, size=500)), [5, 33, 2], [64] * 3 + [1],
+                  list(rng.randint(1, 15, size=20001)), [1] * 8192, list(rng.randint(1, 40, size=9000))):
         st = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
         sse = np.ascontiguousarray(np.stack([st[:-1], st[1:]], 1))
         S, B = len(sizes), int(st[-1])
