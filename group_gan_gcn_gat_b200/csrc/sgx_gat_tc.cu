@@ -32,7 +32,10 @@ namespace sgx {
 namespace gtc {
 
 #ifndef GTC_GROUPS
-#define GTC_GROUPS 3
+#define GTC_GROUPS 3           // measured: 4 groups (GTC_HALVES, 128 registers, no spills) 98.3 us, 3 groups 96.3 us per call
+#endif
+#ifndef GTC_HALVES
+#define GTC_HALVES (GTC_GROUPS >= 4)
 #endif
 #ifndef GTC_FASTPATH
 #define GTC_FASTPATH 1
@@ -93,6 +96,95 @@ __device__ __forceinline__ void attend_core(const uint8_t* __restrict__ wrows, c
     const float inv = 1.f / den;
 #pragma unroll
     for (int f = 0; f < F; ++f) hp[f] *= inv;
+}
+
+// ---- the 72-wide attention layers in two feature blocks (GTC_HALVES): 72 accumulators per thread cap the kernel at 168
+// registers = three tile groups per SM; in blocks of 32 + 40 features (the exponentials are recomputed per block, the first
+// block's ELU outputs wait in 32 spare TMEM columns of the thread's own lane) the kernel fits 128 registers = FOUR groups.
+// Built to test whether a fourth group hides more latency: it does not (98.3 us against 96.3 us, bit-identical results),
+// so the kernel is not bound by the number of resident warps; kept as a compile-time variant (-DGTC_GROUPS=4). ----
+template <int Q0, int NQ>          // feature quads [Q0, Q0 + NQ) of the neighbour rows
+__device__ __forceinline__ void attend_block(const uint8_t* __restrict__ wrows, const float2* __restrict__ st, uint32_t mask,
+                                             float s_i, float m, float alpha, float (&hp)[4 * NQ]) {
+    float den = 0.f;
+#pragma unroll
+    for (int f = 0; f < 4 * NQ; ++f) hp[f] = 0.f;
+    for (uint32_t mm = mask; mm; mm &= mm - 1) {
+        const int q = __ffs(mm) - 1;
+        const float w = fexp(lrelu(s_i + st[q].y, alpha) - m);
+        den += w;
+        const uint8_t* row = wrows + q * 16 + Q0 * CORE;
+#pragma unroll
+        for (int f = 0; f < NQ; ++f) {
+            const float4 v = *reinterpret_cast<const float4*>(row + f * CORE);
+            hp[4 * f] = fmaf(w, v.x, hp[4 * f]); hp[4 * f + 1] = fmaf(w, v.y, hp[4 * f + 1]);
+            hp[4 * f + 2] = fmaf(w, v.z, hp[4 * f + 2]); hp[4 * f + 3] = fmaf(w, v.w, hp[4 * f + 3]);
+        }
+    }
+    const float inv = 1.f / den;
+#pragma unroll
+    for (int f = 0; f < 4 * NQ; ++f) hp[f] = felu(hp[f] * inv);
+}
+
+// hi / lo K cores [C0, C0 + N/8) of an operand with KC hi cores from N values
+template <int N, bool SCALED>
+__device__ __forceinline__ void write_core_block(uint8_t* __restrict__ arow, int c0, int kc_total, const float (&v)[N], float s) {
+#pragma unroll
+    for (int kc = 0; kc < N / 8; ++kc) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float a0 = v[kc * 8 + 2 * j], a1 = v[kc * 8 + 2 * j + 1];
+            if (SCALED) { a0 *= s; a1 *= s; }
+            const uint32_t h = pack_f16_rn(a0, a1);
+            float l0, l1;
+            sub_f16x2(h, a0, a1, l0, l1);
+            hi[j] = h;
+            lo[j] = pack_f16_rn(l0, l1);
+        }
+        *reinterpret_cast<uint4*>(arow + (c0 + kc) * CORE) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(arow + (kc_total + c0 + kc) * CORE) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+// attention + ELU of a 72-wide layer -> the K = 80 operand of the next linear map; returns the inverse row scale
+__device__ __forceinline__ float wide_attend_to_operand(const uint8_t* __restrict__ wrows, const float2* __restrict__ st,
+                                                        uint32_t mask, float s_i, float alpha, uint8_t* __restrict__ arow,
+                                                        uint32_t spare_tmem) {
+    float m = -INFINITY;
+    for (uint32_t mm = mask; mm; mm &= mm - 1) m = fmaxf(m, lrelu(s_i + st[__ffs(mm) - 1].y, alpha));
+    float mxb = 0.f;
+    {
+        float hb[32];                                        // features 40..71
+        attend_block<10, 8>(wrows, st, mask, s_i, m, alpha, hb);
+        uint32_t raw[32];
+#pragma unroll
+        for (int f = 0; f < 32; ++f) { mxb = fmaxf(mxb, fabsf(hb[f])); raw[f] = __float_as_uint(hb[f]); }
+        tmem_st32(spare_tmem, raw);
+    }
+    float ha[40];                                            // features 0..39
+    attend_block<0, 10>(wrows, st, mask, s_i, m, alpha, ha);
+    float mx = mxb;
+#pragma unroll
+    for (int f = 0; f < 40; ++f) mx = fmaxf(mx, fabsf(ha[f]));
+    tmem_wait_st();
+    __syncwarp();                                            // every lane is done reading the Wh rows
+    const bool unscaled = GTC_FASTPATH && __all_sync(0xffffffffu, scale_free(mx));
+    float s = 1.f, inv = 1.f;
+    if (!unscaled) pow2_scale(mx, s, inv);
+    if (unscaled) write_core_block<40, false>(arow, 0, 10, ha, 1.f); else write_core_block<40, true>(arow, 0, 10, ha, s);
+    {
+        uint32_t raw[32];
+        tmem_ld32(spare_tmem, raw);
+        tmem_wait_ld();
+        float hb[32];
+#pragma unroll
+        for (int f = 0; f < 32; ++f) hb[f] = __uint_as_float(raw[f]);
+        if (unscaled) write_core_block<32, false>(arow, 5, 10, hb, 1.f); else write_core_block<32, true>(arow, 5, 10, hb, s);
+    }
+    *reinterpret_cast<uint4*>(arow + 9 * CORE) = make_uint4(0u, 0u, 0u, 0u);      // K padding 72..79
+    *reinterpret_cast<uint4*>(arow + 19 * CORE) = make_uint4(0u, 0u, 0u, 0u);
+    return inv;
 }
 
 // the thread's accumulator row (72 + 2 columns) out of TMEM -> fp32 quads of its own row + (s, t)
@@ -386,6 +478,9 @@ gat_fused_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ lea
         wide_from_tmem(d_mine, sc, arow, sv);
         st[lane] = sv;
         __syncwarp();
+#if GTC_HALVES
+        sc = wide_attend_to_operand(wrows_a, st, group_mask, sv.x, alpha, arow, d_mine + 80) * winv2;
+#else
         {
             float hp[HID];
             attend_core<HID>(wrows_a, st, group_mask, sv.x, alpha, hp);
@@ -394,6 +489,7 @@ gat_fused_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ lea
             __syncwarp();                                    // every lane is done reading the Wh1 rows
             sc = row_to_operand<HID, K2>(arow, hp) * winv2;
         }
+#endif
         // ---- intra GAT, out_att: Wh2 = x1a Wio (+ scores) ----
         run_layer([&]() { issue_layer<K2, N2>(d_tmem, a_s, sbase + OFF_W2, bar); });
         narrow_from_tmem(d_mine, sc, nrow, sv);
@@ -427,6 +523,9 @@ gat_fused_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ lea
         wide_from_tmem(d_mine, sc, arow, sv);
         st[lane] = sv;
         __syncwarp();
+#if GTC_HALVES
+        sc = wide_attend_to_operand(wrows_a, st, leader_mask, sv.x, alpha, arow, d_mine + 80) * winv4;
+#else
         {
             float hp[HID];
             attend_core<HID>(wrows_a, st, leader_mask, sv.x, alpha, hp);
@@ -435,6 +534,7 @@ gat_fused_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ lea
             __syncwarp();
             sc = row_to_operand<HID, K4>(arow, hp) * winv4;
         }
+#endif
         // ---- inter GAT, out_att: Wh4 = hp Weo (+ scores) ----
         run_layer([&]() { issue_layer<K4, N4>(d_tmem, a_s, sbase + OFF_W4, bar); });
         narrow_from_tmem(d_mine, sc, nrow, sv);
