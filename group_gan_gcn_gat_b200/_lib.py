@@ -81,13 +81,14 @@ SIGNATURES = {
     'sgx_gat_encoder_fused_bwd': (ctypes.c_int, [_P] * 8 + [_I64] + [_P] * 10 + [_F32] + [_I32] * 5 + [_P] * 11 +
                                   [_P, _I64, _P]),
     'sgx_lstm_ws_bytes': (_I64, []),
-    'sgx_lstm_encoder_fwd': (ctypes.c_int, [_P, _I32, _I64, _P, _P, _P, _P, _P, _P, _I32, _I32, _P, _P, _I64, _P]),
+    'sgx_lstm_encoder_fwd': (ctypes.c_int, [_P, _I32, _I64, _P, _P, _P, _P, _P, _P, _I32, _I32, _P, _P, _I64, _I32, _P]),
+    'sgx_lstm_prep': (ctypes.c_int, [_P] * 6 + [_I32, _I32, _P, _I64, _P]),
     'sgx_lstm_tape_floats': (_I64, [_I32, _I64, _I32]),
     'sgx_lstm_bwd_ws_bytes': (_I64, [_I32, _I64, _I32]),
     'sgx_lstm_encoder_train_fwd': (ctypes.c_int, [_P, _I32, _I64] + [_P] * 6 + [_I32, _I32, _P, _P, _P]),
     'sgx_lstm_decoder_train_fwd': (ctypes.c_int, [_P, _P, _P, _I32, _I64] + [_P] * 8 + [_I32, _I32, _P, _P, _P, _P]),
     'sgx_lstm_bwd': (ctypes.c_int, [_I32, _P, _I32, _I64] + [_P] * 7 + [_I32, _I32] + [_P] * 9 + [_I64, _P]),
-    'sgx_lstm_decoder_fwd': (ctypes.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I64] + [_P] * 8 + [_I32, _I32, _P, _P, _P, _P, _I64, _P]),
+    'sgx_lstm_decoder_fwd': (ctypes.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I64] + [_P] * 8 + [_I32, _I32, _P, _P, _P, _P, _I64, _I32, _P]),
     'sgx_displacement_errors': (ctypes.c_int, [_P, _P, _P, _I32, _I64, _P, _P, _I32, _I32, _P]),
     'sgx_best_of_k': (ctypes.c_int, [_P, _P, _P, _I64, _I32, _P, _P]),
     'sgx_dense_att_fwd': (ctypes.c_int, [_P, _P, _I64, _F32, _P, _P]),

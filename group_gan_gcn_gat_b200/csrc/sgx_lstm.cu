@@ -434,7 +434,7 @@ int64_t sgx_lstm_tc_ws_bytes();
 int sgx_lstm_tc_run(bool decoder, const float* seq_in, const float* h0, const float* c0, const float* z,
                     const int32_t* ped_scene, int nz, int T, int64_t batch, const float* We, const float* be,
                     const float* W_ih, const float* W_hh, const float* b_ih, const float* b_hh, const float* W_hp,
-                    const float* b_hp, int E, float* seq_out, float* h_out, void* ws, cudaStream_t st);
+                    const float* b_hp, int E, float* seq_out, float* h_out, void* ws, cudaStream_t st, bool ws_prepared);
 
 static bool use_tc(int H, int T, int64_t batch, const void* ws, int64_t ws_bytes) {
     if (!opt_lstm_tc()) return false;      // sgx_set_option("lstm_tc", 0): CUDA-core kernels for every batch (parity tests)
@@ -443,16 +443,28 @@ static bool use_tc(int H, int T, int64_t batch, const void* ws, int64_t ws_bytes
 
 extern "C" int64_t sgx_lstm_ws_bytes(void) { return sgx_lstm_tc_ws_bytes(); }
 
+// Fills a workspace with the tensor-core weight images of one recurrence (embedding folded into the input weights, gate
+// rows pre-scaled, 3-way bf16 splits): pass it to sgx_lstm_encoder_fwd / _decoder_fwd with ws_prepared = 1 for as long as
+// these weights do not change, and the per-call prep launch (4.7 us) disappears.  A no-op for h_dim != 32.
+extern "C" int sgx_lstm_prep(const float* We, const float* be, const float* W_ih, const float* W_hh, const float* b_ih,
+                             const float* b_hh, int32_t E, int32_t H, void* workspace, int64_t ws_bytes, void* stream) {
+    SGX_REQUIRE(We && be && W_ih && W_hh && b_ih && b_hh && workspace, "sgx_lstm_prep: null pointer");
+    SGX_REQUIRE(ws_bytes >= sgx_lstm_tc_ws_bytes(), "sgx_lstm_prep: workspace too small");
+    if (H != 32) return SGX_OK;
+    return sgx_lstm_tc_run(false, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, We, be, W_ih, W_hh, b_ih, b_hh, nullptr,
+                           nullptr, E, nullptr, nullptr, workspace, (cudaStream_t)stream, false);
+}
+
 extern "C" int sgx_lstm_encoder_fwd(const float* obs_rel, int32_t T, int64_t batch, const float* We, const float* be,
                                     const float* W_ih, const float* W_hh, const float* b_ih, const float* b_hh,
                                     int32_t E, int32_t H, float* h_out, void* workspace, int64_t ws_bytes,
-                                    void* stream) {
+                                    int32_t ws_prepared, void* stream) {
     SGX_REQUIRE(obs_rel && We && be && W_ih && W_hh && b_ih && b_hh && h_out, "sgx_lstm_encoder_fwd: null pointer");
     SGX_REQUIRE(T >= 1 && batch >= 1 && batch < ((int64_t)1 << 31) && E >= 1, "sgx_lstm_encoder_fwd: bad shape");
     cudaStream_t st = (cudaStream_t)stream;
     if (use_tc(H, T, batch, workspace, ws_bytes))
         return sgx_lstm_tc_run(false, obs_rel, nullptr, nullptr, nullptr, nullptr, 0, T, batch, We, be, W_ih, W_hh, b_ih,
-                               b_hh, nullptr, nullptr, E, nullptr, h_out, workspace, st);
+                               b_hh, nullptr, nullptr, E, nullptr, h_out, workspace, st, ws_prepared != 0);
     if (H == 32) return launch_encoder<32>(obs_rel, T, batch, We, be, W_ih, W_hh, b_ih, b_hh, E, h_out, st);
     if (H == 48) return launch_encoder<48>(obs_rel, T, batch, We, be, W_ih, W_hh, b_ih, b_hh, E, h_out, st);
     if (H == 64) return launch_encoder<64>(obs_rel, T, batch, We, be, W_ih, W_hh, b_ih, b_hh, E, h_out, st);
@@ -464,7 +476,7 @@ extern "C" int sgx_lstm_decoder_fwd(const float* h0, const float* c0, const floa
                                     const int32_t* ped_scene, int32_t nz, int32_t steps, int64_t batch, const float* We, const float* be, const float* W_ih,
                                     const float* W_hh, const float* b_ih, const float* b_hh, const float* W_hp,
                                     const float* b_hp, int32_t E, int32_t H, float* pred_rel, float* h_final,
-                                    float* c_final, void* workspace, int64_t ws_bytes, void* stream) {
+                                    float* c_final, void* workspace, int64_t ws_bytes, int32_t ws_prepared, void* stream) {
     SGX_REQUIRE(h0 && last_pos_rel && We && be && W_ih && W_hh && b_ih && b_hh && W_hp && b_hp && pred_rel,
                 "sgx_lstm_decoder_fwd: null pointer");
     SGX_REQUIRE(steps >= 1 && batch >= 1 && batch < ((int64_t)1 << 31) && E >= 1, "sgx_lstm_decoder_fwd: bad shape");
@@ -472,7 +484,7 @@ extern "C" int sgx_lstm_decoder_fwd(const float* h0, const float* c0, const floa
     cudaStream_t st = (cudaStream_t)stream;
     if (!c_final && use_tc(H, steps, batch, workspace, ws_bytes))
         return sgx_lstm_tc_run(true, last_pos_rel, h0, c0, z, ped_scene, nz, steps, batch, We, be, W_ih, W_hh, b_ih, b_hh,
-                               W_hp, b_hp, E, pred_rel, h_final, workspace, st);
+                               W_hp, b_hp, E, pred_rel, h_final, workspace, st, ws_prepared != 0);
     if (H == 32)
         return launch_decoder<32>(h0, c0, last_pos_rel, z, ped_scene, nz, steps, batch, We, be, W_ih, W_hh, b_ih, b_hh, W_hp, b_hp, E,
                                   pred_rel, h_final, c_final, st);

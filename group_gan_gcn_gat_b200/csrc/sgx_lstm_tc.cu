@@ -360,10 +360,13 @@ int64_t sgx_lstm_tc_ws_bytes() { return 5 * LT * 128 + 256; }
 int sgx_lstm_tc_run(bool decoder, const float* seq_in, const float* h0, const float* c0, const float* z,
                     const int32_t* ped_scene, int nz, int T, int64_t batch, const float* We, const float* be,
                     const float* W_ih, const float* W_hh, const float* b_ih, const float* b_hh, const float* W_hp,
-                    const float* b_hp, int E, float* seq_out, float* h_out, void* ws, cudaStream_t st) {
+                    const float* b_hp, int E, float* seq_out, float* h_out, void* ws, cudaStream_t st, bool ws_prepared) {
     __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(ws);
-    lstm_tc_prep_kernel<<<blocks_for(5 * LT * 64, 256), 256, 0, st>>>(We, be, W_ih, W_hh, b_ih, b_hh, E, img);
-    SGX_LAUNCH_CHECK();
+    if (!ws_prepared) {                    // (the host side keeps a prepared workspace per module and weight version)
+        lstm_tc_prep_kernel<<<blocks_for(5 * LT * 64, 256), 256, 0, st>>>(We, be, W_ih, W_hh, b_ih, b_hh, E, img);
+        SGX_LAUNCH_CHECK();
+    }
+    if (seq_in == nullptr) return SGX_OK;  // prep-only call (sgx_lstm_prep)
     const int n_tiles = (int)((batch + LT - 1) / LT);
     int dev = 0, sms = 148;
     SGX_CUDA(cudaGetDevice(&dev));

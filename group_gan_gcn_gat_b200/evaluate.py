@@ -171,12 +171,17 @@ class GraphedGenerator:
     so one forward is captured per scene layout and replayed with new trajectories / noise copied into its static
     buffers: 0.93 -> 0.45 ms for the best-of-20 forward of a 64-scene batch.  A different `seq_start_end` (different
     ragged layout = different grids) triggers a re-capture; at most `max_graphs` layouts are kept.
-    Inference only (no autograd through a graph replay); the generator's weights are read at replay time, so in-place
-    weight updates are seen, re-assigned parameters are not.
+    Inference only (no autograd through a graph replay).  The captured launches read the prepared weight images the modules
+    cache per weight version (pooling, recurrences, graph context), so a graph must be re-captured after the weights change
+    (`GraphedGenerator(generator)` again, or `.reset()`).
     """
 
     def __init__(self, generator, max_graphs=8):
         self.generator, self.max_graphs, self._graphs = generator, max_graphs, {}
+
+    def reset(self):
+        """drop the captured graphs (after a weight update)"""
+        self._graphs.clear()
 
     def _capture(self, key, obs_traj, obs_traj_rel, seq_start_end, obs_traj_g, user_noise):
         static = [t.clone() for t in (obs_traj, obs_traj_rel, obs_traj_g, user_noise)]

@@ -575,6 +575,29 @@ def gemm(a, b, relu=False):
 FUSED_LSTM_H = (32, 48, 64)
 
 
+def _lstm_prepared_ws(emb, lstm, batch):
+    """-> (workspace, prepared flag) for the inference recurrences.  Large batches of an h_dim-32 recurrence run the tcgen05
+    kernel, whose weight images live in the workspace: a dedicated buffer per nn.LSTM module, refilled (sgx_lstm_prep) only
+    when a parameter was updated in place or reassigned.  Everything else takes the shared scratch, unprepared."""
+    L = _lib.lib()
+    dev = emb.weight.device
+    if lstm.hidden_size != 32 or batch < 8192 or not _lib.option('lstm_tc'):
+        return _ws(L.sgx_lstm_ws_bytes(), dev), 0
+    ws_ = [t.detach().contiguous() for t in (emb.weight, emb.bias, lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0,
+                                             lstm.bias_hh_l0)]
+    key = _weights_key(ws_) + (torch.cuda.current_stream(dev).cuda_stream,)
+    cache = lstm.__dict__.setdefault('_sgx_tc_prep', {})
+    if cache.get('key') != key:
+        buf = cache.get('buf')
+        if buf is None or buf.device != dev:
+            buf = torch.empty(L.sgx_lstm_ws_bytes(), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.sgx_lstm_prep(*[_ptr(t) for t in ws_], emb.out_features, lstm.hidden_size, _ptr(buf), buf.numel(),
+                                       _stream(emb.weight)), 'sgx_lstm_prep')
+        cache['key'], cache['buf'] = key, buf
+    return cache['buf'], 1
+
+
 def lstm_encoder(obs_rel, emb, lstm):
     """obs_rel [T,batch,2] -> final hidden state [1,batch,H] (Encoder.forward, sgan/models.py:62-92)."""
     obs_rel = _f32(obs_rel, 'obs_traj_rel')
@@ -582,12 +605,12 @@ def lstm_encoder(obs_rel, emb, lstm):
     H, E = lstm.hidden_size, emb.out_features
     out = torch.empty(batch, H, dtype=torch.float32, device=obs_rel.device)
     L = _lib.lib()
-    ws = _ws(L.sgx_lstm_ws_bytes(), obs_rel.device)
+    ws, prepared = _lstm_prepared_ws(emb, lstm, batch)
     with torch.cuda.device(obs_rel.device):
         _lib.check(L.sgx_lstm_encoder_fwd(_ptr(obs_rel), T, batch, _ptr(emb.weight.contiguous()), _ptr(emb.bias.contiguous()),
                                           _ptr(lstm.weight_ih_l0.contiguous()), _ptr(lstm.weight_hh_l0.contiguous()),
                                           _ptr(lstm.bias_ih_l0.contiguous()), _ptr(lstm.bias_hh_l0.contiguous()), E, H,
-                                          _ptr(out), _ptr(ws), ws.numel(), _stream(obs_rel)), 'sgx_lstm_encoder_fwd')
+                                          _ptr(out), _ptr(ws), ws.numel(), prepared, _stream(obs_rel)), 'sgx_lstm_encoder_fwd')
     return out.unsqueeze(0)
 
 
@@ -607,14 +630,15 @@ def lstm_decoder(h0, c0, last_pos_rel, steps, emb, lstm, hidden2pos, want_state=
     hf = torch.empty(batch, H, dtype=torch.float32, device=dev) if want_state else None
     cf = torch.empty(batch, H, dtype=torch.float32, device=dev) if want_state is True else None
     L = _lib.lib()
-    ws = _ws(L.sgx_lstm_ws_bytes(), dev)
+    ws, prepared = _lstm_prepared_ws(emb, lstm, batch)
     with torch.cuda.device(dev):
         _lib.check(L.sgx_lstm_decoder_fwd(_ptr(h0), _ptr(c0), _ptr(last_pos_rel), _ptr(z), _ptr(ped_scene), nz, steps, batch,
                                           _ptr(emb.weight.contiguous()), _ptr(emb.bias.contiguous()),
                                           _ptr(lstm.weight_ih_l0.contiguous()), _ptr(lstm.weight_hh_l0.contiguous()),
                                           _ptr(lstm.bias_ih_l0.contiguous()), _ptr(lstm.bias_hh_l0.contiguous()),
                                           _ptr(hidden2pos.weight.contiguous()), _ptr(hidden2pos.bias.contiguous()), E, H,
-                                          _ptr(pred), _ptr(hf), _ptr(cf), _ptr(ws), ws.numel(), _stream(h0)), 'sgx_lstm_decoder_fwd')
+                                          _ptr(pred), _ptr(hf), _ptr(cf), _ptr(ws), ws.numel(), prepared, _stream(h0)),
+                   'sgx_lstm_decoder_fwd')
     if want_state == 'h':
         return pred, hf
     return (pred, hf, cf) if want_state else pred

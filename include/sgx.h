@@ -328,13 +328,17 @@ int sgx_gat_encoder_fused_bwd(const float* x, const float* grad_out, const int32
 int64_t sgx_lstm_ws_bytes(void);
 int sgx_lstm_encoder_fwd(const float* obs_rel, int32_t T, int64_t batch, const float* We, const float* be,
                          const float* W_ih, const float* W_hh, const float* b_ih, const float* b_hh, int32_t E,
-                         int32_t H, float* h_out, void* workspace, int64_t ws_bytes, void* stream);
+                         int32_t H, float* h_out, void* workspace, int64_t ws_bytes, int32_t ws_prepared, void* stream);
 int sgx_lstm_decoder_fwd(const float* h0, const float* c0, const float* last_pos_rel, const float* z,
                          const int32_t* ped_scene, int32_t nz, int32_t steps, int64_t batch,
                          const float* We, const float* be, const float* W_ih, const float* W_hh, const float* b_ih,
                          const float* b_hh, const float* W_hp, const float* b_hp, int32_t E, int32_t H,
                          float* pred_rel, float* h_final, float* c_final, void* workspace, int64_t ws_bytes,
-                         void* stream);
+                         int32_t ws_prepared, void* stream);
+/* ws_prepared = 1: `workspace` already holds the tensor-core weight images of exactly these weights, written by
+ * sgx_lstm_prep (a workspace the caller keeps per recurrence and weight version); 0: the call builds them itself. */
+int sgx_lstm_prep(const float* We, const float* be, const float* W_ih, const float* W_hh, const float* b_ih,
+                  const float* b_hh, int32_t E, int32_t H, void* workspace, int64_t ws_bytes, void* stream);
 
 /* Training path of the same recurrences (what autograd does through nn.LSTM + the step loop of sgan/models.py:157-175,
  * replaced by one forward kernel that writes a tape and one backward kernel + 2-3 reductions):
