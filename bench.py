@@ -401,8 +401,8 @@ def main():
         """The body of scripts/evaluate_model.py:72-99 for one minibatch, from HOST buffers: H2D of the batch, schedule
         built from the host seq_start_end, K complete generator forwards, best-of-K ADE/FDE reduced on the device,
         D2H of the two sums."""
+        obs_rel = host['obs_traj_rel'].to(dev, non_blocking=True)      # first: the encoder only waits for this one
         obs = host['obs_traj'].to(dev, non_blocking=True)
-        obs_rel = host['obs_traj_rel'].to(dev, non_blocking=True)
         grp = host['obs_traj_g'].to(dev, non_blocking=True)
         gt = host['pred_traj_gt'].to(dev, non_blocking=True)
         sse = host['seq_start_end'].clone()              # a fresh batch object every step: the schedule is rebuilt
@@ -463,7 +463,7 @@ def main():
         side = torch.cuda.Stream(dev)
         main_stream = torch.cuda.current_stream(dev)
         out_pipe = torch.empty(args.steps + args.warmup, 2).pin_memory()
-        keys = ('obs_traj', 'obs_traj_rel', 'obs_traj_g', 'pred_traj_gt')
+        keys = ('obs_traj_rel', 'obs_traj', 'obs_traj_g', 'pred_traj_gt')
         slots = [{k: torch.empty_like(dev_in[k]) for k in keys} for _ in range(2)]    # double buffer, no allocation per step
 
         def stage(i):
