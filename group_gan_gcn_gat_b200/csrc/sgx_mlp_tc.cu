@@ -11,7 +11,11 @@ namespace mtc {
 
 using namespace gtile;
 
-constexpr int GROUPS = 4;
+#ifndef MTC_GROUPS
+#define MTC_GROUPS 4
+#endif
+constexpr int GROUPS = MTC_GROUPS;
+constexpr int TCOLS = 64;            // TMEM columns per group (N <= 64)
 constexpr int NTHREADS = GROUPS * 128;
 constexpr int HID = 64;
 
@@ -101,7 +105,7 @@ mlp2_tc_kernel(const float* __restrict__ xa, int da, const float* __restrict__ x
     uint8_t* arow = abuf + row * 16;
     uint64_t* bar = &bars[grp];
     const uint32_t a_s = sbase + C::OFF_GRP + grp * C::GRP_BYTES;
-    const uint32_t d_tmem = tmem + (uint32_t)grp * 128u;
+    const uint32_t d_tmem = tmem + (uint32_t)grp * TCOLS;
     const uint32_t d_mine = d_tmem + ((uint32_t)(wq * 32) << 16);
     uint32_t parity = 0;
     const float winv1 = s_winv[0], winv2 = s_winv[1];

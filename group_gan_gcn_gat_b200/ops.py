@@ -364,7 +364,7 @@ def gcn_module_fwd_labels(x, labels, ped_start, ped_end, scene_start, W0, W1, V0
     """Inference-only GCNModule forward with the group structure derived inside the tcgen05 kernel from the labels
     (sgx_gcn_module_fused_fwd_labels): scenes <= 32 pedestrians, built dims.  No autograd."""
     x = _f32(x, 'h_states')
-    labels = _f32(labels.reshape(-1), 'labels')
+    labels = _f32(labels.reshape(-1).float(), 'labels')          # the reference compares the label column as floats
     W0, W1, V0, V1, Wo, bo = (_f32(t, 'gcn weight') for t in (W0, W1, V0, V1, Wo, bo))
     _check_gcn_shapes(x, W0, W1, V0, V1, Wo, bo)
     if labels.numel() != x.shape[0]:
@@ -476,7 +476,7 @@ def gat_encoder_fwd_labels(x, labels, ped_start, ped_end, Wi, ai, Wio, aio, We, 
     """Inference-only GATEncoder forward with the group structure derived inside the tcgen05 kernel from the labels
     (sgx_gat_encoder_fused_fwd_labels): scenes <= 32 pedestrians, n_heads 1, dims 40/72/16/24.  No autograd."""
     x = _f32(x, 'h_states')
-    labels = _f32(labels.reshape(-1), 'labels')
+    labels = _f32(labels.reshape(-1).float(), 'labels')          # the reference compares the label column as floats
     ps = [_f32(t, 'gat weight') for t in (Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo)]
     _check_gat_shapes(x, *ps)
     if labels.numel() != x.shape[0]:
