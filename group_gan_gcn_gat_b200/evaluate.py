@@ -9,7 +9,7 @@ import torch
 
 from .losses import displacement_error, final_displacement_error
 from .models import ped_scene_index
-from .schedule import get_schedule
+from .schedule import get_schedule, tiled_schedule
 from .utils import relative_to_abs
 
 
@@ -90,8 +90,7 @@ def _evaluate_batch_folded(generator, obs_traj, obs_traj_rel, seq_start_end, obs
     L = _lib.lib()
     dev = obs_traj.device
     n, s, T = obs_traj.shape[1], sched.n_scenes, pred_traj_gt.shape[0]
-    offs = (torch.arange(k, device=seq_start_end.device, dtype=seq_start_end.dtype) * n).repeat_interleave(s)
-    sse_k = seq_start_end.repeat(k, 1) + offs.unsqueeze(1)
+    sse_k = tiled_schedule(sched, k, dev)                # built on the host from the base schedule: no device read-back
     rel = generator(obs_traj.repeat(1, k, 1), obs_traj_rel.repeat(1, k, 1), sse_k, obs_traj_g.repeat(1, k, 1),
                     user_noise=noise.reshape(k * s, -1)).contiguous()
     gt = _f32(pred_traj_gt.repeat(1, k, 1), 'pred_traj_gt')

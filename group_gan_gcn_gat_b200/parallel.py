@@ -17,7 +17,7 @@ import torch.nn as nn
 
 from .losses import gan_d_loss, gan_g_loss, l2_loss
 from .models import ped_scene_index
-from .schedule import SceneSchedule, get_schedule
+from .schedule import SceneSchedule, get_schedule, tiled_schedule
 from .utils import relative_to_abs
 
 
@@ -212,7 +212,7 @@ def discriminator_step(args, batch, generator, discriminator, optimizer_d, label
         # fake and real trajectories as ONE discriminator batch of 2 x scenes (same weights, independent scenes)
         traj = torch.cat([torch.cat([obs_traj, fake], 0), torch.cat([obs_traj, pred_traj_gt], 0)], 1)
         traj_rel = torch.cat([torch.cat([obs_traj_rel, fake_rel], 0), torch.cat([obs_traj_rel, pred_traj_gt_rel], 0)], 1)
-        scores = discriminator(traj, traj_rel, torch.cat([seq_start_end, seq_start_end + n_local], 0))
+        scores = discriminator(traj, traj_rel, tiled_schedule(seq_start_end, 2, obs_traj.device))
         s_fake, s_real = scores[:n_local], scores[n_local:]
     else:
         s_fake = discriminator(torch.cat([obs_traj, fake], 0), torch.cat([obs_traj_rel, fake_rel], 0), seq_start_end)
@@ -245,15 +245,14 @@ def _folded_samples(generator, obs_traj, obs_traj_rel, obs_traj_g, seq_start_end
     """k generator samples as one forward over k copies of the batch -> fake_rel [pred_len, k * batch, 2] (sample-major).
     noise: optional [k, rows, *noise_dim] (rows = scenes for 'global' mixing) instead of k get_noise draws."""
     from .models import get_noise
-    n, s = obs_traj.shape[1], seq_start_end.shape[0]
+    n, s = obs_traj.shape[1], get_schedule(seq_start_end, obs_traj.device).n_scenes
     if noise is not None:
         noise = noise.reshape(-1, *noise.shape[2:]).to(obs_traj.device)
     elif generator.noise_dim:
         rows = s if generator.noise_mix_type == 'global' else n
         noise = torch.cat([get_noise((rows,) + tuple(generator.noise_dim), generator.noise_type, obs_traj.device)
                            for _ in range(k)], dim=0)
-    offs = (torch.arange(k, device=seq_start_end.device, dtype=seq_start_end.dtype) * n).repeat_interleave(s)
-    sse_k = seq_start_end.repeat(k, 1) + offs.unsqueeze(1)
+    sse_k = tiled_schedule(seq_start_end, k, obs_traj.device)        # a SceneSchedule: no device read-back
     return generator(obs_traj.repeat(1, k, 1), obs_traj_rel.repeat(1, k, 1), sse_k, obs_traj_g.repeat(1, k, 1),
                      user_noise=noise)
 
@@ -275,16 +274,21 @@ def generator_step(args, batch, generator, discriminator, optimizer_g, label_rng
         return {'G_total_loss': 0.0}
     sched = get_schedule(seq_start_end, obs_traj.device)
     mask = loss_mask[:, args.obs_len:]
-    raws = []
+    raws, raw_kn = [], None
     if getattr(args, 'fold_best_k', True) and args.best_k > 1 and _batch_independent(generator):
         # The best_k samples share weights and inputs and differ only in the noise: run them as ONE forward / backward
         # over best_k copies of the batch (SURVEY 8d cfg 4/5: "K folded into the batch dimension").  Same noise stream
         # as the loop (one get_noise draw per sample, in order), same loss terms, 1/best_k of the launches.
         fake_all = _folded_samples(generator, obs_traj, obs_traj_rel, obs_traj_g, seq_start_end, args.best_k, noise)
-        for k in range(args.best_k):
-            fake_rel = fake_all[:, k * n_local:(k + 1) * n_local]
-            if args.l2_loss_weight > 0:
-                raws.append(args.l2_loss_weight * l2_loss(fake_rel, pred_traj_gt_rel, mask, mode='raw'))
+        fake_rel = fake_all[:, (args.best_k - 1) * n_local:]      # the last sample feeds the adversarial term (train.py:466)
+        if args.l2_loss_weight > 0:
+            # l2_loss(..., mode='raw') of all best_k samples in ONE expression (the same masked squared error, summed over
+            # coordinates then time): the per-sample loop was 20 x (slice, sub, pow, mul, 2 sums) + as many autograd nodes,
+            # ~300 launches and 3 ms of host time in a step that is launch-bound
+            T = fake_all.shape[0]
+            err = mask.unsqueeze(2).unsqueeze(0) * (pred_traj_gt_rel.permute(1, 0, 2).unsqueeze(0) -
+                                                    fake_all.view(T, args.best_k, n_local, 2).permute(1, 2, 0, 3)) ** 2
+            raw_kn = args.l2_loss_weight * err.sum(dim=3).sum(dim=2)                     # [best_k, n]
     else:
         for k in range(args.best_k):     # noise: optional [best_k, rows, *noise_dim] (parity runs under sharding)
             fake_rel = generator(obs_traj, obs_traj_rel, seq_start_end, obs_traj_g,
@@ -294,7 +298,7 @@ def generator_step(args, batch, generator, discriminator, optimizer_g, label_rng
     loss = obs_traj.new_zeros(())
     losses = {}
     if args.l2_loss_weight > 0:
-        l2 = variety_l2(torch.stack(raws, dim=1), mask, sched)
+        l2 = variety_l2(raw_kn.t() if raw_kn is not None else torch.stack(raws, dim=1), mask, sched)
         losses['G_l2_loss_rel'] = l2.detach()
         loss = loss + l2
     fake = relative_to_abs(fake_rel, obs_traj[-1])

@@ -131,6 +131,20 @@ def _evict_dead():
         del _cache[k]
 
 
+def tiled_schedule(seq_start_end, k, device):
+    """Schedule of k copies of the batch laid side by side (copy c covers rows c * batch + [start, end) of every scene): what
+    the K-folded forwards and the stacked fake + real discriminator batch run on.  Built from the HOST copy of the base
+    schedule and cached on it -- `seq_start_end.repeat(k, 1) + offsets` on the device made every folded step read the new
+    tensor back (a device synchronisation in the middle of a launch-bound training step)."""
+    base = get_schedule(seq_start_end, device)
+    tiled = base.__dict__.setdefault('_tiled', {})
+    hit = tiled.get(k)
+    if hit is None:
+        big = (base.host_sse[None] + (np.arange(k, dtype=np.int64) * base.batch)[:, None, None]).reshape(-1, 2)
+        hit = tiled[k] = SceneSchedule(big, device)
+    return hit
+
+
 def get_schedule(seq_start_end, device):
     """Cached per seq_start_end tensor object (and its in-place version counter)."""
     device = torch.device(device)
