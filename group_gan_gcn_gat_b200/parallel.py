@@ -250,8 +250,11 @@ def _folded_samples(generator, obs_traj, obs_traj_rel, obs_traj_g, seq_start_end
         noise = noise.reshape(-1, *noise.shape[2:]).to(obs_traj.device)
     elif generator.noise_dim:
         rows = s if generator.noise_mix_type == 'global' else n
-        noise = torch.cat([get_noise((rows,) + tuple(generator.noise_dim), generator.noise_type, obs_traj.device)
-                           for _ in range(k)], dim=0)
+        # the k draws of the sample loop, in order, on the CPU generator (seed-compatible with the reference) -- but ONE
+        # host-to-device copy from pinned memory instead of k synchronous pageable ones
+        noise = torch.cat([get_noise((rows,) + tuple(generator.noise_dim), generator.noise_type) for _ in range(k)], dim=0)
+        if obs_traj.is_cuda:
+            noise = noise.pin_memory().to(obs_traj.device, non_blocking=True)
     sse_k = tiled_schedule(seq_start_end, k, obs_traj.device)        # a SceneSchedule: no device read-back
     return generator(obs_traj.repeat(1, k, 1), obs_traj_rel.repeat(1, k, 1), sse_k, obs_traj_g.repeat(1, k, 1),
                      user_noise=noise)
