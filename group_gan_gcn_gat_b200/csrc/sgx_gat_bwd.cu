@@ -21,7 +21,10 @@
 
 namespace sgx {
 
-constexpr int GB_WARPS = 4;
+#ifndef GB_GLOBAL_GRADS
+#define GB_GLOBAL_GRADS 1            // 1: the CTA's gradient block lives in its HBM partial (red.global), 5 warps per SM;
+#endif                               // 0: in shared memory (30 KB), 4 warps per SM
+constexpr int GB_WARPS = GB_GLOBAL_GRADS ? 5 : 4;
 constexpr int GB_IN = 40, GB_FIN = 24;
 constexpr int RG = 28;                       // row stride of the grad_out rows (24 wide): conflict-free A fragments
 
@@ -146,13 +149,23 @@ gat_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout
     extern __shared__ __align__(16) uint8_t raw[];
     FusedWm& w = *reinterpret_cast<FusedWm*>(raw);
     GatAvec& av = *reinterpret_cast<GatAvec*>(raw + sizeof(FusedWm));
+#if GB_GLOBAL_GRADS
+    // the per-chunk parameter gradients are added straight into this CTA's partial block in HBM (fire-and-forget
+    // red.global.add, ~7.5 k per chunk): the 30 KB it occupied in shared memory is a fifth warp's scratch
+    GatGrad& gr = *reinterpret_cast<GatGrad*>(partials + (int64_t)blockIdx.x * GB_GRAD_FLOATS);
+    float* bufs = reinterpret_cast<float*>(raw + sizeof(FusedWm) + sizeof(GatAvec));
+#else
     GatGrad& gr = *reinterpret_cast<GatGrad*>(raw + sizeof(FusedWm) + sizeof(GatAvec));
     float* bufs = reinterpret_cast<float*>(raw + sizeof(FusedWm) + sizeof(GatAvec) + sizeof(GatGrad));
+#endif
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     fused_load_weights<IN, FIN>(w, Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo);
     for (int e = threadIdx.x; e < 2 * HID; e += blockDim.x) { av.ai[e] = ai[e]; av.ae[e] = ae[e]; }
     for (int e = threadIdx.x; e < 2 * OUT; e += blockDim.x) { av.aio[e] = aio[e]; av.aeo[e] = aeo[e]; }
     for (int e = threadIdx.x; e < GB_GRAD_FLOATS; e += blockDim.x) reinterpret_cast<float*>(&gr)[e] = 0.f;
+#if GB_GLOBAL_GRADS
+    __threadfence();
+#endif
     __syncthreads();
 
     float* P = bufs + warp * GB_SCRATCH;                 // [32][RS]  x / Wh1 / Wh3
@@ -518,9 +531,11 @@ gat_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout
             if (r + 8 < np) *reinterpret_cast<float2*>(grad_x + (int64_t)(p0 + r + 8) * IN + col) = make_float2(c[2], c[3]);
         });
     }
+#if !GB_GLOBAL_GRADS
     __syncthreads();
     float* mine = partials + (int64_t)blockIdx.x * GB_GRAD_FLOATS;
     for (int e = threadIdx.x; e < GB_GRAD_FLOATS; e += blockDim.x) mine[e] = reinterpret_cast<const float*>(&gr)[e];
+#endif
 }
 
 // sums the per-CTA gradient blocks in block order (deterministic) and scatters the ten tensors
@@ -570,7 +585,8 @@ extern "C" int sgx_gat_encoder_fused_bwd(const float* x, const float* grad_out, 
                     "%d/%d/%d/%d)", n_heads, IN, HID_, OUT_, FIN);
     SGX_REQUIRE(ws_bytes >= sgx_gat_encoder_fused_bwd_ws_bytes(), "sgx_gat_encoder_fused_bwd: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
-    const int smem = (int)(sizeof(FusedWm) + sizeof(GatAvec) + sizeof(GatGrad) + GB_WARPS * GB_SCRATCH * sizeof(float));
+    const int smem = (int)(sizeof(FusedWm) + sizeof(GatAvec) + (GB_GLOBAL_GRADS ? 0 : sizeof(GatGrad)) +
+                           GB_WARPS * GB_SCRATCH * sizeof(float));
     SGX_CUDA(cudaFuncSetAttribute(gat_fused_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int grid = (int)std::min<int64_t>((n_chunks + GB_WARPS - 1) / GB_WARPS, 148);
     float* partials = (float*)workspace;

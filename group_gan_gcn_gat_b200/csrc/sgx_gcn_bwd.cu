@@ -20,7 +20,10 @@ namespace sgx {
 namespace gcnb {
 
 constexpr int HID = 72, OUT = 16;
-constexpr int WARPS = 4;
+#ifndef GCB_GLOBAL_GRADS
+#define GCB_GLOBAL_GRADS 1           // 1: the CTA's gradient block lives in its HBM partial (red.global), 5 warps per SM;
+#endif                               // 0: in shared memory (28 KB), 4 warps per SM
+constexpr int WARPS = GCB_GLOBAL_GRADS ? 5 : 4;
 constexpr int RS = 76;                 // 72-wide rows
 constexpr int RA = 20;                 // 16-wide rows
 constexpr int SWW = 72;                // W0 / V0 blocks [K][72]
@@ -33,7 +36,7 @@ struct Cfg {
     static constexpr int WFLOATS = IN * SWW + 2 * HID * SWN + OUT * SWW + 2 * OUT * SWO;
     static constexpr int GRAD_FLOATS = IN * HID + HID * OUT + OUT * HID + HID * OUT + FIN * 2 * OUT + FIN;   // W0 W1 V0 V1 Wo bo
     static constexpr int SCRATCH = 2 * 32 * RS + 5 * 32 * RA + 32 * RG;
-    static constexpr int SMEM = (WFLOATS + GRAD_FLOATS + WARPS * SCRATCH) * (int)sizeof(float);
+    static constexpr int SMEM = (WFLOATS + (GCB_GLOBAL_GRADS ? 0 : GRAD_FLOATS) + WARPS * SCRATCH) * (int)sizeof(float);
 };
 
 template <int F>
@@ -59,13 +62,21 @@ gcn_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout
     float* sV0 = sW1 + HID * SWN;                             // [16][72]
     float* sV1 = sV0 + OUT * SWW;                             // [72][24]
     float* sWoT = sV1 + HID * SWN;                            // [32][SWO] = Wo^T
+#if GCB_GLOBAL_GRADS
+    float* gW0 = partials + (int64_t)blockIdx.x * C::GRAD_FLOATS;      // gradient block = this CTA's partial in HBM (red.global)
+#else
     float* gW0 = sWoT + 2 * OUT * SWO;                        // gradient block, in the order of the partials
+#endif
     float* gW1 = gW0 + IN * HID;
     float* gV0 = gW1 + HID * OUT;
     float* gV1 = gV0 + OUT * HID;
     float* gWo = gV1 + HID * OUT;
     float* gbo = gWo + FIN * 2 * OUT;
+#if GCB_GLOBAL_GRADS
+    float* bufs = sWoT + 2 * OUT * SWO;
+#else
     float* bufs = gbo + FIN;
+#endif
     for (int e = threadIdx.x; e < IN * HID; e += blockDim.x) sW0[e] = W0[e];
     for (int e = threadIdx.x; e < OUT * HID; e += blockDim.x) sV0[e] = V0[e];
     for (int e = threadIdx.x; e < HID * SWN; e += blockDim.x) {
@@ -78,6 +89,9 @@ gcn_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout
         sWoT[e] = n < FIN ? Wo[n * 2 * OUT + k] : 0.f;
     }
     for (int e = threadIdx.x; e < C::GRAD_FLOATS; e += blockDim.x) gW0[e] = 0.f;
+#if GCB_GLOBAL_GRADS
+    __threadfence();
+#endif
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -296,9 +310,11 @@ gcn_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout
         }
         __syncwarp();
     }
+#if !GCB_GLOBAL_GRADS
     __syncthreads();
     float* mine = partials + (int64_t)blockIdx.x * C::GRAD_FLOATS;
     for (int e = threadIdx.x; e < C::GRAD_FLOATS; e += blockDim.x) mine[e] = gW0[e];
+#endif
 }
 
 template <int IN, int FIN>
