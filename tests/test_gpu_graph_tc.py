@@ -231,3 +231,31 @@ def test_tc_weight_images_follow_parameter_updates():
             first = next(mod.parameters())
             first.data = first.data * 1.1                             # reassigned storage (data_ptr)
             close(mod(*args), oracle(mod), 1e-5, name + ' after reassignment')
+
+
+def test_autograd_function_twins_match_the_registered_ops():
+    """ops.call() runs a torch.autograd.Function twin of each custom op under autograd (no torch.library dispatcher on the
+    step path); the twin must give the gradients of the registered op (same forward body, setup, backward)."""
+    import group_gan_gcn_gat_b200.modules as M
+    from group_gan_gcn_gat_b200 import ops
+    from group_gan_gcn_gat_b200.schedule import get_schedule
+    sizes = [5, 12, 3, 33, 7]                      # one scene above 32: general GAT / GCN backward, fused pooling backward
+    sse, x, pos, labs = batch_of(sizes, 31)
+    dev = torch.device(DEV)
+    sched = get_schedule(sse.to(dev), dev)
+    pool = M.PoolHiddenNet(embedding_dim=16, h_dim=32, mlp_dim=64, bottleneck_dim=8, batch_norm=False).to(dev)
+    h = torch.randn(sum(sizes), 32, device=dev)
+    l1, l2 = pool._fused_params()
+    params = (pool.spatial_embedding.weight, pool.spatial_embedding.bias, l1.weight, l1.bias, l2.weight, l2.bias)
+    code = M.resolve_pool_precision(pool.precision, 16, 32, 8)
+    args = (sched.ped_start, sched.ped_end, sched.pair_off, sched.tile_first, sched.n_pairs, *params, code, None)
+    up = torch.randn(sum(sizes), 8, device=dev)
+    grads = []
+    for use_twin in (True, False):
+        hh = h.clone().requires_grad_(True)
+        pp = pos.to(dev).clone().requires_grad_(True)
+        out, _arg = (ops.call(ops.pool_fwd, hh, pp, *args) if use_twin else ops.pool_fwd(hh, pp, *args))
+        grads.append(torch.autograd.grad((out * up).sum(), [hh, pp] + list(params)))
+    for i, (a, b) in enumerate(zip(*grads)):       # (the position gradient is accumulated with shared-memory atomics: not
+        close(a, b, 1e-6, 'gradient %d' % i)        # bit-reproducible between two launches)
+    assert ops._FAST[ops.pool_fwd] is not None and ops._FAST[ops.gat_encoder_fwd] is not None and ops._FAST[ops.gcn_module_fwd] is not None

@@ -228,3 +228,24 @@ def test_batch_independence_guard_of_the_folded_steps():
     drop = nn.Sequential(nn.Linear(4, 4), nn.Dropout(0.5))
     assert not _batch_independent(drop.train())
     assert _batch_independent(drop.eval())
+
+
+def test_tiled_schedule_is_the_schedule_of_k_copies():
+    """schedule.tiled_schedule(sse, k): k copies of the batch side by side, built from the host copy of the base schedule
+    (what the K-folded forwards and the stacked fake + real discriminator batch run on) == the schedule of the explicitly
+    repeated seq_start_end; cached on the base schedule."""
+    from group_gan_gcn_gat_b200.schedule import SceneSchedule, get_schedule, tiled_schedule
+    rng = np.random.RandomState(5)
+    sizes = list(rng.randint(1, 20, size=37))
+    st = np.concatenate([[0], np.cumsum(sizes)])
+    sse = torch.from_numpy(np.stack([st[:-1], st[1:]], 1).astype(np.int64))
+    n = int(st[-1])
+    for k in (1, 2, 20):
+        t = tiled_schedule(sse, k, 'cpu')
+        rep = sse.repeat(k, 1) + (torch.arange(k) * n).repeat_interleave(len(sizes)).unsqueeze(1)
+        ref = SceneSchedule(rep, 'cpu')
+        assert (t.n_scenes, t.batch, t.n_pairs, t.max_n) == (ref.n_scenes, ref.batch, ref.n_pairs, ref.max_n)
+        for name in ('scene_start', 'ped_start', 'ped_end', 'pair_off', 'tile_first'):
+            assert torch.equal(getattr(t, name), getattr(ref, name)), name
+        assert tiled_schedule(sse, k, 'cpu') is t                                  # cached on the base schedule
+        assert get_schedule(t, 'cpu') is t                                         # accepted wherever seq_start_end is
