@@ -246,7 +246,10 @@ pool_bwd_event_kernel(const float* __restrict__ Cr /*[batch][512]*/, const float
 // owns hidden unit k: the block's rows of Cr are staged in shared memory once, the events of the block's pedestrians
 // (argmax pairs never leave a scene) accumulate into a shared dC tile that only thread k touches in column k, and the
 // tile is written once with plain stores.  dW2 / dAeff / dc0 live in registers for the whole kernel (dc0 = the column
-// sums of dC: no separate pass over the 500 MB matrix).  A block spanning more than PB_ROWS rows (a scene > 33) zeroes its
+// sums of dC: no separate pass over the 500 MB matrix).  (Tried and dropped: recomputing the block's Cr rows in the kernel
+// as a 3xTF32 warp GEMM from h instead of reading the GEMM's output -- correct, but the weight fragments do not fit in
+// registers next to the per-channel accumulators and streaming them from L1 made the kernel 1.47 -> 2.53 ms, more than
+// the 0.45 ms GEMM it removes.)  A block spanning more than PB_ROWS rows (a scene > 33) zeroes its
 // own rows and falls back to atomics.
 // ------------------------------------------------------------------------------------------------
 constexpr int PB_IB = 16;            // pedestrians whose scenes start in one block
