@@ -25,6 +25,7 @@
 // round trips; TMEM: 128 columns per group.  Every member of a group computes its group's rows of the inter level
 // (identical operand rows give identical accumulator rows), so no lane is ever predicated off and nothing is zeroed.  The weight images are built in-kernel from the fp32 parameters (a few
 // microseconds per CTA, overlapped across SMs) so the entry point keeps its stateless signature.
+#include <type_traits>
 #include "sgx_gat_fused.cuh"
 #include "sgx_graph_tc.cuh"
 
@@ -57,7 +58,8 @@ constexpr int OFF_W3 = OFF_W2 + 4 * K2 * N2;
 constexpr int OFF_W4 = OFF_W3 + 4 * K3 * N3;
 constexpr int OFF_W5 = OFF_W4 + 4 * K4 * N4;
 constexpr int OFF_BO = OFF_W5 + 4 * K5 * N5;          // float[32]: bo
-constexpr int OFF_WS = OFF_BO + 128;                  // float[8]: inverse weight scales; uint[8]: max |w| bits
+constexpr int OFF_WA = OFF_BO + 128;                  // float[2][16]: We ae1, We ae2 (the inter level's score vectors, fp32)
+constexpr int OFF_WS = OFF_WA + 128;                  // float[8]: inverse weight scales; uint[8]: max |w| bits
 constexpr int OFF_BAR = OFF_WS + 64;                  // GROUPS mbarriers + the TMEM base slot
 constexpr int OFF_GRP = OFF_BAR + 64;
 constexpr int ABUF = 20 * CORE;                       // A operand (K <= 80: 10 hi + 10 lo cores) / 72-wide fp32 rows
@@ -68,7 +70,7 @@ constexpr int STAGE_FLOATS = N1 * K1 + N2 * K2 + N3 * K3 + N4 * K4 + N5 * K5;
 static_assert(OFF_GRP % 128 == 0 && GRP_BYTES % 128 == 0, "operand buffers must stay 128-byte aligned");
 static_assert(STAGE_FLOATS * 4 <= GROUPS * GRP_BYTES, "the fp32 staging of the weight prep lives in the group buffers");
 static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory");
-static_assert(OFF_BAR % 16 == 0, "the prepared blob is copied in 16-byte words");
+static_assert(OFF_BAR % 16 == 0 && 8 * (GROUPS + 2) <= 64, "the prepared blob is one bulk copy; barriers + TMEM slot fit 64 bytes");
 
 // attention of one node over the lanes set in `mask`; neighbour rows in the core layout (quad f of lane q at
 // f * CORE + q * 16 from `wrows`, the first row of this warp), scores (s, t) per lane in `st`.  Same term order as
@@ -76,21 +78,44 @@ static_assert(OFF_BAR % 16 == 0, "the prepared blob is copied in 16-byte words")
 template <int F>
 __device__ __forceinline__ void attend_core(const uint8_t* __restrict__ wrows, const float2* __restrict__ st, uint32_t mask,
                                             float s_i, float alpha, float (&hp)[F]) {
+    // max_j lrelu(s_i + t_j) = lrelu(s_i + max_j t_j) for alpha >= 0 (both roundings are monotone): the first pass is one
+    // shared-memory read and one max per neighbour
     float m = -INFINITY;
-    for (uint32_t mm = mask; mm; mm &= mm - 1) m = fmaxf(m, lrelu(s_i + st[__ffs(mm) - 1].y, alpha));
+    if (alpha >= 0.f) {
+        for (uint32_t mm = mask; mm; mm &= mm - 1) m = fmaxf(m, st[__ffs(mm) - 1].y);
+        m = lrelu(s_i + m, alpha);
+    } else {
+        for (uint32_t mm = mask; mm; mm &= mm - 1) m = fmaxf(m, lrelu(s_i + st[__ffs(mm) - 1].y, alpha));
+    }
     float den = 0.f;
 #pragma unroll
     for (int f = 0; f < F; ++f) hp[f] = 0.f;
-    for (uint32_t mm = mask; mm; mm &= mm - 1) {
-        const int q = __ffs(mm) - 1;
-        const float w = fexp(lrelu(s_i + st[q].y, alpha) - m);
-        den += w;
-        const uint8_t* row = wrows + q * 16;
+    // two neighbours per trip: their score -> exp chains are independent, the sums keep the ascending-lane order
+    for (uint32_t mm = mask; mm;) {
+        const int q0 = __ffs(mm) - 1;
+        mm &= mm - 1;
+        const bool two = mm != 0u;
+        const int q1 = two ? __ffs(mm) - 1 : q0;
+        mm &= mm - 1;
+        const float w0 = fexp(lrelu(s_i + st[q0].y, alpha) - m);
+        const float w1 = fexp(lrelu(s_i + st[q1].y, alpha) - m);
+        const uint8_t* row0 = wrows + q0 * 16;
+        const uint8_t* row1 = wrows + q1 * 16;
+        den += w0;
 #pragma unroll
         for (int f = 0; f < F / 4; ++f) {
-            const float4 v = *reinterpret_cast<const float4*>(row + f * CORE);
-            hp[4 * f] = fmaf(w, v.x, hp[4 * f]); hp[4 * f + 1] = fmaf(w, v.y, hp[4 * f + 1]);
-            hp[4 * f + 2] = fmaf(w, v.z, hp[4 * f + 2]); hp[4 * f + 3] = fmaf(w, v.w, hp[4 * f + 3]);
+            const float4 v = *reinterpret_cast<const float4*>(row0 + f * CORE);
+            hp[4 * f] = fmaf(w0, v.x, hp[4 * f]); hp[4 * f + 1] = fmaf(w0, v.y, hp[4 * f + 1]);
+            hp[4 * f + 2] = fmaf(w0, v.z, hp[4 * f + 2]); hp[4 * f + 3] = fmaf(w0, v.w, hp[4 * f + 3]);
+        }
+        if (two) {
+            den += w1;
+#pragma unroll
+            for (int f = 0; f < F / 4; ++f) {
+                const float4 v = *reinterpret_cast<const float4*>(row1 + f * CORE);
+                hp[4 * f] = fmaf(w1, v.x, hp[4 * f]); hp[4 * f + 1] = fmaf(w1, v.y, hp[4 * f + 1]);
+                hp[4 * f + 2] = fmaf(w1, v.z, hp[4 * f + 2]); hp[4 * f + 3] = fmaf(w1, v.w, hp[4 * f + 3]);
+            }
         }
     }
     const float inv = 1.f / den;
@@ -222,6 +247,47 @@ __device__ __forceinline__ void wide_from_tmem(uint32_t d_mine, float sc, uint8_
         sv = make_float2(__uint_as_float(v3[0]) * sc, __uint_as_float(v3[1]) * sc);
     }
 }
+// the thread's 72 accumulator columns -> ELU -> the K = 80 operand of the next linear map; returns the inverse row scale.
+// Two passes over TMEM in blocks (never 72 live values): the row scale comes from a bound on max |ELU(v)| that needs no
+// exponential, v for v > 0 and min(|v|, 1) otherwise (within a factor 1.6 of the true maximum: at most one bit of the
+// fp16 headroom), then each block is read again, activated and split.
+__device__ __forceinline__ float wide_elu_to_operand(uint32_t d_mine, float sc, uint8_t* __restrict__ arow) {
+    float mx = 0.f;
+    {
+        uint32_t v0[32], v1[32], v2[8];
+        tmem_ld32(d_mine, v0);
+        tmem_ld32(d_mine + 32, v1);
+        tmem_ld8(d_mine + 64, v2);
+        tmem_wait_ld();
+        auto bound = [&](uint32_t raw) {
+            const float v = __uint_as_float(raw) * sc;
+            mx = fmaxf(mx, v > 0.f ? v : fminf(-v, 1.f));     // NaN rows: fmaxf drops the NaN, the values carry it
+        };
+#pragma unroll
+        for (int f = 0; f < 32; ++f) { bound(v0[f]); bound(v1[f]); }
+#pragma unroll
+        for (int f = 0; f < 8; ++f) bound(v2[f]);
+    }
+    const bool unscaled = GTC_FASTPATH && __all_sync(0xffffffffu, scale_free(mx));
+    float s = 1.f, inv = 1.f;
+    if (!unscaled) pow2_scale(mx, s, inv);
+    auto block = [&](auto tag, int col, int core) {
+        constexpr int NB = decltype(tag)::value;
+        uint32_t raw[NB];
+        if constexpr (NB == 32) tmem_ld32(d_mine + col, raw); else tmem_ld8(d_mine + col, raw);
+        tmem_wait_ld();
+        float h[NB];
+#pragma unroll
+        for (int f = 0; f < NB; ++f) h[f] = felu(__uint_as_float(raw[f]) * sc);
+        if (unscaled) write_core_block<NB, false>(arow, core, 10, h, 1.f); else write_core_block<NB, true>(arow, core, 10, h, s);
+    };
+    block(std::integral_constant<int, 32>{}, 0, 0);
+    block(std::integral_constant<int, 32>{}, 32, 4);
+    block(std::integral_constant<int, 8>{}, 64, 8);
+    *reinterpret_cast<uint4*>(arow + 9 * CORE) = make_uint4(0u, 0u, 0u, 0u);      // K padding 72..79
+    *reinterpret_cast<uint4*>(arow + 19 * CORE) = make_uint4(0u, 0u, 0u, 0u);
+    return inv;
+}
 // ... (16 + 2 columns) -> fp32 quads NCORE.. of its own row + (s, t)
 __device__ __forceinline__ void narrow_from_tmem(uint32_t d_mine, float sc, uint8_t* __restrict__ nrow, float2& sv) {
     uint32_t v0[16], v3[2];
@@ -249,6 +315,7 @@ gat_fused_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ lea
     const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
     uint8_t* smem = smem_raw + (sbase - smem_u32(smem_raw));
     float* s_bo = reinterpret_cast<float*>(smem + OFF_BO);
+    float* s_wa = reinterpret_cast<float*>(smem + OFF_WA);
     float* s_winv = reinterpret_cast<float*>(smem + OFF_WS);
     uint32_t* s_wmax = reinterpret_cast<uint32_t*>(smem + OFF_WS + 32);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -271,11 +338,17 @@ gat_fused_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ lea
         cs1 = chunk_scene[(tile + tile_step) * 4 + wq + 1];
     }
 
+    uint64_t* wbar = bars + GROUPS + 1;                      // completion of the prepared blob's bulk copy
     if (threadIdx.x == 0) {
         for (int g = 0; g < GROUPS; ++g) mbar_init(&bars[g], 1);
+        mbar_init(wbar, 1);
         fence_barrier_init();
+        if (prep != nullptr) {                               // in flight behind the TMEM allocation and the first tile's loads
+            mbar_expect_tx(wbar, OFF_BAR);
+            bulk_g2s(smem, prep, OFF_BAR, wbar);
+        }
     }
-    if (threadIdx.x < 8) s_wmax[threadIdx.x] = 0u;
+    if (prep == nullptr && threadIdx.x < 8) s_wmax[threadIdx.x] = 0u;      // (the blob copy owns the region otherwise)
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -287,12 +360,7 @@ gat_fused_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ lea
 
     // ---------------- weight images: copied from a prepared blob (sgx_gat_encoder_tc_prep, cached per weight version by
     // the host side), or built here: fp32 staging [n][k] (in the group buffers), per-matrix scale, hi/lo split ----------------
-    if (prep != nullptr) {
-        for (int e = threadIdx.x; e < OFF_BAR / 16; e += NTHREADS)
-            reinterpret_cast<uint4*>(smem)[e] = reinterpret_cast<const uint4*>(prep)[e];
-        fence_proxy_async();
-        __syncthreads();
-    } else {
+    if (prep == nullptr) {
         float* stage = reinterpret_cast<float*>(smem + OFF_GRP);
         constexpr int S1 = 0, S2 = S1 + N1 * K1, S3 = S2 + N2 * K2, S4 = S3 + N3 * K3, S5 = S4 + N4 * K4;
         for (int e = threadIdx.x; e < STAGE_FLOATS; e += NTHREADS) stage[e] = 0.f;
@@ -325,7 +393,10 @@ gat_fused_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ lea
 #pragma unroll
             for (int c = lane; c < HID; c += 32) part = fmaf(wrow[c], av[c], part);
             part = warp_sum(part);
-            if (lane == 0) put(first ? 0 : 2, (first ? S1 + (HID + which) * K1 : S3 + (HID + which) * K3) + k, part);
+            if (lane == 0) {
+                put(first ? 0 : 2, (first ? S1 + (HID + which) * K1 : S3 + (HID + which) * K3) + k, part);
+                if (!first) s_wa[which * OUT + k] = part;
+            }
         }
         for (int d = threadIdx.x; d < 4 * HID; d += NTHREADS) {
             const bool first = d < 2 * HID;
@@ -395,7 +466,6 @@ gat_fused_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ lea
     const uint32_t d_tmem = tmem + (uint32_t)grp * 128u;
     const uint32_t d_mine = d_tmem + ((uint32_t)(wq * 32) << 16);
     uint32_t parity = 0;
-    const float winv1 = s_winv[0], winv2 = s_winv[1], winv3 = s_winv[2], winv4 = s_winv[3], winv5 = s_winv[4];
 
     // hand the operand rows to the tensor core, wait for the accumulator
     auto run_layer = [&](auto issue) {
@@ -438,6 +508,8 @@ gat_fused_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ lea
     };
     Meta mt = load_meta(p0, p1 - p0);
     load_x(p0, p1 - p0);
+    if (prep != nullptr) mbar_wait(wbar, 0);
+    const float winv1 = s_winv[0], winv2 = s_winv[1], winv3 = s_winv[2], winv4 = s_winv[3], winv5 = s_winv[4];
 
     for (; tile < n_tiles; tile += tile_step) {
         const int np = p1 - p0;
@@ -515,26 +587,24 @@ gat_fused_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ lea
                     xg[4 * f + 2] = fmaf(inv_g, v.z, xg[4 * f + 2]); xg[4 * f + 3] = fmaf(inv_g, v.w, xg[4 * f + 3]);
                 }
             }
-            sc = row_to_operand<OUT, K3>(arow, xg) * winv3;
-        }
-        // ---- inter GAT, layer 1: Wh3 = Xg We (+ scores); the attention reads the LEADER rows of the scene, every member
-        //      of a group holds its leader's row and computes the same result ----
-        run_layer([&]() { issue_layer<K3, N3>(d_tmem, a_s, sbase + OFF_W3, bar); });
-        wide_from_tmem(d_mine, sc, arow, sv);
-        st[lane] = sv;
-        __syncwarp();
-#if GTC_HALVES
-        sc = wide_attend_to_operand(wrows_a, st, leader_mask, sv.x, alpha, arow, d_mine + 80) * winv4;
-#else
-        {
-            float hp[HID];
-            attend_core<HID>(wrows_a, st, leader_mask, sv.x, alpha, hp);
+            // ---- inter GAT, layer 1, aggregated BEFORE the linear map: sum_j a_ij (Xg_j We) = (sum_j a_ij Xg_j) We, so the
+            //      attention over the scene's leaders runs on the 16-wide Xg rows instead of the 72-wide Wh3 rows (4.5x fewer
+            //      FMAs and shared-memory reads in the kernel's heaviest loop).  The scores Xg . (We a) come straight from
+            //      the fp32 vectors the prep keeps; every member of a group holds its leader's row and computes the same
+            //      result. ----
+            float s3 = 0.f, t3 = 0.f;
 #pragma unroll
-            for (int f = 0; f < HID; ++f) hp[f] = felu(hp[f]);
+            for (int o = 0; o < OUT; ++o) { s3 = fmaf(xg[o], s_wa[o], s3); t3 = fmaf(xg[o], s_wa[OUT + o], t3); }
+            __syncwarp();                                    // every lane is done reading the x1 rows
+            store_core_row<OUT>(nrow, xg);
+            st[lane] = make_float2(s3, t3);
             __syncwarp();
-            sc = row_to_operand<HID, K4>(arow, hp) * winv4;
+            float xb[OUT];
+            attend_core<OUT>(wrows_n, st, leader_mask, s3, alpha, xb);
+            sc = row_to_operand<OUT, K3>(arow, xb) * winv3;
         }
-#endif
+        run_layer([&]() { issue_layer<K3, N3>(d_tmem, a_s, sbase + OFF_W3, bar); });
+        sc = wide_elu_to_operand(d_mine, sc, arow) * winv4;
         // ---- inter GAT, out_att: Wh4 = hp Weo (+ scores) ----
         run_layer([&]() { issue_layer<K4, N4>(d_tmem, a_s, sbase + OFF_W4, bar); });
         narrow_from_tmem(d_mine, sc, nrow, sv);

@@ -51,7 +51,7 @@ struct Cfg {
                          STAGE_FLOATS = S5 + N5 * K5;
     static_assert(STAGE_FLOATS * 4 <= GROUPS * GRP_BYTES, "the fp32 staging of the weight prep lives in the group buffers");
     static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory");
-    static_assert(OFF_BAR % 16 == 0, "the prepared blob is copied in 16-byte words");
+    static_assert(OFF_BAR % 16 == 0 && 8 * (GROUPS + 2) <= 64, "the prepared blob is one bulk copy; barriers + TMEM slot fit 64 bytes");
     static_assert(FIN <= 32 && FIN % 4 == 0 && IN % 4 == 0 && IN <= 48, "dims");
 };
 
@@ -142,11 +142,17 @@ gcn_fused_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ lea
         cs1 = chunk_scene[(tile + tile_step) * 4 + wq + 1];
     }
 
+    uint64_t* wbar = bars + GROUPS + 1;                      // completion of the prepared blob's bulk copy
     if (threadIdx.x == 0) {
         for (int g = 0; g < GROUPS; ++g) mbar_init(&bars[g], 1);
+        mbar_init(wbar, 1);
         fence_barrier_init();
+        if (prep != nullptr) {                               // in flight behind the TMEM allocation and the first tile's loads
+            mbar_expect_tx(wbar, C::OFF_BAR);
+            bulk_g2s(smem, prep, C::OFF_BAR, wbar);
+        }
     }
-    if (threadIdx.x < 8) s_wmax[threadIdx.x] = 0u;
+    if (prep == nullptr && threadIdx.x < 8) s_wmax[threadIdx.x] = 0u;      // (the blob copy owns the region otherwise)
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -158,12 +164,7 @@ gcn_fused_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ lea
 
     // ---------------- weight images: copied from a prepared blob (sgx_gcn_module_tc_prep, cached per weight version by
     // the host side), or built here: fp32 staging [n][k] (in the group buffers), per-matrix scale, hi/lo split ----------------
-    if (prep != nullptr) {
-        for (int e = threadIdx.x; e < C::OFF_BAR / 16; e += NTHREADS)
-            reinterpret_cast<uint4*>(smem)[e] = reinterpret_cast<const uint4*>(prep)[e];
-        fence_proxy_async();
-        __syncthreads();
-    } else {
+    if (prep == nullptr) {
         float* stage = reinterpret_cast<float*>(smem + C::OFF_GRP);
         for (int e = threadIdx.x; e < C::STAGE_FLOATS; e += NTHREADS) stage[e] = 0.f;
         __syncthreads();
@@ -214,7 +215,6 @@ gcn_fused_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ lea
     const uint32_t d_tmem = tmem + (uint32_t)grp * 128u;
     const uint32_t d_mine = d_tmem + ((uint32_t)(wq * 32) << 16);
     uint32_t parity = 0;
-    const float winv1 = s_winv[0], winv2 = s_winv[1], winv3 = s_winv[2], winv4 = s_winv[3], winv5 = s_winv[4];
 
     auto run_layer = [&](auto issue) {
         fence_proxy_async();
@@ -254,6 +254,8 @@ gcn_fused_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ lea
     };
     Meta mt = load_meta(p0, p1 - p0);
     load_x(p0, p1 - p0);
+    if (prep != nullptr) mbar_wait(wbar, 0);
+    const float winv1 = s_winv[0], winv2 = s_winv[1], winv3 = s_winv[2], winv4 = s_winv[3], winv5 = s_winv[4];
 
     for (; tile < n_tiles; tile += tile_step) {
         const int np = p1 - p0;
