@@ -32,9 +32,10 @@ struct GatGrad {                             // per-CTA gradient block == layout
     float Wi[GB_IN * HID], ai[2 * HID], Wio[HID * OUT], aio[2 * OUT];
     float We[OUT * HID], ae[2 * HID], Weo[HID * OUT], aeo[2 * OUT];
     float Wo[GB_FIN * 2 * OUT], bo[GB_FIN];
+    float du[2 * OUT];                       // d(We ae1), d(We ae2): the inter level's score vectors (see the reduce kernel)
 };
 constexpr int GB_GRAD_FLOATS = sizeof(GatGrad) / sizeof(float);
-struct GatAvec { float ai[2 * HID], aio[2 * OUT], ae[2 * HID], aeo[2 * OUT]; };
+struct GatAvec { float ai[2 * HID], aio[2 * OUT], ae[2 * HID], aeo[2 * OUT], ue[2 * OUT]; };   // ue = (We ae1, We ae2)
 
 // per-warp scratch (floats): two 72-wide row buffers, four 16-wide, the grad_out rows, scores / statistics
 constexpr int GB_SCRATCH = 2 * 32 * RS + 4 * 32 * RA + 32 * RG + 2 * 32 * 2 + 32 * 4 + 32 * 2 + 8;   // + pad: the d(a) GEMM reads its
@@ -167,8 +168,10 @@ gat_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout
     __threadfence();
 #endif
     __syncthreads();
+    if (threadIdx.x < 2 * OUT) av.ue[threadIdx.x] = w.We[(threadIdx.x % OUT) * SW1 + HID + threadIdx.x / OUT];
+    __syncthreads();
 
-    float* P = bufs + warp * GB_SCRATCH;                 // [32][RS]  x / Wh1 / Wh3
+    float* P = bufs + warp * GB_SCRATCH;                 // [32][RS]  x / Wh1; [32][RA] xbar of the inter level
     float* Q = P + 32 * RS;                              // [32][RS]  x1a / y3 -> d(hp) -> dWh of the 72-wide layers
     float* Xg = Q + 32 * RS;                             // [32][RA]  pooled group state (leader slots)
     float* A = Xg + 32 * RA;                             // [32][RA]  Wh2 / Wh4
@@ -210,6 +213,9 @@ gat_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout
     auto grad_to = [&](float* dst, int ld, int M, int N) {
         return [=](int m0, int nt, const float (&c)[4]) {
             const int m = m0 + g, n = nt * 8 + 2 * t;
+#ifdef GB_EXPERIMENT_NO_ATOMICS
+            if (c[0] == 123.456f)
+#endif
             if (n < N) {
                 if (m < M) { atomicAdd(dst + m * ld + n, c[0]); if (n + 1 < N) atomicAdd(dst + m * ld + n + 1, c[1]); }
                 if (m + 8 < M) { atomicAdd(dst + (m + 8) * ld + n, c[2]); if (n + 1 < N) atomicAdd(dst + (m + 8) * ld + n + 1, c[3]); }
@@ -317,19 +323,32 @@ gat_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout
         }
         __syncwarp();
         // =============== forward recompute, part 2 (inter level, leaders): Xg -> y3 -> Yg ===============
-        warp_gemm_3xtf32<OUT, HID / 8 + 1, RA, SW1>(Xg, w.We, lane, wide_to(P, stA));      // Wh3 -> P, (s3, t3) -> stA
+        // layer 3 aggregated BEFORE its linear map: sum_j a_ij (Xg_j We) = (sum_j a_ij Xg_j) We = xbar We, so the attention
+        // over the scene's leaders and its whole backward run on 16-wide rows instead of 72-wide ones; the scores are
+        // Xg . (We ae1), Xg . (We ae2) with the two vectors the weight block already holds as its score columns
         {
-            float hp[HID];
+            float xg[OUT];
+            load_row<OUT>(Xg + lane * RA, xg);
+            float s3 = 0.f, t3 = 0.f;
 #pragma unroll
-            for (int f = 0; f < HID; ++f) hp[f] = 0.f;
-            if (is_lead) {
-                attend_mask<HID, RS>(P, stA, leader_mask, stA[lane].x, alpha, hp);
-#pragma unroll
-                for (int f = 0; f < HID; ++f) hp[f] = felu(hp[f]);
-            }
-            store_row<HID>(Q + lane * RS, hp);              // y3 (zero rows off the leaders)
+            for (int o = 0; o < OUT; ++o) { s3 = fmaf(xg[o], av.ue[o], s3); t3 = fmaf(xg[o], av.ue[OUT + o], t3); }
+            stA[lane] = make_float2(s3, t3);
         }
         __syncwarp();
+        {
+            float xb[OUT];
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) xb[o] = 0.f;
+            if (is_lead) attend_mask<OUT, RA>(Xg, stA, leader_mask, stA[lane].x, alpha, xb);
+            store_row<OUT>(P + lane * RA, xb);              // xbar (zero rows off the leaders)
+        }
+        __syncwarp();
+        // y3 = elu(xbar We) -> Q (zero rows off the leaders)
+        warp_gemm_3xtf32<OUT, HID / 8, RA, SW1>(P, w.We, lane, [&](int mt, int nt, const float (&c)[4]) {
+            const int r = mt * 16 + g, col = nt * 8 + 2 * t;
+            *reinterpret_cast<float2*>(Q + r * RS + col) = make_float2(felu(c[0]), felu(c[1]));
+            *reinterpret_cast<float2*>(Q + (r + 8) * RS + col) = make_float2(felu(c[2]), felu(c[3]));
+        });
         warp_gemm_3xtf32<HID, OUT / 8 + 1, RS, SW2>(Q, w.Weo, lane, narrow_to(A, stB));    // Wh4 -> A, (s4, t4) -> stB
         float hp4[OUT], yg[OUT];
 #pragma unroll
@@ -407,34 +426,34 @@ gat_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout
             *q0 = make_float2(c[0] * (y0.x > 0.f ? 1.f : y0.x + 1.f), c[1] * (y0.y > 0.f ? 1.f : y0.y + 1.f));
             *q1 = make_float2(c[2] * (y1.x > 0.f ? 1.f : y1.x + 1.f), c[3] * (y1.y > 0.f ? 1.f : y1.y + 1.f));
         });
-        // =============== inter layer 1 (layer 3) backward ===============
+        // =============== inter layer 1 (layer 3) backward, on the aggregated form ===============
+        // Q = d(hp3):  d(We) += xbar^T d(hp3),  d(xbar) = d(hp3) We^T -> D
+        warp_gemm_3xtf32_at<OUT, HID / 8, RA, RS>(P, Q, lane, grad_to(gr.We, HID, OUT, HID));
+        warp_gemm_3xtf32_bt<HID, OUT / 8, RS, SW1>(Q, w.We, lane, narrow_to(D, nullptr));
         ds = 0.f; dt = 0.f;
         {
-            float dh[HID];
-            load_row<HID>(Q + lane * RS, dh);
+            float dxb[OUT];
+            load_row<OUT>(D + lane * RA, dxb);
             if (is_lead) {
                 float4 s3;
-                att_bwd_row<HID, RS>(P, stA, leader_mask, stA[lane].x, alpha, dh, s3, ds);
+                att_bwd_row<OUT, RA>(Xg, stA, leader_mask, stA[lane].x, alpha, dxb, s3, ds);
                 stat[lane] = s3;
             }
         }
         __syncwarp();
         {
-            float dwh[HID];
+            float dxg[OUT];                                 // d(Xg_j) = sum_i a_ij d(xbar_i) + ds_j We ae1 + dt_j We ae2
 #pragma unroll
-            for (int f = 0; f < HID; ++f) dwh[f] = 0.f;
+            for (int o = 0; o < OUT; ++o) dxg[o] = 0.f;
             if (is_lead)
-                att_bwd_col<HID, RS, RS>(P + lane * RS, Q, stA, stat, leader_mask, stA[lane].y, ds, alpha, av.ae, dwh, dt);
+                att_bwd_col<OUT, RA, RA>(Xg + lane * RA, D, stA, stat, leader_mask, stA[lane].y, ds, alpha, av.ue, dxg, dt);
             dstb[lane] = make_float2(is_lead ? ds : 0.f, is_lead ? dt : 0.f);
-            __syncwarp();
-            store_row<HID>(Q + lane * RS, dwh);             // dWh3
+            __syncwarp();                                   // every leader has read the d(xbar) rows
+            store_row<OUT>(D + lane * RA, dxg);             // d(Xg)
         }
         __syncwarp();
-        warp_gemm_3xtf32_at<OUT, HID / 8, RA, RS>(Xg, Q, lane, grad_to(gr.We, HID, OUT, HID));      // d(We) += Xg^T dWh3
-        warp_gemm_3xtf32_at<HID, 1, RS, 2>(P, reinterpret_cast<const float*>(dstb), lane, avec_to(gr.ae, HID));
-        __syncwarp();
-        // d(Xg) = dWh3 We^T -> D
-        warp_gemm_3xtf32_bt<HID, OUT / 8, RS, SW1>(Q, w.We, lane, narrow_to(D, nullptr));
+        // d(We ae1), d(We ae2) [2][16] += (ds, dt)^T Xg: folded into d(We) and d(ae) by the reduce kernel (both are linear)
+        warp_gemm_3xtf32_at<OUT, 1, RA, 2>(Xg, reinterpret_cast<const float*>(dstb), lane, avec_to(gr.du, OUT));
         // pool backward: Xg[l] = sum_{i in g} x1_i / |g|
         if (live) {
 #pragma unroll
@@ -538,21 +557,40 @@ gat_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout
 #endif
 }
 
-// sums the per-CTA gradient blocks in block order (deterministic) and scatters the ten tensors
-__global__ void gat_bwd_reduce_kernel(const float* __restrict__ partials, int n_blocks, float* gWi, float* gai, float* gWio,
+// sums the per-CTA gradient blocks in block order (deterministic) and scatters the ten tensors.  The inter level's first
+// layer is differentiated in its aggregated form, where the scores depend on the parameters through u = We [ae1 | ae2]:
+// with du = the summed d(u), d(We) += du1 ae1^T + du2 ae2^T and d(ae) = We^T du.
+__global__ void gat_bwd_reduce_kernel(const float* __restrict__ partials, int n_blocks, const float* __restrict__ We,
+                                      const float* __restrict__ ae, float* gWi, float* gai, float* gWio,
                                       float* gaio, float* gWe, float* gae, float* gWeo, float* gaeo, float* gWo, float* gbo) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= GB_GRAD_FLOATS) return;
-    float s = 0.f;
-    for (int k = 0; k < n_blocks; ++k) s += partials[(int64_t)k * GB_GRAD_FLOATS + e];
     constexpr int o1 = GB_IN * HID, o2 = o1 + 2 * HID, o3 = o2 + HID * OUT, o4 = o3 + 2 * OUT, o5 = o4 + OUT * HID,
-                  o6 = o5 + 2 * HID, o7 = o6 + HID * OUT, o8 = o7 + 2 * OUT, o9 = o8 + GB_FIN * 2 * OUT;
+                  o6 = o5 + 2 * HID, o7 = o6 + HID * OUT, o8 = o7 + 2 * OUT, o9 = o8 + GB_FIN * 2 * OUT, o10 = o9 + GB_FIN;
+    auto total = [&](int idx) {
+        float s = 0.f;
+        for (int k = 0; k < n_blocks; ++k) s += partials[(int64_t)k * GB_GRAD_FLOATS + idx];
+        return s;
+    };
+    __shared__ float du[2 * OUT];                           // every block sums the 32 d(u) entries for itself
+    if (threadIdx.x < 2 * OUT) du[threadIdx.x] = total(o10 + threadIdx.x);
+    __syncthreads();
+    if (e >= o10) return;
+    if (e >= o5 && e < o6) {                                // d(ae)[which][f] = sum_k We[k][f] du[which][k]
+        const int which = (e - o5) / HID, f = (e - o5) % HID;
+        float s = 0.f;
+        for (int k = 0; k < OUT; ++k) s = fmaf(We[k * HID + f], du[which * OUT + k], s);
+        gae[e - o5] = s;
+        return;
+    }
+    float s = total(e);
     if (e < o1) gWi[e] = s;
     else if (e < o2) gai[e - o1] = s;
     else if (e < o3) gWio[e - o2] = s;
     else if (e < o4) gaio[e - o3] = s;
-    else if (e < o5) gWe[e - o4] = s;
-    else if (e < o6) gae[e - o5] = s;
+    else if (e < o5) {
+        const int k = (e - o4) / HID, f = (e - o4) % HID;
+        gWe[e - o4] = s + du[k] * ae[f] + du[OUT + k] * ae[HID + f];
+    }
     else if (e < o7) gWeo[e - o6] = s;
     else if (e < o8) gaeo[e - o7] = s;
     else if (e < o9) gWo[e - o8] = s;
@@ -594,7 +632,7 @@ extern "C" int sgx_gat_encoder_fused_bwd(const float* x, const float* grad_out, 
                                                             chunk_scene, (int)n_chunks, Wi, ai, Wio, aio, We, ae, Weo, aeo,
                                                             Wo, bo, alpha, grad_x, partials);
     SGX_LAUNCH_CHECK();
-    gat_bwd_reduce_kernel<<<blocks_for(GB_GRAD_FLOATS, 256), 256, 0, st>>>(partials, grid, grad_Wi, grad_ai, grad_Wio,
+    gat_bwd_reduce_kernel<<<blocks_for(GB_GRAD_FLOATS, 256), 256, 0, st>>>(partials, grid, We, ae, grad_Wi, grad_ai, grad_Wio,
                                                                            grad_aio, grad_We, grad_ae, grad_Weo, grad_aeo,
                                                                            grad_Wo, grad_bo);
     SGX_LAUNCH_CHECK();
