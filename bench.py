@@ -733,10 +733,32 @@ def hot_path_op_numbers(dev, n_scenes, hbm, flush):
             xg.grad = None
             (mod(xg, sse, pos, lab) * up).sum().backward()
         fb_ms = timed(fb)
+        # the backward operator alone (no autograd engine around it: the module-level number above carries ~0.3 ms of
+        # host time -- engine thread hand-over, ten gradient allocations -- that the GPU waits for at this size)
+        from group_gan_gcn_gat_b200 import ops
+        from group_gan_gcn_gat_b200.modules import _groups_for
+        from group_gan_gcn_gat_b200.schedule import get_schedule
+        sched = get_schedule(sse, dev)
+        leader, gsize, _gid, ngrp = _groups_for(sched, lab)
+        chunk_scene, n_chunks = sched.chunks(32)
+        with torch.no_grad():
+            if name == 'GATEncoder':
+                ws = (*mod.gat_intra.stacked(), *mod.gat_inter.stacked(), mod.out_embedding.weight, mod.out_embedding.bias)
+                b_only = timed(lambda: ops._DIRECT[ops.gat_encoder_bwd](
+                    x, up, leader, gsize, sched.ped_start, sched.ped_end, sched.n_scenes, *ws, 0.2, sched.scene_start,
+                    chunk_scene, n_chunks, 32, int(sched.max_n)))
+            else:
+                ws = (mod.gcn_intra.W[0], mod.gcn_intra.W[1], mod.gcn_inter.W[0], mod.gcn_inter.W[1],
+                      mod.out_embedding.weight, mod.out_embedding.bias)
+                b_only = timed(lambda: ops._DIRECT[ops.gcn_module_bwd](
+                    x, up, leader, gsize, sched.ped_start, sched.ped_end, sched.scene_start, ngrp, *ws, chunk_scene, n_chunks))
         fwd_b, bwd_b = 260 * n + 16 * n_scenes, 420 * n
         rows.append({'op': name + ' fwd (%s, group structure in-kernel)' % kern, 'bound': 'hbm', 'peds': n, 'ms': f_ms,
                      'algorithmic_bytes': fwd_b, 'achieved': fwd_b / f_ms / 1e6, 'peak': hbm, 'unit': 'GB/s',
                      'frac': fwd_b / f_ms / 1e6 / hbm})
+        rows.append({'op': name + ' bwd (operator call: single-launch backward kernel + reduction)', 'bound': 'hbm', 'peds': n,
+                     'ms': b_only, 'algorithmic_bytes': bwd_b, 'achieved': bwd_b / b_only / 1e6, 'peak': hbm, 'unit': 'GB/s',
+                     'frac': bwd_b / b_only / 1e6 / hbm})
         rows.append({'op': name + ' fwd + bwd (autograd: forward, group_ids, single-launch backward, reduction)',
                      'bound': 'hbm', 'peds': n, 'ms': fb_ms, 'algorithmic_bytes': fwd_b + bwd_b,
                      'achieved': (fwd_b + bwd_b) / fb_ms / 1e6, 'peak': hbm, 'unit': 'GB/s',

@@ -892,6 +892,11 @@ gat_fused_mma_kernel(const float* __restrict__ x, const int32_t* __restrict__ le
             st[r + 8] = make_float2(c[2], c[3]);
         }
     };
+    auto store_wide_elu = [&](int mt, int nt, const float (&c)[4]) {
+        const int r = mt * 16 + g;
+        *reinterpret_cast<float2*>(Bf + r * RS + nt * 8 + 2 * t) = make_float2(felu(c[0]), felu(c[1]));
+        *reinterpret_cast<float2*>(Bf + (r + 8) * RS + nt * 8 + 2 * t) = make_float2(felu(c[2]), felu(c[3]));
+    };
     auto store_narrow = [&](int mt, int nt, const float (&c)[4]) {
         const int r = mt * 16 + g;
         if (nt < OUT / 8) {
@@ -971,23 +976,26 @@ gat_fused_mma_kernel(const float* __restrict__ x, const int32_t* __restrict__ le
                 }
             }
             store_row<OUT>(A + lane * RA, xg);
+            // scores of the inter level's first layer straight from Xg: s = Xg . (We a1), t = Xg . (We a2) -- the two vectors
+            // are the score columns of the weight block
+            float s3 = 0.f, t3 = 0.f;
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) { s3 = fmaf(xg[o], w.We[o * SW1 + HID], s3); t3 = fmaf(xg[o], w.We[o * SW1 + HID + 1], t3); }
+            st[lane] = make_float2(s3, t3);
         }
         __syncwarp();
-        // ---- inter GAT, layer 1 over the leader slots: Wh3 = Xg We (+ scores) -> Bf rows ----
-        warp_gemm_3xtf32<OUT, HID / 8 + 1, RA, SW1>(A, w.We, lane, store_wide);
+        // ---- inter GAT, layer 1 over the leader slots, aggregated BEFORE its linear map: sum_j a_ij (Xg_j We) =
+        //      (sum_j a_ij Xg_j) We, so the attention runs on the 16-wide Xg rows; hp = elu(xbar We) -> Bf rows ----
         {
-            float hp[HID];
+            float xb[OUT];
 #pragma unroll
-            for (int f = 0; f < HID; ++f) hp[f] = 0.f;
-            if (is_lead) {
-                attend_mask<HID, RS>(Bf, st, leader_mask, st[lane].x, alpha, hp);
-#pragma unroll
-                for (int f = 0; f < HID; ++f) hp[f] = felu(hp[f]);
-            }
-            __syncwarp();
-            store_row<HID>(Bf + lane * RS, hp);
+            for (int o = 0; o < OUT; ++o) xb[o] = 0.f;
+            if (is_lead) attend_mask<OUT, RA>(A, st, leader_mask, st[lane].x, alpha, xb);
+            __syncwarp();                                    // every leader has read the Xg rows
+            store_row<OUT>(A + lane * RA, xb);
         }
         __syncwarp();
+        warp_gemm_3xtf32<OUT, HID / 8, RA, SW1>(A, w.We, lane, store_wide_elu);
         // ---- inter GAT, out_att: Wh4 = hp Weo (+ scores) -> A rows ----
         warp_gemm_3xtf32<HID, OUT / 8 + 1, RS, SW2>(Bf, w.Weo, lane, store_narrow);
         {
@@ -1088,6 +1096,11 @@ gat_fused_mma64_kernel(const float* __restrict__ x, const int32_t* __restrict__ 
             st[r + 8] = make_float2(c[2], c[3]);
         }
     };
+    auto store_wide_elu = [&](int mt, int nt, const float (&c)[4]) {
+        const int r = mt * 16 + g;
+        *reinterpret_cast<float2*>(Bf + r * RS + nt * 8 + 2 * t) = make_float2(felu(c[0]), felu(c[1]));
+        *reinterpret_cast<float2*>(Bf + (r + 8) * RS + nt * 8 + 2 * t) = make_float2(felu(c[2]), felu(c[3]));
+    };
     auto store_narrow = [&](int mt, int nt, const float (&c)[4]) {
         const int r = mt * 16 + g;
         if (nt < OUT / 8) {
@@ -1183,27 +1196,27 @@ gat_fused_mma64_kernel(const float* __restrict__ x, const int32_t* __restrict__ 
                 }
             }
             store_row<OUT>(A + (lane + 32 * r) * RA, xg);
+            float s3 = 0.f, t3 = 0.f;                        // scores straight from Xg (see gat_fused_mma_kernel)
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) { s3 = fmaf(xg[o], w.We[o * SW1 + HID], s3); t3 = fmaf(xg[o], w.We[o * SW1 + HID + 1], t3); }
+            st[lane + 32 * r] = make_float2(s3, t3);
         }
         __syncwarp();
-        // ---- inter GAT ----
-        warp_gemm_3xtf32<OUT, HID / 8 + 1, RA, SW1, 4>(A, w.We, lane, store_wide);
+        // ---- inter GAT, first layer aggregated before its linear map ----
         {
-            float hp[2][HID];
+            float xb[2][OUT];
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
 #pragma unroll
-                for (int f = 0; f < HID; ++f) hp[r][f] = 0.f;
-                if (is_lead[r]) {
-                    attend_mask64<HID, RS>(Bf, st, leader_mask[r], st[lane + 32 * r].x, alpha, hp[r]);
-#pragma unroll
-                    for (int f = 0; f < HID; ++f) hp[r][f] = felu(hp[r][f]);
-                }
+                for (int o = 0; o < OUT; ++o) xb[r][o] = 0.f;
+                if (is_lead[r]) attend_mask64<OUT, RA>(A, st, leader_mask[r], st[lane + 32 * r].x, alpha, xb[r]);
             }
             __syncwarp();
 #pragma unroll
-            for (int r = 0; r < 2; ++r) store_row<HID>(Bf + (lane + 32 * r) * RS, hp[r]);
+            for (int r = 0; r < 2; ++r) store_row<OUT>(A + (lane + 32 * r) * RA, xb[r]);
         }
         __syncwarp();
+        warp_gemm_3xtf32<OUT, HID / 8, RA, SW1, 4>(A, w.We, lane, store_wide_elu);
         warp_gemm_3xtf32<HID, OUT / 8 + 1, RS, SW2, 4>(Bf, w.Weo, lane, store_narrow);
         {
             float yg[2][OUT];

@@ -22,9 +22,9 @@
 namespace sgx {
 
 #ifndef GB_GLOBAL_GRADS
-#define GB_GLOBAL_GRADS 1            // 1: the CTA's gradient block lives in its HBM partial (red.global), 5 warps per SM;
-#endif                               // 0: in shared memory (30 KB), 4 warps per SM
-constexpr int GB_WARPS = GB_GLOBAL_GRADS ? 5 : 4;
+#define GB_GLOBAL_GRADS 1            // 1: the CTA's gradient block lives in its HBM partial (red.global), 6 warps per SM;
+#endif                               // 0: in shared memory (30 KB), 5 warps per SM
+constexpr int GB_WARPS = GB_GLOBAL_GRADS ? 6 : 5;
 constexpr int GB_IN = 40, GB_FIN = 24;
 constexpr int RG = 28;                       // row stride of the grad_out rows (24 wide): conflict-free A fragments
 
@@ -37,8 +37,11 @@ struct GatGrad {                             // per-CTA gradient block == layout
 constexpr int GB_GRAD_FLOATS = sizeof(GatGrad) / sizeof(float);
 struct GatAvec { float ai[2 * HID], aio[2 * OUT], ae[2 * HID], aeo[2 * OUT], ue[2 * OUT]; };   // ue = (We ae1, We ae2)
 
-// per-warp scratch (floats): two 72-wide row buffers, four 16-wide, the grad_out rows, scores / statistics
-constexpr int GB_SCRATCH = 2 * 32 * RS + 4 * 32 * RA + 32 * RG + 2 * 32 * 2 + 32 * 4 + 32 * 2 + 8;   // + pad: the d(a) GEMM reads its
+// per-warp scratch (floats): two 72-wide row buffers, four 16-wide, scores / statistics.  The grad_out rows live in the
+// tail of the first wide buffer while it holds nothing wide (between the first layer's attention and the reload of x
+// for the intra level's backward): 31 KB per warp instead of 34.6 KB = one more warp per SM, and the kernel is bound by
+// exactly that (1.28 warps per scheduler, profiles/r02_gat_tc_source_hotspots.md).
+constexpr int GB_SCRATCH = 2 * 32 * RS + 4 * 32 * RA + 2 * 32 * 2 + 32 * 4 + 32 * 2 + 8;   // + pad: the d(a) GEMM reads its
                                              // 2-wide right operand as 8 columns (the extra ones are dropped)
 
 __device__ __forceinline__ float lrelu_grad(float pre, float alpha) { return pre > 0.f ? 1.f : alpha; }
@@ -177,8 +180,8 @@ gat_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout
     float* A = Xg + 32 * RA;                             // [32][RA]  Wh2 / Wh4
     float* B = A + 32 * RA;                              // [32][RA]  x1 / dx2 / d(hp) -> dWh of the 16-wide layers
     float* D = B + 32 * RA;                              // [32][RA]  Yg / x2 / dXg
-    float* G = D + 32 * RA;                              // [32][RG]  grad_out rows
-    float2* stA = reinterpret_cast<float2*>(G + 32 * RG);   // (s, t) of the 72-wide layer being processed
+    float* G = P + 32 * RA;                              // [32][RG]  grad_out rows, in the tail of P (behind xbar)
+    float2* stA = reinterpret_cast<float2*>(D + 32 * RA);   // (s, t) of the 72-wide layer being processed
     float2* stB = stA + 32;                              // (s, t) of the 16-wide layer
     float4* stat = reinterpret_cast<float4*>(stB + 32);  // (m, 1/den, c) per row of the layer in its backward
     float2* dstb = reinterpret_cast<float2*>(stat + 32); // (ds, dt) per row: right operand of the d(a) GEMM
@@ -259,28 +262,11 @@ gat_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout
             for (int c = 0; c < IN / 4; ++c) reinterpret_cast<float4*>(P + lane * RS)[c] = xv[c];
         };
         load_x();
-        {                                                   // grad_out rows -> G
-            float4 gv[FIN / 4];
-#pragma unroll
-            for (int c = 0; c < FIN / 4; ++c) gv[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (live) {
-                const float4* gp = reinterpret_cast<const float4*>(gout + (int64_t)p * FIN);
-#pragma unroll
-                for (int c = 0; c < FIN / 4; ++c) gv[c] = gp[c];
-            }
-#pragma unroll
-            for (int c = 0; c < FIN / 4; ++c) reinterpret_cast<float4*>(G + lane * RG)[c] = gv[c];
-        }
         const bool is_lead = live && (my_lead == lane);
         const uint32_t group_mask = __match_any_sync(0xffffffffu, live ? my_lead : 32 + lane);
         const uint32_t scene_mask = (e >= 32 ? 0xffffffffu : ((1u << e) - 1u)) & ~((1u << b) - 1u);
         const uint32_t leader_mask = __ballot_sync(0xffffffffu, is_lead) & scene_mask;
         __syncwarp();
-        if (lane < FIN) {                                   // d(bo) = column sums of the grad_out rows
-            float sgo = 0.f;
-            for (int r = 0; r < 32; ++r) sgo += G[r * RG + lane];
-            atomicAdd(&gr.bo[lane], sgo);
-        }
 
         // =============== forward recompute, part 1: x -> x1 -> Xg ===============
         warp_gemm_3xtf32<IN, HID / 8 + 1, RS, SW1>(P, w.Wi, lane, wide_to(P, stA));
@@ -296,6 +282,25 @@ gat_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout
             store_row<HID>(Q + lane * RS, hp);              // x1a
         }
         __syncwarp();
+        // the Wh1 rows in P are dead until the intra level's backward reloads x: the grad_out rows move into P's tail
+        {
+            float4 gv[FIN / 4];
+#pragma unroll
+            for (int c = 0; c < FIN / 4; ++c) gv[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live) {
+                const float4* gp = reinterpret_cast<const float4*>(gout + (int64_t)p * FIN);
+#pragma unroll
+                for (int c = 0; c < FIN / 4; ++c) gv[c] = gp[c];
+            }
+#pragma unroll
+            for (int c = 0; c < FIN / 4; ++c) reinterpret_cast<float4*>(G + lane * RG)[c] = gv[c];
+        }
+        __syncwarp();
+        if (lane < FIN) {                                   // d(bo) = column sums of the grad_out rows
+            float sgo = 0.f;
+            for (int r = 0; r < 32; ++r) sgo += G[r * RG + lane];
+            atomicAdd(&gr.bo[lane], sgo);
+        }
         warp_gemm_3xtf32<HID, OUT / 8 + 1, RS, SW2>(Q, w.Wio, lane, narrow_to(A, stB));
         float x1[OUT];
 #pragma unroll

@@ -21,9 +21,9 @@ namespace gcnb {
 
 constexpr int HID = 72, OUT = 16;
 #ifndef GCB_GLOBAL_GRADS
-#define GCB_GLOBAL_GRADS 1           // 1: the CTA's gradient block lives in its HBM partial (red.global), 5 warps per SM;
-#endif                               // 0: in shared memory (28 KB), 4 warps per SM
-constexpr int WARPS = GCB_GLOBAL_GRADS ? 5 : 4;
+#define GCB_GLOBAL_GRADS 1           // 1: the CTA's gradient block lives in its HBM partial (red.global), 6 warps per SM;
+#endif                               // 0: in shared memory (28 KB), 5 warps per SM
+constexpr int WARPS = GCB_GLOBAL_GRADS ? 6 : 5;
 constexpr int RS = 76;                 // 72-wide rows
 constexpr int RA = 20;                 // 16-wide rows
 constexpr int SWW = 72;                // W0 / V0 blocks [K][72]
@@ -32,10 +32,12 @@ constexpr int SWN = 24;                // W1 / V1 blocks [72][16 -> 24]
 template <int IN, int FIN>
 struct Cfg {
     static constexpr int SWO = (FIN % 32 == 0) ? FIN + 8 : FIN;       // Wo^T block [32][SWO]
-    static constexpr int RG = FIN + 4;                                // grad_out rows
+    static constexpr int RG = RS;                                     // grad_out rows: columns 40.. of the P rows (m1 and dM1
+                                                                      // use columns < 40), so they cost no scratch of their own
+    static_assert(IN <= 40 && 40 + FIN <= RS, "grad_out rows live behind the m1 columns of P");
     static constexpr int WFLOATS = IN * SWW + 2 * HID * SWN + OUT * SWW + 2 * OUT * SWO;
     static constexpr int GRAD_FLOATS = IN * HID + HID * OUT + OUT * HID + HID * OUT + FIN * 2 * OUT + FIN;   // W0 W1 V0 V1 Wo bo
-    static constexpr int SCRATCH = 2 * 32 * RS + 5 * 32 * RA + 32 * RG;
+    static constexpr int SCRATCH = 2 * 32 * RS + 5 * 32 * RA;
     static constexpr int SMEM = (WFLOATS + (GCB_GLOBAL_GRADS ? 0 : GRAD_FLOATS) + WARPS * SCRATCH) * (int)sizeof(float);
 };
 
@@ -102,7 +104,7 @@ gcn_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout
     float* A = N1s + 32 * RA;                                 // [32][RA] x1[lead] rows / dcat[:16] / dXg (scene rows)
     float* B = A + 32 * RA;                                   // [32][RA] x2 rows / dcat[16:] / D2 / D1
     float* Ys = B + 32 * RA;                                  // [32][RA] y at the scene's first slot
-    float* G = Ys + 32 * RA;                                  // [32][RG] grad_out rows
+    float* G = P + 40;                                        // [32][RS] grad_out rows, behind the m1 columns of P
 
     auto relu_to = [&](float* dst, int stride) {              // GEMM result -> ReLU -> rows of dst
         return [=](int mt, int nt, const float (&c)[4]) {
