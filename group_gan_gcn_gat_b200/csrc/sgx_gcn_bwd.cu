@@ -21,9 +21,10 @@ namespace gcnb {
 
 constexpr int HID = 72, OUT = 16;
 #ifndef GCB_GLOBAL_GRADS
-#define GCB_GLOBAL_GRADS 1           // 1: the CTA's gradient block lives in its HBM partial (red.global), 6 warps per SM;
-#endif                               // 0: in shared memory (28 KB), 5 warps per SM
-constexpr int WARPS = GCB_GLOBAL_GRADS ? 6 : 5;
+#define GCB_GLOBAL_GRADS 1           // 1: the CTA's gradient block lives in its HBM partial (red.global), 6 chunks in flight per SM;
+#endif                               // 0: in shared memory (28 KB), 5 chunks
+constexpr int PAIRS = GCB_GLOBAL_GRADS ? 6 : 5;          // warp PAIRS: two warps share a chunk's scratch (see the kernel)
+constexpr int WARPS = 2 * PAIRS;
 constexpr int RS = 76;                 // 72-wide rows
 constexpr int RA = 20;                 // 16-wide rows
 constexpr int SWW = 72;                // W0 / V0 blocks [K][72]
@@ -38,7 +39,7 @@ struct Cfg {
     static constexpr int WFLOATS = IN * SWW + 2 * HID * SWN + OUT * SWW + 2 * OUT * SWO;
     static constexpr int GRAD_FLOATS = IN * HID + HID * OUT + OUT * HID + HID * OUT + FIN * 2 * OUT + FIN;   // W0 W1 V0 V1 Wo bo
     static constexpr int SCRATCH = 2 * 32 * RS + 5 * 32 * RA;
-    static constexpr int SMEM = (WFLOATS + (GCB_GLOBAL_GRADS ? 0 : GRAD_FLOATS) + WARPS * SCRATCH) * (int)sizeof(float);
+    static constexpr int SMEM = (WFLOATS + (GCB_GLOBAL_GRADS ? 0 : GRAD_FLOATS) + PAIRS * SCRATCH) * (int)sizeof(float);
 };
 
 template <int F>
@@ -96,8 +97,9 @@ gcn_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout
 #endif
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pair = warp >> 1, role = warp & 1;
     const int g = lane >> 2, t = lane & 3;
-    float* P = bufs + warp * C::SCRATCH;                      // [32][RS] x rows -> group mean m1 (leaders) -> dM1
+    float* P = bufs + pair * C::SCRATCH;                      // [32][RS] x rows -> group mean m1 (leaders) -> dM1
     float* Q = P + 32 * RS;                                   // [32][RS] h1 / k1 (post-ReLU) -> E2 / E
     float* X1s = Q + 32 * RS;                                 // [32][RA] x1 at the leader slots
     float* N1s = X1s + 32 * RA;                               // [32][RA] n1 at the scene's first slot
@@ -142,49 +144,58 @@ gcn_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout
         };
     };
 
-    const int n_warps_total = gridDim.x * WARPS;
-    for (int chunk = blockIdx.x * WARPS + warp; chunk < n_chunks; chunk += n_warps_total) {
+    // Two warps share a chunk: the MAIN warp (role 0) does everything that is lane <-> pedestrian, both take one m-tile of
+    // every warp GEMM (the parameter-gradient GEMMs split their m-tiles the same way); a 64-thread named barrier of the
+    // pair stands wherever rows written by one warp are read by the other.  The kernel is bound by dependent-issue latency
+    // at 1.5 warps per scheduler and ~3/4 of a chunk's time is GEMMs, so the second warp costs no scratch and halves them.
+    auto psync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory"); };
+    const bool main_w = role == 0;
+    const int n_pairs_total = gridDim.x * PAIRS;
+    for (int chunk = blockIdx.x * PAIRS + pair; chunk < n_chunks; chunk += n_pairs_total) {
         const int p0 = scene_start[chunk_scene[chunk]];
         const int np = scene_start[chunk_scene[chunk + 1]] - p0;
         const bool live = lane < np;
         const int p = p0 + lane;
         int b = 0, e = 0, my_lead = lane, k = 1;
-        {
-            float4 xv[IN / 4], gv[FIN / 4];
+        bool is_lead = false, is_head = false;
+        float a = 1.f, cg = 1.f;
+        uint32_t group_mask = 0u, scene_mask = 0u, leader_mask = 0u;
+        if (main_w) {
+            {
+                float4 xv[IN / 4], gv[FIN / 4];
 #pragma unroll
-            for (int c = 0; c < IN / 4; ++c) xv[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int c = 0; c < IN / 4; ++c) xv[c] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int c = 0; c < FIN / 4; ++c) gv[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (live) {
-                b = ped_start[p] - p0; e = ped_end[p] - p0; my_lead = leader[p] - p0; k = gsize[p];
-                const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)p * IN);
-                const float4* gp = reinterpret_cast<const float4*>(gout + (int64_t)p * FIN);
+                for (int c = 0; c < FIN / 4; ++c) gv[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (live) {
+                    b = ped_start[p] - p0; e = ped_end[p] - p0; my_lead = leader[p] - p0; k = gsize[p];
+                    const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)p * IN);
+                    const float4* gp = reinterpret_cast<const float4*>(gout + (int64_t)p * FIN);
 #pragma unroll
-                for (int c = 0; c < IN / 4; ++c) xv[c] = xr[c];
+                    for (int c = 0; c < IN / 4; ++c) xv[c] = xr[c];
 #pragma unroll
-                for (int c = 0; c < FIN / 4; ++c) gv[c] = gp[c];
+                    for (int c = 0; c < FIN / 4; ++c) gv[c] = gp[c];
+                }
+#pragma unroll
+                for (int c = 0; c < IN / 4; ++c) reinterpret_cast<float4*>(Q + lane * RS)[c] = xv[c];      // x rows, transient
+#pragma unroll
+                for (int c = 0; c < FIN / 4; ++c) reinterpret_cast<float4*>(G + lane * RG)[c] = gv[c];
             }
-#pragma unroll
-            for (int c = 0; c < IN / 4; ++c) reinterpret_cast<float4*>(Q + lane * RS)[c] = xv[c];      // x rows, transient
-#pragma unroll
-            for (int c = 0; c < FIN / 4; ++c) reinterpret_cast<float4*>(G + lane * RG)[c] = gv[c];
-        }
-        const bool is_lead = live && my_lead == lane;
-        const bool is_head = live && lane == b;
-        const float a = __frcp_rn((float)k);
-        const uint32_t group_mask = __match_any_sync(0xffffffffu, live ? my_lead : 32 + lane);
-        const uint32_t scene_mask = (e >= 32 ? 0xffffffffu : ((1u << e) - 1u)) & ~((1u << b) - 1u);
-        const uint32_t leader_mask = __ballot_sync(0xffffffffu, is_lead) & scene_mask;
-        const int Gs = __popc(leader_mask);
-        const float cg = __frcp_rn((float)(Gs > 0 ? Gs : 1));
-        __syncwarp();
-        if (lane < FIN) {                                     // d(bo) = column sums of the grad_out rows
-            float sgo = 0.f;
-            for (int r = 0; r < 32; ++r) sgo += G[r * RG + lane];
-            atomicAdd(&gbo[lane], sgo);
-        }
-        // ---- m1 = group mean of x at the leader slots -> P ----
-        {
+            is_lead = live && my_lead == lane;
+            is_head = live && lane == b;
+            a = __frcp_rn((float)k);
+            group_mask = __match_any_sync(0xffffffffu, live ? my_lead : 32 + lane);
+            scene_mask = (e >= 32 ? 0xffffffffu : ((1u << e) - 1u)) & ~((1u << b) - 1u);
+            leader_mask = __ballot_sync(0xffffffffu, is_lead) & scene_mask;
+            const int Gs = __popc(leader_mask);
+            cg = __frcp_rn((float)(Gs > 0 ? Gs : 1));
+            __syncwarp();
+            if (lane < FIN) {                                     // d(bo) = column sums of the grad_out rows
+                float sgo = 0.f;
+                for (int r = 0; r < 32; ++r) sgo += G[r * RG + lane];
+                atomicAdd(&gbo[lane], sgo);
+            }
+            // ---- m1 = group mean of x at the leader slots -> P ----
             float m1[IN];
 #pragma unroll
             for (int c = 0; c < IN; ++c) m1[c] = 0.f;
@@ -201,12 +212,14 @@ gcn_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout
             }
             store_row<IN>(P + lane * RS, m1);
         }
-        __syncwarp();
+        psync();
         // ---- forward: h1 = relu(m1 W0) -> Q ; x1 = relu(h1 W1) -> X1s ----
-        warp_gemm_3xtf32<IN, HID / 8, RS, SWW>(P, sW0, lane, relu_to(Q, RS));
-        warp_gemm_3xtf32<HID, OUT / 8, RS, SWN>(Q, sW1, lane, relu_to(X1s, RA));
+        warp_gemm_3xtf32<IN, HID / 8, RS, SWW>(P, sW0, lane, relu_to(Q, RS), role, 2);
+        psync();
+        warp_gemm_3xtf32<HID, OUT / 8, RS, SWN>(Q, sW1, lane, relu_to(X1s, RA), role, 2);
+        psync();
         // ---- n1 = mean of the scene's group states at the scene's first slot -> N1s ----
-        {
+        if (main_w) {
             float n1[OUT];
 #pragma unroll
             for (int o = 0; o < OUT; ++o) n1[o] = 0.f;
@@ -219,12 +232,14 @@ gcn_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout
             }
             store_row<OUT>(N1s + lane * RA, n1);
         }
-        __syncwarp();
+        psync();
         // ---- k1 = relu(n1 V0) -> Q ; y = relu(k1 V1) -> Ys ----
-        warp_gemm_3xtf32<OUT, HID / 8, RA, SWW>(N1s, sV0, lane, relu_to(Q, RS));
-        warp_gemm_3xtf32<HID, OUT / 8, RS, SWN>(Q, sV1, lane, relu_to(Ys, RA));
+        warp_gemm_3xtf32<OUT, HID / 8, RA, SWW>(N1s, sV0, lane, relu_to(Q, RS), role, 2);
+        psync();
+        warp_gemm_3xtf32<HID, OUT / 8, RS, SWN>(Q, sV1, lane, relu_to(Ys, RA), role, 2);
+        psync();
         // ---- cat = [x1[lead] | a y[head]] ; d(Wo) += grad_out^T cat ----
-        {
+        if (main_w) {
             float c1[OUT], c2[OUT];
 #pragma unroll
             for (int o = 0; o < OUT; ++o) {
@@ -234,74 +249,83 @@ gcn_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout
             store_row<OUT>(A + lane * RA, c1);
             store_row<OUT>(B + lane * RA, c2);
         }
-        __syncwarp();
-        warp_gemm_3xtf32_at<FIN, OUT / 8, RG, RA>(G, A, lane, grad_to(gWo, 2 * OUT, FIN, OUT));
-        warp_gemm_3xtf32_at<FIN, OUT / 8, RG, RA>(G, B, lane, grad_to(gWo + OUT, 2 * OUT, FIN, OUT));
-        __syncwarp();
+        psync();
+        warp_gemm_3xtf32_at_pair<FIN, OUT / 8, RG, RA>(G, A, lane, grad_to(gWo, 2 * OUT, FIN, OUT), role);
+        warp_gemm_3xtf32_at_pair<FIN, OUT / 8, RG, RA>(G, B, lane, grad_to(gWo + OUT, 2 * OUT, FIN, OUT), role);
+        psync();
         // ---- d(cat) = grad_out Wo: columns 0..15 -> A, 16..31 -> B ----
         warp_gemm_3xtf32_bt<FIN, 2 * OUT / 8, RG, SWO>(G, sWoT, lane, [&](int mt, int nt, const float (&c)[4]) {
             const int r = mt * 16 + g;
             float* dst = (nt < OUT / 8 ? A : B) + (nt % (OUT / 8)) * 8 + 2 * t;
             *reinterpret_cast<float2*>(dst + r * RA) = make_float2(c[0], c[1]);
             *reinterpret_cast<float2*>(dst + (r + 8) * RA) = make_float2(c[2], c[3]);
-        });
+        }, role, 2);
+        psync();
         // ---- inter level: D2 = (sum_{i in scene} a_i dx2_i) * [y > 0] at the scene's first slot ----
-        float d2[OUT], dx1s[OUT];
+        float dx1s[OUT];
 #pragma unroll
-        for (int o = 0; o < OUT; ++o) { d2[o] = 0.f; dx1s[o] = 0.f; }
-        {                                                     // x2_i = a_i y: scale every row of d(x2) by its own a_i
-            float4* row = reinterpret_cast<float4*>(B + lane * RA);
-            const float sc = live ? a : 0.f;
+        for (int o = 0; o < OUT; ++o) dx1s[o] = 0.f;
+        if (main_w) {
+            float d2[OUT];
 #pragma unroll
-            for (int c = 0; c < OUT / 4; ++c) { float4 v = row[c]; row[c] = make_float4(sc * v.x, sc * v.y, sc * v.z, sc * v.w); }
-        }
-        __syncwarp();
-        if (is_head) {
-            for (uint32_t mm = scene_mask; mm; mm &= mm - 1) {
-                const int q = __ffs(mm) - 1;
+            for (int o = 0; o < OUT; ++o) d2[o] = 0.f;
+            {                                                     // x2_i = a_i y: scale every row of d(x2) by its own a_i
+                float4* row = reinterpret_cast<float4*>(B + lane * RA);
+                const float sc = live ? a : 0.f;
 #pragma unroll
-                for (int o = 0; o < OUT; ++o) d2[o] += B[q * RA + o];
+                for (int c = 0; c < OUT / 4; ++c) { float4 v = row[c]; row[c] = make_float4(sc * v.x, sc * v.y, sc * v.z, sc * v.w); }
             }
+            __syncwarp();
+            if (is_head) {
+                for (uint32_t mm = scene_mask; mm; mm &= mm - 1) {
+                    const int q = __ffs(mm) - 1;
 #pragma unroll
-            for (int o = 0; o < OUT; ++o) d2[o] = Ys[lane * RA + o] > 0.f ? d2[o] : 0.f;
-        }
-        if (is_lead) {                                        // direct part of d(x1_g): the members' dcat[:16]
-            for (uint32_t mm = group_mask; mm; mm &= mm - 1) {
-                const int q = __ffs(mm) - 1;
+                    for (int o = 0; o < OUT; ++o) d2[o] += B[q * RA + o];
+                }
 #pragma unroll
-                for (int o = 0; o < OUT; ++o) dx1s[o] += A[q * RA + o];
+                for (int o = 0; o < OUT; ++o) d2[o] = Ys[lane * RA + o] > 0.f ? d2[o] : 0.f;
             }
+            if (is_lead) {                                        // direct part of d(x1_g): the members' dcat[:16]
+                for (uint32_t mm = group_mask; mm; mm &= mm - 1) {
+                    const int q = __ffs(mm) - 1;
+#pragma unroll
+                    for (int o = 0; o < OUT; ++o) dx1s[o] += A[q * RA + o];
+                }
+            }
+            __syncwarp();
+            store_row<OUT>(B + lane * RA, d2);                    // D2 rows (zero off the scene heads)
         }
-        __syncwarp();
-        store_row<OUT>(B + lane * RA, d2);                    // D2 rows (zero off the scene heads)
-        __syncwarp();
-        warp_gemm_3xtf32_at<HID, OUT / 8, RS, RA>(Q, B, lane, grad_to(gV1, OUT, HID, OUT));          // d(V1) += k1^T D2
-        __syncwarp();
-        warp_gemm_3xtf32_bt<OUT, HID / 8, RA, SWN>(B, sV1, lane, masked_into(Q));                     // E2 -> Q
-        warp_gemm_3xtf32_at<OUT, HID / 8, RA, RS>(N1s, Q, lane, grad_to(gV0, HID, OUT, HID));        // d(V0) += n1^T E2
-        __syncwarp();
-        warp_gemm_3xtf32_bt<HID, OUT / 8, RS, SWW>(Q, sV0, lane, plain_to(A, RA, OUT));               // E2 V0^T -> A (scene rows)
+        psync();
+        warp_gemm_3xtf32_at_pair<HID, OUT / 8, RS, RA>(Q, B, lane, grad_to(gV1, OUT, HID, OUT), role);    // d(V1) += k1^T D2
+        psync();
+        warp_gemm_3xtf32_bt<OUT, HID / 8, RA, SWN>(B, sV1, lane, masked_into(Q), role, 2);               // E2 -> Q
+        psync();
+        warp_gemm_3xtf32_at_pair<OUT, HID / 8, RA, RS>(N1s, Q, lane, grad_to(gV0, HID, OUT, HID), role);  // d(V0) += n1^T E2 (one m-tile)
+        warp_gemm_3xtf32_bt<HID, OUT / 8, RS, SWW>(Q, sV0, lane, plain_to(A, RA, OUT), role, 2);         // E2 V0^T -> A (scene rows)
+        psync();
         // ---- intra level: D1 = (direct + c E2 V0^T of my scene) * [x1 > 0] at the leader slots -> B ----
-        {
+        if (main_w) {
             float d1[OUT];
 #pragma unroll
             for (int o = 0; o < OUT; ++o) {
                 const float v = dx1s[o] + cg * A[b * RA + o];
                 d1[o] = (is_lead && X1s[lane * RA + o] > 0.f) ? v : 0.f;
             }
-            __syncwarp();
-            store_row<OUT>(B + lane * RA, d1);
+            store_row<OUT>(B + lane * RA, d1);                    // (the pair's last reads of B were before the barrier)
         }
-        // h1 again (Q was reused by the inter level)
-        warp_gemm_3xtf32<IN, HID / 8, RS, SWW>(P, sW0, lane, relu_to(Q, RS));
-        warp_gemm_3xtf32_at<HID, OUT / 8, RS, RA>(Q, B, lane, grad_to(gW1, OUT, HID, OUT));          // d(W1) += h1^T D1
-        __syncwarp();
-        warp_gemm_3xtf32_bt<OUT, HID / 8, RA, SWN>(B, sW1, lane, masked_into(Q));                     // E -> Q
-        warp_gemm_3xtf32_at<IN, HID / 8, RS, RS>(P, Q, lane, grad_to(gW0, HID, IN, HID));            // d(W0) += m1^T E
-        __syncwarp();
-        warp_gemm_3xtf32_bt<HID, IN / 8, RS, SWW>(Q, sW0, lane, plain_to(P, RS, IN));                 // E W0^T -> P (leader rows)
+        // h1 again (Q was reused by the inter level); independent of D1, so the second warp starts while the first writes it
+        warp_gemm_3xtf32<IN, HID / 8, RS, SWW>(P, sW0, lane, relu_to(Q, RS), role, 2);
+        psync();
+        warp_gemm_3xtf32_at_pair<HID, OUT / 8, RS, RA>(Q, B, lane, grad_to(gW1, OUT, HID, OUT), role);    // d(W1) += h1^T D1
+        psync();
+        warp_gemm_3xtf32_bt<OUT, HID / 8, RA, SWN>(B, sW1, lane, masked_into(Q), role, 2);               // E -> Q
+        psync();
+        warp_gemm_3xtf32_at_pair<IN, HID / 8, RS, RS>(P, Q, lane, grad_to(gW0, HID, IN, HID), role);      // d(W0) += m1^T E
+        psync();
+        warp_gemm_3xtf32_bt<HID, IN / 8, RS, SWW>(Q, sW0, lane, plain_to(P, RS, IN), role, 2);           // E W0^T -> P (leader rows)
+        psync();
         // ---- d(x_i) = a_i (E W0^T)[leader(i)] ----
-        if (live) {
+        if (main_w && live) {
             const float4* src = reinterpret_cast<const float4*>(P + my_lead * RS);
             float4* dst = reinterpret_cast<float4*>(grad_x + (int64_t)p * IN);
 #pragma unroll
@@ -310,7 +334,7 @@ gcn_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout
                 dst[c] = make_float4(a * v.x, a * v.y, a * v.z, a * v.w);
             }
         }
-        __syncwarp();
+        psync();                                              // P / Q / G are rewritten by the next chunk's loads
     }
 #if !GCB_GLOBAL_GRADS
     __syncthreads();
@@ -344,7 +368,7 @@ static int launch(const float* x, const float* gout, const int32_t* leader, cons
     using C = Cfg<IN, FIN>;
     auto kern = gcn_fused_bwd_kernel<IN, FIN>;
     SGX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    const int grid = std::min((n_chunks + WARPS - 1) / WARPS, 148);
+    const int grid = std::min((n_chunks + PAIRS - 1) / PAIRS, 148);
     kern<<<grid, WARPS * 32, C::SMEM, st>>>(x, gout, leader, gsize, ps, pe, scene_start, chunk_scene, n_chunks, W0, W1, V0, V1,
                                             Wo, gx, partials);
     SGX_LAUNCH_CHECK();

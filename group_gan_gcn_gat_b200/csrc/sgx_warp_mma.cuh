@@ -28,13 +28,14 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 // C [16 MT x 8 NT] = A [16 MT x K] . B [K x 8 NT] for one warp (MT = 2: the 32 slots of a warp chunk); A rows in shared memory (stride SA floats), B row-major
 // (stride SB).  store(mt, nt, acc) receives the m16n8 accumulator fragment: acc[0..1] = row mt*16 + lane/4, columns
 // nt*8 + 2 (lane%4) + {0,1}; acc[2..3] = the same columns of row + 8.  A __syncwarp precedes the stores of an m-tile,
-// so C may overwrite the A rows of that m-tile.
+// so C may overwrite the A rows of that m-tile.  (mt0, mts): the m-tiles mt0, mt0 + mts, ... only -- two warps that share
+// a chunk's buffers take one m-tile each (the callers put a barrier of the pair around the call).
 template <int K, int NT, int SA, int SB, int MT = 2, class Store>
 __device__ __forceinline__ void warp_gemm_3xtf32(const float* __restrict__ A, const float* __restrict__ B, int lane,
-                                                 Store&& store) {
+                                                 Store&& store, int mt0 = 0, int mts = 1) {
     const int g = lane >> 2, t = lane & 3;
 #pragma unroll 1
-    for (int mt = 0; mt < MT; ++mt) {
+    for (int mt = mt0; mt < MT; mt += mts) {
         float acc[NT][4];
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
@@ -79,10 +80,10 @@ __device__ __forceinline__ void warp_gemm_3xtf32(const float* __restrict__ A, co
 // fragment conventions as warp_gemm_3xtf32.  B fragment loads are 2-way bank conflicted for SB = 24 / 88 (g and g + 4).
 template <int K, int NT, int SA, int SB, int MT = 2, class Store>
 __device__ __forceinline__ void warp_gemm_3xtf32_bt(const float* __restrict__ A, const float* __restrict__ B, int lane,
-                                                    Store&& store) {
+                                                    Store&& store, int mt0 = 0, int mts = 1) {
     const int g = lane >> 2, t = lane & 3;
 #pragma unroll 1
-    for (int mt = 0; mt < MT; ++mt) {
+    for (int mt = mt0; mt < MT; mt += mts) {
         float acc[NT][4];
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
@@ -125,11 +126,11 @@ __device__ __forceinline__ void warp_gemm_3xtf32_bt(const float* __restrict__ A,
 // must be dropped by the caller.  Every one of the 32 rows of A and B must be finite (zero for dead lanes).
 template <int M, int NT, int SA, int SB, class Store>
 __device__ __forceinline__ void warp_gemm_3xtf32_at(const float* __restrict__ A, const float* __restrict__ B, int lane,
-                                                    Store&& store) {
+                                                    Store&& store, int mt0 = 0, int mts = 1) {
     const int g = lane >> 2, t = lane & 3;
     constexpr int MT = (M + 15) / 16;
 #pragma unroll 1
-    for (int mt = 0; mt < MT; ++mt) {
+    for (int mt = mt0; mt < MT; mt += mts) {
         float acc[NT][4];
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
@@ -162,6 +163,20 @@ __device__ __forceinline__ void warp_gemm_3xtf32_at(const float* __restrict__ A,
         }
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) store(mt * 16, nt, acc[nt]);
+    }
+}
+
+// The same product shared by a PAIR of warps along the output columns: role 0 takes the first ceil(NT / 2) n-tiles, role 1
+// the rest (every m-tile each) -- an even split whatever M is, where splitting the m-tiles of M = 16 / 40 / 72 is not.
+template <int M, int NT, int SA, int SB, class Store>
+__device__ __forceinline__ void warp_gemm_3xtf32_at_pair(const float* __restrict__ A, const float* __restrict__ B, int lane,
+                                                         Store&& store, int role) {
+    constexpr int N0 = (NT + 1) / 2, N1 = NT - N0;
+    if (role == 0) {
+        warp_gemm_3xtf32_at<M, N0, SA, SB>(A, B, lane, store);
+    } else if constexpr (N1 > 0) {
+        warp_gemm_3xtf32_at<M, N1, SA, SB>(A, B + N0 * 8, lane,
+                                           [&](int m0, int nt, const float (&c)[4]) { store(m0, nt + N0, c); });
     }
 }
 
