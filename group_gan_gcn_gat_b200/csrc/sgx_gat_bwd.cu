@@ -22,9 +22,10 @@
 namespace sgx {
 
 #ifndef GB_GLOBAL_GRADS
-#define GB_GLOBAL_GRADS 1            // 1: the CTA's gradient block lives in its HBM partial (red.global), 6 warps per SM;
-#endif                               // 0: in shared memory (30 KB), 5 warps per SM
-constexpr int GB_WARPS = GB_GLOBAL_GRADS ? 6 : 5;
+#define GB_GLOBAL_GRADS 1            // 1: the CTA's gradient block lives in its HBM partial (red.global), 6 chunks in flight
+#endif                               // per SM; 0: in shared memory (30 KB), 5 chunks
+constexpr int GB_PAIRS = GB_GLOBAL_GRADS ? 6 : 5;        // warp PAIRS: two warps share a chunk's scratch (see the kernel)
+constexpr int GB_WARPS = 2 * GB_PAIRS;
 constexpr int GB_IN = 40, GB_FIN = 24;
 constexpr int RG = 28;                       // row stride of the grad_out rows (24 wide): conflict-free A fragments
 
@@ -174,7 +175,8 @@ gat_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout
     if (threadIdx.x < 2 * OUT) av.ue[threadIdx.x] = w.We[(threadIdx.x % OUT) * SW1 + HID + threadIdx.x / OUT];
     __syncthreads();
 
-    float* P = bufs + warp * GB_SCRATCH;                 // [32][RS]  x / Wh1; [32][RA] xbar of the inter level
+    const int pair = warp >> 1, role = warp & 1;
+    float* P = bufs + pair * GB_SCRATCH;                 // [32][RS]  x / Wh1; [32][RA] xbar of the inter level
     float* Q = P + 32 * RS;                              // [32][RS]  x1a / y3 -> d(hp) -> dWh of the 72-wide layers
     float* Xg = Q + 32 * RS;                             // [32][RA]  pooled group state (leader slots)
     float* A = Xg + 32 * RA;                             // [32][RA]  Wh2 / Wh4
@@ -237,11 +239,18 @@ gat_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout
         };
     };
 
-    const int n_warps_total = gridDim.x * GB_WARPS;
-    for (int chunk = blockIdx.x * GB_WARPS + warp; chunk < n_chunks; chunk += n_warps_total) {
+    // Two warps share a chunk (as in the GCN backward): the MAIN warp (role 0) owns everything that is lane <-> pedestrian,
+    // both take one m-tile of every warp GEMM, the parameter-gradient GEMMs are split along their output columns.  The
+    // second warp runs the same code as a warp of dead lanes -- every per-lane loop is empty for it and every per-lane
+    // store is the main warp's alone -- so the two execute the same sequence of 64-thread pair barriers, which stand
+    // wherever a __syncwarp stood and after every GEMM that writes rows.
+    auto psync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory"); };
+    const bool main_w = role == 0;
+    const int n_pairs_total = gridDim.x * GB_PAIRS;
+    for (int chunk = blockIdx.x * GB_PAIRS + pair; chunk < n_chunks; chunk += n_pairs_total) {
         const int p0 = scene_start[chunk_scene[chunk]];
         const int np = scene_start[chunk_scene[chunk + 1]] - p0;
-        const bool live = lane < np;
+        const bool live = main_w && lane < np;
         const int p = p0 + lane;
         int b = 0, e = 0, my_lead = lane;
         float inv_g = 1.f;
@@ -259,17 +268,18 @@ gat_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout
                 for (int c = 0; c < IN / 4; ++c) xv[c] = xr[c];
             }
 #pragma unroll
-            for (int c = 0; c < IN / 4; ++c) reinterpret_cast<float4*>(P + lane * RS)[c] = xv[c];
+            for (int c = 0; c < IN / 4; ++c) if (main_w) reinterpret_cast<float4*>(P + lane * RS)[c] = xv[c];
         };
         load_x();
         const bool is_lead = live && (my_lead == lane);
         const uint32_t group_mask = __match_any_sync(0xffffffffu, live ? my_lead : 32 + lane);
         const uint32_t scene_mask = (e >= 32 ? 0xffffffffu : ((1u << e) - 1u)) & ~((1u << b) - 1u);
         const uint32_t leader_mask = __ballot_sync(0xffffffffu, is_lead) & scene_mask;
-        __syncwarp();
+        psync();
 
         // =============== forward recompute, part 1: x -> x1 -> Xg ===============
-        warp_gemm_3xtf32<IN, HID / 8 + 1, RS, SW1>(P, w.Wi, lane, wide_to(P, stA));
+        warp_gemm_3xtf32<IN, HID / 8 + 1, RS, SW1>(P, w.Wi, lane, wide_to(P, stA), role, 2);
+        psync();
         {
             float hp[HID];
 #pragma unroll
@@ -279,9 +289,9 @@ gat_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout
 #pragma unroll
                 for (int f = 0; f < HID; ++f) hp[f] = felu(hp[f]);
             }
-            store_row<HID>(Q + lane * RS, hp);              // x1a
+            if (main_w) store_row<HID>(Q + lane * RS, hp);              // x1a
         }
-        __syncwarp();
+        psync();
         // the Wh1 rows in P are dead until the intra level's backward reloads x: the grad_out rows move into P's tail
         {
             float4 gv[FIN / 4];
@@ -293,15 +303,16 @@ gat_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout
                 for (int c = 0; c < FIN / 4; ++c) gv[c] = gp[c];
             }
 #pragma unroll
-            for (int c = 0; c < FIN / 4; ++c) reinterpret_cast<float4*>(G + lane * RG)[c] = gv[c];
+            for (int c = 0; c < FIN / 4; ++c) if (main_w) reinterpret_cast<float4*>(G + lane * RG)[c] = gv[c];
         }
-        __syncwarp();
-        if (lane < FIN) {                                   // d(bo) = column sums of the grad_out rows
+        psync();
+        if (main_w && lane < FIN) {                         // d(bo) = column sums of the grad_out rows
             float sgo = 0.f;
             for (int r = 0; r < 32; ++r) sgo += G[r * RG + lane];
             atomicAdd(&gr.bo[lane], sgo);
         }
-        warp_gemm_3xtf32<HID, OUT / 8 + 1, RS, SW2>(Q, w.Wio, lane, narrow_to(A, stB));
+        warp_gemm_3xtf32<HID, OUT / 8 + 1, RS, SW2>(Q, w.Wio, lane, narrow_to(A, stB), role, 2);
+        psync();
         float x1[OUT];
 #pragma unroll
         for (int o = 0; o < OUT; ++o) x1[o] = 0.f;
@@ -309,10 +320,10 @@ gat_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout
             attend_mask<OUT, RA>(A, stB, group_mask, stB[lane].x, alpha, x1);
             elu_logsoftmax<OUT>(x1);
         }
-        store_row<OUT>(B + lane * RA, x1);
-        __syncwarp();
+        if (main_w) store_row<OUT>(B + lane * RA, x1);
+        psync();
         // d(Wo)[:, :16] += grad_out^T x1
-        warp_gemm_3xtf32_at<FIN, OUT / 8, RG, RA>(G, B, lane, grad_to(gr.Wo, 2 * OUT, FIN, OUT));
+        warp_gemm_3xtf32_at_pair<FIN, OUT / 8, RG, RA>(G, B, lane, grad_to(gr.Wo, 2 * OUT, FIN, OUT), role);
         {
             float xg[OUT];
 #pragma unroll
@@ -324,9 +335,9 @@ gat_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout
                     for (int o = 0; o < OUT; ++o) xg[o] = fmaf(inv_g, B[q * RA + o], xg[o]);
                 }
             }
-            store_row<OUT>(Xg + lane * RA, xg);
+            if (main_w) store_row<OUT>(Xg + lane * RA, xg);
         }
-        __syncwarp();
+        psync();
         // =============== forward recompute, part 2 (inter level, leaders): Xg -> y3 -> Yg ===============
         // layer 3 aggregated BEFORE its linear map: sum_j a_ij (Xg_j We) = (sum_j a_ij Xg_j) We = xbar We, so the attention
         // over the scene's leaders and its whole backward run on 16-wide rows instead of 72-wide ones; the scores are
@@ -337,24 +348,26 @@ gat_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout
             float s3 = 0.f, t3 = 0.f;
 #pragma unroll
             for (int o = 0; o < OUT; ++o) { s3 = fmaf(xg[o], av.ue[o], s3); t3 = fmaf(xg[o], av.ue[OUT + o], t3); }
-            stA[lane] = make_float2(s3, t3);
+            if (main_w) stA[lane] = make_float2(s3, t3);
         }
-        __syncwarp();
+        psync();
         {
             float xb[OUT];
 #pragma unroll
             for (int o = 0; o < OUT; ++o) xb[o] = 0.f;
             if (is_lead) attend_mask<OUT, RA>(Xg, stA, leader_mask, stA[lane].x, alpha, xb);
-            store_row<OUT>(P + lane * RA, xb);              // xbar (zero rows off the leaders)
+            if (main_w) store_row<OUT>(P + lane * RA, xb);              // xbar (zero rows off the leaders)
         }
-        __syncwarp();
+        psync();
         // y3 = elu(xbar We) -> Q (zero rows off the leaders)
         warp_gemm_3xtf32<OUT, HID / 8, RA, SW1>(P, w.We, lane, [&](int mt, int nt, const float (&c)[4]) {
             const int r = mt * 16 + g, col = nt * 8 + 2 * t;
             *reinterpret_cast<float2*>(Q + r * RS + col) = make_float2(felu(c[0]), felu(c[1]));
             *reinterpret_cast<float2*>(Q + (r + 8) * RS + col) = make_float2(felu(c[2]), felu(c[3]));
-        });
-        warp_gemm_3xtf32<HID, OUT / 8 + 1, RS, SW2>(Q, w.Weo, lane, narrow_to(A, stB));    // Wh4 -> A, (s4, t4) -> stB
+        }, role, 2);
+        psync();
+        warp_gemm_3xtf32<HID, OUT / 8 + 1, RS, SW2>(Q, w.Weo, lane, narrow_to(A, stB), role, 2);    // Wh4 -> A, (s4, t4) -> stB
+        psync();
         float hp4[OUT], yg[OUT];
 #pragma unroll
         for (int o = 0; o < OUT; ++o) { hp4[o] = 0.f; yg[o] = 0.f; }
@@ -364,26 +377,27 @@ gat_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout
             for (int o = 0; o < OUT; ++o) yg[o] = hp4[o];
             elu_logsoftmax<OUT>(yg);
         }
-        store_row<OUT>(D + lane * RA, yg);                  // Yg at the leader slots
-        __syncwarp();
+        if (main_w) store_row<OUT>(D + lane * RA, yg);                  // Yg at the leader slots
+        psync();
         // =============== top: out = [x1 | x2] Wo^T + bo ===============
         {
             float x2[OUT];
 #pragma unroll
             for (int o = 0; o < OUT; ++o) x2[o] = live ? inv_g * D[my_lead * RA + o] : 0.f;
-            store_row<OUT>(B + lane * RA, x2);              // x1 rows are no longer needed in shared memory
+            if (main_w) store_row<OUT>(B + lane * RA, x2);              // x1 rows are no longer needed in shared memory
         }
-        __syncwarp();
+        psync();
         // d(Wo)[:, 16:] += grad_out^T x2
-        warp_gemm_3xtf32_at<FIN, OUT / 8, RG, RA>(G, B, lane, grad_to(gr.Wo + OUT, 2 * OUT, FIN, OUT));
-        __syncwarp();
+        warp_gemm_3xtf32_at_pair<FIN, OUT / 8, RG, RA>(G, B, lane, grad_to(gr.Wo + OUT, 2 * OUT, FIN, OUT), role);
+        psync();
         // d(cat) = grad_out Wo: columns 0..15 = d(x1) (direct part) -> D, columns 16..31 = d(x2) -> B
         warp_gemm_3xtf32_bt<FIN, 2 * OUT / 8, RG, SW2>(G, w.WoT, lane, [&](int mt, int nt, const float (&c)[4]) {
             const int r = mt * 16 + g;
             float* dst = (nt < OUT / 8 ? D : B) + (nt % (OUT / 8)) * 8 + 2 * t;
             *reinterpret_cast<float2*>(dst + r * RA) = make_float2(c[0], c[1]);
             *reinterpret_cast<float2*>(dst + (r + 8) * RA) = make_float2(c[2], c[3]);
-        });
+        }, role, 2);
+        psync();
         float dx1[OUT];                                     // d(x1): direct part now, + pooled part after the inter level
         load_row<OUT>(D + lane * RA, dx1);
         // =============== inter out_att (layer 4) backward ===============
@@ -403,25 +417,25 @@ gat_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout
             elu_logsoftmax_bwd<OUT>(hp4, yg, dyg, dh4);
             float4 s4;
             att_bwd_row<OUT, RA>(A, stB, leader_mask, stB[lane].x, alpha, dh4, s4, ds);
-            stat[lane] = s4;
+            if (main_w) stat[lane] = s4;
         }
-        __syncwarp();                                       // every leader has read the d(x2) rows of its group
-        store_row<OUT>(B + lane * RA, dh4);
-        __syncwarp();
+        psync();                                       // every leader has read the d(x2) rows of its group
+        if (main_w) store_row<OUT>(B + lane * RA, dh4);
+        psync();
         {
             float dwh[OUT];
 #pragma unroll
             for (int o = 0; o < OUT; ++o) dwh[o] = 0.f;
             if (is_lead)
                 att_bwd_col<OUT, RA, RA>(A + lane * RA, B, stB, stat, leader_mask, stB[lane].y, ds, alpha, av.aeo, dwh, dt);
-            dstb[lane] = make_float2(is_lead ? ds : 0.f, is_lead ? dt : 0.f);
-            __syncwarp();
-            store_row<OUT>(B + lane * RA, dwh);             // dWh4
+            if (main_w) dstb[lane] = make_float2(is_lead ? ds : 0.f, is_lead ? dt : 0.f);
+            psync();
+            if (main_w) store_row<OUT>(B + lane * RA, dwh);             // dWh4
         }
-        __syncwarp();
-        warp_gemm_3xtf32_at<HID, OUT / 8, RS, RA>(Q, B, lane, grad_to(gr.Weo, OUT, HID, OUT));      // d(Weo) += y3^T dWh4
-        warp_gemm_3xtf32_at<OUT, 1, RA, 2>(A, reinterpret_cast<const float*>(dstb), lane, avec_to(gr.aeo, OUT));
-        __syncwarp();
+        psync();
+        warp_gemm_3xtf32_at_pair<HID, OUT / 8, RS, RA>(Q, B, lane, grad_to(gr.Weo, OUT, HID, OUT), role);      // d(Weo) += y3^T dWh4
+        warp_gemm_3xtf32_at_pair<OUT, 1, RA, 2>(A, reinterpret_cast<const float*>(dstb), lane, avec_to(gr.aeo, OUT), role);
+        psync();
         // d(y3) = dWh4 Weo^T, times elu'(hp3) read back from y3: d(hp3) -> Q in place
         warp_gemm_3xtf32_bt<OUT, HID / 8, RA, SW2>(B, w.Weo, lane, [&](int mt, int nt, const float (&c)[4]) {
             const int r = mt * 16 + g, col = nt * 8 + 2 * t;
@@ -430,11 +444,13 @@ gat_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout
             const float2 y0 = *q0, y1 = *q1;                // elu'(hp) = 1 for hp > 0 (y = hp > 0), else exp(hp) = y + 1
             *q0 = make_float2(c[0] * (y0.x > 0.f ? 1.f : y0.x + 1.f), c[1] * (y0.y > 0.f ? 1.f : y0.y + 1.f));
             *q1 = make_float2(c[2] * (y1.x > 0.f ? 1.f : y1.x + 1.f), c[3] * (y1.y > 0.f ? 1.f : y1.y + 1.f));
-        });
+        }, role, 2);
+        psync();
         // =============== inter layer 1 (layer 3) backward, on the aggregated form ===============
         // Q = d(hp3):  d(We) += xbar^T d(hp3),  d(xbar) = d(hp3) We^T -> D
-        warp_gemm_3xtf32_at<OUT, HID / 8, RA, RS>(P, Q, lane, grad_to(gr.We, HID, OUT, HID));
-        warp_gemm_3xtf32_bt<HID, OUT / 8, RS, SW1>(Q, w.We, lane, narrow_to(D, nullptr));
+        warp_gemm_3xtf32_at_pair<OUT, HID / 8, RA, RS>(P, Q, lane, grad_to(gr.We, HID, OUT, HID), role);
+        warp_gemm_3xtf32_bt<HID, OUT / 8, RS, SW1>(Q, w.We, lane, narrow_to(D, nullptr), role, 2);
+        psync();
         ds = 0.f; dt = 0.f;
         {
             float dxb[OUT];
@@ -442,33 +458,34 @@ gat_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout
             if (is_lead) {
                 float4 s3;
                 att_bwd_row<OUT, RA>(Xg, stA, leader_mask, stA[lane].x, alpha, dxb, s3, ds);
-                stat[lane] = s3;
+                if (main_w) stat[lane] = s3;
             }
         }
-        __syncwarp();
+        psync();
         {
             float dxg[OUT];                                 // d(Xg_j) = sum_i a_ij d(xbar_i) + ds_j We ae1 + dt_j We ae2
 #pragma unroll
             for (int o = 0; o < OUT; ++o) dxg[o] = 0.f;
             if (is_lead)
                 att_bwd_col<OUT, RA, RA>(Xg + lane * RA, D, stA, stat, leader_mask, stA[lane].y, ds, alpha, av.ue, dxg, dt);
-            dstb[lane] = make_float2(is_lead ? ds : 0.f, is_lead ? dt : 0.f);
-            __syncwarp();                                   // every leader has read the d(xbar) rows
-            store_row<OUT>(D + lane * RA, dxg);             // d(Xg)
+            if (main_w) dstb[lane] = make_float2(is_lead ? ds : 0.f, is_lead ? dt : 0.f);
+            psync();                                   // every leader has read the d(xbar) rows
+            if (main_w) store_row<OUT>(D + lane * RA, dxg);             // d(Xg)
         }
-        __syncwarp();
+        psync();
         // d(We ae1), d(We ae2) [2][16] += (ds, dt)^T Xg: folded into d(We) and d(ae) by the reduce kernel (both are linear)
-        warp_gemm_3xtf32_at<OUT, 1, RA, 2>(Xg, reinterpret_cast<const float*>(dstb), lane, avec_to(gr.du, OUT));
+        warp_gemm_3xtf32_at_pair<OUT, 1, RA, 2>(Xg, reinterpret_cast<const float*>(dstb), lane, avec_to(gr.du, OUT), role);
         // pool backward: Xg[l] = sum_{i in g} x1_i / |g|
         if (live) {
 #pragma unroll
             for (int o = 0; o < OUT; ++o) dx1[o] = fmaf(inv_g, D[my_lead * RA + o], dx1[o]);
         }
-        __syncwarp();
+        psync();
         // =============== intra level: recompute Wh1, x1a, Wh2, hp2 ===============
         load_x();
-        __syncwarp();
-        warp_gemm_3xtf32<IN, HID / 8 + 1, RS, SW1>(P, w.Wi, lane, wide_to(P, stA));        // Wh1 -> P, (s1, t1) -> stA
+        psync();
+        warp_gemm_3xtf32<IN, HID / 8 + 1, RS, SW1>(P, w.Wi, lane, wide_to(P, stA), role, 2);        // Wh1 -> P, (s1, t1) -> stA
+        psync();
         {
             float hp[HID];
 #pragma unroll
@@ -478,10 +495,11 @@ gat_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout
 #pragma unroll
                 for (int f = 0; f < HID; ++f) hp[f] = felu(hp[f]);
             }
-            store_row<HID>(Q + lane * RS, hp);              // x1a
+            if (main_w) store_row<HID>(Q + lane * RS, hp);              // x1a
         }
-        __syncwarp();
-        warp_gemm_3xtf32<HID, OUT / 8 + 1, RS, SW2>(Q, w.Wio, lane, narrow_to(A, stB));    // Wh2 -> A, (s2, t2) -> stB
+        psync();
+        warp_gemm_3xtf32<HID, OUT / 8 + 1, RS, SW2>(Q, w.Wio, lane, narrow_to(A, stB), role, 2);    // Wh2 -> A, (s2, t2) -> stB
+        psync();
         // =============== intra out_att (layer 2) backward ===============
         float dh2[OUT];
 #pragma unroll
@@ -493,24 +511,24 @@ gat_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout
             elu_logsoftmax_bwd<OUT>(hp2, x1, dx1, dh2);
             float4 s2;
             att_bwd_row<OUT, RA>(A, stB, group_mask, stB[lane].x, alpha, dh2, s2, ds);
-            stat[lane] = s2;
+            if (main_w) stat[lane] = s2;
         }
-        store_row<OUT>(B + lane * RA, dh2);
-        __syncwarp();
+        if (main_w) store_row<OUT>(B + lane * RA, dh2);
+        psync();
         {
             float dwh[OUT];
 #pragma unroll
             for (int o = 0; o < OUT; ++o) dwh[o] = 0.f;
             if (live)
                 att_bwd_col<OUT, RA, RA>(A + lane * RA, B, stB, stat, group_mask, stB[lane].y, ds, alpha, av.aio, dwh, dt);
-            dstb[lane] = make_float2(live ? ds : 0.f, live ? dt : 0.f);
-            __syncwarp();
-            store_row<OUT>(B + lane * RA, dwh);             // dWh2
+            if (main_w) dstb[lane] = make_float2(live ? ds : 0.f, live ? dt : 0.f);
+            psync();
+            if (main_w) store_row<OUT>(B + lane * RA, dwh);             // dWh2
         }
-        __syncwarp();
-        warp_gemm_3xtf32_at<HID, OUT / 8, RS, RA>(Q, B, lane, grad_to(gr.Wio, OUT, HID, OUT));      // d(Wio) += x1a^T dWh2
-        warp_gemm_3xtf32_at<OUT, 1, RA, 2>(A, reinterpret_cast<const float*>(dstb), lane, avec_to(gr.aio, OUT));
-        __syncwarp();
+        psync();
+        warp_gemm_3xtf32_at_pair<HID, OUT / 8, RS, RA>(Q, B, lane, grad_to(gr.Wio, OUT, HID, OUT), role);      // d(Wio) += x1a^T dWh2
+        warp_gemm_3xtf32_at_pair<OUT, 1, RA, 2>(A, reinterpret_cast<const float*>(dstb), lane, avec_to(gr.aio, OUT), role);
+        psync();
         // d(x1a) = dWh2 Wio^T, times elu'(hp1) read back from x1a: d(hp1) -> Q in place
         warp_gemm_3xtf32_bt<OUT, HID / 8, RA, SW2>(B, w.Wio, lane, [&](int mt, int nt, const float (&c)[4]) {
             const int r = mt * 16 + g, col = nt * 8 + 2 * t;
@@ -519,7 +537,8 @@ gat_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout
             const float2 y0 = *q0, y1 = *q1;
             *q0 = make_float2(c[0] * (y0.x > 0.f ? 1.f : y0.x + 1.f), c[1] * (y0.y > 0.f ? 1.f : y0.y + 1.f));
             *q1 = make_float2(c[2] * (y1.x > 0.f ? 1.f : y1.x + 1.f), c[3] * (y1.y > 0.f ? 1.f : y1.y + 1.f));
-        });
+        }, role, 2);
+        psync();
         // =============== intra layer 1 backward ===============
         ds = 0.f; dt = 0.f;
         {
@@ -528,32 +547,33 @@ gat_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout
             if (live) {
                 float4 s1;
                 att_bwd_row<HID, RS>(P, stA, group_mask, stA[lane].x, alpha, dh, s1, ds);
-                stat[lane] = s1;
+                if (main_w) stat[lane] = s1;
             }
         }
-        __syncwarp();
+        psync();
         {
             float dwh[HID];
 #pragma unroll
             for (int f = 0; f < HID; ++f) dwh[f] = 0.f;
             if (live)
                 att_bwd_col<HID, RS, RS>(P + lane * RS, Q, stA, stat, group_mask, stA[lane].y, ds, alpha, av.ai, dwh, dt);
-            dstb[lane] = make_float2(live ? ds : 0.f, live ? dt : 0.f);
-            __syncwarp();
-            store_row<HID>(Q + lane * RS, dwh);             // dWh1
+            if (main_w) dstb[lane] = make_float2(live ? ds : 0.f, live ? dt : 0.f);
+            psync();
+            if (main_w) store_row<HID>(Q + lane * RS, dwh);             // dWh1
         }
-        __syncwarp();
-        warp_gemm_3xtf32_at<HID, 1, RS, 2>(P, reinterpret_cast<const float*>(dstb), lane, avec_to(gr.ai, HID));   // needs Wh1
-        __syncwarp();
+        psync();
+        warp_gemm_3xtf32_at_pair<HID, 1, RS, 2>(P, reinterpret_cast<const float*>(dstb), lane, avec_to(gr.ai, HID), role);   // needs Wh1
+        psync();
         load_x();
-        __syncwarp();
-        warp_gemm_3xtf32_at<IN, HID / 8, RS, RS>(P, Q, lane, grad_to(gr.Wi, HID, IN, HID));         // d(Wi) += x^T dWh1
+        psync();
+        warp_gemm_3xtf32_at_pair<IN, HID / 8, RS, RS>(P, Q, lane, grad_to(gr.Wi, HID, IN, HID), role);         // d(Wi) += x^T dWh1
         // d(x) = dWh1 Wi^T -> HBM
         warp_gemm_3xtf32_bt<HID, IN / 8, RS, SW1>(Q, w.Wi, lane, [&](int mt, int nt, const float (&c)[4]) {
             const int r = mt * 16 + g, col = nt * 8 + 2 * t;
             if (r < np) *reinterpret_cast<float2*>(grad_x + (int64_t)(p0 + r) * IN + col) = make_float2(c[0], c[1]);
             if (r + 8 < np) *reinterpret_cast<float2*>(grad_x + (int64_t)(p0 + r + 8) * IN + col) = make_float2(c[2], c[3]);
-        });
+        }, role, 2);
+        psync();
     }
 #if !GB_GLOBAL_GRADS
     __syncthreads();
@@ -629,9 +649,9 @@ extern "C" int sgx_gat_encoder_fused_bwd(const float* x, const float* grad_out, 
     SGX_REQUIRE(ws_bytes >= sgx_gat_encoder_fused_bwd_ws_bytes(), "sgx_gat_encoder_fused_bwd: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     const int smem = (int)(sizeof(FusedWm) + sizeof(GatAvec) + (GB_GLOBAL_GRADS ? 0 : sizeof(GatGrad)) +
-                           GB_WARPS * GB_SCRATCH * sizeof(float));
+                           GB_PAIRS * GB_SCRATCH * sizeof(float));
     SGX_CUDA(cudaFuncSetAttribute(gat_fused_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int grid = (int)std::min<int64_t>((n_chunks + GB_WARPS - 1) / GB_WARPS, 148);
+    const int grid = (int)std::min<int64_t>((n_chunks + GB_PAIRS - 1) / GB_PAIRS, 148);
     float* partials = (float*)workspace;
     gat_fused_bwd_kernel<<<grid, GB_WARPS * 32, smem, st>>>(x, grad_out, leader, group_size, ped_start, ped_end, scene_start,
                                                             chunk_scene, (int)n_chunks, Wi, ai, Wio, aio, We, ae, Weo, aeo,
