@@ -25,7 +25,7 @@ namespace sgx {
 __global__ void colsum_kernel(const float* __restrict__ m, int64_t rows, int cols, float* __restrict__ out);
 
 enum { INTRA = 0, INTER = 1 };
-enum { POST_ELU = 1, POST_ELU_LOGSOFTMAX = 2 };
+enum { POST_NONE = 0, POST_ELU = 1, POST_ELU_LOGSOFTMAX = 2 };   // POST_NONE: the plain weighted sum (aggregate-first layers)
 
 template <int MODE>
 __device__ __forceinline__ bool node_active(const int32_t* __restrict__ leader, int i) {
@@ -87,7 +87,10 @@ att_fwd_kernel(const float* __restrict__ Wh, int ldw, const float* __restrict__ 
     float m, den;
     attend<F, MODE>(Wh, ldw, st, lds, leader, ped_start[i], ped_end[i], leader[i], st[(int64_t)i * lds], alpha, hp, m,
                     den);
-    if (POST == POST_ELU) {
+    if (POST == POST_NONE) {
+#pragma unroll
+        for (int f = 0; f < F; ++f) out[(int64_t)i * ldo + f] = hp[f];
+    } else if (POST == POST_ELU) {
 #pragma unroll
         for (int f = 0; f < F; ++f) out[(int64_t)i * ldo + f] = elu1(hp[f]);
     } else {
@@ -246,12 +249,16 @@ att_fwd_scene_kernel(const float* __restrict__ Wh, int ldw, const float* __restr
         for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
         const float inv = 1.f / d;
         const int64_t i = b + row_i[k];
-        if (POST == POST_ELU) {
+        if (POST == POST_NONE) {
+#pragma unroll
+            for (int u = 0; u < NU; ++u)
+                if (lane + 32 * u < F) out[i * ldo + lane + 32 * u] = acc[k][u] * inv;
+        } else if (POST == POST_ELU) {
 #pragma unroll
             for (int u = 0; u < NU; ++u)
                 if (lane + 32 * u < F) out[i * ldo + lane + 32 * u] = elu1(acc[k][u] * inv);
         } else {
-            static_assert(POST == POST_ELU || F <= 32, "log_softmax epilogue: one feature per lane");
+            static_assert(POST != POST_ELU_LOGSOFTMAX || F <= 32, "log_softmax epilogue: one feature per lane");
             const float uval = lane < F ? elu1(acc[k][0] * inv) : -INFINITY;
             float mx = uval;
 #pragma unroll
@@ -292,7 +299,14 @@ att_bwd_row_kernel(const float* __restrict__ Wh, int ldw, const float* __restric
     float m, den;
     attend<F, MODE>(Wh, ldw, st, lds, leader, b, e, li, s_i, alpha, hp, m, den);
     float c = 0.f;
-    if (POST == POST_ELU) {
+    if (POST == POST_NONE) {
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+            const float d = dOut[(int64_t)i * ldd + f];
+            c = fmaf(d, hp[f], c);
+            hp[f] = d;
+        }
+    } else if (POST == POST_ELU) {
 #pragma unroll
         for (int f = 0; f < F; ++f) {
             float d = dOut[(int64_t)i * ldd + f] * (hp[f] > 0.f ? 1.f : expf(hp[f]));
@@ -462,6 +476,27 @@ __global__ void gat_pool_bwd_kernel(const float* __restrict__ dcat, const float*
 }
 
 
+// ---- aggregate-first first layer (single head, fin < HID: the inter level, 16 -> 72) ----
+// sum_j a_ij (x_j W) = (sum_j a_ij x_j) W = xbar W: the attention (forward and backward) runs on the fin-wide input rows
+// instead of the HID-wide Wh rows; the scores are x . u with u = W [a1 | a2] (stored [2][fin]).
+__global__ void elu_rows_kernel(float* __restrict__ v, int64_t count) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < count) v[e] = elu1(v[e]);
+}
+// d(hp) = d(y) * elu'(hp) with elu'(hp) read back from y = elu(hp): 1 for y > 0, else exp(hp) = y + 1
+__global__ void elu_grad_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ out, int64_t count) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < count) { const float yy = y[e]; out[e] = dy[e] * (yy > 0.f ? 1.f : yy + 1.f); }
+}
+// gW [fin][HID] += du1 a1^T + du2 a2^T   (du [2][fin], a [2][HID])
+__global__ void outer2_add_kernel(const float* __restrict__ du, const float* __restrict__ a, float* __restrict__ gW, int fin, int hid) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < fin * hid) {
+        const int f = e / hid, h = e % hid;
+        gW[e] += du[f] * a[h] + du[fin + f] * a[hid + h];
+    }
+}
+
 struct Level {   // buffers of one GAT (intra or inter)
     float *Wh1, *st1, *x1a, *Wh2, *st2, *U, *Xo;
 };
@@ -501,6 +536,25 @@ static int gat_level_fwd(const float* feat, int fin, const float* W, const float
         SGX_CUDA(cudaMemsetAsync(L.Xo, 0, (size_t)n * OUT * sizeof(float), st));
         SGX_CUDA(cudaMemsetAsync(L.U, 0, (size_t)n * OUT * sizeof(float), st));
     }
+    if (MODE == INTER && nh == 1 && fin == OUT) {
+        // aggregate-first: the Wh1 buffer holds xbar [n][OUT], u [2][OUT] (and du [2][OUT] in the backward) instead
+        float* xbar = L.Wh1;
+        float* u = L.Wh1 + n * OUT;
+        if ((rc = gemm(a, HID, 1, W, 1, HID, u, fin, 2, fin, HID, 0, 0, st))) return rc;              // u = [a1; a2] W^T
+        if ((rc = gemm(feat, fin, 1, u, 1, fin, L.st1, 2, n, 2, fin, 0, 0, st))) return rc;           // (s, t) = feat u^T
+        if (dense) {
+            SGX_CUDA(cudaMemsetAsync(xbar, 0, (size_t)n * OUT * sizeof(float), st));       // rows off the leaders stay zero
+            att_fwd_scene_kernel<OUT, MODE, POST_NONE><<<dgrid, 256, 0, st>>>(feat, fin, L.st1, 2, leader, dense->scene_start,
+                                                                              alpha, xbar, OUT, nullptr);
+        }
+        else
+            att_fwd_kernel<OUT, MODE, POST_NONE><<<blocks_for(n, 128), 128, 0, st>>>(feat, fin, L.st1, 2, leader, ps, pe, (int)n,
+                                                                                     alpha, xbar, OUT, nullptr);
+        SGX_LAUNCH_CHECK();
+        if ((rc = gemm(xbar, OUT, 1, W, HID, 1, L.x1a, ldh, n, HID, fin, 0, 0, st))) return rc;       // hp = xbar W
+        elu_rows_kernel<<<blocks_for(n * HID, 256), 256, 0, st>>>(L.x1a, n * HID);
+        SGX_LAUNCH_CHECK();
+    } else
     for (int k = 0; k < nh; ++k) {
         // Wh1[:, k] = feat W_k ;  st1[:, k] = Wh1[:, k] [a1 a2]
         if ((rc = gemm(feat, fin, 1, W + (int64_t)k * fin * HID, HID, 1, L.Wh1 + k * HID, ldh, n, HID, fin, 0, 0, st)))
@@ -550,6 +604,28 @@ static int gat_level_bwd(const float* feat, int fin, const float* W, const float
     if ((rc = gemm(L.x1a, 1, ldh, w.dWh, OUT, 1, gWout, OUT, ldh, OUT, n, 0, 0, st))) return rc;
     if ((rc = gemm(w.dWh, OUT, 1, Wout, 1, OUT, w.dx1a, ldh, n, ldh, OUT, 0, 0, st))) return rc;
     // ---- heads ----
+    if (MODE == INTER && nh == 1 && fin == OUT) {
+        // aggregated form (see gat_level_fwd): d(hp) = d(x1a) elu'(hp);  dW = xbar^T d(hp);  d(xbar) = d(hp) W^T;  the row /
+        // column roles on the fin-wide rows give d(feat) directly;  du = (ds, dt)^T feat;  dW += du^T [a1; a2];  da = du W
+        const float* xbar = L.Wh1;
+        const float* u = L.Wh1 + n * OUT;
+        float* du = L.Wh1 + n * OUT + 2 * OUT;
+        elu_grad_kernel<<<blocks_for(n * HID, 256), 256, 0, st>>>(w.dx1a, L.x1a, w.dWh, n * HID);
+        SGX_LAUNCH_CHECK();
+        if ((rc = gemm(xbar, 1, OUT, w.dWh, HID, 1, gW, HID, fin, HID, n, 0, 0, st))) return rc;
+        if ((rc = gemm(w.dWh, HID, 1, W, 1, HID, w.dx1a, OUT, n, fin, HID, 0, 0, st))) return rc;     // d(xbar) [n][OUT] (dx1a is consumed)
+        att_bwd_row_kernel<OUT, MODE, POST_NONE><<<nb, 128, 0, st>>>(feat, fin, L.st1, 2, leader, ps, pe, (int)n, alpha, w.dx1a,
+                                                                     OUT, w.dhp, w.stats, w.dst, 2);
+        SGX_LAUNCH_CHECK();
+        att_bwd_col_kernel<OUT, MODE><<<nb, 128, 0, st>>>(feat, fin, L.st1, 2, leader, ps, pe, (int)n, alpha, w.dhp, w.stats, u,
+                                                          dfeat, fin, w.dst, 2);
+        SGX_LAUNCH_CHECK();
+        if ((rc = gemm(w.dst, 1, 2, feat, fin, 1, du, fin, 2, fin, n, 0, 0, st))) return rc;          // du [2][fin]
+        outer2_add_kernel<<<blocks_for(fin * HID, 256), 256, 0, st>>>(du, a, gW, fin, HID);
+        SGX_LAUNCH_CHECK();
+        if ((rc = gemm(du, fin, 1, W, HID, 1, ga, HID, 2, HID, fin, 0, 0, st))) return rc;            // da = du W
+        return SGX_OK;
+    }
     for (int k = 0; k < nh; ++k) {
         att_bwd_row_kernel<HID, MODE, POST_ELU><<<nb, 128, 0, st>>>(L.Wh1 + k * HID, ldh, L.st1 + 2 * k, 2 * nh, leader,
                                                                     ps, pe, (int)n, alpha, w.dx1a + k * HID, ldh, w.dhp,
