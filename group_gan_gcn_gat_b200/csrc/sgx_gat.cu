@@ -37,19 +37,43 @@ __device__ __forceinline__ bool is_neighbour(const int32_t* __restrict__ leader,
 }
 __device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : expm1f(v); }
 
+// Neighbour walk of one node.  INTRA with a member list (next != nullptr): the members of the node's group from the leader
+// (= its first member) on, ascending -- the order of the scan, so the sums are bit-identical; otherwise a scan of the
+// scene [b, e) with the membership test.  A scan costs ~4 instructions per NON-member: at 1024 pedestrians per scene and
+// groups of two or three that was the whole cost of the intra-level kernels.
+template <int MODE, class Fn>
+__device__ __forceinline__ void for_neighbours(const int32_t* __restrict__ leader, const int32_t* __restrict__ next, int b,
+                                               int e, int li, Fn&& fn) {
+    if (MODE == INTRA && next != nullptr) {
+        for (int q = li; q >= 0; q = next[q]) fn(q);
+    } else {
+        for (int q = b; q < e; ++q)
+            if (is_neighbour<MODE>(leader, li, q)) fn(q);
+    }
+}
+// next[p] = the next member of p's group after p in its scene, -1 for the last one
+__global__ void group_next_kernel(const int32_t* __restrict__ leader, const int32_t* __restrict__ ped_end, int n,
+                                  int32_t* __restrict__ next) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int e = ped_end[p], l = leader[p];
+    int q = p + 1;
+    while (q < e && leader[q] != l) ++q;
+    next[p] = q < e ? q : -1;
+}
+
 // one thread per node: hp_i = sum_j softmax_j(lrelu(s_i + t_j)) Wh_j  over the node's neighbourhood
 template <int F, int MODE>
 __device__ __forceinline__ void attend(const float* __restrict__ Wh, int ldw, const float* __restrict__ st, int lds,
                                        const int32_t* __restrict__ leader, int b, int e, int li, float s_i,
-                                       float alpha, float (&hp)[F], float& m_out, float& den_out) {
+                                       float alpha, float (&hp)[F], float& m_out, float& den_out,
+                                       const int32_t* __restrict__ next = nullptr) {
     float m = -INFINITY;
-    for (int q = b; q < e; ++q)
-        if (is_neighbour<MODE>(leader, li, q)) m = fmaxf(m, lrelu(s_i + st[(int64_t)q * lds + 1], alpha));
+    for_neighbours<MODE>(leader, next, b, e, li, [&](int q) { m = fmaxf(m, lrelu(s_i + st[(int64_t)q * lds + 1], alpha)); });
     float den = 0.f;
 #pragma unroll
     for (int f = 0; f < F; ++f) hp[f] = 0.f;
-    for (int q = b; q < e; ++q) {
-        if (!is_neighbour<MODE>(leader, li, q)) continue;
+    for_neighbours<MODE>(leader, next, b, e, li, [&](int q) {
         const float w = expf(lrelu(s_i + st[(int64_t)q * lds + 1], alpha) - m);
         den += w;
         const float4* row = reinterpret_cast<const float4*>(Wh + (int64_t)q * ldw);
@@ -59,7 +83,7 @@ __device__ __forceinline__ void attend(const float* __restrict__ Wh, int ldw, co
             hp[4 * f] = fmaf(w, v.x, hp[4 * f]); hp[4 * f + 1] = fmaf(w, v.y, hp[4 * f + 1]);
             hp[4 * f + 2] = fmaf(w, v.z, hp[4 * f + 2]); hp[4 * f + 3] = fmaf(w, v.w, hp[4 * f + 3]);
         }
-    }
+    });
     const float inv = 1.f / den;
 #pragma unroll
     for (int f = 0; f < F; ++f) hp[f] *= inv;
@@ -72,7 +96,7 @@ __global__ void __launch_bounds__(128)
 att_fwd_kernel(const float* __restrict__ Wh, int ldw, const float* __restrict__ st, int lds,
                const int32_t* __restrict__ leader, const int32_t* __restrict__ ped_start,
                const int32_t* __restrict__ ped_end, int n, float alpha, float* __restrict__ out, int ldo,
-               float* __restrict__ U) {
+               float* __restrict__ U, const int32_t* __restrict__ next = nullptr) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float hp[F];
@@ -86,7 +110,7 @@ att_fwd_kernel(const float* __restrict__ Wh, int ldw, const float* __restrict__ 
     }
     float m, den;
     attend<F, MODE>(Wh, ldw, st, lds, leader, ped_start[i], ped_end[i], leader[i], st[(int64_t)i * lds], alpha, hp, m,
-                    den);
+                    den, next);
     if (POST == POST_NONE) {
 #pragma unroll
         for (int f = 0; f < F; ++f) out[(int64_t)i * ldo + f] = hp[f];
@@ -283,7 +307,7 @@ att_bwd_row_kernel(const float* __restrict__ Wh, int ldw, const float* __restric
                    const int32_t* __restrict__ leader, const int32_t* __restrict__ ped_start,
                    const int32_t* __restrict__ ped_end, int n, float alpha, const float* __restrict__ dOut, int ldd,
                    float* __restrict__ dhp_out /*[n][F]*/, float* __restrict__ stats /*[n][3]*/,
-                   float* __restrict__ dst, int ldds) {
+                   float* __restrict__ dst, int ldds, const int32_t* __restrict__ next = nullptr) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float hp[F];
@@ -297,7 +321,7 @@ att_bwd_row_kernel(const float* __restrict__ Wh, int ldw, const float* __restric
     const int b = ped_start[i], e = ped_end[i], li = leader[i];
     const float s_i = st[(int64_t)i * lds];
     float m, den;
-    attend<F, MODE>(Wh, ldw, st, lds, leader, b, e, li, s_i, alpha, hp, m, den);
+    attend<F, MODE>(Wh, ldw, st, lds, leader, b, e, li, s_i, alpha, hp, m, den, next);
     float c = 0.f;
     if (POST == POST_NONE) {
 #pragma unroll
@@ -336,8 +360,7 @@ att_bwd_row_kernel(const float* __restrict__ Wh, int ldw, const float* __restric
     // ds_i = sum_j alpha_ij (dhp_i . Wh_j - c_i) lrelu'(s_i + t_j)
     float ds = 0.f;
     const float inv_den = 1.f / den;
-    for (int q = b; q < e; ++q) {
-        if (!is_neighbour<MODE>(leader, li, q)) continue;
+    for_neighbours<MODE>(leader, next, b, e, li, [&](int q) {
         const float pre = s_i + st[(int64_t)q * lds + 1];
         const float a_ij = expf(lrelu(pre, alpha) - m) * inv_den;
         const float4* row = reinterpret_cast<const float4*>(Wh + (int64_t)q * ldw);
@@ -349,7 +372,7 @@ att_bwd_row_kernel(const float* __restrict__ Wh, int ldw, const float* __restric
             dot = fmaf(hp[4 * f + 2], v.z, dot); dot = fmaf(hp[4 * f + 3], v.w, dot);
         }
         ds += a_ij * (dot - c) * (pre > 0.f ? 1.f : alpha);
-    }
+    });
     dst[(int64_t)i * ldds] = ds;
 }
 
@@ -361,7 +384,8 @@ att_bwd_col_kernel(const float* __restrict__ Wh, int ldw, const float* __restric
                    const int32_t* __restrict__ leader, const int32_t* __restrict__ ped_start,
                    const int32_t* __restrict__ ped_end, int n, float alpha, const float* __restrict__ dhp,
                    const float* __restrict__ stats, const float* __restrict__ avec /*[2F]*/,
-                   float* __restrict__ dWh, int lddw, float* __restrict__ dst, int ldds) {
+                   float* __restrict__ dWh, int lddw, float* __restrict__ dst, int ldds,
+                   const int32_t* __restrict__ next = nullptr) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     if (!node_active<MODE>(leader, j)) {
@@ -384,8 +408,7 @@ att_bwd_col_kernel(const float* __restrict__ Wh, int ldw, const float* __restric
     for (int f = 0; f < F; ++f) acc[f] = 0.f;
     const float t_j = st[(int64_t)j * lds + 1];
     float dt = 0.f;
-    for (int i = b; i < e; ++i) {
-        if (!is_neighbour<MODE>(leader, lj, i)) continue;
+    for_neighbours<MODE>(leader, next, b, e, lj, [&](int i) {
         const float pre = st[(int64_t)i * lds] + t_j;
         const float m = stats[3 * (int64_t)i], den = stats[3 * (int64_t)i + 1], c = stats[3 * (int64_t)i + 2];
         const float a_ij = expf(lrelu(pre, alpha) - m) / den;
@@ -400,7 +423,7 @@ att_bwd_col_kernel(const float* __restrict__ Wh, int ldw, const float* __restric
             acc[4 * f + 2] = fmaf(a_ij, v.z, acc[4 * f + 2]); acc[4 * f + 3] = fmaf(a_ij, v.w, acc[4 * f + 3]);
         }
         dt += a_ij * (dot - c) * (pre > 0.f ? 1.f : alpha);
-    }
+    });
     const float ds = dst[(int64_t)j * ldds];
     dst[(int64_t)j * ldds + 1] = dt;
 #pragma unroll
@@ -412,7 +435,7 @@ att_bwd_col_kernel(const float* __restrict__ Wh, int ldw, const float* __restric
 template <int OUT>
 __global__ void gat_pool_kernel(const float* __restrict__ X1, const int32_t* __restrict__ leader,
                                 const int32_t* __restrict__ gsize, const int32_t* __restrict__ ped_end, int batch,
-                                float* __restrict__ Xg) {
+                                float* __restrict__ Xg, const int32_t* __restrict__ next = nullptr) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= batch) return;
     float acc[OUT];
@@ -420,11 +443,10 @@ __global__ void gat_pool_kernel(const float* __restrict__ X1, const int32_t* __r
     for (int o = 0; o < OUT; ++o) acc[o] = 0.f;
     if (leader[p] == p) {
         const float a = __frcp_rn((float)gsize[p]);
-        for (int q = p; q < ped_end[p]; ++q) {
-            if (leader[q] != p) continue;
+        for_neighbours<INTRA>(leader, next, p, ped_end[p], p, [&](int q) {
 #pragma unroll
             for (int o = 0; o < OUT; ++o) acc[o] = fmaf(a, X1[(int64_t)q * OUT + o], acc[o]);
-        }
+        });
     }
 #pragma unroll
     for (int o = 0; o < OUT; ++o) Xg[(int64_t)p * OUT + o] = acc[o];
@@ -446,7 +468,7 @@ __global__ void gat_cat_kernel(const float* __restrict__ X1, const float* __rest
 template <int OUT>
 __global__ void gat_unpool_bwd_kernel(const float* __restrict__ dcat, const int32_t* __restrict__ leader,
                                       const int32_t* __restrict__ gsize, const int32_t* __restrict__ ped_end,
-                                      int batch, float* __restrict__ dYg) {
+                                      int batch, float* __restrict__ dYg, const int32_t* __restrict__ next = nullptr) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= batch) return;
     float acc[OUT];
@@ -454,11 +476,10 @@ __global__ void gat_unpool_bwd_kernel(const float* __restrict__ dcat, const int3
     for (int o = 0; o < OUT; ++o) acc[o] = 0.f;
     if (leader[p] == p) {
         const float a = __frcp_rn((float)gsize[p]);
-        for (int q = p; q < ped_end[p]; ++q) {
-            if (leader[q] != p) continue;
+        for_neighbours<INTRA>(leader, next, p, ped_end[p], p, [&](int q) {
 #pragma unroll
             for (int o = 0; o < OUT; ++o) acc[o] = fmaf(a, dcat[(int64_t)q * 2 * OUT + OUT + o], acc[o]);
-        }
+        });
     }
 #pragma unroll
     for (int o = 0; o < OUT; ++o) dYg[(int64_t)p * OUT + o] = acc[o];
@@ -505,6 +526,7 @@ struct GatWs {
     float *Xg, *cat;
     // backward
     float *dcat, *dYg, *dXg, *dX1, *dhp, *stats, *dst, *dWh, *dx1a;
+    int32_t* next;        // next member of the pedestrian's group (group_next_kernel)
 };
 
 static int64_t carve_gat(Carver& c, GatWs& w, int64_t n, int nh) {
@@ -518,6 +540,7 @@ static int64_t carve_gat(Carver& c, GatWs& w, int64_t n, int nh) {
     w.dcat = c.take<float>(n * 2 * OUT); w.dYg = c.take<float>(n * OUT); w.dXg = c.take<float>(n * OUT);
     w.dX1 = c.take<float>(n * OUT); w.dhp = c.take<float>(n * HID); w.stats = c.take<float>(n * 3);
     w.dst = c.take<float>(n * nh * 2); w.dWh = c.take<float>(n * nh * HID); w.dx1a = c.take<float>(n * nh * HID);
+    w.next = c.take<int32_t>(n);
     return c.off;
 }
 
@@ -527,7 +550,8 @@ struct DenseInfo { const int32_t* scene_start; int n_scenes; int max_scene; };
 template <int MODE>
 static int gat_level_fwd(const float* feat, int fin, const float* W, const float* a, const float* Wout,
                          const float* aout, int nh, float alpha, const int32_t* leader, const int32_t* ps,
-                         const int32_t* pe, int64_t n, Level& L, cudaStream_t st, const DenseInfo* dense = nullptr) {
+                         const int32_t* pe, int64_t n, Level& L, cudaStream_t st, const DenseInfo* dense = nullptr,
+                         const int32_t* next = nullptr) {
     int rc;
     const int ldh = nh * HID;
     const dim3 dgrid(dense ? (unsigned)((dense->max_scene + DENSE_ROWS - 1) / DENSE_ROWS) : 1u, dense ? (unsigned)dense->n_scenes : 1u);
@@ -549,7 +573,7 @@ static int gat_level_fwd(const float* feat, int fin, const float* W, const float
         }
         else
             att_fwd_kernel<OUT, MODE, POST_NONE><<<blocks_for(n, 128), 128, 0, st>>>(feat, fin, L.st1, 2, leader, ps, pe, (int)n,
-                                                                                     alpha, xbar, OUT, nullptr);
+                                                                                     alpha, xbar, OUT, nullptr, next);
         SGX_LAUNCH_CHECK();
         if ((rc = gemm(xbar, OUT, 1, W, HID, 1, L.x1a, ldh, n, HID, fin, 0, 0, st))) return rc;       // hp = xbar W
         elu_rows_kernel<<<blocks_for(n * HID, 256), 256, 0, st>>>(L.x1a, n * HID);
@@ -568,7 +592,7 @@ static int gat_level_fwd(const float* feat, int fin, const float* W, const float
                                                                             ldh, nullptr);
         else
             att_fwd_kernel<HID, MODE, POST_ELU><<<blocks_for(n, 128), 128, 0, st>>>(
-                L.Wh1 + k * HID, ldh, L.st1 + 2 * k, 2 * nh, leader, ps, pe, (int)n, alpha, L.x1a + k * HID, ldh, nullptr);
+                L.Wh1 + k * HID, ldh, L.st1 + 2 * k, 2 * nh, leader, ps, pe, (int)n, alpha, L.x1a + k * HID, ldh, nullptr, next);
         SGX_LAUNCH_CHECK();
     }
     if ((rc = gemm(L.x1a, ldh, 1, Wout, OUT, 1, L.Wh2, OUT, n, OUT, ldh, 0, 0, st))) return rc;
@@ -578,7 +602,7 @@ static int gat_level_fwd(const float* feat, int fin, const float* W, const float
                                                                                    dense->scene_start, alpha, L.Xo, OUT, L.U);
     else
         att_fwd_kernel<OUT, MODE, POST_ELU_LOGSOFTMAX><<<blocks_for(n, 128), 128, 0, st>>>(
-            L.Wh2, OUT, L.st2, 2, leader, ps, pe, (int)n, alpha, L.Xo, OUT, L.U);
+            L.Wh2, OUT, L.st2, 2, leader, ps, pe, (int)n, alpha, L.Xo, OUT, L.U, next);
     SGX_LAUNCH_CHECK();
     return SGX_OK;
 }
@@ -594,10 +618,10 @@ static int gat_level_bwd(const float* feat, int fin, const float* W, const float
     const unsigned nb = blocks_for(n, 128);
     // ---- out_att layer ----
     att_bwd_row_kernel<OUT, MODE, POST_ELU_LOGSOFTMAX><<<nb, 128, 0, st>>>(L.Wh2, OUT, L.st2, 2, leader, ps, pe, (int)n,
-                                                                           alpha, dXo, OUT, w.dhp, w.stats, w.dst, 2);
+                                                                           alpha, dXo, OUT, w.dhp, w.stats, w.dst, 2, w.next);
     SGX_LAUNCH_CHECK();
     att_bwd_col_kernel<OUT, MODE><<<nb, 128, 0, st>>>(L.Wh2, OUT, L.st2, 2, leader, ps, pe, (int)n, alpha, w.dhp,
-                                                      w.stats, aout, w.dWh, OUT, w.dst, 2);
+                                                      w.stats, aout, w.dWh, OUT, w.dst, 2, w.next);
     SGX_LAUNCH_CHECK();
     // d(aout) [2][OUT] = dst^T Wh2 ; dWout = x1a^T dWh2 ; dx1a = dWh2 Wout^T
     if ((rc = gemm(w.dst, 1, 2, L.Wh2, OUT, 1, gaout, OUT, 2, OUT, n, 0, 0, st))) return rc;
@@ -629,11 +653,11 @@ static int gat_level_bwd(const float* feat, int fin, const float* W, const float
     for (int k = 0; k < nh; ++k) {
         att_bwd_row_kernel<HID, MODE, POST_ELU><<<nb, 128, 0, st>>>(L.Wh1 + k * HID, ldh, L.st1 + 2 * k, 2 * nh, leader,
                                                                     ps, pe, (int)n, alpha, w.dx1a + k * HID, ldh, w.dhp,
-                                                                    w.stats, w.dst, 2);
+                                                                    w.stats, w.dst, 2, w.next);
         SGX_LAUNCH_CHECK();
         att_bwd_col_kernel<HID, MODE><<<nb, 128, 0, st>>>(L.Wh1 + k * HID, ldh, L.st1 + 2 * k, 2 * nh, leader, ps, pe,
                                                           (int)n, alpha, w.dhp, w.stats, a + (int64_t)k * 2 * HID,
-                                                          w.dWh, HID, w.dst, 2);
+                                                          w.dWh, HID, w.dst, 2, w.next);
         SGX_LAUNCH_CHECK();
         if ((rc = gemm(w.dst, 1, 2, L.Wh1 + k * HID, ldh, 1, ga + (int64_t)k * 2 * HID, HID, 2, HID, n, 0, 0, st)))
             return rc;
@@ -650,8 +674,10 @@ static int gat_forward(const float* x, const int32_t* leader, const int32_t* gsi
                        const float* Wo, const float* bo, float alpha, int nh, int IN, int FIN, float* out, GatWs& w,
                        cudaStream_t st, const DenseInfo* dense = nullptr) {
     int rc;
-    if ((rc = gat_level_fwd<INTRA>(x, IN, Wi, ai, Wio, aio, nh, alpha, leader, ps, pe, n, w.intra, st, dense))) return rc;
-    gat_pool_kernel<OUT><<<blocks_for(n, 128), 128, 0, st>>>(w.intra.Xo, leader, gsize, pe, (int)n, w.Xg);
+    group_next_kernel<<<blocks_for(n, 128), 128, 0, st>>>(leader, pe, (int)n, w.next);      // member lists for the intra level
+    SGX_LAUNCH_CHECK();
+    if ((rc = gat_level_fwd<INTRA>(x, IN, Wi, ai, Wio, aio, nh, alpha, leader, ps, pe, n, w.intra, st, dense, w.next))) return rc;
+    gat_pool_kernel<OUT><<<blocks_for(n, 128), 128, 0, st>>>(w.intra.Xo, leader, gsize, pe, (int)n, w.Xg, w.next);
     SGX_LAUNCH_CHECK();
     if ((rc = gat_level_fwd<INTER>(w.Xg, OUT, We, ae, Weo, aeo, nh, alpha, leader, ps, pe, n, w.inter, st, dense))) return rc;
     gat_cat_kernel<OUT><<<blocks_for(n * OUT, 256), 256, 0, st>>>(w.intra.Xo, w.inter.Xo, leader, gsize, (int)n, w.cat);
@@ -1491,7 +1517,7 @@ static int gat_encoder_bwd_impl(const DenseInfo* dense, const float* x, const fl
     SGX_CUDA(cudaMemsetAsync(grad_bo, 0, (size_t)FIN * 4, st));
     colsum_kernel<<<dim3((FIN + 31) / 32, 64), 256, 0, st>>>(grad_out, n, FIN, grad_bo);
     SGX_LAUNCH_CHECK();
-    gat_unpool_bwd_kernel<OUT><<<blocks_for(n, 128), 128, 0, st>>>(w.dcat, leader, group_size, ped_end, (int)n, w.dYg);
+    gat_unpool_bwd_kernel<OUT><<<blocks_for(n, 128), 128, 0, st>>>(w.dcat, leader, group_size, ped_end, (int)n, w.dYg, w.next);
     SGX_LAUNCH_CHECK();
     if ((rc = gat_level_bwd<INTER>(w.Xg, OUT, We, ae, Weo, aeo, n_heads, alpha, leader, ped_start, ped_end, n, w.inter, w,
                                    w.dYg, w.dXg, grad_We, grad_ae, grad_Weo, grad_aeo, st)))
