@@ -72,6 +72,35 @@ def test_tc_forwards_vs_oracle_and_mma(sizes):
         assert torch.equal(out_labels, out_arrays.detach()), '%s: in-kernel group structure differs from sgx_group_ids' % name
 
 
+@pytest.mark.parametrize('alpha', [0.0, 0.05, 1.0, -0.3])
+def test_gat_leaky_relu_slopes(alpha):
+    """The one-read softmax max pass of the tcgen05 kernel relies on lrelu being monotone (alpha >= 0) and falls back to
+    the per-neighbour form for a negative slope; forward (tcgen05 and mma.sync) against the oracle, and the single-launch
+    backward (aggregated inter layer, d(We) / d(ae) folded in the reduction) against autograd through the oracle."""
+    import group_gan_gcn_gat_b200.modules as M
+    sizes = [9, 32, 1, 17, 5, 28, 3]
+    sse, x, pos, labs = batch_of(sizes, 77)
+    gat = M.GATEncoder(n_units=None, n_heads=1, dropout=0, alpha=alpha)
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in gat.state_dict().items()}
+    xr = x.clone().requires_grad_(True)
+    ref = O.gat_encoder(xr, sse, pos, labs, sd, '', alpha, 1)
+    up = torch.randn_like(ref)
+    (ref * up).sum().backward()
+    gat = gat.to(DEV)
+    args = (sse.to(DEV), pos.to(DEV), labs.to(DEV))
+    with torch.no_grad():
+        close(gat(x.to(DEV), *args), ref, 1e-5, 'tcgen05 forward, alpha %g' % alpha)
+        close(with_option('graph_tc', 0, lambda: gat(x.to(DEV), *args)), ref, 1e-5, 'mma.sync forward, alpha %g' % alpha)
+    xg = x.to(DEV).requires_grad_(True)
+    (gat(xg, *args) * up.to(DEV)).sum().backward()
+    close(xg.grad, xr.grad, 2e-5, 'd(x), alpha %g' % alpha)
+    floor = max(float(v.grad.abs().max()) for v in sd.values())
+    for name, p_ in gat.named_parameters():
+        g_ref = sd[name].grad
+        err = float((p_.grad.cpu().double() - g_ref.double()).abs().max())
+        assert err <= 1e-4 * max(floor, 1e-6), 'd(%s), alpha %g: %.3e (scale %.3e)' % (name, alpha, err, floor)
+
+
 @pytest.mark.parametrize('in_dim,final', [(32, 24), (32, 32), (40, 32)])
 def test_gcn_tc_every_built_instance(in_dim, final):
     sizes = [4, 32, 9, 1, 1, 17, 30, 2, 2, 8]
