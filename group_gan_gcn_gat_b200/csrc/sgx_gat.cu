@@ -37,29 +37,65 @@ __device__ __forceinline__ bool is_neighbour(const int32_t* __restrict__ leader,
 }
 __device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : expm1f(v); }
 
-// Neighbour walk of one node.  INTRA with a member list (next != nullptr): the members of the node's group from the leader
-// (= its first member) on, ascending -- the order of the scan, so the sums are bit-identical; otherwise a scan of the
-// scene [b, e) with the membership test.  A scan costs ~4 instructions per NON-member: at 1024 pedestrians per scene and
-// groups of two or three that was the whole cost of the intra-level kernels.
+// Group lists of a batch (group_lists_kernel), all optional:
+//   next[p]      the next member of p's group after p in its scene, -1 for the last one (the leader is the first member)
+//   lead_list    the scene's leaders compacted to the front of its slot range: lead_list[b + k] = k-th leader, k < G
+//   lead_cnt[b]  G, at the scene's first slot b
+struct Lists {
+    const int32_t* next = nullptr;
+    const int32_t* lead_list = nullptr;
+    const int32_t* lead_cnt = nullptr;
+};
+// Neighbour walk of one node.  With the lists: the members of the node's group from the leader on (INTRA) or the scene's
+// leaders (INTER), ascending -- the order of the scan, so the sums are bit-identical; without: a scan of the scene [b, e)
+// with the membership test.  A scan costs ~4 instructions per NON-member: at 1024 pedestrians per scene and groups of
+// two or three that was the whole cost of the intra-level kernels.
 template <int MODE, class Fn>
-__device__ __forceinline__ void for_neighbours(const int32_t* __restrict__ leader, const int32_t* __restrict__ next, int b,
-                                               int e, int li, Fn&& fn) {
-    if (MODE == INTRA && next != nullptr) {
-        for (int q = li; q >= 0; q = next[q]) fn(q);
+__device__ __forceinline__ void for_neighbours(const int32_t* __restrict__ leader, const Lists& lists, int b, int e, int li,
+                                               Fn&& fn) {
+    if (MODE == INTRA && lists.next != nullptr) {
+        for (int q = li; q >= 0; q = lists.next[q]) fn(q);
+    } else if (MODE == INTER && lists.lead_list != nullptr) {
+        const int ke = b + lists.lead_cnt[b];
+        for (int k = b; k < ke; ++k) fn(lists.lead_list[k]);
     } else {
         for (int q = b; q < e; ++q)
             if (is_neighbour<MODE>(leader, li, q)) fn(q);
     }
 }
-// next[p] = the next member of p's group after p in its scene, -1 for the last one
-__global__ void group_next_kernel(const int32_t* __restrict__ leader, const int32_t* __restrict__ ped_end, int n,
-                                  int32_t* __restrict__ next) {
+// The INTER kernels run one thread per SLOT; with a leader list the k-th slot of a scene acts for the scene's k-th
+// leader, so the active threads are the first G of every scene (full warps) instead of the ~43 % of lanes that happen
+// to be leaders.  Returns the node the thread acts for, or -1; *own_inactive: the slot's own node is not a leader and
+// its output rows must be zeroed by this thread.
+template <int MODE>
+__device__ __forceinline__ int acting_node(const int32_t* __restrict__ leader, const int32_t* __restrict__ ped_start,
+                                           const Lists& lists, int slot, bool* own_inactive) {
+    *own_inactive = !node_active<MODE>(leader, slot);
+    if (MODE == INTER && lists.lead_list != nullptr) {
+        const int b = ped_start[slot];
+        return (slot - b) < lists.lead_cnt[b] ? lists.lead_list[slot] : -1;
+    }
+    return *own_inactive ? -1 : slot;
+}
+__global__ void group_lists_kernel(const int32_t* __restrict__ leader, const int32_t* __restrict__ ped_start,
+                                   const int32_t* __restrict__ ped_end, int n, int32_t* __restrict__ next,
+                                   int32_t* __restrict__ lead_list, int32_t* __restrict__ lead_cnt) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
-    const int e = ped_end[p], l = leader[p];
+    const int b = ped_start[p], e = ped_end[p], l = leader[p];
     int q = p + 1;
     while (q < e && leader[q] != l) ++q;
     next[p] = q < e ? q : -1;
+    if (l == p) {                                            // rank among the scene's leaders
+        int k = 0;
+        for (q = b; q < p; ++q) k += (leader[q] == q) ? 1 : 0;
+        lead_list[b + k] = p;
+    }
+    if (p == b) {
+        int G = 0;
+        for (q = b; q < e; ++q) G += (leader[q] == q) ? 1 : 0;
+        lead_cnt[b] = G;
+    }
 }
 
 // one thread per node: hp_i = sum_j softmax_j(lrelu(s_i + t_j)) Wh_j  over the node's neighbourhood
@@ -67,7 +103,7 @@ template <int F, int MODE>
 __device__ __forceinline__ void attend(const float* __restrict__ Wh, int ldw, const float* __restrict__ st, int lds,
                                        const int32_t* __restrict__ leader, int b, int e, int li, float s_i,
                                        float alpha, float (&hp)[F], float& m_out, float& den_out,
-                                       const int32_t* __restrict__ next = nullptr) {
+                                       Lists next = Lists()) {
     float m = -INFINITY;
     for_neighbours<MODE>(leader, next, b, e, li, [&](int q) { m = fmaxf(m, lrelu(s_i + st[(int64_t)q * lds + 1], alpha)); });
     float den = 0.f;
@@ -96,7 +132,7 @@ __global__ void __launch_bounds__(128)
 att_fwd_kernel(const float* __restrict__ Wh, int ldw, const float* __restrict__ st, int lds,
                const int32_t* __restrict__ leader, const int32_t* __restrict__ ped_start,
                const int32_t* __restrict__ ped_end, int n, float alpha, float* __restrict__ out, int ldo,
-               float* __restrict__ U, const int32_t* __restrict__ next = nullptr) {
+               float* __restrict__ U, Lists next = Lists()) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float hp[F];
@@ -307,17 +343,19 @@ att_bwd_row_kernel(const float* __restrict__ Wh, int ldw, const float* __restric
                    const int32_t* __restrict__ leader, const int32_t* __restrict__ ped_start,
                    const int32_t* __restrict__ ped_end, int n, float alpha, const float* __restrict__ dOut, int ldd,
                    float* __restrict__ dhp_out /*[n][F]*/, float* __restrict__ stats /*[n][3]*/,
-                   float* __restrict__ dst, int ldds, const int32_t* __restrict__ next = nullptr) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+                   float* __restrict__ dst, int ldds, Lists next = Lists()) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n) return;
     float hp[F];
-    if (!node_active<MODE>(leader, i)) {
+    bool own_inactive;
+    const int i = acting_node<MODE>(leader, ped_start, next, slot, &own_inactive);
+    if (own_inactive) {
 #pragma unroll
-        for (int f = 0; f < F; ++f) dhp_out[(int64_t)i * F + f] = 0.f;
-        stats[3 * (int64_t)i] = 0.f; stats[3 * (int64_t)i + 1] = 1.f; stats[3 * (int64_t)i + 2] = 0.f;
-        dst[(int64_t)i * ldds] = 0.f;
-        return;
+        for (int f = 0; f < F; ++f) dhp_out[(int64_t)slot * F + f] = 0.f;
+        stats[3 * (int64_t)slot] = 0.f; stats[3 * (int64_t)slot + 1] = 1.f; stats[3 * (int64_t)slot + 2] = 0.f;
+        dst[(int64_t)slot * ldds] = 0.f;
     }
+    if (i < 0) return;
     const int b = ped_start[i], e = ped_end[i], li = leader[i];
     const float s_i = st[(int64_t)i * lds];
     float m, den;
@@ -385,15 +423,17 @@ att_bwd_col_kernel(const float* __restrict__ Wh, int ldw, const float* __restric
                    const int32_t* __restrict__ ped_end, int n, float alpha, const float* __restrict__ dhp,
                    const float* __restrict__ stats, const float* __restrict__ avec /*[2F]*/,
                    float* __restrict__ dWh, int lddw, float* __restrict__ dst, int ldds,
-                   const int32_t* __restrict__ next = nullptr) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    if (!node_active<MODE>(leader, j)) {
+                   Lists next = Lists()) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n) return;
+    bool own_inactive;
+    const int j = acting_node<MODE>(leader, ped_start, next, slot, &own_inactive);
+    if (own_inactive) {
 #pragma unroll
-        for (int f = 0; f < F; ++f) dWh[(int64_t)j * lddw + f] = 0.f;
-        dst[(int64_t)j * ldds + 1] = 0.f;
-        return;
+        for (int f = 0; f < F; ++f) dWh[(int64_t)slot * lddw + f] = 0.f;
+        dst[(int64_t)slot * ldds + 1] = 0.f;
     }
+    if (j < 0) return;
     const int b = ped_start[j], e = ped_end[j], lj = leader[j];
     float whj[F], acc[F];
     {
@@ -435,7 +475,7 @@ att_bwd_col_kernel(const float* __restrict__ Wh, int ldw, const float* __restric
 template <int OUT>
 __global__ void gat_pool_kernel(const float* __restrict__ X1, const int32_t* __restrict__ leader,
                                 const int32_t* __restrict__ gsize, const int32_t* __restrict__ ped_end, int batch,
-                                float* __restrict__ Xg, const int32_t* __restrict__ next = nullptr) {
+                                float* __restrict__ Xg, Lists next = Lists()) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= batch) return;
     float acc[OUT];
@@ -468,7 +508,7 @@ __global__ void gat_cat_kernel(const float* __restrict__ X1, const float* __rest
 template <int OUT>
 __global__ void gat_unpool_bwd_kernel(const float* __restrict__ dcat, const int32_t* __restrict__ leader,
                                       const int32_t* __restrict__ gsize, const int32_t* __restrict__ ped_end,
-                                      int batch, float* __restrict__ dYg, const int32_t* __restrict__ next = nullptr) {
+                                      int batch, float* __restrict__ dYg, Lists next = Lists()) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= batch) return;
     float acc[OUT];
@@ -526,7 +566,8 @@ struct GatWs {
     float *Xg, *cat;
     // backward
     float *dcat, *dYg, *dXg, *dX1, *dhp, *stats, *dst, *dWh, *dx1a;
-    int32_t* next;        // next member of the pedestrian's group (group_next_kernel)
+    int32_t *next, *lead_list, *lead_cnt;     // group_lists_kernel
+    Lists lists() const { Lists l; l.next = next; l.lead_list = lead_list; l.lead_cnt = lead_cnt; return l; }
 };
 
 static int64_t carve_gat(Carver& c, GatWs& w, int64_t n, int nh) {
@@ -540,7 +581,7 @@ static int64_t carve_gat(Carver& c, GatWs& w, int64_t n, int nh) {
     w.dcat = c.take<float>(n * 2 * OUT); w.dYg = c.take<float>(n * OUT); w.dXg = c.take<float>(n * OUT);
     w.dX1 = c.take<float>(n * OUT); w.dhp = c.take<float>(n * HID); w.stats = c.take<float>(n * 3);
     w.dst = c.take<float>(n * nh * 2); w.dWh = c.take<float>(n * nh * HID); w.dx1a = c.take<float>(n * nh * HID);
-    w.next = c.take<int32_t>(n);
+    w.next = c.take<int32_t>(n); w.lead_list = c.take<int32_t>(n); w.lead_cnt = c.take<int32_t>(n);
     return c.off;
 }
 
@@ -551,7 +592,7 @@ template <int MODE>
 static int gat_level_fwd(const float* feat, int fin, const float* W, const float* a, const float* Wout,
                          const float* aout, int nh, float alpha, const int32_t* leader, const int32_t* ps,
                          const int32_t* pe, int64_t n, Level& L, cudaStream_t st, const DenseInfo* dense = nullptr,
-                         const int32_t* next = nullptr) {
+                         Lists next = Lists()) {
     int rc;
     const int ldh = nh * HID;
     const dim3 dgrid(dense ? (unsigned)((dense->max_scene + DENSE_ROWS - 1) / DENSE_ROWS) : 1u, dense ? (unsigned)dense->n_scenes : 1u);
@@ -618,10 +659,10 @@ static int gat_level_bwd(const float* feat, int fin, const float* W, const float
     const unsigned nb = blocks_for(n, 128);
     // ---- out_att layer ----
     att_bwd_row_kernel<OUT, MODE, POST_ELU_LOGSOFTMAX><<<nb, 128, 0, st>>>(L.Wh2, OUT, L.st2, 2, leader, ps, pe, (int)n,
-                                                                           alpha, dXo, OUT, w.dhp, w.stats, w.dst, 2, w.next);
+                                                                           alpha, dXo, OUT, w.dhp, w.stats, w.dst, 2, w.lists());
     SGX_LAUNCH_CHECK();
     att_bwd_col_kernel<OUT, MODE><<<nb, 128, 0, st>>>(L.Wh2, OUT, L.st2, 2, leader, ps, pe, (int)n, alpha, w.dhp,
-                                                      w.stats, aout, w.dWh, OUT, w.dst, 2, w.next);
+                                                      w.stats, aout, w.dWh, OUT, w.dst, 2, w.lists());
     SGX_LAUNCH_CHECK();
     // d(aout) [2][OUT] = dst^T Wh2 ; dWout = x1a^T dWh2 ; dx1a = dWh2 Wout^T
     if ((rc = gemm(w.dst, 1, 2, L.Wh2, OUT, 1, gaout, OUT, 2, OUT, n, 0, 0, st))) return rc;
@@ -639,10 +680,10 @@ static int gat_level_bwd(const float* feat, int fin, const float* W, const float
         if ((rc = gemm(xbar, 1, OUT, w.dWh, HID, 1, gW, HID, fin, HID, n, 0, 0, st))) return rc;
         if ((rc = gemm(w.dWh, HID, 1, W, 1, HID, w.dx1a, OUT, n, fin, HID, 0, 0, st))) return rc;     // d(xbar) [n][OUT] (dx1a is consumed)
         att_bwd_row_kernel<OUT, MODE, POST_NONE><<<nb, 128, 0, st>>>(feat, fin, L.st1, 2, leader, ps, pe, (int)n, alpha, w.dx1a,
-                                                                     OUT, w.dhp, w.stats, w.dst, 2);
+                                                                     OUT, w.dhp, w.stats, w.dst, 2, w.lists());
         SGX_LAUNCH_CHECK();
         att_bwd_col_kernel<OUT, MODE><<<nb, 128, 0, st>>>(feat, fin, L.st1, 2, leader, ps, pe, (int)n, alpha, w.dhp, w.stats, u,
-                                                          dfeat, fin, w.dst, 2);
+                                                          dfeat, fin, w.dst, 2, w.lists());
         SGX_LAUNCH_CHECK();
         if ((rc = gemm(w.dst, 1, 2, feat, fin, 1, du, fin, 2, fin, n, 0, 0, st))) return rc;          // du [2][fin]
         outer2_add_kernel<<<blocks_for(fin * HID, 256), 256, 0, st>>>(du, a, gW, fin, HID);
@@ -653,11 +694,11 @@ static int gat_level_bwd(const float* feat, int fin, const float* W, const float
     for (int k = 0; k < nh; ++k) {
         att_bwd_row_kernel<HID, MODE, POST_ELU><<<nb, 128, 0, st>>>(L.Wh1 + k * HID, ldh, L.st1 + 2 * k, 2 * nh, leader,
                                                                     ps, pe, (int)n, alpha, w.dx1a + k * HID, ldh, w.dhp,
-                                                                    w.stats, w.dst, 2, w.next);
+                                                                    w.stats, w.dst, 2, w.lists());
         SGX_LAUNCH_CHECK();
         att_bwd_col_kernel<HID, MODE><<<nb, 128, 0, st>>>(L.Wh1 + k * HID, ldh, L.st1 + 2 * k, 2 * nh, leader, ps, pe,
                                                           (int)n, alpha, w.dhp, w.stats, a + (int64_t)k * 2 * HID,
-                                                          w.dWh, HID, w.dst, 2, w.next);
+                                                          w.dWh, HID, w.dst, 2, w.lists());
         SGX_LAUNCH_CHECK();
         if ((rc = gemm(w.dst, 1, 2, L.Wh1 + k * HID, ldh, 1, ga + (int64_t)k * 2 * HID, HID, 2, HID, n, 0, 0, st)))
             return rc;
@@ -674,12 +715,12 @@ static int gat_forward(const float* x, const int32_t* leader, const int32_t* gsi
                        const float* Wo, const float* bo, float alpha, int nh, int IN, int FIN, float* out, GatWs& w,
                        cudaStream_t st, const DenseInfo* dense = nullptr) {
     int rc;
-    group_next_kernel<<<blocks_for(n, 128), 128, 0, st>>>(leader, pe, (int)n, w.next);      // member lists for the intra level
+    group_lists_kernel<<<blocks_for(n, 128), 128, 0, st>>>(leader, ps, pe, (int)n, w.next, w.lead_list, w.lead_cnt);
     SGX_LAUNCH_CHECK();
-    if ((rc = gat_level_fwd<INTRA>(x, IN, Wi, ai, Wio, aio, nh, alpha, leader, ps, pe, n, w.intra, st, dense, w.next))) return rc;
-    gat_pool_kernel<OUT><<<blocks_for(n, 128), 128, 0, st>>>(w.intra.Xo, leader, gsize, pe, (int)n, w.Xg, w.next);
+    if ((rc = gat_level_fwd<INTRA>(x, IN, Wi, ai, Wio, aio, nh, alpha, leader, ps, pe, n, w.intra, st, dense, w.lists()))) return rc;
+    gat_pool_kernel<OUT><<<blocks_for(n, 128), 128, 0, st>>>(w.intra.Xo, leader, gsize, pe, (int)n, w.Xg, w.lists());
     SGX_LAUNCH_CHECK();
-    if ((rc = gat_level_fwd<INTER>(w.Xg, OUT, We, ae, Weo, aeo, nh, alpha, leader, ps, pe, n, w.inter, st, dense))) return rc;
+    if ((rc = gat_level_fwd<INTER>(w.Xg, OUT, We, ae, Weo, aeo, nh, alpha, leader, ps, pe, n, w.inter, st, dense, w.lists()))) return rc;
     gat_cat_kernel<OUT><<<blocks_for(n * OUT, 256), 256, 0, st>>>(w.intra.Xo, w.inter.Xo, leader, gsize, (int)n, w.cat);
     SGX_LAUNCH_CHECK();
     if (out) {
@@ -1517,7 +1558,7 @@ static int gat_encoder_bwd_impl(const DenseInfo* dense, const float* x, const fl
     SGX_CUDA(cudaMemsetAsync(grad_bo, 0, (size_t)FIN * 4, st));
     colsum_kernel<<<dim3((FIN + 31) / 32, 64), 256, 0, st>>>(grad_out, n, FIN, grad_bo);
     SGX_LAUNCH_CHECK();
-    gat_unpool_bwd_kernel<OUT><<<blocks_for(n, 128), 128, 0, st>>>(w.dcat, leader, group_size, ped_end, (int)n, w.dYg, w.next);
+    gat_unpool_bwd_kernel<OUT><<<blocks_for(n, 128), 128, 0, st>>>(w.dcat, leader, group_size, ped_end, (int)n, w.dYg, w.lists());
     SGX_LAUNCH_CHECK();
     if ((rc = gat_level_bwd<INTER>(w.Xg, OUT, We, ae, Weo, aeo, n_heads, alpha, leader, ped_start, ped_end, n, w.inter, w,
                                    w.dYg, w.dXg, grad_We, grad_ae, grad_Weo, grad_aeo, st)))
