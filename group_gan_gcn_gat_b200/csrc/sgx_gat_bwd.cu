@@ -2,18 +2,19 @@
 // n_heads = 1, dims 40 / 72 / 16 / 24 -- what autograd does through sgan/models.py:254-294 (GraphAttentionLayer
 // 198-220, GAT 231-237), scene by scene with dense [N,N,2F] tensors.
 //
-// One WARP per chunk of whole scenes, lanes <-> pedestrians, exactly like the forward (sgx_gat.cu): nothing but x,
-// grad_out, the group structure and grad_x touches HBM.  Per chunk the warp
-//   1. recomputes the forward up to Yg (the saved state between forward and backward is nothing),
-//   2. walks the four attention layers in reverse.  Each layer's backward is a ROW role (softmax statistics, c_i = dhp_i.hp_i,
-//      ds_i) and a COLUMN role (dt_j and dWh_j gathered over the symmetric neighbourhood) on lane masks of the actual
-//      neighbours; the layer's forward values are recomputed right before they are needed so that only two 72-wide row
-//      buffers are alive,
-//   3. runs every linear map of the chain rule as a warp-level 3xTF32 tensor-core GEMM: dX = dY W^T straight from the
-//      forward's weight block (warp_gemm_3xtf32_bt) and the per-chunk parameter gradient dW = input^T dY
-//      (warp_gemm_3xtf32_at), accumulated into a per-CTA shared-memory gradient block.
-// The CTA writes its gradient block once; gat_bwd_reduce_kernel sums the (<= 148) blocks in a fixed order, so the
-// result is deterministic for a given grid.
+// A warp PAIR per chunk of whole scenes, lanes <-> pedestrians (the main warp), exactly like the mma.sync forward
+// (sgx_gat.cu): nothing but x, grad_out, the group structure and grad_x touches HBM.  Per chunk
+//   1. the forward is recomputed up to Yg (the saved state between forward and backward is nothing),
+//   2. the four attention layers are walked in reverse.  Each layer's backward is a ROW role (softmax statistics,
+//      c_i = dhp_i.hp_i, ds_i) and a COLUMN role (dt_j and dWh_j gathered over the symmetric neighbourhood) on lane masks of
+//      the actual neighbours; the layer's forward values are recomputed right before they are needed so that only two
+//      72-wide row buffers are alive.  The inter level's first layer runs in its aggregated form (16-wide rows, see the
+//      kernel body),
+//   3. every linear map of the chain rule is a warp-level 3xTF32 tensor-core GEMM, one m-tile per warp of the pair:
+//      dX = dY W^T straight from the forward's weight block (warp_gemm_3xtf32_bt) and the per-chunk parameter gradient
+//      dW = input^T dY (warp_gemm_3xtf32_at_pair), added with red.global into the CTA's own gradient block in HBM.
+// gat_bwd_reduce_kernel sums the (<= 148) blocks in block order; within a block the chunks' contributions arrive as
+// floating-point atomics, so parameter gradients are reproducible to rounding, not bit for bit.
 // The general multi-pass path (sgx_gat.cu: ~35 launches, intermediates in HBM) remains for larger scenes / more heads.
 #include "sgx_common.cuh"
 #include "sgx_gat_fused.cuh"

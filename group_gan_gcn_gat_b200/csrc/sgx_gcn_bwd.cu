@@ -9,9 +9,10 @@
 //               dXg_g = c E2_s V0^T ;  D1_g = (sum_{i in g} dcat_i[:16] + dXg_g) * [x1_g > 0] ;  E_g = (D1_g W1^T) * [h1_g > 0] ;
 //               dx_i = a_i E_g(i) W0^T ;   dWo += dout^T cat, dV1 += k1^T D2, dV0 += n1^T E2, dW1 += h1^T D1, dW0 += m1^T E.
 // (k a and G c are 1 up to one rounding; the reference's own gradient carries the same rounding.)
-// One WARP per chunk of whole scenes, lanes <-> pedestrians; group rows live at the leader's slot, scene rows at the
-// scene's first slot; every linear map is a warp-level 3xTF32 tensor-core GEMM (sgx_warp_mma.cuh), parameter gradients
-// accumulate in a per-CTA shared-memory block that is written once and reduced in block order (deterministic).
+// A warp PAIR per chunk of whole scenes, lanes <-> pedestrians (the main warp); group rows live at the leader's slot, scene
+// rows at the scene's first slot; every linear map is a warp-level 3xTF32 tensor-core GEMM (sgx_warp_mma.cuh), one m-tile
+// per warp of the pair; parameter gradients are added with red.global into the CTA's own gradient block in HBM and the
+// blocks are reduced in block order (reproducible to rounding: the adds within a block are floating-point atomics).
 #include "sgx_common.cuh"
 #include "sgx_warp_mma.cuh"
 
