@@ -126,7 +126,7 @@ def lib():
         raise SgxError('libsgx_b200.so lacks symbols declared in include/sgx.h: %s' % ', '.join(missing))
     _lib = handle
     # switches are resolved HERE, once, and handed to the library as options (no getenv on any call path)
-    for env, opt in (('SGX_LSTM_TC', b'lstm_tc'), ('SGX_GRAPH_TC', b'graph_tc'), ('SGX_GAT_MMA', b'gat_mma'), ('SGX_GCN_MMA', b'gcn_mma')):
+    for env, opt in (('SGX_LSTM_TC', b'lstm_tc'), ('SGX_GRAPH_TC', b'graph_tc'), ('SGX_PDL', b'pdl'), ('SGX_GAT_MMA', b'gat_mma'), ('SGX_GCN_MMA', b'gcn_mma')):
         if env in os.environ:
             val = 0 if os.environ[env] == '0' else 1
             if handle.sgx_set_option(opt, val) == SGX_OK:                      # unknown in this build: ignored
@@ -134,11 +134,11 @@ def lib():
     return _lib
 
 
-OPTIONS = {'lstm_tc': 1, 'graph_tc': 1}      # host-side mirror of the library switches (defaults of the build)
+OPTIONS = {'lstm_tc': 1, 'graph_tc': 1, 'pdl': 1}      # host-side mirror of the library switches (defaults of the build)
 
 
 def set_option(name, value):
-    """sgx_set_option: 'lstm_tc', 'graph_tc' (and 'gat_mma' / 'gcn_mma' in -DSGX_AB_VARIANTS builds)."""
+    """sgx_set_option: 'lstm_tc', 'graph_tc', 'pdl' (and 'gat_mma' / 'gcn_mma' in -DSGX_AB_VARIANTS builds)."""
     check(lib().sgx_set_option(name.encode(), int(value)), 'sgx_set_option')
     OPTIONS[name] = int(value)
 

@@ -33,6 +33,8 @@ static std::atomic<int> g_opt_lstm_tc{1};
 bool opt_lstm_tc() { return g_opt_lstm_tc.load(std::memory_order_relaxed) != 0; }
 static std::atomic<int> g_opt_graph_tc{1};
 bool opt_graph_tc() { return g_opt_graph_tc.load(std::memory_order_relaxed) != 0; }
+static std::atomic<int> g_opt_pdl{1};
+bool opt_pdl() { return g_opt_pdl.load(std::memory_order_relaxed) != 0; }
 #ifdef SGX_AB_VARIANTS
 static std::atomic<int> g_opt_gat_mma{1}, g_opt_gcn_mma{1};
 bool opt_gat_mma() { return g_opt_gat_mma.load(std::memory_order_relaxed) != 0; }
@@ -45,6 +47,7 @@ extern "C" int sgx_set_option(const char* name, int32_t value) {
     const std::string n(name);
     if (n == "lstm_tc") { sgx::g_opt_lstm_tc.store(value); return SGX_OK; }
     if (n == "graph_tc") { sgx::g_opt_graph_tc.store(value); return SGX_OK; }
+    if (n == "pdl") { sgx::g_opt_pdl.store(value); return SGX_OK; }
 #ifdef SGX_AB_VARIANTS
     if (n == "gat_mma") { sgx::g_opt_gat_mma.store(value); return SGX_OK; }
     if (n == "gcn_mma") { sgx::g_opt_gcn_mma.store(value); return SGX_OK; }

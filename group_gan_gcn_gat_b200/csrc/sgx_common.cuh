@@ -17,6 +17,7 @@ void profile_events(cudaEvent_t* start, cudaEvent_t* stop);
 // process-wide switches (sgx_set_option; resolved once by the host side, never getenv on a call path)
 bool opt_lstm_tc();
 bool opt_graph_tc();      // tcgen05 GATEncoder / GCNModule forwards (default 1); 0: the mma.sync kernels (parity tests)
+bool opt_pdl();           // programmatic dependent launch between the kernels of the SGAN-P chain (default 1)
 #ifdef SGX_AB_VARIANTS
 bool opt_gat_mma();
 bool opt_gcn_mma();
@@ -57,6 +58,33 @@ bool opt_gcn_mma();
 
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 static inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+// Programmatic dependent launch (PDL).  The kernels of one generator forward (encoder recurrence -> pooling statistics ->
+// h image -> pooling -> unpack -> context MLP -> decoder recurrence) are queued back to back on one stream; each of
+// them calls pdl_trigger() first thing and pdl_wait() before its first access to global memory another kernel of the
+// chain may have written (or may still read), so the CTAs of kernel n+1 are resident, with barriers initialised and
+// TMEM requested, while the last CTAs of kernel n drain.  griddepcontrol.wait returns when the prerequisite grid has
+// COMPLETED and its writes are visible, and every kernel of the chain waits before it exits, so completion is
+// transitive along the chain.  A kernel launched without the attribute, or after something that is not a kernel
+// (memset, event record), is ordered as usual and both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                                     Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (pdl && opt_pdl()) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 // carve typed regions out of a caller-provided workspace
 struct Carver {

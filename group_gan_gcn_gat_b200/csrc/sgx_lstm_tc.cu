@@ -178,17 +178,19 @@ lstm_tc_kernel(const float* __restrict__ seq_in, const float* __restrict__ h0, c
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rounds = (n_tiles + gridDim.x * LSLOTS - 1) / (gridDim.x * LSLOTS);
 
+    pdl_trigger();
     if (threadIdx.x == 0) {
         mbar_init(w_full, 1);
         for (int s = 0; s < LSLOTS; ++s) { mbar_init(&a_ready[s], 128); mbar_init(&g_full[s], 1); }
         fence_barrier_init();
     }
-    if (DECODER)
-        for (int e = threadIdx.x; e < 2 * LH + 2; e += LTHREADS) whp[e] = e < 2 * LH ? W_hp[e] : b_hp[e - 2 * LH];
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
+    pdl_wait();          // everything above overlaps the tail of the previous kernel of the chain; no global access yet
+    if (DECODER)
+        for (int e = threadIdx.x; e < 2 * LH + 2; e += LTHREADS) whp[e] = e < 2 * LH ? W_hp[e] : b_hp[e - 2 * LH];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -375,13 +377,13 @@ int sgx_lstm_tc_run(bool decoder, const float* seq_in, const float* h0, const fl
     if (decoder) {
         auto kern = lstm_tc_kernel<true>;
         SGX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LstmTcSmem::TOTAL));
-        kern<<<grid, LTHREADS, LstmTcSmem::TOTAL, st>>>(seq_in, h0, c0, z, ped_scene, nz, T, (int)batch, n_tiles, img, W_hp,
-                                                        b_hp, seq_out, h_out, g_lstm_stats);
+        SGX_CUDA(launch_pdl(kern, dim3(grid), dim3(LTHREADS), LstmTcSmem::TOTAL, st, true, seq_in, h0, c0, z, ped_scene, nz, T,
+                            (int)batch, n_tiles, img, W_hp, b_hp, seq_out, h_out, g_lstm_stats));
     } else {
         auto kern = lstm_tc_kernel<false>;
         SGX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LstmTcSmem::TOTAL));
-        kern<<<grid, LTHREADS, LstmTcSmem::TOTAL, st>>>(seq_in, nullptr, nullptr, nullptr, nullptr, 0, T, (int)batch, n_tiles,
-                                                        img, nullptr, nullptr, nullptr, h_out, g_lstm_stats);
+        SGX_CUDA(launch_pdl(kern, dim3(grid), dim3(LTHREADS), LstmTcSmem::TOTAL, st, true, seq_in, nullptr, nullptr, nullptr,
+                            nullptr, 0, T, (int)batch, n_tiles, img, nullptr, nullptr, nullptr, h_out, g_lstm_stats));
     }
     SGX_LAUNCH_CHECK();
     return SGX_OK;

@@ -56,6 +56,7 @@ mlp2_tc_kernel(const float* __restrict__ xa, int da, const float* __restrict__ x
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = warp >> 2, wq = warp & 3;
 
+    pdl_trigger();
     if (threadIdx.x == 0) {
         for (int g = 0; g < GROUPS; ++g) mbar_init(&bars[g], 1);
         fence_barrier_init();
@@ -69,6 +70,7 @@ mlp2_tc_kernel(const float* __restrict__ xa, int da, const float* __restrict__ x
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_wait();          // barriers and TMEM are set up while the previous kernel of the chain drains; no global access yet
 
     // ---- weight images (W1, W2 are [out][in] row-major = the K-major B operand already), biases ----
     {
@@ -213,7 +215,8 @@ int mlp2_tc_forward(const float* xa, int da, const float* xb, int db, int64_t ba
     SGX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int64_t n_tiles = (batch + 127) / 128;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_tiles + mtc::GROUPS - 1) / mtc::GROUPS, sms));
-    kern<<<grid, mtc::NTHREADS, C::SMEM_TOTAL, st>>>(xa, da, xb, db, batch, W1, b1, W2, b2, OUT, out);
+    SGX_CUDA(launch_pdl(kern, dim3(grid), dim3(mtc::NTHREADS), C::SMEM_TOTAL, st, true, xa, da, xb, db, batch, W1, b1, W2, b2,
+                        OUT, out));
     SGX_LAUNCH_CHECK();
     return SGX_OK;
 }

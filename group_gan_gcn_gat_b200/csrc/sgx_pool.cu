@@ -144,6 +144,8 @@ pool_pair_kernel(const float* __restrict__ Ct, int64_t ldc, const float* __restr
 
 __global__ void pool_unpack_kernel(const unsigned long long* __restrict__ packed, int64_t n, float* __restrict__ out,
                                    int32_t* __restrict__ argmax) {
+    pdl_trigger();
+    pdl_wait();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     unsigned long long p = packed[i];
@@ -455,7 +457,7 @@ int sgx_pool_tc32_prep(const float* We, const float* be, const float* W1, const 
                        int B, void* prep, cudaStream_t st);
 int sgx_pool_fwd_tc32(const float* h, const float* pos, const int32_t* ped_start, const int64_t* pair_off,
                       const int32_t* tile_first, int64_t batch, int64_t n_pairs, const void* prep, const float* b2, int E,
-                      int H, int B, unsigned long long* packed, void* ws, cudaStream_t st);
+                      int H, int B, unsigned long long* packed, void* ws, cudaStream_t st, bool prep_in_this_call);
 
 // Prepared weights: everything that depends on the parameters only (folded first layer, operand images of the
 // tensor-core kernels).  Built once per weight version by sgx_pool_prep; sgx_pool_fwd builds it into its workspace.
@@ -519,6 +521,7 @@ extern "C" int sgx_pool_fwd_prepped(const float* h, const float* pos, const int3
     unsigned long long* packed = ws.take<unsigned long long>(batch * B);
     unsigned* stat = ws.take<unsigned>(64);
     SGX_CUDA(cudaMemsetAsync(packed, 0, (size_t)((char*)stat - (char*)packed) + 256, st));
+    const bool prep_in_this_call = (prep == nullptr);
     if (!prep) {   // weights not prepared by the caller: build the images behind the per-call regions
         void* own = ws.base + pool_call_ws(batch, E, H, B, precision);
         rc = sgx_pool_prep(We, be, W1, b1, W2, b2, E, H, B, precision, own, sgx_pool_prep_bytes(E, H, B, precision), stream);
@@ -531,7 +534,8 @@ extern "C" int sgx_pool_fwd_prepped(const float* h, const float* pos, const int3
                                ws.base + ws.off, st);
         if (rc) return rc;
     } else if (precision == SGX_PRECISION_TC32) {
-        rc = sgx_pool_fwd_tc32(h, pos, ped_start, pair_off, tile_first, batch, n_pairs, prep, b2, E, H, B, packed, stat, st);
+        rc = sgx_pool_fwd_tc32(h, pos, ped_start, pair_off, tile_first, batch, n_pairs, prep, b2, E, H, B, packed, stat, st,
+                               prep_in_this_call);
         if (rc) return rc;
     } else {
         const int64_t ldc = ldc_for(batch);
@@ -559,7 +563,8 @@ extern "C" int sgx_pool_fwd_prepped(const float* h, const float* pos, const int3
         SGX_LAUNCH_CHECK();
         if (ev0 && ev1) SGX_CUDA(cudaEventRecord(ev1, st));
     }
-    pool_unpack_kernel<<<blocks_for(batch * B, 256), 256, 0, st>>>(packed, batch * B, out, argmax);
+    SGX_CUDA(launch_pdl(pool_unpack_kernel, dim3(blocks_for(batch * B, 256)), dim3(256), 0, st, true, packed, batch * B, out,
+                        argmax));
     SGX_LAUNCH_CHECK();
     return SGX_OK;
 }
