@@ -311,6 +311,8 @@ gat_fused_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ lea
                     const float* __restrict__ Weo, const float* __restrict__ aeo, const float* __restrict__ Wo,
                     const float* __restrict__ bo, float alpha, float* __restrict__ out,
                     const uint8_t* __restrict__ prep, uint8_t* __restrict__ prep_out) {
+    pdl_trigger();       // (sgx_common.cuh: the next kernel of the forward may set itself up while this one drains)
+    pdl_wait();          // metadata, x and possibly the weight blob come from launches just before this one
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
     uint8_t* smem = smem_raw + (sbase - smem_u32(smem_raw));
@@ -667,9 +669,9 @@ int gat_fused_tc_forward(const float* x, const int32_t* leader, const int32_t* g
     SGX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int n_tiles = (n_chunks + 3) / 4;
     const int grid = std::max(1, std::min((n_tiles + gtc::GROUPS - 1) / gtc::GROUPS, sms));
-    kern<<<grid, gtc::NTHREADS, gtc::SMEM_TOTAL, st>>>(x, leader, gsize, labels, ps, pe, scene_start, chunk_scene, n_chunks, Wi, ai,
-                                                       Wio, aio, We, ae, Weo, aeo, Wo, bo, alpha, out,
-                                                       (const uint8_t*)prep, (uint8_t*)prep_out);
+    SGX_CUDA(launch_pdl(kern, dim3(grid), dim3(gtc::NTHREADS), gtc::SMEM_TOTAL, st, true, x, leader, gsize, labels, ps, pe,
+                        scene_start, chunk_scene, n_chunks, Wi, ai, Wio, aio, We, ae, Weo, aeo, Wo, bo, alpha, out,
+                        (const uint8_t*)prep, (uint8_t*)prep_out));
     SGX_LAUNCH_CHECK();
     return SGX_OK;
 }

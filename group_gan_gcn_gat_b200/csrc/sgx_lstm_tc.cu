@@ -211,6 +211,10 @@ lstm_tc_kernel(const float* __restrict__ seq_in, const float* __restrict__ h0, c
             for (int t = 0; t < T; ++t, ++use) {
 #pragma unroll
                 for (int s = 0; s < LSLOTS; ++s) {
+                    // a slot without a tile in this round (only the LAST round has such slots, so the slot's barriers
+                    // are never used again): nothing is issued and its epilogue warps have left their loop -- the
+                    // gate math of a dead tile would take its full share of the XU pipe from the live ones
+                    if ((int)blockIdx.x + (r * LSLOTS + s) * (int)gridDim.x >= n_tiles) continue;
                     TWAIT(&a_ready[s], (uint32_t)(use & 1), s);
                     tc_fence_after();
                     if (elect_one()) {
@@ -245,8 +249,9 @@ lstm_tc_kernel(const float* __restrict__ seq_in, const float* __restrict__ h0, c
         int use = 0;
         for (int r = 0; r < rounds; ++r) {
             const int tile = blockIdx.x + (r * LSLOTS + s) * gridDim.x;
+            if (tile >= n_tiles) break;                      // (see the issuer: dead slots of the last round are skipped)
             const int p = tile * LT + row;
-            const bool live = (tile < n_tiles) && (p < batch);
+            const bool live = p < batch;
             float h[LH], c[LH];
             float2 d = make_float2(0.f, 0.f);
 #pragma unroll

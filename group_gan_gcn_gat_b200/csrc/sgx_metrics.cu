@@ -12,6 +12,8 @@ namespace sgx {
 __global__ void displacement_kernel(const float* __restrict__ pred_rel, const float* __restrict__ start_pos,
                                     const float* __restrict__ gt, int T, int batch, float* __restrict__ ade,
                                     float* __restrict__ fde, int K, int k) {
+    pdl_trigger();
+    pdl_wait();
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= batch) return;
     float2 pos = *reinterpret_cast<const float2*>(start_pos + 2 * (int64_t)p);
@@ -54,8 +56,8 @@ extern "C" int sgx_displacement_errors(const float* pred_rel, const float* start
     SGX_REQUIRE(pred_rel && start_pos && gt && ade && fde, "sgx_displacement_errors: null pointer");
     SGX_REQUIRE(T >= 1 && batch >= 1 && batch < ((int64_t)1 << 31) && K >= 1 && k >= 0 && k < K,
                 "sgx_displacement_errors: bad shape");
-    sgx::displacement_kernel<<<sgx::blocks_for(batch, 256), 256, 0, (cudaStream_t)stream>>>(pred_rel, start_pos, gt, T,
-                                                                                           (int)batch, ade, fde, K, k);
+    SGX_CUDA(sgx::launch_pdl(sgx::displacement_kernel, dim3(sgx::blocks_for(batch, 256)), dim3(256), 0, (cudaStream_t)stream,
+                             true, pred_rel, start_pos, gt, T, (int)batch, ade, fde, K, k));
     SGX_LAUNCH_CHECK();
     return SGX_OK;
 }
