@@ -146,11 +146,17 @@ __global__ void pool_unpack_kernel(const unsigned long long* __restrict__ packed
                                    int32_t* __restrict__ argmax) {
     pdl_trigger();
     pdl_wait();
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // four keys per thread (n = batch * bottleneck_dim, a multiple of 8): two 16-byte loads, one 16-byte store each
+    const int64_t i = 4 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
     if (i >= n) return;
-    unsigned long long p = packed[i];
-    out[i] = __uint_as_float((unsigned)(p >> 32));
-    if (argmax) argmax[i] = (int32_t)(unsigned)(p & 0xffffffffu);
+    const ulonglong2 p0 = *reinterpret_cast<const ulonglong2*>(packed + i);
+    const ulonglong2 p1 = *reinterpret_cast<const ulonglong2*>(packed + i + 2);
+    *reinterpret_cast<float4*>(out + i) =
+        make_float4(__uint_as_float((unsigned)(p0.x >> 32)), __uint_as_float((unsigned)(p0.y >> 32)),
+                    __uint_as_float((unsigned)(p1.x >> 32)), __uint_as_float((unsigned)(p1.y >> 32)));
+    if (argmax)
+        *reinterpret_cast<int4*>(argmax + i) = make_int4((int32_t)(unsigned)(p0.x & 0xffffffffu), (int32_t)(unsigned)(p0.y & 0xffffffffu),
+                                                         (int32_t)(unsigned)(p1.x & 0xffffffffu), (int32_t)(unsigned)(p1.y & 0xffffffffu));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -510,6 +516,9 @@ extern "C" int sgx_pool_fwd_prepped(const float* h, const float* pos, const int3
     SGX_REQUIRE(h && pos && ped_start && pair_off && tile_first && We && be && W1 && b1 && W2 && b2 && out && workspace,
                 "sgx_pool_fwd: null pointer");
     SGX_REQUIRE(batch > 0 && n_pairs >= batch, "sgx_pool_fwd: bad batch/n_pairs");
+    SGX_REQUIRE(((uintptr_t)out & 15u) == 0 && ((uintptr_t)argmax & 15u) == 0 && ((uintptr_t)workspace & 15u) == 0 &&
+                    ((uintptr_t)h & 15u) == 0,
+                "sgx_pool_fwd: h, out, argmax and workspace must be 16-byte aligned");
     int rc = check_dims(E, H, B);
     if (rc) return rc;
     SGX_REQUIRE(precision >= SGX_PRECISION_FP32 && precision <= SGX_PRECISION_TC32, "sgx_pool_fwd: unknown precision %d",
@@ -563,7 +572,7 @@ extern "C" int sgx_pool_fwd_prepped(const float* h, const float* pos, const int3
         SGX_LAUNCH_CHECK();
         if (ev0 && ev1) SGX_CUDA(cudaEventRecord(ev1, st));
     }
-    SGX_CUDA(launch_pdl(pool_unpack_kernel, dim3(blocks_for(batch * B, 256)), dim3(256), 0, st, true, packed, batch * B, out,
+    SGX_CUDA(launch_pdl(pool_unpack_kernel, dim3(blocks_for(batch * B / 4, 256)), dim3(256), 0, st, true, packed, batch * B, out,
                         argmax));
     SGX_LAUNCH_CHECK();
     return SGX_OK;

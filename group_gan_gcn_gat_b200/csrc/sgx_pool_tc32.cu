@@ -89,15 +89,27 @@ __global__ void stat_kernel(const float* __restrict__ h, const float* __restrict
     pdl_trigger();
     pdl_wait();
     const int64_t n4 = batch * (H / 4);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     unsigned bh = 0, bd = 0;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (int64_t)gridDim.x * blockDim.x) {
-        const float4 a = reinterpret_cast<const float4*>(h)[t];
-        bh = max(bh, max(max(__float_as_uint(a.x) & 0x7fffffffu, __float_as_uint(a.y) & 0x7fffffffu),
-                         max(__float_as_uint(a.z) & 0x7fffffffu, __float_as_uint(a.w) & 0x7fffffffu)));
-        if (t < batch) {
-            const int q = ped_start[t];
-            bd = max(bd, max(__float_as_uint(pos[2 * t] - pos[2 * q]) & 0x7fffffffu,
-                             __float_as_uint(pos[2 * t + 1] - pos[2 * q + 1]) & 0x7fffffffu));
+    // four independent 16-byte loads in flight per thread and trip (one load per trip left the kernel latency-bound:
+    // 10 us for 28 MB that mostly sit in L2)
+    for (int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t0 < n4; t0 += 4 * stride) {
+        float4 a[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t t = t0 + u * stride;
+            a[u] = t < n4 ? reinterpret_cast<const float4*>(h)[t] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t t = t0 + u * stride;
+            bh = max(bh, max(max(__float_as_uint(a[u].x) & 0x7fffffffu, __float_as_uint(a[u].y) & 0x7fffffffu),
+                             max(__float_as_uint(a[u].z) & 0x7fffffffu, __float_as_uint(a[u].w) & 0x7fffffffu)));
+            if (t < batch) {
+                const int q = ped_start[t];
+                bd = max(bd, max(__float_as_uint(pos[2 * t] - pos[2 * q]) & 0x7fffffffu,
+                                 __float_as_uint(pos[2 * t + 1] - pos[2 * q + 1]) & 0x7fffffffu));
+            }
         }
     }
     bh = __reduce_max_sync(0xffffffffu, bh);

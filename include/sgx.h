@@ -118,7 +118,8 @@ int sgx_group_dense(const float* labels, const int32_t* leader, const int32_t* g
  * precision: SGX_PRECISION_FP32 (CUDA cores; any E, H, B multiple of 8),
  *            SGX_PRECISION_TC32 (tcgen05, fp32-grade; (H,B) = (32,8): sgx_pool_tc32_available) or
  *            SGX_PRECISION_BF16 (tcgen05; (H,B) in {(32,8),(48,48)}) ... see DESIGN.md.
- * workspace: sgx_pool_ws_bytes(batch, E, H, B, precision).
+ * workspace: sgx_pool_ws_bytes(batch, E, H, B, precision).  h, out, argmax and workspace: 16-byte aligned (vector
+ *   loads / stores; every torch allocation is).
  * Prepared weights: everything that depends only on the parameters (the folded first layer
  *   Aeff = W1[:, :E] We, c = W1[:, :E] be + b1, and the operand images of the tensor-core kernels) can be built
  *   once per weight version with sgx_pool_prep into a caller-owned buffer of sgx_pool_prep_bytes() and passed
