@@ -401,12 +401,11 @@ def main():
         """The body of scripts/evaluate_model.py:72-99 for one minibatch, from HOST buffers: H2D of the batch, schedule
         built from the host seq_start_end, K complete generator forwards, best-of-K ADE/FDE reduced on the device,
         D2H of the two sums."""
-        obs_rel = host['obs_traj_rel'].to(dev, non_blocking=True)      # first: the encoder only waits for this one
-        obs = host['obs_traj'].to(dev, non_blocking=True)
-        grp = host['obs_traj_g'].to(dev, non_blocking=True)
-        gt = host['pred_traj_gt'].to(dev, non_blocking=True)
         sse = host['seq_start_end'].clone()              # a fresh batch object every step: the schedule is rebuilt
-        ade, fde = evaluate_batch(gen, obs, obs_rel, sse, grp, gt, K_SAMPLES, fold_samples=False)
+        # pinned HOST tensors straight into the public call: evaluate_batch stages them (copy stream, obs_traj_rel first,
+        # one event per tensor, the compute stream waits for each where the forward first reads it)
+        ade, fde = evaluate_batch(gen, host['obs_traj'], host['obs_traj_rel'], sse, host['obs_traj_g'],
+                                  host['pred_traj_gt'], K_SAMPLES, fold_samples=False)
         out_host.copy_(torch.stack([ade, fde]), non_blocking=True)
         torch.cuda.synchronize()
 

@@ -36,6 +36,8 @@ SIGNATURES = {
     'sgx_schedule_stats': (ctypes.c_int, [_P, _I64, _P]),
     'sgx_schedule_fill': (ctypes.c_int, [_P, _I64, _P, _P, _P, _P, _P]),
     'sgx_schedule_build': (ctypes.c_int, [_P, _I64, _P, _P, _P, _P, _P, _P, _I32, _P, _P]),
+    'sgx_schedule_device_ws_bytes': (_I64, [_I64]),
+    'sgx_schedule_build_device': (ctypes.c_int, [_P, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _I64, _P]),
     'sgx_schedule_partition': (ctypes.c_int, [_P, _I64, _I32, _P, _P]),
     'sgx_schedule_chunks': (ctypes.c_int, [_P, _I64, _I32, _P, _P]),
     'sgx_group_ids': (ctypes.c_int, [_P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P]),
@@ -131,15 +133,19 @@ def lib():
             val = 0 if os.environ[env] == '0' else 1
             if handle.sgx_set_option(opt, val) == SGX_OK:                      # unknown in this build: ignored
                 OPTIONS[opt.decode()] = val
+    if 'SGX_SCHED_DEVICE' in os.environ:
+        OPTIONS['sched_device'] = 0 if os.environ['SGX_SCHED_DEVICE'] == '0' else 1
     return _lib
 
 
-OPTIONS = {'lstm_tc': 1, 'graph_tc': 1, 'pdl': 1}      # host-side mirror of the library switches (defaults of the build)
+HOST_OPTIONS = ('sched_device',)             # switches of the python host side only (the library has no use for them)
+OPTIONS = {'lstm_tc': 1, 'graph_tc': 1, 'pdl': 1, 'sched_device': 1}      # host-side mirror of the library switches (defaults of the build)
 
 
 def set_option(name, value):
-    """sgx_set_option: 'lstm_tc', 'graph_tc', 'pdl' (and 'gat_mma' / 'gcn_mma' in -DSGX_AB_VARIANTS builds)."""
-    check(lib().sgx_set_option(name.encode(), int(value)), 'sgx_set_option')
+    """sgx_set_option: 'lstm_tc', 'graph_tc', 'pdl', and the host-side 'sched_device' (schedule arrays derived on the GPU) (and 'gat_mma' / 'gcn_mma' in -DSGX_AB_VARIANTS builds)."""
+    if name not in HOST_OPTIONS:
+        check(lib().sgx_set_option(name.encode(), int(value)), 'sgx_set_option')
     OPTIONS[name] = int(value)
 
 

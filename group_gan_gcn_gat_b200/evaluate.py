@@ -10,7 +10,7 @@ import torch
 from .losses import displacement_error, final_displacement_error
 from .models import ped_scene_index
 from .schedule import get_schedule, tiled_schedule
-from .utils import relative_to_abs
+from .utils import ready, ready_last, relative_to_abs, stage_host_batch
 
 
 def best_of_k_sum(per_sample, sched):
@@ -30,7 +30,17 @@ def evaluate_batch(generator, obs_traj, obs_traj_rel, seq_start_end, obs_traj_g,
     generator couples batch rows (BatchNorm, active dropout).
     hoist_context=True computes the noise-independent part of the forward (encoder, pooling, graph context:
     everything before sgan/models.py:909) once instead of num_samples times -- bit-identical results when the
-    decoder does not pool per step.  Off by default: the reference recomputes it per sample."""
+    decoder does not pool per step.  Off by default: the reference recomputes it per sample.
+    HOST tensors (scripts/evaluate_model.py:75 receives the batch from a CPU DataLoader) are staged here: copied on a copy
+    stream in the order the forward reads them, the compute stream waiting for each where it is first needed
+    (utils.stage_host_batch), so the first sample's encoder overlaps most of the transfer; pin them for that."""
+    if not obs_traj.is_cuda:
+        gdev = next(generator.parameters()).device
+        if gdev.type == 'cuda':
+            obs_traj, obs_traj_rel, obs_traj_g, pred_traj_gt = stage_host_batch(gdev, obs_traj, obs_traj_rel, obs_traj_g,
+                                                                                pred_traj_gt)
+            if noise is not None:
+                noise = noise.to(gdev, non_blocking=True)
     sched = get_schedule(seq_start_end, obs_traj.device)
     if noise is None and generator.noise_dim and generator.noise_mix_type == 'global':
         # one draw for all K samples on the device generator.  The reference draws each sample on the CPU generator and
@@ -54,8 +64,8 @@ def evaluate_batch(generator, obs_traj, obs_traj_rel, seq_start_end, obs_traj_g,
         ade = torch.empty(batch, num_samples, dtype=torch.float32, device=dev)
         fde = torch.empty_like(ade)
         out2 = torch.empty(2, dtype=torch.float32, device=dev)
-        gt, start = _f32(pred_traj_gt, 'pred_traj_gt'), _f32(obs_traj[-1], 'obs_traj')
         ctx = generator.context(obs_traj, obs_traj_rel, seq_start_end, obs_traj_g) if hoist_context else None
+        gt = start = None
         with torch.cuda.device(dev):
             for k in range(num_samples):
                 nz = None if noise is None else noise[k]
@@ -63,12 +73,15 @@ def evaluate_batch(generator, obs_traj, obs_traj_rel, seq_start_end, obs_traj_g,
                     rel = generator.decode(ctx, obs_traj, obs_traj_rel, seq_start_end, user_noise=nz).contiguous()
                 else:
                     rel = generator(obs_traj, obs_traj_rel, seq_start_end, obs_traj_g, user_noise=nz).contiguous()
+                if gt is None:       # after the first forward is queued: a staged pred_traj_gt is the last tensor to arrive
+                    gt, start = _f32(ready(pred_traj_gt), 'pred_traj_gt'), _f32(ready_last(obs_traj)[-1], 'obs_traj')
                 _lib.check(L.sgx_displacement_errors(_ptr(rel), _ptr(start), _ptr(gt), T, batch, _ptr(ade), _ptr(fde),
                                                      num_samples, k, _stream(rel)), 'sgx_displacement_errors')
             _lib.check(L.sgx_best_of_k(_ptr(ade), _ptr(fde), _ptr(sched.scene_start), sched.n_scenes, num_samples,
                                        _ptr(out2), _stream(ade)), 'sgx_best_of_k')
         return out2[0], out2[1]
     ade, fde = [], []
+    ready_last(obs_traj), ready(pred_traj_gt)
     for k in range(num_samples):
         rel = generator(obs_traj, obs_traj_rel, seq_start_end, obs_traj_g,
                         user_noise=None if noise is None else noise[k])
@@ -89,6 +102,8 @@ def _evaluate_batch_folded(generator, obs_traj, obs_traj_rel, seq_start_end, obs
     from .ops import _f32, _ptr, _stream
     L = _lib.lib()
     dev = obs_traj.device
+    for t in (obs_traj, obs_traj_rel, obs_traj_g, pred_traj_gt):
+        ready(t)                                           # (staged host batch: the folded copies read all of them at once)
     n, s, T = obs_traj.shape[1], sched.n_scenes, pred_traj_gt.shape[0]
     sse_k = tiled_schedule(sched, k, dev)                # built on the host from the base schedule: no device read-back
     rel = generator(obs_traj.repeat(1, k, 1), obs_traj_rel.repeat(1, k, 1), sse_k, obs_traj_g.repeat(1, k, 1),
@@ -139,14 +154,15 @@ def get_generator(checkpoint, device='cuda', context_type='gat', pool_precision=
 @torch.no_grad()
 def evaluate(args, loader, generator, num_samples, noise_for_batch=None, hoist_context=False, fold_samples='auto'):
     """scripts/evaluate_model.py:72-99: best-of-`num_samples` ADE / FDE over a loader of 11-tuples (data.seq_collate /
-    data.DeviceLoader).  Batches already on the generator's device are used as they are; host batches are copied.
+    data.DeviceLoader).  Batches already on the generator's device are used as they are; host batches are staged by
+    evaluate_batch (copy stream, in the order the forward reads them).
     `noise_for_batch(batch_index, n_scenes) -> [num_samples, n_scenes, *noise_dim]` pins the noise (parity runs)."""
     device = next(generator.parameters()).device
     ade_sum = torch.zeros((), dtype=torch.float64, device=device)
     fde_sum = torch.zeros((), dtype=torch.float64, device=device)
     total_traj = 0
     for b, batch in enumerate(loader):
-        batch = [t.to(device, non_blocking=True) for t in batch]
+        # host batches stay on the host here: evaluate_batch stages them in the order the forward reads them
         obs_traj, pred_traj_gt, obs_traj_rel = batch[0], batch[1], batch[2]
         obs_traj_g, seq_start_end = batch[6], batch[10]
         total_traj += pred_traj_gt.size(1)

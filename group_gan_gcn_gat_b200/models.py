@@ -14,6 +14,7 @@ import torch.nn as nn
 from . import ops
 from .modules import GATEncoder, GCNModule, PoolHiddenNet, make_mlp
 from .schedule import get_schedule
+from .utils import ready, ready_last
 
 
 def _fused_lstm_ok(module, lstm, *tensors):
@@ -229,8 +230,8 @@ class TrajectoryGenerator(nn.Module):
 
     def context(self, obs_traj, obs_traj_rel, seq_start_end, obs_traj_g):
         """Everything of forward() that does not depend on the noise sample (encoder, pooling, graph context)."""
-        final_encoder_h = self.encoder(obs_traj_rel)
-        end_pos = obs_traj[-1, :, :]
+        final_encoder_h = self.encoder(ready(obs_traj_rel))      # (ready: staged host batches, utils.stage_host_batch)
+        end_pos = ready_last(obs_traj)[-1, :, :]
         if self.pooling_type:
             pool_h = self.pool_net(final_encoder_h, seq_start_end, end_pos)
             if self.context_type == 'mlp' and self.mlp_decoder_needed():
@@ -244,13 +245,14 @@ class TrajectoryGenerator(nn.Module):
         if not self.mlp_decoder_needed():
             return ctx_in
         if self.context_type == 'gat':
-            return self.gatencoder(ctx_in, seq_start_end, end_pos, obs_traj_g[-1, :, :])
+            return self.gatencoder(ctx_in, seq_start_end, end_pos, ready_last(obs_traj_g)[-1, :, :])
         if self.context_type == 'gcn':
-            return self.gcn_module(ctx_in, seq_start_end, end_pos, obs_traj_g[-1, :, :])
+            return self.gcn_module(ctx_in, seq_start_end, end_pos, ready_last(obs_traj_g)[-1, :, :])
         fused = ops.mlp2(self.mlp_decoder_context, ctx_in)
         return fused if fused is not None else self.mlp_decoder_context(ctx_in)
 
     def decode(self, ctx, obs_traj, obs_traj_rel, seq_start_end, user_noise=None):
+        ready_last(obs_traj), ready(obs_traj_rel)          # (only obs_traj[-1] is read below)
         batch = obs_traj_rel.size(1)
         dec = self.decoder
         if (self.noise_dim and self.noise_mix_type == 'global' and not dec.pool_every_timestep and len(self.noise_dim) == 1

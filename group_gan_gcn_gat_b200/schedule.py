@@ -47,6 +47,30 @@ class SceneSchedule:
             offs[name] = total
             total += (n * np.dtype(dt).itemsize + 15) // 16 * 16
         on_gpu = self.device.type == 'cuda'
+        if on_gpu and _lib.option('sched_device'):
+            # Derived on the GPU (csrc/sgx_schedule.cu): the host has validated seq_start_end and taken its totals (one pass
+            # over the SCENES, above); it uploads 16 bytes per scene and four small launches write the per-pedestrian and
+            # per-tile arrays -- the host pass over the pedestrians and the upload of its arrays (0.75 ms at 65 k scenes,
+            # in front of the first pooling launch of a minibatch) are gone.  The chunk list of the graph kernels is a
+            # sequential greedy packing: built on the host when a graph kernel first asks for it (`chunks`).
+            sse_off = total
+            ws_off = (sse_off + S * 16 + 255) // 256 * 256
+            ws_bytes = int(L.sgx_schedule_device_ws_bytes(S))
+            host_buf, done = _staging(S * 16, self.device)
+            np.frombuffer(host_buf.numpy(), dtype=np.int64, count=2 * S)[:] = sse.reshape(-1)
+            dev_buf = torch.empty(ws_off + ws_bytes, dtype=torch.uint8, device=self.device)
+            dev_buf[sse_off:sse_off + S * 16].copy_(host_buf[:S * 16], non_blocking=True)
+            stream = torch.cuda.current_stream(self.device)
+            done.record(stream)
+            base = dev_buf.data_ptr()
+            with torch.cuda.device(self.device):
+                _lib.check(L.sgx_schedule_build_device(base + sse_off, S, self.batch, self.n_pairs, self.n_tiles,
+                                                       base + offs['scene_start'], base + offs['ped_start'],
+                                                       base + offs['ped_end'], base + offs['pair_off'],
+                                                       base + offs['tile_first'], base + offs['ped_scene'],
+                                                       base + ws_off, ws_bytes, stream.cuda_stream), 'sgx_schedule_build_device')
+            self._finish(dev_buf, offs, B, S, T, None)
+            return
         host_buf, done = _staging(total, self.device) if on_gpu else (torch.empty(max(total, 16), dtype=torch.uint8), None)
         raw = host_buf.numpy()
         view = {name: np.frombuffer(raw, dtype=dt, count=n, offset=offs[name]) for name, dt, n in fields}
@@ -63,6 +87,11 @@ class SceneSchedule:
             done.record(torch.cuda.current_stream(self.device))
         else:
             dev_buf = host_buf
+        self._finish(dev_buf, offs, B, S, T, n_chunks if fused_chunks else -1)
+
+    def _finish(self, dev_buf, offs, B, S, T, n_chunks):
+        """typed views into the one device buffer; n_chunks: count of the chunk list in the buffer, -1: a scene is larger
+        than 32 (no list), None: not built yet (device-built schedule: `chunks` builds it on first use)"""
         self._buf = dev_buf
 
         def dev(name, dt, n):
@@ -74,8 +103,9 @@ class SceneSchedule:
         self.ped_end = dev('ped_end', np.int32, B)
         self.tile_first = dev('tile_first', np.int32, T)
         self._ped_scene32 = dev('ped_scene', np.int32, B)
-        self._chunks[32] = (dev('chunk_scene', np.int32, n_chunks + 1), n_chunks) if fused_chunks else \
-            (self.scene_start[:0], 0)
+        if n_chunks is not None:
+            self._chunks[32] = (dev('chunk_scene', np.int32, n_chunks + 1), n_chunks) if n_chunks >= 0 else \
+                (self.scene_start[:0], 0)
 
     def ped_scene32(self):
         """int32 [batch] scene index of every pedestrian (device), for the noise fold-in of the fused decoder."""
@@ -93,7 +123,7 @@ class SceneSchedule:
                 n = np.zeros(1, np.int64)
                 _lib.check(_lib.lib().sgx_schedule_chunks(self.host_sse.ctypes.data, self.n_scenes, cap,
                                                           buf.ctypes.data, n.ctypes.data), 'chunks')
-                hit = (torch.from_numpy(buf[:int(n[0]) + 1].copy()).to(self.device), int(n[0]))
+                hit = (_upload_i32(buf[:int(n[0]) + 1], self.device), int(n[0]))
             self._chunks[cap] = hit
         return hit
 
@@ -110,9 +140,9 @@ class SceneSchedule:
 _staging_bufs = {}   # device -> (pinned uint8 tensor, event of the last upload that read it)
 
 
-def _staging(nbytes, device):
-    """Grow-only pinned staging buffer per device; waits for the previous upload out of it before it is refilled."""
-    key = (device.type, device.index)
+def _staging(nbytes, device, slot='sched'):
+    """Grow-only pinned staging buffer per device (and use); waits for the previous upload out of it before it is refilled."""
+    key = (device.type, device.index, slot)
     hit = _staging_bufs.get(key)
     if hit is not None:
         hit[1].synchronize()
@@ -121,6 +151,20 @@ def _staging(nbytes, device):
         hit = (buf, torch.cuda.Event())
         _staging_bufs[key] = hit
     return hit
+
+
+def _upload_i32(arr, device):
+    """small int32 host array -> device tensor through its own pinned staging buffer, asynchronously (a pageable
+    `.to(device)` synchronises the host with the stream in the middle of a step)"""
+    if device.type != 'cuda':
+        return torch.from_numpy(np.ascontiguousarray(arr).copy())
+    nbytes = int(arr.size) * 4
+    host_buf, done = _staging(max(nbytes, 16), device, slot='i32')
+    np.frombuffer(host_buf.numpy(), dtype=np.int32, count=arr.size)[:] = arr
+    out = torch.empty(arr.size, dtype=torch.int32, device=device)
+    out.view(torch.uint8).copy_(host_buf[:nbytes], non_blocking=True)
+    done.record(torch.cuda.current_stream(device))
+    return out
 
 
 _cache = {}   # id(tensor) -> (weakref to tensor, version key, schedule); Tensor.__eq__ rules out WeakKeyDictionary

@@ -249,3 +249,11 @@ def test_tiled_schedule_is_the_schedule_of_k_copies():
             assert torch.equal(getattr(t, name), getattr(ref, name)), name
         assert tiled_schedule(sse, k, 'cpu') is t                                  # cached on the base schedule
         assert get_schedule(t, 'cpu') is t                                         # accepted wherever seq_start_end is
+
+
+def test_ready_is_a_no_op_for_tensors_that_were_not_staged():
+    """utils.ready (the wait on a staged host-batch copy) must leave ordinary tensors alone: the generator calls it on
+    every input"""
+    from group_gan_gcn_gat_b200.utils import ready, ready_last
+    t = torch.arange(6.).view(2, 3)
+    assert ready(t) is t and ready_last(t) is t and not hasattr(t, '_sgx_ready') and not hasattr(t, '_sgx_ready_last')
