@@ -38,6 +38,7 @@ SIGNATURES = {
     'sgx_schedule_build': (ctypes.c_int, [_P, _I64, _P, _P, _P, _P, _P, _P, _I32, _P, _P]),
     'sgx_schedule_device_ws_bytes': (_I64, [_I64]),
     'sgx_schedule_build_device': (ctypes.c_int, [_P, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _I64, _P]),
+    'sgx_fetch_pinned': (ctypes.c_int, [_P, _P, _I64, _P]),
     'sgx_schedule_partition': (ctypes.c_int, [_P, _I64, _I32, _P, _P]),
     'sgx_schedule_chunks': (ctypes.c_int, [_P, _I64, _I32, _P, _P]),
     'sgx_group_ids': (ctypes.c_int, [_P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P]),

@@ -12,6 +12,12 @@
 //                    ped_scene, pair_off[p] = pair_base[s] + (p - start_s) N_s;  thread per 128-pair tile t -- binary
 //                    search of the scene holding pair 128 t over pair_base -- tile_first[t] = start_s + (128 t - pair_base[s]) / N_s
 // Integer work, bit-identical to the host pass (tests/test_gpu_schedule.py).
+// seq_start_end may be handed over as a DEVICE pointer or as a pointer into PINNED host memory (cudaHostAlloc: mapped
+// into the device address space under unified addressing): scan A reads it once, over PCIe in the second case, and
+// leaves a device copy for the other launches.  No copy-engine transfer is involved, so the schedule of minibatch k
+// never queues behind the H2D prefetch of minibatch k+1 (a 1 MB cudaMemcpyAsync issued after the 50 MB prefetch stalled
+// the compute stream for 0.75 ms per step in the pipelined evaluation loop).  sgx_fetch_pinned is the same idea for the
+// small chunk lists of the graph kernels.
 #include "sgx_common.cuh"
 
 namespace sgx {
@@ -42,10 +48,11 @@ __device__ __forceinline__ long long block_inclusive_scan(long long v, long long
 
 // WRITE = false: block_sum[b] = sum of N^2 over the block's scenes.  WRITE = true: block_sum holds the EXCLUSIVE scan of
 // those sums; writes pair_base[s] and scene_start[s] (and the closing entries [S]).
+// (WRITE = false additionally copies the scenes it reads to sse_copy: the device copy the later launches use)
 template <bool WRITE>
 __global__ void __launch_bounds__(SCAN_THREADS)
 scan_kernel(const int64_t* __restrict__ sse, int64_t S, long long* __restrict__ block_sum, long long* __restrict__ pair_base,
-            int32_t* __restrict__ scene_start, int64_t batch, int64_t n_pairs) {
+            int32_t* __restrict__ scene_start, int64_t batch, int64_t n_pairs, int64_t* __restrict__ sse_copy) {
     __shared__ long long s_warp[SCAN_THREADS / 32];
     const int64_t s0 = ((int64_t)blockIdx.x * SCAN_THREADS + threadIdx.x) * SCAN_PER_THREAD;
     long long c[SCAN_PER_THREAD], tot = 0;
@@ -58,6 +65,7 @@ scan_kernel(const int64_t* __restrict__ sse, int64_t S, long long* __restrict__ 
             const long long n = ab.y - ab.x;
             c[u] = n * n;
             if (WRITE) scene_start[s] = (int32_t)ab.x;
+            else *reinterpret_cast<longlong2*>(sse_copy + 2 * s) = ab;
         }
         tot += c[u];
     }
@@ -128,6 +136,13 @@ fill_kernel(const int64_t* __restrict__ sse, const long long* __restrict__ pair_
     }
 }
 
+// 16-byte words from mapped pinned host memory (or anywhere) to device memory, by the SMs instead of a copy engine
+__global__ void __launch_bounds__(256)
+fetch_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int64_t n16) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
 }  // namespace sched
 }  // namespace sgx
 
@@ -136,31 +151,42 @@ using namespace sgx;
 extern "C" int64_t sgx_schedule_device_ws_bytes(int64_t S) {
     if (S < 1) return 256;
     const int64_t n_blocks = (S + sched::SCAN_BLOCK - 1) / sched::SCAN_BLOCK;
-    return align_up((S + 1) * 8, 256) + align_up(n_blocks * 8, 256);
+    return align_up((S + 1) * 8, 256) + align_up(n_blocks * 8, 256) + align_up(S * 16, 256);
 }
 
-extern "C" int sgx_schedule_build_device(const int64_t* d_sse, int64_t S, int64_t batch, int64_t n_pairs, int64_t n_tiles,
+extern "C" int sgx_fetch_pinned(void* d_dst, const void* src, int64_t nbytes, void* stream) {
+    SGX_REQUIRE(d_dst && src && nbytes >= 0 && nbytes % 16 == 0 && ((uintptr_t)d_dst & 15u) == 0 && ((uintptr_t)src & 15u) == 0,
+                "sgx_fetch_pinned: pointers and size must be multiples of 16 bytes");
+    if (nbytes == 0) return SGX_OK;
+    sched::fetch_kernel<<<(unsigned)std::min<int64_t>(blocks_for(nbytes / 16, 256), 592), 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)src, (uint4*)d_dst, nbytes / 16);
+    SGX_LAUNCH_CHECK();
+    return SGX_OK;
+}
+
+extern "C" int sgx_schedule_build_device(const int64_t* sse_src, int64_t S, int64_t batch, int64_t n_pairs, int64_t n_tiles,
                                          int32_t* scene_start, int32_t* ped_start, int32_t* ped_end, int64_t* pair_off,
                                          int32_t* tile_first, int32_t* ped_scene, void* workspace, int64_t ws_bytes,
                                          void* stream) {
-    SGX_REQUIRE(d_sse && scene_start && ped_start && ped_end && pair_off && tile_first && ped_scene && workspace,
+    SGX_REQUIRE(sse_src && scene_start && ped_start && ped_end && pair_off && tile_first && ped_scene && workspace,
                 "sgx_schedule_build_device: null pointer");
     SGX_REQUIRE(S >= 1 && batch >= S && batch < ((int64_t)1 << 31) && n_pairs >= batch && n_tiles == (n_pairs + 127) / 128,
                 "sgx_schedule_build_device: totals do not describe a schedule (take them from sgx_schedule_stats)");
     SGX_REQUIRE(ws_bytes >= sgx_schedule_device_ws_bytes(S), "sgx_schedule_build_device: workspace too small");
-    SGX_REQUIRE(((uintptr_t)d_sse & 15u) == 0, "sgx_schedule_build_device: seq_start_end must be 16-byte aligned");
+    SGX_REQUIRE(((uintptr_t)sse_src & 15u) == 0, "sgx_schedule_build_device: seq_start_end must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     Carver ws(workspace);
     long long* pair_base = ws.take<long long>(S + 1);
     const int64_t n_blocks = (S + sched::SCAN_BLOCK - 1) / sched::SCAN_BLOCK;
     long long* block_sum = ws.take<long long>(n_blocks);
-    sched::scan_kernel<false><<<(unsigned)n_blocks, sched::SCAN_THREADS, 0, st>>>(d_sse, S, block_sum, pair_base, scene_start,
-                                                                                 batch, n_pairs);
+    int64_t* d_sse = ws.take<int64_t>(2 * S);
+    sched::scan_kernel<false><<<(unsigned)n_blocks, sched::SCAN_THREADS, 0, st>>>(sse_src, S, block_sum, pair_base, scene_start,
+                                                                                 batch, n_pairs, d_sse);
     SGX_LAUNCH_CHECK();
     sched::scan_blocks_kernel<<<1, sched::SCAN_THREADS, 0, st>>>(block_sum, n_blocks);
     SGX_LAUNCH_CHECK();
     sched::scan_kernel<true><<<(unsigned)n_blocks, sched::SCAN_THREADS, 0, st>>>(d_sse, S, block_sum, pair_base, scene_start,
-                                                                                batch, n_pairs);
+                                                                                batch, n_pairs, nullptr);
     SGX_LAUNCH_CHECK();
     sched::fill_kernel<<<blocks_for(batch + n_tiles, 256), 256, 0, st>>>(d_sse, pair_base, S, batch, n_tiles, n_pairs, ped_start,
                                                                          ped_end, ped_scene, pair_off, tile_first);

@@ -41,20 +41,22 @@ def evaluate_batch(generator, obs_traj, obs_traj_rel, seq_start_end, obs_traj_g,
                                                                                 pred_traj_gt)
             if noise is not None:
                 noise = noise.to(gdev, non_blocking=True)
-    sched = get_schedule(seq_start_end, obs_traj.device)
+    # The schedule is built where it is first needed (the pooling call of the first forward, the folded copies, the
+    # best-of-K reduction) and cached on seq_start_end: the first sample's encoder is queued before the host touches it.
+    n_scenes = seq_start_end.n_scenes if hasattr(seq_start_end, 'n_scenes') else int(seq_start_end.shape[0])
     if noise is None and generator.noise_dim and generator.noise_mix_type == 'global':
         # one draw for all K samples on the device generator.  The reference draws each sample on the CPU generator and
         # copies it (sgan/models.py:23-29), which costs more host time than the whole forward here; pass `noise=` to
         # reproduce a CPU-seeded stream.
         fn = torch.randn if generator.noise_type == 'gaussian' else (lambda *a, **k: torch.rand(*a, **k) * 2 - 1)
-        noise = fn(num_samples, sched.n_scenes, *generator.noise_dim, device=obs_traj.device)
+        noise = fn(num_samples, n_scenes, *generator.noise_dim, device=obs_traj.device)
     dev = obs_traj.device
     if fold_samples == 'auto':
         fold_samples = num_samples > 1 and obs_traj.shape[1] * num_samples <= (1 << 20) and not hoist_context
     if fold_samples and obs_traj.is_cuda and num_samples <= 32 and generator.noise_mix_type == 'global' and \
             noise is not None and _batch_independent(generator):
         return _evaluate_batch_folded(generator, obs_traj, obs_traj_rel, seq_start_end, obs_traj_g, pred_traj_gt,
-                                      num_samples, noise, sched)
+                                      num_samples, noise, get_schedule(seq_start_end, obs_traj.device))
     if obs_traj.is_cuda and num_samples <= 32:
         # fused path: one metrics kernel per sample, one best-of-K kernel (sgx_displacement_errors / sgx_best_of_k)
         from . import _lib
@@ -77,6 +79,7 @@ def evaluate_batch(generator, obs_traj, obs_traj_rel, seq_start_end, obs_traj_g,
                     gt, start = _f32(ready(pred_traj_gt), 'pred_traj_gt'), _f32(ready_last(obs_traj)[-1], 'obs_traj')
                 _lib.check(L.sgx_displacement_errors(_ptr(rel), _ptr(start), _ptr(gt), T, batch, _ptr(ade), _ptr(fde),
                                                      num_samples, k, _stream(rel)), 'sgx_displacement_errors')
+            sched = get_schedule(seq_start_end, dev)                       # (cached by the forwards above)
             _lib.check(L.sgx_best_of_k(_ptr(ade), _ptr(fde), _ptr(sched.scene_start), sched.n_scenes, num_samples,
                                        _ptr(out2), _stream(ade)), 'sgx_best_of_k')
         return out2[0], out2[1]
@@ -88,6 +91,7 @@ def evaluate_batch(generator, obs_traj, obs_traj_rel, seq_start_end, obs_traj_g,
         pred = relative_to_abs(rel, obs_traj[-1])
         ade.append(displacement_error(pred, pred_traj_gt, mode='raw'))
         fde.append(final_displacement_error(pred[-1], pred_traj_gt[-1], mode='raw'))
+    sched = get_schedule(seq_start_end, obs_traj.device)
     return best_of_k_sum(torch.stack(ade, dim=1), sched), best_of_k_sum(torch.stack(fde, dim=1), sched)
 
 

@@ -53,22 +53,22 @@ class SceneSchedule:
             # per-tile arrays -- the host pass over the pedestrians and the upload of its arrays (0.75 ms at 65 k scenes,
             # in front of the first pooling launch of a minibatch) are gone.  The chunk list of the graph kernels is a
             # sequential greedy packing: built on the host when a graph kernel first asks for it (`chunks`).
-            sse_off = total
-            ws_off = (sse_off + S * 16 + 255) // 256 * 256
+            # seq_start_end goes into a pinned staging buffer and the first launch reads it from there (mapped host memory):
+            # no copy-engine transfer, which would queue behind the H2D prefetch of the next minibatch.
+            ws_off = (total + 255) // 256 * 256
             ws_bytes = int(L.sgx_schedule_device_ws_bytes(S))
             host_buf, done = _staging(S * 16, self.device)
             np.frombuffer(host_buf.numpy(), dtype=np.int64, count=2 * S)[:] = sse.reshape(-1)
             dev_buf = torch.empty(ws_off + ws_bytes, dtype=torch.uint8, device=self.device)
-            dev_buf[sse_off:sse_off + S * 16].copy_(host_buf[:S * 16], non_blocking=True)
             stream = torch.cuda.current_stream(self.device)
-            done.record(stream)
             base = dev_buf.data_ptr()
             with torch.cuda.device(self.device):
-                _lib.check(L.sgx_schedule_build_device(base + sse_off, S, self.batch, self.n_pairs, self.n_tiles,
+                _lib.check(L.sgx_schedule_build_device(host_buf.data_ptr(), S, self.batch, self.n_pairs, self.n_tiles,
                                                        base + offs['scene_start'], base + offs['ped_start'],
                                                        base + offs['ped_end'], base + offs['pair_off'],
                                                        base + offs['tile_first'], base + offs['ped_scene'],
                                                        base + ws_off, ws_bytes, stream.cuda_stream), 'sgx_schedule_build_device')
+            done.record(stream)              # the staging buffer is free again once the first launch has read it
             self._finish(dev_buf, offs, B, S, T, None)
             return
         host_buf, done = _staging(total, self.device) if on_gpu else (torch.empty(max(total, 16), dtype=torch.uint8), None)
@@ -154,17 +154,19 @@ def _staging(nbytes, device, slot='sched'):
 
 
 def _upload_i32(arr, device):
-    """small int32 host array -> device tensor through its own pinned staging buffer, asynchronously (a pageable
-    `.to(device)` synchronises the host with the stream in the middle of a step)"""
+    """small int32 host array -> device tensor through its own pinned staging buffer, asynchronously and without a
+    copy-engine transfer (a pageable `.to(device)` synchronises the host with the stream in the middle of a step)"""
     if device.type != 'cuda':
         return torch.from_numpy(np.ascontiguousarray(arr).copy())
-    nbytes = int(arr.size) * 4
-    host_buf, done = _staging(max(nbytes, 16), device, slot='i32')
+    n16 = (int(arr.size) * 4 + 15) // 16 * 16
+    host_buf, done = _staging(max(n16, 16), device, slot='i32')
     np.frombuffer(host_buf.numpy(), dtype=np.int32, count=arr.size)[:] = arr
-    out = torch.empty(arr.size, dtype=torch.int32, device=device)
-    out.view(torch.uint8).copy_(host_buf[:nbytes], non_blocking=True)
-    done.record(torch.cuda.current_stream(device))
-    return out
+    out = torch.empty(n16 // 4, dtype=torch.int32, device=device)
+    stream = torch.cuda.current_stream(device)
+    with torch.cuda.device(device):            # fetched by a kernel from the mapped staging buffer (see SceneSchedule)
+        _lib.check(_lib.lib().sgx_fetch_pinned(out.data_ptr(), host_buf.data_ptr(), n16, stream.cuda_stream), 'sgx_fetch_pinned')
+    done.record(stream)
+    return out[:arr.size]
 
 
 _cache = {}   # id(tensor) -> (weakref to tensor, version key, schedule); Tensor.__eq__ rules out WeakKeyDictionary

@@ -83,16 +83,20 @@ int sgx_schedule_fill(const int64_t* h_seq_start_end, int64_t n_scenes, int32_t*
 int sgx_schedule_build(const int64_t* h_seq_start_end, int64_t n_scenes, int32_t* h_scene_start,
                        int32_t* h_ped_start, int32_t* h_ped_end, int64_t* h_pair_off, int32_t* h_tile_first,
                        int32_t* h_ped_scene, int32_t chunk_cap, int32_t* h_chunk_scene, int64_t* h_n_chunks);
-/* The same arrays as sgx_schedule_build (without the chunk list), derived ON THE DEVICE from a device copy of
- * seq_start_end (int64 [S,2], 16-byte aligned) and the totals of sgx_schedule_stats (batch = stats[0], n_pairs =
- * stats[2], n_tiles = stats[3]): the host validates and uploads 16 bytes per scene instead of filling and uploading
- * ~34 bytes per pedestrian.  Four small launches on `stream`, no synchronisation; bit-identical to the host pass.
- * All output pointers are device pointers; workspace: sgx_schedule_device_ws_bytes(S). */
+/* The same arrays as sgx_schedule_build (without the chunk list), derived ON THE DEVICE from seq_start_end (int64 [S,2],
+ * 16-byte aligned: a device pointer OR a pointer into pinned host memory, which the first launch reads over PCIe -- no
+ * copy-engine transfer that could queue behind the prefetch of the next minibatch) and the totals of sgx_schedule_stats
+ * (batch = stats[0], n_pairs = stats[2], n_tiles = stats[3]): the host validates and hands over 16 bytes per scene instead
+ * of filling and uploading ~34 bytes per pedestrian.  Four small launches on `stream`, no synchronisation; bit-identical
+ * to the host pass.  All output pointers are device pointers; workspace: sgx_schedule_device_ws_bytes(S). */
 int64_t sgx_schedule_device_ws_bytes(int64_t n_scenes);
-int sgx_schedule_build_device(const int64_t* d_seq_start_end, int64_t n_scenes, int64_t batch, int64_t n_pairs,
+int sgx_schedule_build_device(const int64_t* seq_start_end_dev_or_pinned, int64_t n_scenes, int64_t batch, int64_t n_pairs,
                               int64_t n_tiles, int32_t* d_scene_start, int32_t* d_ped_start, int32_t* d_ped_end,
                               int64_t* d_pair_off, int32_t* d_tile_first, int32_t* d_ped_scene, void* workspace,
                               int64_t ws_bytes, void* stream);
+/* nbytes (multiple of 16) from pinned host memory (or device memory) to d_dst by a kernel instead of a copy engine: for
+ * the small index lists of a minibatch that must not wait behind the H2D prefetch of the next one. */
+int sgx_fetch_pinned(void* d_dst, const void* src_pinned, int64_t nbytes, void* stream);
 int sgx_schedule_partition(const int64_t* h_seq_start_end, int64_t n_scenes, int32_t world,
                            int32_t* h_rank_of_scene, int64_t* h_rank_cost);
 /* Greedy packing of consecutive whole scenes into chunks of <= cap pedestrians (fused GAT kernel: one warp per
