@@ -18,7 +18,8 @@ __global__ void displacement_kernel(const float* __restrict__ pred_rel, const fl
     if (p >= batch) return;
     float2 pos = *reinterpret_cast<const float2*>(start_pos + 2 * (int64_t)p);
     float acc = 0.f, last = 0.f;
-    for (int t = 0; t < T; ++t) {
+#pragma unroll 4
+    for (int t = 0; t < T; ++t) {                    // (the loads of four steps are in flight together; the sums stay in step order)
         const float2 d = *reinterpret_cast<const float2*>(pred_rel + ((int64_t)t * batch + p) * 2);
         const float2 g = *reinterpret_cast<const float2*>(gt + ((int64_t)t * batch + p) * 2);
         pos.x += d.x;
@@ -31,22 +32,38 @@ __global__ void displacement_kernel(const float* __restrict__ pred_rel, const fl
     fde[(int64_t)p * K + k] = last;
 }
 
-// one warp per scene: lanes <-> samples (K <= 32); out[0] += min_k sum_p ade[p][k], out[1] likewise for fde
-__global__ void best_of_k_kernel(const float* __restrict__ ade, const float* __restrict__ fde,
-                                 const int32_t* __restrict__ scene_start, int n_scenes, int K, float* __restrict__ out) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= n_scenes) return;
-    const int b = scene_start[warp], e = scene_start[warp + 1];
-    float sa = 0.f, sf = 0.f;
-    if (lane < K)
-        for (int p = b; p < e; ++p) { sa += ade[(int64_t)p * K + lane]; sf += fde[(int64_t)p * K + lane]; }
-    if (lane >= K) { sa = INFINITY; sf = INFINITY; }
+// a warp per scene at a time, lanes <-> samples (K <= 32): out[0] += min_k sum_p ade[p][k], out[1] likewise for fde.
+// Warps stride over the scenes and keep their partial sums; one pair of atomics per BLOCK (65 k scenes used to mean 131 k
+// atomics on two addresses: most of the kernel's 62 us).
+__global__ void __launch_bounds__(256)
+best_of_k_kernel(const float* __restrict__ ade, const float* __restrict__ fde, const int32_t* __restrict__ scene_start,
+                 int n_scenes, int K, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    float ta = 0.f, tf = 0.f;                          // lane 0: this warp's sums over its scenes
+    for (int scene = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; scene < n_scenes; scene += n_warps) {
+        const int b = scene_start[scene], e = scene_start[scene + 1];
+        float sa = 0.f, sf = 0.f;
+        if (lane < K)
+            for (int p = b; p < e; ++p) { sa += ade[(int64_t)p * K + lane]; sf += fde[(int64_t)p * K + lane]; }
+        if (lane >= K) { sa = INFINITY; sf = INFINITY; }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        sa = fminf(sa, __shfl_xor_sync(0xffffffffu, sa, o));
-        sf = fminf(sf, __shfl_xor_sync(0xffffffffu, sf, o));
+        for (int o = 16; o > 0; o >>= 1) {
+            sa = fminf(sa, __shfl_xor_sync(0xffffffffu, sa, o));
+            sf = fminf(sf, __shfl_xor_sync(0xffffffffu, sf, o));
+        }
+        ta += sa;
+        tf += sf;
     }
-    if (lane == 0) { atomicAdd(&out[0], sa); atomicAdd(&out[1], sf); }
+    __shared__ float s_a[8], s_f[8];
+    if (lane == 0) { s_a[wib] = ta; s_f[wib] = tf; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, f = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += s_a[w]; f += s_f[w]; }
+        atomicAdd(&out[0], a);
+        atomicAdd(&out[1], f);
+    }
 }
 
 }  // namespace sgx
@@ -68,7 +85,8 @@ extern "C" int sgx_best_of_k(const float* ade, const float* fde, const int32_t* 
     SGX_UNSUPPORTED(K < 1 || K > 32, "sgx_best_of_k: K=%d samples, built for 1..32", K);
     cudaStream_t st = (cudaStream_t)stream;
     SGX_CUDA(cudaMemsetAsync(out2, 0, 2 * sizeof(float), st));
-    sgx::best_of_k_kernel<<<sgx::blocks_for(n_scenes * 32, 256), 256, 0, st>>>(ade, fde, scene_start, (int)n_scenes, K, out2);
+    sgx::best_of_k_kernel<<<(unsigned)std::min<int64_t>(sgx::blocks_for(n_scenes * 32, 256), 1184), 256, 0, st>>>(
+        ade, fde, scene_start, (int)n_scenes, K, out2);
     SGX_LAUNCH_CHECK();
     return SGX_OK;
 }
